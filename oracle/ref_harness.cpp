@@ -1,0 +1,291 @@
+// TEST INFRASTRUCTURE ONLY — never linked into or called from the product path.
+//
+// Drives the UNMODIFIED reference solver (/root/reference, built by oracle/build_ref.sh into
+// oracle/_ref/) and dumps stage-level data so that (a) the CPU restatement in oracle/ can be
+// pinned against the real reference and (b) small golden fixtures can be committed under
+// tests/golden/.  It is also the reference arm of bench.py (`time` mode).
+//
+// All members of the reference's Solver / TENO / Mesh classes live in headers, so the harness
+// reaches the private state with the usual `#define private public` trick instead of patching
+// reference sources (reference: src/solver/solver.h:226-279, src/numerics/face_reconstruction.h).
+//
+// Usage:
+//   ref_harness dump <input.toml> <out.mlbd> [n_steps=1] [every=1]   stage-level dump of step 0 and every
+//                                                             `every`-th step
+//   ref_harness time <input.toml> <n_steps> [n_warmup=1]      wall-clock per step, JSON on last line
+//   ref_harness mesh <mesh.mlbd> <input.toml> <out.mlbd> [n]  as `dump`, but the mesh arrays are
+//                                                             injected from a file (arbitrary
+//                                                             unstructured tri/quad meshes)
+//
+// Dump container ("MLBD"): repeated records
+//   u32 name_len | name bytes | u32 dtype (0=f64,1=u32,2=i32,3=u8) | u32 ndim | u64 dims[ndim] | raw data
+#include <sstream>
+#define private public
+#define protected public
+#include "solver.h"
+#include "face_reconstruction.h"
+#include "mesh.h"
+#include "zone.h"
+#undef private
+#undef protected
+
+#include <Kokkos_Core.hpp>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct Writer {
+    FILE * f;
+    explicit Writer(const std::string & path) { f = fopen(path.c_str(), "wb"); if (!f) { perror("open"); exit(2);} }
+    ~Writer() { fclose(f); }
+    void rec(const std::string & name, uint32_t dtype, std::vector<uint64_t> dims, const void * data, size_t elt) {
+        uint32_t nl = name.size();
+        fwrite(&nl, 4, 1, f); fwrite(name.data(), 1, nl, f);
+        fwrite(&dtype, 4, 1, f);
+        uint32_t nd = dims.size(); fwrite(&nd, 4, 1, f);
+        size_t n = 1; for (auto d : dims) { fwrite(&d, 8, 1, f); n *= d; }
+        if (n) fwrite(data, elt, n, f);
+    }
+    void f64(const std::string & n, std::vector<uint64_t> d, const double * p) { rec(n, 0, d, p, 8); }
+    void u32(const std::string & n, std::vector<uint64_t> d, const uint32_t * p) { rec(n, 1, d, p, 4); }
+    void i32(const std::string & n, std::vector<uint64_t> d, const int32_t * p) { rec(n, 2, d, p, 4); }
+    void u8(const std::string & n, std::vector<uint64_t> d, const uint8_t * p) { rec(n, 3, d, p, 1); }
+    void scalar(const std::string & n, double v) { f64(n, {1}, &v); }
+};
+
+struct Record { uint32_t dtype; std::vector<uint64_t> dims; std::vector<char> data; };
+std::map<std::string, Record> read_mlbd(const std::string & path) {
+    std::map<std::string, Record> out;
+    FILE * f = fopen(path.c_str(), "rb"); if (!f) { perror("open"); exit(2); }
+    uint32_t nl;
+    while (fread(&nl, 4, 1, f) == 1) {
+        std::string name(nl, 0); if (fread(name.data(), 1, nl, f) != nl) break;
+        Record r; uint32_t nd;
+        if (fread(&r.dtype, 4, 1, f) != 1 || fread(&nd, 4, 1, f) != 1) break;
+        size_t n = 1; r.dims.resize(nd);
+        for (auto & d : r.dims) { if (fread(&d, 8, 1, f) != 1) break; n *= d; }
+        size_t elt = r.dtype == 0 ? 8 : (r.dtype == 3 ? 1 : 4);
+        r.data.resize(n * elt);
+        if (n && fread(r.data.data(), elt, n, f) != n) break;
+        out[name] = std::move(r);
+    }
+    fclose(f);
+    return out;
+}
+
+// Views here are all LayoutRight host views (Serial/OpenMP back-ends): data() is row-major.
+template <class V> std::vector<uint64_t> dims_of(const V & v) {
+    std::vector<uint64_t> d; for (unsigned i = 0; i < V::rank; ++i) d.push_back(v.extent(i)); return d;
+}
+
+void dump_mesh(Writer & w, Mesh & m) {
+    w.f64("node_coords", dims_of(m.h_node_coords), m.h_node_coords.data());
+    w.f64("cell_coords", dims_of(m.h_cell_coords), m.h_cell_coords.data());
+    w.f64("cell_volume", dims_of(m.h_cell_volume), m.h_cell_volume.data());
+    w.f64("face_area", dims_of(m.h_face_area), m.h_face_area.data());
+    w.f64("face_normals", dims_of(m.h_face_normals), m.h_face_normals.data());
+    w.u32("nodes_of_cell", dims_of(m.h_nodes_of_cell), m.h_nodes_of_cell.data());
+    w.u32("offsets_nodes_of_cell", dims_of(m.h_offsets_nodes_of_cell), m.h_offsets_nodes_of_cell.data());
+    w.u32("faces_of_cell", dims_of(m.h_faces_of_cell), m.h_faces_of_cell.data());
+    w.u32("offsets_faces_of_cell", dims_of(m.h_offsets_faces_of_cell), m.h_offsets_faces_of_cell.data());
+    w.u32("nodes_of_face", dims_of(m.h_nodes_of_face), m.h_nodes_of_face.data());
+    w.u32("offsets_nodes_of_face", dims_of(m.h_offsets_nodes_of_face), m.h_offsets_nodes_of_face.data());
+    w.i32("cells_of_face", dims_of(m.h_cells_of_face), m.h_cells_of_face.data());
+    uint32_t iz = 0;
+    for (auto & z : *m.face_zones()) {
+        w.u32("zone:" + std::to_string(iz) + ":" + z.get_name(), dims_of(z.h_faces), z.h_faces.data());
+        ++iz;
+    }
+}
+
+void dump_teno(Writer & w, TENO & t) {
+    uint32_t n_groups = t.h_offsets_stencil_groups.extent(0);
+    uint32_t n_st = t.h_offsets_stencil_groups(n_groups - 1);
+    w.u8("teno:poly_indices", dims_of(t.h_poly_indices), t.h_poly_indices.data());
+    w.u32("teno:offsets_stencil_groups", {n_groups}, t.h_offsets_stencil_groups.data());
+    w.u32("teno:offsets_stencils", {(uint64_t)n_st + 1}, t.h_offsets_stencils.data());  // view is over-allocated (Q5)
+    w.u32("teno:stencils", dims_of(t.h_stencils), t.h_stencils.data());
+    w.u32("teno:offsets_reconstruction_matrices", dims_of(t.h_offsets_reconstruction_matrices), t.h_offsets_reconstruction_matrices.data());
+    w.f64("teno:reconstruction_matrices", dims_of(t.h_reconstruction_matrices), t.h_reconstruction_matrices.data());
+    w.f64("teno:transformed_areas", dims_of(t.h_transformed_areas), t.h_transformed_areas.data());
+    w.f64("teno:integral_psi_target", dims_of(t.h_integral_psi_target), t.h_integral_psi_target.data());
+    w.f64("teno:oscillation_indicator", dims_of(t.h_oscillation_indicator), t.h_oscillation_indicator.data());
+    w.f64("teno:quad_face_points", dims_of(t.quadrature_face.h_points), t.quadrature_face.h_points.data());
+    w.f64("teno:quad_cell_points", dims_of(t.quadrature_cell.h_points), t.quadrature_cell.h_points.data());
+    w.f64("teno:quad_cell_weights", dims_of(t.quadrature_cell.h_weights), t.quadrature_cell.h_weights.data());
+    double meta[3] = {(double)t.n_dof, (double)t.max_cells_per_stencil, (double)t.poly_order};
+    w.f64("teno:meta", {3}, meta);
+}
+
+// Mirrors Solver::init (src/solver/solver.cpp:39-80) but lets the caller replace the mesh between
+// init_mesh() and init_physics().
+void init_with_mesh(Solver & s, const std::string & toml_file, const std::map<std::string, Record> * inj) {
+    s.input = toml::parse(toml_file);
+    s.t = 0.0; s.step = 0; s.t_wall_0 = s.timer.seconds();
+    if (!inj) {
+        s.init_mesh();
+    } else {
+        auto & R = *inj;
+        auto m = std::make_shared<Mesh>();
+        m->set_type(MeshType::FILE);
+        auto get = [&](const char * n) -> const Record & {
+            auto it = R.find(n); if (it == R.end()) { fprintf(stderr, "mesh file lacks %s\n", n); exit(2); } return it->second; };
+        const Record & nc = get("node_coords"), & noc = get("nodes_of_cell"), & onc = get("offsets_nodes_of_cell"),
+                     & foc = get("faces_of_cell"), & ofc = get("offsets_faces_of_cell"), & nof = get("nodes_of_face"),
+                     & onf = get("offsets_nodes_of_face"), & cof = get("cells_of_face");
+        m->n_nodes = nc.dims[0]; m->n_cells = onc.dims[0] - 1; m->n_faces = onf.dims[0] - 1;
+        m->node_coords = Kokkos::View<rtype *[N_DIM]>("node_coords", m->n_nodes);
+        m->cell_coords = Kokkos::View<rtype *[N_DIM]>("cell_coords", m->n_cells);
+        m->cell_volume = Kokkos::View<rtype *>("cell_volume", m->n_cells);
+        m->face_area = Kokkos::View<rtype *>("face_area", m->n_faces);
+        m->face_normals = Kokkos::View<rtype *[N_DIM]>("face_normals", m->n_faces);
+        m->cells_of_face = Kokkos::View<int32_t *[2]>("cells_of_face", m->n_faces);
+        m->nodes_of_cell = Kokkos::View<uint32_t *>("nodes_of_cell", noc.dims[0]);
+        m->offsets_nodes_of_cell = Kokkos::View<uint32_t *>("offsets_nodes_of_cell", onc.dims[0]);
+        m->faces_of_cell = Kokkos::View<uint32_t *>("faces_of_cell", foc.dims[0]);
+        m->offsets_faces_of_cell = Kokkos::View<uint32_t *>("offsets_faces_of_cell", ofc.dims[0]);
+        m->nodes_of_face = Kokkos::View<uint32_t *>("nodes_of_face", nof.dims[0]);
+        m->offsets_nodes_of_face = Kokkos::View<uint32_t *>("offsets_nodes_of_face", onf.dims[0]);
+        m->h_node_coords = Kokkos::create_mirror_view(m->node_coords);
+        m->h_cell_coords = Kokkos::create_mirror_view(m->cell_coords);
+        m->h_cell_volume = Kokkos::create_mirror_view(m->cell_volume);
+        m->h_face_area = Kokkos::create_mirror_view(m->face_area);
+        m->h_face_normals = Kokkos::create_mirror_view(m->face_normals);
+        m->h_cells_of_face = Kokkos::create_mirror_view(m->cells_of_face);
+        m->h_nodes_of_cell = Kokkos::create_mirror_view(m->nodes_of_cell);
+        m->h_offsets_nodes_of_cell = Kokkos::create_mirror_view(m->offsets_nodes_of_cell);
+        m->h_faces_of_cell = Kokkos::create_mirror_view(m->faces_of_cell);
+        m->h_offsets_faces_of_cell = Kokkos::create_mirror_view(m->offsets_faces_of_cell);
+        m->h_nodes_of_face = Kokkos::create_mirror_view(m->nodes_of_face);
+        m->h_offsets_nodes_of_face = Kokkos::create_mirror_view(m->offsets_nodes_of_face);
+        memcpy(m->h_node_coords.data(), nc.data.data(), nc.data.size());
+        memcpy(m->h_cells_of_face.data(), cof.data.data(), cof.data.size());
+        memcpy(m->h_nodes_of_cell.data(), noc.data.data(), noc.data.size());
+        memcpy(m->h_offsets_nodes_of_cell.data(), onc.data.data(), onc.data.size());
+        memcpy(m->h_faces_of_cell.data(), foc.data.data(), foc.data.size());
+        memcpy(m->h_offsets_faces_of_cell.data(), ofc.data.data(), ofc.data.size());
+        memcpy(m->h_nodes_of_face.data(), nof.data.data(), nof.data.size());
+        memcpy(m->h_offsets_nodes_of_face.data(), onf.data.data(), onf.data.size());
+        // zones, in index order: names "zone:<i>:<name>"
+        std::vector<std::pair<int, std::string>> zs;
+        for (auto & kv : R) if (kv.first.rfind("zone:", 0) == 0) {
+            size_t c = kv.first.find(':', 5);
+            zs.push_back({atoi(kv.first.substr(5, c - 5).c_str()), kv.first});
+        }
+        std::sort(zs.begin(), zs.end());
+        for (auto & z : zs) {
+            const Record & r = R.at(z.second);
+            FaceZone fz; size_t c = z.second.find(':', 5);
+            std::string nm = z.second.substr(c + 1);
+            fz.set_name(nm);
+            fz.set_type(nm == "interior" ? FaceZoneType::INTERIOR : FaceZoneType::BOUNDARY);
+            fz.faces = Kokkos::View<uint32_t *>("zone_faces", r.dims[0]);
+            fz.h_faces = Kokkos::create_mirror_view(fz.faces);
+            memcpy(fz.h_faces.data(), r.data.data(), r.data.size());
+            m->m_face_zones.push_back(fz);
+        }
+        // Same order as the generators (src/mesh/mesh.cpp:553-556)
+        m->compute_face_areas(); m->compute_cell_volumes(); m->compute_cell_centroids(); m->compute_face_normals();
+        s.mesh = m;
+    }
+    s.init_physics(); s.init_numerics(); s.init_boundaries(); s.init_run_parameters();
+    s.allocate_memory(); s.register_data(); s.init_output(); s.init_solution();
+    s.copy_host_to_device(); s.mesh->copy_host_to_device();
+    for (auto & b : s.boundaries) b->copy_host_to_device();
+    s.physics->copy_host_to_device();
+    // optional state override: record "U0" [nc][4] (+ "P0" [nc][5]) in the injected file
+    if (inj) {
+        auto it = inj->find("U0");
+        if (it != inj->end()) memcpy(s.conservatives.data(), it->second.data.data(), it->second.data.size());
+        it = inj->find("P0");
+        if (it != inj->end()) memcpy(s.primitives.data(), it->second.data.data(), it->second.data.size());
+    }
+}
+
+int do_dump(Solver & s, const std::string & out, int n_steps, int every) {
+    Writer w(out);
+    dump_mesh(w, *s.mesh);
+    if (auto * t = dynamic_cast<TENO *>(s.face_reconstruction.get())) dump_teno(w, *t);
+    w.f64("face_quad_weights", dims_of(s.face_reconstruction->quadrature_face.h_weights),
+          s.face_reconstruction->quadrature_face.h_weights.data());
+    w.f64("U0", dims_of(s.conservatives), s.conservatives.data());
+    w.f64("P0", dims_of(s.primitives), s.primitives.data());
+    // One bare RHS evaluation of the initial state: stage-1 face values and residual.
+    {
+        Kokkos::View<rtype *[N_CONSERVATIVE]> rhs("rhs_probe", s.mesh->n_cells);
+        s.calc_rhs(s.conservatives, s.face_conservatives, rhs);
+        Kokkos::fence();
+        w.f64("F_stage1", dims_of(s.face_conservatives), s.face_conservatives.data());
+        w.f64("rhs_stage1", dims_of(rhs), rhs.data());
+    }
+    for (int i = 0; i < n_steps; ++i) {
+        s.calc_dt();
+        if (!(i == 0 || (i + 1) % every == 0)) { s.take_step(); continue; }
+        std::string k = "step" + std::to_string(i) + ":";
+        w.scalar(k + "dt", s.dt);
+        w.f64(k + "cfl_local", dims_of(s.cfl_local), s.cfl_local.data());
+        s.take_step();
+        for (size_t r = 0; r < s.rhs_vec.size(); ++r)
+            w.f64(k + "rhs" + std::to_string(r), dims_of(s.rhs_vec[r]), s.rhs_vec[r].data());
+        if (s.solution_vec.size() > 1) w.f64(k + "U_temp", dims_of(s.solution_vec[1]), s.solution_vec[1].data());
+        w.f64(k + "F_last", dims_of(s.face_conservatives), s.face_conservatives.data());
+        w.f64(k + "U", dims_of(s.conservatives), s.conservatives.data());
+        w.f64(k + "P", dims_of(s.primitives), s.primitives.data());
+        w.scalar(k + "t", s.t);
+    }
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char ** argv) {
+    if (argc < 4) { fprintf(stderr, "usage: see header of oracle/ref_harness.cpp\n"); return 2; }
+    std::string mode = argv[1];
+    Kokkos::initialize(argc, argv);
+    int rc = 0;
+    {
+        std::streambuf * old = std::cout.rdbuf();
+        std::ostringstream sink;
+        if (!getenv("REF_HARNESS_VERBOSE")) std::cout.rdbuf(sink.rdbuf());
+        Solver s;
+        if (mode == "dump") {
+            init_with_mesh(s, argv[2], nullptr);
+            rc = do_dump(s, argv[3], argc > 4 ? atoi(argv[4]) : 1, argc > 5 ? atoi(argv[5]) : 1);
+        } else if (mode == "mesh") {
+            auto inj = read_mlbd(argv[2]);
+            init_with_mesh(s, argv[3], &inj);
+            rc = do_dump(s, argv[4], argc > 5 ? atoi(argv[5]) : 1, argc > 6 ? atoi(argv[6]) : 1);
+        } else if (mode == "time") {
+            auto t0 = std::chrono::steady_clock::now();
+            init_with_mesh(s, argv[2], nullptr);
+            auto t1 = std::chrono::steady_clock::now();
+            int n = atoi(argv[3]); int nw = argc > 4 ? atoi(argv[4]) : 1;
+            for (int i = 0; i < nw; ++i) { s.calc_dt(); s.take_step(); }
+            Kokkos::fence();
+            auto t2 = std::chrono::steady_clock::now();
+            for (int i = 0; i < n; ++i) { s.calc_dt(); s.take_step(); }   // Solver::run loop minus checks/output
+            Kokkos::fence();
+            auto t3 = std::chrono::steady_clock::now();
+            std::cout.rdbuf(old);
+            double sec = std::chrono::duration<double>(t3 - t2).count();
+            int n_stages = s.time_integrator->get_n_rhs_vectors();
+            printf("{\"n_cells\": %u, \"n_steps\": %d, \"n_stages\": %d, \"seconds\": %.6e, \"init_seconds\": %.6e, "
+                   "\"s_per_step_per_cell\": %.6e, \"cell_updates_per_s_per_stage\": %.6e, \"threads\": %d}\n",
+                   s.mesh->n_cells, n, n_stages, sec, std::chrono::duration<double>(t1 - t0).count(),
+                   sec / n / s.mesh->n_cells, (double)s.mesh->n_cells * n_stages * n / sec,
+                   (int)Kokkos::DefaultExecutionSpace::concurrency());
+        } else {
+            fprintf(stderr, "unknown mode %s\n", mode.c_str()); rc = 2;
+        }
+        std::cout.rdbuf(old);
+    }
+    Kokkos::finalize();
+    return rc;
+}

@@ -1,0 +1,64 @@
+"""Helpers shared by the parity tests: load tests/golden/*.npz (made by oracle/make_golden.py from the real
+reference) and rebuild the same configuration through the oracle."""
+import json
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MESH_KEYS = ["node_coords", "cell_coords", "cell_volume", "face_area", "face_normals", "nodes_of_cell",
+             "offsets_nodes_of_cell", "faces_of_cell", "offsets_faces_of_cell", "nodes_of_face", "offsets_nodes_of_face",
+             "cells_of_face"]
+ZONES = ["interior", "right", "top", "left", "bottom"]
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    d = {k: z[k] for k in z.files}
+    meta = json.loads(bytes(d.pop("meta")).decode())
+    return meta, d
+
+
+def names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+
+
+def oracle_mesh(oracle, meta):
+    m = meta["mesh"]
+    return oracle.Mesh.generate(m["type"], m["Nx"], m["Ny"], m["Lx"], m["Ly"])
+
+
+def solver_kwargs(meta):
+    r = meta["recon"]
+    kw = dict(recon=r["type"], riemann=meta["riemann"], integrator=meta["integrator"], bcs=meta["bcs"])
+    if r["type"] == "TENO":
+        kw.update(basis=r.get("basis_type", "monomial"), order=r["basis_order"], factor=r.get("max_stencil_size_factor", 2.0))
+    return kw
+
+
+def oracle_solver(oracle, meta, mesh=None):
+    mesh = mesh or oracle_mesh(oracle, meta)
+    return oracle.Solver(mesh, **solver_kwargs(meta))
+
+
+def real_faces(cells_of_face, nodes_of_face):
+    """cartesian_tri over-allocates faces: phantom faces have nodes (0,0)."""
+    nof = np.asarray(nodes_of_face).reshape(-1, 2)
+    return nof[:, 0] != nof[:, 1]
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|, tiny) over finite entries; non-finite patterns must coincide."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    fa, fb = np.isfinite(a), np.isfinite(b)
+    if not np.array_equal(fa, fb):
+        return np.inf
+    if not np.array_equal(np.isnan(a), np.isnan(b)):
+        return np.inf
+    inf_ok = np.array_equal(a[~fa & ~np.isnan(a)], b[~fb & ~np.isnan(b)])
+    if not inf_ok:
+        return np.inf
+    if not fa.any():
+        return 0.0
+    scale = np.maximum(np.abs(b[fb]), 1e-300)
+    return float(np.max(np.abs(a[fa] - b[fb]) / scale))
