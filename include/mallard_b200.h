@@ -1,0 +1,226 @@
+/*
+ * mallard_b200 — C ABI of the B200-native (sm_100a) replacement for Mallard's explicit residual hot path.
+ *
+ * The reference (MatthewBonanni/Mallard, C++20/Kokkos) has no FFI of its own; its extension points are C++
+ * virtual bases and one std::function seam.  Every entry point below replaces one of those seams and cites it
+ * (paths relative to the reference's src/).  Conventions:
+ *   - return 0 on success, non-zero on error; the message is available from mlb_last_error();
+ *     no C++ exception crosses this boundary;
+ *   - all arrays passed in or out are caller-owned HOST buffers in the REFERENCE's numbering and layout
+ *     (row-major / Kokkos LayoutRight: U[nc][4], prim[nc][5], face values [nf][Q][2][4]); the library owns all
+ *     device memory and applies/undoes its own cell/face renumbering internally;
+ *   - one host thread drives one context; calls are synchronous at the ABI unless stated otherwise;
+ *   - there is NO CPU fallback: every compute entry point fails if no CUDA device is usable.
+ */
+#ifndef MALLARD_B200_H
+#define MALLARD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mlb_ctx mlb_ctx;
+typedef struct mlb_host_mesh mlb_host_mesh;
+typedef struct mlb_plan mlb_plan;
+
+/* numerics/face_reconstruction.h:30-38 */
+enum { MLB_RECON_FO = 0, MLB_RECON_TENO = 1 };
+/* numerics/riemann_solver.h:27-37 */
+enum { MLB_RIEMANN_RUSANOV = 0, MLB_RIEMANN_HLL = 1, MLB_RIEMANN_HLLC = 2 };
+/* numerics/time_integrator.h:23-39 */
+enum { MLB_INTEGRATOR_FE = 0, MLB_INTEGRATOR_RK4 = 1, MLB_INTEGRATOR_SSPRK3 = 2 };
+/* boundary/boundary.h:31-45 */
+enum { MLB_BC_SYMMETRY = 0, MLB_BC_EXTRAPOLATION = 1, MLB_BC_WALL_ADIABATIC = 2, MLB_BC_UPT = 3, MLB_BC_P_OUT = 4 };
+/* numerics/basis.h:24-37 */
+enum { MLB_BASIS_MONOMIAL = 0, MLB_BASIS_LEGENDRE = 1 };
+/* mesh/mesh.h:30-42 (generators kept on the host) */
+enum { MLB_MESH_CARTESIAN = 0, MLB_MESH_CARTESIAN_TRI = 1, MLB_MESH_WEDGE = 2 };
+/* new: cell renumbering for locality (no reference equivalent) */
+enum { MLB_RENUMBER_NONE = 0, MLB_RENUMBER_RCM = 1 };
+/* new: floating-point contraction mode of the device kernels.
+ *   STRICT: no FMA contraction and reference summation order — reproduces the rounding of the reference's
+ *           x86-64 Kokkos Serial build operation by operation (libm pow excepted);
+ *   FAST:   FMA contraction allowed (<= 1e-12 relative per step against the reference). */
+enum { MLB_FP_STRICT = 0, MLB_FP_FAST = 1 };
+
+/* mesh/zone.h:57-142 — a named list of faces; the zone called "interior" holds the interior faces. */
+typedef struct {
+    const char *name;
+    uint32_t n_faces;
+    const uint32_t *faces;
+} mlb_zone;
+
+/* mesh/mesh.h:228-253 — the arrays the hot path consumes.  Geometry pointers may be NULL, in which case the
+ * library computes them exactly as Mesh::compute_* does (mesh/mesh.cpp:167-261). */
+typedef struct {
+    uint32_t n_cells, n_faces, n_nodes;
+    const double *node_coords;              /* [n_nodes][2] */
+    const uint32_t *offsets_nodes_of_cell;  /* [n_cells+1] */
+    const uint32_t *nodes_of_cell;
+    const uint32_t *offsets_faces_of_cell;  /* [n_cells+1] */
+    const uint32_t *faces_of_cell;
+    const uint32_t *offsets_nodes_of_face;  /* [n_faces+1] */
+    const uint32_t *nodes_of_face;
+    const int32_t *cells_of_face;           /* [n_faces][2], -1 = boundary */
+    const double *cell_coords;              /* [n_cells][2] or NULL */
+    const double *cell_volume;              /* [n_cells]    or NULL */
+    const double *face_area;                /* [n_faces]    or NULL */
+    const double *face_normals;             /* [n_faces][2] or NULL (area-weighted, out of cell 0) */
+    uint32_t n_zones;
+    const mlb_zone *zones;
+} mlb_mesh;
+
+/* [numerics] + [numerics.face_reconstruction] of the TOML input (solver/solver.cpp:110-186,
+ * numerics/face_reconstruction.cpp:109-116), already parsed. */
+typedef struct {
+    int32_t recon;                   /* MLB_RECON_* */
+    int32_t riemann;                 /* MLB_RIEMANN_* */
+    int32_t integrator;              /* MLB_INTEGRATOR_* */
+    int32_t basis;                   /* MLB_BASIS_* (TENO) */
+    int32_t basis_order;             /* TENO polynomial order p, 1..9 */
+    double max_stencil_size_factor;  /* TENO, default 2.0 */
+    int32_t quadrature_order_cell;   /* Dunavant order, 0 = reference default p+1 */
+    int32_t quadrature_order_face;   /* Gauss-Legendre order, 0 = reference default (p+1)/2 */
+    int32_t fp_mode;                 /* MLB_FP_* */
+    int32_t renumber;                /* MLB_RENUMBER_* */
+    int32_t teno_fixed;              /* 0 = reference-faithful weights; 1 = normalised ("N2") */
+    int32_t keep_stage_rhs;          /* 1 = keep every stage residual for mlb_get_array("rhsN") */
+} mlb_numerics;
+
+/* [physics] (physics/physics.cpp:27-53) */
+typedef struct {
+    double gamma, p_ref, T_ref, rho_ref, p_min, p_max;
+} mlb_physics;
+
+/* one [[boundaries]] entry (solver/solver.cpp:188-237); order of the array = order in the TOML file */
+typedef struct {
+    const char *zone_name;
+    int32_t type;   /* MLB_BC_* */
+    double u[2];    /* upt */
+    double p;       /* upt, p_out */
+    double T;       /* upt */
+} mlb_bc;
+
+/* Domain decomposition (new).  n_ranks == 1 → single GPU.  The exchange itself is driven by the caller's
+ * communicator (see mlb_halo_*). */
+typedef struct {
+    int32_t rank, n_ranks;
+    int32_t device;                  /* CUDA device ordinal for this context */
+} mlb_parallel;
+
+const char *mlb_version(void);
+/* message of the last failed call on `ctx` (or of the last failed mlb_create / stateless call when ctx == NULL) */
+const char *mlb_last_error(const mlb_ctx *ctx);
+
+/* ---- lifetime: replaces Solver::init's init_numerics/init_boundaries/allocate_memory/copy_host_to_device
+ *      (solver/solver.cpp:39-80,297-320).  Runs the mesh preprocessor (renumbering, SoA layout, CSR/ELL flattening of
+ *      the face and TENO-stencil connectivity, TENO tables) and uploads everything. */
+int mlb_create(mlb_ctx **out, const mlb_mesh *mesh, const mlb_numerics *numerics, const mlb_physics *physics,
+               const mlb_bc *bcs, int32_t n_bcs, const mlb_parallel *parallel /* NULL = 1 GPU, device 0 */);
+void mlb_destroy(mlb_ctx *ctx);
+
+/* ---- state: Solver::copy_host_to_device / copy_device_to_host (solver/solver.cpp:322-334) */
+int mlb_set_state(mlb_ctx *ctx, const double *U /* [nc][4] */, const double *prim /* [nc][5] or NULL = recompute */);
+int mlb_get_state(mlb_ctx *ctx, double *U /* or NULL */, double *prim /* or NULL */, double *cfl_local /* or NULL */);
+
+/* ---- FaceReconstruction::calc_face_values (numerics/face_reconstruction.h:75; .cpp:95-99,1081-1106) on the current
+ *      state.  F_out [nf][Q][2][4] in reference layout, entries the reference leaves undefined are written as 0. */
+int mlb_calc_face_values(mlb_ctx *ctx, double *F_out);
+int mlb_n_face_quadrature_points(const mlb_ctx *ctx);
+
+/* ---- the rhs_func seam: Solver::calc_rhs (solver/solver_rhs.cpp:44-55; solver.h:268-270) */
+int mlb_calc_rhs(mlb_ctx *ctx, double *rhs_out /* [nc][4] or NULL */);                   /* on the resident state */
+int mlb_calc_rhs_host(mlb_ctx *ctx, const double *U_in /* [nc][4] */, double *rhs_out);   /* host buffers in/out   */
+
+/* ---- Solver::calc_dt (solver/solver.cpp:580-590,592-742): spectral radius, max-reduction, dt = cfl/max,
+ *      cfl_local *= dt.  Uses the primitives of the last update_primitives, as the reference does. */
+int mlb_calc_dt(mlb_ctx *ctx, double cfl, double *dt_out);
+int mlb_set_dt(mlb_ctx *ctx, double dt);
+
+/* ---- Solver::take_step (solver/solver.cpp:521-531) = TimeIntegrator::take_step (numerics/time_integrator.cpp:57-163)
+ *      + update_primitives.  Uses the dt of the last mlb_calc_dt / mlb_set_dt (dt < 0 → error, solver.cpp:587-589). */
+int mlb_take_step(mlb_ctx *ctx);
+/* same seam with host buffers: H2D of U, one step, D2H of U (the end-to-end path a host-resident driver pays) */
+int mlb_take_step_host(mlb_ctx *ctx, double cfl /* <=0: keep dt */, double *U_inout, double *dt_out);
+/* ---- Solver::run's loop (solver/solver.cpp:352-373) minus checks/output: n_steps x { calc_dt ; take_step },
+ *      device-resident and asynchronous; returns after the last step completed.  cfl <= 0 → fixed dt. */
+int mlb_run(mlb_ctx *ctx, uint32_t n_steps, double cfl, double *t_out, double *dt_last_out);
+int mlb_get_time(mlb_ctx *ctx, double *t, uint64_t *step);
+
+/* ---- test hook mirroring the fake RHS of test/time_integrator_test.cpp:22-28 (NULL clears it) */
+int mlb_set_rhs_override(mlb_ctx *ctx, const double *rhs /* [nc][4] */);
+
+/* ---- introspection / parity hooks.  `name` is one of:
+ *   "perm_cells" (u32[nc], library index -> reference cell), "perm_faces" (u32[n real faces]),
+ *   "rhs0".."rhs3", "U_temp" (f64[nc][4]), "cfl_local" (f64[nc]),
+ *   "teno:offsets_stencil_groups", "teno:offsets_stencils", "teno:stencils", "teno:offsets_reconstruction_matrices"
+ *   (u32, reference CSR layout and numbering, numerics/face_reconstruction.h:201-260),
+ *   "teno:reconstruction_matrices", "teno:transformed_areas", "teno:integral_psi_target",
+ *   "teno:oscillation_indicator" (f64), "teno:poly_indices" (u8[K][2]),
+ *   "stats" (f64[8]: launches, preprocess seconds, device bytes, ...).
+ * out == NULL → only the byte size is returned in *nbytes. */
+int mlb_get_array(mlb_ctx *ctx, const char *name, void *out, uint64_t *nbytes);
+
+/* ---- measurement support: CUDA events on the library's compute stream */
+int mlb_event_record(mlb_ctx *ctx, int32_t slot /* 0..15 */);
+int mlb_event_elapsed_ms(mlb_ctx *ctx, int32_t slot_begin, int32_t slot_end, float *ms);   /* synchronises slot_end */
+/* per-kernel device time accumulated while profiling is on: names[i] / ms[i] / launches[i]; returns count */
+int mlb_profile_enable(mlb_ctx *ctx, int32_t on);
+int mlb_profile_read(mlb_ctx *ctx, int32_t max_entries, const char **names, double *ms, uint64_t *launches);
+uint64_t mlb_launch_count(const mlb_ctx *ctx);
+int mlb_synchronize(mlb_ctx *ctx);
+void *mlb_stream(mlb_ctx *ctx);   /* cudaStream_t of the compute stream */
+
+/* ---- multi-GPU halo exchange (new).  The context of rank r owns the cells with part[c] == r plus ghost
+ *      copies of every remote cell its stencils read.  Each stage the caller moves `send` to the peers and hands back
+ *      `recv`; buffers are DEVICE pointers owned by the library so NCCL / peer copies can use them directly. */
+int mlb_partition(const mlb_mesh *mesh, int32_t n_parts, int32_t *part_out /* [nc] */);
+int mlb_create_partitioned(mlb_ctx **out, const mlb_mesh *mesh, const int32_t *part, const mlb_numerics *numerics,
+                           const mlb_physics *physics, const mlb_bc *bcs, int32_t n_bcs, const mlb_parallel *parallel);
+int mlb_halo_info(mlb_ctx *ctx, int32_t *n_peers, int32_t *peers /* [n_ranks] */, uint64_t *send_counts,
+                  uint64_t *recv_counts /* CELLS per peer (4 doubles each), per exchange */);
+/* ghost cells this rank receives from peer `peer_index` (index into the peers array), as reference cell ids in the
+ * order they occupy the receive buffer; the caller ships each list to its peer, which registers what it must send: */
+int mlb_halo_recv_ids(mlb_ctx *ctx, int32_t peer_index, uint32_t *ref_ids_out /* [recv_counts[peer_index]] */);
+int mlb_halo_set_send_ids(mlb_ctx *ctx, int32_t n_lists, const int32_t *peer_ranks, const uint64_t *counts,
+                          const uint32_t *ref_ids /* concatenated */);
+int mlb_halo_buffers(mlb_ctx *ctx, void **send_dev, void **recv_dev);   /* contiguous, peers in ascending order */
+int mlb_halo_pack(mlb_ctx *ctx, int32_t stage);     /* async on the compute stream */
+int mlb_halo_unpack(mlb_ctx *ctx, int32_t stage);   /* async on the compute stream */
+/* split-phase stepping for callers that own the communicator: stage s of the current step, run after unpack */
+int mlb_n_stages(const mlb_ctx *ctx);
+int mlb_stage(mlb_ctx *ctx, int32_t stage);
+int mlb_local_max_spectral_radius(mlb_ctx *ctx, double *max_out);   /* rank-local part of calc_dt */
+int mlb_apply_dt(mlb_ctx *ctx, double cfl, double global_max);      /* dt = cfl/max ; cfl_local *= dt */
+int mlb_finish_step(mlb_ctx *ctx);                                  /* update_primitives ; t += dt ; step++ */
+int mlb_owned_cells(mlb_ctx *ctx, uint32_t *n_owned, uint32_t *cells_out /* reference ids, or NULL */);
+
+/* ---- stateless device kernels for known-answer tests of the plug-in interfaces */
+/* RiemannSolver::calc_flux (numerics/riemann_solver.h:85-90); L/R rows = rho,u,v,p,h */
+int mlb_riemann_flux(int32_t device, int32_t riemann, int32_t fp_mode, uint64_t n, const double *n_unit /* [n][2] */,
+                     const double *L /* [n][5] */, const double *R /* [n][5] */, double gamma, double *flux /* [n][4] */);
+/* Physics::compute_primitives_from_conservatives (physics/physics.h:852-867) + set_R_cp_cv (physics.cpp:69-73) */
+int mlb_compute_primitives(int32_t device, int32_t fp_mode, const mlb_physics *physics, uint64_t n, const double *U,
+                           double *prim /* [n][5] */, double *R_cp_cv /* [3] or NULL */);
+
+/* ---- the mesh preprocessor alone (host only, no device): what mlb_create uploads.  `part` may be NULL.  Arrays by name:
+ *   "sizes" (u32[12]: N, N_owned, N_recon, NF, n_slots, Q, K, M, Npad, S, Mp, 0), "perm_cells", "perm_faces",
+ *   "slot_face", "slot_nbr" (i32), "rhs_order" (u8), "st_ids", "ghost_owner" (i32 per ghost cell),
+ *   and the "teno:*" tables of mlb_get_array (reference CSR layout; unpartitioned plans only). */
+int mlb_plan_create(mlb_plan **out, const mlb_mesh *mesh, const mlb_numerics *numerics, const mlb_bc *bcs, int32_t n_bcs,
+                    const int32_t *part, const mlb_parallel *parallel);
+int mlb_plan_get(mlb_plan *plan, const char *name, void *out, uint64_t *nbytes);
+void mlb_plan_destroy(mlb_plan *plan);
+
+/* ---- host mesh generators: Mesh::init_cart / init_cart_tri / init_wedge (mesh/mesh.cpp:305-848) */
+int mlb_host_mesh_generate(mlb_host_mesh **out, int32_t type, uint32_t nx, uint32_t ny, double Lx, double Ly);
+int mlb_host_mesh_view(const mlb_host_mesh *m, mlb_mesh *view);   /* pointers stay valid until mlb_host_mesh_free */
+void mlb_host_mesh_free(mlb_host_mesh *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MALLARD_B200_H */

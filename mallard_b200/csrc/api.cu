@@ -1,0 +1,935 @@
+// C-ABI layer (include/mallard_b200.h): context lifetime, state movement, the stepping seams and the parity hooks.
+// Everything that computes runs in the CUDA kernels of kernels_impl.cuh; there is no CPU fallback.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <map>
+#include <memory>
+
+#include "kernel_args.h"
+
+using namespace mlb;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+#define CUDA_OK(expr)                                                                                              \
+    do {                                                                                                           \
+        cudaError_t e_ = (expr);                                                                                   \
+        if (e_ != cudaSuccess)                                                                                     \
+            throw CudaError(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr);                 \
+    } while (0)
+
+template <class T> T * dev_alloc(size_t n) {
+    T * p = nullptr;
+    CUDA_OK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    return p;
+}
+template <class T> T * dev_upload(const std::vector<T> & v, cudaStream_t st) {
+    T * p = dev_alloc<T>(v.size());
+    if (!v.empty()) CUDA_OK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    return p;
+}
+
+void require_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        throw CudaError(std::string("mallard_b200 needs a CUDA device and has no CPU fallback (") + cudaGetErrorString(e) + ")");
+    if (device < 0 || device >= n) throw CudaError("mallard_b200: CUDA device ordinal out of range");
+    CUDA_OK(cudaSetDevice(device));
+}
+
+struct ProfileEntry { double ms = 0.0; uint64_t launches = 0; };
+
+}  // namespace
+
+struct mlb_ctx {
+    std::string err;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    mlb_numerics num{};
+    GasParams gas{};
+    DevPhys phys{};
+    const KernelTable * kt = nullptr;
+    Prep prep;                         // host copy (big TENO tables are released after upload)
+    uint32_t nc_ref = 0, nf_ref = 0;   // reference mesh sizes
+    int n_stages = 1, n_rhs = 1;
+    bool teno = false;
+    int rank = 0, n_ranks = 1;
+
+    DevGeom g{};
+    double * U[3] = {nullptr, nullptr, nullptr};
+    double * k[4] = {nullptr, nullptr, nullptr, nullptr};
+    double * prim = nullptr, * sr = nullptr, * Fc = nullptr, * scal = nullptr, * k_override = nullptr;
+    long long * max_bits = nullptr;
+    unsigned int * blocks_done = nullptr;
+    unsigned long long * step_counter = nullptr;
+    uint32_t * d_perm_cells = nullptr, * d_perm_faces = nullptr;
+    uint32_t * d_st_ids = nullptr;
+    double * d_st_area = nullptr, * d_st_mat = nullptr;
+    double * d_stage = nullptr;        // AoS staging, 5*N doubles (and face export)
+    size_t d_stage_elems = 0;
+    double * h_stage = nullptr;        // pinned host staging
+    size_t h_stage_elems = 0;
+    std::vector<void *> owned_dev;     // everything to cudaFree
+    int cur = 0;                       // U[cur] holds the solution
+    int last_temp = 1;                 // buffer that corresponds to the reference's solution_vec[1]
+    bool has_override = false;
+    size_t device_bytes = 0;
+
+    // halo
+    std::vector<int32_t> peers;
+    std::vector<uint64_t> send_counts, recv_counts;      // cells per peer
+    std::vector<std::vector<uint32_t>> recv_ref_ids;     // per peer: reference ids of ghosts, in recv-buffer order
+    uint32_t * d_send_idx = nullptr, * d_recv_idx = nullptr;
+    double * d_send_buf = nullptr, * d_recv_buf = nullptr;
+    uint64_t n_send = 0, n_recv = 0;
+
+    // measurement
+    cudaEvent_t ev[16] = {};
+    uint64_t launches = 0;
+    bool profiling = false;
+    std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+    std::map<std::string, ProfileEntry> profile;
+    std::vector<std::string> profile_names;   // stable storage for mlb_profile_read
+
+    template <class T> T * track(T * p, size_t n) { owned_dev.push_back((void *)p); device_bytes += n * sizeof(T); return p; }
+    template <class T> T * alloc(size_t n) { return track(dev_alloc<T>(n), n); }
+    template <class T> T * upload(const std::vector<T> & v) { return track(dev_upload(v, stream), v.size()); }
+
+    void flush_profile() {
+        for (auto & p : pending) {
+            float ms = 0.f;
+            cudaEventSynchronize(p.second.second);
+            cudaEventElapsedTime(&ms, p.second.first, p.second.second);
+            auto & e = profile[p.first];
+            e.ms += ms; e.launches++;
+            cudaEventDestroy(p.second.first); cudaEventDestroy(p.second.second);
+        }
+        pending.clear();
+    }
+    template <class F> void launch(const char * name, F && f) {
+        if (profiling) {
+            cudaEvent_t a, b;
+            CUDA_OK(cudaEventCreate(&a)); CUDA_OK(cudaEventCreate(&b));
+            CUDA_OK(cudaEventRecord(a, stream));
+            f();
+            CUDA_OK(cudaEventRecord(b, stream));
+            pending.push_back({name, {a, b}});
+            if (pending.size() >= 2048) flush_profile();
+        } else f();
+        launches++;
+        CUDA_OK(cudaGetLastError());
+    }
+    void ensure_stage(size_t elems) {
+        if (elems > d_stage_elems) {
+            if (d_stage) cudaFree(d_stage);
+            d_stage = dev_alloc<double>(elems); d_stage_elems = elems;
+        }
+        if (elems > h_stage_elems) {
+            if (h_stage) cudaFreeHost(h_stage);
+            CUDA_OK(cudaMallocHost(&h_stage, elems * sizeof(double))); h_stage_elems = elems;
+        }
+    }
+    ~mlb_ctx() {
+        if (stream) cudaStreamSynchronize(stream);
+        for (auto & p : pending) { cudaEventDestroy(p.second.first); cudaEventDestroy(p.second.second); }
+        for (void * p : owned_dev) cudaFree(p);
+        if (d_stage) cudaFree(d_stage);
+        if (h_stage) cudaFreeHost(h_stage);
+        for (auto & e : ev) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+struct mlb_host_mesh { HostMesh m; };
+struct mlb_plan { Prep prep; uint32_t nc_ref = 0, nf_ref = 0; std::vector<int32_t> part; int rank = 0; std::string err; };
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stage schedule (numerics/time_integrator.cpp:57-163).  Buffers: U[cur] = solution, the two others are temporaries.
+// ---------------------------------------------------------------------------------------------------------------
+struct StagePlan { int in, out, base, mode, n_prev, last; double coef, c0, c1, cprev[3]; int kprev[3]; int kstore; };
+
+std::vector<StagePlan> make_plan(const mlb_ctx & c) {
+    const int A = c.cur, B = (c.cur + 1) % 3, C = (c.cur + 2) % 3;
+    std::vector<StagePlan> p;
+    auto mk = [&](int in, int out, int mode, double coef, int kstore) {
+        StagePlan s{}; s.in = in; s.out = out; s.base = A; s.mode = mode; s.coef = coef; s.kstore = kstore; return s; };
+    if (c.num.integrator == MLB_INTEGRATOR_FE) {
+        StagePlan s = mk(A, B, 0, 1.0, 0); s.last = 1; p.push_back(s);
+    } else if (c.num.integrator == MLB_INTEGRATOR_RK4) {
+        p.push_back(mk(A, B, 0, 0.5, 0));
+        p.push_back(mk(B, C, 0, 0.5, 1));
+        p.push_back(mk(C, B, 0, 1.0, 2));
+        StagePlan s = mk(B, A, 2, 1.0 / 6.0, 3);
+        s.n_prev = 3; s.kprev[0] = 0; s.kprev[1] = 1; s.kprev[2] = 2;
+        s.cprev[0] = 1.0 / 6.0; s.cprev[1] = 1.0 / 3.0; s.cprev[2] = 1.0 / 3.0; s.last = 1;
+        p.push_back(s);
+    } else {
+        p.push_back(mk(A, B, 0, 1.0, 0));
+        StagePlan s1 = mk(B, C, 1, 0.25, 1); s1.c0 = 3.0 / 4.0; s1.c1 = 1.0 / 4.0; p.push_back(s1);
+        StagePlan s2 = mk(C, A, 2, 2.0 / 3.0, 2);
+        s2.n_prev = 2; s2.kprev[0] = 0; s2.kprev[1] = 1; s2.cprev[0] = 1.0 / 6.0; s2.cprev[1] = 1.0 / 6.0; s2.last = 1;
+        p.push_back(s2);
+    }
+    return p;
+}
+
+ReconArgs recon_args(mlb_ctx & c, const double * Uin) {
+    ReconArgs r{};
+    r.g = c.g; r.Uin = Uin; r.Fc = c.Fc; r.st_ids = c.d_st_ids; r.st_area = c.d_st_area; r.st_mat = c.d_st_mat;
+    const TenoTables & T = c.prep.teno;
+    r.order = T.order; r.K = T.K; r.M = T.M; r.Mp = T.Mp; r.S = T.S; r.basis = T.basis; r.fixed_weights = c.num.teno_fixed;
+    for (size_t i = 0; i < c.prep.qf_x.size(); i++) r.qf_x[i] = c.prep.qf_x[i];
+    for (int i = 0; i < T.K; i++) { r.psi_bar[i] = T.psi_bar[i]; r.pidx[2 * i] = T.pidx[2 * i]; r.pidx[2 * i + 1] = T.pidx[2 * i + 1]; }
+    for (int i = 0; i < T.K * T.K; i++) r.OI[i] = T.OI[i];
+    return r;
+}
+
+void run_stage(mlb_ctx & c, const StagePlan & s, bool bare, double * k_out) {
+    const double * Uin = c.U[s.in];
+    if (c.teno && !c.has_override) {
+        ReconArgs r = recon_args(c, Uin);
+        c.launch("teno_recon", [&] { c.kt->recon(r, c.stream); });
+    }
+    StageArgs a{};
+    a.g = c.g; a.ph = c.phys; a.Uin = Uin; a.Fc = c.Fc; a.teno = c.teno ? 1 : 0;
+    a.k_override = c.has_override ? c.k_override : nullptr;
+    a.scal = c.scal; a.step_counter = c.step_counter;
+    RkArgs & rk = a.rk;
+    if (bare) { rk.mode = 3; rk.k_store = k_out; }
+    else {
+        rk.mode = s.mode; rk.n_prev = s.n_prev; rk.last_stage = s.last;
+        rk.base = c.U[s.base]; rk.out = c.U[s.out];
+        const bool need_k = c.num.keep_stage_rhs || !s.last;
+        rk.k_store = need_k ? c.k[s.kstore] : nullptr;
+        for (int j = 0; j < s.n_prev; j++) { rk.kprev[j] = c.k[s.kprev[j]]; rk.cprev[j] = s.cprev[j]; }
+        rk.c0 = s.c0; rk.c1 = s.c1; rk.coef = s.coef;
+        rk.prim_out = s.last ? c.prim : nullptr;
+    }
+    c.launch(c.teno ? "flux_stage_teno" : "flux_stage_fo", [&] { c.kt->stage(a, c.stream); });
+}
+
+void finish_plan(mlb_ctx & c, const std::vector<StagePlan> & plan) {
+    if (c.num.integrator == MLB_INTEGRATOR_FE) { c.last_temp = c.cur; c.cur = plan.back().out; }
+    else c.last_temp = plan[plan.size() - 2].out;   // reference's solution_vec[1] after the step
+}
+
+void do_step(mlb_ctx & c) {
+    const auto plan = make_plan(c);
+    for (auto & s : plan) run_stage(c, s, false, nullptr);
+    finish_plan(c, plan);
+}
+
+void do_calc_dt(mlb_ctx & c, double cfl) {
+    CflArgs a{};
+    a.g = c.g; a.gas = c.gas; a.U = c.U[c.cur]; a.prim = c.prim; a.sr_out = c.sr; a.scal = c.scal;
+    a.max_bits = c.max_bits; a.blocks_done = c.blocks_done; a.cfl = cfl;
+    c.launch("cfl", [&] { c.kt->cfl(a, c.stream); });
+}
+
+void read_scalars(mlb_ctx & c, double * out) {
+    CUDA_OK(cudaMemcpyAsync(out, c.scal, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    CUDA_OK(cudaStreamSynchronize(c.stream));
+}
+
+void import_state(mlb_ctx & c, const double * U_host, double * soa, int nv) {
+    const size_t n = (size_t)c.nc_ref * nv;
+    c.ensure_stage(std::max<size_t>(n, 1));
+    CUDA_OK(cudaMemcpyAsync(c.d_stage, U_host, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    launch_import_state(c.d_stage, c.d_perm_cells, c.prep.N, c.prep.Npad, nv, soa, c.stream);
+    c.launches++;
+}
+
+void export_state(mlb_ctx & c, const double * soa, int nv, double * out_host) {
+    const size_t n = (size_t)c.nc_ref * nv;
+    c.ensure_stage(std::max<size_t>(n, 1));
+    if (c.n_ranks > 1) CUDA_OK(cudaMemsetAsync(c.d_stage, 0, n * sizeof(double), c.stream));
+    launch_export_state(soa, c.d_perm_cells, c.prep.N_owned, c.prep.Npad, nv, c.d_stage, c.stream);
+    c.launches++;
+    CUDA_OK(cudaMemcpyAsync(out_host, c.d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    CUDA_OK(cudaStreamSynchronize(c.stream));
+}
+
+mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_numerics * numerics, const mlb_physics * physics,
+                      const mlb_bc * bcs, int32_t n_bcs, const mlb_parallel * par) {
+    if (!mesh || !numerics || !physics) throw std::runtime_error("mlb_create: NULL argument");
+    if (n_bcs > MAX_BCS) throw std::runtime_error("mlb_create: too many boundaries");
+    std::unique_ptr<mlb_ctx> c(new mlb_ctx());
+    c->device = par ? par->device : 0;
+    c->rank = par ? par->rank : 0;
+    c->n_ranks = par ? std::max(1, par->n_ranks) : 1;
+    require_device(c->device);
+    CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->num = *numerics;
+    if (c->num.recon != MLB_RECON_FO && c->num.recon != MLB_RECON_TENO) throw std::runtime_error("Unknown face reconstruction type.");
+    if (c->num.riemann < 0 || c->num.riemann > 2) throw std::runtime_error("Unknown Riemann solver type.");
+    if (c->num.integrator < 0 || c->num.integrator > 2) throw std::runtime_error("Unknown time integrator type.");
+    c->teno = c->num.recon == MLB_RECON_TENO;
+    c->kt = c->num.fp_mode == MLB_FP_FAST ? kernels_fast() : kernels_strict();
+    c->gas = make_gas(*physics);
+    c->n_stages = c->num.integrator == MLB_INTEGRATOR_FE ? 1 : (c->num.integrator == MLB_INTEGRATOR_RK4 ? 4 : 3);
+    c->n_rhs = c->n_stages;
+
+    HostMesh hm;
+    host_mesh_from_view(hm, *mesh);
+    c->nc_ref = hm.nc; c->nf_ref = hm.nf;
+
+    std::vector<std::string> bc_zones;
+    c->phys.gas = c->gas; c->phys.riemann = c->num.riemann; c->phys.n_bcs = n_bcs;
+    for (int b = 0; b < n_bcs; b++) {
+        if (!bcs[b].zone_name) throw std::runtime_error("Boundary name not specified.");
+        if (bcs[b].type < 0 || bcs[b].type > MLB_BC_P_OUT) throw std::runtime_error("Unknown boundary type.");
+        bc_zones.push_back(bcs[b].zone_name);
+        BcParams & d = c->phys.bcs[b];
+        d.type = bcs[b].type;
+        for (double & x : d.data) x = 0.0;
+        if (d.type == MLB_BC_UPT) {   // boundary_upt.cpp:38-73
+            const double rho = bcs[b].p / (c->gas.R * bcs[b].T);
+            const double e = c->gas.cv * bcs[b].T;
+            d.data[0] = rho; d.data[1] = bcs[b].u[0]; d.data[2] = bcs[b].u[1]; d.data[3] = bcs[b].p; d.data[4] = bcs[b].T;
+            d.data[5] = e + bcs[b].p / rho;
+        } else if (d.type == MLB_BC_P_OUT) d.data[0] = bcs[b].p;
+    }
+
+    PrepOptions opt;
+    opt.renumber = c->num.renumber;
+    opt.keep_ref_tables = c->teno && !part && hm.nc <= 200000;
+    opt.part = part; opt.rank = c->rank; opt.n_ranks = c->n_ranks;
+    preprocess(hm, c->num, bc_zones, opt, c->prep);
+    Prep & P = c->prep;
+    for (size_t i = 0; i < P.qf_x.size(); i++) { c->phys.qf_x[i] = P.qf_x[i]; c->phys.qf_w[i] = P.qf_w[i]; }
+    if (c->teno && !c->kt->recon_supported(P.teno.order, P.teno.Mp, P.teno.basis))
+        throw std::runtime_error("TENO: this (basis, order, stencil size) combination has no compiled device kernel "
+                                 "(available: legendre, order 1-4, max_stencil_size_factor 2.0)");
+
+    // ---- upload
+    DevGeom & g = c->g;
+    g.N = P.N; g.N_owned = P.N_owned; g.N_recon = P.N_recon; g.Npad = P.Npad; g.NF = P.NF; g.n_slots = P.n_slots; g.Q = P.Q;
+    g.slot_face = c->upload(P.slot_face); g.slot_nbr = c->upload(P.slot_nbr); g.slot_nslot = c->upload(P.slot_nslot);
+    g.rhs_order = c->upload(P.rhs_order); g.nfc = c->upload(P.n_faces_of_cell);
+    g.cell_vol = c->upload(P.cell_vol); g.cell_xy = c->upload(P.cell_xy);
+    {
+        dvec bs(P.Npad, 0.0);
+        for (uint32_t i = 0; i < P.N; i++) bs[i] = 2.0 * std::pow(P.cell_vol[i], 1.0 / 2);   // solver.cpp:664-665 (libm pow)
+        g.bnd_s = c->upload(bs);
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+    g.face_nx = c->upload(P.face_nx); g.face_ny = c->upload(P.face_ny); g.face_area = c->upload(P.face_area);
+    g.slot_fx = c->teno ? c->upload(P.slot_fx) : nullptr;
+    c->d_perm_cells = c->upload(P.perm_cells);
+    c->d_perm_faces = c->upload(P.perm_faces);
+    const size_t NP = P.Npad;
+    for (int i = 0; i < 3; i++) { c->U[i] = c->alloc<double>(4 * NP); CUDA_OK(cudaMemsetAsync(c->U[i], 0, 4 * NP * sizeof(double), c->stream)); }
+    for (int i = 0; i < c->n_rhs; i++) { c->k[i] = c->alloc<double>(4 * NP); CUDA_OK(cudaMemsetAsync(c->k[i], 0, 4 * NP * sizeof(double), c->stream)); }
+    c->prim = c->alloc<double>(5 * NP); CUDA_OK(cudaMemsetAsync(c->prim, 0, 5 * NP * sizeof(double), c->stream));
+    c->sr = c->alloc<double>(NP); CUDA_OK(cudaMemsetAsync(c->sr, 0, NP * sizeof(double), c->stream));
+    c->scal = c->alloc<double>(SC_COUNT);
+    {
+        double init[SC_COUNT] = {0};
+        init[SC_DT] = -1.0;   // "no dt yet": mlb_take_step refuses negative dt like Solver::calc_dt (solver.cpp:587-589)
+        CUDA_OK(cudaMemcpyAsync(c->scal, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+    c->max_bits = c->alloc<long long>(1);
+    {
+        const double m1 = -1.0; long long bits; std::memcpy(&bits, &m1, 8);
+        CUDA_OK(cudaMemcpy(c->max_bits, &bits, 8, cudaMemcpyHostToDevice));
+    }
+    c->blocks_done = c->alloc<unsigned int>(1); CUDA_OK(cudaMemset(c->blocks_done, 0, 4));
+    c->step_counter = c->alloc<unsigned long long>(1); CUDA_OK(cudaMemset(c->step_counter, 0, 8));
+    if (c->teno) {
+        TenoTables & T = P.teno;
+        c->Fc = c->alloc<double>((size_t)P.n_slots * P.Q * 4 * NP);
+        CUDA_OK(cudaMemsetAsync(c->Fc, 0, (size_t)P.n_slots * P.Q * 4 * NP * sizeof(double), c->stream));
+        c->d_st_ids = c->upload(T.st_ids); c->d_st_area = c->upload(T.st_area); c->d_st_mat = c->upload(T.st_mat);
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        uvec().swap(T.st_ids); dvec().swap(T.st_area); dvec().swap(T.st_mat);   // host copies no longer needed
+    }
+    for (auto & e : c->ev) CUDA_OK(cudaEventCreate(&e));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return c.release();
+}
+
+}  // namespace
+
+#define API_BEGIN(ctx)  try { if (!(ctx)) throw std::runtime_error("NULL context");
+#define API_BEGIN0(ctx) try {
+#define API_END(ctx)                                                       \
+    return 0; }                                                            \
+    catch (const std::exception & e) { if (ctx) (ctx)->err = e.what(); g_err = e.what(); return 1; }
+
+extern "C" {
+
+const char * mlb_version(void) { return "mallard_b200 0.1 (sm_100a)"; }
+const char * mlb_last_error(const mlb_ctx * ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int mlb_create(mlb_ctx ** out, const mlb_mesh * mesh, const mlb_numerics * numerics, const mlb_physics * physics,
+               const mlb_bc * bcs, int32_t n_bcs, const mlb_parallel * parallel) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!out) throw std::runtime_error("mlb_create: out is NULL");
+    *out = nullptr;
+    *out = create_impl(mesh, nullptr, numerics, physics, bcs, n_bcs, parallel);
+    API_END(none)
+}
+
+int mlb_create_partitioned(mlb_ctx ** out, const mlb_mesh * mesh, const int32_t * part, const mlb_numerics * numerics,
+                           const mlb_physics * physics, const mlb_bc * bcs, int32_t n_bcs, const mlb_parallel * parallel) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!out || !part || !parallel) throw std::runtime_error("mlb_create_partitioned: NULL argument");
+    *out = nullptr;
+    mlb_ctx * c = create_impl(mesh, part, numerics, physics, bcs, n_bcs, parallel);
+    // ghosts grouped by owning rank (ascending), in library order within a group
+    std::map<int32_t, std::vector<uint32_t>> by_owner;
+    for (uint32_t i = c->prep.N_owned; i < c->prep.N; i++) by_owner[part[c->prep.perm_cells[i]]].push_back(i);
+    std::vector<uint32_t> recv_idx;
+    for (auto & kv : by_owner) {
+        c->peers.push_back(kv.first);
+        c->recv_counts.push_back(kv.second.size());
+        std::vector<uint32_t> ref;
+        for (uint32_t i : kv.second) { ref.push_back(c->prep.perm_cells[i]); recv_idx.push_back(i); }
+        c->recv_ref_ids.push_back(ref);
+    }
+    c->n_recv = recv_idx.size();
+    c->d_recv_idx = c->upload(recv_idx);
+    c->d_recv_buf = c->alloc<double>(4 * std::max<size_t>(c->n_recv, 1));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    *out = c;
+    API_END(none)
+}
+
+void mlb_destroy(mlb_ctx * ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    delete ctx;
+}
+
+int mlb_set_state(mlb_ctx * c, const double * U, const double * prim) {
+    API_BEGIN(c)
+    if (!U) throw std::runtime_error("mlb_set_state: U is NULL");
+    CUDA_OK(cudaSetDevice(c->device));
+    import_state(*c, U, c->U[c->cur], 4);
+    if (prim) import_state(*c, prim, c->prim, 5);
+    else { c->kt->primitives_soa(c->gas, c->prep.N, c->prep.Npad, c->U[c->cur], c->prim, c->stream); c->launches++; }
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    API_END(c)
+}
+
+int mlb_get_state(mlb_ctx * c, double * U, double * prim, double * cfl_local) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    if (U) export_state(*c, c->U[c->cur], 4, U);
+    if (prim) export_state(*c, c->prim, 5, prim);
+    if (cfl_local) {
+        c->ensure_stage(c->nc_ref);
+        if (c->n_ranks > 1) CUDA_OK(cudaMemsetAsync(c->d_stage, 0, (size_t)c->nc_ref * sizeof(double), c->stream));
+        launch_export_scaled(c->sr, c->scal, SC_DT, c->d_perm_cells, c->prep.N_owned, c->d_stage, c->stream);
+        CUDA_OK(cudaMemcpyAsync(cfl_local, c->d_stage, (size_t)c->nc_ref * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+    API_END(c)
+}
+
+int mlb_n_face_quadrature_points(const mlb_ctx * c) { return c ? c->prep.Q : 0; }
+
+int mlb_calc_face_values(mlb_ctx * c, double * F_out) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    if (c->teno) {
+        ReconArgs r = recon_args(*c, c->U[c->cur]);
+        c->launch("teno_recon", [&] { c->kt->recon(r, c->stream); });
+    }
+    if (F_out) {
+        const size_t n = (size_t)c->nf_ref * c->prep.Q * 8;
+        c->ensure_stage(n);
+        CUDA_OK(cudaMemsetAsync(c->d_stage, 0, n * sizeof(double), c->stream));
+        launch_export_faces(c->teno ? c->Fc : nullptr, c->U[c->cur], c->g.slot_face, c->d_perm_faces, c->prep.N_owned, c->prep.Npad,
+                            c->prep.n_slots, c->prep.Q, c->d_stage, c->stream);
+        c->launches++;
+        CUDA_OK(cudaMemcpyAsync(F_out, c->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    API_END(c)
+}
+
+int mlb_calc_rhs(mlb_ctx * c, double * rhs_out) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    StagePlan s{}; s.in = c->cur;
+    run_stage(*c, s, true, c->k[0]);
+    if (rhs_out) export_state(*c, c->k[0], 4, rhs_out);
+    else CUDA_OK(cudaStreamSynchronize(c->stream));
+    API_END(c)
+}
+
+int mlb_calc_rhs_host(mlb_ctx * c, const double * U_in, double * rhs_out) {
+    API_BEGIN(c)
+    if (!U_in || !rhs_out) throw std::runtime_error("mlb_calc_rhs_host: NULL buffer");
+    CUDA_OK(cudaSetDevice(c->device));
+    const int tmp = (c->cur + 1) % 3;
+    import_state(*c, U_in, c->U[tmp], 4);
+    StagePlan s{}; s.in = tmp;
+    run_stage(*c, s, true, c->k[0]);
+    export_state(*c, c->k[0], 4, rhs_out);
+    API_END(c)
+}
+
+int mlb_calc_dt(mlb_ctx * c, double cfl, double * dt_out) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    if (!(cfl > 0.0)) throw std::runtime_error("mlb_calc_dt: cfl must be positive");
+    do_calc_dt(*c, cfl);
+    double sc[SC_COUNT];
+    read_scalars(*c, sc);
+    if (dt_out) *dt_out = sc[SC_DT];
+    if (sc[SC_DT] < 0.0) throw std::runtime_error("dt negative: " + std::to_string(sc[SC_DT]) + ".");
+    API_END(c)
+}
+
+int mlb_set_dt(mlb_ctx * c, double dt) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    if (dt < 0.0) throw std::runtime_error("dt negative: " + std::to_string(dt) + ".");
+    launch_set_scalar(c->scal, SC_DT, dt, c->stream);
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    API_END(c)
+}
+
+int mlb_take_step(mlb_ctx * c) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    double sc[SC_COUNT];
+    read_scalars(*c, sc);
+    if (sc[SC_DT] < 0.0) throw std::runtime_error("dt negative: " + std::to_string(sc[SC_DT]) + ".");
+    do_step(*c);
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    API_END(c)
+}
+
+int mlb_take_step_host(mlb_ctx * c, double cfl, double * U_inout, double * dt_out) {
+    API_BEGIN(c)
+    if (!U_inout) throw std::runtime_error("mlb_take_step_host: NULL buffer");
+    CUDA_OK(cudaSetDevice(c->device));
+    import_state(*c, U_inout, c->U[c->cur], 4);
+    if (cfl > 0.0) {
+        c->kt->primitives_soa(c->gas, c->prep.N, c->prep.Npad, c->U[c->cur], c->prim, c->stream); c->launches++;
+        do_calc_dt(*c, cfl);
+    }
+    do_step(*c);
+    export_state(*c, c->U[c->cur], 4, U_inout);
+    if (dt_out) { double sc[SC_COUNT]; read_scalars(*c, sc); *dt_out = sc[SC_DT]; }
+    API_END(c)
+}
+
+int mlb_run(mlb_ctx * c, uint32_t n_steps, double cfl, double * t_out, double * dt_last_out) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    if (c->n_ranks > 1) throw std::runtime_error("mlb_run: partitioned contexts are stepped with the split-phase API");
+    for (uint32_t i = 0; i < n_steps; i++) {
+        if (cfl > 0.0) do_calc_dt(*c, cfl);
+        do_step(*c);
+    }
+    double sc[SC_COUNT];
+    read_scalars(*c, sc);
+    if (t_out) *t_out = sc[SC_T];
+    if (dt_last_out) *dt_last_out = sc[SC_DT];
+    if (sc[SC_DT] < 0.0) throw std::runtime_error("dt negative: " + std::to_string(sc[SC_DT]) + ".");
+    API_END(c)
+}
+
+int mlb_get_time(mlb_ctx * c, double * t, uint64_t * step) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    double sc[SC_COUNT];
+    read_scalars(*c, sc);
+    if (t) *t = sc[SC_T];
+    if (step) { unsigned long long s; CUDA_OK(cudaMemcpy(&s, c->step_counter, 8, cudaMemcpyDeviceToHost)); *step = s; }
+    API_END(c)
+}
+
+int mlb_set_rhs_override(mlb_ctx * c, const double * rhs) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    if (!rhs) { c->has_override = false; return 0; }
+    if (!c->k_override) c->k_override = c->alloc<double>(4 * (size_t)c->prep.Npad);
+    import_state(*c, rhs, c->k_override, 4);
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->has_override = true;
+    API_END(c)
+}
+
+int mlb_get_array(mlb_ctx * c, const char * name, void * out, uint64_t * nbytes) {
+    API_BEGIN(c)
+    if (!name || !nbytes) throw std::runtime_error("mlb_get_array: NULL argument");
+    CUDA_OK(cudaSetDevice(c->device));
+    const std::string n = name;
+    const Prep & P = c->prep;
+    const TenoTables & T = P.teno;
+    auto host = [&](const void * p, size_t nb) { if (out) std::memcpy(out, p, nb); *nbytes = nb; };
+    if (n == "perm_cells") host(P.perm_cells.data(), P.perm_cells.size() * 4);
+    else if (n == "perm_faces") host(P.perm_faces.data(), P.perm_faces.size() * 4);
+    else if (n.size() == 4 && n.rfind("rhs", 0) == 0) {
+        const int r = n[3] - '0';
+        if (r < 0 || r >= c->n_rhs) throw std::runtime_error("no such stage residual: " + n);
+        *nbytes = (uint64_t)c->nc_ref * 32;
+        if (out) export_state(*c, c->k[r], 4, (double *)out);
+    } else if (n == "U_temp") {
+        *nbytes = (uint64_t)c->nc_ref * 32;
+        if (out) export_state(*c, c->U[c->last_temp], 4, (double *)out);
+    } else if (n == "cfl_local") {
+        *nbytes = (uint64_t)c->nc_ref * 8;
+        if (out) { if (mlb_get_state(c, nullptr, nullptr, (double *)out)) throw std::runtime_error(c->err); }
+    } else if (n == "stats") {
+        double s[8] = {(double)c->launches, P.seconds, (double)c->device_bytes, (double)P.N, (double)P.N_owned, (double)P.NF,
+                       (double)P.N_recon, (double)c->n_stages};
+        host(s, sizeof(s));
+    } else if (n.rfind("teno:", 0) == 0) {
+        if (!c->teno) throw std::runtime_error("context has no TENO tables");
+        if (n == "teno:integral_psi_target") host(T.psi_bar.data(), T.psi_bar.size() * 8);
+        else if (n == "teno:oscillation_indicator") host(T.OI.data(), T.OI.size() * 8);
+        else if (n == "teno:poly_indices") host(T.pidx.data(), T.pidx.size());
+        else {
+            if (!T.keep_ref) throw std::runtime_error("reference-layout TENO tables were not kept for this context (mesh too large or partitioned)");
+            if (n == "teno:offsets_stencil_groups") host(T.ref_off_groups.data(), T.ref_off_groups.size() * 4);
+            else if (n == "teno:offsets_stencils") host(T.ref_off_stencils.data(), T.ref_off_stencils.size() * 4);
+            else if (n == "teno:stencils") host(T.ref_stencils.data(), T.ref_stencils.size() * 4);
+            else if (n == "teno:offsets_reconstruction_matrices") host(T.ref_off_mats.data(), T.ref_off_mats.size() * 4);
+            else if (n == "teno:reconstruction_matrices") host(T.ref_mats.data(), T.ref_mats.size() * 8);
+            else if (n == "teno:transformed_areas") host(T.ref_areas.data(), T.ref_areas.size() * 8);
+            else throw std::runtime_error("unknown array " + n);
+        }
+    } else throw std::runtime_error("unknown array " + n);
+    API_END(c)
+}
+
+int mlb_event_record(mlb_ctx * c, int32_t slot) {
+    API_BEGIN(c)
+    if (slot < 0 || slot >= 16) throw std::runtime_error("event slot out of range");
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaEventRecord(c->ev[slot], c->stream));
+    API_END(c)
+}
+int mlb_event_elapsed_ms(mlb_ctx * c, int32_t a, int32_t b, float * ms) {
+    API_BEGIN(c)
+    if (a < 0 || a >= 16 || b < 0 || b >= 16 || !ms) throw std::runtime_error("bad event query");
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaEventSynchronize(c->ev[b]));
+    CUDA_OK(cudaEventElapsedTime(ms, c->ev[a], c->ev[b]));
+    API_END(c)
+}
+int mlb_profile_enable(mlb_ctx * c, int32_t on) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    c->flush_profile();
+    if (on && !c->profiling) c->profile.clear();
+    c->profiling = on != 0;
+    API_END(c)
+}
+int mlb_profile_read(mlb_ctx * c, int32_t max_entries, const char ** names, double * ms, uint64_t * launches) {
+    if (!c) return 0;
+    try {
+        cudaSetDevice(c->device);
+        c->flush_profile();
+        c->profile_names.clear();
+        for (auto & kv : c->profile) c->profile_names.push_back(kv.first);
+        int i = 0;
+        for (auto & kv : c->profile) {
+            if (i >= max_entries) break;
+            if (names) names[i] = c->profile_names[i].c_str();
+            if (ms) ms[i] = kv.second.ms;
+            if (launches) launches[i] = kv.second.launches;
+            i++;
+        }
+        return i;
+    } catch (const std::exception & e) { c->err = e.what(); return -1; }
+}
+uint64_t mlb_launch_count(const mlb_ctx * c) { return c ? c->launches : 0; }
+int mlb_synchronize(mlb_ctx * c) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    API_END(c)
+}
+void * mlb_stream(mlb_ctx * c) { return c ? (void *)c->stream : nullptr; }
+
+// ---- multi-GPU -------------------------------------------------------------------------------------------------
+int mlb_halo_info(mlb_ctx * c, int32_t * n_peers, int32_t * peers, uint64_t * send_counts, uint64_t * recv_counts) {
+    API_BEGIN(c)
+    if (n_peers) *n_peers = (int32_t)c->peers.size();
+    for (size_t i = 0; i < c->peers.size(); i++) {
+        if (peers) peers[i] = c->peers[i];
+        if (recv_counts) recv_counts[i] = c->recv_counts[i];
+        if (send_counts) send_counts[i] = i < c->send_counts.size() ? c->send_counts[i] : 0;
+    }
+    API_END(c)
+}
+int mlb_halo_recv_ids(mlb_ctx * c, int32_t peer_index, uint32_t * ref_ids_out) {
+    API_BEGIN(c)
+    if (peer_index < 0 || peer_index >= (int)c->recv_ref_ids.size()) throw std::runtime_error("bad peer index");
+    const auto & v = c->recv_ref_ids[peer_index];
+    if (ref_ids_out) std::memcpy(ref_ids_out, v.data(), v.size() * 4);
+    API_END(c)
+}
+int mlb_halo_set_send_ids(mlb_ctx * c, int32_t n_lists, const int32_t * peer_ranks, const uint64_t * counts, const uint32_t * ref_ids) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    // the lists must come for the same peers, ascending — a symmetric halo graph (face neighbours / stencils) guarantees it
+    std::vector<uint32_t> idx;
+    c->send_counts.assign(c->peers.size(), 0);
+    size_t off = 0;
+    for (int l = 0; l < n_lists; l++) {
+        auto it = std::find(c->peers.begin(), c->peers.end(), peer_ranks[l]);
+        if (it == c->peers.end() && counts[l]) throw std::runtime_error("halo: send list for a rank that sends us nothing (asymmetric halo)");
+        for (uint64_t k = 0; k < counts[l]; k++) {
+            const uint32_t ref = ref_ids[off + k];
+            const uint32_t loc = ref < c->nc_ref ? c->prep.iperm_cells[ref] : NO_FACE;
+            if (loc == NO_FACE || loc >= c->prep.N_owned) throw std::runtime_error("halo: peer requested a cell this rank does not own");
+            idx.push_back(loc);
+        }
+        if (it != c->peers.end()) c->send_counts[it - c->peers.begin()] = counts[l];
+        off += counts[l];
+    }
+    c->n_send = idx.size();
+    c->d_send_idx = c->upload(idx);
+    c->d_send_buf = c->alloc<double>(4 * std::max<size_t>(c->n_send, 1));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    API_END(c)
+}
+int mlb_halo_buffers(mlb_ctx * c, void ** send_dev, void ** recv_dev) {
+    API_BEGIN(c)
+    if (send_dev) *send_dev = c->d_send_buf;
+    if (recv_dev) *recv_dev = c->d_recv_buf;
+    API_END(c)
+}
+static int stage_input_buffer(mlb_ctx * c, int32_t stage) {
+    const auto plan = make_plan(*c);
+    if (stage < 0 || stage >= (int)plan.size()) throw std::runtime_error("stage out of range");
+    return plan[stage].in;
+}
+int mlb_halo_pack(mlb_ctx * c, int32_t stage) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    const int b = stage_input_buffer(c, stage);
+    c->launch("halo_pack", [&] { launch_gather(c->U[b], c->d_send_idx, (uint32_t)c->n_send, c->prep.Npad, c->d_send_buf, c->stream); });
+    API_END(c)
+}
+int mlb_halo_unpack(mlb_ctx * c, int32_t stage) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    const int b = stage_input_buffer(c, stage);
+    c->launch("halo_unpack", [&] { launch_scatter(c->d_recv_buf, c->d_recv_idx, (uint32_t)c->n_recv, c->prep.Npad, c->U[b], c->stream); });
+    if (stage == 0 && c->prep.N > c->prep.N_owned) {   // ghosts' primitives for the CFL kernel (update_primitives of their owners)
+        const uint32_t off = c->prep.N_owned & ~31u;    // keep the SoA column alignment
+        c->kt->primitives_soa(c->gas, c->prep.N - off, c->prep.Npad, c->U[b] + off, c->prim + off, c->stream);
+        c->launches++;
+    }
+    API_END(c)
+}
+int mlb_n_stages(const mlb_ctx * c) { return c ? c->n_stages : 0; }
+int mlb_stage(mlb_ctx * c, int32_t stage) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    const auto plan = make_plan(*c);
+    if (stage < 0 || stage >= (int)plan.size()) throw std::runtime_error("stage out of range");
+    run_stage(*c, plan[stage], false, nullptr);
+    if (stage == (int)plan.size() - 1) finish_plan(*c, plan);
+    API_END(c)
+}
+int mlb_local_max_spectral_radius(mlb_ctx * c, double * max_out) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    do_calc_dt(*c, -1.0);
+    double sc[SC_COUNT];
+    read_scalars(*c, sc);
+    if (max_out) *max_out = sc[SC_MAX_SR];
+    API_END(c)
+}
+int mlb_apply_dt(mlb_ctx * c, double cfl, double global_max) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    launch_apply_dt(c->scal, c->max_bits, cfl, global_max, 1, c->stream);
+    c->launches++;
+    API_END(c)
+}
+int mlb_finish_step(mlb_ctx * c) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    API_END(c)
+}
+int mlb_owned_cells(mlb_ctx * c, uint32_t * n_owned, uint32_t * cells_out) {
+    API_BEGIN(c)
+    if (n_owned) *n_owned = c->prep.N_owned;
+    if (cells_out) std::memcpy(cells_out, c->prep.perm_cells.data(), (size_t)c->prep.N_owned * 4);
+    API_END(c)
+}
+
+// Recursive coordinate bisection on cell centroids (deterministic; ties broken by cell id).
+int mlb_partition(const mlb_mesh * mesh, int32_t n_parts, int32_t * part_out) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!mesh || !part_out || n_parts < 1) throw std::runtime_error("mlb_partition: bad argument");
+    HostMesh hm;
+    host_mesh_from_view(hm, *mesh);
+    std::vector<uint32_t> ids(hm.nc);
+    for (uint32_t i = 0; i < hm.nc; i++) ids[i] = i;
+    struct Job { size_t lo, hi; int32_t p0, np; };
+    std::vector<Job> stack{{0, hm.nc, 0, n_parts}};
+    while (!stack.empty()) {
+        Job j = stack.back(); stack.pop_back();
+        if (j.np == 1) { for (size_t i = j.lo; i < j.hi; i++) part_out[ids[i]] = j.p0; continue; }
+        double mn[2] = {1e300, 1e300}, mx[2] = {-1e300, -1e300};
+        for (size_t i = j.lo; i < j.hi; i++)
+            for (int d = 0; d < 2; d++) { const double x = hm.cell_xy[2 * (size_t)ids[i] + d]; mn[d] = std::min(mn[d], x); mx[d] = std::max(mx[d], x); }
+        const int d = (mx[1] - mn[1] > mx[0] - mn[0]) ? 1 : 0;
+        const int32_t npl = j.np / 2;
+        const size_t mid = j.lo + (size_t)((double)(j.hi - j.lo) * npl / j.np);
+        std::nth_element(ids.begin() + j.lo, ids.begin() + mid, ids.begin() + j.hi, [&](uint32_t a, uint32_t b) {
+            const double xa = hm.cell_xy[2 * (size_t)a + d], xb = hm.cell_xy[2 * (size_t)b + d];
+            return xa != xb ? xa < xb : a < b; });
+        stack.push_back({j.lo, mid, j.p0, npl});
+        stack.push_back({mid, j.hi, j.p0 + npl, j.np - npl});
+    }
+    API_END(none)
+}
+
+// ---- stateless kernels -------------------------------------------------------------------------------------------
+int mlb_riemann_flux(int32_t device, int32_t riemann, int32_t fp_mode, uint64_t n, const double * n_unit, const double * L,
+                     const double * R, double gamma, double * flux) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    require_device(device);
+    if (riemann < 0 || riemann > 2) throw std::runtime_error("Unknown Riemann solver type.");
+    const KernelTable * kt = fp_mode == MLB_FP_FAST ? kernels_fast() : kernels_strict();
+    double * dn = dev_alloc<double>(2 * n), * dl = dev_alloc<double>(5 * n), * dr = dev_alloc<double>(5 * n), * df = dev_alloc<double>(4 * n);
+    CUDA_OK(cudaMemcpy(dn, n_unit, 16 * n, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(dl, L, 40 * n, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(dr, R, 40 * n, cudaMemcpyHostToDevice));
+    kt->riemann_flux(riemann, n, dn, dl, dr, gamma, df, 0);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpy(flux, df, 32 * n, cudaMemcpyDeviceToHost));
+    cudaFree(dn); cudaFree(dl); cudaFree(dr); cudaFree(df);
+    API_END(none)
+}
+
+int mlb_compute_primitives(int32_t device, int32_t fp_mode, const mlb_physics * physics, uint64_t n, const double * U, double * prim,
+                           double * R_cp_cv) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!physics) throw std::runtime_error("physics is NULL");
+    const GasParams g = make_gas(*physics);
+    if (R_cp_cv) { R_cp_cv[0] = g.R; R_cp_cv[1] = g.cp; R_cp_cv[2] = g.cv; }
+    if (n) {
+        require_device(device);
+        const KernelTable * kt = fp_mode == MLB_FP_FAST ? kernels_fast() : kernels_strict();
+        double * du = dev_alloc<double>(4 * n), * dp = dev_alloc<double>(5 * n);
+        CUDA_OK(cudaMemcpy(du, U, 32 * n, cudaMemcpyHostToDevice));
+        kt->primitives(g, n, du, dp, 0);
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaMemcpy(prim, dp, 40 * n, cudaMemcpyDeviceToHost));
+        cudaFree(du); cudaFree(dp);
+    }
+    API_END(none)
+}
+
+// ---- host-only preprocessing plan (no device needed) ------------------------------------------------------------
+int mlb_plan_create(mlb_plan ** out, const mlb_mesh * mesh, const mlb_numerics * numerics, const mlb_bc * bcs, int32_t n_bcs,
+                    const int32_t * part, const mlb_parallel * parallel) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!out || !mesh || !numerics) throw std::runtime_error("mlb_plan_create: NULL argument");
+    *out = nullptr;
+    std::unique_ptr<mlb_plan> p(new mlb_plan());
+    HostMesh hm;
+    host_mesh_from_view(hm, *mesh);
+    p->nc_ref = hm.nc; p->nf_ref = hm.nf;
+    std::vector<std::string> zones;
+    for (int b = 0; b < n_bcs; b++) zones.push_back(bcs[b].zone_name ? bcs[b].zone_name : "");
+    PrepOptions opt;
+    opt.renumber = numerics->renumber;
+    opt.keep_ref_tables = numerics->recon == MLB_RECON_TENO && !part;
+    opt.part = part; opt.rank = parallel ? parallel->rank : 0; opt.n_ranks = parallel ? parallel->n_ranks : 1;
+    p->rank = opt.rank;
+    if (part) p->part.assign(part, part + hm.nc);
+    preprocess(hm, *numerics, zones, opt, p->prep);
+    *out = p.release();
+    API_END(none)
+}
+int mlb_plan_get(mlb_plan * p, const char * name, void * out, uint64_t * nbytes) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!p || !name || !nbytes) throw std::runtime_error("mlb_plan_get: NULL argument");
+    const std::string n = name;
+    const Prep & P = p->prep;
+    const TenoTables & T = P.teno;
+    auto host = [&](const void * q, size_t nb) { if (out) std::memcpy(out, q, nb); *nbytes = nb; };
+    if (n == "sizes") {
+        uint32_t s[12] = {P.N, P.N_owned, P.N_recon, P.NF, (uint32_t)P.n_slots, (uint32_t)P.Q, (uint32_t)T.K, (uint32_t)T.M, P.Npad,
+                          (uint32_t)T.S, (uint32_t)T.Mp, 0};
+        host(s, sizeof(s));
+    }
+    else if (n == "seconds") host(&P.seconds, 8);
+    else if (n == "perm_cells") host(P.perm_cells.data(), P.perm_cells.size() * 4);
+    else if (n == "perm_faces") host(P.perm_faces.data(), P.perm_faces.size() * 4);
+    else if (n == "slot_face") host(P.slot_face.data(), P.slot_face.size() * 4);
+    else if (n == "slot_nbr") host(P.slot_nbr.data(), P.slot_nbr.size() * 4);
+    else if (n == "rhs_order") host(P.rhs_order.data(), P.rhs_order.size());
+    else if (n == "st_ids") host(T.st_ids.data(), T.st_ids.size() * 4);
+    else if (n == "ghost_owner") {
+        std::vector<int32_t> o;
+        for (uint32_t i = P.N_owned; i < P.N; i++) o.push_back(p->part.empty() ? 0 : p->part[P.perm_cells[i]]);
+        host(o.data(), o.size() * 4);
+    }
+    else if (n == "teno:integral_psi_target") host(T.psi_bar.data(), T.psi_bar.size() * 8);
+    else if (n == "teno:oscillation_indicator") host(T.OI.data(), T.OI.size() * 8);
+    else if (n == "teno:poly_indices") host(T.pidx.data(), T.pidx.size());
+    else if (n == "teno:offsets_stencil_groups") host(T.ref_off_groups.data(), T.ref_off_groups.size() * 4);
+    else if (n == "teno:offsets_stencils") host(T.ref_off_stencils.data(), T.ref_off_stencils.size() * 4);
+    else if (n == "teno:stencils") host(T.ref_stencils.data(), T.ref_stencils.size() * 4);
+    else if (n == "teno:offsets_reconstruction_matrices") host(T.ref_off_mats.data(), T.ref_off_mats.size() * 4);
+    else if (n == "teno:reconstruction_matrices") host(T.ref_mats.data(), T.ref_mats.size() * 8);
+    else if (n == "teno:transformed_areas") host(T.ref_areas.data(), T.ref_areas.size() * 8);
+    else throw std::runtime_error("unknown plan array " + n);
+    API_END(none)
+}
+void mlb_plan_destroy(mlb_plan * p) { delete p; }
+
+// ---- host mesh generators ---------------------------------------------------------------------------------------
+int mlb_host_mesh_generate(mlb_host_mesh ** out, int32_t type, uint32_t nx, uint32_t ny, double Lx, double Ly) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!out) throw std::runtime_error("out is NULL");
+    std::unique_ptr<mlb_host_mesh> m(new mlb_host_mesh());
+    host_mesh_generate(m->m, type, nx, ny, Lx, Ly);
+    *out = m.release();
+    API_END(none)
+}
+int mlb_host_mesh_view(const mlb_host_mesh * hm, mlb_mesh * v) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!hm || !v) throw std::runtime_error("NULL argument");
+    HostMesh & m = const_cast<HostMesh &>(hm->m);
+    v->n_cells = m.nc; v->n_faces = m.nf; v->n_nodes = m.nn;
+    v->node_coords = m.node_xy.data();
+    v->offsets_nodes_of_cell = m.onc.data(); v->nodes_of_cell = m.noc.data();
+    v->offsets_faces_of_cell = m.ofc.data(); v->faces_of_cell = m.foc.data();
+    v->offsets_nodes_of_face = m.onf.data(); v->nodes_of_face = m.nof.data();
+    v->cells_of_face = m.cof.data();
+    v->cell_coords = m.cell_xy.data(); v->cell_volume = m.cell_vol.data(); v->face_area = m.face_area.data(); v->face_normals = m.face_n.data();
+    m.zone_views.clear();
+    for (auto & z : m.zones) m.zone_views.push_back({z.name.c_str(), (uint32_t)z.faces.size(), z.faces.data()});
+    v->n_zones = (uint32_t)m.zone_views.size();
+    v->zones = m.zone_views.data();
+    API_END(none)
+}
+void mlb_host_mesh_free(mlb_host_mesh * m) { delete m; }
+
+}  // extern "C"

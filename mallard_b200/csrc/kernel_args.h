@@ -1,0 +1,115 @@
+// Argument blocks passed BY VALUE to the kernels (they live in the constant bank: uniform, broadcast reads) and the
+// launcher table each floating-point mode exports.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "mlb_internal.h"
+
+namespace mlb {
+
+struct DevGeom {
+    uint32_t N, N_owned, N_recon, Npad, NF;
+    int32_t n_slots, Q;
+    const uint32_t * slot_face;   // [n_slots][Npad]
+    const int32_t * slot_nbr;     // [n_slots][Npad]
+    const uint8_t * slot_nslot;   // [n_slots][Npad]
+    const uint8_t * rhs_order;    // [Npad]
+    const uint8_t * nfc;          // [Npad]
+    const double * cell_vol;      // [Npad]
+    const double * cell_xy;       // [2][Npad]
+    const double * bnd_s;         // [Npad] 2*pow(V,1/2) (solver.cpp:662-666), computed on the host with libm pow
+    const double * face_nx, * face_ny, * face_area;   // [NFpad]
+    const double * slot_fx;       // [n_slots][4][Npad]
+};
+
+struct DevPhys {
+    GasParams gas;
+    int32_t riemann, n_bcs;
+    BcParams bcs[MAX_BCS];
+    double qf_x[MAX_Q], qf_w[MAX_Q];
+};
+
+// Device-resident scalars (one small block per context)
+enum { SC_DT = 0, SC_T = 1, SC_MAX_SR = 2, SC_CFL = 3, SC_COUNT = 8 };
+
+// Fused RK stage update, applied to the residual k of the stage just evaluated (numerics/time_integrator.cpp:57-163):
+//   mode 0: out = base + (dt*coef)*k
+//   mode 1: out = (c0*base + c1*in) + (dt*coef)*k                  (SSPRK3 stage 2: axpby then axpy)
+//   mode 2: out = ((base + (dt*cp0)*kp0) + (dt*cp1)*kp1 [+ ...]) + (dt*coef)*k   (final combination)
+//   mode 3: no update (bare residual evaluation)
+struct RkArgs {
+    int32_t mode, n_prev, last_stage, pad_;
+    const double * base;
+    double * out;
+    double * k_store;             // SoA [4][Npad] or null
+    const double * kprev[3];
+    double cprev[3];
+    double c0, c1, coef;
+    double * prim_out;            // SoA [5][Npad] written when last_stage (Solver::update_primitives)
+};
+
+struct StageArgs {
+    DevGeom g;
+    DevPhys ph;
+    RkArgs rk;
+    const double * Uin;           // SoA [4][Npad]: state the residual is evaluated on
+    const double * Fc;            // TENO: cell-centred face values [n_slots][Q][4][Npad]
+    const double * k_override;    // SoA [4][Npad] or null: state-independent residual (test hook)
+    double * scal;                // device scalars
+    unsigned long long * step_counter;
+    int32_t teno;
+};
+
+struct ReconArgs {
+    DevGeom g;
+    const double * Uin;
+    double * Fc;
+    const uint32_t * st_ids;
+    const double * st_area;
+    const double * st_mat;
+    int32_t order, K, M, Mp, S, basis, fixed_weights;
+    double qf_x[MAX_Q];
+    double psi_bar[15];
+    uint8_t pidx[2 * 15];
+    double OI[15 * 15];
+};
+
+struct CflArgs {
+    DevGeom g;
+    GasParams gas;
+    const double * U;             // SoA [4][Npad]
+    const double * prim;          // SoA [5][Npad]
+    double * sr_out;              // [Npad] spectral radius per cell (cfl_local before scaling)
+    double * scal;
+    long long * max_bits;         // running max (as ordered int) — reset by the finishing block
+    unsigned int * blocks_done;
+    double cfl;                   // <= 0: only the local max is produced (multi-GPU: host/all-reduce finishes)
+};
+
+struct KernelTable {
+    const char * name;
+    void (*stage)(const StageArgs &, cudaStream_t);
+    void (*recon)(const ReconArgs &, cudaStream_t);
+    void (*cfl)(const CflArgs &, cudaStream_t);
+    void (*riemann_flux)(int riemann, uint64_t n, const double * nunit, const double * L, const double * R, double gamma,
+                         double * flux, cudaStream_t);
+    void (*primitives)(const GasParams &, uint64_t n, const double * U_aos, double * P_aos, cudaStream_t);
+    void (*primitives_soa)(const GasParams &, uint32_t n, uint32_t npad, const double * U, double * P, cudaStream_t);
+    bool (*recon_supported)(int order, int Mp, int basis);
+};
+
+const KernelTable * kernels_strict();
+const KernelTable * kernels_fast();
+
+// layout helpers (mode independent, utils.cu)
+void launch_import_state(const double * aos, const uint32_t * perm, uint32_t n, uint32_t npad, int nv, double * soa, cudaStream_t);
+void launch_export_state(const double * soa, const uint32_t * perm, uint32_t n, uint32_t npad, int nv, double * aos, cudaStream_t);
+void launch_export_scaled(const double * v, const double * scal, int which, const uint32_t * perm, uint32_t n, double * out, cudaStream_t);
+void launch_gather(const double * soa, const uint32_t * idx, uint32_t n, uint32_t npad, double * buf, cudaStream_t);
+void launch_scatter(const double * buf, const uint32_t * idx, uint32_t n, uint32_t npad, double * soa, cudaStream_t);
+void launch_apply_dt(double * scal, long long * max_bits, double cfl, double global_max, int use_global, cudaStream_t);
+void launch_set_scalar(double * scal, int which, double v, cudaStream_t);
+void launch_export_faces(const double * Fc, const double * U, const uint32_t * slot_face, const uint32_t * perm_faces, uint32_t n,
+                         uint32_t npad, int n_slots, int Q, double * F_aos /* [nf_ref][Q][2][4] */, cudaStream_t);
+
+}  // namespace mlb

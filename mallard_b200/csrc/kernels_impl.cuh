@@ -1,0 +1,574 @@
+// Device kernels of the explicit residual path.  This file is compiled twice, into namespace `strict` with
+// -fmad=false (every product and sum rounds separately, exactly as the reference's x86-64 build does) and into
+// namespace `fast` with FMA contraction enabled.  Summation orders follow the reference in both.
+//
+//   flux_stage_kernel   cell-centric, atomic-free residual gather fused with the RK stage update
+//                       (replaces K1 zero, K2 FirstOrder, K4 interior flux, K5-K9 boundary fluxes, K10 divide-by-volume,
+//                        K11 BLAS-1 stage combinations and K12 update_primitives of SURVEY §2.1)
+//   teno_recon_kernel   TENO reconstruction (K3): one thread per (cell, conserved variable), warp = one 8-cell table tile
+//   cfl_kernel          spectral radius + max reduction + dt (K13, K14)
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+
+#include "kernel_args.h"
+
+#ifndef MLB_KNS
+#error "define MLB_KNS before including kernels_impl.cuh"
+#endif
+
+namespace mlb {
+namespace MLB_KNS {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Physics — Euler::compute_primitives_from_conservatives_impl (physics/physics.h:852-867)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cons_to_prim(const GasParams & g, const double * U, double * P) {
+    const double rho = U[0];
+    const double u0 = U[1] / rho, u1 = U[2] / rho;
+    const double E = U[3] / rho;
+    const double e = E - 0.5 * (u0 * u0 + u1 * u1);
+    const double p = fmax(g.p_min, fmin(g.p_max, (g.gamma - 1.0) * rho * e));   // :842-845
+    P[0] = u0; P[1] = u1; P[2] = p; P[3] = e / g.cv; P[4] = e + p / rho;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Star-state estimators and Riemann fluxes (numerics/riemann_solver.h:206-519)
+// ---------------------------------------------------------------------------------------------------------------
+struct Wn { double rho, un, p, gam; };
+
+__device__ __forceinline__ void star_pvrs(const Wn & l, const Wn & r, double & ps) {   // :206-240, averages branch
+    const double al = sqrt(l.gam * l.p / l.rho), ar = sqrt(r.gam * r.p / r.rho);
+    const double rho_avg = 0.5 * (l.rho + r.rho), a_avg = 0.5 * (al + ar);
+    ps = 0.5 * (l.p + r.p) + 0.5 * (l.un - r.un) * rho_avg * a_avg;
+}
+__device__ __noinline__ void star_trrs(const Wn & l, const Wn & r, double & ps) {      // :243-271
+    const double al = sqrt(l.gam * l.p / l.rho), ar = sqrt(r.gam * r.p / r.rho);
+    const double zl = (l.gam - 1.0) / (2.0 * l.gam), zr = (r.gam - 1.0) / (2.0 * r.gam);
+    const double Plr = pow((l.p / r.p), zl);
+    const double us = (Plr * l.un / al + r.un / ar + 2.0 * (1.0 - Plr) / (l.gam - 1.0)) / (Plr / al + 1.0 / ar);
+    ps = 0.5 * (l.p * pow((1.0 + (l.gam - 1.0) / (2.0 * al) * (l.un - us)), (1.0 / zl)) +
+                r.p * pow((1.0 + (r.gam - 1.0) / (2.0 * ar) * (us - r.un)), (1.0 / zr)));
+}
+__device__ __forceinline__ void star_tsrs(const Wn & l, const Wn & r, double & ps) {   // :274-306, p0 = PVRS guess
+    const double gl = (l.gam - 1.0) / (l.gam + 1.0), gr = (r.gam - 1.0) / (r.gam + 1.0);
+    const double Al = 2.0 / (l.gam + 1.0) / l.rho, Bl = gl * l.p;
+    const double Ar = 2.0 / (r.gam + 1.0) / r.rho, Br = gr * r.p;
+    const double p0 = fmax(0.0, ps);
+    const double ql = sqrt(Al / (p0 + Bl)), qr = sqrt(Ar / (p0 + Br));
+    ps = (ql * l.p + qr * r.p - (r.un - l.un)) / (ql + qr);
+}
+__device__ __forceinline__ double star_pressure(const Wn & l, const Wn & r) {           // ANRS :309-329
+    const double pmax = fmax(l.p, r.p), pmin = fmin(l.p, r.p);
+    const double qmax = pmax / pmin;
+    double ps;
+    star_pvrs(l, r, ps);
+    if (!((qmax < 2.0) && (pmin <= ps) && (ps <= pmax))) {
+        if (ps < pmin) star_trrs(l, r, ps); else star_tsrs(l, r, ps);
+    }
+    return ps;
+}
+
+// One face state as RiemannSolver::calc_flux receives it (riemann_solver.h:85-90)
+struct FaceState { double rho, u, v, p, h; };
+
+template <int RS>
+__device__ __forceinline__ void riemann_flux(double * F, double nx, double ny, const FaceState & L, const FaceState & R, double gam) {
+    const double uln = L.u * nx + L.v * ny, urn = R.u * nx + R.v * ny;
+    const double ulul = L.u * L.u + L.v * L.v, urur = R.u * R.u + R.v * R.v;
+    const double al = sqrt(gam * L.p / L.rho), ar = sqrt(gam * R.p / R.rho);
+    const double El = (L.h + 0.5 * ulul) * L.rho - L.p, Er = (R.h + 0.5 * urur) * R.rho - R.p;
+    const double Ul[4] = {L.rho, L.rho * L.u, L.rho * L.v, El}, Ur[4] = {R.rho, R.rho * R.u, R.rho * R.v, Er};
+    const double Fl[4] = {L.rho * uln, L.rho * L.u * uln + L.p * nx, L.rho * L.v * uln + L.p * ny, (El + L.p) * uln};
+    const double Fr[4] = {R.rho * urn, R.rho * R.u * urn + R.p * nx, R.rho * R.v * urn + R.p * ny, (Er + R.p) * urn};
+    if (RS == MLB_RIEMANN_RUSANOV) {   // :332-375
+        const double smax = fmax(fabs(uln) + al, fabs(urn) + ar);
+#pragma unroll
+        for (int i = 0; i < 4; i++) F[i] = 0.5 * (Fl[i] + Fr[i] + smax * (Ul[i] - Ur[i]));
+        return;
+    }
+    const Wn wl = {L.rho, uln, L.p, gam}, wr = {R.rho, urn, R.p, gam};
+    const double ps = star_pressure(wl, wr);
+    const double ql = (ps <= L.p) ? 1.0 : sqrt(1.0 + (gam + 1.0) / (2.0 * gam) * (ps / L.p - 1.0));
+    const double qr = (ps <= R.p) ? 1.0 : sqrt(1.0 + (gam + 1.0) / (2.0 * gam) * (ps / R.p - 1.0));
+    const double Sl = uln - al * ql, Sr = urn + ar * qr;
+    if (RS == MLB_RIEMANN_HLL) {       // :378-439
+        if (0.0 <= Sl) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) F[i] = Fl[i];
+        } else if (Sr <= 0.0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) F[i] = Fr[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) F[i] = (Sr * Fl[i] - Sl * Fr[i] + Sl * Sr * (Ur[i] - Ul[i])) / (Sr - Sl);
+        }
+        return;
+    }
+    // HLLC "variant 2" :442-519
+    const double Ss = (R.p - L.p + L.rho * uln * (Sl - uln) - R.rho * urn * (Sr - urn)) / (L.rho * (Sl - uln) - R.rho * (Sr - urn));
+    if (0.0 <= Sl) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) F[i] = Fl[i];
+    } else if (Sr <= 0.0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) F[i] = Fr[i];
+    } else {
+        const double D[4] = {0.0, nx, ny, Ss};
+        const double Plr = 0.5 * (L.p + R.p + L.rho * (Sl - uln) * (Ss - uln) + R.rho * (Sr - urn) * (Ss - urn));
+        if (Ss >= 0.0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) F[i] = (Ss * (Sl * Ul[i] - Fl[i]) + Sl * Plr * D[i]) / (Sl - Ss);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) F[i] = (Ss * (Sr * Ur[i] - Fr[i]) + Sr * Plr * D[i]) / (Sr - Ss);
+        }
+    }
+}
+
+// Ghost state of a boundary face from the interior face state (boundary/*.cpp calc_lr_states_impl)
+__device__ __forceinline__ void ghost_state(const BcParams & bc, const GasParams & g, double nx, double ny, const double * Ul,
+                                            const double * Pl, FaceState & R) {
+    switch (bc.type) {
+        case MLB_BC_SYMMETRY: {        // boundary_symmetry.cpp:39-69
+            const double un = Pl[0] * nx + Pl[1] * ny;
+            R.rho = Ul[0]; R.u = Pl[0] - 2.0 * un * nx; R.v = Pl[1] - 2.0 * un * ny; R.p = Pl[2]; R.h = Pl[4];
+            break;
+        }
+        case MLB_BC_UPT:               // boundary_upt.cpp:84-100
+            R.rho = bc.data[0]; R.u = bc.data[1]; R.v = bc.data[2]; R.p = bc.data[3]; R.h = bc.data[5];
+            break;
+        case MLB_BC_P_OUT: {           // boundary_p_out.cpp:58-100
+            const double umag = sqrt(Pl[0] * Pl[0] + Pl[1] * Pl[1]);
+            const double sos = sqrt(g.gamma * Pl[2] / Ul[0]);
+            const double p_out = (umag < sos) ? bc.data[0] : Pl[2];
+            const double rho_bc = p_out / (g.R * Pl[3]);
+            const double e_bc = g.cv * Pl[3];
+            R.rho = rho_bc; R.u = Pl[0]; R.v = Pl[1]; R.p = p_out; R.h = e_bc + p_out / rho_bc;
+            break;
+        }
+        default:                       // extrapolation: boundary_extrapolation.cpp:39-55
+            R.rho = Ul[0]; R.u = Pl[0]; R.v = Pl[1]; R.p = Pl[2]; R.h = Pl[4];
+            break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// RK stage combination (numerics/time_integrator.cpp:57-163; KokkosBlas axpy: y = a*x + y, axpby: y = a*x + b*y)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rk_update(const RkArgs & rk, const double * Uin, uint32_t Npad, uint32_t i, const double * k, double dt,
+                                          double * Unew) {
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        const size_t at = (size_t)v * Npad + i;
+        double y;
+        if (rk.mode == 0) {
+            y = (dt * rk.coef) * k[v] + rk.base[at];
+        } else if (rk.mode == 1) {
+            y = rk.c0 * rk.base[at] + rk.c1 * Uin[at];
+            y = (dt * rk.coef) * k[v] + y;
+        } else {
+            y = rk.base[at];
+            for (int j = 0; j < rk.n_prev; j++) y = (dt * rk.cprev[j]) * rk.kprev[j][at] + y;
+            y = (dt * rk.coef) * k[v] + y;
+        }
+        Unew[v] = y;
+        rk.out[at] = y;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Residual gather + RK update.  One thread per owned cell; every face flux is evaluated by both of its cells so that
+// no atomics are needed and each cell sums its faces in the reference's (Serial back-end) order.
+// ---------------------------------------------------------------------------------------------------------------
+template <int RS, bool TENO>
+__global__ void __launch_bounds__(128) flux_stage_kernel(const __grid_constant__ StageArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.g.N_owned) return;
+    const uint32_t Np = a.g.Npad;
+    const int Q = TENO ? a.g.Q : 1;
+    double k[4];
+    if (a.k_override) {
+#pragma unroll
+        for (int v = 0; v < 4; v++) k[v] = a.k_override[(size_t)v * Np + i];
+    } else {
+        double Us[4], Ps[5];
+        if (!TENO) {
+#pragma unroll
+            for (int v = 0; v < 4; v++) Us[v] = a.Uin[(size_t)v * Np + i];
+            cons_to_prim(a.ph.gas, Us, Ps);
+        }
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        const uint32_t order = a.g.rhs_order[i];
+        const int nf = a.g.nfc[i];
+        for (int jj = 0; jj < nf; jj++) {
+            const int s = (order >> (2 * jj)) & 3;
+            const int32_t nbr = a.g.slot_nbr[(size_t)s * Np + i];
+            if (nbr == INT32_MIN) continue;
+            const uint32_t fcode = a.g.slot_face[(size_t)s * Np + i];
+            const uint32_t f = fcode & 0x7FFFFFFFu, side = fcode >> 31;
+            const double nx = a.g.face_nx[f], ny = a.g.face_ny[f], area = a.g.face_area[f];
+            const int ns = TENO ? a.g.slot_nslot[(size_t)s * Np + i] : 0;
+            const BcParams * bc = nbr < 0 ? &a.ph.bcs[-nbr - 1] : nullptr;
+            double fsum[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int q = 0; q < Q; q++) {
+                double Uo[4], Po[5];   // this cell's side of the face
+                if (TENO) {
+#pragma unroll
+                    for (int v = 0; v < 4; v++) Uo[v] = a.Fc[((size_t)(s * Q + q) * 4 + v) * Np + i];
+                    cons_to_prim(a.ph.gas, Uo, Po);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < 4; v++) Uo[v] = Us[v];
+#pragma unroll
+                    for (int v = 0; v < 5; v++) Po[v] = Ps[v];
+                }
+                double ft[4];
+                const FaceState own = {Uo[0], Po[0], Po[1], Po[2], Po[4]};
+                if (nbr >= 0) {
+                    double Un[4], Pn[5];
+                    if (TENO) {
+#pragma unroll
+                        for (int v = 0; v < 4; v++) Un[v] = a.Fc[((size_t)(ns * Q + q) * 4 + v) * Np + nbr];
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < 4; v++) Un[v] = a.Uin[(size_t)v * Np + nbr];
+                    }
+                    cons_to_prim(a.ph.gas, Un, Pn);
+                    const FaceState oth = {Un[0], Pn[0], Pn[1], Pn[2], Pn[4]};
+                    if (side == 0) riemann_flux<RS>(ft, nx, ny, own, oth, a.ph.gas.gamma);
+                    else riemann_flux<RS>(ft, nx, ny, oth, own, a.ph.gas.gamma);
+                } else if (bc->type == MLB_BC_WALL_ADIABATIC) {   // boundary_wall_adiabatic.cpp:39-70
+                    ft[0] = 0.0; ft[1] = Po[2] * nx; ft[2] = Po[2] * ny; ft[3] = 0.0;
+                } else {
+                    FaceState gh;
+                    ghost_state(*bc, a.ph.gas, nx, ny, Uo, Po, gh);
+                    riemann_flux<RS>(ft, nx, ny, own, gh, a.ph.gas.gamma);
+                }
+                const double wq = a.ph.qf_w[q];
+#pragma unroll
+                for (int v = 0; v < 4; v++) fsum[v] += wq * ft[v];     // flux_functor.h:151
+            }
+            const double sgn_area = (side == 0) ? -area : area;         // flux_functor.h:156-161
+#pragma unroll
+            for (int v = 0; v < 4; v++) { fsum[v] *= 0.5; acc[v] += sgn_area * fsum[v]; }
+        }
+        const double vol = a.g.cell_vol[i];
+#pragma unroll
+        for (int v = 0; v < 4; v++) k[v] = acc[v] / vol;                 // DivideVolumeFunctor solver_rhs.cpp:18-42
+    }
+    if (a.rk.k_store) {
+#pragma unroll
+        for (int v = 0; v < 4; v++) a.rk.k_store[(size_t)v * Np + i] = k[v];
+    }
+    if (a.rk.mode == 3) return;
+    const double dt = a.scal[SC_DT];
+    double Unew[4];
+    rk_update(a.rk, a.Uin, Np, i, k, dt, Unew);
+    if (a.rk.last_stage) {
+        if (a.rk.prim_out) {   // Solver::update_primitives solver.cpp:533-578
+            double P[5];
+            cons_to_prim(a.ph.gas, Unew, P);
+#pragma unroll
+            for (int v = 0; v < 5; v++) a.rk.prim_out[(size_t)v * Np + i] = P[v];
+        }
+        if (i == 0) { a.scal[SC_T] = a.scal[SC_T] + dt; *a.step_counter += 1ull; }   // solver.cpp:529-530
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TENO reconstruction — TENOFunctor::operator() (numerics/face_reconstruction.cpp:866-1039).
+// Thread = (cell, conserved variable); the four variable-threads of a cell share every table address (broadcast) and
+// the eight cells of a warp read eight adjacent entries of the tile-interleaved tables (fully used 32 B sectors,
+// 128 B per double2 request).  Each thread performs the reference's sums in the reference's order.
+// ---------------------------------------------------------------------------------------------------------------
+template <int ORDER>
+__device__ __forceinline__ void legendre_values(double x, double * P) {   // basis.h:81-86, same expression shapes
+    P[0] = 1.0 * (1.0);
+    if (ORDER >= 1) P[1] = 1.0 * (1.0 * x);
+    if (ORDER >= 2) P[2] = 0.5 * (3.0 * x * x - 1.0);
+    if (ORDER >= 3) P[3] = 0.5 * (5.0 * x * x * x - 3.0 * x);
+    if (ORDER >= 4) P[4] = 0.125 * (35.0 * x * x * x * x - 30.0 * x * x + 3.0);
+}
+
+constexpr int RECON_THREADS = 128;
+
+// exponents of the k-th basis function in the reference's graded ordering (p,0),(p-1,1),...,(0,p)
+// (TENO::calc_polynomial_indices, face_reconstruction.cpp:182-215)
+__host__ __device__ constexpr int dof_ey(int k) { int p = 0; while (k > p) { k -= p + 1; p++; } return k; }
+__host__ __device__ constexpr int dof_ex(int k) { int p = 0; while (k > p) { k -= p + 1; p++; } return p - k; }
+
+template <int ORDER, int MP>
+__global__ void __launch_bounds__(RECON_THREADS) teno_recon_kernel(const __grid_constant__ ReconArgs a) {
+    constexpr int K = (ORDER + 1) * (ORDER + 2) / 2;
+    constexpr int MAXS = 1 + MAX_SLOTS;
+    extern __shared__ double dof_sm[];   // [S][K][RECON_THREADS]
+    const int tid = threadIdx.x;
+    const uint32_t cell = blockIdx.x * (RECON_THREADS / 4) + (tid >> 2);
+    const int var = tid & 3;
+    if (cell >= a.g.N_recon) return;
+    const uint32_t Np = a.g.Npad;
+    const size_t tile = cell / TILE;
+    const int lane = cell % TILE;
+    const int S = a.S;
+    const double * Uv = a.Uin + (size_t)var * Np;
+    const double u_self = Uv[cell];
+
+    double w[MAXS];
+    double area0 = 0.5;
+#pragma unroll 1
+    for (int s = 0; s < S; s++) {
+        const size_t sbase = (tile * S + s) * MP;
+        const uint32_t * ids = a.st_ids + sbase * TILE + lane;
+        if (ids[0] == NO_FACE) { w[s] = 0.0; continue; }               // empty stencil :896-899
+        const double * areas = a.st_area + sbase * TILE + lane;
+        double b[MP];
+#pragma unroll
+        for (int m = 0; m < MP; m++) b[m] = areas[m * TILE] * (Uv[ids[m * TILE]] - u_self);   // :903-910
+        if (s == 0) area0 = areas[0];
+        const double2 * mat = reinterpret_cast<const double2 *>(a.st_mat) + ((tile * S + s) * K * (MP / 2)) * TILE + lane;
+        double dof[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {                                   // a = A+ b, k-ascending sums :915-918
+            double sum = 0.0;
+#pragma unroll
+            for (int m2 = 0; m2 < MP / 2; m2++) {
+                const double2 c = mat[(k * (MP / 2) + m2) * TILE];
+                sum += c.x * b[2 * m2];
+                sum += c.y * b[2 * m2 + 1];
+            }
+            dof[k] = sum;
+            dof_sm[(s * K + k) * RECON_THREADS + tid] = sum;
+        }
+        double si = 0.0;                                                // SI = a . (OI a) :922-936
+        double oa[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double t = 0.0;
+#pragma unroll
+            for (int j = 0; j < K; j++) t += a.OI[k * K + j] * dof[j];
+            oa[k] = t;
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) si += dof[k] * oa[k];
+        const double x = si + 1.0e-12;                                  // 1/(SI+eps)^6 :940-944 (pow → 3 multiplications)
+        const double x2 = x * x, x3 = x2 * x;
+        w[s] = 1.0 / (x3 * x3);
+    }
+
+    // non-linear weights :948-981 (reference-faithful: the central weight stays raw in the ENO branch)
+    {
+        double sd = 0.0;
+        for (int s = 1; s < S; s++) sd += w[s];
+        if (w[0] / (sd + w[0]) > 1.0e-7) {
+            w[0] = 1.0;
+            for (int s = 1; s < S; s++) w[s] = 0.0;
+        } else {
+            for (int s = 1; s < S; s++) {
+                if (w[s] / sd > 1.0e-5) w[s] = (1.0 / K);
+                else if (a.fixed_weights) w[s] = 0.0;
+            }
+            sd = 0.0;
+            for (int s = 1; s < S; s++) sd += w[s];
+            for (int s = 1; s < S; s++) w[s] /= sd;
+            if (a.fixed_weights) w[0] = 0.0;
+        }
+    }
+
+    double cbar[K];                                                     // psi_bar_k / area_t[s][0] :1028-1029
+#pragma unroll
+    for (int k = 0; k < K; k++) cbar[k] = a.psi_bar[k] / area0;
+
+    const int nf = a.g.nfc[cell];
+    const int Q = a.g.Q;
+    for (int j = 0; j < nf; j++) {                                      // :985-1034
+        const double * fx = a.g.slot_fx + ((size_t)j * 4) * Np + cell;
+        const double x0 = fx[0], y0 = fx[Np], x1 = fx[2 * (size_t)Np], y1 = fx[3 * (size_t)Np];
+        for (int q = 0; q < Q; q++) {
+            const double tq = (a.qf_x[q] + 1.0) * 0.5;
+            const double xq = tq * (x1 - x0) + x0, yq = tq * (y1 - y0) + y0;
+            double Px[ORDER + 1], Py[ORDER + 1];
+            legendre_values<ORDER>(xq, Px);
+            legendre_values<ORDER>(yq, Py);
+            double out = u_self;
+#pragma unroll 1
+            for (int s = 0; s < S; s++) {
+                if (w[s] == 0.0) continue;
+#pragma unroll
+                for (int k = 0; k < K; k++)
+                    out += w[s] * dof_sm[(s * K + k) * RECON_THREADS + tid] * (Px[dof_ex(k)] * Py[dof_ey(k)] + cbar[k]);
+            }
+            a.Fc[((size_t)(j * Q + q) * 4 + var) * Np + cell] = out;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Spectral radius + max + dt — SpectralRadiusFunctor / Solver::calc_dt (solver/solver.cpp:580-742)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cfl_kernel(const __grid_constant__ CflArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t Np = a.g.Npad;
+    double sr = -1.0;
+    if (i < a.g.N_owned) {
+        double conv = 0.0, acou = 0.0;
+        const int nf = a.g.nfc[i];
+        const double rho_s = a.U[i], u_s = a.prim[i], v_s = a.prim[(size_t)Np + i], p_s = a.prim[2 * (size_t)Np + i];
+        const double sos_s = sqrt(a.gas.gamma * p_s / rho_s);
+        for (int j = 0; j < nf; j++) {
+            const uint32_t fcode = a.g.slot_face[(size_t)j * Np + i];
+            const uint32_t f = fcode & 0x7FFFFFFFu, side = fcode >> 31;
+            const double nx = a.g.face_nx[f], ny = a.g.face_ny[f];
+            const int32_t nbr = a.g.slot_nbr[(size_t)j * Np + i];
+            double sx, sy, sos_l, sos_r, ul, vl, ur, vr;
+            if (nbr < 0) {   // boundary "hack" :662-666 — l = r = this cell
+                sx = a.g.bnd_s[i]; sy = sx;
+                sos_l = sos_s; sos_r = sos_s; ul = u_s; vl = v_s; ur = u_s; vr = v_s;
+            } else {
+                const double rho_n = a.U[nbr], u_n = a.prim[nbr], v_n = a.prim[(size_t)Np + nbr], p_n = a.prim[2 * (size_t)Np + nbr];
+                const double sos_n = sqrt(a.gas.gamma * p_n / rho_n);
+                const double dxs = a.g.cell_xy[i], dys = a.g.cell_xy[(size_t)Np + i];
+                const double dxn = a.g.cell_xy[nbr], dyn = a.g.cell_xy[(size_t)Np + nbr];
+                if (side == 0) { sx = dxn - dxs; sy = dyn - dys; sos_l = sos_s; sos_r = sos_n; ul = u_s; vl = v_s; ur = u_n; vr = v_n; }
+                else           { sx = dxs - dxn; sy = dys - dyn; sos_l = sos_n; sos_r = sos_s; ul = u_n; vl = v_n; ur = u_s; vr = v_s; }
+            }
+            const double dx_n = fabs(sx * nx + sy * ny);
+            const double sos_f = 0.5 * (sos_l + sos_r);
+            const double uf = 0.5 * (ul + ur), vf = 0.5 * (vl + vr);
+            const double un = fabs(uf * nx + vf * ny);
+            conv += un / dx_n;
+            const double r = sos_f / dx_n;
+            acou += r * r;
+        }
+        const double geom = 3.0 / nf;
+        conv *= 1.37 * geom;
+        acou = 1.37 * sqrt(geom * acou);
+        sr = conv + acou;
+        a.sr_out[i] = sr;
+    }
+    // block max (NaN never wins: Kokkos::Max joins with `<`)
+    __shared__ double red[256];
+    red[threadIdx.x] = (sr == sr) ? sr : -1.0;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        atomicMax(a.max_bits, __double_as_longlong(red[0]));
+        __threadfence();
+        const unsigned int done = atomicAdd(a.blocks_done, 1u);
+        if (done == gridDim.x - 1) {   // last block: publish max and dt, reset the accumulators
+            const double mx = __longlong_as_double(atomicAdd((unsigned long long *)a.max_bits, 0ull));
+            a.scal[SC_MAX_SR] = mx;
+            if (a.cfl > 0.0) { a.scal[SC_DT] = a.cfl / mx; a.scal[SC_CFL] = a.cfl; }
+            *a.max_bits = __double_as_longlong(-1.0);
+            *a.blocks_done = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stateless kernels for the plug-in level known-answer tests
+// ---------------------------------------------------------------------------------------------------------------
+template <int RS>
+__global__ void riemann_kernel(uint64_t n, const double * nunit, const double * L, const double * R, double gamma, double * flux) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const FaceState l = {L[5 * i], L[5 * i + 1], L[5 * i + 2], L[5 * i + 3], L[5 * i + 4]};
+    const FaceState r = {R[5 * i], R[5 * i + 1], R[5 * i + 2], R[5 * i + 3], R[5 * i + 4]};
+    double F[4];
+    riemann_flux<RS>(F, nunit[2 * i], nunit[2 * i + 1], l, r, gamma);
+    for (int v = 0; v < 4; v++) flux[4 * i + v] = F[v];
+}
+
+__global__ void prims_aos_kernel(const GasParams g, uint64_t n, const double * U, double * P) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double u[4] = {U[4 * i], U[4 * i + 1], U[4 * i + 2], U[4 * i + 3]}, p[5];
+    cons_to_prim(g, u, p);
+    for (int v = 0; v < 5; v++) P[5 * i + v] = p[v];
+}
+
+__global__ void prims_soa_kernel(const GasParams g, uint32_t n, uint32_t npad, const double * U, double * P) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double u[4], p[5];
+    for (int v = 0; v < 4; v++) u[v] = U[(size_t)v * npad + i];
+    cons_to_prim(g, u, p);
+    for (int v = 0; v < 5; v++) P[(size_t)v * npad + i] = p[v];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Launchers
+// ---------------------------------------------------------------------------------------------------------------
+template <int RS>
+static void launch_stage_rs(const StageArgs & a, cudaStream_t st) {
+    const unsigned grid = (a.g.N_owned + 127u) / 128u;
+    if (grid == 0) return;
+    if (a.teno) flux_stage_kernel<RS, true><<<grid, 128, 0, st>>>(a);
+    else flux_stage_kernel<RS, false><<<grid, 128, 0, st>>>(a);
+}
+static void launch_stage(const StageArgs & a, cudaStream_t st) {
+    switch (a.ph.riemann) {
+        case MLB_RIEMANN_RUSANOV: launch_stage_rs<MLB_RIEMANN_RUSANOV>(a, st); break;
+        case MLB_RIEMANN_HLL: launch_stage_rs<MLB_RIEMANN_HLL>(a, st); break;
+        default: launch_stage_rs<MLB_RIEMANN_HLLC>(a, st); break;
+    }
+}
+
+template <int ORDER, int MP>
+static void launch_recon_t(const ReconArgs & a, cudaStream_t st) {
+    constexpr int K = (ORDER + 1) * (ORDER + 2) / 2;
+    const size_t smem = (size_t)a.S * K * RECON_THREADS * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(teno_recon_kernel<ORDER, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1 + MAX_SLOTS) * K * RECON_THREADS * sizeof(double)));
+        configured = true;
+    }
+    const unsigned cells_per_block = RECON_THREADS / 4;
+    const unsigned grid = (a.g.N_recon + cells_per_block - 1) / cells_per_block;
+    if (grid == 0) return;
+    teno_recon_kernel<ORDER, MP><<<grid, RECON_THREADS, smem, st>>>(a);
+}
+static bool recon_supported(int order, int Mp, int basis) {
+    if (basis != MLB_BASIS_LEGENDRE) return false;
+    return (order == 1 && Mp == 6) || (order == 2 && Mp == 12) || (order == 3 && Mp == 20) || (order == 4 && Mp == 30);
+}
+static void launch_recon(const ReconArgs & a, cudaStream_t st) {
+    if (a.order == 1 && a.Mp == 6) launch_recon_t<1, 6>(a, st);
+    else if (a.order == 2 && a.Mp == 12) launch_recon_t<2, 12>(a, st);
+    else if (a.order == 3 && a.Mp == 20) launch_recon_t<3, 20>(a, st);
+    else if (a.order == 4 && a.Mp == 30) launch_recon_t<4, 30>(a, st);
+}
+
+static void launch_cfl(const CflArgs & a, cudaStream_t st) {
+    const unsigned grid = (a.g.N_owned + 255u) / 256u;
+    if (grid == 0) return;
+    cfl_kernel<<<grid, 256, 0, st>>>(a);
+}
+
+static void launch_riemann(int riemann, uint64_t n, const double * nunit, const double * L, const double * R, double gamma,
+                           double * flux, cudaStream_t st) {
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (!grid) return;
+    if (riemann == MLB_RIEMANN_RUSANOV) riemann_kernel<MLB_RIEMANN_RUSANOV><<<grid, 128, 0, st>>>(n, nunit, L, R, gamma, flux);
+    else if (riemann == MLB_RIEMANN_HLL) riemann_kernel<MLB_RIEMANN_HLL><<<grid, 128, 0, st>>>(n, nunit, L, R, gamma, flux);
+    else riemann_kernel<MLB_RIEMANN_HLLC><<<grid, 128, 0, st>>>(n, nunit, L, R, gamma, flux);
+}
+static void launch_prims(const GasParams & g, uint64_t n, const double * U, double * P, cudaStream_t st) {
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (grid) prims_aos_kernel<<<grid, 128, 0, st>>>(g, n, U, P);
+}
+static void launch_prims_soa(const GasParams & g, uint32_t n, uint32_t npad, const double * U, double * P, cudaStream_t st) {
+    const unsigned grid = (n + 127u) / 128u;
+    if (grid) prims_soa_kernel<<<grid, 128, 0, st>>>(g, n, npad, U, P);
+}
+
+#define MLB_STR2(x) #x
+#define MLB_STR(x) MLB_STR2(x)
+static const KernelTable table = {MLB_STR(MLB_KNS), launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
+                                  launch_prims_soa, recon_supported};
+
+}  // namespace MLB_KNS
+}  // namespace mlb

@@ -1,0 +1,116 @@
+// Internal declarations shared by the host preprocessor, the kernels and the C-ABI layer.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/mallard_b200.h"
+
+namespace mlb {
+
+typedef std::vector<double> dvec;
+typedef std::vector<uint32_t> uvec;
+typedef std::vector<int32_t> ivec;
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host mesh in the reference's numbering (mesh/mesh.h:228-253)
+// ---------------------------------------------------------------------------------------------------------------
+struct HostZone { std::string name; uvec faces; };
+struct HostMesh {
+    uint32_t nc = 0, nf = 0, nn = 0;
+    dvec node_xy, cell_xy, cell_vol, face_area, face_n;
+    uvec noc, onc, foc, ofc, nof, onf;
+    ivec cof;
+    std::vector<HostZone> zones;
+    std::vector<mlb_zone> zone_views;   // for mlb_host_mesh_view
+    int nfc(uint32_t c) const { return (int)(ofc[c + 1] - ofc[c]); }
+    int nnc(uint32_t c) const { return (int)(onc[c + 1] - onc[c]); }
+    const HostZone * zone(const std::string & n) const { for (auto & z : zones) if (z.name == n) return &z; return nullptr; }
+};
+void host_mesh_generate(HostMesh & m, int type, uint32_t nx, uint32_t ny, double Lx, double Ly);
+void host_mesh_from_view(HostMesh & m, const mlb_mesh & v);
+void host_mesh_geometry(HostMesh & m);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gas constants (physics/physics.cpp:69-73)
+// ---------------------------------------------------------------------------------------------------------------
+struct GasParams { double gamma, p_min, p_max, R, cp, cv; };
+GasParams make_gas(const mlb_physics & p);
+
+// Boundary condition as the device sees it: type + data[6] (boundary_upt.cpp:38-73: rho,u,v,p,T,h ; p_out: p)
+struct BcParams { int32_t type; double data[6]; };
+constexpr int MAX_BCS = 16;
+constexpr int MAX_SLOTS = 4;    // faces per cell (triangles 3, quads 4)
+constexpr int MAX_Q = 7;        // Gauss-Legendre orders 1..7 (numerics/quadrature.cpp:23-151)
+constexpr int MAX_K = 55;       // (p+1)(p+2)/2 for p <= 9
+
+// ---------------------------------------------------------------------------------------------------------------
+// Preprocessor output (all in LIBRARY numbering; perm arrays map back to the reference)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t NO_FACE = 0xFFFFFFFFu;
+constexpr int TILE = 8;         // cells per interleaved TENO table tile (one warp = 8 cells x 4 variables)
+
+struct TenoTables {
+    int basis = 1, order = 0, K = 0, M = 0, Mp = 0, S = 0;   // Mp = M padded to even, S = stencil slots per cell (1 + max faces)
+    int nq_cell = 0;
+    std::vector<uint8_t> pidx;    // [K][2]
+    dvec qc_xy, qc_w;             // Dunavant cell quadrature
+    dvec psi_bar, OI;             // [K], [K][K]
+    // Tile-interleaved tables, n_tiles = ceil(N / TILE):
+    //   st_ids  [tile][S][Mp][TILE]      u32   library cell ids; empty stencil -> all NO_FACE
+    //   st_area [tile][S][Mp][TILE]      f64   transformed areas (0 padding)
+    //   st_mat  [tile][S][K][Mp/2][TILE][2] f64  pseudo-inverse rows, m-pairs interleaved across the tile's cells
+    uvec st_ids;
+    dvec st_area, st_mat;
+    // Reference-layout CSR copies (reference numbering) for parity checks (optional, small meshes only)
+    bool keep_ref = false;
+    uvec ref_off_groups, ref_off_stencils, ref_stencils, ref_off_mats;
+    dvec ref_mats, ref_areas;
+};
+
+struct Prep {
+    uint32_t N = 0;        // cells owned+ghost held by this context
+    uint32_t N_owned = 0;  // cells [0, N_owned) are updated here; [N_owned, N) are ghosts (multi-GPU)
+    uint32_t N_recon = 0;  // cells [0, N_recon) are reconstructed (owned + first ghost ring)
+    uint32_t Npad = 0;     // N rounded up to a multiple of 32
+    uint32_t NF = 0;       // real faces held (phantom faces dropped)
+    uint32_t NFpad = 0;
+    int n_slots = 0;       // max faces per cell
+    int Q = 1;
+    uvec perm_cells;       // library cell -> reference cell
+    uvec iperm_cells;      // reference cell -> library cell (NO_FACE if not held)
+    uvec perm_faces;       // library face -> reference face
+    // per cell, per face slot j (faces_of_cell order), SoA [n_slots][Npad]:
+    uvec slot_face;        // library face id | side << 31 ; NO_FACE if the cell has fewer faces
+    ivec slot_nbr;         // >= 0 neighbour library cell ; < 0 : -(bc index + 1) ; INT32_MIN = none / unassigned boundary
+    std::vector<uint8_t> slot_nslot;   // [n_slots][Npad] neighbour's slot index of the shared face (TENO gather)
+    std::vector<uint8_t> rhs_order;    // [Npad] 4 x 2 bit: slot visited i-th in the reference's accumulation order (Q16)
+    std::vector<uint8_t> n_faces_of_cell;   // [Npad]
+    dvec cell_vol;         // [Npad]
+    dvec cell_xy;          // [2][Npad]
+    dvec face_nx, face_ny, face_area;   // [NFpad] unit normal (common_math.h:101-106) and area
+    dvec slot_fx;          // TENO: [n_slots][4][Npad] face end points in the cell's reference coordinates
+    dvec qf_x, qf_w;       // face quadrature
+    TenoTables teno;
+    double seconds = 0.0;
+};
+
+struct PrepOptions {
+    int renumber = MLB_RENUMBER_RCM;
+    bool keep_ref_tables = false;
+    const int32_t * part = nullptr;   // partition vector (reference numbering) or null
+    int rank = 0, n_ranks = 1;
+};
+
+void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<std::string> & bc_zones,
+                const PrepOptions & opt, Prep & out);
+
+void gauss_legendre_rule(int order, dvec & x, dvec & w);
+void dunavant_rule(int order, dvec & xy, dvec & w);
+
+// RCM ordering of the cell dual graph (host). Returns library->reference permutation.
+void rcm_order(const HostMesh & m, const std::vector<uint32_t> & cells, uvec & order);
+
+}  // namespace mlb

@@ -1,0 +1,105 @@
+// Layout / bookkeeping kernels that do no floating-point arithmetic of the path (or a single IEEE operation), shared by
+// both floating-point modes: AoS(reference numbering) <-> SoA(library numbering) conversion, halo pack/unpack, dt.
+#include "kernel_args.h"
+
+namespace mlb {
+
+namespace {
+
+// soa[v][i] = aos[perm[i]][v]
+__global__ void import_kernel(const double * __restrict__ aos, const uint32_t * __restrict__ perm, uint32_t n, uint32_t npad, int nv,
+                              double * __restrict__ soa) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t src = (size_t)perm[i] * nv;
+    for (int v = 0; v < nv; v++) soa[(size_t)v * npad + i] = aos[src + v];
+}
+
+// aos[perm[i]][v] = soa[v][i]
+__global__ void export_kernel(const double * __restrict__ soa, const uint32_t * __restrict__ perm, uint32_t n, uint32_t npad, int nv,
+                              double * __restrict__ aos) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t dst = (size_t)perm[i] * nv;
+    for (int v = 0; v < nv; v++) aos[dst + v] = soa[(size_t)v * npad + i];
+}
+
+// out[perm[i]] = scal[which] * v[i]   — KokkosBlas::scal(cfl_local, dt, cfl_local), solver/solver.cpp:584
+__global__ void export_scaled_kernel(const double * __restrict__ v, const double * __restrict__ scal, int which,
+                                     const uint32_t * __restrict__ perm, uint32_t n, double * __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[perm[i]] = scal[which] * v[i];
+}
+
+// buf[k][v] = soa[v][idx[k]]  /  soa[v][idx[k]] = buf[k][v]   (halo pack / unpack, 4 conserved variables)
+__global__ void gather_kernel(const double * __restrict__ soa, const uint32_t * __restrict__ idx, uint32_t n, uint32_t npad,
+                              double * __restrict__ buf) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 4u * n) return;
+    const uint32_t k = t >> 2, v = t & 3u;
+    buf[t] = soa[(size_t)v * npad + idx[k]];
+}
+__global__ void scatter_kernel(const double * __restrict__ buf, const uint32_t * __restrict__ idx, uint32_t n, uint32_t npad,
+                               double * __restrict__ soa) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 4u * n) return;
+    const uint32_t k = t >> 2, v = t & 3u;
+    soa[(size_t)v * npad + idx[k]] = buf[t];
+}
+
+__global__ void apply_dt_kernel(double * scal, long long * max_bits, double cfl, double global_max, int use_global) {
+    const double mx = use_global ? global_max : scal[SC_MAX_SR];
+    scal[SC_MAX_SR] = mx;
+    scal[SC_DT] = cfl / mx;       // Solver::calc_dt solver/solver.cpp:583
+    scal[SC_CFL] = cfl;
+    (void)max_bits;
+}
+
+__global__ void set_scalar_kernel(double * scal, int which, double v) { scal[which] = v; }
+
+// Face values in the reference layout F[f_ref][q][side][v] from the cell-centred storage (or from U for first order)
+__global__ void export_faces_kernel(const double * __restrict__ Fc, const double * __restrict__ U, const uint32_t * __restrict__ slot_face,
+                                    const uint32_t * __restrict__ perm_faces, uint32_t n, uint32_t npad, int n_slots, int Q,
+                                    double * __restrict__ F) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int j = 0; j < n_slots; j++) {
+        const uint32_t fcode = slot_face[(size_t)j * npad + i];
+        if (fcode == NO_FACE) continue;
+        const uint32_t f = perm_faces[fcode & 0x7FFFFFFFu], side = fcode >> 31;
+        for (int q = 0; q < Q; q++)
+            for (int v = 0; v < 4; v++)
+                F[(((size_t)f * Q + q) * 2 + side) * 4 + v] = Fc ? Fc[((size_t)(j * Q + q) * 4 + v) * npad + i] : U[(size_t)v * npad + i];
+    }
+}
+
+inline unsigned blocks(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+void launch_import_state(const double * aos, const uint32_t * perm, uint32_t n, uint32_t npad, int nv, double * soa, cudaStream_t st) {
+    if (n) import_kernel<<<blocks(n, 256), 256, 0, st>>>(aos, perm, n, npad, nv, soa);
+}
+void launch_export_state(const double * soa, const uint32_t * perm, uint32_t n, uint32_t npad, int nv, double * aos, cudaStream_t st) {
+    if (n) export_kernel<<<blocks(n, 256), 256, 0, st>>>(soa, perm, n, npad, nv, aos);
+}
+void launch_export_scaled(const double * v, const double * scal, int which, const uint32_t * perm, uint32_t n, double * out, cudaStream_t st) {
+    if (n) export_scaled_kernel<<<blocks(n, 256), 256, 0, st>>>(v, scal, which, perm, n, out);
+}
+void launch_gather(const double * soa, const uint32_t * idx, uint32_t n, uint32_t npad, double * buf, cudaStream_t st) {
+    if (n) gather_kernel<<<blocks(4ull * n, 256), 256, 0, st>>>(soa, idx, n, npad, buf);
+}
+void launch_scatter(const double * buf, const uint32_t * idx, uint32_t n, uint32_t npad, double * soa, cudaStream_t st) {
+    if (n) scatter_kernel<<<blocks(4ull * n, 256), 256, 0, st>>>(buf, idx, n, npad, soa);
+}
+void launch_apply_dt(double * scal, long long * max_bits, double cfl, double global_max, int use_global, cudaStream_t st) {
+    apply_dt_kernel<<<1, 1, 0, st>>>(scal, max_bits, cfl, global_max, use_global);
+}
+void launch_set_scalar(double * scal, int which, double v, cudaStream_t st) { set_scalar_kernel<<<1, 1, 0, st>>>(scal, which, v); }
+void launch_export_faces(const double * Fc, const double * U, const uint32_t * slot_face, const uint32_t * perm_faces, uint32_t n,
+                         uint32_t npad, int n_slots, int Q, double * F_aos, cudaStream_t st) {
+    if (n) export_faces_kernel<<<blocks(n, 256), 256, 0, st>>>(Fc, U, slot_face, perm_faces, n, npad, n_slots, Q, F_aos);
+}
+
+}  // namespace mlb

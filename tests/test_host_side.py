@@ -1,0 +1,155 @@
+"""CPU-side tests of the product's host code: C-ABI surface, host mesh generators, mesh preprocessor.
+No compute entry point is called here (no GPU in this suite); parity of the host-built tables is checked against the
+oracle and against the fixtures generated from the real reference."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+import mallard_b200 as mb
+from mallard_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "mallard_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mlb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    L = C.CDLL(_abi.LIB_PATH)
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, missing
+    assert declared == set(_abi.SYMBOLS), declared ^ set(_abi.SYMBOLS)
+    assert b"sm_100a" in mb.lib().mlb_version()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the failure path needs a box without CUDA")
+    m = mb.Mesh.generate("cartesian", 4, 2, 1.0, 0.5)
+    with pytest.raises(mb.MallardError, match="no CPU fallback"):
+        mb.Solver(m, "FO", "HLLC", "SSPRK3", bcs=[dict(name=n, type="symmetry") for n in ("left", "right", "top", "bottom")])
+    with pytest.raises(mb.MallardError, match="no CPU fallback"):
+        mb.riemann_flux("HLLC", [(1.0, 0.0)], [[1, 0, 0, 1, 3.5]], [[1, 0, 0, 1, 3.5]])
+
+
+def test_interface_errors_mirror_reference():
+    m = mb.Mesh.generate("cartesian", 4, 2, 1.0, 0.5)
+    with pytest.raises(mb.MallardError, match="Unknown mesh type"):       # mesh/mesh.cpp:35-36
+        mb.Mesh.generate("file", 2, 2)
+    with pytest.raises(mb.MallardError, match="Unknown Riemann solver type"):   # solver/solver.cpp:130-132
+        mb.Solver(m, "FO", "Roe", "SSPRK3")
+    with pytest.raises(mb.MallardError, match="Unknown time integrator type"):  # default "LSSSPRK3" is not in the map
+        mb.Solver(m, "FO", "HLLC", "LSSSPRK3")
+    with pytest.raises(mb.MallardError, match="not found in mesh"):             # solver/solver.cpp:211-213
+        mb.Solver(m, "FO", "HLLC", "SSPRK3", bcs=[dict(name="inlet", type="symmetry")])
+    with pytest.raises(mb.MallardError, match="Missing p for boundary"):        # boundary_p_out.cpp:38-40
+        mb.Solver(m, "FO", "HLLC", "SSPRK3", bcs=[dict(name="right", type="p_out")])
+    tri = mb.Mesh.generate("cartesian", 8, 8)
+    with pytest.raises(mb.MallardError, match="only been implemented for triangular"):   # face_reconstruction.cpp:485-487
+        mb.Plan(tri, "TENO", order=2)
+
+
+@pytest.mark.parametrize("mtype,nx,ny,Lx,Ly", [("cartesian", 7, 5, 2.0, 1.0), ("cartesian", 1000, 1, 1.0, 0.001),
+                                               ("cartesian_tri", 6, 9, 1.0, 1.5), ("cartesian_tri", 1, 1, 1.0, 1.0),
+                                               ("wedge", 30, 10, 4.0, 1.5), ("wedge", 150, 50, 4.0, 1.5)])
+def test_host_mesh_generators_bit_exact(oracle_mod, mtype, nx, ny, Lx, Ly):
+    ref = oracle_mod.Mesh.generate(mtype, nx, ny, Lx, Ly)
+    got = mb.Mesh.generate(mtype, nx, ny, Lx, Ly)
+    for k, v in ref.arrays().items():
+        a = got.arrays[k].reshape(v.shape)
+        if k == "face_normals":
+            assert np.array_equal(np.isnan(a), np.isnan(v))
+            a, v = np.nan_to_num(a), np.nan_to_num(v)
+        assert np.array_equal(a, v), k
+    assert [n for n, _ in got.zones] == gu.ZONES
+    for n, f in got.zones:
+        assert np.array_equal(f, ref.zone(n)), n
+
+
+@pytest.mark.parametrize("name", [n for n in gu.names() if n.startswith("teno")])
+def test_teno_tables_bit_exact_against_reference(name):
+    meta, g = gu.load(name)
+    mm = meta["mesh"]
+    mesh = mb.Mesh.generate(mm["type"], mm["Nx"], mm["Ny"], mm["Lx"], mm["Ly"])
+    r = meta["recon"]
+    for renumber in ("rcm", "none"):
+        plan = mb.Plan(mesh, "TENO", basis=r["basis_type"], order=r["basis_order"], factor=r["max_stencil_size_factor"],
+                       bcs=meta["bcs"], renumber=renumber)
+        for k in g:
+            if k.startswith("teno:") and k not in ("teno:meta", "teno:quad_cell_points", "teno:quad_cell_weights", "teno:quad_face_points"):
+                got = plan.get(k)
+                assert np.array_equal(got.reshape(g[k].shape), g[k]), (k, renumber)
+
+
+def test_teno_tables_bit_exact_against_oracle_larger_mesh(oracle_mod):
+    om = oracle_mod.Mesh.generate("cartesian_tri", 14, 11, 1.0, 0.8)
+    osol = oracle_mod.Solver(om, "TENO", order=3, bcs=[dict(name=n, type="symmetry") for n in ("left", "right", "top", "bottom")])
+    mesh = mb.Mesh.generate("cartesian_tri", 14, 11, 1.0, 0.8)
+    plan = mb.Plan(mesh, "TENO", order=3)
+    for k in ("teno:offsets_stencil_groups", "teno:offsets_stencils", "teno:stencils", "teno:offsets_reconstruction_matrices",
+              "teno:reconstruction_matrices", "teno:transformed_areas", "teno:integral_psi_target", "teno:oscillation_indicator"):
+        assert np.array_equal(plan.get(k), osol.get(k).reshape(-1)), k
+
+
+@pytest.mark.parametrize("mtype,nx,ny", [("cartesian", 40, 30), ("cartesian_tri", 25, 20), ("wedge", 30, 10)])
+def test_renumbering_is_a_valid_deterministic_permutation(mtype, nx, ny):
+    mesh = mb.Mesh.generate(mtype, nx, ny, 2.0, 1.0)
+    p1 = mb.Plan(mesh, "FO", renumber="rcm")
+    p2 = mb.Plan(mesh, "FO", renumber="rcm")
+    perm = p1.get("perm_cells")
+    assert np.array_equal(perm, p2.get("perm_cells"))
+    assert np.array_equal(np.sort(perm), np.arange(mesh.n_cells))
+    # faces: every real face exactly once, ordered by owner (lower library cell id)
+    pf = p1.get("perm_faces")
+    real = gu.real_faces(mesh.arrays["cells_of_face"], mesh.arrays["nodes_of_face"])
+    assert np.array_equal(np.sort(pf), np.nonzero(real)[0])
+    inv = np.empty(mesh.n_cells, dtype=np.int64); inv[perm] = np.arange(mesh.n_cells)
+    cof = mesh.arrays["cells_of_face"][pf]
+    a = inv[cof[:, 0]]; b = np.where(cof[:, 1] >= 0, inv[np.maximum(cof[:, 1], 0)], np.iinfo(np.int64).max)
+    owner = np.minimum(a, b)
+    assert np.all(np.diff(owner) >= 0)
+    # RCM does not blow up the bandwidth of the dual graph compared with the generator's natural order
+    inter = cof[:, 1] >= 0
+    bw_rcm = np.abs(a[inter] - b[inter]).max()
+    bw_nat = np.abs(cof[inter, 0] - cof[inter, 1]).max()
+    assert bw_rcm <= 2 * bw_nat + 2
+    ident = mb.Plan(mesh, "FO", renumber="none").get("perm_cells")
+    assert np.array_equal(ident, np.arange(mesh.n_cells))
+
+
+def test_rhs_accumulation_order_matches_reference_zone_order():
+    """Per cell, slots must be visited interior-zone order first, then boundaries in input order."""
+    mesh = mb.Mesh.generate("cartesian", 6, 4, 1.0, 1.0)
+    bcs = [dict(name=n, type="symmetry") for n in ("bottom", "left", "top", "right")]   # deliberately not the zone order
+    plan = mb.Plan(mesh, "FO", bcs=bcs, renumber="rcm")
+    perm, pf = plan.get("perm_cells"), plan.get("perm_faces")
+    sf = plan.get("slot_face").reshape(plan.n_slots, plan.Npad)
+    order = plan.get("rhs_order")
+    key = {}
+    for k, f in enumerate(mesh.get_face_zone("interior")):
+        key[int(f)] = (0, k)
+    for b, bc in enumerate(bcs):
+        for k, f in enumerate(mesh.get_face_zone(bc["name"])):
+            key[int(f)] = (1 + b, k)
+    for i in range(plan.N):
+        visited = [int(pf[sf[(order[i] >> (2 * j)) & 3, i] & 0x7FFFFFFF]) for j in range(4)]
+        keys = [key[f] for f in visited]
+        assert keys == sorted(keys), (i, visited)
+        foc = mesh.arrays["faces_of_cell"][4 * perm[i]:4 * perm[i] + 4]
+        assert sorted(visited) == sorted(int(x) for x in foc)
+
+
+def test_partition_is_balanced_and_deterministic():
+    mesh = mb.Mesh.generate("cartesian_tri", 20, 16, 2.0, 1.0)
+    for n in (2, 3, 4, 8):
+        p1, p2 = mb.partition(mesh, n), mb.partition(mesh, n)
+        assert np.array_equal(p1, p2)
+        counts = np.bincount(p1, minlength=n)
+        assert counts.min() > 0 and counts.max() - counts.min() <= n
+    assert np.all(mb.partition(mesh, 1) == 0)
