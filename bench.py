@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""bench.py — cell-updates/s per RK stage of the explicit residual hot path (BASELINE.json metric).
+
+Workload (N=1): BASELINE.json configs[1] = examples/riemann_2d: cartesian_tri 1024x1024 (2 097 152 triangles), four-quadrant
+Riemann initial condition, TENO (legendre, p=3) + HLLC + SSPRK3, cfl = 0.1.  A "step" is one full time step of
+Solver::run's loop: calc_dt + the three RK stages (each: TENO reconstruction kernel, residual/flux/RK-update kernel).
+    value = n_cells * n_stages * K / t        [cell-updates/s per RK stage], state and tables resident in HBM.
+    e2e   = same through the take_step seam with HOST buffers: per step H2D of U from pinned memory, the step, D2H of U.
+For N>1 (torchrun, one rank per GPU) every rank owns one 1024x1024-quad block of a (1024*N)x1024 mesh (weak scaling); the
+per-stage halo exchange of ghost-cell states goes over NCCL.
+
+`--impl reference` times the UNMODIFIED reference (oracle/_ref, Kokkos OpenMP, FP64) on the host cores on a bounded sample
+of the same workload (same numerics, smaller mesh) — or the oracle port if the reference binary is absent.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import numpy as np  # noqa: E402
+
+N_STAGES = 3
+ALG_BYTES_STAGE = 7592.0    # TENO p=3 tri, whole stage (reference layout)
+ALG_BYTES_RECON = 7472.0    # of which the reconstruction kernel: A+ 6400, areas 640, ids 320, offsets 20, state 32, geometry 60
+SYM4 = [dict(name=n, type="symmetry") for n in ("left", "right", "top", "bottom")]
+
+
+def riemann2d_state(xy, gas_R=None):
+    """examples/riemann_2d/input.toml:17-48 evaluated at the cell centroids (Solver::init_solution_analytical)."""
+    x, y = xy[:, 0], xy[:, 1]
+    l, r, b, t = (x < 0.8).astype(float), (x >= 0.8).astype(float), (y < 0.8).astype(float), (y >= 0.8).astype(float)
+    rho = 1.5 * r * t + 0.532258064516129 * l * t + 0.137992831541219 * l * b + 0.532258064516129 * r * b
+    u = 0.0 * r * t + 1.206045378311055 * l * t + 1.206045378311055 * l * b + 0.0 * r * b
+    v = 0.0 * r * t + 0.0 * l * t + 1.206045378311055 * l * b + 1.206045378311055 * r * b
+    p = 1.5 * r * t + 0.3 * l * t + 0.029032258064516 * l * b + 0.3 * r * b
+    gamma = 1.4
+    R = 101325.0 / (298.15 * 1.225)
+    cp = R * gamma / (gamma - 1.0)
+    cv = cp / gamma
+    T = p / (rho * R)
+    e = cv * T
+    E = e + 0.5 * (u * u + v * v)
+    U = np.stack([rho, rho * u, rho * v, rho * E], 1)
+    P = np.stack([u, v, p, T, e + p / rho], 1)
+    return U, P
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (recipe of B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def write_ref_toml(path, nx, ny, n_steps):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import make_golden
+    case = dict(mesh=dict(type="cartesian_tri", Nx=nx, Ny=ny, Lx=1.0, Ly=1.0), ic=make_golden.RIEMANN2D_IC, bcs=SYM4, cfl=0.1,
+                riemann="HLLC", integrator="SSPRK3", recon=make_golden.TENO3, n_steps=n_steps)
+    make_golden.write_toml(case, path, n_steps)
+
+
+def reference_cpu(n_steps, n_warmup, nx=96, ny=96):
+    """Times the reference's own CPU implementation on a bounded sample.  Returns (value, dict)."""
+    harness = os.path.join(ROOT, "oracle", "_ref", "bin", "ref_harness")
+    cores = host_cores()
+    nc = 2 * nx * ny
+    sample = "riemann_2d numerics (TENO p=3 legendre, HLLC, SSPRK3, cfl 0.1) on cartesian_tri %dx%d = %d cells, %d steps" % (nx, ny, nc, n_steps)
+    if os.path.exists(harness):
+        with tempfile.TemporaryDirectory() as td:
+            toml = os.path.join(td, "input.toml")
+            write_ref_toml(toml, nx, ny, n_steps + n_warmup)
+            env = dict(os.environ, OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="spread", OMP_PLACES="cores")
+            out = subprocess.run([harness, "time", toml, str(n_steps), str(n_warmup)], env=env, capture_output=True, text=True, check=True)
+            line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+            r = json.loads(line)
+        return r["cell_updates_per_s_per_stage"], dict(kind="reference", cores=int(r["threads"]), sample=sample + " (reference Kokkos OpenMP build, oracle/_ref)",
+                                                        ms_per_step=1e3 * r["seconds"] / n_steps, init_seconds=r["init_seconds"])
+    import oracle
+    oracle.build()
+    om = oracle.Mesh.generate("cartesian_tri", nx, ny, 1.0, 1.0)
+    so = oracle.Solver(om, "TENO", "HLLC", "SSPRK3", order=3, bcs=SYM4)
+    U, P = riemann2d_state(om.get("cell_coords"))
+    so.set_state(U, P)
+    for _ in range(n_warmup):
+        so.take_step(so.calc_dt(0.1) if np.isfinite(so.get("U")).all() else 1e-6)
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        try:
+            dt = so.calc_dt(0.1)
+        except Exception:
+            dt = 1e-6
+        so.take_step(dt if dt > 0 else 1e-6)
+    sec = time.perf_counter() - t0
+    return nc * N_STAGES * n_steps / sec, dict(kind="port", cores=1, sample=sample + " (oracle port, scalar)", ms_per_step=1e3 * sec / n_steps)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=1024)
+    ap.add_argument("--ny", type=int, default=1024)
+    ap.add_argument("--fp", default="strict", choices=["strict", "fast"])
+    ap.add_argument("--recon", default="TENO", choices=["TENO", "FO"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = "examples/riemann_2d: cartesian_tri %dx%d, TENO(legendre,p=3)+HLLC+SSPRK3, cfl=0.1, four-quadrant IC" % (a.nx, a.ny)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(a.steps, 10))
+        value, info = reference_cpu(steps, max(1, min(a.warmup, 2)))
+        line = {"impl": "reference", "metric": "cell-updates/s per RK stage", "value": value, "unit": "cell-updates/s", "n_gpus": a.gpus,
+                "steps": steps, "warmup": max(1, min(a.warmup, 2)), "ms_per_step": info["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload, "sample": info["sample"]},
+                "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+                "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import mallard_b200 as mb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    if world > 1:
+        import bench_multi
+        return bench_multi.run(a, rank, world, local_rank, workload)
+
+    torch.cuda.set_device(0)
+    t_setup = time.perf_counter()
+    mesh = mb.Mesh.generate("cartesian_tri", a.nx, a.ny, 1.0, 1.0)
+    nc = mesh.n_cells
+    U0, P0 = riemann2d_state(mesh.arrays["cell_coords"])
+    s = mb.Solver(mesh, a.recon, "HLLC", "SSPRK3", order=3, bcs=SYM4, fp_mode=a.fp, keep_stage_rhs=False)
+    stats = s.get("stats")
+    setup_s = time.perf_counter() - t_setup
+    s.set_state(U0, P0)
+
+    # ---- device-resident timing (the state is reset before every timed region: reference-faithful TENO spreads NaN from
+    #      the initial discontinuities by about one stencil width per stage, exactly as the reference does)
+    s.run(a.warmup, cfl=0.1)
+    launches0 = s.launch_count
+    clocks = ClockSampler(0)
+    clocks.start()
+    s.synchronize()
+    s.event_record(0)
+    s.run(a.steps, cfl=0.1)
+    s.event_record(1)
+    ms = s.event_elapsed_ms(0, 1)
+    clk = clocks.stop()
+    launches = s.launch_count - launches0
+    value = nc * N_STAGES * a.steps / (ms * 1e-3)
+
+    # ---- per-kernel device time over the same region (CUDA events on the library's stream) for the roofline
+    s.set_state(U0, P0)
+    s.run(a.warmup, cfl=0.1)
+    s.profile(True)
+    s.run(a.steps, cfl=0.1)
+    prof = s.profile_read()
+    s.profile(False)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    top = max(prof, key=lambda k: prof[k][0]) if prof else None
+    roof = None
+    kernels = {k: {"ms_total": v[0], "launches": int(v[1]), "ms_per_launch": v[0] / max(1, v[1])} for k, v in prof.items()}
+    if top:
+        per_launch_ms = prof[top][0] / prof[top][1]
+        alg = {"teno_recon": ALG_BYTES_RECON, "flux_stage_teno": ALG_BYTES_STAGE - ALG_BYTES_RECON, "flux_stage_fo": 152.0, "cfl": 200.0}.get(top, ALG_BYTES_STAGE)
+        achieved = alg * nc / (per_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_cell": alg, "share_of_step": prof[top][0] / sum(v[0] for v in prof.values())}
+        stage_ms = sum(prof[k][0] for k in prof if k != "cfl") / (a.steps * N_STAGES)
+        roof["stage_achieved"] = ALG_BYTES_STAGE * nc / (stage_ms * 1e-3) / 1e9
+        roof["stage_frac"] = roof["stage_achieved"] / peak
+
+    # ---- end to end through the take_step seam with host buffers (pinned): H2D U, calc_dt + step, D2H U every step
+    e2e = None
+    if not a.no_e2e:
+        pin = torch.empty((nc, 4), dtype=torch.float64, pin_memory=True)
+        Uh = pin.numpy()
+        Uh[:] = U0
+        k_e2e = max(3, min(a.steps, 10))
+        for _ in range(3):
+            s.take_step_host(Uh, cfl=0.1)
+        Uh[:] = U0
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            s.take_step_host(Uh, cfl=0.1)
+        sec = time.perf_counter() - t0
+        e2e = {"value": nc * N_STAGES * k_e2e / sec, "unit": "cell-updates/s", "h2d_bytes_per_step": nc * 32, "d2h_bytes_per_step": nc * 32 + 64,
+               "steps": k_e2e, "ms_per_step": 1e3 * sec / k_e2e, "api": "mlb_take_step_host (C ABI; host buffers in reference layout)"}
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        try:
+            v, info = reference_cpu(3, 1)
+            cpu = {"value": v, "unit": "cell-updates/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
+        except Exception as ex:   # the baseline is reported, never required for the GPU number
+            cpu = {"value": None, "unit": "cell-updates/s", "cores": host_cores(), "kind": "unavailable", "sample": str(ex)[:200]}
+
+    line = {"metric": "cell-updates/s per RK stage", "value": value, "unit": "cell-updates/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "n_cells": nc, "fp_mode": a.fp, "recon": a.recon, "l2": "inputs larger than L2 (TENO tables %.1f GB per stage)" % (stats[2] / 1e9),
+                       "device_bytes": stats[2], "preprocess_seconds": stats[1], "setup_seconds": setup_s,
+                       "note": "reference-faithful TENO: like the reference, the state turns non-finite inside step 1 (SURVEY 0.2); cost is data-independent"},
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "kernels": kernels}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

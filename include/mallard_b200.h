@@ -86,7 +86,8 @@ typedef struct {
     int32_t quadrature_order_face;   /* Gauss-Legendre order, 0 = reference default (p+1)/2 */
     int32_t fp_mode;                 /* MLB_FP_* */
     int32_t renumber;                /* MLB_RENUMBER_* */
-    int32_t teno_fixed;              /* 0 = reference-faithful weights; 1 = normalised ("N2") */
+    int32_t teno_fixed;              /* 0 = reference-faithful TENO (it turns non-finite within a step, as the
+                                        reference does); 1 = normalised weights + mean-free basis (new, no oracle) */
     int32_t keep_stage_rhs;          /* 1 = keep every stage residual for mlb_get_array("rhsN") */
 } mlb_numerics;
 

@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(RECON_THREADS) teno_recon_kernel(const __grid_
 
     double cbar[K];                                                     // psi_bar_k / area_t[s][0] :1028-1029
 #pragma unroll
-    for (int k = 0; k < K; k++) cbar[k] = a.psi_bar[k] / area0;
+    for (int k = 0; k < K; k++) cbar[k] = a.fixed_weights ? -a.psi_bar[k] : a.psi_bar[k] / area0;   // fixed: mean-free basis
 
     const int nf = a.g.nfc[cell];
     const int Q = a.g.Q;

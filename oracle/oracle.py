@@ -52,6 +52,7 @@ def lib():
         L.orc_solver_add_bc.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p]
         L.orc_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_set_rhs_override.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_set_teno_fixed.argtypes = [C.c_void_p, C.c_int]
         L.orc_calc_face_values.argtypes = [C.c_void_p]
         L.orc_calc_rhs.argtypes = [C.c_void_p]
         L.orc_calc_dt.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
@@ -154,7 +155,7 @@ class Solver:
     """Mirror of the reference Solver's hot-path surface (src/solver/solver.h:47-108)."""
 
     def __init__(self, mesh, recon="FO", riemann="HLLC", integrator="SSPRK3", gas=None, basis="legendre", order=3,
-                 factor=2.0, quad_cell_order=0, quad_face_order=0, bcs=()):
+                 factor=2.0, quad_cell_order=0, quad_face_order=0, bcs=(), teno_fixed=False):
         self.mesh = mesh
         g = gas6(gas)
         self.h = lib().orc_solver_create(mesh.h, RECON[recon], RIEMANN[riemann], INTEGRATOR[integrator], _ptr(g),
@@ -163,6 +164,8 @@ class Solver:
             raise RuntimeError(lib().orc_last_error().decode())
         for bc in bcs:
             self.add_bc(**bc)
+        if teno_fixed:
+            lib().orc_set_teno_fixed(self.h, 1)
 
     def add_bc(self, name, type, u=(0.0, 0.0), p=0.0, T=0.0):
         data = np.zeros(4)

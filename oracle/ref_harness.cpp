@@ -267,10 +267,13 @@ int main(int argc, char ** argv) {
             init_with_mesh(s, argv[2], nullptr);
             auto t1 = std::chrono::steady_clock::now();
             int n = atoi(argv[3]); int nw = argc > 4 ? atoi(argv[4]) : 1;
-            for (int i = 0; i < nw; ++i) { s.calc_dt(); s.take_step(); }
+            // Solver::calc_dt throws "dt negative" once every cell is NaN (reference-faithful TENO does that on small
+            // meshes); for timing the work is the same, so keep stepping.
+            auto safe_dt = [&]() { try { s.calc_dt(); } catch (const std::exception &) {} };
+            for (int i = 0; i < nw; ++i) { safe_dt(); s.take_step(); }
             Kokkos::fence();
             auto t2 = std::chrono::steady_clock::now();
-            for (int i = 0; i < n; ++i) { s.calc_dt(); s.take_step(); }   // Solver::run loop minus checks/output
+            for (int i = 0; i < n; ++i) { safe_dt(); s.take_step(); }   // Solver::run loop minus checks/output
             Kokkos::fence();
             auto t3 = std::chrono::steady_clock::now();
             std::cout.rdbuf(old);

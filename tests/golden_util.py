@@ -62,3 +62,22 @@ def rel_err(a, b):
         return 0.0
     scale = np.maximum(np.abs(b[fb]), 1e-300)
     return float(np.max(np.abs(a[fa] - b[fb]) / scale))
+
+
+def field_err(a, b):
+    """Error relative to the FIELD scale: max over variables (last axis) of max|a-b| / max|b|.  Non-finite patterns must
+    coincide (NaN with NaN, +-Inf with the same Inf).  This is the metric for FMA-contracted (FAST) results: entries that
+    are exact zeros or heavy cancellations in the reference have no meaningful element-wise relative error."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    if a.shape != b.shape:
+        return np.inf
+    fa, fb = np.isfinite(a), np.isfinite(b)
+    if not np.array_equal(fa, fb) or not np.array_equal(np.isnan(a), np.isnan(b)):
+        return np.inf
+    if not np.array_equal(a[~fa & ~np.isnan(a)], b[~fb & ~np.isnan(b)]):
+        return np.inf
+    a2 = np.where(fa, a, 0.0).reshape(-1, a.shape[-1]) if a.ndim > 1 else np.where(fa, a, 0.0).reshape(-1, 1)
+    b2 = np.where(fb, b, 0.0).reshape(-1, b.shape[-1]) if b.ndim > 1 else np.where(fb, b, 0.0).reshape(-1, 1)
+    col = np.abs(b2).max(axis=0)
+    scale = np.maximum(np.maximum(col, 1e-6 * col.max()), 1e-300)   # an identically-zero component is measured against the others
+    return float(np.max(np.abs(a2 - b2).max(axis=0) / scale))
