@@ -150,7 +150,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=1024)
     ap.add_argument("--ny", type=int, default=1024)
-    ap.add_argument("--fp", default="strict", choices=["strict", "fast"])
+    ap.add_argument("--fp", default="fast", choices=["strict", "fast"])
     ap.add_argument("--recon", default="TENO", choices=["TENO", "FO"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -226,7 +226,8 @@ def main():
     kernels = {k: {"ms_total": v[0], "launches": int(v[1]), "ms_per_launch": v[0] / max(1, v[1])} for k, v in prof.items()}
     if top:
         per_launch_ms = prof[top][0] / prof[top][1]
-        alg = {"teno_recon": ALG_BYTES_RECON, "flux_stage_teno": ALG_BYTES_STAGE - ALG_BYTES_RECON, "flux_stage_fo": 152.0, "cfl": 200.0}.get(top, ALG_BYTES_STAGE)
+        alg = {"teno_recon": ALG_BYTES_RECON, "teno_stream": ALG_BYTES_RECON, "flux_stage_teno": ALG_BYTES_STAGE - ALG_BYTES_RECON, "flux_stage_fo": 152.0,
+               "cfl": 200.0}.get(top, ALG_BYTES_STAGE)
         achieved = alg * nc / (per_launch_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_cell": alg, "share_of_step": prof[top][0] / sum(v[0] for v in prof.values())}

@@ -194,8 +194,15 @@ int mlb_halo_unpack(mlb_ctx *ctx, int32_t stage);   /* async on the compute stre
 /* split-phase stepping for callers that own the communicator: stage s of the current step, run after unpack */
 int mlb_n_stages(const mlb_ctx *ctx);
 int mlb_stage(mlb_ctx *ctx, int32_t stage);
-int mlb_local_max_spectral_radius(mlb_ctx *ctx, double *max_out);   /* rank-local part of calc_dt */
+int mlb_local_max_spectral_radius(mlb_ctx *ctx, double *max_out);   /* rank-local part of calc_dt; max_out == NULL: async */
 int mlb_apply_dt(mlb_ctx *ctx, double cfl, double global_max);      /* dt = cfl/max ; cfl_local *= dt */
+/* device-resident variant for communicators that reduce in place (ncclAllReduce(max) on mlb_scalars_device() + 2):
+ * the scalar block holds doubles { dt, t, max spectral radius, cfl, ... }; no host round trip per step */
+void *mlb_scalars_device(mlb_ctx *ctx);
+int mlb_apply_dt_device(mlb_ctx *ctx, double cfl);
+/* owned cells only, host buffers [n_owned][4] in the order of mlb_owned_cells (what a rank-local driver holds) */
+int mlb_set_owned(mlb_ctx *ctx, const double *U_owned);
+int mlb_get_owned(mlb_ctx *ctx, double *U_owned);
 int mlb_finish_step(mlb_ctx *ctx);                                  /* update_primitives ; t += dt ; step++ */
 int mlb_owned_cells(mlb_ctx *ctx, uint32_t *n_owned, uint32_t *cells_out /* reference ids, or NULL */);
 
@@ -210,6 +217,8 @@ int mlb_compute_primitives(int32_t device, int32_t fp_mode, const mlb_physics *p
 /* ---- the mesh preprocessor alone (host only, no device): what mlb_create uploads.  `part` may be NULL.  Arrays by name:
  *   "sizes" (u32[12]: N, N_owned, N_recon, NF, n_slots, Q, K, M, Npad, S, Mp, 0), "perm_cells", "perm_faces",
  *   "slot_face", "slot_nbr" (i32), "rhs_order" (u8), "st_ids", "ghost_owner" (i32 per ghost cell),
+ *   "fm_ids" (u32), "fm_mat", "fm_area0", "OIs" (f64; compact streaming tables, fp_mode FAST only),
+ *   "halo_peers" (i32), "halo_recv_counts" (u64), "halo_recv_ids" (u32, concatenated; partitioned plans only),
  *   and the "teno:*" tables of mlb_get_array (reference CSR layout; unpartitioned plans only). */
 int mlb_plan_create(mlb_plan **out, const mlb_mesh *mesh, const mlb_numerics *numerics, const mlb_bc *bcs, int32_t n_bcs,
                     const int32_t *part, const mlb_parallel *parallel);

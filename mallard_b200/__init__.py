@@ -159,12 +159,13 @@ class Plan:
 
     _DT = {"sizes": np.uint32, "perm_cells": np.uint32, "perm_faces": np.uint32, "slot_face": np.uint32, "slot_nbr": np.int32,
            "rhs_order": np.uint8, "st_ids": np.uint32, "ghost_owner": np.int32, "teno:poly_indices": np.uint8,
+           "fm_ids": np.uint32, "halo_peers": np.int32, "halo_recv_counts": np.uint64, "halo_recv_ids": np.uint32,
            "teno:offsets_stencil_groups": np.uint32, "teno:offsets_stencils": np.uint32, "teno:stencils": np.uint32,
            "teno:offsets_reconstruction_matrices": np.uint32}
 
     def __init__(self, mesh, recon="FO", basis="legendre", order=3, factor=2.0, quad_cell_order=0, quad_face_order=0, bcs=(),
-                 renumber="rcm", part=None, rank=0, n_ranks=1):
-        num = _numerics(recon, "HLLC", "SSPRK3", basis, order, factor, quad_cell_order, quad_face_order, "strict", renumber, False, False)
+                 renumber="rcm", part=None, rank=0, n_ranks=1, fp_mode="strict"):
+        num = _numerics(recon, "HLLC", "SSPRK3", basis, order, factor, quad_cell_order, quad_face_order, fp_mode, renumber, False, False)
         keep = []
         cb = (_abi.Bc * max(1, len(bcs)))()
         for i, b in enumerate(bcs):
@@ -411,10 +412,33 @@ class Solver:
     def stage(self, s):
         self._ok(lib().mlb_stage(self._h, s))
 
-    def local_max_spectral_radius(self):
+    def local_max_spectral_radius(self, sync=True):
+        """Rank-local part of calc_dt.  sync=False leaves the value in the device scalar block (scalars_device()[2])."""
+        if not sync:
+            self._ok(lib().mlb_local_max_spectral_radius(self._h, None))
+            return None
         m = C.c_double()
         self._ok(lib().mlb_local_max_spectral_radius(self._h, C.byref(m)))
         return m.value
+
+    def scalars_device(self):
+        """Device pointer of the scalar block: doubles {dt, t, max spectral radius, cfl, ...}."""
+        return lib().mlb_scalars_device(self._h)
+
+    def apply_dt_device(self, cfl):
+        self._ok(lib().mlb_apply_dt_device(self._h, cfl))
+
+    def set_owned(self, U_owned):
+        U_owned = np.ascontiguousarray(U_owned, dtype=np.float64)
+        self._ok(lib().mlb_set_owned(self._h, _ptr(U_owned)))
+
+    def get_owned(self, out=None):
+        if out is None:
+            n = C.c_uint32()
+            self._ok(lib().mlb_owned_cells(self._h, C.byref(n), None))
+            out = np.empty((n.value, 4))
+        self._ok(lib().mlb_get_owned(self._h, _ptr(out)))
+        return out
 
     def apply_dt(self, cfl, global_max):
         self._ok(lib().mlb_apply_dt(self._h, cfl, global_max))

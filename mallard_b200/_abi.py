@@ -89,6 +89,10 @@ SYMBOLS = {
     "mlb_stage": (C.c_int, [VP, I32]),
     "mlb_local_max_spectral_radius": (C.c_int, [VP, C.POINTER(DBL)]),
     "mlb_apply_dt": (C.c_int, [VP, DBL, DBL]),
+    "mlb_scalars_device": (VP, [VP]),
+    "mlb_apply_dt_device": (C.c_int, [VP, DBL]),
+    "mlb_set_owned": (C.c_int, [VP, VP]),
+    "mlb_get_owned": (C.c_int, [VP, VP]),
     "mlb_finish_step": (C.c_int, [VP]),
     "mlb_owned_cells": (C.c_int, [VP, C.POINTER(U32), VP]),
     "mlb_riemann_flux": (C.c_int, [I32, I32, I32, U64, VP, VP, VP, DBL, VP]),

@@ -71,6 +71,10 @@ struct mlb_ctx {
     uint32_t * d_perm_cells = nullptr, * d_perm_faces = nullptr;
     uint32_t * d_st_ids = nullptr;
     double * d_st_area = nullptr, * d_st_mat = nullptr;
+    bool streaming = false;            // FAST mode: compact streaming tables + teno_stream_kernel
+    uint32_t * d_fm_ids = nullptr;
+    double * d_fm_mat = nullptr, * d_fm_area0 = nullptr;
+    uint32_t n_ftiles = 0;
     double * d_stage = nullptr;        // AoS staging, 5*N doubles (and face export)
     size_t d_stage_elems = 0;
     double * h_stage = nullptr;        // pinned host staging
@@ -147,6 +151,21 @@ struct mlb_ctx {
 };
 
 struct mlb_host_mesh { HostMesh m; };
+
+// Ghost cells grouped by owning rank (ascending), in library order within a group: the layout of the receive buffer.
+static void halo_recv_lists(const Prep & P, const int32_t * part, std::vector<int32_t> & peers, std::vector<uint64_t> & counts,
+                            std::vector<std::vector<uint32_t>> & ref_ids, std::vector<uint32_t> & recv_idx) {
+    std::map<int32_t, std::vector<uint32_t>> by_owner;
+    for (uint32_t i = P.N_owned; i < P.N; i++) by_owner[part[P.perm_cells[i]]].push_back(i);
+    peers.clear(); counts.clear(); ref_ids.clear(); recv_idx.clear();
+    for (auto & kv : by_owner) {
+        peers.push_back(kv.first);
+        counts.push_back(kv.second.size());
+        std::vector<uint32_t> ref;
+        for (uint32_t i : kv.second) { ref.push_back(P.perm_cells[i]); recv_idx.push_back(i); }
+        ref_ids.push_back(std::move(ref));
+    }
+}
 struct mlb_plan { Prep prep; uint32_t nc_ref = 0, nf_ref = 0; std::vector<int32_t> part; int rank = 0; std::string err; };
 
 namespace {
@@ -192,12 +211,30 @@ ReconArgs recon_args(mlb_ctx & c, const double * Uin) {
     return r;
 }
 
-void run_stage(mlb_ctx & c, const StagePlan & s, bool bare, double * k_out) {
-    const double * Uin = c.U[s.in];
-    if (c.teno && !c.has_override) {
+ReconStreamArgs stream_args(mlb_ctx & c, const double * Uin) {
+    ReconStreamArgs r{};
+    const TenoTables & T = c.prep.teno;
+    r.g = c.g; r.Uin = Uin; r.Fc = c.Fc; r.mat = c.d_fm_mat; r.ids = c.d_fm_ids; r.area0 = c.d_fm_area0;
+    r.n_tiles = c.n_ftiles; r.order = T.order; r.fixed_weights = c.num.teno_fixed;
+    for (size_t i = 0; i < c.prep.qf_x.size() && i < 4; i++) r.qf_x[i] = c.prep.qf_x[i];
+    for (int i = 0; i < T.K; i++) r.psi_bar[i] = T.psi_bar[i];
+    for (size_t i = 0; i < T.OIs.size(); i++) r.OIs[i] = T.OIs[i];
+    return r;
+}
+
+void run_recon(mlb_ctx & c, const double * Uin) {
+    if (c.streaming) {
+        ReconStreamArgs r = stream_args(c, Uin);
+        c.launch("teno_stream", [&] { c.kt->recon_stream(r, c.stream); });
+    } else {
         ReconArgs r = recon_args(c, Uin);
         c.launch("teno_recon", [&] { c.kt->recon(r, c.stream); });
     }
+}
+
+void run_stage(mlb_ctx & c, const StagePlan & s, bool bare, double * k_out) {
+    const double * Uin = c.U[s.in];
+    if (c.teno && !c.has_override) run_recon(c, Uin);
     StageArgs a{};
     a.g = c.g; a.ph = c.phys; a.Uin = Uin; a.Fc = c.Fc; a.teno = c.teno ? 1 : 0;
     a.k_override = c.has_override ? c.k_override : nullptr;
@@ -301,11 +338,20 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
     PrepOptions opt;
     opt.renumber = c->num.renumber;
     opt.keep_ref_tables = c->teno && !part && hm.nc <= 200000;
+    if (c->teno && c->num.fp_mode == MLB_FP_FAST && c->kt->stream_supported) {
+        int n_slots = 0;
+        for (uint32_t cc = 0; cc < hm.nc; cc++) n_slots = std::max(n_slots, hm.nfc(cc));
+        const int p = c->num.basis_order, K = (p + 1) * (p + 2) / 2;
+        const double factor = c->num.max_stencil_size_factor > 0 ? c->num.max_stencil_size_factor : 2.0;
+        const int Q = c->num.quadrature_order_face > 0 ? c->num.quadrature_order_face : (p + 1) / 2;
+        c->streaming = c->kt->stream_supported(p, (int)(uint16_t)(factor * K), Q, c->num.basis, n_slots);
+    }
+    opt.fast_tables = c->streaming;
     opt.part = part; opt.rank = c->rank; opt.n_ranks = c->n_ranks;
     preprocess(hm, c->num, bc_zones, opt, c->prep);
     Prep & P = c->prep;
     for (size_t i = 0; i < P.qf_x.size(); i++) { c->phys.qf_x[i] = P.qf_x[i]; c->phys.qf_w[i] = P.qf_w[i]; }
-    if (c->teno && !c->kt->recon_supported(P.teno.order, P.teno.Mp, P.teno.basis))
+    if (c->teno && !c->streaming && !c->kt->recon_supported(P.teno.order, P.teno.Mp, P.teno.basis))
         throw std::runtime_error("TENO: this (basis, order, stencil size) combination has no compiled device kernel "
                                  "(available: legendre, order 1-4, max_stencil_size_factor 2.0)");
 
@@ -348,9 +394,15 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
         TenoTables & T = P.teno;
         c->Fc = c->alloc<double>((size_t)P.n_slots * P.Q * 4 * NP);
         CUDA_OK(cudaMemsetAsync(c->Fc, 0, (size_t)P.n_slots * P.Q * 4 * NP * sizeof(double), c->stream));
-        c->d_st_ids = c->upload(T.st_ids); c->d_st_area = c->upload(T.st_area); c->d_st_mat = c->upload(T.st_mat);
+        if (c->streaming) {
+            c->n_ftiles = (uint32_t)((P.N_recon + FAST_CT - 1) / FAST_CT);
+            c->d_fm_ids = c->upload(T.fm_ids); c->d_fm_area0 = c->upload(T.fm_area0); c->d_fm_mat = c->upload(T.fm_mat);
+        } else {
+            c->d_st_ids = c->upload(T.st_ids); c->d_st_area = c->upload(T.st_area); c->d_st_mat = c->upload(T.st_mat);
+        }
         CUDA_OK(cudaStreamSynchronize(c->stream));
         uvec().swap(T.st_ids); dvec().swap(T.st_area); dvec().swap(T.st_mat);   // host copies no longer needed
+        uvec().swap(T.fm_ids); dvec().swap(T.fm_area0); dvec().swap(T.fm_mat);
     }
     for (auto & e : c->ev) CUDA_OK(cudaEventCreate(&e));
     CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -387,17 +439,8 @@ int mlb_create_partitioned(mlb_ctx ** out, const mlb_mesh * mesh, const int32_t 
     if (!out || !part || !parallel) throw std::runtime_error("mlb_create_partitioned: NULL argument");
     *out = nullptr;
     mlb_ctx * c = create_impl(mesh, part, numerics, physics, bcs, n_bcs, parallel);
-    // ghosts grouped by owning rank (ascending), in library order within a group
-    std::map<int32_t, std::vector<uint32_t>> by_owner;
-    for (uint32_t i = c->prep.N_owned; i < c->prep.N; i++) by_owner[part[c->prep.perm_cells[i]]].push_back(i);
     std::vector<uint32_t> recv_idx;
-    for (auto & kv : by_owner) {
-        c->peers.push_back(kv.first);
-        c->recv_counts.push_back(kv.second.size());
-        std::vector<uint32_t> ref;
-        for (uint32_t i : kv.second) { ref.push_back(c->prep.perm_cells[i]); recv_idx.push_back(i); }
-        c->recv_ref_ids.push_back(ref);
-    }
+    halo_recv_lists(c->prep, part, c->peers, c->recv_counts, c->recv_ref_ids, recv_idx);
     c->n_recv = recv_idx.size();
     c->d_recv_idx = c->upload(recv_idx);
     c->d_recv_buf = c->alloc<double>(4 * std::max<size_t>(c->n_recv, 1));
@@ -443,10 +486,7 @@ int mlb_n_face_quadrature_points(const mlb_ctx * c) { return c ? c->prep.Q : 0; 
 int mlb_calc_face_values(mlb_ctx * c, double * F_out) {
     API_BEGIN(c)
     CUDA_OK(cudaSetDevice(c->device));
-    if (c->teno) {
-        ReconArgs r = recon_args(*c, c->U[c->cur]);
-        c->launch("teno_recon", [&] { c->kt->recon(r, c->stream); });
-    }
+    if (c->teno) run_recon(*c, c->U[c->cur]);
     if (F_out) {
         const size_t n = (size_t)c->nf_ref * c->prep.Q * 8;
         c->ensure_stage(n);
@@ -681,13 +721,23 @@ int mlb_halo_recv_ids(mlb_ctx * c, int32_t peer_index, uint32_t * ref_ids_out) {
 int mlb_halo_set_send_ids(mlb_ctx * c, int32_t n_lists, const int32_t * peer_ranks, const uint64_t * counts, const uint32_t * ref_ids) {
     API_BEGIN(c)
     CUDA_OK(cudaSetDevice(c->device));
-    // the lists must come for the same peers, ascending — a symmetric halo graph (face neighbours / stencils) guarantees it
+    // lists must be given in ascending peer order (the send buffer is laid out peer by peer in that order).  A peer that
+    // only receives from this rank (TENO stencils are not symmetric) joins the peer list with an empty receive list,
+    // which leaves the receive-buffer offsets unchanged.
+    for (int l = 1; l < n_lists; l++)
+        if (peer_ranks[l] <= peer_ranks[l - 1]) throw std::runtime_error("halo: send lists must be in ascending peer order");
+    for (int l = 0; l < n_lists; l++) {
+        if (!counts[l] || std::find(c->peers.begin(), c->peers.end(), peer_ranks[l]) != c->peers.end()) continue;
+        const size_t at = std::lower_bound(c->peers.begin(), c->peers.end(), peer_ranks[l]) - c->peers.begin();
+        c->peers.insert(c->peers.begin() + at, peer_ranks[l]);
+        c->recv_counts.insert(c->recv_counts.begin() + at, 0);
+        c->recv_ref_ids.insert(c->recv_ref_ids.begin() + at, std::vector<uint32_t>());
+    }
     std::vector<uint32_t> idx;
     c->send_counts.assign(c->peers.size(), 0);
     size_t off = 0;
     for (int l = 0; l < n_lists; l++) {
         auto it = std::find(c->peers.begin(), c->peers.end(), peer_ranks[l]);
-        if (it == c->peers.end() && counts[l]) throw std::runtime_error("halo: send list for a rank that sends us nothing (asymmetric halo)");
         for (uint64_t k = 0; k < counts[l]; k++) {
             const uint32_t ref = ref_ids[off + k];
             const uint32_t loc = ref < c->nc_ref ? c->prep.iperm_cells[ref] : NO_FACE;
@@ -747,9 +797,45 @@ int mlb_local_max_spectral_radius(mlb_ctx * c, double * max_out) {
     API_BEGIN(c)
     CUDA_OK(cudaSetDevice(c->device));
     do_calc_dt(*c, -1.0);
-    double sc[SC_COUNT];
-    read_scalars(*c, sc);
-    if (max_out) *max_out = sc[SC_MAX_SR];
+    if (max_out) {   // NULL: stay asynchronous, the value is left in the device scalar block (mlb_scalars_device()[2])
+        double sc[SC_COUNT];
+        read_scalars(*c, sc);
+        *max_out = sc[SC_MAX_SR];
+    }
+    API_END(c)
+}
+void * mlb_scalars_device(mlb_ctx * c) { return c ? (void *)c->scal : nullptr; }
+int mlb_apply_dt_device(mlb_ctx * c, double cfl) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    launch_apply_dt(c->scal, c->max_bits, cfl, 0.0, 0, c->stream);
+    c->launches++;
+    API_END(c)
+}
+int mlb_set_owned(mlb_ctx * c, const double * U_owned) {
+    API_BEGIN(c)
+    if (!U_owned) throw std::runtime_error("mlb_set_owned: NULL buffer");
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->prep.N_owned * 4;
+    c->ensure_stage(std::max<size_t>(n, 1));
+    CUDA_OK(cudaMemcpyAsync(c->d_stage, U_owned, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    launch_import_state(c->d_stage, nullptr, c->prep.N_owned, c->prep.Npad, 4, c->U[c->cur], c->stream);
+    c->launches++;
+    // primitives of the owned cells (Solver::update_primitives); ghosts get theirs at the stage-0 unpack
+    c->kt->primitives_soa(c->gas, c->prep.N_owned, c->prep.Npad, c->U[c->cur], c->prim, c->stream);
+    c->launches++;
+    API_END(c)
+}
+int mlb_get_owned(mlb_ctx * c, double * U_owned) {
+    API_BEGIN(c)
+    if (!U_owned) throw std::runtime_error("mlb_get_owned: NULL buffer");
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->prep.N_owned * 4;
+    c->ensure_stage(std::max<size_t>(n, 1));
+    launch_export_state(c->U[c->cur], nullptr, c->prep.N_owned, c->prep.Npad, 4, c->d_stage, c->stream);
+    c->launches++;
+    CUDA_OK(cudaMemcpyAsync(U_owned, c->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
     API_END(c)
 }
 int mlb_apply_dt(mlb_ctx * c, double cfl, double global_max) {
@@ -856,6 +942,7 @@ int mlb_plan_create(mlb_plan ** out, const mlb_mesh * mesh, const mlb_numerics *
     PrepOptions opt;
     opt.renumber = numerics->renumber;
     opt.keep_ref_tables = numerics->recon == MLB_RECON_TENO && !part;
+    opt.fast_tables = numerics->recon == MLB_RECON_TENO && numerics->fp_mode == MLB_FP_FAST;
     opt.part = part; opt.rank = parallel ? parallel->rank : 0; opt.n_ranks = parallel ? parallel->n_ranks : 1;
     p->rank = opt.rank;
     if (part) p->part.assign(part, part + hm.nc);
@@ -883,6 +970,18 @@ int mlb_plan_get(mlb_plan * p, const char * name, void * out, uint64_t * nbytes)
     else if (n == "slot_nbr") host(P.slot_nbr.data(), P.slot_nbr.size() * 4);
     else if (n == "rhs_order") host(P.rhs_order.data(), P.rhs_order.size());
     else if (n == "st_ids") host(T.st_ids.data(), T.st_ids.size() * 4);
+    else if (n == "fm_ids") host(T.fm_ids.data(), T.fm_ids.size() * 4);
+    else if (n == "fm_mat") host(T.fm_mat.data(), T.fm_mat.size() * 8);
+    else if (n == "fm_area0") host(T.fm_area0.data(), T.fm_area0.size() * 8);
+    else if (n == "OIs") host(T.OIs.data(), T.OIs.size() * 8);
+    else if (n == "halo_peers" || n == "halo_recv_counts" || n == "halo_recv_ids") {
+        if (p->part.empty()) throw std::runtime_error("plan is not partitioned");
+        std::vector<int32_t> peers; std::vector<uint64_t> counts; std::vector<std::vector<uint32_t>> ids; std::vector<uint32_t> idx;
+        halo_recv_lists(P, p->part.data(), peers, counts, ids, idx);
+        if (n == "halo_peers") host(peers.data(), peers.size() * 4);
+        else if (n == "halo_recv_counts") host(counts.data(), counts.size() * 8);
+        else { std::vector<uint32_t> flat; for (auto & v : ids) flat.insert(flat.end(), v.begin(), v.end()); host(flat.data(), flat.size() * 4); }
+    }
     else if (n == "ghost_owner") {
         std::vector<int32_t> o;
         for (uint32_t i = P.N_owned; i < P.N; i++) o.push_back(p->part.empty() ? 0 : p->part[P.perm_cells[i]]);

@@ -74,6 +74,20 @@ struct ReconArgs {
     double OI[15 * 15];
 };
 
+struct ReconStreamArgs {       // teno_stream.cuh
+    DevGeom g;
+    const double * Uin;
+    double * Fc;
+    const double * mat;
+    const uint32_t * ids;
+    const double * area0;
+    uint32_t n_tiles;
+    int32_t order, fixed_weights;
+    double qf_x[4];
+    double psi_bar[15];
+    double OIs[14 * 14];
+};
+
 struct CflArgs {
     DevGeom g;
     GasParams gas;
@@ -96,6 +110,9 @@ struct KernelTable {
     void (*primitives)(const GasParams &, uint64_t n, const double * U_aos, double * P_aos, cudaStream_t);
     void (*primitives_soa)(const GasParams &, uint32_t n, uint32_t npad, const double * U, double * P, cudaStream_t);
     bool (*recon_supported)(int order, int Mp, int basis);
+    // FAST mode only (null in the STRICT table): streaming TENO reconstruction over the compact tables
+    void (*recon_stream)(const ReconStreamArgs &, cudaStream_t);
+    bool (*stream_supported)(int order, int M, int Q, int basis, int n_slots);
 };
 
 const KernelTable * kernels_strict();

@@ -403,6 +403,10 @@ __global__ void __launch_bounds__(RECON_THREADS) teno_recon_kernel(const __grid_
     }
 }
 
+#ifdef MLB_STREAM_KERNELS
+#include "teno_stream.cuh"
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------
 // Spectral radius + max + dt — SpectralRadiusFunctor / Solver::calc_dt (solver/solver.cpp:580-742)
 // ---------------------------------------------------------------------------------------------------------------
@@ -567,8 +571,13 @@ static void launch_prims_soa(const GasParams & g, uint32_t n, uint32_t npad, con
 
 #define MLB_STR2(x) #x
 #define MLB_STR(x) MLB_STR2(x)
+#ifdef MLB_STREAM_KERNELS
 static const KernelTable table = {MLB_STR(MLB_KNS), launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
-                                  launch_prims_soa, recon_supported};
+                                  launch_prims_soa, recon_supported, stream::launch_stream, stream::stream_supported};
+#else
+static const KernelTable table = {MLB_STR(MLB_KNS), launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
+                                  launch_prims_soa, recon_supported, nullptr, nullptr};
+#endif
 
 }  // namespace MLB_KNS
 }  // namespace mlb

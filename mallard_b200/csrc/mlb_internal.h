@@ -52,6 +52,12 @@ constexpr int MAX_K = 55;       // (p+1)(p+2)/2 for p <= 9
 constexpr uint32_t NO_FACE = 0xFFFFFFFFu;
 constexpr int TILE = 8;         // cells per interleaved TENO table tile (one warp = 8 cells x 4 variables)
 
+// Streaming (FAST mode) table layout, see teno_stream.cuh: tiles of FAST_CT cells, S = 1 + 3 stencil slots (triangles)
+constexpr int FAST_CT = 32;
+constexpr int FAST_S = 4;
+constexpr int fast_rows_per_chunk(int order) { return order == 1 ? 2 : order == 2 ? 5 : order == 3 ? 3 : 2; }
+constexpr int fast_stages(int order) { return order == 1 ? 8 : 6; }
+
 struct TenoTables {
     int basis = 1, order = 0, K = 0, M = 0, Mp = 0, S = 0;   // Mp = M padded to even, S = stencil slots per cell (1 + max faces)
     int nq_cell = 0;
@@ -64,6 +70,15 @@ struct TenoTables {
     //   st_mat  [tile][S][K][Mp/2][TILE][2] f64  pseudo-inverse rows, m-pairs interleaved across the tile's cells
     uvec st_ids;
     dvec st_area, st_mat;
+    // Compact streaming tables (FAST mode), n_ftiles = ceil(N_recon / FAST_CT):
+    //   fm_ids   [ftile][S][M-1][FAST_CT]                 u32  columns m = 1..M-1; empty stencil / padding cell -> NO_FACE
+    //   fm_mat   [ftile][S][K-1][(M-1)/2 pairs | 1][FAST_CT]  f64  rows k = 1..K-1 of A+ with area_t folded into the columns;
+    //                                                      per row: (M-1)/2 column pairs [pair][cell][2], then [cell] singles
+    //   fm_area0 [ftile * FAST_CT]                         f64  area_t of the cell itself (central stencil, m = 0)
+    //   OIs      [K-1][K-1]  upper-triangular fold of the oscillation matrix: OI[k][k] on the diagonal, OI[k][j] + OI[j][k] above
+    bool fast = false;
+    uvec fm_ids;
+    dvec fm_mat, fm_area0, OIs;
     // Reference-layout CSR copies (reference numbering) for parity checks (optional, small meshes only)
     bool keep_ref = false;
     uvec ref_off_groups, ref_off_stencils, ref_stencils, ref_off_mats;
@@ -100,6 +115,7 @@ struct Prep {
 struct PrepOptions {
     int renumber = MLB_RENUMBER_RCM;
     bool keep_ref_tables = false;
+    bool fast_tables = false;         // build the compact streaming tables instead of the bit-faithful ones
     const int32_t * part = nullptr;   // partition vector (reference numbering) or null
     int rank = 0, n_ranks = 1;
 };

@@ -675,8 +675,18 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
     // ---- TENO tables
     if (teno) {
         const int K = T.K, M = T.M, Mp = T.Mp, S = T.S;
+        T.fast = opt.fast_tables;
+        const bool strict_tables = !T.fast || T.keep_ref;        // bit-faithful layout (STRICT kernels, parity hooks)
+        if (T.fast && (S != FAST_S || M != 2 * K)) throw std::runtime_error("streaming TENO tables need triangles and max_stencil_size_factor 2");
         T.st_area.assign(n_tiles * S * Mp * TILE, 0.0);
-        T.st_mat.assign(n_tiles * S * K * Mp * TILE, 0.0);
+        if (strict_tables) T.st_mat.assign(n_tiles * S * K * Mp * TILE, 0.0);
+        const int KR = K - 1, MC = M - 1, NPAIR = MC / 2;
+        const size_t n_ftiles = (n_recon + FAST_CT - 1) / FAST_CT;
+        const size_t frow = (size_t)(2 * NPAIR + 1) * FAST_CT;   // doubles per stored row of one tile
+        if (T.fast) {
+            T.fm_mat.assign(n_ftiles * S * KR * frow, 0.0);
+            T.fm_area0.assign(n_ftiles * FAST_CT, 0.5);
+        }
         T.psi_bar.assign(K, 0.0);
         {   // integral_psi_target: row 0 of REFERENCE cell 0's central stencil, i.e. the cell itself (:598-602)
             MatrixScratch w;
@@ -702,9 +712,24 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
                         for (int k2 = 0; k2 < M; k2++) st[k2] = T.st_ids[(base + k2) * TILE + lane];
                         stencil_matrix(m, T, order[i], st.data(), M, T.psi_bar.data(), at.data(), Ai.data(), w);
                         for (int k2 = 0; k2 < M; k2++) T.st_area[(base + k2) * TILE + lane] = at[k2];
-                        for (int k = 0; k < K; k++)
-                            for (int k2 = 0; k2 < M; k2++)
-                                T.st_mat[((((tile * S + s) * K + k) * (Mp / 2) + k2 / 2) * TILE + lane) * 2 + (k2 & 1)] = Ai[(size_t)k * M + k2];
+                        if (strict_tables)
+                            for (int k = 0; k < K; k++)
+                                for (int k2 = 0; k2 < M; k2++)
+                                    T.st_mat[((((tile * S + s) * K + k) * (Mp / 2) + k2 / 2) * TILE + lane) * 2 + (k2 & 1)] = Ai[(size_t)k * M + k2];
+                        if (T.fast) {   // rows 1..K-1, columns 1..M-1, transformed areas folded into the columns
+                            const size_t ft = i / FAST_CT, fl = i % FAST_CT;
+                            for (int k2 = 0; k2 < M; k2++) if (Ai[k2] != 0.0) throw std::runtime_error("TENO: reconstruction matrix has a non-zero first row; compact tables unavailable (use fp_mode strict)");
+                            for (int k = 0; k < K; k++) if (Ai[(size_t)k * M] != 0.0) throw std::runtime_error("TENO: reconstruction matrix has a non-zero first column; compact tables unavailable (use fp_mode strict)");
+                            if (s == 0) T.fm_area0[i] = at[0];
+                            for (int k = 1; k < K; k++) {
+                                double * row = &T.fm_mat[((ft * S + s) * KR + (k - 1)) * frow];
+                                for (int c = 0; c < MC; c++) {
+                                    const double v = Ai[(size_t)k * M + (c + 1)] * at[c + 1];
+                                    if (c < 2 * NPAIR) row[((size_t)(c / 2) * FAST_CT + fl) * 2 + (c & 1)] = v;
+                                    else row[(size_t)2 * NPAIR * FAST_CT + fl] = v;
+                                }
+                            }
+                        }
                     }
                 } catch (const std::exception & e) {
 #pragma omp critical
@@ -750,6 +775,23 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
                     }
                     for (int k2 = M; k2 < Mp; k2++) T.st_ids[(base + k2) * TILE + lane] = (uint32_t)(tile * TILE + lane);
                 }
+        if (T.fast) {
+            T.fm_ids.assign(n_ftiles * S * MC * FAST_CT, NO_FACE);
+#pragma omp parallel for schedule(static)
+            for (int64_t ii = 0; ii < (int64_t)n_recon; ii++) {
+                const size_t tile = (size_t)ii / TILE, lane = (size_t)ii % TILE, ft = (size_t)ii / FAST_CT, fl = (size_t)ii % FAST_CT;
+                for (int s = 0; s < S; s++) {
+                    const size_t base = (tile * S + s) * Mp;
+                    if (T.st_ids[base * TILE + lane] == NO_FACE) continue;
+                    for (int c = 0; c < MC; c++) T.fm_ids[((ft * S + s) * MC + c) * FAST_CT + fl] = T.st_ids[(base + c + 1) * TILE + lane];
+                }
+            }
+            T.OIs.assign((size_t)KR * KR, 0.0);
+            for (int k = 1; k < K; k++)
+                for (int j = k; j < K; j++)   // a^T OI a = sum_k OI_kk a_k^2 + sum_{k<j} (OI_kj + OI_jk) a_k a_j
+                    T.OIs[(size_t)(k - 1) * KR + (j - 1)] = j == k ? T.OI[(size_t)k * K + k] : T.OI[(size_t)k * K + j] + T.OI[(size_t)j * K + k];
+            if (!strict_tables) { uvec().swap(T.st_ids); dvec().swap(T.st_area); }
+        }
     }
     P.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }

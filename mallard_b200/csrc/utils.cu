@@ -6,12 +6,12 @@ namespace mlb {
 
 namespace {
 
-// soa[v][i] = aos[perm[i]][v]
+// soa[v][i] = aos[perm[i]][v]   (perm == nullptr: identity)
 __global__ void import_kernel(const double * __restrict__ aos, const uint32_t * __restrict__ perm, uint32_t n, uint32_t npad, int nv,
                               double * __restrict__ soa) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const size_t src = (size_t)perm[i] * nv;
+    const size_t src = (size_t)(perm ? perm[i] : i) * nv;
     for (int v = 0; v < nv; v++) soa[(size_t)v * npad + i] = aos[src + v];
 }
 
@@ -20,7 +20,7 @@ __global__ void export_kernel(const double * __restrict__ soa, const uint32_t * 
                               double * __restrict__ aos) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const size_t dst = (size_t)perm[i] * nv;
+    const size_t dst = (size_t)(perm ? perm[i] : i) * nv;
     for (int v = 0; v < nv; v++) aos[dst + v] = soa[(size_t)v * npad + i];
 }
 

@@ -1,0 +1,151 @@
+"""Partitioned (multi-GPU) execution on the device.  (1) several rank contexts on ONE GPU with the halo exchange done by
+device-to-device copies between the library's buffers: every rank's result must equal the single-context result bit for
+bit in STRICT mode; (2) with >= 2 GPUs, the real thing: one process per GPU, NCCL halo exchange + all-reduce of dt."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import mallard_b200 as mb
+from mallard_b200.parallel import device_tensor
+
+pytestmark = pytest.mark.gpu
+SYM4 = [dict(name=n, type="symmetry") for n in ("left", "right", "top", "bottom")]
+
+
+def _state(xy):
+    rho = 1.0 + 0.3 * np.sin(2 * np.pi * xy[:, 0]) * np.cos(2 * np.pi * 1.5 * xy[:, 1])
+    u = 0.4 + 0.2 * np.cos(2 * np.pi * xy[:, 1]); v = -0.3 + 0.2 * np.sin(2 * np.pi * xy[:, 0])
+    p = 1.0 + 0.2 * np.cos(2 * np.pi * (xy[:, 0] - xy[:, 1]))
+    e = p / (0.4 * rho)
+    return np.stack([rho, rho * u, rho * v, rho * (e + 0.5 * (u * u + v * v))], 1)
+
+
+class Loopback:
+    """n rank contexts on one device; exchange = copies between their send/receive buffers."""
+
+    def __init__(self, mesh, part, n, **kw):
+        self.s = [mb.Solver(mesh, part=part, rank=r, n_ranks=n, device=0, **kw) for r in range(n)]
+        wants = []
+        for s in self.s:
+            peers, _, rc = s.halo_info()
+            wants.append({int(p): s.halo_recv_ids(i, rc[i]) for i, p in enumerate(peers)})
+        for r, s in enumerate(self.s):
+            send = {q: wants[q][r] for q in range(n) if q != r and r in wants[q] and len(wants[q][r])}
+            sp = sorted(send)
+            s.halo_set_send_ids(sp, [send[p] for p in sp])
+        self.info = [s.halo_info() for s in self.s]
+        self.buf = []
+        for s, (peers, sc, rc) in zip(self.s, self.info):
+            a, b = s.halo_buffers()
+            self.buf.append((device_tensor(a, 4 * int(sc.sum()), 0), device_tensor(b, 4 * int(rc.sum()), 0)))
+
+    def exchange(self, stage):
+        for s in self.s:
+            s.halo_pack(stage)
+        for s in self.s:
+            s.synchronize()
+        for r, (peers, sc, rc) in enumerate(self.info):
+            ro = 0
+            for p, n_recv in zip(peers, rc):
+                pp, psc, _ = self.info[int(p)]
+                so = 4 * int(psc[:list(pp).index(r)].sum())
+                n = 4 * int(n_recv)
+                assert int(psc[list(pp).index(r)]) == int(n_recv)
+                self.buf[r][1][ro:ro + n].copy_(self.buf[int(p)][0][so:so + n])
+                ro += n
+        torch.cuda.synchronize()
+        for s in self.s:
+            s.halo_unpack(stage)
+
+    def step(self, cfl):
+        self.exchange(0)
+        mx = max(s.local_max_spectral_radius() for s in self.s)
+        for s in self.s:
+            s.apply_dt(cfl, mx)
+            s.stage(0)
+        for st in range(1, self.s[0].n_stages):
+            self.exchange(st)
+            for s in self.s:
+                s.stage(st)
+        for s in self.s:
+            s.finish_step()
+
+    def state(self):
+        return sum(s.get_state() for s in self.s)   # every rank exports zeros outside its own cells
+
+
+@pytest.mark.parametrize("recon,integ,n_ranks,fp", [("FO", "SSPRK3", 2, "strict"), ("FO", "RK4", 3, "strict"), ("TENO", "SSPRK3", 2, "strict"),
+                                                    ("TENO", "SSPRK3", 4, "strict"), ("TENO", "SSPRK3", 3, "fast")])
+def test_partitioned_ranks_reproduce_the_single_context_run(recon, integ, n_ranks, fp):
+    mtype = "cartesian_tri" if recon == "TENO" else "wedge"
+    mesh = mb.Mesh.generate(mtype, 36, 24, 4.0, 1.5)
+    U0 = _state(mesh.arrays["cell_coords"])
+    kw = dict(recon=recon, riemann="HLLC", integrator=integ, order=3, bcs=SYM4, fp_mode=fp, teno_fixed=True)
+    one = mb.Solver(mesh, **kw)
+    one.set_state(U0)
+    part = mb.partition(mesh, n_ranks)
+    many = Loopback(mesh, part, n_ranks, **kw)
+    for s in many.s:
+        s.set_state(U0)
+    for _ in range(3):
+        one.calc_dt(0.3)
+        one.take_step()
+        many.step(0.3)
+    U1, Un = one.get_state(), many.state()
+    assert np.isfinite(U1).all()
+    if fp == "strict":
+        assert np.array_equal(U1, Un)           # same per-cell operation order whatever the partition
+    else:
+        assert np.abs(Un - U1).max() <= 1e-12 * np.abs(U1).max()
+    t1, n1 = one.time()
+    for s in many.s:
+        t, n = s.time()
+        assert n == n1 and t == t1
+    # owned-cell host seam: set_owned / get_owned round trip in owned_cells order
+    s0 = many.s[0]
+    own = s0.owned_cells()
+    assert np.array_equal(s0.get_owned(), Un[own])
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from mallard_b200.parallel import DistributedSolver
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="4")
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        mesh = mb.Mesh.generate("cartesian_tri", 48, 32, 2.0, 1.0)
+        U0 = _state(mesh.arrays["cell_coords"])
+        part = mb.partition(mesh, world)
+        ds = DistributedSolver(mesh, part, rank, world, rank, recon="TENO", riemann="HLLC", integrator="SSPRK3", order=3, bcs=SYM4,
+                               fp_mode="strict", teno_fixed=True)
+        ds.set_state(U0)
+        t, n = ds.run(3, cfl=0.3)
+        U = ds.gather_state()
+        if rank == 0:
+            np.save(os.path.join(out_dir, "U.npy"), U)
+            np.save(os.path.join(out_dir, "t.npy"), np.array([t, n]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_nccl_halo_exchange_matches_single_gpu(tmp_path):
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mesh = mb.Mesh.generate("cartesian_tri", 48, 32, 2.0, 1.0)
+    one = mb.Solver(mesh, "TENO", "HLLC", "SSPRK3", order=3, bcs=SYM4, fp_mode="strict", teno_fixed=True)
+    one.set_state(_state(mesh.arrays["cell_coords"]))
+    t, _ = one.run(3, cfl=0.3)
+    assert np.array_equal(np.load(tmp_path / "U.npy"), one.get_state())
+    assert np.load(tmp_path / "t.npy")[0] == t

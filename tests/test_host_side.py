@@ -153,3 +153,52 @@ def test_partition_is_balanced_and_deterministic():
         counts = np.bincount(p1, minlength=n)
         assert counts.min() > 0 and counts.max() - counts.min() <= n
     assert np.all(mb.partition(mesh, 1) == 0)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_streaming_tables_are_the_reference_tables_compacted(order):
+    """FAST mode streams compact tables (mallard_b200/csrc/teno_stream.cuh): rows 1..K-1 x columns 1..M-1 of every
+    reference matrix with the transformed areas folded into the columns.  What is dropped must be exact zeros and what is
+    kept must be the reference value times the reference area, bit for bit."""
+    mesh = mb.Mesh.generate("cartesian_tri", 9, 7, 1.0, 0.7)
+    plan = mb.Plan(mesh, "TENO", order=order, fp_mode="fast")
+    K, M, S, CT = plan.K, plan.M, 4, 32
+    KR, MC = K - 1, M - 1
+    npair = MC // 2
+    off_g, off_s = plan.get("teno:offsets_stencil_groups"), plan.get("teno:offsets_stencils")
+    sten, mats, areas = plan.get("teno:stencils"), plan.get("teno:reconstruction_matrices"), plan.get("teno:transformed_areas")
+    perm = plan.get("perm_cells")
+    inv = np.empty(mesh.n_cells, np.int64); inv[perm] = np.arange(mesh.n_cells)
+    n_ft = (plan.N_recon + CT - 1) // CT
+    ids = plan.get("fm_ids").reshape(n_ft, S, MC, CT)
+    mat = plan.get("fm_mat").reshape(n_ft, S, KR, (2 * npair + 1) * CT)
+    a0 = plan.get("fm_area0")
+    OI = plan.get("teno:oscillation_indicator").reshape(K, K)
+    assert not OI[0].any() and not OI[:, 0].any()               # the constant mode carries no oscillation
+    OIs = plan.get("OIs").reshape(KR, KR)
+    O = OI[1:, 1:]
+    assert np.array_equal(OIs, np.triu(O + O.T, 1) + np.diag(np.diag(O)))   # a^T OI a folded onto the upper triangle
+    n_empty = 0
+    for i in range(plan.N_recon):
+        c = int(perm[i]); ft, fl = divmod(i, CT)
+        for s in range(S):
+            g = off_g[c] + s
+            lo, hi = int(off_s[g]), int(off_s[g + 1])
+            row = mat[ft, s]
+            got = np.empty((KR, MC))
+            for m in range(MC):
+                got[:, m] = row[:, (m // 2 * CT + fl) * 2 + (m & 1)] if m < 2 * npair else row[:, 2 * npair * CT + fl]
+            if hi == lo:
+                assert (ids[ft, s, :, fl] == 0xFFFFFFFF).all() and not got.any()
+                n_empty += 1
+                continue
+            A = mats[K * lo:K * hi].reshape(K, M); ar = areas[lo:hi]
+            assert not A[0].any() and not A[:, 0].any()
+            assert np.array_equal(ids[ft, s, :, fl], inv[sten[lo + 1:hi]])
+            if s == 0:
+                assert a0[i] == ar[0]
+            assert np.array_equal(got, A[1:, 1:] * ar[None, 1:])
+    assert n_empty > 0    # boundary faces have no directional stencil
+    for i in range(plan.N_recon, n_ft * CT):   # padding cells of the last tile
+        ft, fl = divmod(i, CT)
+        assert (ids[ft, :, :, fl] == 0xFFFFFFFF).all()
