@@ -226,7 +226,7 @@ def main():
     kernels = {k: {"ms_total": v[0], "launches": int(v[1]), "ms_per_launch": v[0] / max(1, v[1])} for k, v in prof.items()}
     if top:
         per_launch_ms = prof[top][0] / prof[top][1]
-        alg = {"teno_recon": ALG_BYTES_RECON, "teno_stream": ALG_BYTES_RECON, "flux_stage_teno": ALG_BYTES_STAGE - ALG_BYTES_RECON, "flux_stage_fo": 152.0,
+        alg = {"teno_recon": ALG_BYTES_RECON, "teno_stream": ALG_BYTES_RECON, "face_flux_teno": 48.0, "gather_stage": 72.0, "face_flux_fo": 80.0,
                "cfl": 200.0}.get(top, ALG_BYTES_STAGE)
         achieved = alg * nc / (per_launch_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,

@@ -20,6 +20,9 @@ struct DevGeom {
     const double * bnd_s;         // [Npad] 2*pow(V,1/2) (solver.cpp:662-666), computed on the host with libm pow
     const double * face_nx, * face_ny, * face_area;   // [NFpad]
     const double * slot_fx;       // [n_slots][4][Npad]
+    const uint32_t * face_cl;     // [NFpad] cell on side 0 (normal points out of it)
+    const int32_t * face_cr;      // [NFpad] cell on side 1 ; < 0: -(bc index + 1) ; INT32_MIN: no flux
+    const uint8_t * face_slots;   // [NFpad] slot of the face in cell 0 | slot in cell 1 << 4 (TENO face values are cell-centred)
 };
 
 struct DevPhys {
@@ -54,6 +57,7 @@ struct StageArgs {
     RkArgs rk;
     const double * Uin;           // SoA [4][Npad]: state the residual is evaluated on
     const double * Fc;            // TENO: cell-centred face values [n_slots][Q][4][Npad]
+    double * AF;                  // [NFpad][4] area * quadrature-averaged flux per face (written by the face kernel)
     const double * k_override;    // SoA [4][Npad] or null: state-independent residual (test hook)
     double * scal;                // device scalars
     unsigned long long * step_counter;
@@ -102,6 +106,7 @@ struct CflArgs {
 
 struct KernelTable {
     const char * name;
+    void (*faces)(const StageArgs &, cudaStream_t);
     void (*stage)(const StageArgs &, cudaStream_t);
     void (*recon)(const ReconArgs &, cudaStream_t);
     void (*cfl)(const CflArgs &, cudaStream_t);

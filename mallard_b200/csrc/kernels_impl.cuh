@@ -2,9 +2,11 @@
 // -fmad=false (every product and sum rounds separately, exactly as the reference's x86-64 build does) and into
 // namespace `fast` with FMA contraction enabled.  Summation orders follow the reference in both.
 //
-//   flux_stage_kernel   cell-centric, atomic-free residual gather fused with the RK stage update
-//                       (replaces K1 zero, K2 FirstOrder, K4 interior flux, K5-K9 boundary fluxes, K10 divide-by-volume,
-//                        K11 BLAS-1 stage combinations and K12 update_primitives of SURVEY §2.1)
+//   face_flux_kernel    one thread per face: quadrature loop over the Riemann flux of interior and boundary faces
+//                       (replaces K2 FirstOrder, K4 interior flux, K5-K9 boundary fluxes of SURVEY §2.1)
+//   gather_stage_kernel cell-centric, atomic-free residual gather fused with the RK stage update
+//                       (replaces K1 zero, the atomic scatter of K4-K9, K10 divide-by-volume, K11 BLAS-1 stage
+//                        combinations and K12 update_primitives)
 //   teno_recon_kernel   TENO reconstruction (K3): one thread per (cell, conserved variable), warp = one 8-cell table tile
 //   cfl_kernel          spectral radius + max reduction + dt (K13, K14)
 #include <cfloat>
@@ -23,13 +25,22 @@ namespace MLB_KNS {
 // ---------------------------------------------------------------------------------------------------------------
 // Physics — Euler::compute_primitives_from_conservatives_impl (physics/physics.h:852-867)
 // ---------------------------------------------------------------------------------------------------------------
+// FAST mode replaces repeated divisions by one reciprocal and multiplications (<= 2 ulp, inside the 1e-12 budget);
+// STRICT mode performs the reference's divisions.
+#ifdef MLB_STREAM_KERNELS
+#define MLB_DIV_BY(inv, den, x) ((x) * (inv))
+#else
+#define MLB_DIV_BY(inv, den, x) ((void)(inv), (x) / (den))
+#endif
+
 __device__ __forceinline__ void cons_to_prim(const GasParams & g, const double * U, double * P) {
     const double rho = U[0];
-    const double u0 = U[1] / rho, u1 = U[2] / rho;
-    const double E = U[3] / rho;
+    const double ir = 1.0 / rho;
+    const double u0 = MLB_DIV_BY(ir, rho, U[1]), u1 = MLB_DIV_BY(ir, rho, U[2]);
+    const double E = MLB_DIV_BY(ir, rho, U[3]);
     const double e = E - 0.5 * (u0 * u0 + u1 * u1);
     const double p = fmax(g.p_min, fmin(g.p_max, (g.gamma - 1.0) * rho * e));   // :842-845
-    P[0] = u0; P[1] = u1; P[2] = p; P[3] = e / g.cv; P[4] = e + p / rho;
+    P[0] = u0; P[1] = u1; P[2] = p; P[3] = e / g.cv; P[4] = e + MLB_DIV_BY(ir, rho, p);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -100,8 +111,9 @@ __device__ __forceinline__ void riemann_flux(double * F, double nx, double ny, c
 #pragma unroll
             for (int i = 0; i < 4; i++) F[i] = Fr[i];
         } else {
+            const double den = Sr - Sl, inv = 1.0 / den;
 #pragma unroll
-            for (int i = 0; i < 4; i++) F[i] = (Sr * Fl[i] - Sl * Fr[i] + Sl * Sr * (Ur[i] - Ul[i])) / (Sr - Sl);
+            for (int i = 0; i < 4; i++) F[i] = MLB_DIV_BY(inv, den, Sr * Fl[i] - Sl * Fr[i] + Sl * Sr * (Ur[i] - Ul[i]));
         }
         return;
     }
@@ -117,11 +129,13 @@ __device__ __forceinline__ void riemann_flux(double * F, double nx, double ny, c
         const double D[4] = {0.0, nx, ny, Ss};
         const double Plr = 0.5 * (L.p + R.p + L.rho * (Sl - uln) * (Ss - uln) + R.rho * (Sr - urn) * (Ss - urn));
         if (Ss >= 0.0) {
+            const double den = Sl - Ss, inv = 1.0 / den;
 #pragma unroll
-            for (int i = 0; i < 4; i++) F[i] = (Ss * (Sl * Ul[i] - Fl[i]) + Sl * Plr * D[i]) / (Sl - Ss);
+            for (int i = 0; i < 4; i++) F[i] = MLB_DIV_BY(inv, den, Ss * (Sl * Ul[i] - Fl[i]) + Sl * Plr * D[i]);
         } else {
+            const double den = Sr - Ss, inv = 1.0 / den;
 #pragma unroll
-            for (int i = 0; i < 4; i++) F[i] = (Ss * (Sr * Ur[i] - Fr[i]) + Sr * Plr * D[i]) / (Sr - Ss);
+            for (int i = 0; i < 4; i++) F[i] = MLB_DIV_BY(inv, den, Ss * (Sr * Ur[i] - Fr[i]) + Sr * Plr * D[i]);
         }
     }
 }
@@ -178,84 +192,89 @@ __device__ __forceinline__ void rk_update(const RkArgs & rk, const double * Uin,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Residual gather + RK update.  One thread per owned cell; every face flux is evaluated by both of its cells so that
-// no atomics are needed and each cell sums its faces in the reference's (Serial back-end) order.
+// Face fluxes.  One thread per face: quadrature loop over the Riemann flux (BaseFluxFunctor::call_impl,
+// numerics/flux_functor.h:124-162; boundary ghost states boundary/*.cpp), result A * (1/2 sum_q w_q F_q) stored once per
+// face.  The reference scatters -+ that product into both cells with atomic_add; here the cells gather it (next kernel).
 // ---------------------------------------------------------------------------------------------------------------
 template <int RS, bool TENO>
-__global__ void __launch_bounds__(128) flux_stage_kernel(const __grid_constant__ StageArgs a) {
+__global__ void __launch_bounds__(128) face_flux_kernel(const __grid_constant__ StageArgs a) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.g.NF) return;
+    const uint32_t Np = a.g.Npad;
+    const int Q = TENO ? a.g.Q : 1;
+    const uint32_t cl = a.g.face_cl[f];
+    const int32_t cr = a.g.face_cr[f];
+    double4 * out = reinterpret_cast<double4 *>(a.AF) + f;
+    if (cr == INT32_MIN) { *out = make_double4(0.0, 0.0, 0.0, 0.0); return; }   // boundary zone without a [[boundaries]] entry
+    const double nx = a.g.face_nx[f], ny = a.g.face_ny[f], area = a.g.face_area[f];
+    const uint32_t slots = TENO ? a.g.face_slots[f] : 0u;
+    const int sl = slots & 15u, sr = slots >> 4;
+    const BcParams * bc = cr < 0 ? &a.ph.bcs[-cr - 1] : nullptr;
+    double fsum[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int q = 0; q < Q; q++) {
+        double Ul[4], Pl[5];
+#pragma unroll
+        for (int v = 0; v < 4; v++) Ul[v] = TENO ? a.Fc[((size_t)(sl * Q + q) * 4 + v) * Np + cl] : a.Uin[(size_t)v * Np + cl];
+        cons_to_prim(a.ph.gas, Ul, Pl);
+        const FaceState L = {Ul[0], Pl[0], Pl[1], Pl[2], Pl[4]};
+        double ft[4];
+        if (cr >= 0) {
+            double Ur[4], Pr[5];
+#pragma unroll
+            for (int v = 0; v < 4; v++) Ur[v] = TENO ? a.Fc[((size_t)(sr * Q + q) * 4 + v) * Np + cr] : a.Uin[(size_t)v * Np + cr];
+            cons_to_prim(a.ph.gas, Ur, Pr);
+            const FaceState R = {Ur[0], Pr[0], Pr[1], Pr[2], Pr[4]};
+            riemann_flux<RS>(ft, nx, ny, L, R, a.ph.gas.gamma);
+        } else if (bc->type == MLB_BC_WALL_ADIABATIC) {   // boundary_wall_adiabatic.cpp:39-70
+            ft[0] = 0.0; ft[1] = Pl[2] * nx; ft[2] = Pl[2] * ny; ft[3] = 0.0;
+        } else {
+            FaceState gh;
+            ghost_state(*bc, a.ph.gas, nx, ny, Ul, Pl, gh);
+            riemann_flux<RS>(ft, nx, ny, L, gh, a.ph.gas.gamma);
+        }
+        const double wq = a.ph.qf_w[q];
+#pragma unroll
+        for (int v = 0; v < 4; v++) fsum[v] += wq * ft[v];     // flux_functor.h:151
+    }
+#pragma unroll
+    for (int v = 0; v < 4; v++) fsum[v] = area * (fsum[v] * 0.5);   // flux_functor.h:153,156-161: (-A)*F == -(A*F) exactly
+    *out = make_double4(fsum[0], fsum[1], fsum[2], fsum[3]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Residual gather + RK update.  One thread per owned cell, no atomics: each cell sums -+ the stored face products in
+// the reference's (Serial back-end) accumulation order, divides by its volume (DivideVolumeFunctor,
+// solver_rhs.cpp:18-42) and applies the stage combination; the last stage also refreshes the primitives.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_stage_kernel(const __grid_constant__ StageArgs a) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.g.N_owned) return;
     const uint32_t Np = a.g.Npad;
-    const int Q = TENO ? a.g.Q : 1;
     double k[4];
     if (a.k_override) {
 #pragma unroll
         for (int v = 0; v < 4; v++) k[v] = a.k_override[(size_t)v * Np + i];
     } else {
-        double Us[4], Ps[5];
-        if (!TENO) {
-#pragma unroll
-            for (int v = 0; v < 4; v++) Us[v] = a.Uin[(size_t)v * Np + i];
-            cons_to_prim(a.ph.gas, Us, Ps);
-        }
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         const uint32_t order = a.g.rhs_order[i];
         const int nf = a.g.nfc[i];
-        for (int jj = 0; jj < nf; jj++) {
-            const int s = (order >> (2 * jj)) & 3;
-            const int32_t nbr = a.g.slot_nbr[(size_t)s * Np + i];
-            if (nbr == INT32_MIN) continue;
-            const uint32_t fcode = a.g.slot_face[(size_t)s * Np + i];
-            const uint32_t f = fcode & 0x7FFFFFFFu, side = fcode >> 31;
-            const double nx = a.g.face_nx[f], ny = a.g.face_ny[f], area = a.g.face_area[f];
-            const int ns = TENO ? a.g.slot_nslot[(size_t)s * Np + i] : 0;
-            const BcParams * bc = nbr < 0 ? &a.ph.bcs[-nbr - 1] : nullptr;
-            double fsum[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int q = 0; q < Q; q++) {
-                double Uo[4], Po[5];   // this cell's side of the face
-                if (TENO) {
+        const double4 * AF = reinterpret_cast<const double4 *>(a.AF);
 #pragma unroll
-                    for (int v = 0; v < 4; v++) Uo[v] = a.Fc[((size_t)(s * Q + q) * 4 + v) * Np + i];
-                    cons_to_prim(a.ph.gas, Uo, Po);
-                } else {
-#pragma unroll
-                    for (int v = 0; v < 4; v++) Uo[v] = Us[v];
-#pragma unroll
-                    for (int v = 0; v < 5; v++) Po[v] = Ps[v];
+        for (int jj = 0; jj < MAX_SLOTS; jj++) {
+            if (jj < nf) {
+                const int s = (order >> (2 * jj)) & 3;
+                const int32_t nbr = a.g.slot_nbr[(size_t)s * Np + i];
+                if (nbr != INT32_MIN) {
+                    const uint32_t fcode = a.g.slot_face[(size_t)s * Np + i];
+                    const double4 P = AF[fcode & 0x7FFFFFFFu];
+                    if (fcode >> 31) { acc[0] += P.x; acc[1] += P.y; acc[2] += P.z; acc[3] += P.w; }
+                    else             { acc[0] -= P.x; acc[1] -= P.y; acc[2] -= P.z; acc[3] -= P.w; }
                 }
-                double ft[4];
-                const FaceState own = {Uo[0], Po[0], Po[1], Po[2], Po[4]};
-                if (nbr >= 0) {
-                    double Un[4], Pn[5];
-                    if (TENO) {
-#pragma unroll
-                        for (int v = 0; v < 4; v++) Un[v] = a.Fc[((size_t)(ns * Q + q) * 4 + v) * Np + nbr];
-                    } else {
-#pragma unroll
-                        for (int v = 0; v < 4; v++) Un[v] = a.Uin[(size_t)v * Np + nbr];
-                    }
-                    cons_to_prim(a.ph.gas, Un, Pn);
-                    const FaceState oth = {Un[0], Pn[0], Pn[1], Pn[2], Pn[4]};
-                    if (side == 0) riemann_flux<RS>(ft, nx, ny, own, oth, a.ph.gas.gamma);
-                    else riemann_flux<RS>(ft, nx, ny, oth, own, a.ph.gas.gamma);
-                } else if (bc->type == MLB_BC_WALL_ADIABATIC) {   // boundary_wall_adiabatic.cpp:39-70
-                    ft[0] = 0.0; ft[1] = Po[2] * nx; ft[2] = Po[2] * ny; ft[3] = 0.0;
-                } else {
-                    FaceState gh;
-                    ghost_state(*bc, a.ph.gas, nx, ny, Uo, Po, gh);
-                    riemann_flux<RS>(ft, nx, ny, own, gh, a.ph.gas.gamma);
-                }
-                const double wq = a.ph.qf_w[q];
-#pragma unroll
-                for (int v = 0; v < 4; v++) fsum[v] += wq * ft[v];     // flux_functor.h:151
             }
-            const double sgn_area = (side == 0) ? -area : area;         // flux_functor.h:156-161
-#pragma unroll
-            for (int v = 0; v < 4; v++) { fsum[v] *= 0.5; acc[v] += sgn_area * fsum[v]; }
         }
         const double vol = a.g.cell_vol[i];
 #pragma unroll
-        for (int v = 0; v < 4; v++) k[v] = acc[v] / vol;                 // DivideVolumeFunctor solver_rhs.cpp:18-42
+        for (int v = 0; v < 4; v++) k[v] = acc[v] / vol;
     }
     if (a.rk.k_store) {
 #pragma unroll
@@ -507,18 +526,22 @@ __global__ void prims_soa_kernel(const GasParams g, uint32_t n, uint32_t npad, c
 // Launchers
 // ---------------------------------------------------------------------------------------------------------------
 template <int RS>
-static void launch_stage_rs(const StageArgs & a, cudaStream_t st) {
-    const unsigned grid = (a.g.N_owned + 127u) / 128u;
+static void launch_faces_rs(const StageArgs & a, cudaStream_t st) {
+    const unsigned grid = (a.g.NF + 127u) / 128u;
     if (grid == 0) return;
-    if (a.teno) flux_stage_kernel<RS, true><<<grid, 128, 0, st>>>(a);
-    else flux_stage_kernel<RS, false><<<grid, 128, 0, st>>>(a);
+    if (a.teno) face_flux_kernel<RS, true><<<grid, 128, 0, st>>>(a);
+    else face_flux_kernel<RS, false><<<grid, 128, 0, st>>>(a);
+}
+static void launch_faces(const StageArgs & a, cudaStream_t st) {
+    switch (a.ph.riemann) {
+        case MLB_RIEMANN_RUSANOV: launch_faces_rs<MLB_RIEMANN_RUSANOV>(a, st); break;
+        case MLB_RIEMANN_HLL: launch_faces_rs<MLB_RIEMANN_HLL>(a, st); break;
+        default: launch_faces_rs<MLB_RIEMANN_HLLC>(a, st); break;
+    }
 }
 static void launch_stage(const StageArgs & a, cudaStream_t st) {
-    switch (a.ph.riemann) {
-        case MLB_RIEMANN_RUSANOV: launch_stage_rs<MLB_RIEMANN_RUSANOV>(a, st); break;
-        case MLB_RIEMANN_HLL: launch_stage_rs<MLB_RIEMANN_HLL>(a, st); break;
-        default: launch_stage_rs<MLB_RIEMANN_HLLC>(a, st); break;
-    }
+    const unsigned grid = (a.g.N_owned + 255u) / 256u;
+    if (grid) gather_stage_kernel<<<grid, 256, 0, st>>>(a);
 }
 
 template <int ORDER, int MP>
@@ -572,10 +595,10 @@ static void launch_prims_soa(const GasParams & g, uint32_t n, uint32_t npad, con
 #define MLB_STR2(x) #x
 #define MLB_STR(x) MLB_STR2(x)
 #ifdef MLB_STREAM_KERNELS
-static const KernelTable table = {MLB_STR(MLB_KNS), launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
+static const KernelTable table = {MLB_STR(MLB_KNS), launch_faces, launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
                                   launch_prims_soa, recon_supported, stream::launch_stream, stream::stream_supported};
 #else
-static const KernelTable table = {MLB_STR(MLB_KNS), launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
+static const KernelTable table = {MLB_STR(MLB_KNS), launch_faces, launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
                                   launch_prims_soa, recon_supported, nullptr, nullptr};
 #endif
 

@@ -56,7 +56,7 @@ constexpr int TILE = 8;         // cells per interleaved TENO table tile (one wa
 constexpr int FAST_CT = 32;
 constexpr int FAST_S = 4;
 constexpr int fast_rows_per_chunk(int order) { return order == 1 ? 2 : order == 2 ? 5 : order == 3 ? 3 : 2; }
-constexpr int fast_stages(int order) { return order == 1 ? 8 : 6; }
+constexpr int fast_stages(int /*order*/) { return 4; }
 
 struct TenoTables {
     int basis = 1, order = 0, K = 0, M = 0, Mp = 0, S = 0;   // Mp = M padded to even, S = stencil slots per cell (1 + max faces)
@@ -107,6 +107,9 @@ struct Prep {
     dvec cell_xy;          // [2][Npad]
     dvec face_nx, face_ny, face_area;   // [NFpad] unit normal (common_math.h:101-106) and area
     dvec slot_fx;          // TENO: [n_slots][4][Npad] face end points in the cell's reference coordinates
+    uvec face_cl;          // [NFpad] library cell on side 0 of the face
+    ivec face_cr;          // [NFpad] library cell on side 1 ; < 0: -(bc index + 1) ; INT32_MIN: no flux through this face
+    std::vector<uint8_t> face_slots;   // [NFpad] slot in cell 0 | slot in cell 1 << 4
     dvec qf_x, qf_w;       // face quadrature
     TenoTables teno;
     double seconds = 0.0;

@@ -67,12 +67,39 @@ __device__ __forceinline__ void bulk_g2s(void * dst, const void * src, uint32_t 
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 
+__device__ __forceinline__ uint32_t mbar_test(uint64_t * bar, uint32_t parity) {   // non-blocking probe
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred P1;\n\t"
+                 "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, P1;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __forceinline__ void cp_async8(void * dst, const void * src) {                    // LDGSTS: no register staging
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int ORDER> struct Smem {
+    using C = Cfg<ORDER>;
+    static constexpr int UB_ROWS = C::MC + 1;                                   // gathered neighbour values + the cell's own
+    static constexpr size_t RING = (size_t)fast_stages(ORDER) * C::CHUNK_BYTES;
+    static constexpr size_t UBUF = (size_t)2 * UB_ROWS * CONSUMERS * 8;         // double-buffered over stencils
+    static constexpr size_t FXBUF = (size_t)2 * 13 * CT * 8;                    // face end points (12) + area_t[0], per tile parity
+    static constexpr size_t TOTAL = RING + UBUF + FXBUF;
+};
+
 template <int ORDER, int STAGES>
 __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_constant__ ReconStreamArgs a) {
     using C = Cfg<ORDER>;
-    constexpr int K = C::K, KR = C::KR, MC = C::MC, NP = C::NP, Q = C::Q, S = FAST_S;
-    extern __shared__ __align__(128) unsigned char ring[];   // STAGES x CHUNK_BYTES
+    using SM = Smem<ORDER>;
+    constexpr int K = C::K, KR = C::KR, MC = C::MC, NP = C::NP, Q = C::Q, S = FAST_S, NF = FAST_S - 1;
+    constexpr int CPT = S * C::NCH;                            // chunks per tile
+    extern __shared__ __align__(128) unsigned char smem[];     // ring | ubuf | fxbuf
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
+    unsigned char * ring = smem;
+    double * ubuf = reinterpret_cast<double *>(smem + SM::RING);
+    double * fxbuf = reinterpret_cast<double *>(smem + SM::RING + SM::UBUF);
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -89,8 +116,8 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
             uint32_t g = 0;
             for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const unsigned char * src = reinterpret_cast<const unsigned char *>(a.mat) + (size_t)tile * (S * C::NCH) * C::CHUNK_BYTES;
-                for (int ch = 0; ch < S * C::NCH; ch++, g++) {
+                const unsigned char * src = reinterpret_cast<const unsigned char *>(a.mat) + (size_t)tile * CPT * C::CHUNK_BYTES;
+                for (int ch = 0; ch < CPT; ch++, g++) {
                     const uint32_t st = g % STAGES, use = g / STAGES;
                     mbar_wait(&empty_bar[st], (use & 1u) ^ 1u);      // first use of a stage passes immediately
                     mbar_expect_tx(&full_bar[st], C::CHUNK_BYTES);
@@ -102,34 +129,109 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
     }
 
     // ---------------- consumers ----------------
+    // Everything a consumer reads from global memory is requested one stencil ahead with cp.async (LDGSTS, no register
+    // staging) into per-thread shared-memory slots, so that no warp ever sits on a global-load scoreboard:
+    //   ubuf[parity of s][m][tid]   neighbour values of the stencil's cells (+ the cell's own value, row MC, for s = 0)
+    //   fxbuf[parity of tile][i][cell]   face end points and area_t[0] of the tile (loaded by the cell's 4 variable-threads)
     const int cl = tid >> 2, var = tid & 3;
     const uint32_t Np = a.g.Npad;
     const double * __restrict__ Uv = a.Uin + (size_t)var * Np;
-    uint32_t g = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t cell = tile * CT + cl;
-        const bool live = cell < a.g.N_recon;
-        const double u_self = live ? Uv[cell] : 0.0;
+    uint32_t tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+
+    auto prefetch_tile_geometry = [&](uint32_t t, uint32_t parity) {
+        const uint32_t cell = t * CT + cl;
+        if (cell >= a.g.N_recon) return;
+        double * dst = fxbuf + (size_t)parity * 13 * CT + cl;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {                                 // value index var + 4 i of the 12 (slot j, component)
+            const int v = var + 4 * i;
+            cp_async8(dst + v * CT, a.g.slot_fx + (size_t)v * Np + cell);
+        }
+        if (var == 0) cp_async8(dst + 12 * CT, a.area0 + cell);
+    };
+
+    uint32_t id[MC];                                                  // ids of the NEXT stencil to be gathered
+    bool empty_cur;                                                   // is the stencil whose values are in flight empty?
+    {
         const uint32_t * __restrict__ ids = a.ids + (size_t)tile * (S * MC * CT) + cl;
-        double dof[S][KR];
-        double w[S];
-        uint32_t id[MC];
 #pragma unroll
         for (int m = 0; m < MC; m++) id[m] = ids[m * CT];
+        empty_cur = id[0] == NO_FACE;
+        double * dst = ubuf + tid;
+        if (!empty_cur) {
+#pragma unroll
+            for (int m = 0; m < MC; m++) cp_async8(dst + m * CONSUMERS, Uv + id[m]);
+        }
+        if (tile * CT + cl < a.g.N_recon) cp_async8(dst + MC * CONSUMERS, Uv + tile * CT + cl);
+        prefetch_tile_geometry(tile, 0);
+        cp_async_commit();
+#pragma unroll
+        for (int m = 0; m < MC; m++) id[m] = ids[(MC + m) * CT];
+    }
+
+    uint32_t ready = 0;
+    for (uint32_t it = 0; tile < n_tiles; it++) {
+        const uint32_t next = tile + gridDim.x;
+        const bool has_next = next < n_tiles;
+        const uint32_t cell = tile * CT + cl;
+        const bool live = cell < a.g.N_recon;
+        double u_self = 0.0;
+        double dof[S][KR];
+        double w[S];
 #pragma unroll
         for (int s = 0; s < S; s++) {
-            const bool empty = !live || id[0] == NO_FACE;            // empty stencil (:896-899) or padding cell
+            // 1. the gathers of this stencil were issued one stencil ago
+            cp_async_wait_all();
+            const double * ub = ubuf + (size_t)(s & 1) * SM::UB_ROWS * CONSUMERS + tid;
+            if (s == 0) u_self = live ? ub[MC * CONSUMERS] : 0.0;
+            const bool empty = empty_cur;                             // empty stencil (:896-899) or padding cell
             double b[MC];
 #pragma unroll
-            for (int m = 0; m < MC; m++) b[m] = empty ? 0.0 : Uv[id[m]] - u_self;
-            if (s + 1 < S) {                                          // ids of the next stencil travel while this one computes
+            for (int m = 0; m < MC; m++) b[m] = empty ? 0.0 : ub[m * CONSUMERS] - u_self;
+            // 2. request the next stencil's values (the next tile's first stencil after the last one of this tile); its
+            //    ids were loaded one stencil ago
+            empty_cur = id[0] == NO_FACE;
+            if (s + 1 < S || has_next) {
+                double * dst = ubuf + (size_t)((s + 1) & 1) * SM::UB_ROWS * CONSUMERS + tid;
+                if (!empty_cur) {
 #pragma unroll
-                for (int m = 0; m < MC; m++) id[m] = ids[((s + 1) * MC + m) * CT];
+                    for (int m = 0; m < MC; m++) cp_async8(dst + m * CONSUMERS, Uv + id[m]);
+                }
+                if (s + 1 == S) {
+                    if (next * CT + cl < a.g.N_recon) cp_async8(dst + MC * CONSUMERS, Uv + next * CT + cl);
+                    prefetch_tile_geometry(next, (it + 1) & 1);
+                }
             }
+            cp_async_commit();
+            // 3. ids of the stencil after that (plain loads: they have a whole stencil's compute to arrive)
+            {
+                const bool in_tile = s + 2 < S;
+                const uint32_t t2 = in_tile ? tile : next;
+                const int s2 = in_tile ? s + 2 : s + 2 - S;
+                if (in_tile || has_next) {
+                    const uint32_t * __restrict__ ids2 = a.ids + ((size_t)t2 * S + s2) * (MC * CT) + cl;
 #pragma unroll
-            for (int ch = 0; ch < C::NCH; ch++, g++) {
-                const uint32_t st = g % STAGES, use = g / STAGES;
-                mbar_wait(&full_bar[st], use & 1u);
+                    for (int m = 0; m < MC; m++) id[m] = ids2[m * CT];
+                } else {
+#pragma unroll
+                    for (int m = 0; m < MC; m++) id[m] = NO_FACE;
+                }
+            }
+            // 4. dofs a_k = sum_m A'[k][m] b[m], rows arriving chunk by chunk through the ring
+#pragma unroll
+            for (int ch = 0; ch < C::NCH; ch++) {
+                const int pos = s * C::NCH + ch;
+                uint32_t st, use;
+                if (CPT % STAGES == 0) { st = pos % STAGES; use = it * (CPT / STAGES) + pos / STAGES; }
+                else { const uint32_t g = it * CPT + pos; st = g % STAGES; use = g / STAGES; }
+                if (!ready) mbar_wait(&full_bar[st], use & 1u);
+                {   // probe the next chunk's barrier now; the answer is needed only after this chunk's arithmetic
+                    uint32_t st2, use2;
+                    if (CPT % STAGES == 0) { st2 = (pos + 1) % STAGES; use2 = it * (CPT / STAGES) + (pos + 1) / STAGES; }
+                    else { const uint32_t g2 = it * CPT + pos + 1; st2 = g2 % STAGES; use2 = g2 / STAGES; }
+                    ready = mbar_test(&full_bar[st2], use2 & 1u);
+                }
                 const unsigned char * base = ring + (size_t)st * C::CHUNK_BYTES + cl * 16;
 #pragma unroll
                 for (int r = 0; r < C::RC; r++) {
@@ -162,10 +264,9 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
             const double x2 = x * x, x3 = x2 * x;
             w[s] = empty ? 0.0 : 1.0 / (x3 * x3);
         }
-        if (!live) continue;
 
-        // non-linear weights :948-981 (reference-faithful unless fixed_weights)
-        {
+        if (live) {
+            // non-linear weights :948-981 (reference-faithful unless fixed_weights)
             double sd = 0.0;
 #pragma unroll
             for (int s = 1; s < S; s++) sd += w[s];
@@ -198,29 +299,35 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
                 for (int k = 0; k < KR; k++) c[k] = fma(w[s], dof[s][k], c[k]);
             }
         }
-        const double area0 = a.area0[cell];
-        double cb = 0.0;                                              // sum_k c_k psi_bar_k / area_t[0]  (:1028-1029)
-        const double cscale = a.fixed_weights ? -1.0 : 1.0 / area0;
+        // the tile's geometry was requested a whole tile ago by the cell's four variable-threads (same warp) and waited
+        // for at the top of stencil 0; the __syncwarp()s of the chunk loop made it visible to the other lanes
+        __syncwarp();
+        if (live) {
+            const double * fx = fxbuf + (size_t)(it & 1) * 13 * CT + cl;
+            const double area0 = fx[12 * CT];
+            double cb = 0.0;                                          // sum_k c_k psi_bar_k / area_t[0]  (:1028-1029)
+            const double cscale = a.fixed_weights ? -1.0 : 1.0 / area0;
 #pragma unroll
-        for (int k = 0; k < KR; k++) cb = fma(c[k], a.psi_bar[k + 1] * cscale, cb);
-
-        const int nf = a.g.nfc[cell];
-        for (int j = 0; j < nf; j++) {                                // :985-1034
-            const double * fx = a.g.slot_fx + ((size_t)j * 4) * Np + cell;
-            const double x0 = fx[0], y0 = fx[Np], x1 = fx[2 * (size_t)Np], y1 = fx[3 * (size_t)Np];
+            for (int k = 0; k < KR; k++) cb = fma(c[k], a.psi_bar[k + 1] * cscale, cb);
 #pragma unroll
-            for (int q = 0; q < Q; q++) {
-                const double tq = (a.qf_x[q] + 1.0) * 0.5;
-                const double xq = tq * (x1 - x0) + x0, yq = tq * (y1 - y0) + y0;
-                double Px[ORDER + 1], Py[ORDER + 1];
-                legendre_values<ORDER>(xq, Px);
-                legendre_values<ORDER>(yq, Py);
-                double out = u_self + cb;
+            for (int j = 0; j < NF; j++) {                            // :985-1034 (triangles: always three faces)
+                const double x0 = fx[(4 * j) * CT], y0 = fx[(4 * j + 1) * CT], x1 = fx[(4 * j + 2) * CT], y1 = fx[(4 * j + 3) * CT];
 #pragma unroll
-                for (int k = 0; k < KR; k++) out = fma(c[k], Px[dof_ex(k + 1)] * Py[dof_ey(k + 1)], out);
-                a.Fc[((size_t)(j * Q + q) * 4 + var) * Np + cell] = out;
+                for (int q = 0; q < Q; q++) {
+                    const double tq = (a.qf_x[q] + 1.0) * 0.5;
+                    const double xq = tq * (x1 - x0) + x0, yq = tq * (y1 - y0) + y0;
+                    double Px[ORDER + 1], Py[ORDER + 1];
+                    legendre_values<ORDER>(xq, Px);
+                    legendre_values<ORDER>(yq, Py);
+                    double out = u_self + cb;
+#pragma unroll
+                    for (int k = 0; k < KR; k++) out = fma(c[k], Px[dof_ex(k + 1)] * Py[dof_ey(k + 1)], out);
+                    a.Fc[((size_t)(j * Q + q) * 4 + var) * Np + cell] = out;
+                }
             }
         }
+        __syncwarp();   // fxbuf[it & 1] is rewritten (by other lanes of this warp) two tiles from now at the earliest
+        tile = next;
     }
 }
 
@@ -228,7 +335,7 @@ template <int ORDER>
 static void launch_stream_t(const ReconStreamArgs & a, cudaStream_t st) {
     using C = Cfg<ORDER>;
     constexpr int STAGES = fast_stages(ORDER);
-    const size_t smem = (size_t)STAGES * C::CHUNK_BYTES;
+    const size_t smem = Smem<ORDER>::TOTAL;
     static int ctas = 0;
     if (!ctas) {
         cudaFuncSetAttribute(teno_stream_kernel<ORDER, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
