@@ -12,6 +12,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <utility>
 
 #include "kernel_args.h"
 
@@ -317,6 +318,14 @@ constexpr int RECON_THREADS = 128;
 __host__ __device__ constexpr int dof_ey(int k) { int p = 0; while (k > p) { k -= p + 1; p++; } return k; }
 __host__ __device__ constexpr int dof_ex(int k) { int p = 0; while (k > p) { k -= p + 1; p++; } return p - k; }
 
+// out += w * dof_k * (psi_k(x, y) + cbar_k) for k = 0..K-1 in order (:1021-1030), exponents resolved at compile time
+template <int K, int... Ks>
+__device__ __forceinline__ double poly_accumulate(double out, double w, const double * dof_sm_tid, const double * Px, const double * Py,
+                                                  const double * cbar, std::integer_sequence<int, Ks...>) {
+    ((out += w * dof_sm_tid[Ks * RECON_THREADS] * (Px[std::integral_constant<int, dof_ex(Ks)>::value] * Py[std::integral_constant<int, dof_ey(Ks)>::value] + cbar[Ks])), ...);
+    return out;
+}
+
 template <int ORDER, int MP>
 __global__ void __launch_bounds__(RECON_THREADS) teno_recon_kernel(const __grid_constant__ ReconArgs a) {
     constexpr int K = (ORDER + 1) * (ORDER + 2) / 2;
@@ -413,9 +422,7 @@ __global__ void __launch_bounds__(RECON_THREADS) teno_recon_kernel(const __grid_
 #pragma unroll 1
             for (int s = 0; s < S; s++) {
                 if (w[s] == 0.0) continue;
-#pragma unroll
-                for (int k = 0; k < K; k++)
-                    out += w[s] * dof_sm[(s * K + k) * RECON_THREADS + tid] * (Px[dof_ex(k)] * Py[dof_ey(k)] + cbar[k]);
+                out = poly_accumulate<K>(out, w[s], dof_sm + (size_t)(s * K) * RECON_THREADS + tid, Px, Py, cbar, std::make_integer_sequence<int, K>{});
             }
             a.Fc[((size_t)(j * Q + q) * 4 + var) * Np + cell] = out;
         }

@@ -21,6 +21,7 @@
 //   Results differ from the reference by rounding only (<= 1e-12 relative per step, asserted in tests/test_gpu_parity.py);
 //   the bit-faithful variant is teno_recon_kernel in STRICT mode.
 #pragma once
+#include <utility>
 
 namespace stream {
 
@@ -80,20 +81,34 @@ __device__ __forceinline__ void cp_async8(void * dst, const void * src) {       
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int ORDER> struct Smem {
+// Sum_k c[k] psi_k(x, y) over the stored dofs k = 1..K-1 with the exponents resolved at compile time (a run-time
+// dof_ex()/dof_ey() would index Px/Py dynamically and push them into local memory).
+template <int... Ks>
+__device__ __forceinline__ double poly_sum(const double * c, const double * Px, const double * Py, double out, std::integer_sequence<int, Ks...>) {
+    ((out = fma(c[Ks], Px[std::integral_constant<int, dof_ex(Ks + 1)>::value] * Py[std::integral_constant<int, dof_ey(Ks + 1)>::value], out)), ...);
+    return out;
+}
+
+constexpr int FX_ROWS = 17;   // per tile and cell: 12 face end-point coordinates, area_t[0], the cell's 4 conserved values
+
+template <int ORDER, bool ASYNC> struct Smem {
     using C = Cfg<ORDER>;
-    static constexpr int UB_ROWS = C::MC + 1;                                   // gathered neighbour values + the cell's own
-    static constexpr size_t RING = (size_t)fast_stages(ORDER) * C::CHUNK_BYTES;
-    static constexpr size_t UBUF = (size_t)2 * UB_ROWS * CONSUMERS * 8;         // double-buffered over stencils
-    static constexpr size_t FXBUF = (size_t)2 * 13 * CT * 8;                    // face end points (12) + area_t[0], per tile parity
+    static constexpr int STAGES = ASYNC ? 4 : (ORDER == 4 ? 6 : 7);
+    static constexpr size_t RING = (size_t)STAGES * C::CHUNK_BYTES;
+    static constexpr size_t UBUF = ASYNC ? (size_t)2 * C::MC * CONSUMERS * 8 : 0;   // gathered neighbour values, double-buffered over stencils
+    static constexpr size_t FXBUF = (size_t)2 * FX_ROWS * CT * 8;                  // per tile parity
     static constexpr size_t TOTAL = RING + UBUF + FXBUF;
 };
 
-template <int ORDER, int STAGES>
+// ASYNC = true : neighbour values are requested one stencil ahead with cp.async (LDGSTS, no register staging) into
+//                per-thread shared-memory slots; 4 ring stages.
+// ASYNC = false: neighbour values are loaded into registers at the top of each stencil (one exposed L1/L2 latency per
+//                stencil, covered by the other resident warps); the shared memory saved buys a 7-stage ring.
+template <int ORDER, bool ASYNC>
 __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_constant__ ReconStreamArgs a) {
     using C = Cfg<ORDER>;
-    using SM = Smem<ORDER>;
-    constexpr int K = C::K, KR = C::KR, MC = C::MC, NP = C::NP, Q = C::Q, S = FAST_S, NF = FAST_S - 1;
+    using SM = Smem<ORDER, ASYNC>;
+    constexpr int K = C::K, KR = C::KR, MC = C::MC, NP = C::NP, Q = C::Q, S = FAST_S, NF = FAST_S - 1, STAGES = SM::STAGES;
     constexpr int CPT = S * C::NCH;                            // chunks per tile
     extern __shared__ __align__(128) unsigned char smem[];     // ring | ubuf | fxbuf
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
@@ -129,45 +144,47 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
     }
 
     // ---------------- consumers ----------------
-    // Everything a consumer reads from global memory is requested one stencil ahead with cp.async (LDGSTS, no register
-    // staging) into per-thread shared-memory slots, so that no warp ever sits on a global-load scoreboard:
-    //   ubuf[parity of s][m][tid]   neighbour values of the stencil's cells (+ the cell's own value, row MC, for s = 0)
-    //   fxbuf[parity of tile][i][cell]   face end points and area_t[0] of the tile (loaded by the cell's 4 variable-threads)
+    //   fxbuf[parity of tile][row][cell]   face end points, area_t[0] and the cell's own state, requested a tile ahead with
+    //                                      cp.async by the cell's four variable-threads (same warp)
+    //   ubuf[parity of s][m][tid]          (ASYNC) neighbour values of the stencil's cells, requested a stencil ahead
     const int cl = tid >> 2, var = tid & 3;
     const uint32_t Np = a.g.Npad;
     const double * __restrict__ Uv = a.Uin + (size_t)var * Np;
     uint32_t tile = blockIdx.x;
     if (tile >= n_tiles) return;
 
-    auto prefetch_tile_geometry = [&](uint32_t t, uint32_t parity) {
+    auto prefetch_tile = [&](uint32_t t, uint32_t parity) {
         const uint32_t cell = t * CT + cl;
         if (cell >= a.g.N_recon) return;
-        double * dst = fxbuf + (size_t)parity * 13 * CT + cl;
+        double * dst = fxbuf + (size_t)parity * FX_ROWS * CT + cl;
 #pragma unroll
         for (int i = 0; i < 3; i++) {                                 // value index var + 4 i of the 12 (slot j, component)
             const int v = var + 4 * i;
             cp_async8(dst + v * CT, a.g.slot_fx + (size_t)v * Np + cell);
         }
         if (var == 0) cp_async8(dst + 12 * CT, a.area0 + cell);
+        cp_async8(dst + (13 + var) * CT, Uv + cell);
     };
 
-    uint32_t id[MC];                                                  // ids of the NEXT stencil to be gathered
-    bool empty_cur;                                                   // is the stencil whose values are in flight empty?
+    uint32_t id[MC];   // ASYNC: ids of the stencil to be requested next; otherwise ids of the stencil about to be gathered
+    bool empty_cur = false;
     {
         const uint32_t * __restrict__ ids = a.ids + (size_t)tile * (S * MC * CT) + cl;
 #pragma unroll
         for (int m = 0; m < MC; m++) id[m] = ids[m * CT];
-        empty_cur = id[0] == NO_FACE;
-        double * dst = ubuf + tid;
-        if (!empty_cur) {
+        prefetch_tile(tile, 0);
+        if (ASYNC) {
+            empty_cur = id[0] == NO_FACE;
+            if (!empty_cur) {
 #pragma unroll
-            for (int m = 0; m < MC; m++) cp_async8(dst + m * CONSUMERS, Uv + id[m]);
+                for (int m = 0; m < MC; m++) cp_async8(ubuf + tid + m * CONSUMERS, Uv + id[m]);
+            }
         }
-        if (tile * CT + cl < a.g.N_recon) cp_async8(dst + MC * CONSUMERS, Uv + tile * CT + cl);
-        prefetch_tile_geometry(tile, 0);
         cp_async_commit();
+        if (ASYNC) {
 #pragma unroll
-        for (int m = 0; m < MC; m++) id[m] = ids[(MC + m) * CT];
+            for (int m = 0; m < MC; m++) id[m] = ids[(MC + m) * CT];
+        }
     }
 
     uint32_t ready = 0;
@@ -176,39 +193,45 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
         const bool has_next = next < n_tiles;
         const uint32_t cell = tile * CT + cl;
         const bool live = cell < a.g.N_recon;
+        const double * fx = fxbuf + (size_t)(it & 1) * FX_ROWS * CT + cl;
         double u_self = 0.0;
         double dof[S][KR];
         double w[S];
 #pragma unroll
         for (int s = 0; s < S; s++) {
-            // 1. the gathers of this stencil were issued one stencil ago
-            cp_async_wait_all();
-            const double * ub = ubuf + (size_t)(s & 1) * SM::UB_ROWS * CONSUMERS + tid;
-            if (s == 0) u_self = live ? ub[MC * CONSUMERS] : 0.0;
-            const bool empty = empty_cur;                             // empty stencil (:896-899) or padding cell
+            // 1. right-hand side b[m] = U[nbr m] - U[cell]
+            bool empty;
             double b[MC];
+            if (ASYNC) {
+                cp_async_wait_all();                                  // requested one stencil (tile data: one tile) ago
+                if (s == 0) u_self = live ? fx[(13 + var) * CT] : 0.0;
+                empty = empty_cur;                                    // empty stencil (:896-899) or padding cell
+                const double * ub = ubuf + (size_t)(s & 1) * MC * CONSUMERS + tid;
 #pragma unroll
-            for (int m = 0; m < MC; m++) b[m] = empty ? 0.0 : ub[m * CONSUMERS] - u_self;
-            // 2. request the next stencil's values (the next tile's first stencil after the last one of this tile); its
-            //    ids were loaded one stencil ago
-            empty_cur = id[0] == NO_FACE;
-            if (s + 1 < S || has_next) {
-                double * dst = ubuf + (size_t)((s + 1) & 1) * SM::UB_ROWS * CONSUMERS + tid;
-                if (!empty_cur) {
+                for (int m = 0; m < MC; m++) b[m] = empty ? 0.0 : ub[m * CONSUMERS] - u_self;
+            } else {
+                if (s == 0) { cp_async_wait_all(); u_self = live ? fx[(13 + var) * CT] : 0.0; }
+                empty = id[0] == NO_FACE;
+#pragma unroll
+                for (int m = 0; m < MC; m++) b[m] = empty ? 0.0 : Uv[id[m]] - u_self;
+            }
+            // 2. requests for what comes next (the next tile's first stencil after the last one of this tile)
+            if (ASYNC) {
+                empty_cur = id[0] == NO_FACE;                         // id[]: the next stencil's, loaded one stencil ago
+                if ((s + 1 < S || has_next) && !empty_cur) {
+                    double * dst = ubuf + (size_t)((s + 1) & 1) * MC * CONSUMERS + tid;
 #pragma unroll
                     for (int m = 0; m < MC; m++) cp_async8(dst + m * CONSUMERS, Uv + id[m]);
                 }
-                if (s + 1 == S) {
-                    if (next * CT + cl < a.g.N_recon) cp_async8(dst + MC * CONSUMERS, Uv + next * CT + cl);
-                    prefetch_tile_geometry(next, (it + 1) & 1);
-                }
             }
-            cp_async_commit();
-            // 3. ids of the stencil after that (plain loads: they have a whole stencil's compute to arrive)
+            if (s + 1 == S && has_next) prefetch_tile(next, (it + 1) & 1);
+            if (ASYNC || s + 1 == S) cp_async_commit();
+            // 3. ids (plain coalesced loads; consumed a stencil later): ASYNC two stencils ahead, otherwise one
             {
-                const bool in_tile = s + 2 < S;
+                constexpr int ahead = ASYNC ? 2 : 1;
+                const bool in_tile = s + ahead < S;
                 const uint32_t t2 = in_tile ? tile : next;
-                const int s2 = in_tile ? s + 2 : s + 2 - S;
+                const int s2 = in_tile ? s + ahead : s + ahead - S;
                 if (in_tile || has_next) {
                     const uint32_t * __restrict__ ids2 = a.ids + ((size_t)t2 * S + s2) * (MC * CT) + cl;
 #pragma unroll
@@ -283,8 +306,9 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
                 sd = 0.0;
 #pragma unroll
                 for (int s = 1; s < S; s++) sd += w[s];
+                const double isd = 1.0 / sd;
 #pragma unroll
-                for (int s = 1; s < S; s++) w[s] /= sd;
+                for (int s = 1; s < S; s++) w[s] *= isd;
                 if (a.fixed_weights) w[0] = 0.0;
             }
         }
@@ -299,11 +323,9 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
                 for (int k = 0; k < KR; k++) c[k] = fma(w[s], dof[s][k], c[k]);
             }
         }
-        // the tile's geometry was requested a whole tile ago by the cell's four variable-threads (same warp) and waited
-        // for at the top of stencil 0; the __syncwarp()s of the chunk loop made it visible to the other lanes
-        __syncwarp();
+        // the tile's geometry was waited for at the top of stencil 0; the __syncwarp()s of the chunk loop made the other
+        // lanes' copies visible
         if (live) {
-            const double * fx = fxbuf + (size_t)(it & 1) * 13 * CT + cl;
             const double area0 = fx[12 * CT];
             double cb = 0.0;                                          // sum_k c_k psi_bar_k / area_t[0]  (:1028-1029)
             const double cscale = a.fixed_weights ? -1.0 : 1.0 / area0;
@@ -319,10 +341,7 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
                     double Px[ORDER + 1], Py[ORDER + 1];
                     legendre_values<ORDER>(xq, Px);
                     legendre_values<ORDER>(yq, Py);
-                    double out = u_self + cb;
-#pragma unroll
-                    for (int k = 0; k < KR; k++) out = fma(c[k], Px[dof_ex(k + 1)] * Py[dof_ey(k + 1)], out);
-                    a.Fc[((size_t)(j * Q + q) * 4 + var) * Np + cell] = out;
+                    a.Fc[((size_t)(j * Q + q) * 4 + var) * Np + cell] = poly_sum(c, Px, Py, u_self + cb, std::make_integer_sequence<int, KR>{});
                 }
             }
         }
@@ -331,23 +350,25 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
     }
 }
 
-template <int ORDER>
-static void launch_stream_t(const ReconStreamArgs & a, cudaStream_t st) {
-    using C = Cfg<ORDER>;
-    constexpr int STAGES = fast_stages(ORDER);
-    const size_t smem = Smem<ORDER>::TOTAL;
+template <int ORDER, bool ASYNC>
+static void launch_stream_v(const ReconStreamArgs & a, cudaStream_t st) {
+    const size_t smem = Smem<ORDER, ASYNC>::TOTAL;
     static int ctas = 0;
     if (!ctas) {
-        cudaFuncSetAttribute(teno_stream_kernel<ORDER, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(teno_stream_kernel<ORDER, ASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, teno_stream_kernel<ORDER, STAGES>, THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, teno_stream_kernel<ORDER, ASYNC>, THREADS, smem);
         ctas = sms * (per_sm > 0 ? per_sm : 1);
     }
     if (!a.n_tiles) return;
     const unsigned grid = a.n_tiles < (uint32_t)ctas ? a.n_tiles : (unsigned)ctas;   // persistent: one CTA slot per resident CTA
-    teno_stream_kernel<ORDER, STAGES><<<grid, THREADS, smem, st>>>(a);
+    teno_stream_kernel<ORDER, ASYNC><<<grid, THREADS, smem, st>>>(a);
+}
+template <int ORDER>
+static void launch_stream_t(const ReconStreamArgs & a, cudaStream_t st) {
+    if (a.async_gather) launch_stream_v<ORDER, true>(a, st); else launch_stream_v<ORDER, false>(a, st);
 }
 
 static bool stream_supported(int order, int M, int Q, int basis, int n_slots) {
