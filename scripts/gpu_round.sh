@@ -10,8 +10,8 @@ tail -5 gpurun_out/pytest_gpu.log
 if [ "${BENCH:-1}" = 1 ]; then
 $T 600 python bench.py --steps 20 --warmup 3 ${BENCH_ARGS:-} > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-MLB_STREAM_GATHER=async $T 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e ${BENCH_ARGS:-} > gpurun_out/bench_async.json 2> gpurun_out/bench_async.err; echo "bench async-gather rc=$?"
-tail -c 700 gpurun_out/bench_async.json
+MLB_STREAM_GATHER=direct $T 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e ${BENCH_ARGS:-} > gpurun_out/bench_direct.json 2> gpurun_out/bench_direct.err; echo "bench direct-gather rc=$?"
+tail -c 700 gpurun_out/bench_direct.json
 if [ "${STRICT:-1}" = 1 ]; then
 $T 600 python bench.py --steps 20 --warmup 3 --fp strict --no-cpu-baseline ${BENCH_ARGS:-} > gpurun_out/bench_strict.json 2> gpurun_out/bench_strict.err; echo "bench strict rc=$?"
 tail -c 1000 gpurun_out/bench_strict.json
