@@ -22,7 +22,8 @@ def run(a, rank, world, local_rank, workload):
 
     torch.cuda.set_device(local_rank)
     # host preprocessing is OpenMP-parallel inside every rank: share the cores instead of oversubscribing them
-    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, bench.host_cores() // world)))
+    # (torchrun presets OMP_NUM_THREADS=1, which would serialise the TENO table construction)
+    mb.set_host_threads(max(1, bench.host_cores() // world))
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     t_setup = time.perf_counter()

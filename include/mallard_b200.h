@@ -113,6 +113,8 @@ typedef struct {
 } mlb_parallel;
 
 const char *mlb_version(void);
+/* OpenMP threads used by the host preprocessor (n <= 0: query only); returns the value in effect */
+int mlb_set_host_threads(int32_t n);
 /* message of the last failed call on `ctx` (or of the last failed mlb_create / stateless call when ctx == NULL) */
 const char *mlb_last_error(const mlb_ctx *ctx);
 

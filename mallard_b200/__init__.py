@@ -12,7 +12,7 @@ import numpy as np
 from . import _abi
 from ._abi import BASIS, BC, FP, INTEGRATOR, MESH, RECON, RENUMBER, RIEMANN, build, lib  # noqa: F401
 
-__all__ = ["Mesh", "Solver", "Plan", "riemann_flux", "compute_primitives", "partition", "build", "lib"]
+__all__ = ["Mesh", "Solver", "Plan", "riemann_flux", "compute_primitives", "partition", "set_host_threads", "build", "lib"]
 
 DEFAULT_GAS = dict(gamma=1.4, p_ref=101325.0, T_ref=298.15, rho_ref=1.225, p_min=-1e20, p_max=1e20)
 _MESH_KEYS = ["node_coords", "offsets_nodes_of_cell", "nodes_of_cell", "offsets_faces_of_cell", "faces_of_cell",
@@ -124,6 +124,11 @@ class Mesh:
         v.n_zones = len(self.zones)
         v.zones = zs
         return v, keep
+
+
+def set_host_threads(n):
+    """OpenMP threads of the host preprocessor (launchers such as torchrun preset OMP_NUM_THREADS=1)."""
+    return lib().mlb_set_host_threads(int(n))
 
 
 def partition(mesh, n_parts):

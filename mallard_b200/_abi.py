@@ -53,6 +53,7 @@ class Parallel(C.Structure):
 VP, I32, U32, U64, DBL = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, C.c_double
 SYMBOLS = {
     "mlb_version": (C.c_char_p, []),
+    "mlb_set_host_threads": (C.c_int, [I32]),
     "mlb_last_error": (C.c_char_p, [VP]),
     "mlb_create": (C.c_int, [C.POINTER(VP), C.POINTER(MeshView), C.POINTER(Numerics), C.POINTER(Physics), C.POINTER(Bc), I32, C.POINTER(Parallel)]),
     "mlb_destroy": (None, [VP]),

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <map>
 #include <memory>
+#include <omp.h>
 
 #include "kernel_args.h"
 
@@ -425,6 +426,10 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
 extern "C" {
 
 const char * mlb_version(void) { return "mallard_b200 0.1 (sm_100a)"; }
+int mlb_set_host_threads(int32_t n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
 const char * mlb_last_error(const mlb_ctx * ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
 
 int mlb_create(mlb_ctx ** out, const mlb_mesh * mesh, const mlb_numerics * numerics, const mlb_physics * physics,

@@ -65,6 +65,11 @@ $CXX_BIN $CXXFLAGS $INC "$REF/src/main.cpp" "$OUT/lib/libmallard_ref.a" $LIBS -o
 if [ -f "$HERE/ref_harness.cpp" ]; then
   $CXX_BIN $CXXFLAGS $INC "$HERE/ref_harness.cpp" "$OUT/lib/libmallard_ref.a" $LIBS -o "$OUT/bin/ref_harness"
 fi
+# the reference host driving the B200 library through its C ABI (integration proof)
+if [ -f "$HERE/dropin_harness.cpp" ] && [ -f "$HERE/../mallard_b200/libmallard_b200.so" ]; then
+  $CXX_BIN $CXXFLAGS $INC "$HERE/dropin_harness.cpp" "$OUT/lib/libmallard_ref.a" $LIBS \
+     -L"$HERE/../mallard_b200" -lmallard_b200 -Wl,-rpath,'$ORIGIN/../../../mallard_b200' -o "$OUT/bin/mallard_dropin"
+fi
 if [ "${BUILD_REF_TESTS:-0}" = 1 ]; then
   G="$REF/src/external/kokkos/tpls/gtest"
   $CXX_BIN $CXXFLAGS $INC -I"$G" -I"$REF/test" "$REF"/test/*.cpp "$G/gtest/gtest-all.cc" \

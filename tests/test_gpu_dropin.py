@@ -1,0 +1,164 @@
+"""End-to-end drop-in check: the UNMODIFIED reference host (TOML input, mesh generator, exprtk initial condition, checks,
+VTU writer; oracle/_ref/bin/mallard_dropin, see oracle/dropin_harness.cpp and INTEGRATION.md) with Solver::run's three
+hot-path seams rerouted through libmallard_b200.so, against the unmodified reference itself (oracle/_ref/bin/Mallard,
+Kokkos on the host cores), on the reference's own example inputs.  Compared artefact: the VTU files both runs write.
+Both binaries are built where /root/reference exists (oracle/build_ref.sh) and travel to the GPU box prebuilt."""
+import hashlib
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "bin", "Mallard")
+DROPIN = os.path.join(ROOT, "oracle", "_ref", "bin", "mallard_dropin")
+
+SOD = """
+[run]
+t_stop = 0.2
+cfl = 1.0
+[mesh]
+type = "cartesian"
+Nx = 1000
+Ny = 1
+Lx = 1.0
+Ly = 0.001
+[initialize]
+type = "analytical"
+rho = "var l := x <  0.5; var r := x >= 0.5; 1.0 * l + 0.125 * r"
+u = ["0.0", "0.0"]
+p = "var l := x <  0.5; var r := x >= 0.5; 1.0 * l + 0.1 * r"
+%(bcs)s
+[numerics]
+riemann_solver = "HLLC"
+time_integrator = "SSPRK3"
+check_nan = true
+[numerics.face_reconstruction]
+type = "FO"
+[physics]
+type = "euler"
+gamma = 1.4
+p_ref = 101325.0
+T_ref = 298.15
+rho_ref = 1.225
+[output]
+check_interval = 100
+[[write_data]]
+prefix = "./solut/all/sod_all"
+format = "vtu"
+geometry = "all"
+interval = 100
+variables = ["CFL", "RHO", "RHOU_X", "RHOU_Y", "RHOE", "U_X",  "U_Y", "P", "T", "H"]
+""" % dict(bcs="\n".join('[[boundaries]]\nname = "%s"\ntype = "symmetry"' % n for n in ("left", "right", "top", "bottom")))
+
+WEDGE = """
+[run]
+n_steps = 400
+cfl = 1.0
+[mesh]
+type = "wedge"
+Nx = 150
+Ny = 50
+Lx = 4.0
+Ly = 1.5
+[initialize]
+type = "constant"
+u = [600.0, 0.0]
+p = 101325.0
+T = 300.0
+[[boundaries]]
+name = "left"
+type = "upt"
+u = [600.0, 0.0]
+p = 101325.0
+T = 300.0
+[[boundaries]]
+name = "right"
+type = "p_out"
+p = 101325.0
+[[boundaries]]
+name = "top"
+type = "symmetry"
+[[boundaries]]
+name = "bottom"
+type = "symmetry"
+[numerics]
+riemann_solver = "HLLC"
+time_integrator = "SSPRK3"
+check_nan = true
+[numerics.face_reconstruction]
+type = "FO"
+[physics]
+type = "euler"
+gamma = 1.4
+p_ref = 101325.0
+T_ref = 298.15
+rho_ref = 1.225
+[output]
+check_interval = 100
+[[write_data]]
+prefix = "./solut/all/wedge_all"
+format = "vtu"
+geometry = "all"
+interval = 200
+variables = ["CFL", "RHO", "RHOU_X", "RHOU_Y", "RHOE", "U_X",  "U_Y", "P", "T", "H"]
+"""
+
+
+def read_vtu(path):
+    """Arrays of a reference-written VTU (raw appended data, 4-byte length headers; src/io/data_writer.cpp:93-244)."""
+    raw = open(path, "rb").read()
+    head, _, tail = raw.partition(b'<AppendedData encoding="raw">')
+    payload = tail[tail.index(b"_") + 1:]
+    out = {}
+    dt = {"Float64": np.float64, "Float32": np.float32, "UInt32": np.uint32, "UInt8": np.uint8, "Int32": np.int32}
+    for i, m in enumerate(re.finditer(rb'<DataArray type="(\w+)"(?: Name="(\w+)")?[^>]*offset="(\d+)"', head)):
+        typ, name, off = m.group(1).decode(), (m.group(2) or b"points%d" % i).decode(), int(m.group(3))
+        n = int(np.frombuffer(payload, np.uint32, 1, off)[0])
+        out[name] = np.frombuffer(payload, dt[typ], n // np.dtype(dt[typ]).itemsize, off + 4)
+    return out
+
+
+def run(binary, toml, workdir, extra=()):
+    os.makedirs(os.path.join(workdir, "solut", "all"))
+    open(os.path.join(workdir, "input.toml"), "w").write(toml)
+    env = dict(os.environ, OMP_NUM_THREADS="1", OMP_PROC_BIND="false")   # serial reference: deterministic atomics
+    p = subprocess.run([binary, "-i", "input.toml", *extra], cwd=workdir, env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return p.stdout
+
+
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(DROPIN)), reason="oracle/_ref binaries not built (need /root/reference)")
+@pytest.mark.parametrize("name,toml,fp,tol", [("sod", SOD, "strict", 1e-9), ("sod", SOD, "fast", 1e-9), ("wedge", WEDGE, "strict", 0.0),
+                                              ("wedge", WEDGE, "fast", 1e-10)])
+def test_reference_host_with_b200_hot_path_writes_the_reference_solution(tmp_path, name, toml, fp, tol):
+    a, b = str(tmp_path / "ref"), str(tmp_path / "b200")
+    run(REF, toml, a)
+    out = run(DROPIN, toml, b, ("--fp", fp, "--quiet"))
+    info = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    fa, fb = sorted(os.listdir(os.path.join(a, "solut", "all"))), sorted(os.listdir(os.path.join(b, "solut", "all")))
+    assert fa == fb and len(fa) >= 3                       # same output schedule: same number of steps, same stop condition
+    worst, identical = 0.0, 0
+    for f in fa:
+        pa, pb = os.path.join(a, "solut", "all", f), os.path.join(b, "solut", "all", f)
+        identical += hashlib.md5(open(pa, "rb").read()).hexdigest() == hashlib.md5(open(pb, "rb").read()).hexdigest()
+        va, vb = read_vtu(pa), read_vtu(pb)
+        assert va.keys() == vb.keys()
+        scale = {k: np.abs(v).max() for k, v in va.items()}
+        for k in va:
+            if va[k].dtype.kind != "f":
+                assert np.array_equal(va[k], vb[k]), (f, k)
+                continue
+            # vector components share one scale (the cross-flow component of a 1-D problem is exactly 0 in the reference)
+            group = [g for g in (("RHOU_X", "RHOU_Y"), ("U_X", "U_Y")) if k in g]
+            ref_scale = max([scale[k]] + [scale[x] for g in group for x in g] + [1e-300])
+            worst = max(worst, float(np.abs(va[k] - vb[k]).max() / ref_scale))
+    print("%s[%s]: %d steps, %d/%d VTU files byte-identical to the reference's, worst field difference %.2e; %.3g cell-updates/s/stage "
+          "through the reference host loop" % (name, fp, info["steps"], identical, len(fa), worst, info["cell_updates_per_s_per_stage"]))
+    assert worst <= tol
+    if tol == 0.0:
+        assert identical == len(fa)
