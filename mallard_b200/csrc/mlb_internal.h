@@ -71,7 +71,7 @@ struct TenoTables {
     uvec st_ids;
     dvec st_area, st_mat;
     // Compact streaming tables (FAST mode), n_ftiles = ceil(N_recon / FAST_CT):
-    //   fm_ids   [ftile][S][M-1][FAST_CT]                 u32  columns m = 1..M-1; empty stencil / padding cell -> NO_FACE
+    //   fm_ids   [ftile][S][M-1][FAST_CT]                 u32  columns m = 1..M-1; empty stencil / padding cell -> the cell itself
     //   fm_mat   [ftile][S][K-1][(M-1)/2 pairs | 1][FAST_CT]  f64  rows k = 1..K-1 of A+ with area_t folded into the columns;
     //                                                      per row: (M-1)/2 column pairs [pair][cell][2], then [cell] singles
     //   fm_area0 [ftile * FAST_CT]                         f64  area_t of the cell itself (central stencil, m = 0)

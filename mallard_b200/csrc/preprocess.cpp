@@ -798,14 +798,17 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
                     for (int k2 = M; k2 < Mp; k2++) T.st_ids[(base + k2) * TILE + lane] = (uint32_t)(tile * TILE + lane);
                 }
         if (T.fast) {
-            T.fm_ids.assign(n_ftiles * S * MC * FAST_CT, NO_FACE);
+            // an empty stencil (boundary face) and the padding cells of the last tile list the cell itself: the gather
+            // stays in bounds without a predicate, and "first id == own id" marks the stencil as empty
+            T.fm_ids.resize(n_ftiles * S * MC * FAST_CT);
 #pragma omp parallel for schedule(static)
-            for (int64_t ii = 0; ii < (int64_t)n_recon; ii++) {
+            for (int64_t ii = 0; ii < (int64_t)(n_ftiles * FAST_CT); ii++) {
                 const size_t tile = (size_t)ii / TILE, lane = (size_t)ii % TILE, ft = (size_t)ii / FAST_CT, fl = (size_t)ii % FAST_CT;
                 for (int s = 0; s < S; s++) {
                     const size_t base = (tile * S + s) * Mp;
-                    if (T.st_ids[base * TILE + lane] == NO_FACE) continue;
-                    for (int c = 0; c < MC; c++) T.fm_ids[((ft * S + s) * MC + c) * FAST_CT + fl] = T.st_ids[(base + c + 1) * TILE + lane];
+                    const bool empty = ii >= (int64_t)n_recon || T.st_ids[base * TILE + lane] == NO_FACE;
+                    for (int c = 0; c < MC; c++)
+                        T.fm_ids[((ft * S + s) * MC + c) * FAST_CT + fl] = empty ? (uint32_t)ii : T.st_ids[(base + c + 1) * TILE + lane];
                 }
             }
             T.OIs.assign((size_t)KR * KR, 0.0);

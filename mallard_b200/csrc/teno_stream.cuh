@@ -174,11 +174,9 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
         for (int m = 0; m < MC; m++) id[m] = ids[m * CT];
         prefetch_tile(tile, 0);
         if (ASYNC) {
-            empty_cur = id[0] == NO_FACE;
-            if (!empty_cur) {
+            empty_cur = id[0] == tile * CT + cl;
 #pragma unroll
-                for (int m = 0; m < MC; m++) cp_async8(ubuf + tid + m * CONSUMERS, Uv + id[m]);
-            }
+            for (int m = 0; m < MC; m++) cp_async8(ubuf + tid + m * CONSUMERS, Uv + id[m]);
         }
         cp_async_commit();
         if (ASYNC) {
@@ -208,17 +206,17 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
                 empty = empty_cur;                                    // empty stencil (:896-899) or padding cell
                 const double * ub = ubuf + (size_t)(s & 1) * MC * CONSUMERS + tid;
 #pragma unroll
-                for (int m = 0; m < MC; m++) b[m] = empty ? 0.0 : ub[m * CONSUMERS] - u_self;
+                for (int m = 0; m < MC; m++) b[m] = ub[m * CONSUMERS] - u_self;
             } else {
                 if (s == 0) { cp_async_wait_all(); u_self = live ? fx[(13 + var) * CT] : 0.0; }
-                empty = id[0] == NO_FACE;
+                empty = id[0] == cell;                                // an empty stencil lists the cell itself (b = 0)
 #pragma unroll
-                for (int m = 0; m < MC; m++) b[m] = empty ? 0.0 : Uv[id[m]] - u_self;
+                for (int m = 0; m < MC; m++) b[m] = Uv[id[m]] - u_self;
             }
             // 2. requests for what comes next (the next tile's first stencil after the last one of this tile)
             if (ASYNC) {
-                empty_cur = id[0] == NO_FACE;                         // id[]: the next stencil's, loaded one stencil ago
-                if ((s + 1 < S || has_next) && !empty_cur) {
+                empty_cur = id[0] == (s + 1 < S ? cell : next * CT + cl);   // id[]: the next stencil's, loaded one stencil ago
+                if (s + 1 < S || has_next) {
                     double * dst = ubuf + (size_t)((s + 1) & 1) * MC * CONSUMERS + tid;
 #pragma unroll
                     for (int m = 0; m < MC; m++) cp_async8(dst + m * CONSUMERS, Uv + id[m]);
@@ -236,9 +234,6 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
                     const uint32_t * __restrict__ ids2 = a.ids + ((size_t)t2 * S + s2) * (MC * CT) + cl;
 #pragma unroll
                     for (int m = 0; m < MC; m++) id[m] = ids2[m * CT];
-                } else {
-#pragma unroll
-                    for (int m = 0; m < MC; m++) id[m] = NO_FACE;
                 }
             }
             // 4. dofs a_k = sum_m A'[k][m] b[m], rows arriving chunk by chunk through the ring

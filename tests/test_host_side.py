@@ -188,8 +188,8 @@ def test_streaming_tables_are_the_reference_tables_compacted(order):
             got = np.empty((KR, MC))
             for m in range(MC):
                 got[:, m] = row[:, (m // 2 * CT + fl) * 2 + (m & 1)] if m < 2 * npair else row[:, 2 * npair * CT + fl]
-            if hi == lo:
-                assert (ids[ft, s, :, fl] == 0xFFFFFFFF).all() and not got.any()
+            if hi == lo:   # an empty stencil lists the cell itself (zero right-hand side) and carries a zero matrix
+                assert (ids[ft, s, :, fl] == i).all() and not got.any()
                 n_empty += 1
                 continue
             A = mats[K * lo:K * hi].reshape(K, M); ar = areas[lo:hi]
@@ -201,4 +201,4 @@ def test_streaming_tables_are_the_reference_tables_compacted(order):
     assert n_empty > 0    # boundary faces have no directional stencil
     for i in range(plan.N_recon, n_ft * CT):   # padding cells of the last tile
         ft, fl = divmod(i, CT)
-        assert (ids[ft, :, :, fl] == 0xFFFFFFFF).all()
+        assert (ids[ft, :, :, fl] == i).all()
