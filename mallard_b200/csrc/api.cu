@@ -217,8 +217,7 @@ ReconStreamArgs stream_args(mlb_ctx & c, const double * Uin) {
     const TenoTables & T = c.prep.teno;
     r.g = c.g; r.Uin = Uin; r.Fc = c.Fc; r.mat = c.d_fm_mat; r.ids = c.d_fm_ids; r.area0 = c.d_fm_area0;
     r.n_tiles = c.n_ftiles; r.order = T.order; r.fixed_weights = c.num.teno_fixed;
-    static const int variant = [] { const char * e = getenv("MLB_STREAM_GATHER"); return e && !strcmp(e, "direct") ? 0 : 1; }();
-    r.async_gather = variant;   // tuning knob: how neighbour values reach the consumers (see teno_stream.cuh)
+    r.async_gather = 1;
     for (size_t i = 0; i < c.prep.qf_x.size() && i < 4; i++) r.qf_x[i] = c.prep.qf_x[i];
     for (int i = 0; i < T.K; i++) r.psi_bar[i] = T.psi_bar[i];
     for (size_t i = 0; i < T.OIs.size(); i++) r.OIs[i] = T.OIs[i];
@@ -380,7 +379,7 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
     const size_t NP = P.Npad;
     for (int i = 0; i < 3; i++) { c->U[i] = c->alloc<double>(4 * NP); CUDA_OK(cudaMemsetAsync(c->U[i], 0, 4 * NP * sizeof(double), c->stream)); }
     for (int i = 0; i < c->n_rhs; i++) { c->k[i] = c->alloc<double>(4 * NP); CUDA_OK(cudaMemsetAsync(c->k[i], 0, 4 * NP * sizeof(double), c->stream)); }
-    c->prim = c->alloc<double>(5 * NP); CUDA_OK(cudaMemsetAsync(c->prim, 0, 5 * NP * sizeof(double), c->stream));
+    c->prim = c->alloc<double>(6 * NP); CUDA_OK(cudaMemsetAsync(c->prim, 0, 6 * NP * sizeof(double), c->stream));
     c->sr = c->alloc<double>(NP); CUDA_OK(cudaMemsetAsync(c->sr, 0, NP * sizeof(double), c->stream));
     c->scal = c->alloc<double>(SC_COUNT);
     {
@@ -470,7 +469,7 @@ int mlb_set_state(mlb_ctx * c, const double * U, const double * prim) {
     if (!U) throw std::runtime_error("mlb_set_state: U is NULL");
     CUDA_OK(cudaSetDevice(c->device));
     import_state(*c, U, c->U[c->cur], 4);
-    if (prim) import_state(*c, prim, c->prim, 5);
+    if (prim) { import_state(*c, prim, c->prim, 5); launch_rho_plane(c->U[c->cur], c->prep.N, c->prep.Npad, c->prim, c->stream); c->launches++; }
     else { c->kt->primitives_soa(c->gas, c->prep.N, c->prep.Npad, c->U[c->cur], c->prim, c->stream); c->launches++; }
     CUDA_OK(cudaStreamSynchronize(c->stream));
     API_END(c)
@@ -788,7 +787,7 @@ int mlb_halo_unpack(mlb_ctx * c, int32_t stage) {
     c->launch("halo_unpack", [&] { launch_scatter(c->d_recv_buf, c->d_recv_idx, (uint32_t)c->n_recv, c->prep.Npad, c->U[b], c->stream); });
     if (stage == 0 && c->prep.N > c->prep.N_owned) {   // ghosts' primitives for the CFL kernel (update_primitives of their owners)
         const uint32_t off = c->prep.N_owned & ~31u;    // keep the SoA column alignment
-        c->kt->primitives_soa(c->gas, c->prep.N - off, c->prep.Npad, c->U[b] + off, c->prim + off, c->stream);
+        c->kt->primitives_soa(c->gas, c->prep.N - off, c->prep.Npad, c->U[b] + 4 * (size_t)off, c->prim + off, c->stream);
         c->launches++;
     }
     API_END(c)

@@ -44,21 +44,21 @@ struct RkArgs {
     int32_t mode, n_prev, last_stage, pad_;
     const double * base;
     double * out;
-    double * k_store;             // SoA [4][Npad] or null
+    double * k_store;             // AoS [Npad][4] or null
     const double * kprev[3];
     double cprev[3];
     double c0, c1, coef;
-    double * prim_out;            // SoA [5][Npad] written when last_stage (Solver::update_primitives)
+    double * prim_out;            // SoA [6][Npad] (u, v, p, T, h, rho) written when last_stage (Solver::update_primitives)
 };
 
 struct StageArgs {
     DevGeom g;
     DevPhys ph;
     RkArgs rk;
-    const double * Uin;           // SoA [4][Npad]: state the residual is evaluated on
-    const double * Fc;            // TENO: cell-centred face values [n_slots][Q][4][Npad]
+    const double * Uin;           // AoS [Npad][4]: state the residual is evaluated on
+    const double * Fc;            // TENO: cell-centred face values AoS [Npad][n_slots * Q][4]
     double * AF;                  // [NFpad][4] area * quadrature-averaged flux per face (written by the face kernel)
-    const double * k_override;    // SoA [4][Npad] or null: state-independent residual (test hook)
+    const double * k_override;    // AoS [Npad][4] or null: state-independent residual (test hook)
     double * scal;                // device scalars
     unsigned long long * step_counter;
     int32_t teno;
@@ -95,8 +95,8 @@ struct ReconStreamArgs {       // teno_stream.cuh
 struct CflArgs {
     DevGeom g;
     GasParams gas;
-    const double * U;             // SoA [4][Npad]
-    const double * prim;          // SoA [5][Npad]
+    const double * U;             // AoS [Npad][4] (unused: rho comes from prim[5])
+    const double * prim;          // SoA [6][Npad]
     double * sr_out;              // [Npad] spectral radius per cell (cfl_local before scaling)
     double * scal;
     long long * max_bits;         // running max (as ordered int) — reset by the finishing block
@@ -126,6 +126,7 @@ const KernelTable * kernels_fast();
 // layout helpers (mode independent, utils.cu)
 void launch_import_state(const double * aos, const uint32_t * perm, uint32_t n, uint32_t npad, int nv, double * soa, cudaStream_t);
 void launch_export_state(const double * soa, const uint32_t * perm, uint32_t n, uint32_t npad, int nv, double * aos, cudaStream_t);
+void launch_rho_plane(const double * U_aos, uint32_t n, uint32_t npad, double * prim, cudaStream_t);
 void launch_export_scaled(const double * v, const double * scal, int which, const uint32_t * perm, uint32_t n, double * out, cudaStream_t);
 void launch_gather(const double * soa, const uint32_t * idx, uint32_t n, uint32_t npad, double * buf, cudaStream_t);
 void launch_scatter(const double * buf, const uint32_t * idx, uint32_t n, uint32_t npad, double * soa, cudaStream_t);

@@ -9,6 +9,11 @@
 //                        combinations and K12 update_primitives)
 //   teno_recon_kernel   TENO reconstruction (K3): one thread per (cell, conserved variable), warp = one 8-cell table tile
 //   cfl_kernel          spectral radius + max reduction + dt (K13, K14)
+//
+// Layout: conserved states and residuals are AoS [cell][4] (one 32-byte sector per cell: every gather of a neighbour's
+// state moves exactly the bytes it uses; per-cell streaming accesses are 2 x 128-bit); primitives are SoA [6][Npad]
+// (u, v, p, T, h as the reference's primitives view, plus rho for the CFL kernel); TENO face values are cell-centred
+// AoS Fc[cell][slot * Q + q][4].
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -171,25 +176,41 @@ __device__ __forceinline__ void ghost_state(const BcParams & bc, const GasParams
 // ---------------------------------------------------------------------------------------------------------------
 // RK stage combination (numerics/time_integrator.cpp:57-163; KokkosBlas axpy: y = a*x + y, axpby: y = a*x + b*y)
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void rk_update(const RkArgs & rk, const double * Uin, uint32_t Npad, uint32_t i, const double * k, double dt,
-                                          double * Unew) {
+__device__ __forceinline__ void ld4(const double * p, size_t i, double * out) {
+    const double4 t = reinterpret_cast<const double4 *>(p)[i];
+    out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+}
+__device__ __forceinline__ void st4(double * p, size_t i, const double * v) {
+    reinterpret_cast<double4 *>(p)[i] = make_double4(v[0], v[1], v[2], v[3]);
+}
+
+__device__ __forceinline__ void rk_update(const RkArgs & rk, const double * Uin, uint32_t i, const double * k, double dt, double * Unew) {
+    double base[4];
+    ld4(rk.base, i, base);
+    if (rk.mode == 0) {
 #pragma unroll
-    for (int v = 0; v < 4; v++) {
-        const size_t at = (size_t)v * Npad + i;
-        double y;
-        if (rk.mode == 0) {
-            y = (dt * rk.coef) * k[v] + rk.base[at];
-        } else if (rk.mode == 1) {
-            y = rk.c0 * rk.base[at] + rk.c1 * Uin[at];
-            y = (dt * rk.coef) * k[v] + y;
-        } else {
-            y = rk.base[at];
-            for (int j = 0; j < rk.n_prev; j++) y = (dt * rk.cprev[j]) * rk.kprev[j][at] + y;
-            y = (dt * rk.coef) * k[v] + y;
+        for (int v = 0; v < 4; v++) Unew[v] = (dt * rk.coef) * k[v] + base[v];
+    } else if (rk.mode == 1) {
+        double uin[4];
+        ld4(Uin, i, uin);
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const double y = rk.c0 * base[v] + rk.c1 * uin[v];
+            Unew[v] = (dt * rk.coef) * k[v] + y;
         }
-        Unew[v] = y;
-        rk.out[at] = y;
+    } else {
+#pragma unroll
+        for (int v = 0; v < 4; v++) Unew[v] = base[v];
+        for (int j = 0; j < rk.n_prev; j++) {
+            double kp[4];
+            ld4(rk.kprev[j], i, kp);
+#pragma unroll
+            for (int v = 0; v < 4; v++) Unew[v] = (dt * rk.cprev[j]) * kp[v] + Unew[v];
+        }
+#pragma unroll
+        for (int v = 0; v < 4; v++) Unew[v] = (dt * rk.coef) * k[v] + Unew[v];
     }
+    st4(rk.out, i, Unew);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -201,8 +222,8 @@ template <int RS, bool TENO>
 __global__ void __launch_bounds__(128) face_flux_kernel(const __grid_constant__ StageArgs a) {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= a.g.NF) return;
-    const uint32_t Np = a.g.Npad;
     const int Q = TENO ? a.g.Q : 1;
+    const int NPT = a.g.n_slots * Q;                     // face-value points per cell
     const uint32_t cl = a.g.face_cl[f];
     const int32_t cr = a.g.face_cr[f];
     double4 * out = reinterpret_cast<double4 *>(a.AF) + f;
@@ -214,15 +235,13 @@ __global__ void __launch_bounds__(128) face_flux_kernel(const __grid_constant__ 
     double fsum[4] = {0.0, 0.0, 0.0, 0.0};
     for (int q = 0; q < Q; q++) {
         double Ul[4], Pl[5];
-#pragma unroll
-        for (int v = 0; v < 4; v++) Ul[v] = TENO ? a.Fc[((size_t)(sl * Q + q) * 4 + v) * Np + cl] : a.Uin[(size_t)v * Np + cl];
+        if (TENO) ld4(a.Fc, (size_t)cl * NPT + (sl * Q + q), Ul); else ld4(a.Uin, cl, Ul);
         cons_to_prim(a.ph.gas, Ul, Pl);
         const FaceState L = {Ul[0], Pl[0], Pl[1], Pl[2], Pl[4]};
         double ft[4];
         if (cr >= 0) {
             double Ur[4], Pr[5];
-#pragma unroll
-            for (int v = 0; v < 4; v++) Ur[v] = TENO ? a.Fc[((size_t)(sr * Q + q) * 4 + v) * Np + cr] : a.Uin[(size_t)v * Np + cr];
+            if (TENO) ld4(a.Fc, (size_t)cr * NPT + (sr * Q + q), Ur); else ld4(a.Uin, (size_t)cr, Ur);
             cons_to_prim(a.ph.gas, Ur, Pr);
             const FaceState R = {Ur[0], Pr[0], Pr[1], Pr[2], Pr[4]};
             riemann_flux<RS>(ft, nx, ny, L, R, a.ph.gas.gamma);
@@ -253,8 +272,7 @@ __global__ void __launch_bounds__(256) gather_stage_kernel(const __grid_constant
     const uint32_t Np = a.g.Npad;
     double k[4];
     if (a.k_override) {
-#pragma unroll
-        for (int v = 0; v < 4; v++) k[v] = a.k_override[(size_t)v * Np + i];
+        ld4(a.k_override, i, k);
     } else {
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         const uint32_t order = a.g.rhs_order[i];
@@ -277,20 +295,18 @@ __global__ void __launch_bounds__(256) gather_stage_kernel(const __grid_constant
 #pragma unroll
         for (int v = 0; v < 4; v++) k[v] = acc[v] / vol;
     }
-    if (a.rk.k_store) {
-#pragma unroll
-        for (int v = 0; v < 4; v++) a.rk.k_store[(size_t)v * Np + i] = k[v];
-    }
+    if (a.rk.k_store) st4(a.rk.k_store, i, k);
     if (a.rk.mode == 3) return;
     const double dt = a.scal[SC_DT];
     double Unew[4];
-    rk_update(a.rk, a.Uin, Np, i, k, dt, Unew);
+    rk_update(a.rk, a.Uin, i, k, dt, Unew);
     if (a.rk.last_stage) {
         if (a.rk.prim_out) {   // Solver::update_primitives solver.cpp:533-578
             double P[5];
             cons_to_prim(a.ph.gas, Unew, P);
 #pragma unroll
             for (int v = 0; v < 5; v++) a.rk.prim_out[(size_t)v * Np + i] = P[v];
+            a.rk.prim_out[5 * (size_t)Np + i] = Unew[0];
         }
         if (i == 0) { a.scal[SC_T] = a.scal[SC_T] + dt; *a.step_counter += 1ull; }   // solver.cpp:529-530
     }
@@ -339,8 +355,8 @@ __global__ void __launch_bounds__(RECON_THREADS) teno_recon_kernel(const __grid_
     const size_t tile = cell / TILE;
     const int lane = cell % TILE;
     const int S = a.S;
-    const double * Uv = a.Uin + (size_t)var * Np;
-    const double u_self = Uv[cell];
+    const double * Uv = a.Uin + var;                                     // AoS [cell][4]: Uv[4 * c] is this thread's variable
+    const double u_self = Uv[4 * (size_t)cell];
 
     double w[MAXS];
     double area0 = 0.5;
@@ -352,7 +368,7 @@ __global__ void __launch_bounds__(RECON_THREADS) teno_recon_kernel(const __grid_
         const double * areas = a.st_area + sbase * TILE + lane;
         double b[MP];
 #pragma unroll
-        for (int m = 0; m < MP; m++) b[m] = areas[m * TILE] * (Uv[ids[m * TILE]] - u_self);   // :903-910
+        for (int m = 0; m < MP; m++) b[m] = areas[m * TILE] * (Uv[4 * (size_t)ids[m * TILE]] - u_self);   // :903-910
         if (s == 0) area0 = areas[0];
         const double2 * mat = reinterpret_cast<const double2 *>(a.st_mat) + ((tile * S + s) * K * (MP / 2)) * TILE + lane;
         double dof[K];
@@ -443,7 +459,7 @@ __global__ void __launch_bounds__(256) cfl_kernel(const __grid_constant__ CflArg
     if (i < a.g.N_owned) {
         double conv = 0.0, acou = 0.0;
         const int nf = a.g.nfc[i];
-        const double rho_s = a.U[i], u_s = a.prim[i], v_s = a.prim[(size_t)Np + i], p_s = a.prim[2 * (size_t)Np + i];
+        const double rho_s = a.prim[5 * (size_t)Np + i], u_s = a.prim[i], v_s = a.prim[(size_t)Np + i], p_s = a.prim[2 * (size_t)Np + i];
         const double sos_s = sqrt(a.gas.gamma * p_s / rho_s);
         for (int j = 0; j < nf; j++) {
             const uint32_t fcode = a.g.slot_face[(size_t)j * Np + i];
@@ -455,7 +471,7 @@ __global__ void __launch_bounds__(256) cfl_kernel(const __grid_constant__ CflArg
                 sx = a.g.bnd_s[i]; sy = sx;
                 sos_l = sos_s; sos_r = sos_s; ul = u_s; vl = v_s; ur = u_s; vr = v_s;
             } else {
-                const double rho_n = a.U[nbr], u_n = a.prim[nbr], v_n = a.prim[(size_t)Np + nbr], p_n = a.prim[2 * (size_t)Np + nbr];
+                const double rho_n = a.prim[5 * (size_t)Np + nbr], u_n = a.prim[nbr], v_n = a.prim[(size_t)Np + nbr], p_n = a.prim[2 * (size_t)Np + nbr];
                 const double sos_n = sqrt(a.gas.gamma * p_n / rho_n);
                 const double dxs = a.g.cell_xy[i], dys = a.g.cell_xy[(size_t)Np + i];
                 const double dxn = a.g.cell_xy[nbr], dyn = a.g.cell_xy[(size_t)Np + nbr];
@@ -520,13 +536,15 @@ __global__ void prims_aos_kernel(const GasParams g, uint64_t n, const double * U
     for (int v = 0; v < 5; v++) P[5 * i + v] = p[v];
 }
 
+// primitives (SoA [6][npad]: u, v, p, T, h, rho) of AoS states
 __global__ void prims_soa_kernel(const GasParams g, uint32_t n, uint32_t npad, const double * U, double * P) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double u[4], p[5];
-    for (int v = 0; v < 4; v++) u[v] = U[(size_t)v * npad + i];
+    ld4(U, i, u);
     cons_to_prim(g, u, p);
     for (int v = 0; v < 5; v++) P[(size_t)v * npad + i] = p[v];
+    P[5 * (size_t)npad + i] = u[0];
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -91,25 +91,26 @@ __device__ __forceinline__ double poly_sum(const double * c, const double * Px, 
 
 constexpr int FX_ROWS = 17;   // per tile and cell: 12 face end-point coordinates, area_t[0], the cell's 4 conserved values
 
-template <int ORDER, bool ASYNC> struct Smem {
+template <int ORDER> struct Smem {
     using C = Cfg<ORDER>;
-    static constexpr int STAGES = ASYNC ? 4 : (ORDER == 4 ? 6 : 7);
+    static constexpr int STAGES = fast_stages(ORDER);
     static constexpr size_t RING = (size_t)STAGES * C::CHUNK_BYTES;
-    static constexpr size_t UBUF = ASYNC ? (size_t)2 * C::MC * CONSUMERS * 8 : 0;   // gathered neighbour values, double-buffered over stencils
-    static constexpr size_t FXBUF = (size_t)2 * FX_ROWS * CT * 8;                  // per tile parity
+    static constexpr size_t UBUF = (size_t)2 * C::MC * CT * 4 * 8;      // neighbour states [m][cell][4], double-buffered over stencils
+    static constexpr size_t FXBUF = (size_t)2 * FX_ROWS * CT * 8;      // per tile parity
     static constexpr size_t TOTAL = RING + UBUF + FXBUF;
 };
 
-// ASYNC = true : neighbour values are requested one stencil ahead with cp.async (LDGSTS, no register staging) into
-//                per-thread shared-memory slots; 4 ring stages.
-// ASYNC = false: neighbour values are loaded into registers at the top of each stencil (one exposed L1/L2 latency per
-//                stencil, covered by the other resident warps); the shared memory saved buys a 7-stage ring.
-template <int ORDER, bool ASYNC>
+__device__ __forceinline__ void cp_async16(void * dst, const void * src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+template <int ORDER>
 __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_constant__ ReconStreamArgs a) {
     using C = Cfg<ORDER>;
-    using SM = Smem<ORDER, ASYNC>;
+    using SM = Smem<ORDER>;
     constexpr int K = C::K, KR = C::KR, MC = C::MC, NP = C::NP, Q = C::Q, S = FAST_S, NF = FAST_S - 1, STAGES = SM::STAGES;
     constexpr int CPT = S * C::NCH;                            // chunks per tile
+    constexpr int NG = (MC + 3) / 4;                           // neighbour states each of a cell's 4 threads fetches per stencil
     extern __shared__ __align__(128) unsigned char smem[];     // ring | ubuf | fxbuf
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
     unsigned char * ring = smem;
@@ -144,12 +145,14 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
     }
 
     // ---------------- consumers ----------------
-    //   fxbuf[parity of tile][row][cell]   face end points, area_t[0] and the cell's own state, requested a tile ahead with
-    //                                      cp.async by the cell's four variable-threads (same warp)
-    //   ubuf[parity of s][m][tid]          (ASYNC) neighbour values of the stencil's cells, requested a stencil ahead
+    // Nothing a consumer needs from global memory is waited for: it is requested with cp.async (LDGSTS: global → shared
+    // memory without register staging) one stencil (neighbour states) or one tile (geometry, own state) ahead.
+    //   ubuf[parity of s][m][cell][4]      conserved states of the stencil's cells: one 32-byte sector per neighbour, fetched
+    //                                      by the cell's four variable-threads in turn (thread `var` takes m = var, var + 4, ...)
+    //   fxbuf[parity of tile][row][cell]   face end points, area_t[0] and the cell's own state
+    // The four variable-threads of a cell sit in one warp, so a __syncwarp() after cp.async.wait_all publishes the copies.
     const int cl = tid >> 2, var = tid & 3;
     const uint32_t Np = a.g.Npad;
-    const double * __restrict__ Uv = a.Uin + (size_t)var * Np;
     uint32_t tile = blockIdx.x;
     if (tile >= n_tiles) return;
 
@@ -163,27 +166,34 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
             cp_async8(dst + v * CT, a.g.slot_fx + (size_t)v * Np + cell);
         }
         if (var == 0) cp_async8(dst + 12 * CT, a.area0 + cell);
-        cp_async8(dst + (13 + var) * CT, Uv + cell);
+        cp_async8(dst + (13 + var) * CT, a.Uin + 4 * (size_t)cell + var);
+    };
+    uint32_t id[NG], id0;                                             // ids this thread fetches for the NEXT stencil; its first id
+    auto load_ids = [&](uint32_t t, int s) {
+        const uint32_t * __restrict__ p = a.ids + ((size_t)t * S + s) * (MC * CT) + cl;
+        id0 = p[0];
+#pragma unroll
+        for (int i = 0; i < NG; i++) id[i] = (var + 4 * i < MC) ? p[(var + 4 * i) * CT] : 0u;
+    };
+    auto request_states = [&](int parity) {
+        double * dst = ubuf + ((size_t)parity * MC * CT + cl) * 4;
+#pragma unroll
+        for (int i = 0; i < NG; i++) {
+            if (var + 4 * i < MC) {
+                const double * src = a.Uin + 4 * (size_t)id[i];
+                cp_async16(dst + (size_t)(var + 4 * i) * CT * 4, src);
+                cp_async16(dst + (size_t)(var + 4 * i) * CT * 4 + 2, src + 2);
+            }
+        }
     };
 
-    uint32_t id[MC];   // ASYNC: ids of the stencil to be requested next; otherwise ids of the stencil about to be gathered
-    bool empty_cur = false;
-    {
-        const uint32_t * __restrict__ ids = a.ids + (size_t)tile * (S * MC * CT) + cl;
-#pragma unroll
-        for (int m = 0; m < MC; m++) id[m] = ids[m * CT];
-        prefetch_tile(tile, 0);
-        if (ASYNC) {
-            empty_cur = id[0] == tile * CT + cl;
-#pragma unroll
-            for (int m = 0; m < MC; m++) cp_async8(ubuf + tid + m * CONSUMERS, Uv + id[m]);
-        }
-        cp_async_commit();
-        if (ASYNC) {
-#pragma unroll
-            for (int m = 0; m < MC; m++) id[m] = ids[(MC + m) * CT];
-        }
-    }
+    bool empty_cur;                                                   // is the stencil whose states are in flight empty?
+    load_ids(tile, 0);
+    prefetch_tile(tile, 0);
+    empty_cur = id0 == tile * CT + cl;                                // an empty stencil lists the cell itself (b = 0)
+    request_states(0);
+    cp_async_commit();
+    load_ids(tile, 1);
 
     uint32_t ready = 0;
     for (uint32_t it = 0; tile < n_tiles; it++) {
@@ -197,44 +207,27 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
         double w[S];
 #pragma unroll
         for (int s = 0; s < S; s++) {
-            // 1. right-hand side b[m] = U[nbr m] - U[cell]
-            bool empty;
+            // 1. right-hand side b[m] = U[nbr m] - U[cell]: requested one stencil (own state: one tile) ago
+            cp_async_wait_all();
+            __syncwarp();
+            if (s == 0) u_self = live ? fx[(13 + var) * CT] : 0.0;
+            const bool empty = empty_cur;                             // empty stencil (:896-899) or padding cell
             double b[MC];
-            if (ASYNC) {
-                cp_async_wait_all();                                  // requested one stencil (tile data: one tile) ago
-                if (s == 0) u_self = live ? fx[(13 + var) * CT] : 0.0;
-                empty = empty_cur;                                    // empty stencil (:896-899) or padding cell
-                const double * ub = ubuf + (size_t)(s & 1) * MC * CONSUMERS + tid;
+            {
+                const double * ub = ubuf + (size_t)(s & 1) * MC * CT * 4 + tid;
 #pragma unroll
                 for (int m = 0; m < MC; m++) b[m] = ub[m * CONSUMERS] - u_self;
-            } else {
-                if (s == 0) { cp_async_wait_all(); u_self = live ? fx[(13 + var) * CT] : 0.0; }
-                empty = id[0] == cell;                                // an empty stencil lists the cell itself (b = 0)
-#pragma unroll
-                for (int m = 0; m < MC; m++) b[m] = Uv[id[m]] - u_self;
             }
-            // 2. requests for what comes next (the next tile's first stencil after the last one of this tile)
-            if (ASYNC) {
-                empty_cur = id[0] == (s + 1 < S ? cell : next * CT + cl);   // id[]: the next stencil's, loaded one stencil ago
-                if (s + 1 < S || has_next) {
-                    double * dst = ubuf + (size_t)((s + 1) & 1) * MC * CONSUMERS + tid;
-#pragma unroll
-                    for (int m = 0; m < MC; m++) cp_async8(dst + m * CONSUMERS, Uv + id[m]);
-                }
-            }
+            // 2. requests for what comes next (the next tile's first stencil after the last one of this tile); the ids
+            //    were loaded one stencil ago
+            empty_cur = id0 == (s + 1 < S ? cell : next * CT + cl);
+            if (s + 1 < S || has_next) request_states((s + 1) & 1);
             if (s + 1 == S && has_next) prefetch_tile(next, (it + 1) & 1);
-            if (ASYNC || s + 1 == S) cp_async_commit();
-            // 3. ids (plain coalesced loads; consumed a stencil later): ASYNC two stencils ahead, otherwise one
+            cp_async_commit();
+            // 3. ids of the stencil after that (plain coalesced loads, consumed a stencil later)
             {
-                constexpr int ahead = ASYNC ? 2 : 1;
-                const bool in_tile = s + ahead < S;
-                const uint32_t t2 = in_tile ? tile : next;
-                const int s2 = in_tile ? s + ahead : s + ahead - S;
-                if (in_tile || has_next) {
-                    const uint32_t * __restrict__ ids2 = a.ids + ((size_t)t2 * S + s2) * (MC * CT) + cl;
-#pragma unroll
-                    for (int m = 0; m < MC; m++) id[m] = ids2[m * CT];
-                }
+                const bool in_tile = s + 2 < S;
+                if (in_tile || has_next) load_ids(in_tile ? tile : next, in_tile ? s + 2 : s + 2 - S);
             }
             // 4. dofs a_k = sum_m A'[k][m] b[m], rows arriving chunk by chunk through the ring
 #pragma unroll
@@ -306,26 +299,24 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
                 for (int s = 1; s < S; s++) w[s] *= isd;
                 if (a.fixed_weights) w[0] = 0.0;
             }
-        }
-        // combined polynomial c_k = sum_s w_s a_sk over the stencils the reference does not skip (:1011)
-        double c[KR];
+            // combined polynomial c_k = sum_s w_s a_sk over the stencils the reference does not skip (:1011)
+            double c[KR];
 #pragma unroll
-        for (int k = 0; k < KR; k++) c[k] = 0.0;
+            for (int k = 0; k < KR; k++) c[k] = 0.0;
 #pragma unroll
-        for (int s = 0; s < S; s++) {
-            if (w[s] != 0.0) {
+            for (int s = 0; s < S; s++) {
+                if (w[s] != 0.0) {
 #pragma unroll
-                for (int k = 0; k < KR; k++) c[k] = fma(w[s], dof[s][k], c[k]);
+                    for (int k = 0; k < KR; k++) c[k] = fma(w[s], dof[s][k], c[k]);
+                }
             }
-        }
-        // the tile's geometry was waited for at the top of stencil 0; the __syncwarp()s of the chunk loop made the other
-        // lanes' copies visible
-        if (live) {
+            // the tile's geometry was waited for at the top of stencil 0 (and published by the __syncwarp() there)
             const double area0 = fx[12 * CT];
             double cb = 0.0;                                          // sum_k c_k psi_bar_k / area_t[0]  (:1028-1029)
             const double cscale = a.fixed_weights ? -1.0 : 1.0 / area0;
 #pragma unroll
             for (int k = 0; k < KR; k++) cb = fma(c[k], a.psi_bar[k + 1] * cscale, cb);
+            double * out = a.Fc + (size_t)cell * (NF * Q) * 4 + var;  // Fc[cell][slot * Q + q][var]
 #pragma unroll
             for (int j = 0; j < NF; j++) {                            // :985-1034 (triangles: always three faces)
                 const double x0 = fx[(4 * j) * CT], y0 = fx[(4 * j + 1) * CT], x1 = fx[(4 * j + 2) * CT], y1 = fx[(4 * j + 3) * CT];
@@ -336,7 +327,7 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
                     double Px[ORDER + 1], Py[ORDER + 1];
                     legendre_values<ORDER>(xq, Px);
                     legendre_values<ORDER>(yq, Py);
-                    a.Fc[((size_t)(j * Q + q) * 4 + var) * Np + cell] = poly_sum(c, Px, Py, u_self + cb, std::make_integer_sequence<int, KR>{});
+                    out[(j * Q + q) * 4] = poly_sum(c, Px, Py, u_self + cb, std::make_integer_sequence<int, KR>{});
                 }
             }
         }
@@ -345,25 +336,21 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
     }
 }
 
-template <int ORDER, bool ASYNC>
-static void launch_stream_v(const ReconStreamArgs & a, cudaStream_t st) {
-    const size_t smem = Smem<ORDER, ASYNC>::TOTAL;
+template <int ORDER>
+static void launch_stream_t(const ReconStreamArgs & a, cudaStream_t st) {
+    const size_t smem = Smem<ORDER>::TOTAL;
     static int ctas = 0;
     if (!ctas) {
-        cudaFuncSetAttribute(teno_stream_kernel<ORDER, ASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(teno_stream_kernel<ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, teno_stream_kernel<ORDER, ASYNC>, THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, teno_stream_kernel<ORDER>, THREADS, smem);
         ctas = sms * (per_sm > 0 ? per_sm : 1);
     }
     if (!a.n_tiles) return;
     const unsigned grid = a.n_tiles < (uint32_t)ctas ? a.n_tiles : (unsigned)ctas;   // persistent: one CTA slot per resident CTA
-    teno_stream_kernel<ORDER, ASYNC><<<grid, THREADS, smem, st>>>(a);
-}
-template <int ORDER>
-static void launch_stream_t(const ReconStreamArgs & a, cudaStream_t st) {
-    if (a.async_gather) launch_stream_v<ORDER, true>(a, st); else launch_stream_v<ORDER, false>(a, st);
+    teno_stream_kernel<ORDER><<<grid, THREADS, smem, st>>>(a);
 }
 
 static bool stream_supported(int order, int M, int Q, int basis, int n_slots) {

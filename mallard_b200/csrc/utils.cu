@@ -6,22 +6,31 @@ namespace mlb {
 
 namespace {
 
-// soa[v][i] = aos[perm[i]][v]   (perm == nullptr: identity)
+// dst[i][v] (nv == 4: states and residuals are AoS on the device) or dst[v][i] (primitives: SoA) = src[perm[i]][v];
+// perm == nullptr: identity
 __global__ void import_kernel(const double * __restrict__ aos, const uint32_t * __restrict__ perm, uint32_t n, uint32_t npad, int nv,
-                              double * __restrict__ soa) {
+                              double * __restrict__ dst) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const size_t src = (size_t)(perm ? perm[i] : i) * nv;
-    for (int v = 0; v < nv; v++) soa[(size_t)v * npad + i] = aos[src + v];
+    if (nv == 4) for (int v = 0; v < 4; v++) dst[4 * (size_t)i + v] = aos[src + v];
+    else for (int v = 0; v < nv; v++) dst[(size_t)v * npad + i] = aos[src + v];
 }
 
-// aos[perm[i]][v] = soa[v][i]
-__global__ void export_kernel(const double * __restrict__ soa, const uint32_t * __restrict__ perm, uint32_t n, uint32_t npad, int nv,
+// the inverse
+__global__ void export_kernel(const double * __restrict__ srcdev, const uint32_t * __restrict__ perm, uint32_t n, uint32_t npad, int nv,
                               double * __restrict__ aos) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const size_t dst = (size_t)(perm ? perm[i] : i) * nv;
-    for (int v = 0; v < nv; v++) aos[dst + v] = soa[(size_t)v * npad + i];
+    if (nv == 4) for (int v = 0; v < 4; v++) aos[dst + v] = srcdev[4 * (size_t)i + v];
+    else for (int v = 0; v < nv; v++) aos[dst + v] = srcdev[(size_t)v * npad + i];
+}
+
+// prim[5][i] = U[i][0]: the density plane the CFL kernel reads next to the reference's five primitives
+__global__ void rho_plane_kernel(const double * __restrict__ U, uint32_t n, uint32_t npad, double * __restrict__ prim) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) prim[5 * (size_t)npad + i] = U[4 * (size_t)i];
 }
 
 // out[perm[i]] = scal[which] * v[i]   — KokkosBlas::scal(cfl_local, dt, cfl_local), solver/solver.cpp:584
@@ -38,14 +47,14 @@ __global__ void gather_kernel(const double * __restrict__ soa, const uint32_t * 
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 4u * n) return;
     const uint32_t k = t >> 2, v = t & 3u;
-    buf[t] = soa[(size_t)v * npad + idx[k]];
+    buf[t] = soa[4 * (size_t)idx[k] + v];
 }
 __global__ void scatter_kernel(const double * __restrict__ buf, const uint32_t * __restrict__ idx, uint32_t n, uint32_t npad,
                                double * __restrict__ soa) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 4u * n) return;
     const uint32_t k = t >> 2, v = t & 3u;
-    soa[(size_t)v * npad + idx[k]] = buf[t];
+    soa[4 * (size_t)idx[k] + v] = buf[t];
 }
 
 __global__ void apply_dt_kernel(double * scal, long long * max_bits, double cfl, double global_max, int use_global) {
@@ -70,7 +79,7 @@ __global__ void export_faces_kernel(const double * __restrict__ Fc, const double
         const uint32_t f = perm_faces[fcode & 0x7FFFFFFFu], side = fcode >> 31;
         for (int q = 0; q < Q; q++)
             for (int v = 0; v < 4; v++)
-                F[(((size_t)f * Q + q) * 2 + side) * 4 + v] = Fc ? Fc[((size_t)(j * Q + q) * 4 + v) * npad + i] : U[(size_t)v * npad + i];
+                F[(((size_t)f * Q + q) * 2 + side) * 4 + v] = Fc ? Fc[((size_t)i * (n_slots * Q) + (j * Q + q)) * 4 + v] : U[4 * (size_t)i + v];
     }
 }
 
@@ -83,6 +92,9 @@ void launch_import_state(const double * aos, const uint32_t * perm, uint32_t n, 
 }
 void launch_export_state(const double * soa, const uint32_t * perm, uint32_t n, uint32_t npad, int nv, double * aos, cudaStream_t st) {
     if (n) export_kernel<<<blocks(n, 256), 256, 0, st>>>(soa, perm, n, npad, nv, aos);
+}
+void launch_rho_plane(const double * U, uint32_t n, uint32_t npad, double * prim, cudaStream_t st) {
+    if (n) rho_plane_kernel<<<blocks(n, 256), 256, 0, st>>>(U, n, npad, prim);
 }
 void launch_export_scaled(const double * v, const double * scal, int which, const uint32_t * perm, uint32_t n, double * out, cudaStream_t st) {
     if (n) export_scaled_kernel<<<blocks(n, 256), 256, 0, st>>>(v, scal, which, perm, n, out);

@@ -70,8 +70,13 @@ int main(int argc, char ** argv) {
             Mesh & m = *s.mesh;
 
             // ---- the reference's host mesh arrays, as they are (mesh/mesh.h:242-253)
+            std::vector<std::string> zone_names;                    // FaceZone::get_name() returns by value
+            for (auto & z : *m.face_zones()) zone_names.push_back(z.get_name());
             std::vector<mlb_zone> zones;
-            for (auto & z : *m.face_zones()) zones.push_back({z.get_name().c_str(), (uint32_t)z.h_faces.extent(0), z.h_faces.data()});
+            {
+                size_t iz = 0;
+                for (auto & z : *m.face_zones()) zones.push_back({zone_names[iz++].c_str(), (uint32_t)z.h_faces.extent(0), z.h_faces.data()});
+            }
             mlb_mesh mm{};
             mm.n_cells = m.n_cells; mm.n_faces = m.n_faces; mm.n_nodes = m.n_nodes;
             mm.node_coords = m.h_node_coords.data();

@@ -10,8 +10,6 @@ tail -5 gpurun_out/pytest_gpu.log
 if [ "${BENCH:-1}" = 1 ]; then
 $T 600 python bench.py --steps 20 --warmup 3 ${BENCH_ARGS:-} > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-MLB_STREAM_GATHER=direct $T 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e ${BENCH_ARGS:-} > gpurun_out/bench_direct.json 2> gpurun_out/bench_direct.err; echo "bench direct-gather rc=$?"
-tail -c 700 gpurun_out/bench_direct.json
 if [ "${STRICT:-1}" = 1 ]; then
 $T 600 python bench.py --steps 20 --warmup 3 --fp strict --no-cpu-baseline ${BENCH_ARGS:-} > gpurun_out/bench_strict.json 2> gpurun_out/bench_strict.err; echo "bench strict rc=$?"
 tail -c 1000 gpurun_out/bench_strict.json
@@ -20,7 +18,7 @@ fi
 if [ "${NCU:-1}" = 1 ]; then
 $T 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline ${BENCH_ARGS:-} > gpurun_out/ncu_launches.log 2>&1
-$T 900 ncu --set full --clock-control none --import-source on -k regex:'teno_|flux_stage' -s 6 -c 4 -f -o gpurun_out/prof \
+$T 900 ncu --set full --clock-control none --import-source on -k regex:'teno_|face_flux|gather_stage|cfl_kernel' -s 8 -c 7 -f -o gpurun_out/prof \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline ${BENCH_ARGS:-} > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out
 fi

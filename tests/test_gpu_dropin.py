@@ -134,7 +134,7 @@ def run(binary, toml, workdir, extra=()):
 
 @pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(DROPIN)), reason="oracle/_ref binaries not built (need /root/reference)")
 @pytest.mark.parametrize("name,toml,fp,tol", [("sod", SOD, "strict", 1e-9), ("sod", SOD, "fast", 1e-9), ("wedge", WEDGE, "strict", 0.0),
-                                              ("wedge", WEDGE, "fast", 1e-10)])
+                                              ("wedge", WEDGE, "fast", 1e-10)], ids=["sod-strict", "sod-fast", "wedge-strict", "wedge-fast"])
 def test_reference_host_with_b200_hot_path_writes_the_reference_solution(tmp_path, name, toml, fp, tol):
     a, b = str(tmp_path / "ref"), str(tmp_path / "b200")
     run(REF, toml, a)
