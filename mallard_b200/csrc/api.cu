@@ -217,7 +217,8 @@ ReconStreamArgs stream_args(mlb_ctx & c, const double * Uin) {
     const TenoTables & T = c.prep.teno;
     r.g = c.g; r.Uin = Uin; r.Fc = c.Fc; r.mat = c.d_fm_mat; r.ids = c.d_fm_ids; r.area0 = c.d_fm_area0;
     r.n_tiles = c.n_ftiles; r.order = T.order; r.fixed_weights = c.num.teno_fixed;
-    r.async_gather = 1;
+    static const int variant = [] { const char * e = getenv("MLB_STREAM_GATHER"); return e && !strcmp(e, "ownvar") ? 2 : 1; }();
+    r.async_gather = variant;   // tuning knob: which lanes fetch which neighbour bytes (see teno_stream.cuh)
     for (size_t i = 0; i < c.prep.qf_x.size() && i < 4; i++) r.qf_x[i] = c.prep.qf_x[i];
     for (int i = 0; i < T.K; i++) r.psi_bar[i] = T.psi_bar[i];
     for (size_t i = 0; i < T.OIs.size(); i++) r.OIs[i] = T.OIs[i];

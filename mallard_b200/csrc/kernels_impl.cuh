@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(RECON_THREADS) teno_recon_kernel(const __grid_
                 if (w[s] == 0.0) continue;
                 out = poly_accumulate<K>(out, w[s], dof_sm + (size_t)(s * K) * RECON_THREADS + tid, Px, Py, cbar, std::make_integer_sequence<int, K>{});
             }
-            a.Fc[((size_t)(j * Q + q) * 4 + var) * Np + cell] = out;
+            a.Fc[((size_t)cell * (a.g.n_slots * Q) + (j * Q + q)) * 4 + var] = out;
         }
     }
 }

@@ -104,13 +104,16 @@ __device__ __forceinline__ void cp_async16(void * dst, const void * src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 
-template <int ORDER>
+// OWNVAR = false: the four variable-threads of a cell share the fetch of a neighbour list (16-byte copies, thread `var` takes
+//                  neighbours var, var + 4, ...); OWNVAR = true: every thread fetches its own variable (8 bytes) of every
+//                  neighbour — the four lanes of a cell then hit the same 32-byte sector and the same shared-memory row.
+template <int ORDER, bool OWNVAR>
 __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_constant__ ReconStreamArgs a) {
     using C = Cfg<ORDER>;
     using SM = Smem<ORDER>;
     constexpr int K = C::K, KR = C::KR, MC = C::MC, NP = C::NP, Q = C::Q, S = FAST_S, NF = FAST_S - 1, STAGES = SM::STAGES;
     constexpr int CPT = S * C::NCH;                            // chunks per tile
-    constexpr int NG = (MC + 3) / 4;                           // neighbour states each of a cell's 4 threads fetches per stencil
+    constexpr int NG = OWNVAR ? MC : (MC + 3) / 4;             // neighbour states a thread requests per stencil
     extern __shared__ __align__(128) unsigned char smem[];     // ring | ubuf | fxbuf
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
     unsigned char * ring = smem;
@@ -171,18 +174,30 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
     uint32_t id[NG], id0;                                             // ids this thread fetches for the NEXT stencil; its first id
     auto load_ids = [&](uint32_t t, int s) {
         const uint32_t * __restrict__ p = a.ids + ((size_t)t * S + s) * (MC * CT) + cl;
-        id0 = p[0];
+        if (OWNVAR) {
 #pragma unroll
-        for (int i = 0; i < NG; i++) id[i] = (var + 4 * i < MC) ? p[(var + 4 * i) * CT] : 0u;
+            for (int i = 0; i < NG; i++) id[i] = p[i * CT];
+            id0 = id[0];
+        } else {
+            id0 = p[0];
+#pragma unroll
+            for (int i = 0; i < NG; i++) id[i] = (var + 4 * i < MC) ? p[(var + 4 * i) * CT] : 0u;
+        }
     };
     auto request_states = [&](int parity) {
-        double * dst = ubuf + ((size_t)parity * MC * CT + cl) * 4;
+        if (OWNVAR) {
+            double * dst = ubuf + (size_t)parity * MC * CT * 4 + tid;
 #pragma unroll
-        for (int i = 0; i < NG; i++) {
-            if (var + 4 * i < MC) {
-                const double * src = a.Uin + 4 * (size_t)id[i];
-                cp_async16(dst + (size_t)(var + 4 * i) * CT * 4, src);
-                cp_async16(dst + (size_t)(var + 4 * i) * CT * 4 + 2, src + 2);
+            for (int i = 0; i < NG; i++) cp_async8(dst + (size_t)i * CONSUMERS, a.Uin + 4 * (size_t)id[i] + var);
+        } else {
+            double * dst = ubuf + ((size_t)parity * MC * CT + cl) * 4;
+#pragma unroll
+            for (int i = 0; i < NG; i++) {
+                if (var + 4 * i < MC) {
+                    const double * src = a.Uin + 4 * (size_t)id[i];
+                    cp_async16(dst + (size_t)(var + 4 * i) * CT * 4, src);
+                    cp_async16(dst + (size_t)(var + 4 * i) * CT * 4 + 2, src + 2);
+                }
             }
         }
     };
@@ -336,21 +351,25 @@ __global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_co
     }
 }
 
-template <int ORDER>
-static void launch_stream_t(const ReconStreamArgs & a, cudaStream_t st) {
+template <int ORDER, bool OWNVAR>
+static void launch_stream_v(const ReconStreamArgs & a, cudaStream_t st) {
     const size_t smem = Smem<ORDER>::TOTAL;
     static int ctas = 0;
     if (!ctas) {
-        cudaFuncSetAttribute(teno_stream_kernel<ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(teno_stream_kernel<ORDER, OWNVAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, teno_stream_kernel<ORDER>, THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, teno_stream_kernel<ORDER, OWNVAR>, THREADS, smem);
         ctas = sms * (per_sm > 0 ? per_sm : 1);
     }
     if (!a.n_tiles) return;
     const unsigned grid = a.n_tiles < (uint32_t)ctas ? a.n_tiles : (unsigned)ctas;   // persistent: one CTA slot per resident CTA
-    teno_stream_kernel<ORDER><<<grid, THREADS, smem, st>>>(a);
+    teno_stream_kernel<ORDER, OWNVAR><<<grid, THREADS, smem, st>>>(a);
+}
+template <int ORDER>
+static void launch_stream_t(const ReconStreamArgs & a, cudaStream_t st) {
+    if (a.async_gather == 2) launch_stream_v<ORDER, true>(a, st); else launch_stream_v<ORDER, false>(a, st);
 }
 
 static bool stream_supported(int order, int M, int Q, int basis, int n_slots) {

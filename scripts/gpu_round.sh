@@ -10,6 +10,10 @@ tail -5 gpurun_out/pytest_gpu.log
 if [ "${BENCH:-1}" = 1 ]; then
 $T 600 python bench.py --steps 20 --warmup 3 ${BENCH_ARGS:-} > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+if [ -n "${VARIANT:-}" ]; then
+MLB_STREAM_GATHER=$VARIANT $T 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e ${BENCH_ARGS:-} > gpurun_out/bench_$VARIANT.json 2> gpurun_out/bench_$VARIANT.err; echo "bench $VARIANT rc=$?"
+tail -c 600 gpurun_out/bench_$VARIANT.json
+fi
 if [ "${STRICT:-1}" = 1 ]; then
 $T 600 python bench.py --steps 20 --warmup 3 --fp strict --no-cpu-baseline ${BENCH_ARGS:-} > gpurun_out/bench_strict.json 2> gpurun_out/bench_strict.err; echo "bench strict rc=$?"
 tail -c 1000 gpurun_out/bench_strict.json
