@@ -264,6 +264,8 @@ def main():
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "n_cells": nc, "fp_mode": a.fp, "recon": a.recon, "l2": "inputs larger than L2 (TENO tables %.1f GB per stage)" % (stats[2] / 1e9),
                        "device_bytes": stats[2], "preprocess_seconds": stats[1], "setup_seconds": setup_s,
+                       "preprocess": {"host_total_s": stats[1], "host_stencil_search_s": stats[8], "host_matrices_s": stats[9],
+                                      "device_table_build_s": stats[10]},
                        "note": "reference-faithful TENO: like the reference, the state turns non-finite inside step 1 (SURVEY 0.2); cost is data-independent"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "kernels": kernels}
     print(json.dumps(line))

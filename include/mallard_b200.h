@@ -229,6 +229,9 @@ void mlb_plan_destroy(mlb_plan *plan);
 
 /* ---- host mesh generators: Mesh::init_cart / init_cart_tri / init_wedge (mesh/mesh.cpp:305-848) */
 int mlb_host_mesh_generate(mlb_host_mesh **out, int32_t type, uint32_t nx, uint32_t ny, double Lx, double Ly);
+/* connectivity + node coordinates supplied by the caller (any unstructured mesh of triangles / quads); geometry computed as
+ * Mesh::compute_cell_centroids / compute_cell_volumes / compute_face_areas / compute_face_normals do (mesh/mesh.cpp:167-261) */
+int mlb_host_mesh_from_arrays(mlb_host_mesh **out, const mlb_mesh *mesh);
 int mlb_host_mesh_view(const mlb_host_mesh *m, mlb_mesh *view);   /* pointers stay valid until mlb_host_mesh_free */
 void mlb_host_mesh_free(mlb_host_mesh *m);
 

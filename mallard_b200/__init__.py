@@ -51,6 +51,12 @@ class Mesh:
         h = C.c_void_p()
         if lib().mlb_host_mesh_generate(C.byref(h), MESH[mtype], Nx, Ny, Lx, Ly):
             raise MallardError(_last_error())
+        m._take(h)
+        return m
+
+    def _take(self, h):
+        """Copies the arrays of a library-side host mesh into numpy and frees it."""
+        m = self
         m._h = h
         v = _abi.MeshView()
         if lib().mlb_host_mesh_view(h, C.byref(v)):
@@ -71,12 +77,22 @@ class Mesh:
             cell_coords=arr(v.cell_coords, 2 * nc, np.float64).reshape(nc, 2),
             cell_volume=arr(v.cell_volume, nc, np.float64), face_area=arr(v.face_area, nf, np.float64),
             face_normals=arr(v.face_normals, 2 * nf, np.float64).reshape(nf, 2))
+        m.zones = []
         for i in range(v.n_zones):
             z = v.zones[i]
             m.zones.append((z.name.decode(), arr(z.faces, z.n_faces, np.uint32)))
         lib().mlb_host_mesh_free(h)
         m._h = None
-        return m
+
+    def compute_geometry(self):
+        """Cell centroids / volumes, face areas / normals from connectivity and node coordinates
+        (Mesh::compute_* , src/mesh/mesh.cpp:167-261), through the library's host code."""
+        v, keep = self.view()
+        h = C.c_void_p()
+        if lib().mlb_host_mesh_from_arrays(C.byref(h), C.byref(v)):
+            raise MallardError(_last_error())
+        self._take(h)
+        return self
 
     @classmethod
     def from_arrays(cls, arrays, zones):
@@ -338,7 +354,7 @@ class Solver:
         rhs = None if rhs is None else np.ascontiguousarray(rhs, dtype=np.float64)
         self._ok(lib().mlb_set_rhs_override(self._h, _ptr(rhs)))
 
-    _ARRAY_DTYPES = {"perm_cells": np.uint32, "perm_faces": np.uint32, "teno:poly_indices": np.uint8,
+    _ARRAY_DTYPES = {"dev:fm_ids": np.uint32, "perm_cells": np.uint32, "perm_faces": np.uint32, "teno:poly_indices": np.uint8,
                      "teno:offsets_stencil_groups": np.uint32, "teno:offsets_stencils": np.uint32, "teno:stencils": np.uint32,
                      "teno:offsets_reconstruction_matrices": np.uint32}
 

@@ -4,7 +4,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmallard_b200.so")
+LIB_PATH = os.environ.get("MLB_LIB") or os.path.join(_HERE, "libmallard_b200.so")   # MLB_LIB: A/B kernel experiments
 
 RECON = {"FO": 0, "TENO": 1}
 RIEMANN = {"Rusanov": 0, "HLL": 1, "HLLC": 2}
@@ -102,6 +102,7 @@ SYMBOLS = {
     "mlb_plan_get": (C.c_int, [VP, C.c_char_p, VP, C.POINTER(U64)]),
     "mlb_plan_destroy": (None, [VP]),
     "mlb_host_mesh_generate": (C.c_int, [C.POINTER(VP), I32, U32, U32, DBL, DBL]),
+    "mlb_host_mesh_from_arrays": (C.c_int, [C.POINTER(VP), C.POINTER(MeshView)]),
     "mlb_host_mesh_view": (C.c_int, [VP, C.POINTER(MeshView)]),
     "mlb_host_mesh_free": (None, [VP]),
 }

@@ -85,6 +85,7 @@ struct mlb_ctx {
     int last_temp = 1;                 // buffer that corresponds to the reference's solution_vec[1]
     bool has_override = false;
     size_t device_bytes = 0;
+    double table_build_ms = 0.0;       // device-side TENO table construction (teno_tables.cu)
 
     // halo
     std::vector<int32_t> peers;
@@ -298,6 +299,42 @@ void export_state(mlb_ctx & c, const double * soa, int nv, double * out_host) {
     CUDA_OK(cudaStreamSynchronize(c.stream));
 }
 
+// the reconstruction matrices of the compact tables are computed in HBM (teno_tables.cu), bit-identical to
+// the host preprocessor's; only stencil ids and node coordinates are uploaded.
+void build_tables_on_device(mlb_ctx & c) {
+    TenoTables & T = c.prep.teno;
+    const int KR = T.K - 1, MC = T.M - 1;
+    const size_t frow = (size_t)(2 * (MC / 2) + 1) * FAST_CT;
+    const size_t n_mat = (size_t)c.n_ftiles * FAST_S * KR * frow;
+    c.d_fm_mat = c.alloc<double>(n_mat);
+    c.d_fm_area0 = c.alloc<double>((size_t)c.n_ftiles * FAST_CT);
+    double * d_tri = dev_upload(T.tri_xy, c.stream);
+    int * d_err = dev_alloc<int>(1);
+    CUDA_OK(cudaMemsetAsync(d_err, 0, sizeof(int), c.stream));
+    TableBuildArgs a{};
+    a.n_recon = c.prep.N_recon; a.n_ftiles = c.n_ftiles; a.order = T.order; a.nq = T.nq_cell;
+    a.tri_xy = d_tri; a.fm_ids = c.d_fm_ids; a.fm_mat = c.d_fm_mat; a.fm_area0 = c.d_fm_area0; a.err_flag = d_err;
+    for (int q = 0; q < T.nq_cell; q++) { a.qc_xy[2 * q] = T.qc_xy[2 * q]; a.qc_xy[2 * q + 1] = T.qc_xy[2 * q + 1]; a.qc_w[q] = T.qc_w[q]; }
+    for (int k = 0; k < T.K; k++) a.psi_bar[k] = T.psi_bar[k];
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    CUDA_OK(cudaEventRecord(e0, c.stream));
+    launch_teno_tables(a, c.stream);
+    c.launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(e1, c.stream));
+    int err = 0;
+    CUDA_OK(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    CUDA_OK(cudaStreamSynchronize(c.stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c.table_build_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_tri); cudaFree(d_err);
+    if (err) throw std::runtime_error("TENO: reconstruction matrix has a non-zero first column; compact tables unavailable (use fp_mode strict)");
+    if (getenv("MLB_PREP_TIMING")) fprintf(stderr, "[mlb] device table build: %u cells, %.2f ms\n", c.prep.N_recon, ms);
+}
+
 mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_numerics * numerics, const mlb_physics * physics,
                       const mlb_bc * bcs, int32_t n_bcs, const mlb_parallel * par) {
     if (!mesh || !numerics || !physics) throw std::runtime_error("mlb_create: NULL argument");
@@ -351,6 +388,11 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
         c->streaming = c->kt->stream_supported(p, (int)(uint16_t)(factor * K), Q, c->num.basis, n_slots);
     }
     opt.fast_tables = c->streaming;
+    {   // the compact tables' matrices are built on the device unless MLB_HOST_TABLES=1 asks for the host path (parity check)
+        const char * e = getenv("MLB_HOST_TABLES");
+        const int p = c->num.basis_order;
+        opt.device_tables = c->streaming && !(e && e[0] == '1') && teno_tables_device_supported(p, c->num.basis, 7 /* Dunavant rules have <= 7 points */);
+    }
     opt.part = part; opt.rank = c->rank; opt.n_ranks = c->n_ranks;
     preprocess(hm, c->num, bc_zones, opt, c->prep);
     Prep & P = c->prep;
@@ -402,13 +444,15 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
         CUDA_OK(cudaMemsetAsync(c->Fc, 0, (size_t)P.n_slots * P.Q * 4 * NP * sizeof(double), c->stream));
         if (c->streaming) {
             c->n_ftiles = (uint32_t)((P.N_recon + FAST_CT - 1) / FAST_CT);
-            c->d_fm_ids = c->upload(T.fm_ids); c->d_fm_area0 = c->upload(T.fm_area0); c->d_fm_mat = c->upload(T.fm_mat);
+            c->d_fm_ids = c->upload(T.fm_ids);
+            if (opt.device_tables) build_tables_on_device(*c);
+            else { c->d_fm_area0 = c->upload(T.fm_area0); c->d_fm_mat = c->upload(T.fm_mat); }
         } else {
             c->d_st_ids = c->upload(T.st_ids); c->d_st_area = c->upload(T.st_area); c->d_st_mat = c->upload(T.st_mat);
         }
         CUDA_OK(cudaStreamSynchronize(c->stream));
         uvec().swap(T.st_ids); dvec().swap(T.st_area); dvec().swap(T.st_mat);   // host copies no longer needed
-        uvec().swap(T.fm_ids); dvec().swap(T.fm_area0); dvec().swap(T.fm_mat);
+        uvec().swap(T.fm_ids); dvec().swap(T.fm_area0); dvec().swap(T.fm_mat); dvec().swap(T.tri_xy);
     }
     for (auto & e : c->ev) CUDA_OK(cudaEventCreate(&e));
     CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -637,9 +681,17 @@ int mlb_get_array(mlb_ctx * c, const char * name, void * out, uint64_t * nbytes)
     } else if (n == "cfl_local") {
         *nbytes = (uint64_t)c->nc_ref * 8;
         if (out) { if (mlb_get_state(c, nullptr, nullptr, (double *)out)) throw std::runtime_error(c->err); }
+    } else if (n == "dev:fm_mat" || n == "dev:fm_area0" || n == "dev:fm_ids") {   // the device-resident compact tables, as they are
+        if (!c->streaming) throw std::runtime_error("context has no streaming TENO tables");
+        const int KR = T.K - 1, MC = T.M - 1;
+        const size_t frow = (size_t)(2 * (MC / 2) + 1) * FAST_CT;
+        const void * src = n == "dev:fm_mat" ? (const void *)c->d_fm_mat : n == "dev:fm_area0" ? (const void *)c->d_fm_area0 : (const void *)c->d_fm_ids;
+        *nbytes = n == "dev:fm_mat" ? (uint64_t)c->n_ftiles * FAST_S * KR * frow * 8 : n == "dev:fm_area0" ? (uint64_t)c->n_ftiles * FAST_CT * 8
+                                    : (uint64_t)c->n_ftiles * FAST_S * MC * FAST_CT * 4;
+        if (out) CUDA_OK(cudaMemcpy(out, src, *nbytes, cudaMemcpyDeviceToHost));
     } else if (n == "stats") {
-        double s[8] = {(double)c->launches, P.seconds, (double)c->device_bytes, (double)P.N, (double)P.N_owned, (double)P.NF,
-                       (double)P.N_recon, (double)c->n_stages};
+        double s[12] = {(double)c->launches, P.seconds, (double)c->device_bytes, (double)P.N, (double)P.N_owned, (double)P.NF,
+                        (double)P.N_recon, (double)c->n_stages, P.seconds_stencils, P.seconds_matrices, c->table_build_ms * 1e-3, 0.0};
         host(s, sizeof(s));
     } else if (n.rfind("teno:", 0) == 0) {
         if (!c->teno) throw std::runtime_error("context has no TENO tables");
@@ -1018,6 +1070,17 @@ int mlb_host_mesh_generate(mlb_host_mesh ** out, int32_t type, uint32_t nx, uint
     if (!out) throw std::runtime_error("out is NULL");
     std::unique_ptr<mlb_host_mesh> m(new mlb_host_mesh());
     host_mesh_generate(m->m, type, nx, ny, Lx, Ly);
+    *out = m.release();
+    API_END(none)
+}
+int mlb_host_mesh_from_arrays(mlb_host_mesh ** out, const mlb_mesh * mesh) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!out || !mesh) throw std::runtime_error("NULL argument");
+    std::unique_ptr<mlb_host_mesh> m(new mlb_host_mesh());
+    mlb_mesh v = *mesh;
+    v.cell_coords = nullptr;   // geometry is always recomputed here (Mesh::compute_cell_centroids/volumes/face_areas/normals, mesh/mesh.cpp:167-261)
+    host_mesh_from_view(m->m, v);
     *out = m.release();
     API_END(none)
 }

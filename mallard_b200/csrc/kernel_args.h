@@ -92,6 +92,18 @@ struct ReconStreamArgs {       // teno_stream.cuh
     double OIs[14 * 14];
 };
 
+struct TableBuildArgs {        // teno_tables.cu: reconstruction matrices built on the device
+    uint32_t n_recon, n_ftiles;
+    int32_t order, nq;
+    const double * tri_xy;        // [Npad][6] node coordinates of every held cell (library numbering, nodes_of_cell order)
+    const uint32_t * fm_ids;      // compact stencil ids (library numbering)
+    double * fm_mat;
+    double * fm_area0;
+    int * err_flag;
+    double qc_xy[14], qc_w[7];    // Dunavant cell quadrature
+    double psi_bar[15];
+};
+
 struct CflArgs {
     DevGeom g;
     GasParams gas;
@@ -122,6 +134,10 @@ struct KernelTable {
 
 const KernelTable * kernels_strict();
 const KernelTable * kernels_fast();
+
+// device-side construction of the compact TENO tables (teno_tables.cu)
+bool teno_tables_device_supported(int order, int basis, int nq);
+void launch_teno_tables(const TableBuildArgs & a, cudaStream_t st);
 
 // layout helpers (mode independent, utils.cu)
 void launch_import_state(const double * aos, const uint32_t * perm, uint32_t n, uint32_t npad, int nv, double * soa, cudaStream_t);

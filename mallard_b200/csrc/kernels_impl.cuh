@@ -218,47 +218,84 @@ __device__ __forceinline__ void rk_update(const RkArgs & rk, const double * Uin,
 // numerics/flux_functor.h:124-162; boundary ghost states boundary/*.cpp), result A * (1/2 sum_q w_q F_q) stored once per
 // face.  The reference scatters -+ that product into both cells with atomic_add; here the cells gather it (next kernel).
 // ---------------------------------------------------------------------------------------------------------------
-template <int RS, bool TENO>
-__global__ void __launch_bounds__(128) face_flux_kernel(const __grid_constant__ StageArgs a) {
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= a.g.NF) return;
-    const int Q = TENO ? a.g.Q : 1;
+#ifndef MLB_FLUX_MINB
+#define MLB_FLUX_MINB 4
+#endif
+// QT > 0: the number of face quadrature points is known at compile time and ONE THREAD PER (face, quadrature point) solves
+// one Riemann problem; the QT lanes of a face then combine w_q F_q in the reference's q order with warp shuffles (same
+// rounding as the sequential loop) and lane 0 stores.  Twice the parallelism and half the dependent sqrt/div chain per
+// thread of a per-face loop.  QT = 0: one thread per face loops over a run-time Q.
+template <int RS, bool TENO, int QT>
+__global__ void __launch_bounds__(128, MLB_FLUX_MINB) face_flux_kernel(const __grid_constant__ StageArgs a) {
+    constexpr int TPF = QT > 0 ? QT : 1;                 // threads per face (1, 2 or 4: divides the warp)
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = gid / TPF < a.g.NF;
+    const uint32_t f = valid ? gid / TPF : a.g.NF - 1;   // surplus lanes recompute the last face and do not store
+    const int lane_q = gid % TPF;
+    const int Q = !TENO ? 1 : (QT > 0 ? QT : a.g.Q);
     const int NPT = a.g.n_slots * Q;                     // face-value points per cell
     const uint32_t cl = a.g.face_cl[f];
     const int32_t cr = a.g.face_cr[f];
-    double4 * out = reinterpret_cast<double4 *>(a.AF) + f;
-    if (cr == INT32_MIN) { *out = make_double4(0.0, 0.0, 0.0, 0.0); return; }   // boundary zone without a [[boundaries]] entry
     const double nx = a.g.face_nx[f], ny = a.g.face_ny[f], area = a.g.face_area[f];
     const uint32_t slots = TENO ? a.g.face_slots[f] : 0u;
     const int sl = slots & 15u, sr = slots >> 4;
-    const BcParams * bc = cr < 0 ? &a.ph.bcs[-cr - 1] : nullptr;
-    double fsum[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int q = 0; q < Q; q++) {
+    const bool no_flux = cr == INT32_MIN;                // boundary zone without a [[boundaries]] entry
+    const BcParams * bc = (cr < 0 && !no_flux) ? &a.ph.bcs[-cr - 1] : nullptr;
+
+    auto flux_at = [&](int q, double * ft) {
         double Ul[4], Pl[5];
         if (TENO) ld4(a.Fc, (size_t)cl * NPT + (sl * Q + q), Ul); else ld4(a.Uin, cl, Ul);
-        cons_to_prim(a.ph.gas, Ul, Pl);
-        const FaceState L = {Ul[0], Pl[0], Pl[1], Pl[2], Pl[4]};
-        double ft[4];
         if (cr >= 0) {
             double Ur[4], Pr[5];
             if (TENO) ld4(a.Fc, (size_t)cr * NPT + (sr * Q + q), Ur); else ld4(a.Uin, (size_t)cr, Ur);
+            cons_to_prim(a.ph.gas, Ul, Pl);
             cons_to_prim(a.ph.gas, Ur, Pr);
+            const FaceState L = {Ul[0], Pl[0], Pl[1], Pl[2], Pl[4]};
             const FaceState R = {Ur[0], Pr[0], Pr[1], Pr[2], Pr[4]};
             riemann_flux<RS>(ft, nx, ny, L, R, a.ph.gas.gamma);
-        } else if (bc->type == MLB_BC_WALL_ADIABATIC) {   // boundary_wall_adiabatic.cpp:39-70
+            return;
+        }
+        cons_to_prim(a.ph.gas, Ul, Pl);
+        const FaceState L = {Ul[0], Pl[0], Pl[1], Pl[2], Pl[4]};
+        if (bc->type == MLB_BC_WALL_ADIABATIC) {          // boundary_wall_adiabatic.cpp:39-70
             ft[0] = 0.0; ft[1] = Pl[2] * nx; ft[2] = Pl[2] * ny; ft[3] = 0.0;
         } else {
             FaceState gh;
             ghost_state(*bc, a.ph.gas, nx, ny, Ul, Pl, gh);
             riemann_flux<RS>(ft, nx, ny, L, gh, a.ph.gas.gamma);
         }
-        const double wq = a.ph.qf_w[q];
+    };
+
+    double fsum[4] = {0.0, 0.0, 0.0, 0.0};
+    if (QT == 0) {
+        if (!no_flux)
+            for (int q = 0; q < Q; q++) {
+                double ft[4];
+                flux_at(q, ft);
+                const double wq = a.ph.qf_w[q];
 #pragma unroll
-        for (int v = 0; v < 4; v++) fsum[v] += wq * ft[v];     // flux_functor.h:151
+                for (int v = 0; v < 4; v++) fsum[v] += wq * ft[v];     // flux_functor.h:151
+            }
+    } else {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        if (!no_flux) {
+            double ft[4];
+            flux_at(lane_q, ft);
+            const double wq = a.ph.qf_w[lane_q];
+#pragma unroll
+            for (int v = 0; v < 4; v++) t[v] = wq * ft[v];
+        }
+#pragma unroll
+        for (int q = 0; q < TPF; q++) {                                // fsum = ((0 + t_0) + t_1) + ..., flux_functor.h:151
+#pragma unroll
+            for (int v = 0; v < 4; v++) fsum[v] += __shfl_sync(0xffffffffu, t[v], q, TPF);
+        }
+        if (lane_q != 0) return;
     }
+    if (!valid) return;
 #pragma unroll
     for (int v = 0; v < 4; v++) fsum[v] = area * (fsum[v] * 0.5);   // flux_functor.h:153,156-161: (-A)*F == -(A*F) exactly
-    *out = make_double4(fsum[0], fsum[1], fsum[2], fsum[3]);
+    reinterpret_cast<double4 *>(a.AF)[f] = make_double4(fsum[0], fsum[1], fsum[2], fsum[3]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -552,10 +589,12 @@ __global__ void prims_soa_kernel(const GasParams g, uint32_t n, uint32_t npad, c
 // ---------------------------------------------------------------------------------------------------------------
 template <int RS>
 static void launch_faces_rs(const StageArgs & a, cudaStream_t st) {
-    const unsigned grid = (a.g.NF + 127u) / 128u;
-    if (grid == 0) return;
-    if (a.teno) face_flux_kernel<RS, true><<<grid, 128, 0, st>>>(a);
-    else face_flux_kernel<RS, false><<<grid, 128, 0, st>>>(a);
+    if (a.g.NF == 0) return;
+    auto grid = [&](unsigned tpf) { return (unsigned)(((uint64_t)a.g.NF * tpf + 127u) / 128u); };
+    if (!a.teno) face_flux_kernel<RS, false, 1><<<grid(1), 128, 0, st>>>(a);
+    else if (a.g.Q == 1) face_flux_kernel<RS, true, 1><<<grid(1), 128, 0, st>>>(a);
+    else if (a.g.Q == 2) face_flux_kernel<RS, true, 2><<<grid(2), 128, 0, st>>>(a);
+    else face_flux_kernel<RS, true, 0><<<grid(1), 128, 0, st>>>(a);
 }
 static void launch_faces(const StageArgs & a, cudaStream_t st) {
     switch (a.ph.riemann) {

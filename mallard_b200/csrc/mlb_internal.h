@@ -79,6 +79,7 @@ struct TenoTables {
     bool fast = false;
     uvec fm_ids;
     dvec fm_mat, fm_area0, OIs;
+    dvec tri_xy;                  // [Npad][6] node coordinates per held cell (library numbering) when the device builds fm_mat
     // Reference-layout CSR copies (reference numbering) for parity checks (optional, small meshes only)
     bool keep_ref = false;
     uvec ref_off_groups, ref_off_stencils, ref_stencils, ref_off_mats;
@@ -112,13 +113,14 @@ struct Prep {
     std::vector<uint8_t> face_slots;   // [NFpad] slot in cell 0 | slot in cell 1 << 4
     dvec qf_x, qf_w;       // face quadrature
     TenoTables teno;
-    double seconds = 0.0;
+    double seconds = 0.0, seconds_stencils = 0.0, seconds_matrices = 0.0;
 };
 
 struct PrepOptions {
     int renumber = MLB_RENUMBER_RCM;
     bool keep_ref_tables = false;
     bool fast_tables = false;         // build the compact streaming tables instead of the bit-faithful ones
+    bool device_tables = false;       // ... and leave their matrices to the device (teno_tables.cu); the host emits ids + node coordinates
     const int32_t * part = nullptr;   // partition vector (reference numbering) or null
     int rank = 0, n_ranks = 1;
 };

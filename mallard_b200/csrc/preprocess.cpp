@@ -12,6 +12,8 @@
 #include <chrono>
 #include <cmath>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <numeric>
 #include <queue>
@@ -550,6 +552,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
             }
         }
         if (!err.empty()) throw std::runtime_error(err);
+        P.seconds_stencils = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (opt.part) {
             for (uint32_t x : T.st_ids) if (x != NO_FACE && !cls[x]) { cls[x] = 3; g2.push_back(x); }
             std::sort(g2.begin(), g2.end());
@@ -700,14 +703,26 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
         T.fast = opt.fast_tables;
         const bool strict_tables = !T.fast || T.keep_ref;        // bit-faithful layout (STRICT kernels, parity hooks)
         if (T.fast && (S != FAST_S || M != 2 * K)) throw std::runtime_error("streaming TENO tables need triangles and max_stencil_size_factor 2");
-        T.st_area.assign(n_tiles * S * Mp * TILE, 0.0);
+        if (strict_tables || !opt.device_tables) T.st_area.assign(n_tiles * S * Mp * TILE, 0.0);
         if (strict_tables) T.st_mat.assign(n_tiles * S * K * Mp * TILE, 0.0);
         const int KR = K - 1, MC = M - 1, NPAIR = MC / 2;
         const size_t n_ftiles = (n_recon + FAST_CT - 1) / FAST_CT;
         const size_t frow = (size_t)(2 * NPAIR + 1) * FAST_CT;   // doubles per stored row of one tile
-        if (T.fast) {
+        const bool host_fm = T.fast && !opt.device_tables;       // device_tables: teno_tables.cu builds fm_mat / fm_area0 in HBM
+        if (host_fm) {
             T.fm_mat.assign(n_ftiles * S * KR * frow, 0.0);
             T.fm_area0.assign(n_ftiles * FAST_CT, 0.5);
+        }
+        if (T.fast && opt.device_tables) {   // node coordinates of every held cell, library numbering (the kernel's only geometry input)
+            T.tri_xy.assign(6 * (size_t)P.Npad, 0.0);
+#pragma omp parallel for schedule(static)
+            for (int64_t ii = 0; ii < (int64_t)N; ii++) {
+                const uint32_t * cn = &m.noc[m.onc[order[ii]]];
+                for (int k2 = 0; k2 < 3; k2++) {
+                    T.tri_xy[6 * (size_t)ii + 2 * k2] = m.node_xy[2 * (size_t)cn[k2]];
+                    T.tri_xy[6 * (size_t)ii + 2 * k2 + 1] = m.node_xy[2 * (size_t)cn[k2] + 1];
+                }
+            }
         }
         T.psi_bar.assign(K, 0.0);
         {   // integral_psi_target: row 0 of REFERENCE cell 0's central stencil, i.e. the cell itself (:598-602)
@@ -718,6 +733,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
             for (int k = 0; k < K; k++) T.psi_bar[k] = w.A[k] / a0;
         }
         std::string err;
+        const auto t_mat = std::chrono::steady_clock::now();
 #pragma omp parallel
         {
             MatrixScratch w;
@@ -727,6 +743,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
             for (int64_t ii = 0; ii < (int64_t)n_recon; ii++) {
                 const uint32_t i = (uint32_t)ii;
                 const size_t tile = i / TILE, lane = i % TILE;
+                if (!strict_tables && !host_fm) continue;           // every matrix is built on the device
                 try {
                     for (int s = 0; s < S; s++) {
                         const size_t base = (tile * S + s) * Mp;
@@ -738,7 +755,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
                             for (int k = 0; k < K; k++)
                                 for (int k2 = 0; k2 < M; k2++)
                                     T.st_mat[((((tile * S + s) * K + k) * (Mp / 2) + k2 / 2) * TILE + lane) * 2 + (k2 & 1)] = Ai[(size_t)k * M + k2];
-                        if (T.fast) {   // rows 1..K-1, columns 1..M-1, transformed areas folded into the columns
+                        if (host_fm) {   // rows 1..K-1, columns 1..M-1, transformed areas folded into the columns
                             const size_t ft = i / FAST_CT, fl = i % FAST_CT;
                             for (int k2 = 0; k2 < M; k2++) if (Ai[k2] != 0.0) throw std::runtime_error("TENO: reconstruction matrix has a non-zero first row; compact tables unavailable (use fp_mode strict)");
                             for (int k = 0; k < K; k++) if (Ai[(size_t)k * M] != 0.0) throw std::runtime_error("TENO: reconstruction matrix has a non-zero first column; compact tables unavailable (use fp_mode strict)");
@@ -760,6 +777,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
             }
         }
         if (!err.empty()) throw std::runtime_error(err);
+        P.seconds_matrices = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_mat).count();
         oscillation_matrix(T);
         if (T.keep_ref) {   // re-emit in the reference's CSR layout and numbering (face_reconstruction.h:201-260)
             if (opt.part) throw std::runtime_error("reference-layout TENO tables are only kept for unpartitioned contexts");
@@ -819,6 +837,8 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
         }
     }
     P.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (getenv("MLB_PREP_TIMING"))
+        fprintf(stderr, "[mlb] preprocess: %u cells, total %.2f s (stencil search %.2f s, matrices %.2f s)\n", P.N, P.seconds, P.seconds_stencils, P.seconds_matrices);
 }
 
 }  // namespace mlb

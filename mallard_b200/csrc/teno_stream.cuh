@@ -107,8 +107,19 @@ __device__ __forceinline__ void cp_async16(void * dst, const void * src) {
 // OWNVAR = false: the four variable-threads of a cell share the fetch of a neighbour list (16-byte copies, thread `var` takes
 //                  neighbours var, var + 4, ...); OWNVAR = true: every thread fetches its own variable (8 bytes) of every
 //                  neighbour — the four lanes of a cell then hit the same 32-byte sector and the same shared-memory row.
+// 2 CTAs of 5 warps per SM leave 65536 / 320 = 204 registers per thread; __launch_bounds__(160, 2) rounds the block up
+// to 192 threads and caps at 168 (which spills), hence the explicit cap.
+#ifndef MLB_STREAM_MAXNREG
+#define MLB_STREAM_MAXNREG 200
+#endif
 template <int ORDER, bool OWNVAR>
-__global__ void __launch_bounds__(THREADS, 2) teno_stream_kernel(const __grid_constant__ ReconStreamArgs a) {
+__global__ void
+#if MLB_STREAM_MAXNREG > 0
+__maxnreg__(MLB_STREAM_MAXNREG)
+#else
+__launch_bounds__(THREADS, 2)
+#endif
+teno_stream_kernel(const __grid_constant__ ReconStreamArgs a) {
     using C = Cfg<ORDER>;
     using SM = Smem<ORDER>;
     constexpr int K = C::K, KR = C::KR, MC = C::MC, NP = C::NP, Q = C::Q, S = FAST_S, NF = FAST_S - 1, STAGES = SM::STAGES;

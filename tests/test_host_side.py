@@ -202,3 +202,25 @@ def test_streaming_tables_are_the_reference_tables_compacted(order):
     for i in range(plan.N_recon, n_ft * CT):   # padding cells of the last tile
         ft, fl = divmod(i, CT)
         assert (ids[ft, :, :, fl] == i).all()
+
+
+def test_synthetic_unstructured_mesh_matches_oracle_geometry_and_teno_tables(oracle_mod):
+    """The jittered, id-shuffled triangulation (BASELINE configs[3] family) as plain arrays: geometry computed by the library's
+    host code and the TENO tables of the host preprocessor are bit-identical to the oracle's on the same arrays."""
+    from mallard_b200 import synthetic as syn
+    mesh = syn.jittered_tri(14, 11, 10.0, 10.0, seed=12345)
+    a = mesh.arrays
+    keys = ["node_coords", "offsets_nodes_of_cell", "nodes_of_cell", "offsets_faces_of_cell", "faces_of_cell",
+            "offsets_nodes_of_face", "nodes_of_face", "cells_of_face"]
+    om = oracle_mod.Mesh.from_arrays({k: a[k] for k in keys}, mesh.zones)
+    for k in ("cell_coords", "cell_volume", "face_area", "face_normals"):
+        assert np.array_equal(om.get(k).reshape(-1), a[k].reshape(-1)), k
+    assert abs(a["cell_volume"].sum() - 100.0) < 1e-10 and a["cell_volume"].min() > 0
+    assert sorted(len(f) for n, f in mesh.zones if n != "interior") == [11, 11, 14, 14]
+    # a second call with the same seed gives the same mesh; another seed a different one
+    assert np.array_equal(syn.jittered_tri(14, 11, 10.0, 10.0, seed=12345).arrays["cells_of_face"], a["cells_of_face"])
+    assert not np.array_equal(syn.jittered_tri(14, 11, 10.0, 10.0, seed=1).arrays["cells_of_face"], a["cells_of_face"])
+    plan = mb.Plan(mesh, "TENO", order=3, bcs=syn.EXTRAP4, fp_mode="strict")
+    so = oracle_mod.Solver(om, "TENO", "HLLC", "SSPRK3", order=3, bcs=syn.EXTRAP4)
+    for k in ("teno:stencils", "teno:reconstruction_matrices", "teno:transformed_areas", "teno:offsets_stencils"):
+        assert np.array_equal(plan.get(k), so.get(k)), k
