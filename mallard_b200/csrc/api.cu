@@ -217,7 +217,7 @@ ReconStreamArgs stream_args(mlb_ctx & c, const double * Uin) {
     ReconStreamArgs r{};
     const TenoTables & T = c.prep.teno;
     r.g = c.g; r.Uin = Uin; r.Fc = c.Fc; r.mat = c.d_fm_mat; r.ids = c.d_fm_ids; r.area0 = c.d_fm_area0;
-    r.n_tiles = c.n_ftiles; r.order = T.order; r.fixed_weights = c.num.teno_fixed;
+    r.n_tiles = c.n_ftiles; r.order = T.order; r.fixed_weights = c.num.teno_fixed; r.basis = T.basis;
     static const int variant = [] { const char * e = getenv("MLB_STREAM_GATHER"); return e && !strcmp(e, "ownvar") ? 2 : 1; }();
     r.async_gather = variant;   // tuning knob: which lanes fetch which neighbour bytes (see teno_stream.cuh)
     for (size_t i = 0; i < c.prep.qf_x.size() && i < 4; i++) r.qf_x[i] = c.prep.qf_x[i];
@@ -399,7 +399,7 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
     for (size_t i = 0; i < P.qf_x.size(); i++) { c->phys.qf_x[i] = P.qf_x[i]; c->phys.qf_w[i] = P.qf_w[i]; }
     if (c->teno && !c->streaming && !c->kt->recon_supported(P.teno.order, P.teno.Mp, P.teno.basis))
         throw std::runtime_error("TENO: this (basis, order, stencil size) combination has no compiled device kernel "
-                                 "(available: legendre, order 1-4, max_stencil_size_factor 2.0)");
+                                 "(available: legendre / monomial, order 1-4, max_stencil_size_factor 2.0)");
 
     // ---- upload
     DevGeom & g = c->g;

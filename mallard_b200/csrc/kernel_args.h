@@ -86,7 +86,7 @@ struct ReconStreamArgs {       // teno_stream.cuh
     const uint32_t * ids;
     const double * area0;
     uint32_t n_tiles;
-    int32_t order, fixed_weights, async_gather;
+    int32_t order, fixed_weights, async_gather, basis;
     double qf_x[4];
     double psi_bar[15];
     double OIs[14 * 14];

@@ -364,6 +364,21 @@ __device__ __forceinline__ void legendre_values(double x, double * P) {   // bas
     if (ORDER >= 4) P[4] = 0.125 * (35.0 * x * x * x * x - 30.0 * x * x + 3.0);
 }
 
+// 1-D basis values psi_0..psi_ORDER at x: Legendre as above, or the reference's default monomials (basis.h:66-70,
+// Kokkos::pow(x, p): libm pow in STRICT mode, repeated multiplication in FAST mode)
+template <int ORDER>
+__device__ __forceinline__ void basis_values(int basis, double x, double * P) {
+    if (basis == MLB_BASIS_LEGENDRE) { legendre_values<ORDER>(x, P); return; }
+#ifdef MLB_STREAM_KERNELS
+    P[0] = 1.0;
+#pragma unroll
+    for (int d = 1; d <= ORDER; d++) P[d] = P[d - 1] * x;
+#else
+#pragma unroll
+    for (int d = 0; d <= ORDER; d++) P[d] = pow(x, (double)d);
+#endif
+}
+
 constexpr int RECON_THREADS = 128;
 
 // exponents of the k-th basis function in the reference's graded ordering (p,0),(p-1,1),...,(0,p)
@@ -469,8 +484,8 @@ __global__ void __launch_bounds__(RECON_THREADS) teno_recon_kernel(const __grid_
             const double tq = (a.qf_x[q] + 1.0) * 0.5;
             const double xq = tq * (x1 - x0) + x0, yq = tq * (y1 - y0) + y0;
             double Px[ORDER + 1], Py[ORDER + 1];
-            legendre_values<ORDER>(xq, Px);
-            legendre_values<ORDER>(yq, Py);
+            basis_values<ORDER>(a.basis, xq, Px);
+            basis_values<ORDER>(a.basis, yq, Py);
             double out = u_self;
 #pragma unroll 1
             for (int s = 0; s < S; s++) {
@@ -623,7 +638,7 @@ static void launch_recon_t(const ReconArgs & a, cudaStream_t st) {
     teno_recon_kernel<ORDER, MP><<<grid, RECON_THREADS, smem, st>>>(a);
 }
 static bool recon_supported(int order, int Mp, int basis) {
-    if (basis != MLB_BASIS_LEGENDRE) return false;
+    if (basis != MLB_BASIS_LEGENDRE && basis != MLB_BASIS_MONOMIAL) return false;
     return (order == 1 && Mp == 6) || (order == 2 && Mp == 12) || (order == 3 && Mp == 20) || (order == 4 && Mp == 30);
 }
 static void launch_recon(const ReconArgs & a, cudaStream_t st) {

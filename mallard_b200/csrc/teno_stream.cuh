@@ -351,8 +351,8 @@ teno_stream_kernel(const __grid_constant__ ReconStreamArgs a) {
                     const double tq = (a.qf_x[q] + 1.0) * 0.5;
                     const double xq = tq * (x1 - x0) + x0, yq = tq * (y1 - y0) + y0;
                     double Px[ORDER + 1], Py[ORDER + 1];
-                    legendre_values<ORDER>(xq, Px);
-                    legendre_values<ORDER>(yq, Py);
+                    basis_values<ORDER>(a.basis, xq, Px);
+                    basis_values<ORDER>(a.basis, yq, Py);
                     out[(j * Q + q) * 4] = poly_sum(c, Px, Py, u_self + cb, std::make_integer_sequence<int, KR>{});
                 }
             }
@@ -384,7 +384,7 @@ static void launch_stream_t(const ReconStreamArgs & a, cudaStream_t st) {
 }
 
 static bool stream_supported(int order, int M, int Q, int basis, int n_slots) {
-    if (basis != MLB_BASIS_LEGENDRE || n_slots != FAST_S - 1) return false;
+    if ((basis != MLB_BASIS_LEGENDRE && basis != MLB_BASIS_MONOMIAL) || n_slots != FAST_S - 1) return false;
     if (order < 1 || order > 4) return false;
     const int K = (order + 1) * (order + 2) / 2;
     return M == 2 * K && Q == (order + 1) / 2;

@@ -75,6 +75,16 @@ CASES = {
                                 riemann="Rusanov", integrator="SSPRK3",
                                 recon=dict(type="TENO", basis_type="legendre", basis_order=2, max_stencil_size_factor=2.0),
                                 n_steps=1, every=1, keep_mesh=False, keep_teno=True),
+    # the reference's DEFAULT basis (face_reconstruction.cpp:110): monomials, incl. the derivative quirk in the oscillation
+    # indicator (basis.h:72-78)
+    "teno_monomial_7x6_p3": dict(mesh=dict(type="cartesian_tri", Nx=7, Ny=6, Lx=1.0, Ly=1.0), ic=SMOOTH_IC, bcs=SYM4, cfl=0.1,
+                                 riemann="HLLC", integrator="SSPRK3",
+                                 recon=dict(type="TENO", basis_type="monomial", basis_order=3, max_stencil_size_factor=2.0),
+                                 n_steps=1, every=1, keep_mesh=False, keep_teno=True),
+    "teno_monomial_9x8_p2": dict(mesh=dict(type="cartesian_tri", Nx=9, Ny=8, Lx=1.2, Ly=1.0), ic=SMOOTH_IC, bcs=EXTRAP4, cfl=0.1,
+                                 riemann="HLL", integrator="RK4",
+                                 recon=dict(type="TENO", basis_type="monomial", basis_order=2, max_stencil_size_factor=2.0),
+                                 n_steps=1, every=1, keep_mesh=False, keep_teno=False),
 }
 
 

@@ -347,3 +347,23 @@ def test_vortex_on_unstructured_mesh_properties():
     sf.set_state(U0)
     sf.run(3, cfl=0.3)
     assert gu.field_err(sf.get_state(), res[0]) <= 3 * TOL
+
+
+@pytest.mark.parametrize("fp", ["strict", "fast"])
+@pytest.mark.parametrize("order,fixed", [(1, True), (2, True), (3, False), (3, True), (4, True)])
+def test_monomial_basis_vs_oracle(oracle_mod, order, fixed, fp):
+    """basis_type = "monomial" is the reference's default (face_reconstruction.cpp:110); basis values go through pow
+    (basis.h:66-70), so STRICT is within rounding of libm rather than bit-exact."""
+    om = oracle_mod.Mesh.generate("cartesian_tri", 20, 16, 2.0, 1.0)
+    mesh = mb.Mesh.generate("cartesian_tri", 20, 16, 2.0, 1.0)
+    kw = dict(recon="TENO", riemann="HLLC", integrator="SSPRK3", bcs=SYM4, basis="monomial", order=order, teno_fixed=fixed)
+    so = oracle_mod.Solver(om, **kw)
+    sg = mb.Solver(mesh, fp_mode=fp, **kw)
+    U0 = _random_smooth_state(mesh.arrays["cell_coords"], np.random.default_rng(23))
+    so.set_state(U0); sg.set_state(U0)
+    err = gu.rel_err if fp == "strict" else gu.field_err
+    real = gu.real_faces(mesh.arrays["cells_of_face"], mesh.arrays["nodes_of_face"])
+    assert err(sg.calc_face_values()[real][:, :, 0], so.calc_face_values()[real][:, :, 0]) <= TOL
+    dto, dtg = so.calc_dt(0.3), sg.calc_dt(0.3)
+    so.take_step(dto); sg.take_step()
+    assert err(sg.get_state(), so.get("U")) <= TOL
