@@ -204,6 +204,7 @@ class Plan:
         self._h = h
         s = self.get("sizes")
         (self.N, self.N_owned, self.N_recon, self.NF, self.n_slots, self.Q, self.K, self.M, self.Npad, self.S, self.Mp) = (int(x) for x in s[:11])
+        self.stream_tile = int(s[11])    # cells per tile of the streaming (FAST mode) TENO tables
 
     def get(self, name):
         nb = C.c_uint64()

@@ -1022,7 +1022,7 @@ int mlb_plan_get(mlb_plan * p, const char * name, void * out, uint64_t * nbytes)
     auto host = [&](const void * q, size_t nb) { if (out) std::memcpy(out, q, nb); *nbytes = nb; };
     if (n == "sizes") {
         uint32_t s[12] = {P.N, P.N_owned, P.N_recon, P.NF, (uint32_t)P.n_slots, (uint32_t)P.Q, (uint32_t)T.K, (uint32_t)T.M, P.Npad,
-                          (uint32_t)T.S, (uint32_t)T.Mp, 0};
+                          (uint32_t)T.S, (uint32_t)T.Mp, (uint32_t)FAST_CT};
         host(s, sizeof(s));
     }
     else if (n == "seconds") host(&P.seconds, 8);

@@ -78,6 +78,9 @@ __device__ __forceinline__ uint32_t mbar_test(uint64_t * bar, uint32_t parity) {
 __device__ __forceinline__ void cp_async8(void * dst, const void * src) {                    // LDGSTS: no register staging
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void * dst, const void * src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -91,6 +94,18 @@ __device__ __forceinline__ double poly_sum(const double * c, const double * Px, 
 
 constexpr int FX_ROWS = 17;   // per tile and cell: 12 face end-point coordinates, area_t[0], the cell's 4 conserved values
 
+static bool stream_supported(int order, int M, int Q, int basis, int n_slots) {
+    if ((basis != MLB_BASIS_LEGENDRE && basis != MLB_BASIS_MONOMIAL) || n_slots != FAST_S - 1) return false;
+    if (order < 1 || order > 4) return false;
+    const int K = (order + 1) * (order + 2) / 2;
+    return M == 2 * K && Q == (order + 1) / 2;
+}
+
+#if MLB_FAST_CT != 32
+}  // namespace stream
+#include "teno_stream_warp.cuh"
+namespace stream {
+#else
 template <int ORDER> struct Smem {
     using C = Cfg<ORDER>;
     static constexpr int STAGES = fast_stages(ORDER);
@@ -100,19 +115,15 @@ template <int ORDER> struct Smem {
     static constexpr size_t TOTAL = RING + UBUF + FXBUF;
 };
 
-__device__ __forceinline__ void cp_async16(void * dst, const void * src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-
 // OWNVAR = false: the four variable-threads of a cell share the fetch of a neighbour list (16-byte copies, thread `var` takes
 //                  neighbours var, var + 4, ...); OWNVAR = true: every thread fetches its own variable (8 bytes) of every
 //                  neighbour — the four lanes of a cell then hit the same 32-byte sector and the same shared-memory row.
-// 2 CTAs of 5 warps per SM leave 65536 / 320 = 204 registers per thread; __launch_bounds__(160, 2) rounds the block up
-// to 192 threads and caps at 168 (which spills), hence the explicit cap.
+// 2 CTAs of 5 warps per SM put 3 warps on two of the four schedulers: 16384 / 3 / 32 = 170 registers per thread
+// (a cap of 200 silently drops the kernel to ONE CTA per SM, profiles/r01h).
 #ifndef MLB_STREAM_MAXNREG
-#define MLB_STREAM_MAXNREG 200
+#define MLB_STREAM_MAXNREG 168
 #endif
-template <int ORDER, bool OWNVAR>
+template <int ORDER, bool OWNVAR, bool MONO>
 __global__ void
 #if MLB_STREAM_MAXNREG > 0
 __maxnreg__(MLB_STREAM_MAXNREG)
@@ -351,8 +362,8 @@ teno_stream_kernel(const __grid_constant__ ReconStreamArgs a) {
                     const double tq = (a.qf_x[q] + 1.0) * 0.5;
                     const double xq = tq * (x1 - x0) + x0, yq = tq * (y1 - y0) + y0;
                     double Px[ORDER + 1], Py[ORDER + 1];
-                    basis_values<ORDER>(a.basis, xq, Px);
-                    basis_values<ORDER>(a.basis, yq, Py);
+                    basis_values<ORDER>(MONO ? MLB_BASIS_MONOMIAL : MLB_BASIS_LEGENDRE, xq, Px);
+                    basis_values<ORDER>(MONO ? MLB_BASIS_MONOMIAL : MLB_BASIS_LEGENDRE, yq, Py);
                     out[(j * Q + q) * 4] = poly_sum(c, Px, Py, u_self + cb, std::make_integer_sequence<int, KR>{});
                 }
             }
@@ -362,33 +373,29 @@ teno_stream_kernel(const __grid_constant__ ReconStreamArgs a) {
     }
 }
 
-template <int ORDER, bool OWNVAR>
+template <int ORDER, bool OWNVAR, bool MONO>
 static void launch_stream_v(const ReconStreamArgs & a, cudaStream_t st) {
     const size_t smem = Smem<ORDER>::TOTAL;
     static int ctas = 0;
     if (!ctas) {
-        cudaFuncSetAttribute(teno_stream_kernel<ORDER, OWNVAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(teno_stream_kernel<ORDER, OWNVAR, MONO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, teno_stream_kernel<ORDER, OWNVAR>, THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, teno_stream_kernel<ORDER, OWNVAR, MONO>, THREADS, smem);
         ctas = sms * (per_sm > 0 ? per_sm : 1);
     }
     if (!a.n_tiles) return;
     const unsigned grid = a.n_tiles < (uint32_t)ctas ? a.n_tiles : (unsigned)ctas;   // persistent: one CTA slot per resident CTA
-    teno_stream_kernel<ORDER, OWNVAR><<<grid, THREADS, smem, st>>>(a);
+    teno_stream_kernel<ORDER, OWNVAR, MONO><<<grid, THREADS, smem, st>>>(a);
 }
 template <int ORDER>
 static void launch_stream_t(const ReconStreamArgs & a, cudaStream_t st) {
-    if (a.async_gather == 2) launch_stream_v<ORDER, true>(a, st); else launch_stream_v<ORDER, false>(a, st);
+    const bool mono = a.basis == MLB_BASIS_MONOMIAL;
+    if (a.async_gather == 2) { if (mono) launch_stream_v<ORDER, true, true>(a, st); else launch_stream_v<ORDER, true, false>(a, st); }
+    else { if (mono) launch_stream_v<ORDER, false, true>(a, st); else launch_stream_v<ORDER, false, false>(a, st); }
 }
 
-static bool stream_supported(int order, int M, int Q, int basis, int n_slots) {
-    if ((basis != MLB_BASIS_LEGENDRE && basis != MLB_BASIS_MONOMIAL) || n_slots != FAST_S - 1) return false;
-    if (order < 1 || order > 4) return false;
-    const int K = (order + 1) * (order + 2) / 2;
-    return M == 2 * K && Q == (order + 1) / 2;
-}
 static void launch_stream(const ReconStreamArgs & a, cudaStream_t st) {
     switch (a.order) {
         case 1: launch_stream_t<1>(a, st); break;
@@ -398,5 +405,6 @@ static void launch_stream(const ReconStreamArgs & a, cudaStream_t st) {
         default: break;
     }
 }
+#endif  // MLB_FAST_CT == 32
 
 }  // namespace stream

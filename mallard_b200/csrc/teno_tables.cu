@@ -10,7 +10,8 @@
 // -ffp-contract=off) operation by operation, so the tables are BIT-IDENTICAL to the host-built (= the reference's) ones:
 // + - * / and sqrt are correctly rounded on both sides.  tests/test_gpu_parity.py asserts the equality.
 //
-// Mapping: thread = (cell, stencil); warp = the 32 cells of one table tile (stores of a warp are 512 contiguous bytes).
+// Mapping: thread = (cell, stencil); FAST_CT consecutive threads = the cells of one table tile (their stores are FAST_CT x 16
+// contiguous bytes).
 // The R factor (the only array the O(rows^2 cols^2) Householder sweep touches) lives in shared memory, element-major
 // ([element][thread]: conflict-free); the original matrix and the solve workspace are per-thread local arrays.
 #include <cuda_runtime.h>
@@ -59,10 +60,11 @@ __global__ void __launch_bounds__(TbCfg<ORDER>::THREADS) teno_tables_kernel(cons
 #define V_(i) v[(i) * TB_THREADS]
 #define C_(i) cb[(i) * TB_THREADS]
 
-    // warp w of the grid handles (tile, stencil) = (w / S, w % S)
-    const uint32_t gw = (blockIdx.x * TB_THREADS + tid) >> 5;
+    // group g of FAST_CT consecutive threads handles (tile, stencil) = (g / S, g % S)
+    static_assert(TB_THREADS % CT == 0, "thread block = whole tiles");
+    const uint32_t gw = (blockIdx.x * TB_THREADS + tid) / CT;
     const uint32_t ft = gw / S;
-    const int s = gw % S, fl = tid & 31;
+    const int s = gw % S, fl = tid % CT;
     if (ft >= a.n_ftiles) return;
     const uint32_t cell = ft * CT + fl;
     constexpr size_t FROW = (size_t)(2 * NP + 1) * CT;
@@ -194,8 +196,8 @@ void launch_t(const TableBuildArgs & a, cudaStream_t st) {
     constexpr int K = (ORDER + 1) * (ORDER + 2) / 2, M = 2 * K, KR = K - 1, MC = M - 1, TB_THREADS = TbCfg<ORDER>::THREADS;
     const size_t smem = ((size_t)MC * KR + 2 * MC) * TB_THREADS * sizeof(double);
     cudaFuncSetAttribute(teno_tables_kernel<ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const uint64_t warps = (uint64_t)a.n_ftiles * FAST_S;
-    const unsigned grid = (unsigned)((warps * 32 + TB_THREADS - 1) / TB_THREADS);
+    const uint64_t groups = (uint64_t)a.n_ftiles * FAST_S;
+    const unsigned grid = (unsigned)((groups * FAST_CT + TB_THREADS - 1) / TB_THREADS);
     if (grid) teno_tables_kernel<ORDER><<<grid, TB_THREADS, smem, st>>>(a);
 }
 
