@@ -62,7 +62,10 @@ constexpr int TILE = 8;         // cells per interleaved TENO table tile (one wa
 constexpr int FAST_CT = MLB_FAST_CT;
 static_assert(FAST_CT == 8 || FAST_CT == 32, "streaming tile = 8 cells (warp-private rings) or 32 cells (CTA ring)");
 constexpr int FAST_S = 4;
-constexpr int fast_rows_per_chunk(int order) { return order == 1 ? 2 : order == 2 ? 5 : order == 3 ? 3 : 2; }
+#ifndef MLB_FAST_RC3
+#define MLB_FAST_RC3 3
+#endif
+constexpr int fast_rows_per_chunk(int order) { return order == 1 ? 2 : order == 2 ? 5 : order == 3 ? MLB_FAST_RC3 : 2; }
 constexpr int fast_stages(int /*order*/) { return 4; }
 
 struct TenoTables {

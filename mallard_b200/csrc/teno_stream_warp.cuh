@@ -43,11 +43,19 @@ template <int ORDER> struct WSmem {
     static constexpr size_t RING = (size_t)STAGES * C::CHUNK_BYTES;
     static constexpr size_t UBUF = (size_t)C::MC * UROW * 8;
     static constexpr size_t FXBUF = (size_t)2 * FX_ROWS * CT * 8;             // per tile parity
-    static constexpr size_t PER_WARP = (RING + UBUF + FXBUF + 127) / 128 * 128;
+    static constexpr size_t ZERO = 16;                                         // a 0.0 the "no column" lanes multiply with
+    static constexpr size_t PER_WARP = (RING + UBUF + FXBUF + ZERO + 127) / 128 * 128;
     static constexpr size_t TOTAL = PER_WARP * WARPS;
 };
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// stencil ids: a volatile load keeps its place in the instruction stream (one stencil ahead of its use); left to the
+// compiler it sinks next to the address computation that consumes it and exposes the full global-load latency
+__device__ __forceinline__ uint32_t ld_id(const uint32_t * p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 
 template <int ORDER, bool MONO>
 __global__ void __launch_bounds__(WTHREADS, MLB_WARP_MINB) teno_stream_warp_kernel(const __grid_constant__ ReconStreamArgs a) {
@@ -66,6 +74,7 @@ __global__ void __launch_bounds__(WTHREADS, MLB_WARP_MINB) teno_stream_warp_kern
     unsigned char * ring = smem + (size_t)warp * SM::PER_WARP;
     double * ubuf = reinterpret_cast<double *>(ring + SM::RING);
     double * fxbuf = reinterpret_cast<double *>(ring + SM::RING + SM::UBUF);
+    double * zero = reinterpret_cast<double *>(ring + SM::RING + SM::UBUF + SM::FXBUF);
     uint64_t * full_bar = full_bars[warp];
 
     const uint32_t n_tiles = a.n_tiles;
@@ -77,6 +86,7 @@ __global__ void __launch_bounds__(WTHREADS, MLB_WARP_MINB) teno_stream_warp_kern
     if (lane == 0) {
         for (int i = 0; i < STAGES; i++) mbar_init(&full_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        zero[0] = 0.0; zero[1] = 0.0;
     }
     __syncwarp();
 
@@ -100,16 +110,20 @@ __global__ void __launch_bounds__(WTHREADS, MLB_WARP_MINB) teno_stream_warp_kern
     const int h = (lane >> 3) & 1;                                    // column half (constant within a quarter-warp)
     const int cl = (lane >> 4) * 4 + ((lane & 7) >> 1);               // cell of the tile
     const int p = lane & 1;                                           // variable pair (2p, 2p + 1)
-    const int var = 2 * p + h;                                        // the variable this lane owns after the exchange
+    const int var = 2 * p + h;                                        // X: the variable this lane owns; Y = 2p + 1 - h goes to the partner lane
     const int sub = p + 2 * h;                                        // 0..3: share of the per-cell prefetches
     const uint32_t Np = a.g.Npad;
 
-    // the lane's last column slot: a column pair, the single column (MC - 1), or nothing
+    // the lane's last column slot: a column pair, the single column (MC - 1), or nothing.  Its two table entries are read
+    // with two 64-bit loads whose addresses point at the pair, at (single, zero word) or at (zero word, zero word), so
+    // the row loop has no lane-dependent selects and a neighbouring cell's entry is never multiplied (not even by zero).
     const int pi_last = 2 * (NSLOT - 1) + h;
     const int kind = pi_last < NP ? 0 : (pi_last == NP ? 1 : 2);
     const uint32_t off_reg = (uint32_t)(h * CT * 16 + cl * 16);       // + i * 2 CT 16
-    const uint32_t off_last = kind == 0 ? (uint32_t)(pi_last * CT * 16 + cl * 16) : (kind == 1 ? (uint32_t)(NP * CT * 16 + (cl >> 1) * 16) : (uint32_t)(cl * 16));
-    const bool sel_y = kind == 1 && (cl & 1);
+    const uint32_t zero_off = (uint32_t)(reinterpret_cast<unsigned char *>(zero) - ring);
+    const uint32_t off_lx = kind == 0 ? (uint32_t)(pi_last * CT * 16 + cl * 16) : (kind == 1 ? (uint32_t)(NP * CT * 16 + cl * 8) : 0u);
+    const uint32_t off_ly = off_lx + 8;
+    const bool lx_row = kind != 2, ly_row = kind == 0;                // does the entry live in the table row (else: the zero word)?
     const int lcol0 = kind == 0 ? 2 * pi_last : (kind == 1 ? MC - 1 : 0);
     const int lcol1 = kind == 0 ? lcol0 + 1 : lcol0;
 
@@ -128,15 +142,15 @@ __global__ void __launch_bounds__(WTHREADS, MLB_WARP_MINB) teno_stream_warp_kern
         cp_async8(dst + (13 + sub) * CT, a.Uin + 4 * (size_t)cell + sub);
     };
     uint32_t id[2 * NI], id0;                                         // ids this lane fetches for the NEXT stencil; the stencil's first id
-    auto load_ids = [&](uint32_t t, int s) {
+    auto load_ids = [&](uint32_t t, uint32_t s) {
         const uint32_t * __restrict__ q = a.ids + ((size_t)t * S + s) * (MC * CT) + cl;
-        id0 = q[0];
+        id0 = ld_id(q);
 #pragma unroll
         for (int i = 0; i < NI; i++)
 #pragma unroll
             for (int j = 0; j < 2; j++) {
                 const int m = 4 * i + 2 * h + j;
-                id[2 * i + j] = m < MC ? q[m * CT] : 0u;
+                id[2 * i + j] = ld_id(q + (m < MC ? m : MC - 1) * CT);   // the surplus slot repeats the last id and is never requested
             }
     };
     auto request_states = [&]() {
@@ -167,30 +181,34 @@ __global__ void __launch_bounds__(WTHREADS, MLB_WARP_MINB) teno_stream_warp_kern
         const uint32_t cell = tile * CT + cl;
         const bool live = cell < a.g.N_recon;
         const double * fx = fxbuf + (size_t)(it & 1) * FX_ROWS * CT + cl;
-        double uA = 0.0, uB = 0.0;
+        double uX = 0.0, uY = 0.0;
         double dof[S][KR];
         double w[S];
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-            // 1. right-hand sides b[m] = U[nbr m] - U[cell] of the lane's columns, both variables of its pair
+        // The stencil loop is NOT unrolled (the body is ~10 kB of SASS; four copies of it thrash the instruction cache,
+        // ncu r01h: 13 % of the stall samples were "no instruction"); its results are filed into dof[s][] / w[s] by
+        // warp-uniform branches at the end of the body.
+#pragma unroll 1
+        for (uint32_t s = 0; s < (uint32_t)S; s++) {
+            // 1. right-hand sides b[m] = U[nbr m] - U[cell] of the lane's columns, for X and Y
             cp_async_wait_all();
             __syncwarp();
-            if (s == 0) { uA = live ? fx[(13 + 2 * p) * CT] : 0.0; uB = live ? fx[(14 + 2 * p) * CT] : 0.0; }
+            if (s == 0) {
+                uX = live ? fx[(13 + var) * CT] : 0.0;
+                uY = live ? fx[(13 + (var ^ 1)) * CT] : 0.0;          // 2p + 1 - h = (2p + h) ^ 1
+            }
             const bool empty = empty_cur;                             // empty stencil (:896-899) or padding cell
-            double bA[NSLOT][2], bB[NSLOT][2];
+            double bX[NSLOT][2], bY[NSLOT][2];
             {
-                const double * ub = ubuf + cl * 4 + 2 * p;
+                const double * ubx = ubuf + cl * 4 + var, * uby = ubuf + cl * 4 + (var ^ 1);
 #pragma unroll
                 for (int i = 0; i < NSLOT - 1; i++) {
-                    const double2 t0 = *reinterpret_cast<const double2 *>(ub + (4 * i + 2 * h) * UROW);
-                    const double2 t1 = *reinterpret_cast<const double2 *>(ub + (4 * i + 2 * h + 1) * UROW);
-                    bA[i][0] = t0.x - uA; bB[i][0] = t0.y - uB;
-                    bA[i][1] = t1.x - uA; bB[i][1] = t1.y - uB;
+                    bX[i][0] = ubx[(4 * i + 2 * h) * UROW] - uX;     bY[i][0] = uby[(4 * i + 2 * h) * UROW] - uY;
+                    bX[i][1] = ubx[(4 * i + 2 * h + 1) * UROW] - uX; bY[i][1] = uby[(4 * i + 2 * h + 1) * UROW] - uY;
                 }
-                const double2 t0 = *reinterpret_cast<const double2 *>(ub + lcol0 * UROW);
-                const double2 t1 = *reinterpret_cast<const double2 *>(ub + lcol1 * UROW);
-                bA[NSLOT - 1][0] = kind == 2 ? 0.0 : t0.x - uA; bB[NSLOT - 1][0] = kind == 2 ? 0.0 : t0.y - uB;
-                bA[NSLOT - 1][1] = kind == 0 ? t1.x - uA : 0.0; bB[NSLOT - 1][1] = kind == 0 ? t1.y - uB : 0.0;
+                const double x0 = ubx[lcol0 * UROW] - uX, y0 = uby[lcol0 * UROW] - uY;
+                const double x1 = ubx[lcol1 * UROW] - uX, y1 = uby[lcol1 * UROW] - uY;
+                bX[NSLOT - 1][0] = kind == 2 ? 0.0 : x0; bY[NSLOT - 1][0] = kind == 2 ? 0.0 : y0;
+                bX[NSLOT - 1][1] = kind == 0 ? x1 : 0.0; bY[NSLOT - 1][1] = kind == 0 ? y1 : 0.0;
             }
             __syncwarp();                                             // the warp's reads of ubuf precede its next writes
             // 2. requests for what comes next (the next tile's first stencil after the last one of this tile)
@@ -198,44 +216,51 @@ __global__ void __launch_bounds__(WTHREADS, MLB_WARP_MINB) teno_stream_warp_kern
             if (s + 1 < S || has_next) request_states();
             if (s + 1 == S && has_next) prefetch_tile(next, (it + 1) & 1);
             cp_async_commit();
-            // 3. ids of the stencil after that (plain loads, consumed a stencil later)
+            // 3. ids of the stencil after that (consumed a stencil later)
             {
                 const bool in_tile = s + 2 < S;
                 if (in_tile || has_next) load_ids(in_tile ? tile : next, in_tile ? s + 2 : s + 2 - S);
             }
-            // 4. dofs a_k = sum_m A'[k][m] b[m]: each lane sums its half of the columns for two variables; the halves
-            //    are exchanged with one shuffle per row
+            // 4. dofs a_k = sum_m A'[k][m] b[m]: each lane sums its half of the columns for X and Y; the partner's half of
+            //    X arrives with one shuffle per row
+            double d[KR];
 #pragma unroll
             for (int ch = 0; ch < C::NCH; ch++) {
                 if (!ready) mbar_wait(&full_bar[c_st], c_par);
                 const uint32_t n_st = c_st + 1 == STAGES ? 0u : c_st + 1, n_par = c_st + 1 == STAGES ? c_par ^ 1u : c_par;
                 ready = mbar_test(&full_bar[n_st], n_par);            // probe the next chunk now, use the answer after this chunk's arithmetic
                 const unsigned char * base = ring + (size_t)c_st * C::CHUNK_BYTES;
+                // the RC rows of a chunk form one basic block (all dot products first, then the shuffles), so that the
+                // scheduler overlaps the shared-memory loads of one row with the FMA chains of another
+                double sx[C::RC], sy[C::RC];
 #pragma unroll
                 for (int r = 0; r < C::RC; r++) {
                     const unsigned char * row = base + (size_t)r * C::ROW_DOUBLES * 8;
-                    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+                    double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+#ifndef MLB_WARP_NOMATH   /* bench-only probe (A/B build): data movement without the dot products */
 #pragma unroll
                     for (int i = 0; i < NSLOT - 1; i++) {
                         const double2 c = *reinterpret_cast<const double2 *>(row + off_reg + i * 2 * CT * 16);
-                        a0 = fma(c.x, bA[i][0], a0); a1 = fma(c.y, bA[i][1], a1);
-                        b0 = fma(c.x, bB[i][0], b0); b1 = fma(c.y, bB[i][1], b1);
+                        x0 = fma(c.x, bX[i][0], x0); x1 = fma(c.y, bX[i][1], x1);
+                        y0 = fma(c.x, bY[i][0], y0); y1 = fma(c.y, bY[i][1], y1);
                     }
                     {
-                        const double2 t = *reinterpret_cast<const double2 *>(row + off_last);
-                        const double cx = kind == 2 ? 0.0 : (sel_y ? t.y : t.x);
-                        const double cy = kind == 0 ? t.y : 0.0;
-                        a0 = fma(cx, bA[NSLOT - 1][0], a0); a1 = fma(cy, bA[NSLOT - 1][1], a1);
-                        b0 = fma(cx, bB[NSLOT - 1][0], b0); b1 = fma(cy, bB[NSLOT - 1][1], b1);
+                        const double cx = *reinterpret_cast<const double *>((lx_row ? row : ring + zero_off) + (lx_row ? off_lx : 0u));
+                        const double cy = *reinterpret_cast<const double *>((ly_row ? row : ring + zero_off) + (ly_row ? off_ly : 0u));
+                        x0 = fma(cx, bX[NSLOT - 1][0], x0); x1 = fma(cy, bX[NSLOT - 1][1], x1);
+                        y0 = fma(cx, bY[NSLOT - 1][0], y0); y1 = fma(cy, bY[NSLOT - 1][1], y1);
                     }
-                    const double pa = a0 + a1, pb = b0 + b1;
-                    const double send = h ? pa : pb, keep = h ? pb : pa;
-                    dof[s][ch * C::RC + r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+#endif
+                    sx[r] = x0 + x1; sy[r] = y0 + y1;
                 }
+#pragma unroll
+                for (int r = 0; r < C::RC; r++) d[ch * C::RC + r] = sx[r] + __shfl_xor_sync(0xffffffffu, sy[r], 8);
                 __syncwarp();                                         // every lane is done with the stage
                 if (lane == 0 && p_g < n_chunks) {                    // refill it with the chunk STAGES ahead
-                    fence_proxy_async();
-                    issue();
+#ifdef MLB_WARP_PROXY_FENCE
+                    fence_proxy_async();                              // generic-proxy READS followed by an async-proxy write need no
+#endif                                                                // proxy fence (the same release/acquire pattern as a TMA pipeline's
+                    issue();                                          // consumer_release -> producer_acquire); kept as an A/B switch
                 }
                 c_st = n_st; c_par = n_par;
             }
@@ -246,28 +271,37 @@ __global__ void __launch_bounds__(WTHREADS, MLB_WARP_MINB) teno_stream_warp_kern
             for (int k = 0; k < KR; k++) {
                 double t = 0.0;
 #pragma unroll
-                for (int j = k; j < KR; j++) t = fma(a.OIs[k * KR + j], dof[s][j], t);
-                si = fma(dof[s][k], t, si);
+                for (int j = k; j < KR; j++) t = fma(a.OIs[k * KR + j], d[j], t);
+                si = fma(d[k], t, si);
             }
             const double x = si + 1.0e-12;                            // 1/(SI+eps)^6 :940-944
             const double x2 = x * x, x3 = x2 * x;
-            w[s] = empty ? 0.0 : 1.0 / (x3 * x3);
+            const double ws = empty ? 0.0 : 1.0 / (x3 * x3);
+#pragma unroll
+            for (int t = 0; t < S; t++) {
+                if (s == (uint32_t)t) {                               // warp-uniform
+                    w[t] = ws;
+#pragma unroll
+                    for (int k = 0; k < KR; k++) dof[t][k] = d[k];
+                }
+            }
         }
 
         if (live) {
-            const double u_self = h ? uB : uA;
+            const double u_self = uX;
             // non-linear weights :948-981 (reference-faithful unless fixed_weights)
             double sd = 0.0;
 #pragma unroll
             for (int s = 1; s < S; s++) sd += w[s];
-            if (w[0] / (sd + w[0]) > 1.0e-7) {
+            // thresholds as products: w/x > c  <=>  w > c x for x > 0, and both are false when x is 0, Inf or NaN
+            if (w[0] > 1.0e-7 * (sd + w[0])) {
                 w[0] = 1.0;
 #pragma unroll
                 for (int s = 1; s < S; s++) w[s] = 0.0;
             } else {
 #pragma unroll
                 for (int s = 1; s < S; s++) {
-                    if (w[s] / sd > 1.0e-5) w[s] = (1.0 / K);
+                    if (w[s] > 1.0e-5 * sd) w[s] = (1.0 / K);
                     else if (a.fixed_weights) w[s] = 0.0;
                 }
                 sd = 0.0;
