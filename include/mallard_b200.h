@@ -191,10 +191,22 @@ int mlb_halo_recv_ids(mlb_ctx *ctx, int32_t peer_index, uint32_t *ref_ids_out /*
 int mlb_halo_set_send_ids(mlb_ctx *ctx, int32_t n_lists, const int32_t *peer_ranks, const uint64_t *counts,
                           const uint32_t *ref_ids /* concatenated */);
 int mlb_halo_buffers(mlb_ctx *ctx, void **send_dev, void **recv_dev);   /* contiguous, peers in ascending order */
-int mlb_halo_pack(mlb_ctx *ctx, int32_t stage);     /* async on the compute stream */
-int mlb_halo_unpack(mlb_ctx *ctx, int32_t stage);   /* async on the compute stream */
-/* split-phase stepping for callers that own the communicator: stage s of the current step, run after unpack */
+/* The exchange runs on the context's COMMUNICATION stream (mlb_comm_stream; cudaStream_t), concurrently with the interior
+ * work of the stage on the compute stream:
+ *   mlb_halo_pack   waits (on the device) for everything enqueued on the compute stream so far, then fills `send`;
+ *   the caller enqueues its transfers send -> peers, peers -> recv ON mlb_comm_stream (ncclSend/ncclRecv, peer copies);
+ *   mlb_halo_unpack scatters `recv` into the ghost cells; the compute stream's first reader of ghost data (the rim part
+ *   of mlb_stage, the CFL kernel) waits for it on the device.  Nothing here blocks the host. */
+int mlb_halo_pack(mlb_ctx *ctx, int32_t stage);
+int mlb_halo_unpack(mlb_ctx *ctx, int32_t stage);
+void *mlb_comm_stream(mlb_ctx *ctx);
+/* split-phase stepping for callers that own the communicator: stage s of the current step.
+ * mlb_stage_begin (optional) enqueues the reconstruction of the interior cells (TENO stencils made of owned cells only;
+ * the preprocessor numbers them first) — call it right after the exchange has been enqueued; mlb_stage waits for the
+ * unpack, reconstructs the remaining cells and runs the flux / residual / RK kernels.  Without mlb_stage_begin,
+ * mlb_stage does both parts itself, in the same order. */
 int mlb_n_stages(const mlb_ctx *ctx);
+int mlb_stage_begin(mlb_ctx *ctx, int32_t stage);
 int mlb_stage(mlb_ctx *ctx, int32_t stage);
 int mlb_local_max_spectral_radius(mlb_ctx *ctx, double *max_out);   /* rank-local part of calc_dt; max_out == NULL: async */
 int mlb_apply_dt(mlb_ctx *ctx, double cfl, double global_max);      /* dt = cfl/max ; cfl_local *= dt */
@@ -217,7 +229,8 @@ int mlb_compute_primitives(int32_t device, int32_t fp_mode, const mlb_physics *p
                            double *prim /* [n][5] */, double *R_cp_cv /* [3] or NULL */);
 
 /* ---- the mesh preprocessor alone (host only, no device): what mlb_create uploads.  `part` may be NULL.  Arrays by name:
- *   "sizes" (u32[12]: N, N_owned, N_recon, NF, n_slots, Q, K, M, Npad, S, Mp, 0), "perm_cells", "perm_faces",
+ *   "sizes" (u32[12]: N, N_owned, N_recon, NF, n_slots, Q, K, M, Npad, S, Mp, streaming tile size), "n_interior" (u32:
+ *   owned cells [0, n_interior) have TENO stencils without ghosts), "perm_cells", "perm_faces",
  *   "slot_face", "slot_nbr" (i32), "rhs_order" (u8), "st_ids", "ghost_owner" (i32 per ghost cell),
  *   "fm_ids" (u32), "fm_mat", "fm_area0", "OIs" (f64; compact streaming tables, fp_mode FAST only),
  *   "halo_peers" (i32), "halo_recv_counts" (u64), "halo_recv_ids" (u32, concatenated; partitioned plans only),

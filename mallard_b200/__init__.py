@@ -178,7 +178,7 @@ def _physics(gas):
 class Plan:
     """The mesh preprocessor's output alone (host only; no device needed): renumbering, slot tables, TENO tables."""
 
-    _DT = {"sizes": np.uint32, "perm_cells": np.uint32, "perm_faces": np.uint32, "slot_face": np.uint32, "slot_nbr": np.int32,
+    _DT = {"sizes": np.uint32, "n_interior": np.uint32, "perm_cells": np.uint32, "perm_faces": np.uint32, "slot_face": np.uint32, "slot_nbr": np.int32,
            "rhs_order": np.uint8, "st_ids": np.uint32, "ghost_owner": np.int32, "teno:poly_indices": np.uint8,
            "fm_ids": np.uint32, "halo_peers": np.int32, "halo_recv_counts": np.uint64, "halo_recv_ids": np.uint32,
            "teno:offsets_stencil_groups": np.uint32, "teno:offsets_stencils": np.uint32, "teno:stencils": np.uint32,
@@ -431,6 +431,10 @@ class Solver:
     def halo_unpack(self, stage):
         self._ok(lib().mlb_halo_unpack(self._h, stage))
 
+    def stage_begin(self, s):
+        """Enqueues the reconstruction of the interior cells of stage s (overlaps the halo exchange in flight)."""
+        self._ok(lib().mlb_stage_begin(self._h, s))
+
     def stage(self, s):
         self._ok(lib().mlb_stage(self._h, s))
 
@@ -478,6 +482,11 @@ class Solver:
     @property
     def stream(self):
         return lib().mlb_stream(self._h)
+
+    @property
+    def comm_stream(self):
+        """cudaStream_t the halo pack / transfers / unpack are ordered on (the compute stream when unpartitioned)."""
+        return lib().mlb_comm_stream(self._h)
 
 
 def riemann_flux(kind, n_unit, L, R, gamma=1.4, fp_mode="strict", device=0):

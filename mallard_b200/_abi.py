@@ -78,6 +78,7 @@ SYMBOLS = {
     "mlb_launch_count": (U64, [VP]),
     "mlb_synchronize": (C.c_int, [VP]),
     "mlb_stream": (VP, [VP]),
+    "mlb_comm_stream": (VP, [VP]),
     "mlb_partition": (C.c_int, [C.POINTER(MeshView), I32, VP]),
     "mlb_create_partitioned": (C.c_int, [C.POINTER(VP), C.POINTER(MeshView), VP, C.POINTER(Numerics), C.POINTER(Physics), C.POINTER(Bc), I32, C.POINTER(Parallel)]),
     "mlb_halo_info": (C.c_int, [VP, C.POINTER(I32), VP, VP, VP]),
@@ -88,6 +89,7 @@ SYMBOLS = {
     "mlb_halo_unpack": (C.c_int, [VP, I32]),
     "mlb_n_stages": (C.c_int, [VP]),
     "mlb_stage": (C.c_int, [VP, I32]),
+    "mlb_stage_begin": (C.c_int, [VP, I32]),
     "mlb_local_max_spectral_radius": (C.c_int, [VP, C.POINTER(DBL)]),
     "mlb_apply_dt": (C.c_int, [VP, DBL, DBL]),
     "mlb_scalars_device": (VP, [VP]),

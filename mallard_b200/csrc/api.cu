@@ -94,6 +94,13 @@ struct mlb_ctx {
     uint32_t * d_send_idx = nullptr, * d_recv_idx = nullptr;
     double * d_send_buf = nullptr, * d_recv_buf = nullptr;
     uint64_t n_send = 0, n_recv = 0;
+    // The exchange lives on its own stream: pack -> (caller's communicator) -> unpack run on comm_stream while the compute
+    // stream reconstructs the interior cells; ev_state orders pack after the producer of the state, ev_halo orders the
+    // first reader of ghost data after unpack.
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_state = nullptr, ev_halo = nullptr;
+    bool halo_pending = false;         // an unpack has been enqueued that the compute stream has not waited for yet
+    int stage_begun = -1;              // stage whose interior reconstruction is already enqueued (mlb_stage_begin)
 
     // measurement
     cudaEvent_t ev[16] = {};
@@ -148,6 +155,9 @@ struct mlb_ctx {
         if (d_stage) cudaFree(d_stage);
         if (h_stage) cudaFreeHost(h_stage);
         for (auto & e : ev) if (e) cudaEventDestroy(e);
+        if (comm_stream) { cudaStreamSynchronize(comm_stream); cudaStreamDestroy(comm_stream); }
+        if (ev_state) cudaEventDestroy(ev_state);
+        if (ev_halo) cudaEventDestroy(ev_halo);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -226,11 +236,25 @@ ReconStreamArgs stream_args(mlb_ctx & c, const double * Uin) {
     return r;
 }
 
-void run_recon(mlb_ctx & c, const double * Uin) {
+// The compute stream's first reader of ghost data waits for the unpack enqueued on the communication stream.
+void wait_halo(mlb_ctx & c) {
+    if (c.halo_pending) { CUDA_OK(cudaStreamWaitEvent(c.stream, c.ev_halo, 0)); c.halo_pending = false; }
+}
+
+// Tiles made of interior cells only (stencils without ghosts): their reconstruction overlaps the halo exchange.
+uint32_t interior_tiles(const mlb_ctx & c) {
+    return (c.streaming && FAST_CT == 8 && c.n_ranks > 1) ? c.prep.N_interior / FAST_CT : 0u;
+}
+
+// phase 0: everything; 1: interior tiles only (before the halo wait); 2: the remaining tiles
+void run_recon(mlb_ctx & c, const double * Uin, int phase = 0) {
     if (c.streaming) {
         ReconStreamArgs r = stream_args(c, Uin);
-        c.launch("teno_stream", [&] { c.kt->recon_stream(r, c.stream); });
-    } else {
+        const uint32_t ti = interior_tiles(c);
+        if (phase == 1) r.n_tiles = ti;
+        if (phase == 2) r.tile_begin = ti;
+        if (r.n_tiles > r.tile_begin) c.launch("teno_stream", [&] { c.kt->recon_stream(r, c.stream); });
+    } else if (phase != 1) {
         ReconArgs r = recon_args(c, Uin);
         c.launch("teno_recon", [&] { c.kt->recon(r, c.stream); });
     }
@@ -238,7 +262,19 @@ void run_recon(mlb_ctx & c, const double * Uin) {
 
 void run_stage(mlb_ctx & c, const StagePlan & s, bool bare, double * k_out) {
     const double * Uin = c.U[s.in];
-    if (c.teno && !c.has_override) run_recon(c, Uin);
+    const bool recon = c.teno && !c.has_override;
+    if (c.stage_begun >= 0) {              // mlb_stage_begin already enqueued the interior tiles
+        c.stage_begun = -1;
+        wait_halo(c);
+        if (recon) run_recon(c, Uin, 2);
+    } else if (recon && c.halo_pending && interior_tiles(c)) {
+        run_recon(c, Uin, 1);
+        wait_halo(c);
+        run_recon(c, Uin, 2);
+    } else {
+        wait_halo(c);
+        if (recon) run_recon(c, Uin);
+    }
     StageArgs a{};
     a.g = c.g; a.ph = c.phys; a.Uin = Uin; a.Fc = c.Fc; a.AF = c.AF; a.teno = c.teno ? 1 : 0;
     a.k_override = c.has_override ? c.k_override : nullptr;
@@ -273,6 +309,7 @@ void do_calc_dt(mlb_ctx & c, double cfl) {
     CflArgs a{};
     a.g = c.g; a.gas = c.gas; a.U = c.U[c.cur]; a.prim = c.prim; a.sr_out = c.sr; a.scal = c.scal;
     a.max_bits = c.max_bits; a.blocks_done = c.blocks_done; a.cfl = cfl;
+    wait_halo(c);   // the CFL kernel reads the ghosts' primitives
     c.launch("cfl", [&] { c.kt->cfl(a, c.stream); });
 }
 
@@ -345,6 +382,11 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
     c->n_ranks = par ? std::max(1, par->n_ranks) : 1;
     require_device(c->device);
     CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (c->n_ranks > 1) {
+        CUDA_OK(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&c->ev_state, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+    }
     c->num = *numerics;
     if (c->num.recon != MLB_RECON_FO && c->num.recon != MLB_RECON_TENO) throw std::runtime_error("Unknown face reconstruction type.");
     if (c->num.riemann < 0 || c->num.riemann > 2) throw std::runtime_error("Unknown Riemann solver type.");
@@ -757,10 +799,12 @@ uint64_t mlb_launch_count(const mlb_ctx * c) { return c ? c->launches : 0; }
 int mlb_synchronize(mlb_ctx * c) {
     API_BEGIN(c)
     CUDA_OK(cudaSetDevice(c->device));
+    if (c->comm_stream) CUDA_OK(cudaStreamSynchronize(c->comm_stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     API_END(c)
 }
 void * mlb_stream(mlb_ctx * c) { return c ? (void *)c->stream : nullptr; }
+void * mlb_comm_stream(mlb_ctx * c) { return c ? (void *)(c->comm_stream ? c->comm_stream : c->stream) : nullptr; }
 
 // ---- multi-GPU -------------------------------------------------------------------------------------------------
 int mlb_halo_info(mlb_ctx * c, int32_t * n_peers, int32_t * peers, uint64_t * send_counts, uint64_t * recv_counts) {
@@ -830,19 +874,30 @@ int mlb_halo_pack(mlb_ctx * c, int32_t stage) {
     API_BEGIN(c)
     CUDA_OK(cudaSetDevice(c->device));
     const int b = stage_input_buffer(c, stage);
-    c->launch("halo_pack", [&] { launch_gather(c->U[b], c->d_send_idx, (uint32_t)c->n_send, c->prep.Npad, c->d_send_buf, c->stream); });
+    cudaStream_t cs = c->comm_stream ? c->comm_stream : c->stream;
+    if (c->comm_stream) {                  // everything enqueued on the compute stream so far produces the state to be sent
+        CUDA_OK(cudaEventRecord(c->ev_state, c->stream));
+        CUDA_OK(cudaStreamWaitEvent(cs, c->ev_state, 0));
+    }
+    launch_gather(c->U[b], c->d_send_idx, (uint32_t)c->n_send, c->prep.Npad, c->d_send_buf, cs);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
     API_END(c)
 }
 int mlb_halo_unpack(mlb_ctx * c, int32_t stage) {
     API_BEGIN(c)
     CUDA_OK(cudaSetDevice(c->device));
     const int b = stage_input_buffer(c, stage);
-    c->launch("halo_unpack", [&] { launch_scatter(c->d_recv_buf, c->d_recv_idx, (uint32_t)c->n_recv, c->prep.Npad, c->U[b], c->stream); });
+    cudaStream_t cs = c->comm_stream ? c->comm_stream : c->stream;
+    launch_scatter(c->d_recv_buf, c->d_recv_idx, (uint32_t)c->n_recv, c->prep.Npad, c->U[b], cs);
+    c->launches++;
     if (stage == 0 && c->prep.N > c->prep.N_owned) {   // ghosts' primitives for the CFL kernel (update_primitives of their owners)
         const uint32_t off = c->prep.N_owned & ~31u;    // keep the SoA column alignment
-        c->kt->primitives_soa(c->gas, c->prep.N - off, c->prep.Npad, c->U[b] + 4 * (size_t)off, c->prim + off, c->stream);
+        c->kt->primitives_soa(c->gas, c->prep.N - off, c->prep.Npad, c->U[b] + 4 * (size_t)off, c->prim + off, cs);
         c->launches++;
     }
+    CUDA_OK(cudaGetLastError());
+    if (c->comm_stream) { CUDA_OK(cudaEventRecord(c->ev_halo, cs)); c->halo_pending = true; }
     API_END(c)
 }
 int mlb_n_stages(const mlb_ctx * c) { return c ? c->n_stages : 0; }
@@ -851,8 +906,21 @@ int mlb_stage(mlb_ctx * c, int32_t stage) {
     CUDA_OK(cudaSetDevice(c->device));
     const auto plan = make_plan(*c);
     if (stage < 0 || stage >= (int)plan.size()) throw std::runtime_error("stage out of range");
+    if (c->stage_begun >= 0 && c->stage_begun != stage) throw std::runtime_error("mlb_stage: a different stage was begun with mlb_stage_begin");
     run_stage(*c, plan[stage], false, nullptr);
     if (stage == (int)plan.size() - 1) finish_plan(*c, plan);
+    API_END(c)
+}
+int mlb_stage_begin(mlb_ctx * c, int32_t stage) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    const auto plan = make_plan(*c);
+    if (stage < 0 || stage >= (int)plan.size()) throw std::runtime_error("stage out of range");
+    if (c->stage_begun >= 0) throw std::runtime_error("mlb_stage_begin: the previous stage has not been finished with mlb_stage");
+    if (c->teno && !c->has_override && interior_tiles(*c)) {
+        run_recon(*c, c->U[plan[stage].in], 1);
+        c->stage_begun = stage;
+    }
     API_END(c)
 }
 int mlb_local_max_spectral_radius(mlb_ctx * c, double * max_out) {
@@ -910,6 +978,7 @@ int mlb_apply_dt(mlb_ctx * c, double cfl, double global_max) {
 int mlb_finish_step(mlb_ctx * c) {
     API_BEGIN(c)
     CUDA_OK(cudaSetDevice(c->device));
+    if (c->comm_stream) CUDA_OK(cudaStreamSynchronize(c->comm_stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     API_END(c)
 }
@@ -1026,6 +1095,7 @@ int mlb_plan_get(mlb_plan * p, const char * name, void * out, uint64_t * nbytes)
         host(s, sizeof(s));
     }
     else if (n == "seconds") host(&P.seconds, 8);
+    else if (n == "n_interior") host(&P.N_interior, 4);
     else if (n == "perm_cells") host(P.perm_cells.data(), P.perm_cells.size() * 4);
     else if (n == "perm_faces") host(P.perm_faces.data(), P.perm_faces.size() * 4);
     else if (n == "slot_face") host(P.slot_face.data(), P.slot_face.size() * 4);

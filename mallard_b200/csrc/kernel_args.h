@@ -85,7 +85,8 @@ struct ReconStreamArgs {       // teno_stream.cuh
     const double * mat;
     const uint32_t * ids;
     const double * area0;
-    uint32_t n_tiles;
+    uint32_t n_tiles;             // tiles [tile_begin, n_tiles) are processed by this launch
+    uint32_t tile_begin;
     int32_t order, fixed_weights, async_gather, basis;
     double qf_x[4];
     double psi_bar[15];

@@ -219,7 +219,7 @@ __device__ __forceinline__ void rk_update(const RkArgs & rk, const double * Uin,
 // face.  The reference scatters -+ that product into both cells with atomic_add; here the cells gather it (next kernel).
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef MLB_FLUX_MINB
-#define MLB_FLUX_MINB 4
+#define MLB_FLUX_MINB 8   // 64 registers: occupancy beats the 216 bytes of spills (A/B on B200: 0.48 -> 0.37 ms per launch, profiles/r01h)
 #endif
 // QT > 0: the number of face quadrature points is known at compile time and ONE THREAD PER (face, quadrature point) solves
 // one Riemann problem; the QT lanes of a face then combine w_q F_q in the reference's q order with warp shuffles (same

@@ -100,6 +100,8 @@ struct Prep {
     uint32_t N = 0;        // cells owned+ghost held by this context
     uint32_t N_owned = 0;  // cells [0, N_owned) are updated here; [N_owned, N) are ghosts (multi-GPU)
     uint32_t N_recon = 0;  // cells [0, N_recon) are reconstructed (owned + first ghost ring)
+    uint32_t N_interior = 0;  // owned cells [0, N_interior) have TENO stencils made of owned cells only: their reconstruction
+                              // does not wait for the halo exchange (multi-GPU overlap); = N_owned when unpartitioned
     uint32_t Npad = 0;     // N rounded up to a multiple of 32
     uint32_t NF = 0;       // real faces held (phantom faces dropped)
     uint32_t NFpad = 0;

@@ -525,6 +525,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
     const uint32_t n_owned = (uint32_t)order.size();
     order.insert(order.end(), g1.begin(), g1.end());
     const uint32_t n_recon = (uint32_t)order.size();
+    uint32_t n_interior = opt.part ? 0u : n_owned;   // first order: no reconstruction kernel to overlap
 
     // ---- TENO stencils for owned + ring-1 cells (parallel), written into the tile layout with REFERENCE ids first;
     //      state-only ghosts are whatever else those stencils touch
@@ -554,13 +555,42 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
         if (!err.empty()) throw std::runtime_error(err);
         P.seconds_stencils = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (opt.part) {
+            // Interior-first order of the owned cells: a cell whose stencils hold owned cells only can be reconstructed
+            // while the ghost states are still in flight.  The partition is stable, so each class keeps its RCM order.
+            std::vector<uint8_t> rim(n_owned, 0);
+#pragma omp parallel for schedule(static)
+            for (int64_t ii = 0; ii < (int64_t)n_owned; ii++) {
+                const size_t tile = (size_t)ii / TILE, lane = (size_t)ii % TILE;
+                for (int s = 0; s < T.S && !rim[ii]; s++)
+                    for (int k = 0; k < T.M; k++) {
+                        const uint32_t x = T.st_ids[((tile * T.S + s) * T.Mp + k) * TILE + lane];
+                        if (x != NO_FACE && cls[x] != 1) { rim[ii] = 1; break; }
+                    }
+            }
+            uvec newpos(n_recon);
+            uint32_t a = 0;
+            for (uint32_t ii = 0; ii < n_owned; ii++) if (!rim[ii]) newpos[ii] = a++;
+            n_interior = a;
+            for (uint32_t ii = 0; ii < n_owned; ii++) if (rim[ii]) newpos[ii] = a++;
+            for (uint32_t ii = n_owned; ii < n_recon; ii++) newpos[ii] = ii;
+            uvec ids2(T.st_ids.size(), NO_FACE), order2(order.size());
+#pragma omp parallel for schedule(static)
+            for (int64_t ii = 0; ii < (int64_t)n_recon; ii++) {
+                const size_t tile = (size_t)ii / TILE, lane = (size_t)ii % TILE, jj = newpos[ii], tile2 = jj / TILE, lane2 = jj % TILE;
+                order2[jj] = order[ii];
+                for (int s = 0; s < T.S; s++)
+                    for (int k = 0; k < T.Mp; k++)
+                        ids2[((tile2 * T.S + s) * T.Mp + k) * TILE + lane2] = T.st_ids[((tile * T.S + s) * T.Mp + k) * TILE + lane];
+            }
+            T.st_ids.swap(ids2);
+            order.swap(order2);
             for (uint32_t x : T.st_ids) if (x != NO_FACE && !cls[x]) { cls[x] = 3; g2.push_back(x); }
             std::sort(g2.begin(), g2.end());
             order.insert(order.end(), g2.begin(), g2.end());
         }
     }
     const uint32_t N = (uint32_t)order.size();
-    P.N = N; P.N_owned = n_owned; P.N_recon = n_recon;
+    P.N = N; P.N_owned = n_owned; P.N_recon = n_recon; P.N_interior = n_interior;
     P.Npad = (N + 31u) & ~31u;
     P.perm_cells = order;
     P.iperm_cells.assign(m.nc, NO_FACE);

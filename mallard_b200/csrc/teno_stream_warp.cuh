@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(WTHREADS, MLB_WARP_MINB) teno_stream_warp_kern
 
     const uint32_t n_tiles = a.n_tiles;
     const uint32_t n_warps = gridDim.x * WARPS;
-    const uint32_t gw = blockIdx.x * WARPS + warp;             // neighbouring warps stream neighbouring tiles
+    const uint32_t gw = a.tile_begin + blockIdx.x * WARPS + warp;   // the warp's first tile: neighbouring warps stream neighbouring tiles
     if (gw >= n_tiles) return;
     const uint32_t n_chunks = ((n_tiles - gw + n_warps - 1) / n_warps) * CPT;   // this warp's chunks
 
@@ -361,8 +361,8 @@ static void launch_stream_w(const ReconStreamArgs & a, cudaStream_t st) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, teno_stream_warp_kernel<ORDER, MONO>, WTHREADS, smem);
         ctas = sms * (per_sm > 0 ? per_sm : 1);
     }
-    if (!a.n_tiles) return;
-    const uint32_t need = (a.n_tiles + WARPS - 1) / WARPS;
+    if (a.n_tiles <= a.tile_begin) return;
+    const uint32_t need = (a.n_tiles - a.tile_begin + WARPS - 1) / WARPS;
     const unsigned grid = need < (uint32_t)ctas ? need : (unsigned)ctas;   // persistent: one CTA per resident CTA slot
     teno_stream_warp_kernel<ORDER, MONO><<<grid, WTHREADS, smem, st>>>(a);
 }

@@ -4,8 +4,12 @@ One process per GPU.  The mesh is partitioned over the ranks (mallard_b200.parti
 rank's context owns its cells plus ghost copies of every remote cell its residual stencils read.  Per RK stage the ghost
 conserved states (4 doubles per cell) are exchanged peer to peer, per step one double is all-reduced (max) for dt:
 
-    stage 0:  pack -> send/recv -> unpack -> [local max spectral radius -> all_reduce(max) -> dt] -> stage kernels
-    stage s:  pack -> send/recv -> unpack -> stage kernels
+    communication stream:  pack -> send/recv -> unpack                       (per stage)
+    compute stream:        reconstruction of the INTERIOR cells | wait for unpack | rim cells, fluxes, residual + RK update
+                           (stage 0 also: local max spectral radius -> all_reduce(max) -> dt, between the two halves)
+
+The preprocessor numbers the owned cells whose TENO stencils contain no ghost first, so the bulk of a stage (the
+table-streaming reconstruction kernel) runs while the ghost states are in flight.
 
 The communicator is torch.distributed: NCCL over NVLink/NVSwitch on the GPU box (send/recv straight from / into the
 library's device buffers, enqueued on the library's compute stream — no host staging, no host synchronisation inside a
@@ -85,6 +89,7 @@ class DistributedSolver:
         self.recv_t = device_tensor(rp, 4 * int(self.recv_counts.sum()), self.device)
         self.scal_t = device_tensor(s.scalars_device(), 8, self.device)
         self.stream = torch.cuda.ExternalStream(s.stream, device=self.device)
+        self.comm = torch.cuda.ExternalStream(s.comm_stream, device=self.device)
         self.n_stages = s.n_stages
         self.owned = s.owned_cells()
 
@@ -96,9 +101,10 @@ class DistributedSolver:
     def exchange(self, stage):
         s = self.s
         s.halo_pack(stage)
-        with torch.cuda.stream(self.stream):
+        with torch.cuda.stream(self.comm):
             halo_exchange(self.send_t, self.recv_t, self.peers, self.send_counts, self.recv_counts, self.group)
         s.halo_unpack(stage)
+        s.stage_begin(stage)       # interior cells: overlaps the exchange just enqueued
 
     def step(self, cfl=None):
         """One time step; cfl=None keeps the dt set by set_dt.  Fully asynchronous on the device."""

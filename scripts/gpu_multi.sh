@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 N=${NGPU:-2}
 T="timeout -s KILL"
 nvidia-smi -L > gpurun_out/multi_host.txt; nproc >> gpurun_out/multi_host.txt
-$T 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/pytest_multi.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_multi.log
+$T 600 python -m pytest ${PYTEST_TARGET:-tests/test_gpu_multi.py} -m gpu -x -q > gpurun_out/pytest_multi.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_multi.log
 tail -5 gpurun_out/pytest_multi.log
 for n in ${NLIST:-$N}; do
   if [ "$n" = 1 ]; then

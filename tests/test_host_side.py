@@ -225,3 +225,27 @@ def test_synthetic_unstructured_mesh_matches_oracle_geometry_and_teno_tables(ora
     so = oracle_mod.Solver(om, "TENO", "HLLC", "SSPRK3", order=3, bcs=syn.EXTRAP4)
     for k in ("teno:stencils", "teno:reconstruction_matrices", "teno:transformed_areas", "teno:offsets_stencils"):
         assert np.array_equal(plan.get(k), so.get(k)), k
+
+
+SYM4 = [dict(name=n, type="symmetry") for n in ("left", "right", "top", "bottom")]
+
+
+@pytest.mark.parametrize("n_ranks", [2, 3])
+def test_partitioned_plan_numbers_interior_cells_first(n_ranks):
+    """Multi-GPU overlap: the owned cells whose TENO stencils hold owned cells only come first, so their
+    reconstruction can run while the ghost states are in flight; each class keeps the unpartitioned plan's relative order."""
+    mesh = mb.Mesh.generate("cartesian_tri", 30, 20, 3.0, 2.0)
+    part = mb.partition(mesh, n_ranks)
+    whole = mb.Plan(mesh, "TENO", order=3, bcs=SYM4, fp_mode="fast")
+    for r in range(n_ranks):
+        plan = mb.Plan(mesh, "TENO", order=3, bcs=SYM4, fp_mode="fast", part=part, rank=r, n_ranks=n_ranks)
+        ni = int(plan.get("n_interior")[0])
+        CT, S, MC = plan.stream_tile, 4, plan.M - 1
+        n_ft = (plan.N_recon + CT - 1) // CT
+        ids = plan.get("fm_ids").reshape(n_ft, S, MC, CT)
+        touches_ghost = np.array([(ids[i // CT, :, :, i % CT] >= plan.N_owned).any() for i in range(plan.N_owned)])
+        assert 0 < ni < plan.N_owned
+        assert not touches_ghost[:ni].any() and touches_ghost[ni:].all()
+        perm = plan.get("perm_cells")
+        assert (part[perm[:plan.N_owned]] == r).all() and (part[perm[plan.N_owned:]] != r).all()
+        assert int(whole.get("n_interior")[0]) == whole.N_owned
