@@ -148,6 +148,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="riemann_2d", choices=["riemann_2d", "vortex"],
+                    help="riemann_2d = BASELINE configs[1] (the metric's configuration); vortex = configs[3] family: isentropic vortex on a "
+                         "jittered, id-shuffled triangulation (--nx 2828 --ny 2828 = 16 M cells)")
     ap.add_argument("--nx", type=int, default=1024)
     ap.add_argument("--ny", type=int, default=1024)
     ap.add_argument("--fp", default="fast", choices=["strict", "fast"])
@@ -159,6 +162,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = "examples/riemann_2d: cartesian_tri %dx%d, TENO(legendre,p=3)+HLLC+SSPRK3, cfl=0.1, four-quadrant IC" % (a.nx, a.ny)
+    if a.workload == "vortex":
+        workload = ("synthetic isentropic vortex on a jittered (+-0.15 h, seed 12345), id-shuffled triangulation %dx%d of [0,10]^2, "
+                    "TENO(legendre,p=3)+HLLC+SSPRK3, cfl=0.1, extrapolation BCs" % (a.nx, a.ny))
 
     if a.impl == "reference":
         if rank != 0:
@@ -184,10 +190,19 @@ def main():
 
     torch.cuda.set_device(0)
     t_setup = time.perf_counter()
-    mesh = mb.Mesh.generate("cartesian_tri", a.nx, a.ny, 1.0, 1.0)
+    if a.workload == "vortex":
+        from mallard_b200 import synthetic as syn
+        mb.set_host_threads(host_cores())
+        mesh = syn.jittered_tri(a.nx, a.ny, 10.0, 10.0, seed=12345)
+        U0, P0, bcs = syn.isentropic_vortex(mesh.arrays["cell_coords"]), None, syn.EXTRAP4
+        a.no_cpu_baseline = True      # the reference cannot read an unstructured mesh (mesh.cpp:41-43); its per-cell cost is mesh independent
+    else:
+        mesh = mb.Mesh.generate("cartesian_tri", a.nx, a.ny, 1.0, 1.0)
+        U0, P0 = riemann2d_state(mesh.arrays["cell_coords"])
+        bcs = SYM4
     nc = mesh.n_cells
-    U0, P0 = riemann2d_state(mesh.arrays["cell_coords"])
-    s = mb.Solver(mesh, a.recon, "HLLC", "SSPRK3", order=3, bcs=SYM4, fp_mode=a.fp, keep_stage_rhs=False)
+    mesh_s = time.perf_counter() - t_setup
+    s = mb.Solver(mesh, a.recon, "HLLC", "SSPRK3", order=3, bcs=bcs, fp_mode=a.fp, keep_stage_rhs=False)
     stats = s.get("stats")
     setup_s = time.perf_counter() - t_setup
     s.set_state(U0, P0)
@@ -229,7 +244,16 @@ def main():
         alg = {"teno_recon": ALG_BYTES_RECON, "teno_stream": ALG_BYTES_RECON, "face_flux_teno": 48.0, "gather_stage": 72.0, "face_flux_fo": 80.0,
                "cfl": 200.0}.get(top, ALG_BYTES_STAGE)
         achieved = alg * nc / (per_launch_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this very
+        # workload (profiles/ncu_traffic.json, written by scripts/ncu_summary.py); null for any other workload / size
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if tj.get("n_cells") == nc and tj.get("workload") == a.workload and tj.get("fp_mode") == a.fp:
+                traffic = tj["bytes_per_launch"].get(top)
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_cell": alg, "share_of_step": prof[top][0] / sum(v[0] for v in prof.values())}
         stage_ms = sum(prof[k][0] for k in prof if k != "cfl") / (a.steps * N_STAGES)
         roof["stage_achieved"] = ALG_BYTES_STAGE * nc / (stage_ms * 1e-3) / 1e9
@@ -263,7 +287,7 @@ def main():
     line = {"metric": "cell-updates/s per RK stage", "value": value, "unit": "cell-updates/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "n_cells": nc, "fp_mode": a.fp, "recon": a.recon, "l2": "inputs larger than L2 (TENO tables %.1f GB per stage)" % (stats[2] / 1e9),
-                       "device_bytes": stats[2], "preprocess_seconds": stats[1], "setup_seconds": setup_s,
+                       "device_bytes": stats[2], "preprocess_seconds": stats[1], "setup_seconds": setup_s, "mesh_seconds": mesh_s,
                        "preprocess": {"host_total_s": stats[1], "host_stencil_search_s": stats[8], "host_matrices_s": stats[9],
                                       "device_table_build_s": stats[10]},
                        "note": "reference-faithful TENO: like the reference, the state turns non-finite inside step 1 (SURVEY 0.2); cost is data-independent"},

@@ -466,6 +466,10 @@ void rcm_order(const HostMesh & m, const std::vector<uint32_t> & cells, uvec & o
 void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<std::string> & bc_zones,
                 const PrepOptions & opt, Prep & P) {
     const auto t0 = std::chrono::steady_clock::now();
+    const bool timing = getenv("MLB_PREP_TIMING") != nullptr;
+    auto tick = [&](const char * what) {
+        if (timing) fprintf(stderr, "[mlb]   %-28s at %.2f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    };
     const bool teno = num.recon == MLB_RECON_TENO;
     int n_slots = 0;
     for (uint32_t c = 0; c < m.nc; c++) n_slots = std::max(n_slots, m.nfc(c));
@@ -527,6 +531,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
     const uint32_t n_recon = (uint32_t)order.size();
     uint32_t n_interior = opt.part ? 0u : n_owned;   // first order: no reconstruction kernel to overlap
 
+    tick("renumbering done");
     // ---- TENO stencils for owned + ring-1 cells (parallel), written into the tile layout with REFERENCE ids first;
     //      state-only ghosts are whatever else those stencils touch
     const size_t n_tiles = (n_recon + TILE - 1) / TILE;
@@ -596,6 +601,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
     P.iperm_cells.assign(m.nc, NO_FACE);
     for (uint32_t i = 0; i < N; i++) P.iperm_cells[order[i]] = i;
 
+    tick("stencils done");
     // ---- faces of owned cells, ordered by (owner = lower library cell id, other)
     {
         std::vector<std::pair<uint64_t, uint32_t>> keyed;
@@ -620,6 +626,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
     std::vector<uint32_t> iperm_faces(m.nf, NO_FACE);
     for (uint32_t i = 0; i < P.NF; i++) iperm_faces[P.perm_faces[i]] = i;
 
+    tick("faces ordered");
     // ---- zone binding: order key of every face = (0, pos in interior zone) or (1 + bc index, pos in its zone)
     std::vector<int32_t> face_bc(m.nf, INT32_MIN);          // bc index for boundary faces with a [[boundaries]] entry
     std::vector<uint64_t> face_key(m.nf, UINT64_MAX);
@@ -635,6 +642,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
         }
     }
 
+    tick("zones bound");
     // ---- geometry in library numbering
     const uint32_t Np = P.Npad;
     P.cell_vol.assign(Np, 1.0);
@@ -657,6 +665,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
         P.face_area[i] = m.face_area[f];
     }
 
+    tick("geometry done");
     // ---- slots
     P.slot_face.assign((size_t)n_slots * Np, NO_FACE);
     P.slot_nbr.assign((size_t)n_slots * Np, INT32_MIN);
@@ -705,6 +714,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
         P.rhs_order[i] = code;
     }
 
+    tick("slots done");
     // ---- face-centred view of the same connectivity (face flux kernel)
     P.face_cl.assign(P.NFpad, 0u);
     P.face_cr.assign(P.NFpad, INT32_MIN);
@@ -727,6 +737,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
             }
         }
 
+    tick("face view done");
     // ---- TENO tables
     if (teno) {
         const int K = T.K, M = T.M, Mp = T.Mp, S = T.S;

@@ -25,7 +25,37 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio"]
 
 
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+BENCH_NAME = [("teno_stream", "teno_stream"), ("teno_recon", "teno_recon"), ("face_flux", "face_flux_teno"), ("gather_stage", "gather_stage"), ("cfl_kernel", "cfl")]
+
+
+def write_traffic(rows, idx, units, path, meta):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (first captured launch of each kernel) -> JSON for bench.py"""
+    import json
+    out = {}
+    for r in rows:
+        name = r[idx["Kernel Name"]]
+        key = next((b for pat, b in BENCH_NAME if pat in name), None)
+        if key is None or key in out:
+            continue
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(r[idx[m]].replace(",", "")) * UNIT[units[idx[m]]]
+        out[key] = tot
+    meta = dict(kv.split("=", 1) for kv in meta)
+    if "n_cells" in meta:
+        meta["n_cells"] = int(meta["n_cells"])
+    json.dump(dict(meta, bytes_per_launch=out, source="ncu --set full --clock-control none (dram__bytes_read.sum + dram__bytes_write.sum)"),
+              open(path, "w"), indent=1)
+
+
 def main():
+    if "--traffic" in sys.argv:      # ncu_summary.py prof.ncu-rep --traffic out.json key=value ...
+        i = sys.argv.index("--traffic")
+        raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        write_traffic(rows[2:], {h: j for j, h in enumerate(rows[0])}, rows[1], sys.argv[i + 1], sys.argv[i + 2:])
+        return
     rep = sys.argv[1]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
