@@ -153,6 +153,16 @@ int mlb_take_step_host(mlb_ctx *ctx, double cfl /* <=0: keep dt */, double *U_in
 int mlb_run(mlb_ctx *ctx, uint32_t n_steps, double cfl, double *t_out, double *dt_last_out);
 int mlb_get_time(mlb_ctx *ctx, double *t, uint64_t *step);
 
+/* ---- diagnostics and output fed from the device-resident fields.
+ * mlb_field_ranges: the scalar ranges Solver::do_checks prints (max_array / min_array, solver/solver.cpp:434-443,
+ *   common/common_math.h:577-614) for RHO, RHOU_X, RHOU_Y, RHOE, U_X, U_Y, P, T, H, and the number of NaN entries
+ *   Solver::check_fields looks for (solver/solver.cpp:470-498), as one device reduction - no copy of the state.
+ * mlb_write_vtu: DataWriter::write_vtu (io/data_writer.cpp:93-244), byte-identical file "<prefix>_<step:06>.vtu";
+ *   names[] as in the TOML `variables` list ("CFL", "RHO", ..., "H"); `mesh` = the arrays given to mlb_create. */
+int mlb_field_ranges(mlb_ctx *ctx, double *min9, double *max9, uint64_t *n_nan);
+int mlb_write_vtu(mlb_ctx *ctx, const mlb_mesh *mesh, const char *prefix, uint32_t step, int32_t n_vars,
+                  const char *const *names);
+
 /* ---- test hook mirroring the fake RHS of test/time_integrator_test.cpp:22-28 (NULL clears it) */
 int mlb_set_rhs_override(mlb_ctx *ctx, const double *rhs /* [nc][4] */);
 

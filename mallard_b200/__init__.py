@@ -303,6 +303,22 @@ class Solver:
         out = (U,) + ((P,) if prim else ()) + ((Cl,) if cfl_local else ())
         return out[0] if len(out) == 1 else out
 
+    # -- Solver::do_checks / check_fields (solver/solver.cpp:422-498) as device reductions
+    FIELD_NAMES = ("RHO", "RHOU_X", "RHOU_Y", "RHOE", "U_X", "U_Y", "P", "T", "H")
+
+    def field_ranges(self):
+        """({name: (min, max)}, number of NaN entries) of the conserved and primitive fields, reduced on the device."""
+        mn, mx, nn = np.empty(9), np.empty(9), C.c_uint64()
+        self._ok(lib().mlb_field_ranges(self._h, _ptr(mn), _ptr(mx), C.byref(nn)))
+        return {n: (float(a), float(b)) for n, a, b in zip(self.FIELD_NAMES, mn, mx)}, int(nn.value)
+
+    # -- DataWriter::write_vtu (io/data_writer.cpp:93-244)
+    def write_vtu(self, prefix, step, variables=("CFL", "RHO", "RHOU_X", "RHOU_Y", "RHOE", "U_X", "U_Y", "P", "T", "H")):
+        v, keep = self.mesh.view()
+        names = (C.c_char_p * len(variables))(*[x.encode() for x in variables])
+        self._ok(lib().mlb_write_vtu(self._h, C.byref(v), str(prefix).encode(), int(step), len(variables), names))
+        return "%s_%06d.vtu" % (prefix, step)
+
     # -- FaceReconstruction::calc_face_values
     def calc_face_values(self):
         F = np.empty((self.nf, self.n_quad, 2, 4))

@@ -69,6 +69,8 @@ SYMBOLS = {
     "mlb_take_step_host": (C.c_int, [VP, DBL, VP, C.POINTER(DBL)]),
     "mlb_run": (C.c_int, [VP, U32, DBL, C.POINTER(DBL), C.POINTER(DBL)]),
     "mlb_get_time": (C.c_int, [VP, C.POINTER(DBL), C.POINTER(U64)]),
+    "mlb_field_ranges": (C.c_int, [VP, VP, VP, C.POINTER(U64)]),
+    "mlb_write_vtu": (C.c_int, [VP, C.POINTER(MeshView), C.c_char_p, C.c_uint32, C.c_int32, C.POINTER(C.c_char_p)]),
     "mlb_set_rhs_override": (C.c_int, [VP, VP]),
     "mlb_get_array": (C.c_int, [VP, C.c_char_p, VP, C.POINTER(U64)]),
     "mlb_event_record": (C.c_int, [VP, I32]),

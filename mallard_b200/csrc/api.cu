@@ -691,6 +691,106 @@ int mlb_get_time(mlb_ctx * c, double * t, uint64_t * step) {
     API_END(c)
 }
 
+// ---- N3: diagnostics and output fed from the device-resident fields ------------------------------------
+// Solver::do_checks' scalar ranges (solver.cpp:434-443) and check_fields' NaN test (solver.cpp:470-498) as one device
+// reduction: no per-step copy of the state to the host (the reference does copy_device_to_host() every step, solver.cpp:423).
+int mlb_field_ranges(mlb_ctx * c, double * min9, double * max9, uint64_t * n_nan) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    const int nb = field_ranges_blocks(c->prep.N_owned);
+    double * d_part = dev_alloc<double>((size_t)nb * 18 + 18);
+    unsigned long long * d_nan = dev_alloc<unsigned long long>(1);
+    CUDA_OK(cudaMemsetAsync(d_nan, 0, 8, c->stream));
+    launch_field_ranges(c->U[c->cur], c->prim, c->prep.N_owned, c->prep.Npad, d_part, d_part + (size_t)nb * 18, d_nan, c->stream);
+    c->launches += 2;
+    CUDA_OK(cudaGetLastError());
+    double h[18];
+    unsigned long long hn = 0;
+    CUDA_OK(cudaMemcpyAsync(h, d_part + (size_t)nb * 18, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(&hn, d_nan, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_part); cudaFree(d_nan);
+    for (int f = 0; f < 9; f++) { if (min9) min9[f] = h[f]; if (max9) max9[f] = h[9 + f]; }
+    if (n_nan) *n_nan = hn;
+    API_END(c)
+}
+
+// DataWriter::write_vtu (io/data_writer.cpp:93-244), byte for byte: same XML header, same appended-data blocks (4-byte
+// length words, Float64 cell data, 3-component points, UInt32 connectivity / offsets, cell type 7).  The requested
+// variables are gathered on the device into one plane each (reference numbering), copied once, and written with one
+// fwrite per block instead of one ofstream::write per value.
+int mlb_write_vtu(mlb_ctx * c, const mlb_mesh * mesh, const char * prefix, uint32_t step, int32_t n_vars, const char * const * names) {
+    API_BEGIN(c)
+    if (!mesh || !prefix || !names) throw std::runtime_error("mlb_write_vtu: NULL argument");
+    if (n_vars <= 0) throw std::runtime_error("DataWriter: No variables specified.");
+    if (n_vars > 16) throw std::runtime_error("mlb_write_vtu: at most 16 variables");
+    if (c->n_ranks > 1) throw std::runtime_error("mlb_write_vtu: partitioned contexts write through mlb_get_owned");
+    if (mesh->n_cells != c->nc_ref) throw std::runtime_error("mlb_write_vtu: mesh does not match the context");
+    static const char * const NAMES[10] = {"RHO", "RHOU_X", "RHOU_Y", "RHOE", "U_X", "U_Y", "P", "T", "H", "CFL"};   // common_typedef.h:36-49, solver.cpp:349
+    int32_t codes[16];
+    for (int v = 0; v < n_vars; v++) {
+        codes[v] = -1;
+        for (int k = 0; k < 10; k++) if (!strcmp(names[v], NAMES[k])) codes[v] = k;
+        if (codes[v] < 0) throw std::runtime_error(std::string("DataWriter: Unknown variable: ") + names[v] + ".");
+    }
+    CUDA_OK(cudaSetDevice(c->device));
+    const uint32_t nc = mesh->n_cells, nn = mesh->n_nodes;
+    const size_t n = (size_t)n_vars * nc;
+    c->ensure_stage(n);
+    launch_export_fields(n_vars, codes, c->U[c->cur], c->prim, c->sr, c->scal, c->d_perm_cells, c->prep.N_owned, c->prep.Npad, nc, c->d_stage, c->stream);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(c->h_stage, c->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+
+    char fname[4096];
+    snprintf(fname, sizeof(fname), "%s_%06u.vtu", prefix, step);          // LEN_STEP = 6, common_io.h:19
+    FILE * out = fopen(fname, "wb");
+    if (!out) throw std::runtime_error(std::string("DataWriter::write_vtu: Could not open file: ") + fname + ".");
+    const uint64_t len_conn = mesh->offsets_nodes_of_cell[nc] - mesh->offsets_nodes_of_cell[0];
+    uint64_t off = 0;
+    fprintf(out, "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n");
+    fprintf(out, "  <UnstructuredGrid>\n    <Piece NumberOfPoints=\"%u\" NumberOfCells=\"%u\">\n", nn, nc);
+    fprintf(out, "      <PointData>\n      </PointData>\n      <CellData>\n");
+    for (int v = 0; v < n_vars; v++) {
+        fprintf(out, "        <DataArray type=\"Float64\" Name=\"%s\" format=\"appended\" offset=\"%llu\">\n        </DataArray>\n", names[v], (unsigned long long)off);
+        off += 4 + (uint64_t)nc * 8;
+    }
+    fprintf(out, "      </CellData>\n      <Points>\n");
+    fprintf(out, "        <DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"appended\" offset=\"%llu\">\n        </DataArray>\n", (unsigned long long)off);
+    off += 4 + (uint64_t)nn * 3 * 8;
+    fprintf(out, "      </Points>\n      <Cells>\n");
+    fprintf(out, "        <DataArray type=\"UInt32\" Name=\"connectivity\" format=\"appended\" offset=\"%llu\">\n        </DataArray>\n", (unsigned long long)off);
+    off += 4 + len_conn * 4;
+    fprintf(out, "        <DataArray type=\"UInt32\" Name=\"offsets\" format=\"appended\" offset=\"%llu\">\n        </DataArray>\n", (unsigned long long)off);
+    off += 4 + (uint64_t)nc * 4;
+    fprintf(out, "        <DataArray type=\"UInt8\" Name=\"types\" format=\"appended\" offset=\"%llu\">\n        </DataArray>\n", (unsigned long long)off);
+    fprintf(out, "      </Cells>\n    </Piece>\n  </UnstructuredGrid>\n<AppendedData encoding=\"raw\">\n_");
+    auto block = [&](uint64_t n_bytes, const void * data) {               // the reference writes the low 4 bytes of a u_int64_t length
+        fwrite(&n_bytes, 4, 1, out);
+        if (n_bytes) fwrite(data, 1, n_bytes, out);
+    };
+    for (int v = 0; v < n_vars; v++) block((uint64_t)nc * 8, c->h_stage + (size_t)v * nc);
+    {
+        std::vector<double> pts((size_t)nn * 3);
+        for (uint32_t i = 0; i < nn; i++) { pts[3 * (size_t)i] = mesh->node_coords[2 * (size_t)i]; pts[3 * (size_t)i + 1] = mesh->node_coords[2 * (size_t)i + 1]; pts[3 * (size_t)i + 2] = 0.0; }
+        block((uint64_t)nn * 3 * 8, pts.data());
+    }
+    block(len_conn * 4, mesh->nodes_of_cell + mesh->offsets_nodes_of_cell[0]);
+    {
+        std::vector<uint32_t> offs(nc);
+        for (uint32_t i = 0; i < nc; i++) offs[i] = mesh->offsets_nodes_of_cell[i + 1] - mesh->offsets_nodes_of_cell[0];
+        block((uint64_t)nc * 4, offs.data());
+    }
+    {
+        std::vector<uint8_t> types(nc, 7);
+        block((uint64_t)nc, types.data());
+    }
+    fprintf(out, "\n</AppendedData>\n</VTKFile>\n");
+    if (fclose(out) != 0) throw std::runtime_error(std::string("DataWriter::write_vtu: Could not write to file: ") + fname + ".");
+    API_END(c)
+}
+
 int mlb_set_rhs_override(mlb_ctx * c, const double * rhs) {
     API_BEGIN(c)
     CUDA_OK(cudaSetDevice(c->device));

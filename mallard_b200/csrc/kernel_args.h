@@ -149,6 +149,12 @@ void launch_gather(const double * soa, const uint32_t * idx, uint32_t n, uint32_
 void launch_scatter(const double * buf, const uint32_t * idx, uint32_t n, uint32_t npad, double * soa, cudaStream_t);
 void launch_apply_dt(double * scal, long long * max_bits, double cfl, double global_max, int use_global, cudaStream_t);
 void launch_set_scalar(double * scal, int which, double v, cudaStream_t);
+// N3: output fields as variable planes in reference numbering, and the do_checks / check_fields reductions
+void launch_export_fields(int n_fields, const int32_t * codes, const double * U, const double * prim, const double * sr, const double * scal,
+                          const uint32_t * perm, uint32_t n, uint32_t npad, uint32_t n_ref, double * out, cudaStream_t);
+int field_ranges_blocks(uint32_t n);
+void launch_field_ranges(const double * U, const double * prim, uint32_t n, uint32_t npad, double * partial /* [blocks][18] */,
+                         double * out18, unsigned long long * nan_count, cudaStream_t);
 void launch_export_faces(const double * Fc, const double * U, const uint32_t * slot_face, const uint32_t * perm_faces, uint32_t n,
                          uint32_t npad, int n_slots, int Q, double * F_aos /* [nf_ref][Q][2][4] */, cudaStream_t);
 

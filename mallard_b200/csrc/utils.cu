@@ -1,5 +1,7 @@
 // Layout / bookkeeping kernels that do no floating-point arithmetic of the path (or a single IEEE operation), shared by
 // both floating-point modes: AoS(reference numbering) <-> SoA(library numbering) conversion, halo pack/unpack, dt.
+#include <cfloat>
+
 #include "kernel_args.h"
 
 namespace mlb {
@@ -83,9 +85,95 @@ __global__ void export_faces_kernel(const double * __restrict__ Fc, const double
     }
 }
 
+// Output fields as the reference's writer sees them (solver.cpp:336-350: Data views of conservatives, primitives, cfl_local),
+// one plane per requested variable in REFERENCE numbering: out[v][perm[i]].  code 0-3 conserved, 4-8 primitives, 9 CFL.
+struct FieldCodes { int32_t n; int32_t code[16]; };
+__device__ __forceinline__ double field_value(int code, uint32_t i, uint32_t npad, const double * U, const double * prim, const double * sr,
+                                              const double * scal) {
+    if (code < 4) return U[4 * (size_t)i + code];
+    if (code < 9) return prim[(size_t)(code - 4) * npad + i];
+    return scal[SC_DT] * sr[i];                          // KokkosBlas::scal(cfl_local, dt, cfl_local), solver.cpp:584
+}
+__global__ void export_fields_kernel(FieldCodes fc, const double * __restrict__ U, const double * __restrict__ prim,
+                                     const double * __restrict__ sr, const double * __restrict__ scal, const uint32_t * __restrict__ perm,
+                                     uint32_t n, uint32_t npad, uint32_t n_ref, double * __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t r = perm ? perm[i] : i;
+    for (int v = 0; v < fc.n; v++) out[(size_t)v * n_ref + r] = field_value(fc.code[v], i, npad, U, prim, sr, scal);
+}
+
+// max_array / min_array of Solver::do_checks (solver.cpp:434-437, common_math.h:577-614) and the NaN count of check_fields
+// (solver.cpp:470-498) in one pass over the device-resident fields: 9 fields x {min, max}.  A comparison with NaN is false
+// on both sides, exactly as `if (a > max)` / `if (a < min)` in the reference's reducers.
+__global__ void __launch_bounds__(256) field_ranges_kernel(const double * __restrict__ U, const double * __restrict__ prim, uint32_t n, uint32_t npad,
+                                                           double * __restrict__ partial /* [grid][18] */, unsigned long long * __restrict__ nan_count) {
+    __shared__ double red[8][18];
+    double mn[9], mx[9];
+#pragma unroll
+    for (int f = 0; f < 9; f++) { mn[f] = DBL_MAX; mx[f] = -DBL_MAX; }
+    unsigned nan = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int f = 0; f < 9; f++) {
+            const double v = f < 4 ? U[4 * (size_t)i + f] : prim[(size_t)(f - 4) * npad + i];
+            if (v < mn[f]) mn[f] = v;
+            if (v > mx[f]) mx[f] = v;
+            nan += (v != v);
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < 9; f++)
+        for (int o = 16; o > 0; o >>= 1) {
+            const double a = __shfl_xor_sync(0xffffffffu, mn[f], o), b = __shfl_xor_sync(0xffffffffu, mx[f], o);
+            if (a < mn[f]) mn[f] = a;
+            if (b > mx[f]) mx[f] = b;
+        }
+    for (int o = 16; o > 0; o >>= 1) nan += __shfl_xor_sync(0xffffffffu, nan, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        for (int f = 0; f < 9; f++) { red[w][f] = mn[f]; red[w][9 + f] = mx[f]; }
+        if (nan) atomicAdd(nan_count, (unsigned long long)nan);
+    }
+    __syncthreads();
+    if (threadIdx.x < 18) {
+        double v = red[0][threadIdx.x];
+        for (int k = 1; k < 8; k++) {
+            const double o = red[k][threadIdx.x];
+            if (threadIdx.x < 9 ? o < v : o > v) v = o;
+        }
+        partial[(size_t)blockIdx.x * 18 + threadIdx.x] = v;
+    }
+}
+__global__ void field_ranges_finish_kernel(const double * __restrict__ partial, int n_blocks, double * __restrict__ out /* [18] */) {
+    const int t = threadIdx.x;
+    if (t >= 18) return;
+    double v = partial[t];
+    for (int k = 1; k < n_blocks; k++) {
+        const double o = partial[(size_t)k * 18 + t];
+        if (t < 9 ? o < v : o > v) v = o;
+    }
+    out[t] = v;
+}
+
 inline unsigned blocks(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
+
+void launch_export_fields(int n_fields, const int32_t * codes, const double * U, const double * prim, const double * sr, const double * scal,
+                          const uint32_t * perm, uint32_t n, uint32_t npad, uint32_t n_ref, double * out, cudaStream_t st) {
+    FieldCodes fc{};
+    fc.n = n_fields;
+    for (int i = 0; i < n_fields && i < 16; i++) fc.code[i] = codes[i];
+    if (n) export_fields_kernel<<<blocks(n, 256), 256, 0, st>>>(fc, U, prim, sr, scal, perm, n, npad, n_ref, out);
+}
+int field_ranges_blocks(uint32_t n) { const unsigned b = blocks(n, 256); return (int)(b < 592u ? (b ? b : 1u) : 592u); }
+void launch_field_ranges(const double * U, const double * prim, uint32_t n, uint32_t npad, double * partial, double * out18,
+                         unsigned long long * nan_count, cudaStream_t st) {
+    const int nb = field_ranges_blocks(n);
+    field_ranges_kernel<<<nb, 256, 0, st>>>(U, prim, n, npad, partial, nan_count);
+    field_ranges_finish_kernel<<<1, 32, 0, st>>>(partial, nb, out18);
+}
 
 void launch_import_state(const double * aos, const uint32_t * perm, uint32_t n, uint32_t npad, int nv, double * soa, cudaStream_t st) {
     if (n) import_kernel<<<blocks(n, 256), 256, 0, st>>>(aos, perm, n, npad, nv, soa);

@@ -12,7 +12,12 @@
 // reference's own host views, which this harness fills from the GPU.  Because all members live in headers, the private
 // state is reached with `#define private public` instead of patching reference sources (same trick as ref_harness.cpp).
 //
-// Usage: mallard_dropin -i input.toml [--fp strict|fast] [--quiet]
+// --native-io also replaces the two callers either side of the path: do_checks' scalar ranges and
+// check_fields' NaN test come from mlb_field_ranges (a device reduction), and the VTU files are written by
+// mlb_write_vtu ("<prefix>_native_<step>.vtu") straight from the device-resident fields; the per-step
+// copy_device_to_host() of the reference (solver.cpp:423) disappears.
+//
+// Usage: mallard_dropin -i input.toml [--fp strict|fast] [--quiet] [--native-io]
 // Last line of stdout: JSON with steps, t, wall seconds of the loop and cell-updates/s per RK stage.
 #include <sstream>
 #define private public
@@ -50,11 +55,12 @@ int enum_of(const std::string & s, std::initializer_list<std::pair<const char *,
 
 int main(int argc, char ** argv) {
     std::string input_file, fp = "strict";
-    bool quiet = false;
+    bool quiet = false, native_io = false;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "-i") && i + 1 < argc) input_file = argv[++i];
         else if (!strcmp(argv[i], "--fp") && i + 1 < argc) fp = argv[++i];
         else if (!strcmp(argv[i], "--quiet")) quiet = true;
+        else if (!strcmp(argv[i], "--native-io")) native_io = true;
     }
     if (input_file.empty()) { fprintf(stderr, "usage: mallard_dropin -i input.toml [--fp strict|fast] [--quiet]\n"); return 2; }
     Kokkos::initialize(argc, argv);
@@ -135,6 +141,50 @@ int main(int argc, char ** argv) {
 
             // ---- Solver::run (solver.cpp:352-373) with the seams rerouted
             const int n_stages = mlb_n_stages(ctx);
+            if (native_io) {
+                // writers as the reference configured them (DataWriter::init): prefix, interval, variable names
+                auto write_native = [&](bool force) {
+                    for (auto & w : s.data_writers) {
+                        if (!((s.step % w->interval == 0) || force)) continue;          // DataWriter::write, data_writer.cpp:77-80
+                        std::vector<std::string> vn;
+                        for (auto * d : w->data_ptrs) vn.push_back(d->name());
+                        std::vector<const char *> vp;
+                        for (auto & x : vn) vp.push_back(x.c_str());
+                        MLB_OK(mlb_write_vtu(ctx, &mm, (w->prefix + "_native").c_str(), s.step, (int32_t)vp.size(), vp.data()));
+                    }
+                };
+                static const char * const NAMES[9] = {"RHO", "RHOU_X", "RHOU_Y", "RHOE", "U_X", "U_Y", "P", "T", "H"};
+                write_native(true);
+                auto t0n = std::chrono::steady_clock::now();
+                while (!s.done()) {
+                    if (s.step % s.check_interval == 0) {                               // Solver::do_checks, solver.cpp:422-443
+                        double mn[9], mx[9];
+                        MLB_OK(mlb_field_ranges(ctx, mn, mx, nullptr));
+                        s.print_step_info();
+                        for (int i = 0; i < 9; i++)
+                            std::cout << "> Scalar range: " << NAMES[i] << " = [" << mn[i] << ", " << mx[i] << "]" << std::endl;
+                    }
+                    if (s.use_cfl) MLB_OK(mlb_calc_dt(ctx, s.cfl, &s.dt));
+                    else MLB_OK(mlb_set_dt(ctx, s.dt));
+                    MLB_OK(mlb_take_step(ctx));
+                    s.step++;
+                    s.t += s.dt;
+                    if (s.check_nan) {                                                  // Solver::check_fields, solver.cpp:470-498
+                        uint64_t n_nan = 0;
+                        MLB_OK(mlb_field_ranges(ctx, nullptr, nullptr, &n_nan));
+                        if (n_nan) throw std::runtime_error("NaN found in fields.");
+                    }
+                    write_native(false);
+                }
+                auto t1n = std::chrono::steady_clock::now();
+                write_native(true);
+                std::cout.rdbuf(old);
+                const double secn = std::chrono::duration<double>(t1n - t0n).count();
+                printf("{\"n_cells\": %u, \"steps\": %u, \"t\": %.17g, \"dt_last\": %.17g, \"seconds\": %.6e, \"cell_updates_per_s_per_stage\": %.6e, "
+                       "\"fp_mode\": \"%s\", \"launches\": %llu, \"native_io\": true}\n",
+                       m.n_cells, (unsigned)s.step, (double)s.t, (double)s.dt, secn, (double)m.n_cells * n_stages * s.step / secn, fp.c_str(),
+                       (unsigned long long)mlb_launch_count(ctx));
+            } else {
             s.write_data(true);
             auto t0 = std::chrono::steady_clock::now();
             while (!s.done()) {
@@ -159,6 +209,7 @@ int main(int argc, char ** argv) {
                    "\"fp_mode\": \"%s\", \"launches\": %llu}\n",
                    m.n_cells, (unsigned)s.step, (double)s.t, (double)s.dt, sec, (double)m.n_cells * n_stages * s.step / sec, fp.c_str(),
                    (unsigned long long)mlb_launch_count(ctx));
+            }
         } catch (const std::exception & e) {
             std::cout.rdbuf(old);
             fprintf(stderr, "mallard_dropin: %s\n", e.what());

@@ -162,3 +162,38 @@ def test_reference_host_with_b200_hot_path_writes_the_reference_solution(tmp_pat
     assert worst <= tol
     if tol == 0.0:
         assert identical == len(fa)
+
+
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(DROPIN)), reason="oracle/_ref binaries not built (need /root/reference)")
+@pytest.mark.parametrize("name,toml,tol", [("sod", SOD, 1e-9), ("wedge", WEDGE, 0.0)], ids=["sod", "wedge"])
+def test_native_vtu_writer_and_device_side_checks(tmp_path, name, toml, tol):
+    """--native-io replaces the reference's per-step copy_device_to_host + do_checks + check_fields + VTU writer
+    with mlb_field_ranges (device reduction) and mlb_write_vtu (fed from the device-resident fields).  The files must be
+    the reference writer's byte for byte wherever the fields are (wedge, STRICT mode), and the "Scalar range" lines of the
+    log must read the same."""
+    a, b = str(tmp_path / "ref"), str(tmp_path / "native")
+    out_ref = run(REF, toml, a)
+    out_nat = run(DROPIN, toml, b, ("--fp", "strict", "--native-io"))
+    fa = sorted(os.listdir(os.path.join(a, "solut", "all")))
+    fb = sorted(os.listdir(os.path.join(b, "solut", "all")))
+    assert [f.replace("_native", "") for f in fb] == fa and len(fa) >= 3
+    for f, g in zip(fa, fb):
+        ra, rb = open(os.path.join(a, "solut", "all", f), "rb").read(), open(os.path.join(b, "solut", "all", g), "rb").read()
+        assert len(ra) == len(rb)
+        # the XML part (header, offsets, footer) is identical whatever the field values
+        cut = ra.index(b'<AppendedData encoding="raw">')
+        assert ra[:cut] == rb[:cut] and ra[-40:] == rb[-40:]
+        if tol == 0.0:
+            assert ra == rb, f
+        else:
+            va, vb = read_vtu(os.path.join(a, "solut", "all", f)), read_vtu(os.path.join(b, "solut", "all", g))
+            for k in va:
+                if va[k].dtype.kind != "f":
+                    assert np.array_equal(va[k], vb[k])
+                else:
+                    assert np.abs(va[k] - vb[k]).max() <= tol * max(np.abs(va[k]).max(), 1.0), (f, k)
+    ranges = lambda txt: [l for l in txt.splitlines() if l.startswith("> Scalar range:")]
+    ra, rb = ranges(out_ref), ranges(out_nat)
+    assert len(ra) == len(rb) and len(ra) >= 9
+    if tol == 0.0:
+        assert ra == rb

@@ -240,7 +240,7 @@ def test_host_buffer_seams_match_resident_path():
     assert dt_b == dt and np.array_equal(U1, a.get_state())
 
 
-@pytest.mark.parametrize("recon,n", [("FO", 700), ("TENO", 256)])
+@pytest.mark.parametrize("recon,n", [("FO", 700), ("TENO", 256), ("TENO", 1024)])   # 1024: BASELINE configs[1]'s full size
 def test_large_mesh_properties(recon, n):
     """Size-independent properties at sizes the oracle cannot reach quickly: free-stream preservation and discrete
     conservation (sum of V*rhs vanishes in the interior; with symmetry walls the mass residual sums to zero)."""
@@ -267,6 +267,32 @@ def test_large_mesh_properties(recon, n):
     assert np.isfinite(U).all() and t > 0
     mass0, mass1 = np.sum(V * U0[:, 0]), np.sum(V * U[:, 0])
     assert abs(mass1 - mass0) < 1e-12 * mass0
+
+
+def test_full_size_riemann2d_fast_mode_matches_the_bit_faithful_mode():
+    """BASELINE configs[1] at its full size (cartesian_tri 1024^2, four-quadrant IC, TENO p=3 + HLLC + SSPRK3): the oracle
+    needs ~8 minutes of serial preprocessing there, so parity is carried by transitivity - STRICT mode is pinned bit-exact
+    against the reference on the small fixtures, and here the FAST path (compact device-built tables, warp-private
+    streaming kernel, FMA) must agree with STRICT on stage-1 face values, the residual and one full step."""
+    import bench
+    mesh = mb.Mesh.generate("cartesian_tri", 1024, 1024, 1.0, 1.0)
+    U0, P0 = bench.riemann2d_state(mesh.arrays["cell_coords"])
+    out = {}
+    for fp in ("strict", "fast"):
+        s = mb.Solver(mesh, "TENO", "HLLC", "SSPRK3", order=3, bcs=SYM4, fp_mode=fp, teno_fixed=True, keep_stage_rhs=False)
+        s.set_state(U0, P0)
+        real = gu.real_faces(mesh.arrays["cells_of_face"], mesh.arrays["nodes_of_face"])
+        F = s.calc_face_values()[real][:, :, 0]
+        rhs = s.calc_rhs()
+        dt = s.calc_dt(0.1)
+        s.take_step()
+        out[fp] = (F, rhs, dt, s.get_state())
+        s.close()
+    assert gu.field_err(out["fast"][0], out["strict"][0]) <= TOL
+    assert gu.field_err(out["fast"][1], out["strict"][1]) <= 1e-10     # residual: flux differences divided by cell volumes ~ 5e-7
+    assert abs(out["fast"][2] - out["strict"][2]) <= TOL * out["strict"][2]
+    assert np.isfinite(out["strict"][3]).all()
+    assert gu.field_err(out["fast"][3], out["strict"][3]) <= TOL
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -374,3 +400,25 @@ def test_monomial_basis_vs_oracle(oracle_mod, order, fixed, fp):
     dto, dtg = so.calc_dt(0.3), sg.calc_dt(0.3)
     so.take_step(dto); sg.take_step()
     assert err(sg.get_state(), so.get("U")) <= TOL
+
+
+def test_device_side_field_ranges_and_nan_count():
+    """mlb_field_ranges = max_array / min_array of Solver::do_checks (solver.cpp:434-437; `a > max` / `a < min`, so NaN never
+    wins) + the NaN test of check_fields (solver.cpp:470-498), against numpy on the exported state."""
+    mesh = mb.Mesh.generate("wedge", 60, 40, 4.0, 1.5)
+    s = mb.Solver(mesh, "FO", "HLLC", "SSPRK3", bcs=SYM4, fp_mode="strict")
+    U0 = _random_smooth_state(mesh.arrays["cell_coords"], np.random.default_rng(5))
+    s.set_state(U0)
+    s.run(2, cfl=0.5)
+    U, P = s.get_state(prim=True)
+    rng, n_nan = s.field_ranges()
+    assert n_nan == 0
+    for i, n in enumerate(s.FIELD_NAMES):
+        col = U[:, i] if i < 4 else P[:, i - 4]
+        assert rng[n] == (col.min(), col.max()), n
+    U0[17, 2] = np.nan
+    s.set_state(U0)
+    rng, n_nan = s.field_ranges()
+    U, P = s.get_state(prim=True)
+    assert n_nan == int(np.isnan(U).sum() + np.isnan(P).sum()) and n_nan >= 2
+    assert rng["RHOU_Y"] == (np.nanmin(U[:, 2]), np.nanmax(U[:, 2]))
