@@ -92,7 +92,8 @@ __device__ __forceinline__ double field_value(int code, uint32_t i, uint32_t npa
                                               const double * scal) {
     if (code < 4) return U[4 * (size_t)i + code];
     if (code < 9) return prim[(size_t)(code - 4) * npad + i];
-    return scal[SC_DT] * sr[i];                          // KokkosBlas::scal(cfl_local, dt, cfl_local), solver.cpp:584
+    const double r = sr[i];                              // 0 until the first calc_dt: the reference's cfl_local is +0 then
+    return r == 0.0 ? 0.0 : scal[SC_DT] * r;             // KokkosBlas::scal(cfl_local, dt, cfl_local), solver.cpp:584
 }
 __global__ void export_fields_kernel(FieldCodes fc, const double * __restrict__ U, const double * __restrict__ prim,
                                      const double * __restrict__ sr, const double * __restrict__ scal, const uint32_t * __restrict__ perm,
