@@ -155,6 +155,9 @@ def main():
     ap.add_argument("--ny", type=int, default=1024)
     ap.add_argument("--fp", default="fast", choices=["strict", "fast"])
     ap.add_argument("--recon", default="TENO", choices=["TENO", "FO"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every GPU owns an nx x ny block (default, the driver's scaling run); strong = the nx x ny mesh is "
+                         "split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
@@ -197,8 +200,10 @@ def main():
         U0, P0, bcs = syn.isentropic_vortex(mesh.arrays["cell_coords"]), None, syn.EXTRAP4
         a.no_cpu_baseline = True      # the reference cannot read an unstructured mesh (mesh.cpp:41-43); its per-cell cost is mesh independent
     else:
-        mesh = mb.Mesh.generate("cartesian_tri", a.nx, a.ny, 1.0, 1.0)
-        U0, P0 = riemann2d_state(mesh.arrays["cell_coords"])
+        Lx = a.nx / float(a.ny)                          # square cells; 1024 x 1024 is the reference's unit square
+        mesh = mb.Mesh.generate("cartesian_tri", a.nx, a.ny, Lx, 1.0)
+        xy = mesh.arrays["cell_coords"]
+        U0, P0 = riemann2d_state(np.stack([xy[:, 0] / Lx, xy[:, 1]], 1))
         bcs = SYM4
     nc = mesh.n_cells
     mesh_s = time.perf_counter() - t_setup
