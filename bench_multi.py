@@ -27,16 +27,27 @@ def run(a, rank, world, local_rank, workload):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     t_setup = time.perf_counter()
-    strong = getattr(a, "scaling", "weak") == "strong"
-    gnx = a.nx if strong else a.nx * world                                   # strong: the given mesh is split; weak: one block per GPU
-    Lx = gnx / float(a.ny)                                                    # square cells
-    mesh = mb.Mesh.generate("cartesian_tri", gnx, a.ny, Lx, 1.0)
-    nc = mesh.n_cells
-    xy = mesh.arrays["cell_coords"]
-    part = np.minimum((xy[:, 0] * (world / Lx)).astype(np.int32), world - 1)  # rank r owns the strip x in [r, r+1) Lx / world
-    U0, P0 = bench.riemann2d_state(np.stack([xy[:, 0] / Lx, xy[:, 1]], 1))    # the four-quadrant IC stretched over the strip
+    strong = getattr(a, "scaling", "weak") == "strong" or a.workload == "vortex"
+    if a.workload == "vortex":
+        # BASELINE configs[3]: ONE jittered, id-shuffled triangulation (a.nx x a.ny quads) split over the GPUs by the library's
+        # recursive coordinate bisection (mlb_partition) - an irregular cut through an unstructured numbering
+        from mallard_b200 import synthetic as syn
+        mesh = syn.jittered_tri(a.nx, a.ny, 10.0, 10.0, seed=12345)
+        nc = mesh.n_cells
+        part = mb.partition(mesh, world)
+        U0, P0, bcs = syn.isentropic_vortex(mesh.arrays["cell_coords"]), None, syn.EXTRAP4
+        gnx = a.nx
+    else:
+        gnx = a.nx if strong else a.nx * world                                   # strong: the given mesh is split; weak: one block per GPU
+        Lx = gnx / float(a.ny)                                                    # square cells
+        mesh = mb.Mesh.generate("cartesian_tri", gnx, a.ny, Lx, 1.0)
+        nc = mesh.n_cells
+        xy = mesh.arrays["cell_coords"]
+        part = np.minimum((xy[:, 0] * (world / Lx)).astype(np.int32), world - 1)  # rank r owns the strip x in [r, r+1) Lx / world
+        U0, P0 = bench.riemann2d_state(np.stack([xy[:, 0] / Lx, xy[:, 1]], 1))    # the four-quadrant IC stretched over the strip
+        bcs = bench.SYM4
     ds = DistributedSolver(mesh, part, rank, world, local_rank, recon=a.recon, riemann="HLLC", integrator="SSPRK3", order=3,
-                           bcs=bench.SYM4, fp_mode=a.fp, keep_stage_rhs=False)
+                           bcs=bcs, fp_mode=a.fp, keep_stage_rhs=False)
     s = ds.s
     stats = s.get("stats")
     n_owned = int(stats[4])
@@ -96,7 +107,8 @@ def run(a, rank, world, local_rank, workload):
         line = {"metric": "cell-updates/s per RK stage", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload + ("; the mesh is" if strong else " per GPU; global mesh %dx%d" % (gnx, a.ny)) + " partitioned in x over %d GPUs" % world,
+                "config": {"workload": workload + ("; partitioned by recursive coordinate bisection over %d GPUs" % world if a.workload == "vortex" else
+                                                  ("; the mesh is" if strong else " per GPU; global mesh %dx%d" % (gnx, a.ny)) + " partitioned in x over %d GPUs" % world),
                            "n_cells": nc, "cells_per_gpu": n_owned, "fp_mode": a.fp, "recon": a.recon,
                            "l2": "inputs larger than L2 (TENO tables %.1f GB per GPU per stage)" % (stats[2] / 1e9),
                            "halo": {"max_send_cells_per_stage": int(halo[0].item()), "max_recv_cells_per_stage": int(halo[1].item()),
