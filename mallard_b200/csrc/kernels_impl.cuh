@@ -17,6 +17,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <utility>
 
 #include "kernel_args.h"
@@ -499,6 +500,8 @@ __global__ void __launch_bounds__(RECON_THREADS) teno_recon_kernel(const __grid_
 
 #ifdef MLB_STREAM_KERNELS
 #include "teno_stream.cuh"
+#else
+#include "teno_strict_stream.cuh"
 #endif
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -642,6 +645,14 @@ static bool recon_supported(int order, int Mp, int basis) {
     return (order == 1 && Mp == 6) || (order == 2 && Mp == 12) || (order == 3 && Mp == 20) || (order == 4 && Mp == 30);
 }
 static void launch_recon(const ReconArgs & a, cudaStream_t st) {
+#ifndef MLB_STREAM_KERNELS
+    if (sstream::strict_stream_supported(a)) {       // bit-faithful AND streaming (teno_strict_stream.cuh); same results as below
+        if (a.order == 1 && a.Mp == 6) return sstream::launch_strict_stream<1, 6>(a, st);
+        if (a.order == 2 && a.Mp == 12) return sstream::launch_strict_stream<2, 12>(a, st);
+        if (a.order == 3 && a.Mp == 20) return sstream::launch_strict_stream<3, 20>(a, st);
+        if (a.order == 4 && a.Mp == 30) return sstream::launch_strict_stream<4, 30>(a, st);
+    }
+#endif
     if (a.order == 1 && a.Mp == 6) launch_recon_t<1, 6>(a, st);
     else if (a.order == 2 && a.Mp == 12) launch_recon_t<2, 12>(a, st);
     else if (a.order == 3 && a.Mp == 20) launch_recon_t<3, 20>(a, st);

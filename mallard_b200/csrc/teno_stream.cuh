@@ -23,6 +23,8 @@
 #pragma once
 #include <utility>
 
+#include "stream_ptx.cuh"
+
 namespace stream {
 
 constexpr int CT = FAST_CT;            // cells per tile
@@ -44,46 +46,6 @@ template <int ORDER> struct Cfg {
     static_assert(CHUNK_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t * bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
-        "@P1 bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void * dst, const void * src, uint32_t bytes, uint64_t * bar, uint64_t policy) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
-}
-
-__device__ __forceinline__ uint32_t mbar_test(uint64_t * bar, uint32_t parity) {   // non-blocking probe
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred P1;\n\t"
-                 "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-                 "selp.u32 %0, 1, 0, P1;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok;
-}
-__device__ __forceinline__ void cp_async8(void * dst, const void * src) {                    // LDGSTS: no register staging
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void * dst, const void * src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 // Sum_k c[k] psi_k(x, y) over the stored dofs k = 1..K-1 with the exponents resolved at compile time (a run-time
 // dof_ex()/dof_ey() would index Px/Py dynamically and push them into local memory).
 template <int... Ks>
@@ -91,8 +53,6 @@ __device__ __forceinline__ double poly_sum(const double * c, const double * Px, 
     ((out = fma(c[Ks], Px[std::integral_constant<int, dof_ex(Ks + 1)>::value] * Py[std::integral_constant<int, dof_ey(Ks + 1)>::value], out)), ...);
     return out;
 }
-
-constexpr int FX_ROWS = 17;   // per tile and cell: 12 face end-point coordinates, area_t[0], the cell's 4 conserved values
 
 static bool stream_supported(int order, int M, int Q, int basis, int n_slots) {
     if ((basis != MLB_BASIS_LEGENDRE && basis != MLB_BASIS_MONOMIAL) || n_slots != FAST_S - 1) return false;

@@ -48,15 +48,6 @@ template <int ORDER> struct WSmem {
     static constexpr size_t TOTAL = PER_WARP * WARPS;
 };
 
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// stencil ids: a volatile load keeps its place in the instruction stream (one stencil ahead of its use); left to the
-// compiler it sinks next to the address computation that consumes it and exposes the full global-load latency
-__device__ __forceinline__ uint32_t ld_id(const uint32_t * p) {
-    uint32_t v;
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-
 template <int ORDER, bool MONO>
 __global__ void __launch_bounds__(WTHREADS, MLB_WARP_MINB) teno_stream_warp_kernel(const __grid_constant__ ReconStreamArgs a) {
     using C = Cfg<ORDER>;
