@@ -13,6 +13,25 @@ import time
 import numpy as np
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the end-to-end leg (and the
+    threads that fill them) sit on the GPU's NUMA node instead of wherever the launcher started the process.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if len(cpus) >= 2:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run(a, rank, world, local_rank, workload):
     import torch
     import torch.distributed as dist
@@ -21,9 +40,11 @@ def run(a, rank, world, local_rank, workload):
     from mallard_b200.parallel import DistributedSolver
 
     torch.cuda.set_device(local_rank)
+    total_cores = bench.host_cores()
+    numa = bind_to_gpu_numa_node(local_rank)     # before any pinned allocation: first touch then lands next to the GPU
     # host preprocessing is OpenMP-parallel inside every rank: share the cores instead of oversubscribing them
     # (torchrun presets OMP_NUM_THREADS=1, which would serialise the TENO table construction)
-    mb.set_host_threads(max(1, bench.host_cores() // world))
+    mb.set_host_threads(max(1, min(total_cores // world, bench.host_cores())))
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     t_setup = time.perf_counter()
@@ -113,7 +134,7 @@ def run(a, rank, world, local_rank, workload):
                            "l2": "inputs larger than L2 (TENO tables %.1f GB per GPU per stage)" % (stats[2] / 1e9),
                            "halo": {"max_send_cells_per_stage": int(halo[0].item()), "max_recv_cells_per_stage": int(halo[1].item()),
                                     "max_peers": int(halo[2].item()), "transport": "NCCL send/recv between device buffers + all_reduce(max) of dt"},
-                           "setup_seconds": setup_s},
+                           "setup_seconds": setup_s, "cpus_bound_per_rank": numa},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None}
         print(json.dumps(line))
     dist.barrier()

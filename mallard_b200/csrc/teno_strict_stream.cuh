@@ -24,11 +24,12 @@ template <int ORDER, int MP> struct SCfg {
     static constexpr int K = (ORDER + 1) * (ORDER + 2) / 2;
     static constexpr int ROWB = (MP / 2) * SCT * 16;                          // bytes of one matrix row of a tile
     static constexpr int AREAB = MP * SCT * 8;                                // bytes of a stencil's transformed areas
-    static constexpr int RC = ORDER == 3 ? 2 : 3;                             // rows per chunk (divides K = 3, 6, 10, 15)
+    static constexpr int RC = ORDER == 3 ? 5 : 3;                             // rows per chunk (divides K = 3, 6, 10, 15): the rows of a chunk
+                                                                              // are independent m-ascending chains - the kernel's only ILP
     static constexpr int NCH = K / RC;
     static constexpr int CPS = 1 + NCH;                                       // chunks per stencil: areas, then the rows
     static constexpr int STAGEB = AREAB > RC * ROWB ? AREAB : RC * ROWB;
-    static constexpr int STAGES = 18000 / STAGEB > 8 ? 8 : (18000 / STAGEB < 2 ? 2 : 18000 / STAGEB);
+    static constexpr int STAGES = 19500 / STAGEB > 8 ? 8 : (19500 / STAGEB < 2 ? 2 : 19500 / STAGEB);
     static constexpr size_t RING = (size_t)STAGES * STAGEB;
     static constexpr size_t UBUF = (size_t)MP * SCT * 4 * 8;                  // neighbour states [m][cell][4]
     static constexpr size_t FXBUF = (size_t)2 * FX_ROWS * SCT * 8;
