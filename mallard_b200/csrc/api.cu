@@ -97,6 +97,7 @@ struct mlb_ctx {
     // The exchange lives on its own stream: pack -> (caller's communicator) -> unpack run on comm_stream while the compute
     // stream reconstructs the interior cells; ev_state orders pack after the producer of the state, ev_halo orders the
     // first reader of ghost data after unpack.
+    double * d_ranges = nullptr;       // mlb_field_ranges scratch
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_state = nullptr, ev_halo = nullptr;
     bool halo_pending = false;         // an unpack has been enqueued that the compute stream has not waited for yet
@@ -698,8 +699,11 @@ int mlb_field_ranges(mlb_ctx * c, double * min9, double * max9, uint64_t * n_nan
     API_BEGIN(c)
     CUDA_OK(cudaSetDevice(c->device));
     const int nb = field_ranges_blocks(c->prep.N_owned);
-    double * d_part = dev_alloc<double>((size_t)nb * 18 + 18);
-    unsigned long long * d_nan = dev_alloc<unsigned long long>(1);
+    if (!c->d_ranges) {                                   // per-block partials, the 18 results and the NaN counter: allocated once
+        c->d_ranges = c->alloc<double>((size_t)nb * 18 + 18 + 1);
+    }
+    double * d_part = c->d_ranges;
+    unsigned long long * d_nan = reinterpret_cast<unsigned long long *>(c->d_ranges + (size_t)nb * 18 + 18);
     CUDA_OK(cudaMemsetAsync(d_nan, 0, 8, c->stream));
     launch_field_ranges(c->U[c->cur], c->prim, c->prep.N_owned, c->prep.Npad, d_part, d_part + (size_t)nb * 18, d_nan, c->stream);
     c->launches += 2;
@@ -709,7 +713,6 @@ int mlb_field_ranges(mlb_ctx * c, double * min9, double * max9, uint64_t * n_nan
     CUDA_OK(cudaMemcpyAsync(h, d_part + (size_t)nb * 18, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaMemcpyAsync(&hn, d_nan, 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    cudaFree(d_part); cudaFree(d_nan);
     for (int f = 0; f < 9; f++) { if (min9) min9[f] = h[f]; if (max9) max9[f] = h[9 + f]; }
     if (n_nan) *n_nan = hn;
     API_END(c)
