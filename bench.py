@@ -164,7 +164,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = "examples/riemann_2d: cartesian_tri %dx%d, TENO(legendre,p=3)+HLLC+SSPRK3, cfl=0.1, four-quadrant IC" % (a.nx, a.ny)
+    workload = "examples/riemann_2d: cartesian_tri %dx%d, %s+HLLC+SSPRK3, cfl=0.1, four-quadrant IC" % (
+        a.nx, a.ny, "TENO(legendre,p=3)" if a.recon == "TENO" else "first-order reconstruction")
     if a.workload == "vortex":
         workload = ("synthetic isentropic vortex on a jittered (+-0.15 h, seed 12345), id-shuffled triangulation %dx%d of [0,10]^2, "
                     "TENO(legendre,p=3)+HLLC+SSPRK3, cfl=0.1, extrapolation BCs" % (a.nx, a.ny))
@@ -264,7 +265,9 @@ def main():
                 "frac_traffic": (traffic / (per_launch_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_cell": alg, "share_of_step": prof[top][0] / sum(v[0] for v in prof.values())}
         stage_ms = sum(prof[k][0] for k in prof if k != "cfl") / (a.steps * N_STAGES)
-        roof["stage_achieved"] = ALG_BYTES_STAGE * nc / (stage_ms * 1e-3) / 1e9
+        alg_stage = ALG_BYTES_STAGE if a.recon == "TENO" else 152.0      # first order on triangles = 152 B per cell-update
+        roof["stage_algorithmic_bytes_per_cell"] = alg_stage
+        roof["stage_achieved"] = alg_stage * nc / (stage_ms * 1e-3) / 1e9
         roof["stage_frac"] = roof["stage_achieved"] / peak
 
     # ---- end to end through the take_step seam with host buffers (pinned): H2D U, calc_dt + step, D2H U every step
@@ -294,11 +297,12 @@ def main():
 
     line = {"metric": "cell-updates/s per RK stage", "value": value, "unit": "cell-updates/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "n_cells": nc, "fp_mode": a.fp, "recon": a.recon, "l2": "inputs larger than L2 (TENO tables %.1f GB per stage)" % (stats[2] / 1e9),
+            "config": {"workload": workload, "n_cells": nc, "fp_mode": a.fp, "recon": a.recon, "l2": ("inputs larger than L2 (TENO tables %.1f GB per stage)" if a.recon == "TENO" else "inputs larger than L2 (%.1f GB of state, connectivity and face products per stage)") % (stats[2] / 1e9),
                        "device_bytes": stats[2], "preprocess_seconds": stats[1], "setup_seconds": setup_s, "mesh_seconds": mesh_s,
                        "preprocess": {"host_total_s": stats[1], "host_stencil_search_s": stats[8], "host_matrices_s": stats[9],
                                       "device_table_build_s": stats[10]},
-                       "note": "reference-faithful TENO: like the reference, the state turns non-finite inside step 1 (SURVEY 0.2); cost is data-independent"},
+                       "note": ("reference-faithful TENO: like the reference, the state turns non-finite inside step 1 (SURVEY 0.2); cost is "
+                                "data-independent") if a.recon == "TENO" else "first-order path (the numerics of examples/sod and examples/wedge)"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "kernels": kernels}
     print(json.dumps(line))
 
