@@ -9,6 +9,10 @@ Solver::run's loop: calc_dt + the three RK stages (each: TENO reconstruction ker
 For N>1 (torchrun, one rank per GPU) every rank owns one 1024x1024-quad block of a (1024*N)x1024 mesh (weak scaling); the
 per-stage halo exchange of ghost-cell states goes over NCCL.
 
+`--workload vortex --nx 2828 --ny 2828` is BASELINE configs[3] (isentropic vortex on a 16 M-cell jittered, id-shuffled
+triangulation; with torchrun the ONE mesh is split by recursive coordinate bisection: strong scaling); `--recon FO` the
+first-order numerics of examples/sod and examples/wedge; `--fp strict` the bit-faithful mode.
+
 `--impl reference` times the UNMODIFIED reference (oracle/_ref, Kokkos OpenMP, FP64) on the host cores on a bounded sample
 of the same workload (same numerics, smaller mesh) — or the oracle port if the reference binary is absent.
 """
