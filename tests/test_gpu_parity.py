@@ -428,3 +428,28 @@ def test_device_side_field_ranges_and_nan_count():
     U, P = s.get_state(prim=True)
     assert n_nan == int(np.isnan(U).sum() + np.isnan(P).sum()) and n_nan >= 2
     assert rng["RHOU_Y"] == (np.nanmin(U[:, 2]), np.nanmax(U[:, 2]))
+
+
+def test_fast_mode_drift_over_a_run(capsys):
+    """north_star: "<= 1e-12 per step, with drift reported over the run".  Vortex advection on a jittered unstructured mesh,
+    normalised TENO weights (the reference-faithful ones go non-finite within a step), 200 steps: FAST (FMA, compact
+    device-built tables, re-associated sums) against the bit-faithful STRICT mode, sampled every 25 steps."""
+    from mallard_b200 import synthetic as syn
+    mesh = syn.jittered_tri(96, 96, 10.0, 10.0, seed=5)
+    U0 = syn.isentropic_vortex(mesh.arrays["cell_coords"])
+    kw = dict(recon="TENO", riemann="HLLC", integrator="SSPRK3", order=3, bcs=syn.EXTRAP4, teno_fixed=True, keep_stage_rhs=False)
+    ss, sf = mb.Solver(mesh, fp_mode="strict", **kw), mb.Solver(mesh, fp_mode="fast", **kw)
+    ss.set_state(U0); sf.set_state(U0)
+    rows = []
+    for k in range(8):
+        ss.run(25, cfl=0.1); sf.run(25, cfl=0.1)
+        Us, Uf = ss.get_state(), sf.get_state()
+        assert np.isfinite(Us).all()
+        rows.append((25 * (k + 1), gu.field_err(Uf, Us), abs(sf.time()[0] - ss.time()[0]) / ss.time()[0]))
+    with capsys.disabled():
+        print("\nFAST vs STRICT drift (max field-relative difference of U; relative difference of t):")
+        for n, e, te in rows:
+            print("  step %4d   dU %.2e   dt %.2e" % (n, e, te))
+    assert rows[0][1] <= 25 * TOL                # <= 1e-12 per step
+    assert rows[-1][1] <= 200 * TOL              # no super-linear growth over the run
+    assert rows[-1][2] <= 200 * 1e-15
