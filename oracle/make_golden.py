@@ -75,6 +75,15 @@ CASES = {
                                 riemann="Rusanov", integrator="SSPRK3",
                                 recon=dict(type="TENO", basis_type="legendre", basis_order=2, max_stencil_size_factor=2.0),
                                 n_steps=1, every=1, keep_mesh=False, keep_teno=True),
+    # the lowest and the highest order the device kernels are instantiated for (K = 3, M = 6 and K = 15, M = 30)
+    "teno_legendre_6x5_p1": dict(mesh=dict(type="cartesian_tri", Nx=6, Ny=5, Lx=1.0, Ly=0.8), ic=SMOOTH_IC, bcs=SYM4, cfl=0.1,
+                                 riemann="Rusanov", integrator="FE",
+                                 recon=dict(type="TENO", basis_type="legendre", basis_order=1, max_stencil_size_factor=2.0),
+                                 n_steps=1, every=1, keep_mesh=False, keep_teno=True),
+    "teno_legendre_9x8_p4": dict(mesh=dict(type="cartesian_tri", Nx=9, Ny=8, Lx=1.0, Ly=0.9), ic=SMOOTH_IC, bcs=EXTRAP4, cfl=0.1,
+                                 riemann="HLLC", integrator="SSPRK3",
+                                 recon=dict(type="TENO", basis_type="legendre", basis_order=4, max_stencil_size_factor=2.0),
+                                 n_steps=1, every=1, keep_mesh=False, keep_teno=False),
     # the reference's DEFAULT basis (face_reconstruction.cpp:110): monomials, incl. the derivative quirk in the oscillation
     # indicator (basis.h:72-78)
     "teno_monomial_7x6_p3": dict(mesh=dict(type="cartesian_tri", Nx=7, Ny=6, Lx=1.0, Ly=1.0), ic=SMOOTH_IC, bcs=SYM4, cfl=0.1,
