@@ -152,7 +152,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="riemann_2d", choices=["riemann_2d", "vortex"],
+    ap.add_argument("--workload", default="riemann_2d", choices=["riemann_2d", "vortex", "sod", "wedge"],
                     help="riemann_2d = BASELINE configs[1] (the metric's configuration); vortex = configs[3] family: isentropic vortex on a "
                          "jittered, id-shuffled triangulation (--nx 2828 --ny 2828 = 16 M cells)")
     ap.add_argument("--nx", type=int, default=1024)
@@ -198,7 +198,31 @@ def main():
 
     torch.cuda.set_device(0)
     t_setup = time.perf_counter()
-    if a.workload == "vortex":
+    cfl, integ = 0.1, "SSPRK3"
+    if a.workload in ("sod", "wedge"):
+        # BASELINE configs[0] / configs[2] verbatim (examples/sod, examples/wedge): first order + HLLC + SSPRK3, cfl 1.  A few
+        # thousand cells: a step is launch-bound, mlb_run replays it as a CUDA graph.  Use --steps 2000 or more.
+        a.recon, a.no_cpu_baseline, a.no_e2e, cfl = "FO", True, True, 1.0
+        R = 101325.0 / (298.15 * 1.225)
+        cv = R / 0.4
+        if a.workload == "sod":
+            mesh = mb.Mesh.generate("cartesian", 1000, 1, 1.0, 1.0e-3)
+            x = mesh.arrays["cell_coords"][:, 0]
+            rho, p = np.where(x < 0.5, 1.0, 0.125), np.where(x < 0.5, 1.0, 0.1)
+            u = np.zeros_like(x)
+            bcs = SYM4
+            workload = "examples/sod: cartesian 1000x1, first order + HLLC + SSPRK3, cfl 1"
+        else:
+            mesh = mb.Mesh.generate("wedge", 150, 50, 4.0, 1.5)
+            n = mesh.n_cells
+            p, T, u = np.full(n, 101325.0), np.full(n, 300.0), np.full(n, 600.0)
+            rho = p / (R * T)
+            bcs = [dict(name="left", type="upt", u=[600.0, 0.0], p=101325.0, T=300.0), dict(name="right", type="p_out", p=101325.0),
+                   dict(name="top", type="symmetry"), dict(name="bottom", type="symmetry")]
+            workload = "examples/wedge: wedge 150x50 quads, upt / p_out / symmetry, first order + HLLC + SSPRK3, cfl 1"
+        e = p / (0.4 * rho)
+        U0, P0 = np.stack([rho, rho * u, 0.0 * rho, rho * (e + 0.5 * u * u)], 1), None
+    elif a.workload == "vortex":
         from mallard_b200 import synthetic as syn
         mb.set_host_threads(host_cores())
         mesh = syn.jittered_tri(a.nx, a.ny, 10.0, 10.0, seed=12345)
@@ -212,20 +236,20 @@ def main():
         bcs = SYM4
     nc = mesh.n_cells
     mesh_s = time.perf_counter() - t_setup
-    s = mb.Solver(mesh, a.recon, "HLLC", "SSPRK3", order=3, bcs=bcs, fp_mode=a.fp, keep_stage_rhs=False)
+    s = mb.Solver(mesh, a.recon, "HLLC", integ, order=3, bcs=bcs, fp_mode=a.fp, keep_stage_rhs=False)
     stats = s.get("stats")
     setup_s = time.perf_counter() - t_setup
     s.set_state(U0, P0)
 
     # ---- device-resident timing (the state is reset before every timed region: reference-faithful TENO spreads NaN from
     #      the initial discontinuities by about one stencil width per stage, exactly as the reference does)
-    s.run(a.warmup, cfl=0.1)
+    s.run(a.warmup, cfl=cfl)
     launches0 = s.launch_count
     clocks = ClockSampler(0)
     clocks.start()
     s.synchronize()
     s.event_record(0)
-    s.run(a.steps, cfl=0.1)
+    s.run(a.steps, cfl=cfl)
     s.event_record(1)
     ms = s.event_elapsed_ms(0, 1)
     clk = clocks.stop()
@@ -234,9 +258,9 @@ def main():
 
     # ---- per-kernel device time over the same region (CUDA events on the library's stream) for the roofline
     s.set_state(U0, P0)
-    s.run(a.warmup, cfl=0.1)
+    s.run(a.warmup, cfl=cfl)
     s.profile(True)
-    s.run(a.steps, cfl=0.1)
+    s.run(a.steps, cfl=cfl)
     prof = s.profile_read()
     s.profile(False)
     peaks = {}
@@ -282,11 +306,11 @@ def main():
         Uh[:] = U0
         k_e2e = max(3, min(a.steps, 10))
         for _ in range(3):
-            s.take_step_host(Uh, cfl=0.1)
+            s.take_step_host(Uh, cfl=cfl)
         Uh[:] = U0
         t0 = time.perf_counter()
         for _ in range(k_e2e):
-            s.take_step_host(Uh, cfl=0.1)
+            s.take_step_host(Uh, cfl=cfl)
         sec = time.perf_counter() - t0
         e2e = {"value": nc * N_STAGES * k_e2e / sec, "unit": "cell-updates/s", "h2d_bytes_per_step": nc * 32, "d2h_bytes_per_step": nc * 32 + 64,
                "steps": k_e2e, "ms_per_step": 1e3 * sec / k_e2e, "api": "mlb_take_step_host (C ABI; host buffers in reference layout)"}
@@ -301,7 +325,9 @@ def main():
 
     line = {"metric": "cell-updates/s per RK stage", "value": value, "unit": "cell-updates/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "n_cells": nc, "fp_mode": a.fp, "recon": a.recon, "l2": ("inputs larger than L2 (TENO tables %.1f GB per stage)" if a.recon == "TENO" else "inputs larger than L2 (%.1f GB of state, connectivity and face products per stage)") % (stats[2] / 1e9),
+            "config": {"workload": workload, "n_cells": nc, "fp_mode": a.fp, "recon": a.recon, "l2": (("inputs larger than L2 (TENO tables %.1f GB per stage)" if a.recon == "TENO" else "inputs larger than L2 (%.1f GB of state, connectivity and face products per stage)") % (stats[2] / 1e9))
+                             if stats[2] > 252e6 else "working set %.1f MB fits in L2: a launch-bound configuration, steps replayed as a CUDA graph" % (stats[2] / 1e6),
+                       "graph_replayed_steps": int(s.get("stats")[11]),
                        "device_bytes": stats[2], "preprocess_seconds": stats[1], "setup_seconds": setup_s, "mesh_seconds": mesh_s,
                        "preprocess": {"host_total_s": stats[1], "host_stencil_search_s": stats[8], "host_matrices_s": stats[9],
                                       "device_table_build_s": stats[10]},

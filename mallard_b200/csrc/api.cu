@@ -106,6 +106,7 @@ struct mlb_ctx {
     // measurement
     cudaEvent_t ev[16] = {};
     uint64_t launches = 0;
+    uint64_t graph_replays = 0;        // steps of mlb_run executed as CUDA graph replays
     bool profiling = false;
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
     std::map<std::string, ProfileEntry> profile;
@@ -670,10 +671,37 @@ int mlb_run(mlb_ctx * c, uint32_t n_steps, double cfl, double * t_out, double * 
     API_BEGIN(c)
     CUDA_OK(cudaSetDevice(c->device));
     if (c->n_ranks > 1) throw std::runtime_error("mlb_run: partitioned contexts are stepped with the split-phase API");
-    for (uint32_t i = 0; i < n_steps; i++) {
+    auto one_step = [&] {
         if (cfl > 0.0) do_calc_dt(*c, cfl);
         do_step(*c);
+    };
+    // Small meshes (examples/sod: 1000 cells, examples/wedge: 7500) are launch-bound: 7-10 kernels of a few microseconds per
+    // step.  One step is captured into a CUDA graph and replayed; dt, t and the step counter live on the device, and the
+    // stage buffers of SSPRK3 / RK4 return to the same rotation after a step, so every replay is the same graph.
+    static const bool graphs = [] { const char * e = getenv("MLB_RUN_GRAPH"); return !(e && e[0] == '0'); }();
+    uint32_t done = 0;
+    if (graphs && !c->profiling && n_steps >= 8 && c->num.integrator != MLB_INTEGRATOR_FE) {
+        one_step();                                   // eager: function attributes, occupancy queries, error reporting
+        done = 1;
+        const uint64_t l0 = c->launches;
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ge = nullptr;
+        CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        bool ok = true;
+        try { one_step(); } catch (...) { ok = false; }
+        const cudaError_t ec = cudaStreamEndCapture(c->stream, &g);
+        const uint64_t per_step = c->launches - l0;
+        c->launches = l0;                             // nothing ran during the capture
+        if (ok && ec == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) {
+            for (; done < n_steps; done++) { CUDA_OK(cudaGraphLaunch(ge, c->stream)); c->launches += per_step; }
+            c->graph_replays += n_steps - 1;
+        } else {
+            cudaGetLastError();                       // capture not possible here: fall through to plain launches
+        }
+        if (ge) cudaGraphExecDestroy(ge);
+        if (g) cudaGraphDestroy(g);
     }
+    for (; done < n_steps; done++) one_step();
     double sc[SC_COUNT];
     read_scalars(*c, sc);
     if (t_out) *t_out = sc[SC_T];
@@ -836,7 +864,7 @@ int mlb_get_array(mlb_ctx * c, const char * name, void * out, uint64_t * nbytes)
         if (out) CUDA_OK(cudaMemcpy(out, src, *nbytes, cudaMemcpyDeviceToHost));
     } else if (n == "stats") {
         double s[12] = {(double)c->launches, P.seconds, (double)c->device_bytes, (double)P.N, (double)P.N_owned, (double)P.NF,
-                        (double)P.N_recon, (double)c->n_stages, P.seconds_stencils, P.seconds_matrices, c->table_build_ms * 1e-3, 0.0};
+                        (double)P.N_recon, (double)c->n_stages, P.seconds_stencils, P.seconds_matrices, c->table_build_ms * 1e-3, (double)c->graph_replays};
         host(s, sizeof(s));
     } else if (n.rfind("teno:", 0) == 0) {
         if (!c->teno) throw std::runtime_error("context has no TENO tables");

@@ -453,3 +453,21 @@ def test_fast_mode_drift_over_a_run(capsys):
     assert rows[0][1] <= 25 * TOL                # <= 1e-12 per step
     assert rows[-1][1] <= 200 * TOL              # no super-linear growth over the run
     assert rows[-1][2] <= 200 * 1e-15
+
+
+@pytest.mark.parametrize("recon,integ", [("FO", "SSPRK3"), ("TENO", "RK4")])
+def test_graph_replayed_run_equals_step_by_step(recon, integ):
+    """mlb_run captures one step (CFL kernel + stages) into a CUDA graph and replays it (n_steps >= 8); the result must be
+    the one of calc_dt + take_step issued step by step, bit for bit."""
+    mesh = mb.Mesh.generate("cartesian_tri", 24, 18, 1.0, 0.75)
+    U0 = _random_smooth_state(mesh.arrays["cell_coords"], np.random.default_rng(9))
+    kw = dict(recon=recon, riemann="HLLC", integrator=integ, order=2, bcs=SYM4, fp_mode="fast", teno_fixed=True, keep_stage_rhs=False)
+    a, b = mb.Solver(mesh, **kw), mb.Solver(mesh, **kw)
+    a.set_state(U0); b.set_state(U0)
+    t, dt = a.run(20, cfl=0.3)
+    for _ in range(20):
+        b.calc_dt(0.3)
+        b.take_step()
+    assert int(a.get("stats")[11]) == 19 and int(b.get("stats")[11]) == 0
+    assert np.array_equal(a.get_state(), b.get_state())
+    assert a.time() == b.time() and a.time()[1] == 20
