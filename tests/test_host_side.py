@@ -249,3 +249,19 @@ def test_partitioned_plan_numbers_interior_cells_first(n_ranks):
         perm = plan.get("perm_cells")
         assert (part[perm[:plan.N_owned]] == r).all() and (part[perm[plan.N_owned:]] != r).all()
         assert int(whole.get("n_interior")[0]) == whole.N_owned
+
+
+def test_bench_reference_arm_line_and_no_gpu_failure():
+    """bench.py's contract on a box without a GPU: the reference arm (oracle/_ref, or the oracle port) prints one JSON line
+    with the metric's keys; the product arm refuses to run (no CPU fallback)."""
+    import json
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT) if ROOT not in sys.path else None
+    import bench
+    value, info = bench.reference_cpu(2, 1, nx=20, ny=16)
+    assert value > 0 and info["kind"] in ("reference", "port") and info["cores"] >= 1 and "640 cells" in info["sample"]
+    import torch
+    if not torch.cuda.is_available():
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True)
+        assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
