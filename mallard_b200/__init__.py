@@ -64,6 +64,8 @@ class Mesh:
         nc, nf, nn = v.n_cells, v.n_faces, v.n_nodes
 
         def arr(p, n, dt):
+            if not p or n == 0:                      # an empty zone (the interior zone of a one-cell mesh) has no storage
+                return np.empty(0, dtype=dt)
             return np.ctypeslib.as_array(C.cast(p, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,)).copy()
         onc = arr(v.offsets_nodes_of_cell, nc + 1, np.uint32)
         ofc = arr(v.offsets_faces_of_cell, nc + 1, np.uint32)

@@ -471,3 +471,20 @@ def test_graph_replayed_run_equals_step_by_step(recon, integ):
     assert int(a.get("stats")[11]) == 19 and int(b.get("stats")[11]) == 0
     assert np.array_equal(a.get_state(), b.get_state())
     assert a.time() == b.time() and a.time()[1] == 20
+
+
+@pytest.mark.parametrize("mtype,nx,ny", [("cartesian", 1, 1), ("cartesian_tri", 1, 1), ("cartesian", 3, 1)])
+def test_tiny_meshes_vs_oracle(oracle_mod, mtype, nx, ny):
+    """Edge case: one or two cells, every (or almost every) face on a boundary, empty or one-face interior zone."""
+    bcs = [dict(name="left", type="symmetry"), dict(name="right", type="extrapolation"), dict(name="top", type="wall_adiabatic"),
+           dict(name="bottom", type="symmetry")]
+    mesh, om = mb.Mesh.generate(mtype, nx, ny, 1.0, 0.5), oracle_mod.Mesh.generate(mtype, nx, ny, 1.0, 0.5)
+    U0 = _random_smooth_state(mesh.arrays["cell_coords"], np.random.default_rng(3))
+    sg = mb.Solver(mesh, "FO", "HLLC", "SSPRK3", bcs=bcs, fp_mode="strict")
+    so = oracle_mod.Solver(om, "FO", "HLLC", "SSPRK3", bcs=bcs)
+    sg.set_state(U0); so.set_state(U0)
+    assert np.array_equal(sg.calc_rhs(), so.calc_rhs())
+    dto, dtg = so.calc_dt(0.5), sg.calc_dt(0.5)
+    assert dtg == dto
+    so.take_step(dto); sg.take_step()
+    assert np.array_equal(sg.get_state(), so.get("U"))

@@ -265,3 +265,17 @@ def test_bench_reference_arm_line_and_no_gpu_failure():
     if not torch.cuda.is_available():
         p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True)
         assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
+
+
+def test_degenerate_meshes_are_handled_on_the_host():
+    """Edge cases: a one-cell mesh (empty interior zone, every face on a boundary), and TENO on meshes that cannot fill a
+    stencil of M cells or that contain quadrilaterals (the reference throws for both)."""
+    m = mb.Mesh.generate("cartesian", 1, 1, 1.0, 1.0)
+    assert m.n_cells == 1 and dict((n, len(f)) for n, f in m.zones)["interior"] == 0
+    p = mb.Plan(m, "FO", bcs=SYM4)
+    assert (p.N, p.NF) == (1, 4)
+    with pytest.raises(mb.MallardError, match="only been implemented for triangular cells"):    # face_reconstruction.cpp:485-487
+        mb.Plan(m, "TENO", order=3, bcs=SYM4)
+    for n in (1, 2, 3):
+        with pytest.raises(mb.MallardError, match="too small to fill a stencil"):
+            mb.Plan(mb.Mesh.generate("cartesian_tri", n, n, 1.0, 1.0), "TENO", order=3, bcs=SYM4, fp_mode="fast")
