@@ -18,8 +18,12 @@
 //     and every lane issues half as many table loads for the same number of FMAs.
 //   * Neighbour states: ubuf[m][cell][4], single-buffered.  The right-hand sides are in registers before the next
 //     stencil's states are requested (a __syncwarp() orders the warp's reads before its own cp.async writes).  Writes
-//     (lane = 16-byte half p of neighbour 4i + 2h + j) and reads ((column, variable pair) as one 128-bit load) are both
-//     128 contiguous bytes per quarter-warp.
+//     (lane = 16-byte half p of neighbour 4i + 2h + j) are 128 contiguous bytes per quarter-warp; a lane reads its own
+//     variable X = 2p + h and the partner's Y = X ^ 1 of each of its columns, so the row loop needs no lane-dependent
+//     selects: it accumulates (x, y), ships y to the partner lane and keeps x.
+//   * The stencil loop is rolled (four unrolled copies are ~100 kB of SASS and thrash the instruction cache); the rows
+//     of a chunk form one basic block so that loads of one row overlap the FMA chains of another; the ids of a stencil
+//     are fetched with volatile loads one stencil before they are used.
 #pragma once
 
 namespace stream {
