@@ -279,3 +279,21 @@ def test_degenerate_meshes_are_handled_on_the_host():
     for n in (1, 2, 3):
         with pytest.raises(mb.MallardError, match="too small to fill a stencil"):
             mb.Plan(mb.Mesh.generate("cartesian_tri", n, n, 1.0, 1.0), "TENO", order=3, bcs=SYM4, fp_mode="fast")
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """The boundary is a C ABI: include/mallard_b200.h must compile as C99 (no C++ or torch types) and a C program must link
+    against libmallard_b200.so and call it."""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "mallard_b200.h"\n'
+                   'int main(void) {\n  mlb_host_mesh *m = 0;\n  mlb_mesh v;\n'
+                   '  if (mlb_host_mesh_generate(&m, 1, 3, 2, 1.0, 1.0)) return 1;\n'
+                   '  if (mlb_host_mesh_view(m, &v)) return 2;\n'
+                   '  printf("%s %u\\n", mlb_version(), v.n_cells);\n  mlb_host_mesh_free(m);\n  return 0;\n}\n')
+    exe = tmp_path / "t"
+    libdir = os.path.join(ROOT, "mallard_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-L", libdir, "-lmallard_b200", "-Wl,-rpath," + libdir, "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    assert out.startswith("mallard_b200") and out.split()[-1] == "12"      # cartesian_tri 3 x 2 = 12 triangles
