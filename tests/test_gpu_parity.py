@@ -488,3 +488,23 @@ def test_tiny_meshes_vs_oracle(oracle_mod, mtype, nx, ny):
     assert dtg == dto
     so.take_step(dto); sg.take_step()
     assert np.array_equal(sg.get_state(), so.get("U"))
+
+
+def test_mesh_read_from_a_gmsh_file_runs_like_the_same_mesh_from_arrays(tmp_path):
+    """the vortex on a jittered triangulation handed over as arrays, and on the same mesh written to a Gmsh
+    file and read back (faces renumbered, hence a different - equally valid - accumulation order in the residual)."""
+    from mallard_b200 import meshio, synthetic as syn
+    mesh = syn.jittered_tri(40, 32, 10.0, 8.0, seed=21)
+    path = tmp_path / "vortex.msh"
+    meshio.write_gmsh(mesh, str(path))
+    back = meshio.read_gmsh(str(path))
+    U0 = syn.isentropic_vortex(mesh.arrays["cell_coords"], centre=(5.0, 4.0))
+    res = []
+    for m in (mesh, back):
+        bcs = [dict(name=n, type="extrapolation") for n, _ in m.zones if n != "interior"]
+        s = mb.Solver(m, "TENO", "HLLC", "SSPRK3", order=3, bcs=bcs, fp_mode="strict", teno_fixed=True, keep_stage_rhs=False)
+        s.set_state(U0)
+        s.run(3, cfl=0.3)
+        res.append(s.get_state())
+    assert np.isfinite(res[0]).all()
+    assert gu.field_err(res[1], res[0]) <= 3 * TOL

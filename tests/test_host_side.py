@@ -297,3 +297,45 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
                            "-L", libdir, "-lmallard_b200", "-Wl,-rpath," + libdir, "-o", str(exe)])
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
     assert out.startswith("mallard_b200") and out.split()[-1] == "12"      # cartesian_tri 3 x 2 = 12 triangles
+
+
+@pytest.mark.parametrize("kind", ["tri", "quad"])
+def test_gmsh_file_round_trip(tmp_path, kind):
+    """a mesh written to Gmsh MSH 2.2 and read back holds the same nodes, cells, boundary zones and (bit for
+    bit, being computed by the same host code from the same node order) cell volumes; faces are renumbered."""
+    from mallard_b200 import meshio, synthetic as syn
+    mesh = syn.jittered_tri(9, 7, 3.0, 2.0, seed=4) if kind == "tri" else mb.Mesh.generate("wedge", 12, 6, 4.0, 1.5)
+    path = tmp_path / "mesh.msh"
+    meshio.write_gmsh(mesh, str(path))
+    back = meshio.read_gmsh(str(path))
+    a, b = mesh.arrays, back.arrays
+    assert back.n_cells == mesh.n_cells and back.n_nodes == mesh.n_nodes
+    assert np.array_equal(a["node_coords"], b["node_coords"])
+    assert np.array_equal(a["nodes_of_cell"], b["nodes_of_cell"]) and np.array_equal(a["offsets_nodes_of_cell"], b["offsets_nodes_of_cell"])
+    assert np.array_equal(a["cell_volume"], b["cell_volume"]) and np.array_equal(a["cell_coords"], b["cell_coords"])
+    real = gu.real_faces(a["cells_of_face"], a["nodes_of_face"])
+    assert back.n_faces == int(real.sum())
+    edge = lambda arr, f: frozenset(map(int, arr["nodes_of_face"].reshape(-1, 2)[f]))
+    za, zb = dict(mesh.zones), dict(back.zones)
+    assert set(za) == set(zb)
+    for n in za:
+        assert {edge(a, f) for f in za[n]} == {edge(b, f) for f in zb[n]}, n
+    # every face: side 0 is the lower-numbered cell, normals point out of it, areas match the originals
+    cof = b["cells_of_face"].reshape(-1, 2)
+    assert ((cof[:, 1] < 0) | (cof[:, 0] < cof[:, 1])).all()
+    area_a = {edge(a, f): a["face_area"][f] for f in np.nonzero(real)[0]}
+    assert all(area_a[edge(b, f)] == b["face_area"][f] for f in range(back.n_faces))
+    plan = mb.Plan(back, "TENO" if kind == "tri" else "FO", order=2, bcs=[dict(name=n, type="extrapolation") for n in zb if n != "interior"],
+                   fp_mode="fast")
+    assert plan.N == back.n_cells
+
+
+def test_gmsh_reader_rejects_what_it_cannot_represent(tmp_path):
+    from mallard_b200 import meshio
+    p = tmp_path / "bad.msh"
+    p.write_text("$MeshFormat\n4.1 0 8\n$EndMeshFormat\n")
+    with pytest.raises(ValueError, match="MSH 2.x ASCII"):
+        meshio.read_gmsh(str(p))
+    p.write_text("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n3\n1 0 0 0\n2 1 0 0\n3 0 1 0\n$EndNodes\n$Elements\n1\n1 1 2 1 1 1 2\n$EndElements\n")
+    with pytest.raises(ValueError, match="no triangles or quadrilaterals"):
+        meshio.read_gmsh(str(p))
