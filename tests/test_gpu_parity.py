@@ -508,3 +508,20 @@ def test_mesh_read_from_a_gmsh_file_runs_like_the_same_mesh_from_arrays(tmp_path
         res.append(s.get_state())
     assert np.isfinite(res[0]).all()
     assert gu.field_err(res[1], res[0]) <= 3 * TOL
+
+
+def test_python_write_vtu_holds_the_exported_fields(tmp_path):
+    """Solver.write_vtu (mlb_write_vtu) from Python: the appended arrays are the state get_state returns, in file order."""
+    from test_gpu_dropin import read_vtu
+    mesh = mb.Mesh.generate("wedge", 20, 8, 4.0, 1.5)
+    s = mb.Solver(mesh, "FO", "HLLC", "SSPRK3", bcs=SYM4, fp_mode="strict")
+    s.set_state(_random_smooth_state(mesh.arrays["cell_coords"], np.random.default_rng(8)))
+    s.run(4, cfl=0.5)
+    name = s.write_vtu(str(tmp_path / "w"), 4, ["RHO", "RHOE", "P", "H", "CFL"])
+    v = read_vtu(name)
+    U, P, cfl = s.get_state(prim=True, cfl_local=True)
+    assert np.array_equal(v["RHO"], U[:, 0]) and np.array_equal(v["RHOE"], U[:, 3])
+    assert np.array_equal(v["P"], P[:, 2]) and np.array_equal(v["H"], P[:, 4]) and np.array_equal(v["CFL"], cfl)
+    assert np.array_equal(v["connectivity"], mesh.arrays["nodes_of_cell"]) and (v["types"] == 7).all()
+    with pytest.raises(mb.MallardError, match="Unknown variable"):
+        s.write_vtu(str(tmp_path / "w"), 5, ["RHO", "VORTICITY"])
