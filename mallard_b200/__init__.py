@@ -420,11 +420,12 @@ class Solver:
     # -- multi-GPU split-phase surface
     def halo_info(self):
         n = C.c_int32()
-        peers = np.zeros(64, dtype=np.int32)
-        sc = np.zeros(64, dtype=np.uint64)
-        rc = np.zeros(64, dtype=np.uint64)
-        self._ok(lib().mlb_halo_info(self._h, C.byref(n), _ptr(peers), _ptr(sc), _ptr(rc)))
+        self._ok(lib().mlb_halo_info(self._h, C.byref(n), None, None, None))      # count first: the arrays are sized from it
         k = n.value
+        peers = np.zeros(max(k, 1), dtype=np.int32)
+        sc = np.zeros(max(k, 1), dtype=np.uint64)
+        rc = np.zeros(max(k, 1), dtype=np.uint64)
+        self._ok(lib().mlb_halo_info(self._h, C.byref(n), _ptr(peers), _ptr(sc), _ptr(rc)))
         return peers[:k].copy(), sc[:k].copy(), rc[:k].copy()
 
     def halo_recv_ids(self, peer_index, count):

@@ -245,7 +245,7 @@ void wait_halo(mlb_ctx & c) {
 
 // Tiles made of interior cells only (stencils without ghosts): their reconstruction overlaps the halo exchange.
 uint32_t interior_tiles(const mlb_ctx & c) {
-    return (c.streaming && FAST_CT == 8 && c.n_ranks > 1) ? c.prep.N_interior / FAST_CT : 0u;
+    return (c.streaming && c.n_ranks > 1) ? c.prep.N_interior / FAST_CT : 0u;
 }
 
 // phase 0: everything; 1: interior tiles only (before the halo wait); 2: the remaining tiles
@@ -318,6 +318,15 @@ void do_calc_dt(mlb_ctx & c, double cfl) {
 void read_scalars(mlb_ctx & c, double * out) {
     CUDA_OK(cudaMemcpyAsync(out, c.scal, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     CUDA_OK(cudaStreamSynchronize(c.stream));
+}
+
+// Solver::calc_dt's `if (dt < 0) throw` (solver.cpp:587-589).  The stage kernels treat a negative device-resident dt as
+// "no step" (the solution, t and the step counter stay as they are), so reporting after the fact loses nothing.
+double require_dt(mlb_ctx & c) {
+    double sc[SC_COUNT];
+    read_scalars(c, sc);
+    if (sc[SC_DT] < 0.0) throw std::runtime_error("dt negative: " + std::to_string(sc[SC_DT]) + ".");
+    return sc[SC_DT];
 }
 
 void import_state(mlb_ctx & c, const double * U_host, double * soa, int nv) {
@@ -644,9 +653,7 @@ int mlb_set_dt(mlb_ctx * c, double dt) {
 int mlb_take_step(mlb_ctx * c) {
     API_BEGIN(c)
     CUDA_OK(cudaSetDevice(c->device));
-    double sc[SC_COUNT];
-    read_scalars(*c, sc);
-    if (sc[SC_DT] < 0.0) throw std::runtime_error("dt negative: " + std::to_string(sc[SC_DT]) + ".");
+    require_dt(*c);
     do_step(*c);
     CUDA_OK(cudaStreamSynchronize(c->stream));
     API_END(c)
@@ -656,6 +663,7 @@ int mlb_take_step_host(mlb_ctx * c, double cfl, double * U_inout, double * dt_ou
     API_BEGIN(c)
     if (!U_inout) throw std::runtime_error("mlb_take_step_host: NULL buffer");
     CUDA_OK(cudaSetDevice(c->device));
+    if (!(cfl > 0.0)) require_dt(*c);      // fixed dt: refuse before the resident state is touched
     import_state(*c, U_inout, c->U[c->cur], 4);
     if (cfl > 0.0) {
         c->kt->primitives_soa(c->gas, c->prep.N, c->prep.Npad, c->U[c->cur], c->prim, c->stream); c->launches++;
@@ -663,14 +671,18 @@ int mlb_take_step_host(mlb_ctx * c, double cfl, double * U_inout, double * dt_ou
     }
     do_step(*c);
     export_state(*c, c->U[c->cur], 4, U_inout);
-    if (dt_out) { double sc[SC_COUNT]; read_scalars(*c, sc); *dt_out = sc[SC_DT]; }
+    double sc[SC_COUNT];
+    read_scalars(*c, sc);                  // 64 bytes behind the state's D2H on the same stream
+    if (dt_out) *dt_out = sc[SC_DT];
+    if (sc[SC_DT] < 0.0) throw std::runtime_error("dt negative: " + std::to_string(sc[SC_DT]) + ".");   // the step was a no-op
     API_END(c)
 }
 
 int mlb_run(mlb_ctx * c, uint32_t n_steps, double cfl, double * t_out, double * dt_last_out) {
     API_BEGIN(c)
     CUDA_OK(cudaSetDevice(c->device));
-    if (c->n_ranks > 1) throw std::runtime_error("mlb_run: partitioned contexts are stepped with the split-phase API");
+    if (c->n_ranks > 1) throw std::runtime_error("mlb_run: partitioned contexts are stepped with mlb_run_distributed or the split-phase API");
+    if (!(cfl > 0.0) && n_steps) require_dt(*c);
     auto one_step = [&] {
         if (cfl > 0.0) do_calc_dt(*c, cfl);
         do_step(*c);
@@ -1110,7 +1122,7 @@ int mlb_finish_step(mlb_ctx * c) {
     API_BEGIN(c)
     CUDA_OK(cudaSetDevice(c->device));
     if (c->comm_stream) CUDA_OK(cudaStreamSynchronize(c->comm_stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
+    require_dt(*c);                        // synchronises the compute stream
     API_END(c)
 }
 int mlb_owned_cells(mlb_ctx * c, uint32_t * n_owned, uint32_t * cells_out) {

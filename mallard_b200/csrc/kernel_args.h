@@ -140,6 +140,14 @@ const KernelTable * kernels_fast();
 bool teno_tables_device_supported(int order, int basis, int nq);
 void launch_teno_tables(const TableBuildArgs & a, cudaStream_t st);
 
+// Launch configuration is a property of (kernel, DEVICE): the opt-in to more than 48 kB of dynamic shared memory is per
+// device, and so are the SM count and the occupancy a persistent grid is sized from.  Cached per (kernel, device ordinal),
+// thread-safe, every CUDA return code checked (throws std::runtime_error).  utils.cu.
+//   persistent_ctas: opts `kernel` into `smem` bytes on the CURRENT device and returns SMs x resident CTAs per SM
+//   ensure_dynamic_smem: the opt-in alone (kernels launched with a problem-sized grid)
+int persistent_ctas(const void * kernel, int threads, size_t smem);
+void ensure_dynamic_smem(const void * kernel, size_t smem);
+
 // layout helpers (mode independent, utils.cu)
 void launch_import_state(const double * aos, const uint32_t * perm, uint32_t n, uint32_t npad, int nv, double * soa, cudaStream_t);
 void launch_export_state(const double * soa, const uint32_t * perm, uint32_t n, uint32_t npad, int nv, double * aos, cudaStream_t);

@@ -147,6 +147,99 @@ __device__ __forceinline__ void riemann_flux(double * F, double nx, double ny, c
     }
 }
 
+#ifdef MLB_STREAM_KERNELS
+// ---------------------------------------------------------------------------------------------------------------
+// FAST mode: the same wave-speed estimates and fluxes (numerics/riemann_solver.h:206-519) with the algebra arranged for the
+// FP64 pipe, which is what bounds the face kernel (a double-precision division or square root is a ~10-instruction
+// dependent chain): one reciprocal per state instead of four divisions, a^2 = gamma p (1/rho), a q = sqrt(gamma (1/rho)
+// (p + c (p* - p))) instead of sqrt(..) * sqrt(1 + c (p*/p - 1)), rho E taken from the conserved state instead of being
+// rebuilt from h, and only the side of the fan the face lies in is evaluated.  Differences to riemann_flux<RS>() are a
+// few ulp (inside the 1e-12 per-step budget; tests/test_gpu_parity.py::test_riemann_*).  The rarely taken TRRS / TSRS
+// estimators stay out of line.
+// ---------------------------------------------------------------------------------------------------------------
+struct FaceCons { double rho, u, v, p, E, ir; };   // E = rho * total energy per mass, ir = 1 / rho
+
+__device__ __forceinline__ FaceCons face_cons(const GasParams & g, const double * U) {
+    FaceCons s;
+    s.rho = U[0]; s.ir = 1.0 / U[0];
+    s.u = U[1] * s.ir; s.v = U[2] * s.ir;
+    const double e = U[3] * s.ir - 0.5 * (s.u * s.u + s.v * s.v);
+    s.p = fmax(g.p_min, fmin(g.p_max, (g.gamma - 1.0) * s.rho * e));   // physics.h:842-845
+    s.E = U[3];
+    return s;
+}
+__device__ __forceinline__ FaceCons face_cons(const FaceState & f) {   // ghost states arrive as (rho, u, v, p, h)
+    FaceCons s;
+    s.rho = f.rho; s.ir = 1.0 / f.rho; s.u = f.u; s.v = f.v; s.p = f.p;
+    s.E = (f.h + 0.5 * (f.u * f.u + f.v * f.v)) * f.rho - f.p;
+    return s;
+}
+__device__ __noinline__ double star_pressure_rare(double rl, double unl, double pl, double rr, double unr, double pr, double gam, double ps) {
+    const Wn l = {rl, unl, pl, gam}, r = {rr, unr, pr, gam};
+    if (ps < fmin(pl, pr)) star_trrs(l, r, ps); else star_tsrs(l, r, ps);
+    return ps;
+}
+
+template <int RS>
+__device__ __forceinline__ void riemann_flux_lean(double * F, double nx, double ny, const FaceCons & L, const FaceCons & R, double gam) {
+    const double uln = L.u * nx + L.v * ny, urn = R.u * nx + R.v * ny;
+    const double al = sqrt(gam * L.p * L.ir), ar = sqrt(gam * R.p * R.ir);
+    const double ml = L.rho * uln, mr = R.rho * urn;
+    if (RS == MLB_RIEMANN_RUSANOV) {   // :332-375
+        const double smax = fmax(fabs(uln) + al, fabs(urn) + ar);
+        F[0] = 0.5 * (ml + mr + smax * (L.rho - R.rho));
+        F[1] = 0.5 * ((ml * L.u + L.p * nx) + (mr * R.u + R.p * nx) + smax * (L.rho * L.u - R.rho * R.u));
+        F[2] = 0.5 * ((ml * L.v + L.p * ny) + (mr * R.v + R.p * ny) + smax * (L.rho * L.v - R.rho * R.v));
+        F[3] = 0.5 * ((L.E + L.p) * uln + (R.E + R.p) * urn + smax * (L.E - R.E));
+        return;
+    }
+    // ANRS :309-329 with the PVRS guess :206-240 inline
+    const double pmax = fmax(L.p, R.p), pmin = fmin(L.p, R.p);
+    double ps = 0.5 * (L.p + R.p) + 0.5 * (uln - urn) * (0.5 * (L.rho + R.rho)) * (0.5 * (al + ar));
+    const bool q_small = pmin > 0.0 ? pmax < 2.0 * pmin : pmax / pmin < 2.0;
+    if (!(q_small && (pmin <= ps) && (ps <= pmax))) ps = star_pressure_rare(L.rho, uln, L.p, R.rho, urn, R.p, gam, ps);
+    const double c = (gam + 1.0) / (2.0 * gam);
+    const double Sl = uln - ((ps <= L.p) ? al : sqrt(gam * L.ir * (L.p + c * (ps - L.p))));
+    const double Sr = urn + ((ps <= R.p) ? ar : sqrt(gam * R.ir * (R.p + c * (ps - R.p))));
+    if (RS == MLB_RIEMANN_HLL) {       // :378-439
+        const double Fl[4] = {ml, ml * L.u + L.p * nx, ml * L.v + L.p * ny, (L.E + L.p) * uln};
+        const double Fr[4] = {mr, mr * R.u + R.p * nx, mr * R.v + R.p * ny, (R.E + R.p) * urn};
+        if (0.0 <= Sl) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) F[i] = Fl[i];
+        } else if (Sr <= 0.0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) F[i] = Fr[i];
+        } else {
+            const double Ul[4] = {L.rho, L.rho * L.u, L.rho * L.v, L.E}, Ur[4] = {R.rho, R.rho * R.u, R.rho * R.v, R.E};
+            const double inv = 1.0 / (Sr - Sl);
+#pragma unroll
+            for (int i = 0; i < 4; i++) F[i] = (Sr * Fl[i] - Sl * Fr[i] + Sl * Sr * (Ur[i] - Ul[i])) * inv;
+        }
+        return;
+    }
+    // HLLC "variant 2" :442-519: F = F_K, or F*_K = (S* (S_K U_K - F_K) + S_K P_LR D) / (S_K - S*), K the side of the contact
+    const double dl = L.rho * (Sl - uln), dr = R.rho * (Sr - urn);
+    const double Ss = (R.p - L.p + dl * uln - dr * urn) / (dl - dr);
+    const bool pure = (0.0 <= Sl) || (Sr <= 0.0);
+    const bool left = (0.0 <= Sl) || (!(Sr <= 0.0) && (Ss >= 0.0));
+    const double rK = left ? L.rho : R.rho, uK = left ? L.u : R.u, vK = left ? L.v : R.v, pK = left ? L.p : R.p, EK = left ? L.E : R.E;
+    const double unK = left ? uln : urn, mK = left ? ml : mr, SK = left ? Sl : Sr;
+    const double FK[4] = {mK, mK * uK + pK * nx, mK * vK + pK * ny, (EK + pK) * unK};
+    if (pure) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) F[i] = FK[i];
+    } else {
+        const double Plr = 0.5 * (L.p + R.p + dl * (Ss - uln) + dr * (Ss - urn));
+        const double inv = 1.0 / (SK - Ss);
+        const double UK[4] = {rK, rK * uK, rK * vK, EK}, D[4] = {0.0, nx, ny, Ss};
+        const double sp = SK * Plr;
+#pragma unroll
+        for (int i = 0; i < 4; i++) F[i] = (Ss * (SK * UK[i] - FK[i]) + sp * D[i]) * inv;
+    }
+}
+#endif  // MLB_STREAM_KERNELS
+
 // Ghost state of a boundary face from the interior face state (boundary/*.cpp calc_lr_states_impl)
 __device__ __forceinline__ void ghost_state(const BcParams & bc, const GasParams & g, double nx, double ny, const double * Ul,
                                             const double * Pl, FaceState & R) {
@@ -247,23 +340,32 @@ __global__ void __launch_bounds__(128, MLB_FLUX_MINB) face_flux_kernel(const __g
         double Ul[4], Pl[5];
         if (TENO) ld4(a.Fc, (size_t)cl * NPT + (sl * Q + q), Ul); else ld4(a.Uin, cl, Ul);
         if (cr >= 0) {
-            double Ur[4], Pr[5];
+            double Ur[4];
             if (TENO) ld4(a.Fc, (size_t)cr * NPT + (sr * Q + q), Ur); else ld4(a.Uin, (size_t)cr, Ur);
+#ifdef MLB_STREAM_KERNELS
+            riemann_flux_lean<RS>(ft, nx, ny, face_cons(a.ph.gas, Ul), face_cons(a.ph.gas, Ur), a.ph.gas.gamma);
+#else
+            double Pr[5];
             cons_to_prim(a.ph.gas, Ul, Pl);
             cons_to_prim(a.ph.gas, Ur, Pr);
             const FaceState L = {Ul[0], Pl[0], Pl[1], Pl[2], Pl[4]};
             const FaceState R = {Ur[0], Pr[0], Pr[1], Pr[2], Pr[4]};
             riemann_flux<RS>(ft, nx, ny, L, R, a.ph.gas.gamma);
+#endif
             return;
         }
         cons_to_prim(a.ph.gas, Ul, Pl);
-        const FaceState L = {Ul[0], Pl[0], Pl[1], Pl[2], Pl[4]};
         if (bc->type == MLB_BC_WALL_ADIABATIC) {          // boundary_wall_adiabatic.cpp:39-70
             ft[0] = 0.0; ft[1] = Pl[2] * nx; ft[2] = Pl[2] * ny; ft[3] = 0.0;
         } else {
             FaceState gh;
             ghost_state(*bc, a.ph.gas, nx, ny, Ul, Pl, gh);
+#ifdef MLB_STREAM_KERNELS
+            riemann_flux_lean<RS>(ft, nx, ny, face_cons(a.ph.gas, Ul), face_cons(gh), a.ph.gas.gamma);
+#else
+            const FaceState L = {Ul[0], Pl[0], Pl[1], Pl[2], Pl[4]};
             riemann_flux<RS>(ft, nx, ny, L, gh, a.ph.gas.gamma);
+#endif
         }
     };
 
@@ -336,6 +438,14 @@ __global__ void __launch_bounds__(256) gather_stage_kernel(const __grid_constant
     if (a.rk.k_store) st4(a.rk.k_store, i, k);
     if (a.rk.mode == 3) return;
     const double dt = a.scal[SC_DT];
+    if (dt < 0.0) {   // the reference throws in calc_dt BEFORE take_step (solver.cpp:587-589): a step with a negative dt leaves the
+        if (a.rk.last_stage) {   // solution, the time and the step counter untouched; the host reports the error when it next reads dt
+            double b[4];
+            ld4(a.rk.base, i, b);
+            st4(a.rk.out, i, b);
+        }
+        return;
+    }
     double Unew[4];
     rk_update(a.rk, a.Uin, i, k, dt, Unew);
     if (a.rk.last_stage) {
@@ -579,7 +689,11 @@ __global__ void riemann_kernel(uint64_t n, const double * nunit, const double * 
     const FaceState l = {L[5 * i], L[5 * i + 1], L[5 * i + 2], L[5 * i + 3], L[5 * i + 4]};
     const FaceState r = {R[5 * i], R[5 * i + 1], R[5 * i + 2], R[5 * i + 3], R[5 * i + 4]};
     double F[4];
+#ifdef MLB_STREAM_KERNELS
+    riemann_flux_lean<RS>(F, nunit[2 * i], nunit[2 * i + 1], face_cons(l), face_cons(r), gamma);
+#else
     riemann_flux<RS>(F, nunit[2 * i], nunit[2 * i + 1], l, r, gamma);
+#endif
     for (int v = 0; v < 4; v++) flux[4 * i + v] = F[v];
 }
 
@@ -630,11 +744,7 @@ template <int ORDER, int MP>
 static void launch_recon_t(const ReconArgs & a, cudaStream_t st) {
     constexpr int K = (ORDER + 1) * (ORDER + 2) / 2;
     const size_t smem = (size_t)a.S * K * RECON_THREADS * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(teno_recon_kernel<ORDER, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1 + MAX_SLOTS) * K * RECON_THREADS * sizeof(double)));
-        configured = true;
-    }
+    ensure_dynamic_smem(reinterpret_cast<const void *>(teno_recon_kernel<ORDER, MP>), (size_t)(1 + MAX_SLOTS) * K * RECON_THREADS * sizeof(double));
     const unsigned cells_per_block = RECON_THREADS / 4;
     const unsigned grid = (a.g.N_recon + cells_per_block - 1) / cells_per_block;
     if (grid == 0) return;

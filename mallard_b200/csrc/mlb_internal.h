@@ -52,15 +52,9 @@ constexpr int MAX_K = 55;       // (p+1)(p+2)/2 for p <= 9
 constexpr uint32_t NO_FACE = 0xFFFFFFFFu;
 constexpr int TILE = 8;         // cells per interleaved TENO table tile (one warp = 8 cells x 4 variables)
 
-// Streaming (FAST mode) table layout: tiles of FAST_CT cells, S = 1 + 3 stencil slots (triangles).
-//   FAST_CT = 8  (default): a tile belongs to ONE WARP, which streams it through its own shared-memory ring
-//                           (teno_stream_warp.cuh);
-//   FAST_CT = 32 (A/B build, -DMLB_FAST_CT=32): a tile belongs to a CTA of 4 consumer warps + 1 producer warp (teno_stream.cuh).
-#ifndef MLB_FAST_CT
-#define MLB_FAST_CT 8
-#endif
-constexpr int FAST_CT = MLB_FAST_CT;
-static_assert(FAST_CT == 8 || FAST_CT == 32, "streaming tile = 8 cells (warp-private rings) or 32 cells (CTA ring)");
+// Streaming (FAST mode) table layout: tiles of FAST_CT = 8 cells; a tile belongs to ONE WARP, which streams it through its
+// own shared-memory ring (teno_stream_warp.cuh).  S = 1 + 3 stencil slots (triangles).
+constexpr int FAST_CT = 8;
 constexpr int FAST_S = 4;
 #ifndef MLB_FAST_RC3
 #define MLB_FAST_RC3 3

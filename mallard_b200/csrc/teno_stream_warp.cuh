@@ -350,16 +350,8 @@ __global__ void __launch_bounds__(WTHREADS, MLB_WARP_MINB) teno_stream_warp_kern
 template <int ORDER, bool MONO>
 static void launch_stream_w(const ReconStreamArgs & a, cudaStream_t st) {
     const size_t smem = WSmem<ORDER>::TOTAL;
-    static int ctas = 0;
-    if (!ctas) {
-        cudaFuncSetAttribute(teno_stream_warp_kernel<ORDER, MONO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, teno_stream_warp_kernel<ORDER, MONO>, WTHREADS, smem);
-        ctas = sms * (per_sm > 0 ? per_sm : 1);
-    }
     if (a.n_tiles <= a.tile_begin) return;
+    const int ctas = persistent_ctas(reinterpret_cast<const void *>(teno_stream_warp_kernel<ORDER, MONO>), WTHREADS, smem);
     const uint32_t need = (a.n_tiles - a.tile_begin + WARPS - 1) / WARPS;
     const unsigned grid = need < (uint32_t)ctas ? need : (unsigned)ctas;   // persistent: one CTA per resident CTA slot
     teno_stream_warp_kernel<ORDER, MONO><<<grid, WTHREADS, smem, st>>>(a);

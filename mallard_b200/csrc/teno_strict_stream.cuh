@@ -278,17 +278,9 @@ __global__ void __launch_bounds__(STHREADS, 2) teno_strict_stream_kernel(const _
 template <int ORDER, int MP>
 static void launch_strict_stream(const ReconArgs & a, cudaStream_t st) {
     const size_t smem = SCfg<ORDER, MP>::TOTAL;
-    static int ctas = 0;
-    if (!ctas) {
-        cudaFuncSetAttribute(teno_strict_stream_kernel<ORDER, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, teno_strict_stream_kernel<ORDER, MP>, STHREADS, smem);
-        ctas = sms * (per_sm > 0 ? per_sm : 1);
-    }
     const uint32_t n_tiles = (a.g.N_recon + SCT - 1) / SCT;
     if (!n_tiles) return;
+    const int ctas = persistent_ctas(reinterpret_cast<const void *>(teno_strict_stream_kernel<ORDER, MP>), STHREADS, smem);
     const uint32_t need = (n_tiles + SWARPS - 1) / SWARPS;
     teno_strict_stream_kernel<ORDER, MP><<<need < (uint32_t)ctas ? need : (unsigned)ctas, STHREADS, smem, st>>>(a);
 }

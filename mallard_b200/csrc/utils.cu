@@ -1,10 +1,50 @@
 // Layout / bookkeeping kernels that do no floating-point arithmetic of the path (or a single IEEE operation), shared by
 // both floating-point modes: AoS(reference numbering) <-> SoA(library numbering) conversion, halo pack/unpack, dt.
 #include <cfloat>
+#include <map>
+#include <mutex>
 
 #include "kernel_args.h"
 
 namespace mlb {
+
+// ---- per-(kernel, device) launch configuration (see kernel_args.h)
+namespace {
+std::mutex cfg_mutex;
+std::map<std::pair<const void *, int>, int> cfg_ctas;      // persistent grid size
+std::map<std::pair<const void *, int>, size_t> cfg_smem;   // largest dynamic shared-memory size opted into
+void cfg_check(cudaError_t e, const char * what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what);
+}
+void opt_in_locked(const void * kernel, int dev, size_t smem) {
+    size_t & have = cfg_smem[{kernel, dev}];
+    if (smem <= have) return;
+    cfg_check(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    have = smem;
+}
+}  // namespace
+
+void ensure_dynamic_smem(const void * kernel, size_t smem) {
+    int dev = 0;
+    cfg_check(cudaGetDevice(&dev), "cudaGetDevice");
+    std::lock_guard<std::mutex> lock(cfg_mutex);
+    opt_in_locked(kernel, dev, smem);
+}
+
+int persistent_ctas(const void * kernel, int threads, size_t smem) {
+    int dev = 0;
+    cfg_check(cudaGetDevice(&dev), "cudaGetDevice");
+    std::lock_guard<std::mutex> lock(cfg_mutex);
+    const auto key = std::make_pair(kernel, dev);
+    const auto it = cfg_ctas.find(key);
+    if (it != cfg_ctas.end()) return it->second;
+    opt_in_locked(kernel, dev, smem);
+    int sms = 0, per_sm = 0;
+    cfg_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute(MultiProcessorCount)");
+    cfg_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem), "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (sms < 1 || per_sm < 1) throw std::runtime_error("streaming kernel does not fit on this device (shared memory / registers)");
+    return cfg_ctas[key] = sms * per_sm;
+}
 
 namespace {
 
@@ -40,7 +80,8 @@ __global__ void export_scaled_kernel(const double * __restrict__ v, const double
                                      const uint32_t * __restrict__ perm, uint32_t n, double * __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    out[perm[i]] = scal[which] * v[i];
+    const double r = v[i];                               // 0 until the first calc_dt: the reference's cfl_local is +0 then
+    out[perm[i]] = r == 0.0 ? 0.0 : scal[which] * r;
 }
 
 // buf[k][v] = soa[v][idx[k]]  /  soa[v][idx[k]] = buf[k][v]   (halo pack / unpack, 4 conserved variables)

@@ -106,8 +106,8 @@ int main(int argc, char ** argv) {
             num.basis = MLB_BASIS_LEGENDRE; num.basis_order = 3; num.max_stencil_size_factor = 2.0;
             if (num.recon == MLB_RECON_TENO) {
                 const auto & fr = toml::find(in, "numerics", "face_reconstruction");
-                num.basis = enum_of(toml::find_or<std::string>(fr, "basis_type", "legendre"), {{"monomial", MLB_BASIS_MONOMIAL}, {"legendre", MLB_BASIS_LEGENDRE}}, "basis");
-                num.basis_order = toml::find_or<int>(fr, "basis_order", 3);
+                num.basis = enum_of(toml::find_or<std::string>(fr, "basis_type", "monomial") /* the reference's default, face_reconstruction.cpp:110 */, {{"monomial", MLB_BASIS_MONOMIAL}, {"legendre", MLB_BASIS_LEGENDRE}}, "basis");
+                num.basis_order = toml::find<int>(fr, "basis_order");   // required by the reference too (:111)
                 num.max_stencil_size_factor = toml::find_or<double>(fr, "max_stencil_size_factor", 2.0);
                 num.quadrature_order_cell = toml::find_or<int>(fr, "quadrature_order_cell", 0);
                 num.quadrature_order_face = toml::find_or<int>(fr, "quadrature_order_face", 0);

@@ -83,3 +83,25 @@ def field_err(a, b):
     # against the largest component: FMA contraction leaves ~1e-17 there where the reference cancels exactly
     scale = np.maximum(np.maximum(col, 1e-3 * col.max()), 1e-300)
     return float(np.max(np.abs(a2 - b2).max(axis=0) / scale))
+
+
+def elem_err(a, b, floor=1e-9):
+    """ELEMENT-wise relative error max |a-b| / max(|b|, floor * column scale) over the entries finite in both (printed and
+    bounded next to field_err for FAST-mode results: the floor keeps exact zeros / complete cancellations of the reference
+    from dividing by nothing, everything above it is measured against its own magnitude)."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    a2 = a.reshape(-1, a.shape[-1]) if a.ndim > 1 else a.reshape(-1, 1)
+    b2 = b.reshape(-1, b.shape[-1]) if b.ndim > 1 else b.reshape(-1, 1)
+    ok = np.isfinite(a2) & np.isfinite(b2)
+    if not ok.any():
+        return 0.0
+    col = np.where(ok, np.abs(b2), 0.0).max(axis=0)
+    den = np.maximum(np.abs(b2), floor * np.maximum(col, 1e-300)[None, :])
+    return float(np.max(np.where(ok, np.abs(a2 - b2) / den, 0.0)))
+
+
+def pattern_mismatch(a, b):
+    """Fraction of entries whose finite / NaN / +-Inf class differs."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    cls = lambda x: np.where(np.isnan(x), 3, np.where(np.isposinf(x), 1, np.where(np.isneginf(x), 2, 0)))
+    return float((cls(a) != cls(b)).mean())

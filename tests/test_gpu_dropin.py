@@ -197,3 +197,128 @@ def test_native_vtu_writer_and_device_side_checks(tmp_path, name, toml, tol):
     assert len(ra) == len(rb) and len(ra) >= 9
     if tol == 0.0:
         assert ra == rb
+
+
+# ---- examples/wedge to its own stop time (t_stop = 0.1, 7938 steps; the parametrised case above stops after 400) -----------
+WEDGE_FULL = WEDGE.replace("n_steps = 400", "t_stop = 0.1").replace("interval = 200", "interval = 2000")
+
+
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(DROPIN)), reason="oracle/_ref binaries not built (need /root/reference)")
+def test_wedge_to_t_stop_through_the_reference_host(tmp_path):
+    """BASELINE configs[2] verbatim (examples/wedge/input.toml: t_stop = 0.1): the reference host loop decides when to stop
+    from the dt the library returns, so the step count (7938) is itself a parity result.  STRICT: every VTU file byte-identical
+    to the stock binary's; FAST: fields within 1e-9 of the field scale after ~8000 steps (drift over the run)."""
+    a = str(tmp_path / "ref")
+    run(REF, WEDGE_FULL, a)
+    fa = sorted(os.listdir(os.path.join(a, "solut", "all")))
+    assert len(fa) >= 5
+    for fp, tol in (("strict", 0.0), ("fast", 1e-9)):
+        b = str(tmp_path / fp)
+        out = run(DROPIN, WEDGE_FULL, b, ("--fp", fp, "--quiet"))
+        info = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+        fb = sorted(os.listdir(os.path.join(b, "solut", "all")))
+        assert fa == fb, (fa, fb)                              # same number of steps to t_stop: the last file carries the step count
+        worst = 0.0
+        for f in fa:
+            ra, rb = open(os.path.join(a, "solut", "all", f), "rb").read(), open(os.path.join(b, "solut", "all", f), "rb").read()
+            if tol == 0.0:
+                assert ra == rb, f
+                continue
+            va, vb = read_vtu(os.path.join(a, "solut", "all", f)), read_vtu(os.path.join(b, "solut", "all", f))
+            for k in va:
+                if va[k].dtype.kind == "f":
+                    group = [g for g in (("RHOU_X", "RHOU_Y"), ("U_X", "U_Y")) if k in g]
+                    sc = max([np.abs(va[k]).max()] + [np.abs(va[x]).max() for g in group for x in g] + [1e-300])
+                    worst = max(worst, float(np.abs(va[k] - vb[k]).max() / sc))
+        print("wedge to t_stop [%s]: %d steps, last file %s, worst field difference %.2e" % (fp, info["steps"], fa[-1], worst))
+        assert worst <= tol
+
+
+# ---- TENO through the reference host ------------------------------------------------------------------------------------
+def _teno_toml(ic, n_steps, basis):
+    rho, ux, uy, pp = ic
+    return """
+[run]
+n_steps = %d
+cfl = 0.1
+[mesh]
+type = "cartesian_tri"
+Nx = 24
+Ny = 20
+Lx = 1.0
+Ly = 1.0
+[initialize]
+type = "analytical"
+rho = "%s"
+u = ["%s", "%s"]
+p = "%s"
+%s
+[numerics]
+riemann_solver = "HLLC"
+time_integrator = "SSPRK3"
+check_nan = false
+[numerics.face_reconstruction]
+type = "TENO"
+%sbasis_order = 3
+max_stencil_size_factor = 2.0
+[physics]
+type = "euler"
+gamma = 1.4
+p_ref = 101325.0
+T_ref = 298.15
+rho_ref = 1.225
+[output]
+check_interval = 1
+[[write_data]]
+prefix = "./solut/all/teno_all"
+format = "vtu"
+geometry = "all"
+interval = 1
+variables = ["CFL", "RHO", "RHOU_X", "RHOU_Y", "RHOE", "U_X",  "U_Y", "P", "T", "H"]
+""" % (n_steps, rho, ux, uy, pp, "\n".join('[[boundaries]]\nname = "%s"\ntype = "symmetry"' % n for n in ("left", "right", "top", "bottom")),
+       ('basis_type = "%s"\n' % basis) if basis else "")
+
+
+_Q = "var l := x <  0.8; var r := x >= 0.8; var b := y <  0.8; var t := y >= 0.8; "
+TENO_RIEMANN = (_Q + "1.5 * r * t + 0.532258064516129 * l * t + 0.137992831541219 * l * b + 0.532258064516129 * r * b",
+                _Q + "0.0 * r * t + 1.206045378311055 * l * t + 1.206045378311055 * l * b + 0.0 * r * b",
+                _Q + "0.0 * r * t + 0.0 * l * t + 1.206045378311055 * l * b + 1.206045378311055 * r * b",
+                _Q + "1.5 * r * t + 0.3 * l * t + 0.029032258064516 * l * b + 0.3 * r * b")
+TENO_SMOOTH = ("1.0 + 0.2 * sin(2 * pi * x) * cos(2 * pi * y)", "0.5 + 0.1 * cos(2 * pi * x)", "0.3 + 0.1 * sin(2 * pi * y)",
+               "1.0 + 0.1 * cos(2 * pi * (x + y))")
+
+
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(DROPIN)), reason="oracle/_ref binaries not built (need /root/reference)")
+@pytest.mark.parametrize("ic,n_steps,basis", [(TENO_RIEMANN, 1, "legendre"), (TENO_SMOOTH, 1, "legendre"), (TENO_SMOOTH, 1, None)],
+                         ids=["riemann_2d-IC", "smooth-IC", "smooth-IC-default-basis(monomial)"])
+@pytest.mark.parametrize("fp", ["strict", "fast"])
+def test_teno_toml_through_the_reference_host(tmp_path, ic, n_steps, basis, fp):
+    """examples/riemann_2d's numerics block (TENO + HLLC + SSPRK3, cfl 0.1) on a small cartesian_tri mesh through the
+    UNMODIFIED reference host with the hot path rerouted, against the stock binary, after the first step.  On the
+    four-quadrant IC the reference turns non-finite inside that step: the non-finite pattern of every written
+    field must coincide and the finite entries agree (NaN-pattern-aware comparison)."""
+    toml = _teno_toml(ic, n_steps, basis)
+    a, b = str(tmp_path / "ref"), str(tmp_path / "b200")
+    run(REF, toml, a)
+    run(DROPIN, toml, b, ("--fp", fp, "--quiet"))
+    fa, fb = sorted(os.listdir(os.path.join(a, "solut", "all"))), sorted(os.listdir(os.path.join(b, "solut", "all")))
+    assert fa == fb and len(fa) == n_steps + 1
+    worst, n_bad = 0.0, 0
+    for f in fa:
+        va, vb = read_vtu(os.path.join(a, "solut", "all", f)), read_vtu(os.path.join(b, "solut", "all", f))
+        for k in va:
+            if va[k].dtype.kind != "f":
+                assert np.array_equal(va[k], vb[k]), (f, k)
+                continue
+            x, y = va[k].astype(np.float64), vb[k].astype(np.float64)
+            assert np.array_equal(np.isnan(x), np.isnan(y)), (f, k, int(np.isnan(x).sum()), int(np.isnan(y).sum()))
+            assert np.array_equal(np.isinf(x), np.isinf(y)) and np.array_equal(x[np.isinf(x)], y[np.isinf(y)]), (f, k)
+            ok = np.isfinite(x)
+            n_bad += int((~ok).sum())
+            if ok.any():
+                # each finite entry against its own magnitude, floored at 1e-6 of the field's largest finite entry (the
+                # discontinuity branch leaves entries many orders of magnitude apart in one field)
+                den = np.maximum(np.abs(x[ok]), 1e-6 * np.abs(x[ok]).max() + 1e-300)
+                worst = max(worst, float(np.max(np.abs(x[ok] - y[ok]) / den)))
+    print("TENO through the reference host [%s]: %d non-finite entries (coinciding), worst finite difference %.2e" % (fp, n_bad, worst))
+    assert worst <= (1e-11 if fp == "strict" else 1e-9)
