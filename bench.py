@@ -96,6 +96,18 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def hbm_peak():
+    """(GB/s, where it comes from): the driver-written measurement, else the profiling recipe's fallback."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    if "hbm_gbs" in peaks:
+        return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -162,6 +174,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = every GPU owns an nx x ny block (default, the driver's scaling run); strong = the nx x ny mesh is "
                          "split over the GPUs")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling records (16 M / 64 M-cell partitioned vortex mesh) appended to "
+                                                              "the default riemann_2d line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
@@ -263,13 +277,7 @@ def main():
     s.run(a.steps, cfl=cfl)
     prof = s.profile_read()
     s.profile(False)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    peak, peak_src = hbm_peak()
     top = max(prof, key=lambda k: prof[k][0]) if prof else None
     roof = None
     kernels = {k: {"ms_total": v[0], "launches": int(v[1]), "ms_per_launch": v[0] / max(1, v[1])} for k, v in prof.items()}
@@ -323,17 +331,26 @@ def main():
         except Exception as ex:   # the baseline is reported, never required for the GPU number
             cpu = {"value": None, "unit": "cell-updates/s", "cores": host_cores(), "kind": "unavailable", "sample": str(ex)[:200]}
 
+    # ---- strong-scaling records: this N's point of the 16 M-cell (BASELINE configs[3]) / 64 M-cell partitioned vortex meshes
+    strong = None
+    graph_replayed = int(s.get("stats")[11])
+    if a.workload == "riemann_2d" and a.recon == "TENO" and not a.no_strong and (a.nx, a.ny) == (1024, 1024):
+        import bench_multi
+        s.close()
+        mb.set_host_threads(host_cores())
+        strong = bench_multi.strong_records(a, 0, 1, 0, peak, peak_src)
+
     line = {"metric": "cell-updates/s per RK stage", "value": value, "unit": "cell-updates/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "n_cells": nc, "fp_mode": a.fp, "recon": a.recon, "l2": (("inputs larger than L2 (TENO tables %.1f GB per stage)" if a.recon == "TENO" else "inputs larger than L2 (%.1f GB of state, connectivity and face products per stage)") % (stats[2] / 1e9))
                              if stats[2] > 252e6 else "working set %.1f MB fits in L2: a launch-bound configuration, steps replayed as a CUDA graph" % (stats[2] / 1e6),
-                       "graph_replayed_steps": int(s.get("stats")[11]),
+                       "graph_replayed_steps": graph_replayed,
                        "device_bytes": stats[2], "preprocess_seconds": stats[1], "setup_seconds": setup_s, "mesh_seconds": mesh_s,
                        "preprocess": {"host_total_s": stats[1], "host_stencil_search_s": stats[8], "host_matrices_s": stats[9],
                                       "device_table_build_s": stats[10]},
                        "note": ("reference-faithful TENO: like the reference, the state turns non-finite inside step 1 (SURVEY 0.2); cost is "
                                 "data-independent") if a.recon == "TENO" else "first-order path (the numerics of examples/sod and examples/wedge)"},
-            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "kernels": kernels}
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "kernels": kernels, "strong": strong}
     print(json.dumps(line))
 
 

@@ -1,16 +1,29 @@
-"""bench.py's N>1 leg (launched by torchrun, one rank per GPU).
+"""bench.py's multi-GPU legs (launched by torchrun, one rank per GPU) and the strong-scaling records of every line.
 
-Weak scaling of BASELINE.json configs[1]: every rank owns one nx x ny block (2*nx*ny triangles) of a (nx*N) x ny
-cartesian_tri mesh; the global mesh is partitioned in x by cell centroid.  Per RK stage the ghost-cell conserved states are
-exchanged peer to peer with NCCL send/recv straight between the library's device buffers, per step one double is
-all-reduced (max) for dt (mallard_b200/parallel.py).  Timing: barrier + device synchronise on both sides, CUDA events on
-the library's compute stream, MAX over ranks.
+Main line, N > 1 — weak scaling of BASELINE.json configs[1]: every rank owns one nx x ny block (2*nx*ny triangles) of a
+(nx*N) x ny cartesian_tri mesh, partitioned in x by cell centroid.
+
+`strong` records (every N, appended to the same JSON line) — BASELINE.json configs[3] / [4] family: ONE jittered, id-shuffled
+triangulation (2828^2 quads = 16.0 M cells; 5657^2 = 64.0 M cells where it fits) cut by the library's recursive coordinate
+bisection; every rank builds ITS PART of the mesh only (synthetic.jittered_tri_local -> mlb_create_local), so no rank ever holds
+the global mesh.  value = global cells x stages x steps / time; efficiency is value_N / (N x value_1) of the same mesh.
+
+Both are driven by the library's native driver (mlb_comm_init / mlb_run_distributed: grouped ncclSend/ncclRecv between the
+library's device buffers on the communication stream under the reconstruction of the interior cells, ncclAllReduce(max) of dt,
+the step replayed as a CUDA graph).  torch.distributed ships the NCCL id, provides the barriers and reduces the timings.
+Timing: barrier + device synchronise on both sides, CUDA events on the library's compute stream, MAX over ranks.
 """
 import json
 import os
+import resource
 import time
 
 import numpy as np
+
+T_START = time.perf_counter()
+STRONG_MESHES = (("vortex_16M", 2828), ("vortex_64M", 5657))      # BASELINE configs[3] (16 M cells) and the configs[4] mesh (64 M)
+MAX_CELLS_PER_GPU = 24.0e6                                        # TENO p=3 tables: 6.5 kB per cell of 180 GB
+TIME_BUDGET_S = 560.0                                             # do not start another strong record after this much wall time
 
 
 def bind_to_gpu_numa_node(index):
@@ -32,6 +45,157 @@ def bind_to_gpu_numa_node(index):
     return None
 
 
+def _reduce(x, world, op="max"):
+    if world == 1:
+        return np.asarray(x, dtype=np.float64)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(np.asarray(x, dtype=np.float64), device="cuda")
+    dist.all_reduce(t, op={"max": dist.ReduceOp.MAX, "sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN}[op])
+    return t.cpu().numpy()
+
+
+def _barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+class Run:
+    """One partitioned (or single-GPU) solver and its timed loop."""
+
+    def __init__(self, solver, ds, world):
+        self.s, self.ds, self.world = solver, ds, world
+
+    def steps(self, n, cfl):
+        if self.ds is not None:
+            self.ds.run(n, cfl)
+        else:
+            self.s.run(n, cfl=cfl)
+
+    def timed(self, n, cfl):
+        s = self.s
+        _barrier(self.world)
+        s.synchronize()
+        s.event_record(0)
+        self.steps(n, cfl)
+        s.event_record(1)
+        ms = s.event_elapsed_ms(0, 1)
+        s.synchronize()
+        _barrier(self.world)
+        return float(_reduce([ms], self.world)[0])
+
+    def recon_roofline(self, n_steps, cfl, n_stages, peak, peak_src, alg_bytes):
+        """Per-kernel device time over n_steps (CUDA events on the compute stream, steps issued eagerly): the reconstruction
+        kernel's time per stage on the SLOWEST rank (interior + rim launches) against its algorithmic bytes."""
+        s = self.s
+        s.profile(True)
+        self.steps(n_steps, cfl)
+        prof = s.profile_read()
+        s.profile(False)
+        tot = sum(v[0] for v in prof.values())
+        rec = prof.get("teno_stream", prof.get("teno_recon", (0.0, 0)))
+        n_recon = int(s.get("stats")[6])
+        ms_stage = rec[0] / (n_steps * n_stages)
+        ach = alg_bytes * n_recon / (ms_stage * 1e-3) / 1e9 if ms_stage > 0 else 0.0
+        stage_all = sum(v[0] for k, v in prof.items() if k != "cfl") / (n_steps * n_stages)
+        worst = _reduce([ms_stage, stage_all], self.world, "max")
+        fr = _reduce([ach / peak], self.world, "min")
+        return {"bound": "hbm", "kernel": "teno_stream (interior + rim launches of a stage)", "achieved": float(fr[0] * peak), "peak": peak, "unit": "GB/s",
+                "frac": float(fr[0]), "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_cell": alg_bytes,
+                "rank": "slowest", "ms_per_stage_slowest_rank": float(worst[0]), "all_kernels_ms_per_stage_slowest_rank": float(worst[1]),
+                "cells_reconstructed_this_rank": n_recon, "share_of_step_this_rank": rec[0] / tot if tot else None,
+                "kernels_this_rank": {k: {"ms_total": v[0], "launches": int(v[1])} for k, v in prof.items()}}
+
+
+def strong_record(name, nq, a, rank, world, device, peak, peak_src):
+    """Strong scaling: the nq x nq jittered, id-shuffled triangulation of [0,10]^2 split over `world` GPUs."""
+    import bench
+    import mallard_b200 as mb
+    from mallard_b200 import synthetic as syn
+    nc = 2 * nq * nq
+    rec = {"workload": "%s: isentropic vortex, jittered (+-0.15 h, seed 12345), id-shuffled triangulation %dx%d of [0,10]^2 (%d cells), "
+                       "TENO(legendre,p=3)+HLLC+SSPRK3, cfl 0.1, extrapolation BCs; recursive coordinate bisection over %d GPU(s), rank-local ingest"
+                       % (name, nq, nq, nc, world), "n_cells": nc, "n_gpus": world, "scaling": "strong"}
+    t0 = time.perf_counter()
+    layers, lp, ds, s = 8, None, None, None
+    for attempt in range(3):
+        lp = syn.jittered_tri_local(nq, nq, 10.0, 10.0, world, rank, seed=12345, layers=layers)
+        ok = 1.0
+        try:
+            kw = dict(recon="TENO", riemann="HLLC", integrator="SSPRK3", order=3, bcs=syn.EXTRAP4, fp_mode=a.fp, keep_stage_rhs=False)
+            if world > 1:
+                s = mb.Solver(lp.mesh, part=lp.part_local, rank=rank, n_ranks=world, device=device, local=lp.local, **kw)
+            else:
+                s = mb.Solver(lp.mesh, device=device, **kw)
+        except mb.MallardError as ex:
+            if "more ghost layers" not in str(ex):
+                raise
+            ok, s = 0.0, None
+        if _reduce([ok], world, "min")[0] > 0:      # every rank must agree before anything collective happens
+            break
+        if s is not None:
+            s.close()
+        layers *= 2
+    else:
+        raise RuntimeError("rank-local mesh: ghost layers insufficient")
+    if world > 1:
+        from mallard_b200.parallel import DistributedSolver
+        ds = DistributedSolver.from_solver(s, rank, world, device, local=lp.local, native=True)
+    stats = s.get("stats")
+    n_owned = int(stats[4])
+    s.set_state(syn.isentropic_vortex(lp.mesh.arrays["cell_coords"]))
+    setup_s = time.perf_counter() - t0
+    run = Run(s, ds, world)
+    run.timed(a.warmup, 0.1)
+    ms = run.timed(a.steps, 0.1)
+    rec.update(value=nc * bench.N_STAGES * a.steps / (ms * 1e-3), unit="cell-updates/s", ms_per_step=ms / a.steps, steps=a.steps, warmup=a.warmup)
+    rec["roofline"] = run.recon_roofline(max(2, min(a.steps, 5)), 0.1, bench.N_STAGES, peak, peak_src, bench.ALG_BYTES_RECON)
+    if world > 1:
+        peers, sc, rc = s.halo_info()
+        h = _reduce([float(sc.sum()), float(rc.sum()), float(len(peers))], world, "max")
+        rec["halo"] = {"max_send_cells_per_stage": int(h[0]), "max_recv_cells_per_stage": int(h[1]), "max_peers": int(h[2]),
+                       "transport": "grouped ncclSend/ncclRecv between device buffers + ncclAllReduce(max) of dt, inside the library; step replayed as a CUDA graph"}
+        own = _reduce([float(n_owned)], world, "max")
+        rec["cells_per_gpu_max"] = int(own[0])
+    mem = _reduce([resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1048576.0, stats[2] / 1e9, float(lp.mesh.n_cells), setup_s, stats[1], lp.seconds], world, "max")
+    rec.update(host_rss_gb_per_rank_max=float(mem[0]), device_gb_per_rank_max=float(mem[1]), local_mesh_cells_max=int(mem[2]), ghost_layers=layers,
+               setup_seconds=float(mem[3]), preprocess_seconds=float(mem[4]), mesh_seconds=float(mem[5]), graph_replayed_steps=int(s.get("stats")[11]))
+    # efficiency against this mesh's own 1-GPU run: measured in the same job when N == 1, else taken from the committed N=1 line
+    base = None
+    try:
+        base = json.load(open(os.path.join(bench.ROOT, "profiles", "r02_strong_baselines.json"))).get(name)
+    except Exception:
+        pass
+    if world == 1:
+        rec["efficiency"] = 1.0
+    elif base and base.get("n_gpus") and base.get("value"):
+        rec["efficiency"] = rec["value"] / (world / base["n_gpus"] * base["value"])
+        rec["efficiency_base"] = "profiles/r02_strong_baselines.json: %s on %d GPU(s), %.4g cell-updates/s" % (name, base["n_gpus"], base["value"])
+    s.close()
+    return rec
+
+
+def strong_records(a, rank, world, device, peak, peak_src):
+    out = []
+    for name, nq in STRONG_MESHES:
+        nc = 2 * nq * nq
+        if nc / world > MAX_CELLS_PER_GPU:
+            out.append({"workload": name, "n_cells": nc, "skipped": "%.1f M cells per GPU do not fit 180 GB" % (nc / world / 1e6)})
+            continue
+        elapsed = float(_reduce([time.perf_counter() - T_START], world, "max")[0])
+        if elapsed > TIME_BUDGET_S:
+            out.append({"workload": name, "n_cells": nc, "skipped": "time budget of the bench run (%.0f s elapsed)" % elapsed})
+            continue
+        try:
+            out.append(strong_record(name, nq, a, rank, world, device, peak, peak_src))
+        except Exception as ex:      # a strong record never costs the main line
+            if world > 1:
+                raise
+            out.append({"workload": name, "n_cells": nc, "error": str(ex)[:300]})
+    return out
+
+
 def run(a, rank, world, local_rank, workload):
     import torch
     import torch.distributed as dist
@@ -46,16 +210,17 @@ def run(a, rank, world, local_rank, workload):
     # (torchrun presets OMP_NUM_THREADS=1, which would serialise the TENO table construction)
     mb.set_host_threads(max(1, min(total_cores // world, bench.host_cores())))
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peak, peak_src = bench.hbm_peak()
 
     t_setup = time.perf_counter()
     strong = getattr(a, "scaling", "weak") == "strong" or a.workload == "vortex"
+    local = None
     if a.workload == "vortex":
         # BASELINE configs[3]: ONE jittered, id-shuffled triangulation (a.nx x a.ny quads) split over the GPUs by the library's
-        # recursive coordinate bisection (mlb_partition) - an irregular cut through an unstructured numbering
+        # recursive coordinate bisection - an irregular cut through an unstructured numbering; rank-local ingest
         from mallard_b200 import synthetic as syn
-        mesh = syn.jittered_tri(a.nx, a.ny, 10.0, 10.0, seed=12345)
-        nc = mesh.n_cells
-        part = mb.partition(mesh, world)
+        lp = syn.jittered_tri_local(a.nx, a.ny, 10.0, 10.0, world, rank, seed=12345, layers=10)
+        mesh, part, local, nc = lp.mesh, lp.part_local, lp.local, lp.n_global
         U0, P0, bcs = syn.isentropic_vortex(mesh.arrays["cell_coords"]), None, syn.EXTRAP4
         gnx = a.nx
     else:
@@ -67,75 +232,68 @@ def run(a, rank, world, local_rank, workload):
         part = np.minimum((xy[:, 0] * (world / Lx)).astype(np.int32), world - 1)  # rank r owns the strip x in [r, r+1) Lx / world
         U0, P0 = bench.riemann2d_state(np.stack([xy[:, 0] / Lx, xy[:, 1]], 1))    # the four-quadrant IC stretched over the strip
         bcs = bench.SYM4
-    ds = DistributedSolver(mesh, part, rank, world, local_rank, recon=a.recon, riemann="HLLC", integrator="SSPRK3", order=3,
-                           bcs=bcs, fp_mode=a.fp, keep_stage_rhs=False)
+    ds = DistributedSolver(mesh, part, rank, world, local_rank, local=local, native=True, recon=a.recon, riemann="HLLC", integrator="SSPRK3",
+                           order=3, bcs=bcs, fp_mode=a.fp, keep_stage_rhs=False)
     s = ds.s
     stats = s.get("stats")
     n_owned = int(stats[4])
     setup_s = time.perf_counter() - t_setup
     ds.set_state(U0, P0)
+    owned_ids = ds.owned
 
-    def timed(n_steps):
-        dist.barrier()
-        s.synchronize()
-        s.event_record(0)
-        for _ in range(n_steps):
-            ds.step(0.1)
-        s.event_record(1)
-        ms = s.event_elapsed_ms(0, 1)
-        s.synchronize()
-        dist.barrier()
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    timed(a.warmup)
+    run_ = Run(s, ds, world)
+    run_.timed(a.warmup, 0.1)
     launches0 = s.launch_count
     clocks = bench.ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ms = timed(a.steps)
+    ms = run_.timed(a.steps, 0.1)
     clk = clocks.stop() if rank == 0 else None
     launches = s.launch_count - launches0
     value = nc * bench.N_STAGES * a.steps / (ms * 1e-3)
+    replays = int(s.get("stats")[11])
+    ds.set_state(U0, P0)
+    roof = run_.recon_roofline(max(2, min(a.steps, 5)), 0.1, bench.N_STAGES, peak, peak_src, bench.ALG_BYTES_RECON) if a.recon == "TENO" else None
 
     # ---- end to end: per step H2D of the rank's own cells from pinned memory, the step (halo + all-reduce), D2H
     e2e = None
     if not a.no_e2e:
         pin = torch.empty((n_owned, 4), dtype=torch.float64, pin_memory=True)
         Uh = pin.numpy()
-        Uh[:] = U0[ds.owned]
+        Uh[:] = U0[owned_ids]
         k_e2e = max(3, min(a.steps, 10))
         for _ in range(2):
             ds.step_host(Uh, 0.1)
-        Uh[:] = U0[ds.owned]
+        Uh[:] = U0[owned_ids]
         dist.barrier()
         t0 = time.perf_counter()
         for _ in range(k_e2e):
             ds.step_host(Uh, 0.1)
         dist.barrier()
-        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec = float(t.item())
+        sec = float(_reduce([time.perf_counter() - t0], world)[0])
         e2e = {"value": nc * bench.N_STAGES * k_e2e / sec, "unit": "cell-updates/s", "h2d_bytes_per_step": nc * 32, "d2h_bytes_per_step": nc * 32,
                "steps": k_e2e, "ms_per_step": 1e3 * sec / k_e2e,
-               "api": "DistributedSolver.step_host (mlb_set_owned / split-phase stage API / mlb_get_owned; host buffers of the rank's own cells)"}
+               "api": "mlb_take_step_distributed_host (C ABI: pinned host buffers of the rank's own cells -> device, the partitioned step incl. "
+                      "NCCL halo exchange and dt all-reduce inside the library, device -> host)"}
 
     peers, sc, rc = ds.peers, ds.send_counts, ds.recv_counts
-    halo = torch.tensor([float(sc.sum()), float(rc.sum()), float(len(peers))], dtype=torch.float64, device="cuda")
-    dist.all_reduce(halo, op=dist.ReduceOp.MAX)
+    halo = _reduce([float(sc.sum()), float(rc.sum()), float(len(peers))], world)
+    s.close()
+    strong_recs = strong_records(a, rank, world, local_rank, peak, peak_src) if (a.workload == "riemann_2d" and not a.no_strong) else None
     if rank == 0:
         line = {"metric": "cell-updates/s per RK stage", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload + ("; partitioned by recursive coordinate bisection over %d GPUs" % world if a.workload == "vortex" else
+                "config": {"workload": workload + ("; partitioned by recursive coordinate bisection over %d GPUs, rank-local ingest" % world if a.workload == "vortex" else
                                                   ("; the mesh is" if strong else " per GPU; global mesh %dx%d" % (gnx, a.ny)) + " partitioned in x over %d GPUs" % world),
                            "n_cells": nc, "cells_per_gpu": n_owned, "fp_mode": a.fp, "recon": a.recon,
                            "l2": "inputs larger than L2 (TENO tables %.1f GB per GPU per stage)" % (stats[2] / 1e9),
-                           "halo": {"max_send_cells_per_stage": int(halo[0].item()), "max_recv_cells_per_stage": int(halo[1].item()),
-                                    "max_peers": int(halo[2].item()), "transport": "NCCL send/recv between device buffers + all_reduce(max) of dt"},
+                           "driver": "native (mlb_comm_init / mlb_run_distributed): NCCL inside the library, %d of %d timed steps replayed as a CUDA graph"
+                                     % (min(replays, a.steps), a.steps),
+                           "halo": {"max_send_cells_per_stage": int(halo[0]), "max_recv_cells_per_stage": int(halo[1]),
+                                    "max_peers": int(halo[2]), "transport": "grouped ncclSend/ncclRecv between device buffers + ncclAllReduce(max) of dt"},
                            "setup_seconds": setup_s, "cpus_bound_per_rank": numa},
-                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None}
-        print(json.dumps(line))
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": None, "strong": strong_recs}
+        print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()

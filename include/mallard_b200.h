@@ -191,9 +191,32 @@ void *mlb_stream(mlb_ctx *ctx);   /* cudaStream_t of the compute stream */
  *      copies of every remote cell its stencils read.  Each stage the caller moves `send` to the peers and hands back
  *      `recv`; buffers are DEVICE pointers owned by the library so NCCL / peer copies can use them directly. */
 int mlb_partition(const mlb_mesh *mesh, int32_t n_parts, int32_t *part_out /* [nc] */);
+/* the same recursive coordinate bisection from the centroids alone (a rank that holds only its part of the mesh can still
+ * compute the global partition: 16 bytes per cell) */
+int mlb_partition_coords(uint64_t n_cells, const double *cell_xy /* [n_cells][2] */, int32_t n_parts, int32_t *part_out);
 int mlb_create_partitioned(mlb_ctx **out, const mlb_mesh *mesh, const int32_t *part, const mlb_numerics *numerics,
                            const mlb_physics *physics, const mlb_bc *bcs, int32_t n_bcs, const mlb_parallel *parallel);
-int mlb_halo_info(mlb_ctx *ctx, int32_t *n_peers, int32_t *peers /* [n_ranks] */, uint64_t *send_counts,
+/* Rank-local ingest: the context is created from THIS RANK'S PART of the mesh only - its own cells plus enough layers of ghost
+ * cells for every stencil search to stay inside - so that no rank ever holds the global mesh.  Rules for `local_mesh`:
+ *   - cells, faces (and zones) keep the relative order of their global ids (global_cell_ids strictly ascending; zone face lists
+ *     in the global zone's order): stencil membership depends on that order, and with it preserved every table and
+ *     every result is bit-identical to the context mlb_create_partitioned builds from the global mesh;
+ *   - a face whose other cell is not part of the local mesh is marked cells_of_face[f] = {present cell, -2} ("cut"); -1 stays
+ *     "boundary".  Creation fails ("needs more ghost layers") if a stencil search or an owned cell touches a cut face;
+ *   - part_local[i] = owning rank of local cell i.
+ * All arrays crossing the ABI afterwards (mlb_set_state, mlb_get_state ...) are in the LOCAL mesh's numbering; the halo id
+ * lists (mlb_halo_recv_ids / mlb_halo_set_send_ids) are in GLOBAL ids. */
+typedef struct {
+    uint32_t n_global_cells;
+    const uint32_t *global_cell_ids;   /* [local_mesh->n_cells], strictly ascending */
+    double cell0_nodes[6];             /* x,y of the three nodes of GLOBAL cell 0 in nodes_of_cell order: the reference takes
+                                          integral_psi_target from its cell 0 (numerics/face_reconstruction.cpp:598-602) */
+} mlb_local_mesh;
+int mlb_create_local(mlb_ctx **out, const mlb_mesh *local_mesh, const int32_t *part_local, const mlb_local_mesh *local,
+                     const mlb_numerics *numerics, const mlb_physics *physics, const mlb_bc *bcs, int32_t n_bcs,
+                     const mlb_parallel *parallel);
+/* n_peers first (arrays NULL), then arrays of at least *n_peers entries (never more than n_ranks - 1) */
+int mlb_halo_info(mlb_ctx *ctx, int32_t *n_peers, int32_t *peers /* [n_peers] */, uint64_t *send_counts,
                   uint64_t *recv_counts /* CELLS per peer (4 doubles each), per exchange */);
 /* ghost cells this rank receives from peer `peer_index` (index into the peers array), as reference cell ids in the
  * order they occupy the receive buffer; the caller ships each list to its peer, which registers what it must send: */
@@ -230,6 +253,23 @@ int mlb_get_owned(mlb_ctx *ctx, double *U_owned);
 int mlb_finish_step(mlb_ctx *ctx);                                  /* update_primitives ; t += dt ; step++ */
 int mlb_owned_cells(mlb_ctx *ctx, uint32_t *n_owned, uint32_t *cells_out /* reference ids, or NULL */);
 
+/* ---- native multi-GPU driver: NCCL over NVLink / NVSwitch inside the library (libnccl.so.2 is resolved at run time; a process
+ *      that already carries an NCCL, e.g. PyTorch's, keeps using that one).  One process per GPU:
+ *        rank 0: mlb_comm_unique_id(id) ; the host ships the MLB_COMM_ID_BYTES bytes to every rank (MPI_Bcast, a file, ...)
+ *        all:    mlb_comm_init(ctx, id)       communicators + the exchange plan (replaces mlb_halo_recv_ids / _set_send_ids)
+ *                mlb_run_distributed(...)     Solver::run's loop: per stage pack -> grouped ncclSend/ncclRecv -> unpack on the
+ *                                             communication stream under the reconstruction of the interior cells, per step one
+ *                                             ncclAllReduce(max) of the spectral radius; the whole step (both streams, NCCL
+ *                                             included) is captured once and replayed as a CUDA graph; no host code between stages
+ *                mlb_take_step_distributed_host(...)  the take_step seam with HOST buffers of the rank's own cells
+ *      Collective: every rank of the partition must make the same calls in the same order. */
+#define MLB_COMM_ID_BYTES 128
+int mlb_comm_unique_id(void *id_out /* MLB_COMM_ID_BYTES */);
+int mlb_comm_init(mlb_ctx *ctx, const void *id /* MLB_COMM_ID_BYTES */);
+int mlb_run_distributed(mlb_ctx *ctx, uint32_t n_steps, double cfl /* <= 0: fixed dt */, double *t_out, double *dt_last_out);
+int mlb_take_step_distributed_host(mlb_ctx *ctx, double cfl, double *U_owned_inout /* [n_owned][4], mlb_owned_cells order */,
+                                   double *dt_out);
+
 /* ---- stateless device kernels for known-answer tests of the plug-in interfaces */
 /* RiemannSolver::calc_flux (numerics/riemann_solver.h:85-90); L/R rows = rho,u,v,p,h */
 int mlb_riemann_flux(int32_t device, int32_t riemann, int32_t fp_mode, uint64_t n, const double *n_unit /* [n][2] */,
@@ -247,6 +287,9 @@ int mlb_compute_primitives(int32_t device, int32_t fp_mode, const mlb_physics *p
  *   and the "teno:*" tables of mlb_get_array (reference CSR layout; unpartitioned plans only). */
 int mlb_plan_create(mlb_plan **out, const mlb_mesh *mesh, const mlb_numerics *numerics, const mlb_bc *bcs, int32_t n_bcs,
                     const int32_t *part, const mlb_parallel *parallel);
+/* the plan of a rank-local mesh (see mlb_create_local); cell ids in its arrays are in the LOCAL mesh's numbering */
+int mlb_plan_create_local(mlb_plan **out, const mlb_mesh *local_mesh, const mlb_numerics *numerics, const mlb_bc *bcs,
+                          int32_t n_bcs, const int32_t *part_local, const mlb_parallel *parallel, const mlb_local_mesh *local);
 int mlb_plan_get(mlb_plan *plan, const char *name, void *out, uint64_t *nbytes);
 void mlb_plan_destroy(mlb_plan *plan);
 

@@ -12,7 +12,9 @@ import numpy as np
 from . import _abi
 from ._abi import BASIS, BC, FP, INTEGRATOR, MESH, RECON, RENUMBER, RIEMANN, build, lib  # noqa: F401
 
-__all__ = ["Mesh", "Solver", "Plan", "riemann_flux", "compute_primitives", "partition", "set_host_threads", "build", "lib"]
+__all__ = ["Mesh", "Solver", "Plan", "riemann_flux", "compute_primitives", "partition", "partition_coords", "comm_unique_id",
+           "set_host_threads", "build", "lib"]
+COMM_ID_BYTES = 128
 
 DEFAULT_GAS = dict(gamma=1.4, p_ref=101325.0, T_ref=298.15, rho_ref=1.225, p_min=-1e20, p_max=1e20)
 _MESH_KEYS = ["node_coords", "offsets_nodes_of_cell", "nodes_of_cell", "offsets_faces_of_cell", "faces_of_cell",
@@ -158,6 +160,23 @@ def partition(mesh, n_parts):
     return part
 
 
+def partition_coords(cell_xy, n_parts):
+    """The same partition from the cell centroids alone ([n][2]); what a rank that holds only its part of the mesh calls."""
+    xy = np.ascontiguousarray(cell_xy, dtype=np.float64).reshape(-1, 2)
+    part = np.empty(xy.shape[0], dtype=np.int32)
+    if lib().mlb_partition_coords(xy.shape[0], _ptr(xy), n_parts, _ptr(part)):
+        raise MallardError(_last_error())
+    return part
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library (rank 0 calls it and ships the bytes to every rank)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    if lib().mlb_comm_unique_id(buf):
+        raise MallardError(_last_error())
+    return bytes(buf.raw)
+
+
 def _numerics(recon, riemann, integrator, basis, order, factor, quad_cell, quad_face, fp_mode, renumber, teno_fixed, keep_rhs):
     for table, key, what in ((RECON, recon, "face reconstruction"), (RIEMANN, riemann, "Riemann solver"),
                              (INTEGRATOR, integrator, "time integrator")):
@@ -177,6 +196,17 @@ def _physics(gas):
     return _abi.Physics(g["gamma"], g["p_ref"], g["T_ref"], g["rho_ref"], g["p_min"], g["p_max"])
 
 
+def _local_struct(local, mesh):
+    """mlb_local_mesh from dict(global_ids, n_global, cell0_nodes); returns (struct, keepalive)."""
+    gid = np.ascontiguousarray(local["global_ids"], dtype=np.uint32)
+    assert len(gid) == mesh.n_cells
+    lm = _abi.LocalMesh()
+    lm.n_global_cells, lm.global_cell_ids = int(local["n_global"]), _ptr(gid)
+    for i in range(6):
+        lm.cell0_nodes[i] = float(local["cell0_nodes"][i])
+    return lm, gid
+
+
 class Plan:
     """The mesh preprocessor's output alone (host only; no device needed): renumbering, slot tables, TENO tables."""
 
@@ -187,7 +217,7 @@ class Plan:
            "teno:offsets_reconstruction_matrices": np.uint32}
 
     def __init__(self, mesh, recon="FO", basis="legendre", order=3, factor=2.0, quad_cell_order=0, quad_face_order=0, bcs=(),
-                 renumber="rcm", part=None, rank=0, n_ranks=1, fp_mode="strict"):
+                 renumber="rcm", part=None, rank=0, n_ranks=1, fp_mode="strict", local=None):
         num = _numerics(recon, "HLLC", "SSPRK3", basis, order, factor, quad_cell_order, quad_face_order, fp_mode, renumber, False, False)
         keep = []
         cb = (_abi.Bc * max(1, len(bcs)))()
@@ -201,7 +231,12 @@ class Plan:
         h = C.c_void_p()
         self._h = None
         pp = None if part is None else np.ascontiguousarray(part, dtype=np.int32)
-        if lib().mlb_plan_create(C.byref(h), C.byref(v), C.byref(num), cb, len(bcs), _ptr(pp), C.byref(par)):
+        if local is not None:
+            lm, lkeep = _local_struct(local, mesh)
+            rc = lib().mlb_plan_create_local(C.byref(h), C.byref(v), C.byref(num), cb, len(bcs), _ptr(pp), C.byref(par), C.byref(lm))
+        else:
+            rc = lib().mlb_plan_create(C.byref(h), C.byref(v), C.byref(num), cb, len(bcs), _ptr(pp), C.byref(par))
+        if rc:
             raise MallardError(_last_error())
         self._h = h
         s = self.get("sizes")
@@ -233,7 +268,9 @@ class Solver:
 
     def __init__(self, mesh, recon="FO", riemann="HLLC", integrator="SSPRK3", gas=None, basis="legendre", order=3, factor=2.0,
                  quad_cell_order=0, quad_face_order=0, bcs=(), fp_mode="strict", renumber="rcm", teno_fixed=False,
-                 keep_stage_rhs=True, device=0, part=None, rank=0, n_ranks=1):
+                 keep_stage_rhs=True, device=0, part=None, rank=0, n_ranks=1, local=None):
+        """part: partition vector over the cells of `mesh` (multi-GPU).  local: `mesh` is this rank's part of a larger mesh
+        (local_mesh.extract_local / synthetic.jittered_tri_local): dict(global_ids, n_global, cell0_nodes) -> mlb_create_local."""
         self.mesh = mesh
         self.nc, self.nf = mesh.n_cells, mesh.n_faces
         self._h = None
@@ -266,6 +303,11 @@ class Solver:
         h = C.c_void_p()
         if part is None:
             rc = lib().mlb_create(C.byref(h), C.byref(v), C.byref(num), C.byref(phys), cb, len(bcs), C.byref(par))
+        elif local is not None:
+            part = np.ascontiguousarray(part, dtype=np.int32)
+            assert len(part) == mesh.n_cells
+            lm, lkeep = _local_struct(local, mesh)
+            rc = lib().mlb_create_local(C.byref(h), C.byref(v), _ptr(part), C.byref(lm), C.byref(num), C.byref(phys), cb, len(bcs), C.byref(par))
         else:
             part = np.ascontiguousarray(part, dtype=np.int32)
             rc = lib().mlb_create_partitioned(C.byref(h), C.byref(v), _ptr(part), C.byref(num), C.byref(phys), cb, len(bcs), C.byref(par))
@@ -389,6 +431,20 @@ class Solver:
         elif name == "teno:poly_indices":
             out = out.reshape(-1, 2)
         return out
+
+    # -- native multi-GPU driver (NCCL inside the library)
+    def comm_init(self, unique_id):
+        self._ok(lib().mlb_comm_init(self._h, C.c_char_p(unique_id)))
+
+    def run_distributed(self, n_steps, cfl=0.0):
+        t, dt = C.c_double(), C.c_double()
+        self._ok(lib().mlb_run_distributed(self._h, n_steps, cfl, C.byref(t), C.byref(dt)))
+        return t.value, dt.value
+
+    def take_step_distributed_host(self, U_owned, cfl=0.0):
+        dt = C.c_double()
+        self._ok(lib().mlb_take_step_distributed_host(self._h, cfl, _ptr(U_owned), C.byref(dt)))
+        return U_owned, dt.value
 
     # -- measurement
     def event_record(self, slot):

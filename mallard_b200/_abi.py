@@ -49,6 +49,10 @@ class Parallel(C.Structure):
     _fields_ = [("rank", C.c_int32), ("n_ranks", C.c_int32), ("device", C.c_int32)]
 
 
+class LocalMesh(C.Structure):
+    _fields_ = [("n_global_cells", C.c_uint32), ("global_cell_ids", C.c_void_p), ("cell0_nodes", C.c_double * 6)]
+
+
 # every symbol include/mallard_b200.h declares: name -> (restype, argtypes)
 VP, I32, U32, U64, DBL = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, C.c_double
 SYMBOLS = {
@@ -83,6 +87,12 @@ SYMBOLS = {
     "mlb_comm_stream": (VP, [VP]),
     "mlb_partition": (C.c_int, [C.POINTER(MeshView), I32, VP]),
     "mlb_create_partitioned": (C.c_int, [C.POINTER(VP), C.POINTER(MeshView), VP, C.POINTER(Numerics), C.POINTER(Physics), C.POINTER(Bc), I32, C.POINTER(Parallel)]),
+    "mlb_partition_coords": (C.c_int, [U64, VP, I32, VP]),
+    "mlb_create_local": (C.c_int, [C.POINTER(VP), C.POINTER(MeshView), VP, C.POINTER(LocalMesh), C.POINTER(Numerics), C.POINTER(Physics), C.POINTER(Bc), I32, C.POINTER(Parallel)]),
+    "mlb_comm_unique_id": (C.c_int, [VP]),
+    "mlb_comm_init": (C.c_int, [VP, VP]),
+    "mlb_run_distributed": (C.c_int, [VP, U32, DBL, C.POINTER(DBL), C.POINTER(DBL)]),
+    "mlb_take_step_distributed_host": (C.c_int, [VP, DBL, VP, C.POINTER(DBL)]),
     "mlb_halo_info": (C.c_int, [VP, C.POINTER(I32), VP, VP, VP]),
     "mlb_halo_recv_ids": (C.c_int, [VP, I32, VP]),
     "mlb_halo_set_send_ids": (C.c_int, [VP, I32, VP, VP, VP]),
@@ -103,6 +113,7 @@ SYMBOLS = {
     "mlb_riemann_flux": (C.c_int, [I32, I32, I32, U64, VP, VP, VP, DBL, VP]),
     "mlb_compute_primitives": (C.c_int, [I32, I32, C.POINTER(Physics), U64, VP, VP, VP]),
     "mlb_plan_create": (C.c_int, [C.POINTER(VP), C.POINTER(MeshView), C.POINTER(Numerics), C.POINTER(Bc), I32, VP, C.POINTER(Parallel)]),
+    "mlb_plan_create_local": (C.c_int, [C.POINTER(VP), C.POINTER(MeshView), C.POINTER(Numerics), C.POINTER(Bc), I32, VP, C.POINTER(Parallel), C.POINTER(LocalMesh)]),
     "mlb_plan_get": (C.c_int, [VP, C.c_char_p, VP, C.POINTER(U64)]),
     "mlb_plan_destroy": (None, [VP]),
     "mlb_host_mesh_generate": (C.c_int, [C.POINTER(VP), I32, U32, U32, DBL, DBL]),

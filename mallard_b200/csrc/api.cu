@@ -9,6 +9,7 @@
 #include <omp.h>
 
 #include "kernel_args.h"
+#include "nccl_dyn.h"
 
 using namespace mlb;
 
@@ -45,6 +46,13 @@ void require_device(int device) {
 }
 
 struct ProfileEntry { double ms = 0.0; uint64_t launches = 0; };
+
+#define NCCL_OK(expr)                                                                                              \
+    do {                                                                                                           \
+        ncclResult_t r_ = (expr);                                                                                  \
+        if (r_ != ncclSuccess)                                                                                     \
+            throw std::runtime_error(std::string("NCCL error: ") + nccl().GetErrorString(r_) + " at " #expr);      \
+    } while (0)
 
 }  // namespace
 
@@ -102,6 +110,11 @@ struct mlb_ctx {
     cudaEvent_t ev_state = nullptr, ev_halo = nullptr;
     bool halo_pending = false;         // an unpack has been enqueued that the compute stream has not waited for yet
     int stage_begun = -1;              // stage whose interior reconstruction is already enqueued (mlb_stage_begin)
+    // rank-local ingest: global id of every cell of the (local) mesh this context was created from; empty = the mesh is global
+    std::vector<uint32_t> global_ids;
+    // native multi-GPU driver (mlb_comm_init): one communicator for the per-stage neighbour exchange on comm_stream, a second
+    // (ncclCommSplit duplicate) for the per-step all-reduce of the spectral radius on the compute stream
+    ncclComm_t nccl_p2p = nullptr, nccl_coll = nullptr;
 
     // measurement
     cudaEvent_t ev[16] = {};
@@ -152,6 +165,11 @@ struct mlb_ctx {
     }
     ~mlb_ctx() {
         if (stream) cudaStreamSynchronize(stream);
+        if (comm_stream) cudaStreamSynchronize(comm_stream);
+        try {
+            if (nccl_coll) nccl().CommDestroy(nccl_coll);
+            if (nccl_p2p) nccl().CommDestroy(nccl_p2p);
+        } catch (...) {}
         for (auto & p : pending) { cudaEventDestroy(p.second.first); cudaEventDestroy(p.second.second); }
         for (void * p : owned_dev) cudaFree(p);
         if (d_stage) cudaFree(d_stage);
@@ -384,7 +402,7 @@ void build_tables_on_device(mlb_ctx & c) {
 }
 
 mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_numerics * numerics, const mlb_physics * physics,
-                      const mlb_bc * bcs, int32_t n_bcs, const mlb_parallel * par) {
+                      const mlb_bc * bcs, int32_t n_bcs, const mlb_parallel * par, const mlb_local_mesh * local = nullptr) {
     if (!mesh || !numerics || !physics) throw std::runtime_error("mlb_create: NULL argument");
     if (n_bcs > MAX_BCS) throw std::runtime_error("mlb_create: too many boundaries");
     std::unique_ptr<mlb_ctx> c(new mlb_ctx());
@@ -447,6 +465,18 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
         opt.device_tables = c->streaming && !(e && e[0] == '1') && teno_tables_device_supported(p, c->num.basis, 7 /* Dunavant rules have <= 7 points */);
     }
     opt.part = part; opt.rank = c->rank; opt.n_ranks = c->n_ranks;
+    if (local) {   // rank-local ingest: the mesh holds this rank's cells and enough ghost layers, in the global order
+        if (!local->global_cell_ids) throw std::runtime_error("mlb_create_local: global_cell_ids is NULL");
+        c->global_ids.assign(local->global_cell_ids, local->global_cell_ids + hm.nc);
+        for (uint32_t i = 1; i < hm.nc; i++)
+            if (c->global_ids[i] <= c->global_ids[i - 1]) throw std::runtime_error("mlb_create_local: global_cell_ids must be strictly ascending (the local numbering keeps the global order)");
+        if (hm.nc && c->global_ids.back() >= local->n_global_cells) throw std::runtime_error("mlb_create_local: global cell id out of range");
+        opt.psi_ref_tri = local->cell0_nodes;
+        opt.keep_ref_tables = false;
+    } else {
+        for (size_t f = 0; f < hm.nf; f++)
+            if (hm.cof[2 * f + 1] == CUT_FACE) throw std::runtime_error("mlb_create: cells_of_face holds a cut-face marker (-2); rank-local meshes go through mlb_create_local");
+    }
     preprocess(hm, c->num, bc_zones, opt, c->prep);
     Prep & P = c->prep;
     for (size_t i = 0; i < P.qf_x.size(); i++) { c->phys.qf_x[i] = P.qf_x[i]; c->phys.qf_w[i] = P.qf_w[i]; }
@@ -512,6 +542,156 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
     return c.release();
 }
 
+
+// Cell ids crossing the ABI are in the numbering of the mesh the context was created from; contexts created from a rank-local
+// mesh (mlb_create_local) exchange GLOBAL ids with their peers.
+uint32_t to_global(const mlb_ctx & c, uint32_t mesh_id) { return c.global_ids.empty() ? mesh_id : c.global_ids[mesh_id]; }
+uint32_t from_global(const mlb_ctx & c, uint32_t gid) {
+    if (c.global_ids.empty()) return gid < c.nc_ref ? gid : NO_FACE;
+    const auto it = std::lower_bound(c.global_ids.begin(), c.global_ids.end(), gid);
+    return (it != c.global_ids.end() && *it == gid) ? (uint32_t)(it - c.global_ids.begin()) : NO_FACE;
+}
+
+// What this rank must send: per peer (ascending), the cells the peer holds as ghosts, in the order of the peer's receive buffer.
+// A peer that only receives from this rank (TENO stencils are not symmetric) joins the peer list with an empty receive list,
+// which leaves the receive-buffer offsets unchanged.
+void set_send_ids(mlb_ctx & c, int32_t n_lists, const int32_t * peer_ranks, const uint64_t * counts, const uint32_t * ids) {
+    for (int l = 1; l < n_lists; l++)
+        if (peer_ranks[l] <= peer_ranks[l - 1]) throw std::runtime_error("halo: send lists must be in ascending peer order");
+    for (int l = 0; l < n_lists; l++) {
+        if (!counts[l] || std::find(c.peers.begin(), c.peers.end(), peer_ranks[l]) != c.peers.end()) continue;
+        const size_t at = std::lower_bound(c.peers.begin(), c.peers.end(), peer_ranks[l]) - c.peers.begin();
+        c.peers.insert(c.peers.begin() + at, peer_ranks[l]);
+        c.recv_counts.insert(c.recv_counts.begin() + at, 0);
+        c.recv_ref_ids.insert(c.recv_ref_ids.begin() + at, std::vector<uint32_t>());
+    }
+    std::vector<uint32_t> idx;
+    c.send_counts.assign(c.peers.size(), 0);
+    size_t off = 0;
+    for (int l = 0; l < n_lists; l++) {
+        auto it = std::find(c.peers.begin(), c.peers.end(), peer_ranks[l]);
+        for (uint64_t k = 0; k < counts[l]; k++) {
+            const uint32_t ref = from_global(c, ids[off + k]);
+            const uint32_t loc = ref != NO_FACE ? c.prep.iperm_cells[ref] : NO_FACE;
+            if (loc == NO_FACE || loc >= c.prep.N_owned) throw std::runtime_error("halo: peer requested a cell this rank does not own");
+            idx.push_back(loc);
+        }
+        if (it != c.peers.end()) c.send_counts[it - c.peers.begin()] = counts[l];
+        off += counts[l];
+    }
+    c.n_send = idx.size();
+    c.d_send_idx = c.upload(idx);
+    c.d_send_buf = c.alloc<double>(4 * std::max<size_t>(c.n_send, 1));
+    CUDA_OK(cudaStreamSynchronize(c.stream));
+}
+
+void halo_pack(mlb_ctx & c, int buf) {
+    cudaStream_t cs = c.comm_stream ? c.comm_stream : c.stream;
+    if (c.comm_stream) {                  // everything enqueued on the compute stream so far produces the state to be sent
+        CUDA_OK(cudaEventRecord(c.ev_state, c.stream));
+        CUDA_OK(cudaStreamWaitEvent(cs, c.ev_state, 0));
+    }
+    launch_gather(c.U[buf], c.d_send_idx, (uint32_t)c.n_send, c.prep.Npad, c.d_send_buf, cs);
+    c.launches++;
+    CUDA_OK(cudaGetLastError());
+}
+
+void halo_unpack(mlb_ctx & c, int buf, bool first_stage) {
+    cudaStream_t cs = c.comm_stream ? c.comm_stream : c.stream;
+    launch_scatter(c.d_recv_buf, c.d_recv_idx, (uint32_t)c.n_recv, c.prep.Npad, c.U[buf], cs);
+    c.launches++;
+    if (first_stage && c.prep.N > c.prep.N_owned) {   // ghosts' primitives for the CFL kernel (update_primitives of their owners)
+        const uint32_t off = c.prep.N_owned & ~31u;    // keep the SoA column alignment
+        c.kt->primitives_soa(c.gas, c.prep.N - off, c.prep.Npad, c.U[buf] + 4 * (size_t)off, c.prim + off, cs);
+        c.launches++;
+    }
+    CUDA_OK(cudaGetLastError());
+    if (c.comm_stream) { CUDA_OK(cudaEventRecord(c.ev_halo, cs)); c.halo_pending = true; }
+}
+
+// ---- native multi-GPU driver: NCCL over NVLink, no host code between the stages of a step -----------------------------------
+void require_comm(const mlb_ctx & c) {
+    if (!c.nccl_p2p) throw std::runtime_error("the context has no communicator: call mlb_comm_init first");
+}
+
+// pack -> grouped ncclSend / ncclRecv between the library's device buffers -> unpack, all on the communication stream
+void nccl_exchange(mlb_ctx & c, int buf, bool first_stage) {
+    const NcclApi & N = nccl();
+    halo_pack(c, buf);
+    NCCL_OK(N.GroupStart());
+    size_t so = 0, ro = 0;
+    for (size_t i = 0; i < c.peers.size(); i++) {
+        const size_t sc = 4 * (size_t)c.send_counts[i], rc = 4 * (size_t)c.recv_counts[i];
+        if (rc) NCCL_OK(N.Recv(c.d_recv_buf + ro, rc, ncclDouble, c.peers[i], c.nccl_p2p, c.comm_stream));
+        if (sc) NCCL_OK(N.Send(c.d_send_buf + so, sc, ncclDouble, c.peers[i], c.nccl_p2p, c.comm_stream));
+        so += sc; ro += rc;
+    }
+    NCCL_OK(N.GroupEnd());
+    halo_unpack(c, buf, first_stage);
+}
+
+// One time step over the partitioned mesh (mallard_b200/parallel.py documents the same schedule):
+//   communication stream:  pack -> send/recv -> unpack                                                   (per stage)
+//   compute stream:        reconstruction of the INTERIOR tiles | wait(unpack) | rim tiles, fluxes, residual + RK update
+//                          stage 0 also: local max spectral radius -> ncclAllReduce(max) -> dt, between the two halves
+void do_step_distributed(mlb_ctx & c, double cfl) {
+    const NcclApi & N = nccl();
+    const auto plan = make_plan(c);
+    for (size_t st = 0; st < plan.size(); st++) {
+        nccl_exchange(c, plan[st].in, st == 0);
+        if (c.teno && !c.has_override && interior_tiles(c)) { run_recon(c, c.U[plan[st].in], 1); c.stage_begun = (int)st; }
+        if (st == 0 && cfl > 0.0) {
+            do_calc_dt(c, -1.0);           // rank-local maximum; waits for the unpack (the CFL kernel reads the ghosts' primitives)
+            NCCL_OK(N.AllReduce(c.scal + SC_MAX_SR, c.scal + SC_MAX_SR, 1, ncclDouble, ncclMax, c.nccl_coll, c.stream));
+            launch_apply_dt(c.scal, c.max_bits, cfl, 0.0, 0, c.stream);
+            c.launches++;
+        }
+        run_stage(c, plan[st], false, nullptr);
+    }
+    finish_plan(c, plan);
+}
+
+// Every rank tells every peer which of the peer's cells it holds as ghosts (global / mesh ids, in receive-buffer order): an
+// all-gather of the count matrix, then one grouped send/recv of the id lists.  Collective over the communicator.
+void exchange_halo_plan(mlb_ctx & c) {
+    const NcclApi & N = nccl();
+    const int n = c.n_ranks;
+    std::vector<uint64_t> want((size_t)n, 0), all((size_t)n * n, 0);
+    for (size_t i = 0; i < c.peers.size(); i++) want[c.peers[i]] = c.recv_counts[i];
+    uint64_t * d_want = dev_upload(want, c.stream), * d_all = dev_alloc<uint64_t>((size_t)n * n);
+    NCCL_OK(N.AllGather(d_want, d_all, (size_t)n, ncclUint64, c.nccl_coll, c.stream));
+    CUDA_OK(cudaMemcpyAsync(all.data(), d_all, all.size() * 8, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_OK(cudaStreamSynchronize(c.stream));
+    std::vector<uint32_t> out_ids;
+    for (size_t i = 0; i < c.peers.size(); i++)
+        for (uint32_t id : c.recv_ref_ids[i]) out_ids.push_back(to_global(c, id));
+    std::vector<int32_t> from;
+    std::vector<uint64_t> counts;
+    size_t n_in = 0;
+    for (int p = 0; p < n; p++) {
+        const uint64_t k = all[(size_t)p * n + c.rank];      // what rank p receives from this rank
+        if (p != c.rank && k) { from.push_back(p); counts.push_back(k); n_in += k; }
+    }
+    uint32_t * d_out = dev_upload(out_ids, c.stream), * d_in = dev_alloc<uint32_t>(n_in);
+    NCCL_OK(N.GroupStart());
+    size_t off = 0;
+    for (size_t i = 0; i < c.peers.size(); i++) {
+        if (c.recv_counts[i]) NCCL_OK(N.Send(d_out + off, c.recv_counts[i], ncclUint32, c.peers[i], c.nccl_p2p, c.stream));
+        off += c.recv_counts[i];
+    }
+    off = 0;
+    for (size_t l = 0; l < from.size(); l++) {
+        NCCL_OK(N.Recv(d_in + off, counts[l], ncclUint32, from[l], c.nccl_p2p, c.stream));
+        off += counts[l];
+    }
+    NCCL_OK(N.GroupEnd());
+    std::vector<uint32_t> in_ids(n_in);
+    if (n_in) CUDA_OK(cudaMemcpyAsync(in_ids.data(), d_in, n_in * 4, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_OK(cudaStreamSynchronize(c.stream));
+    cudaFree(d_want); cudaFree(d_all); cudaFree(d_out); cudaFree(d_in);
+    set_send_ids(c, (int32_t)from.size(), from.data(), counts.data(), in_ids.data());
+}
+
 }  // namespace
 
 #define API_BEGIN(ctx)  try { if (!(ctx)) throw std::runtime_error("NULL context");
@@ -539,20 +719,38 @@ int mlb_create(mlb_ctx ** out, const mlb_mesh * mesh, const mlb_numerics * numer
     API_END(none)
 }
 
+static mlb_ctx * create_with_halo(const mlb_mesh * mesh, const int32_t * part, const mlb_numerics * numerics, const mlb_physics * physics,
+                                  const mlb_bc * bcs, int32_t n_bcs, const mlb_parallel * parallel, const mlb_local_mesh * local) {
+    mlb_ctx * c = create_impl(mesh, part, numerics, physics, bcs, n_bcs, parallel, local);
+    try {
+        std::vector<uint32_t> recv_idx;
+        halo_recv_lists(c->prep, part, c->peers, c->recv_counts, c->recv_ref_ids, recv_idx);
+        c->n_recv = recv_idx.size();
+        c->d_recv_idx = c->upload(recv_idx);
+        c->d_recv_buf = c->alloc<double>(4 * std::max<size_t>(c->n_recv, 1));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+    } catch (...) { delete c; throw; }
+    return c;
+}
+
 int mlb_create_partitioned(mlb_ctx ** out, const mlb_mesh * mesh, const int32_t * part, const mlb_numerics * numerics,
                            const mlb_physics * physics, const mlb_bc * bcs, int32_t n_bcs, const mlb_parallel * parallel) {
     mlb_ctx * none = nullptr;
     API_BEGIN0(none)
     if (!out || !part || !parallel) throw std::runtime_error("mlb_create_partitioned: NULL argument");
     *out = nullptr;
-    mlb_ctx * c = create_impl(mesh, part, numerics, physics, bcs, n_bcs, parallel);
-    std::vector<uint32_t> recv_idx;
-    halo_recv_lists(c->prep, part, c->peers, c->recv_counts, c->recv_ref_ids, recv_idx);
-    c->n_recv = recv_idx.size();
-    c->d_recv_idx = c->upload(recv_idx);
-    c->d_recv_buf = c->alloc<double>(4 * std::max<size_t>(c->n_recv, 1));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
-    *out = c;
+    *out = create_with_halo(mesh, part, numerics, physics, bcs, n_bcs, parallel, nullptr);
+    API_END(none)
+}
+
+int mlb_create_local(mlb_ctx ** out, const mlb_mesh * local_mesh, const int32_t * part_local, const mlb_local_mesh * local,
+                     const mlb_numerics * numerics, const mlb_physics * physics, const mlb_bc * bcs, int32_t n_bcs,
+                     const mlb_parallel * parallel) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!out || !part_local || !parallel || !local) throw std::runtime_error("mlb_create_local: NULL argument");
+    *out = nullptr;
+    *out = create_with_halo(local_mesh, part_local, numerics, physics, bcs, n_bcs, parallel, local);
     API_END(none)
 }
 
@@ -964,42 +1162,13 @@ int mlb_halo_recv_ids(mlb_ctx * c, int32_t peer_index, uint32_t * ref_ids_out) {
     API_BEGIN(c)
     if (peer_index < 0 || peer_index >= (int)c->recv_ref_ids.size()) throw std::runtime_error("bad peer index");
     const auto & v = c->recv_ref_ids[peer_index];
-    if (ref_ids_out) std::memcpy(ref_ids_out, v.data(), v.size() * 4);
+    if (ref_ids_out) for (size_t i = 0; i < v.size(); i++) ref_ids_out[i] = to_global(*c, v[i]);
     API_END(c)
 }
 int mlb_halo_set_send_ids(mlb_ctx * c, int32_t n_lists, const int32_t * peer_ranks, const uint64_t * counts, const uint32_t * ref_ids) {
     API_BEGIN(c)
     CUDA_OK(cudaSetDevice(c->device));
-    // lists must be given in ascending peer order (the send buffer is laid out peer by peer in that order).  A peer that
-    // only receives from this rank (TENO stencils are not symmetric) joins the peer list with an empty receive list,
-    // which leaves the receive-buffer offsets unchanged.
-    for (int l = 1; l < n_lists; l++)
-        if (peer_ranks[l] <= peer_ranks[l - 1]) throw std::runtime_error("halo: send lists must be in ascending peer order");
-    for (int l = 0; l < n_lists; l++) {
-        if (!counts[l] || std::find(c->peers.begin(), c->peers.end(), peer_ranks[l]) != c->peers.end()) continue;
-        const size_t at = std::lower_bound(c->peers.begin(), c->peers.end(), peer_ranks[l]) - c->peers.begin();
-        c->peers.insert(c->peers.begin() + at, peer_ranks[l]);
-        c->recv_counts.insert(c->recv_counts.begin() + at, 0);
-        c->recv_ref_ids.insert(c->recv_ref_ids.begin() + at, std::vector<uint32_t>());
-    }
-    std::vector<uint32_t> idx;
-    c->send_counts.assign(c->peers.size(), 0);
-    size_t off = 0;
-    for (int l = 0; l < n_lists; l++) {
-        auto it = std::find(c->peers.begin(), c->peers.end(), peer_ranks[l]);
-        for (uint64_t k = 0; k < counts[l]; k++) {
-            const uint32_t ref = ref_ids[off + k];
-            const uint32_t loc = ref < c->nc_ref ? c->prep.iperm_cells[ref] : NO_FACE;
-            if (loc == NO_FACE || loc >= c->prep.N_owned) throw std::runtime_error("halo: peer requested a cell this rank does not own");
-            idx.push_back(loc);
-        }
-        if (it != c->peers.end()) c->send_counts[it - c->peers.begin()] = counts[l];
-        off += counts[l];
-    }
-    c->n_send = idx.size();
-    c->d_send_idx = c->upload(idx);
-    c->d_send_buf = c->alloc<double>(4 * std::max<size_t>(c->n_send, 1));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
+    set_send_ids(*c, n_lists, peer_ranks, counts, ref_ids);
     API_END(c)
 }
 int mlb_halo_buffers(mlb_ctx * c, void ** send_dev, void ** recv_dev) {
@@ -1016,31 +1185,13 @@ static int stage_input_buffer(mlb_ctx * c, int32_t stage) {
 int mlb_halo_pack(mlb_ctx * c, int32_t stage) {
     API_BEGIN(c)
     CUDA_OK(cudaSetDevice(c->device));
-    const int b = stage_input_buffer(c, stage);
-    cudaStream_t cs = c->comm_stream ? c->comm_stream : c->stream;
-    if (c->comm_stream) {                  // everything enqueued on the compute stream so far produces the state to be sent
-        CUDA_OK(cudaEventRecord(c->ev_state, c->stream));
-        CUDA_OK(cudaStreamWaitEvent(cs, c->ev_state, 0));
-    }
-    launch_gather(c->U[b], c->d_send_idx, (uint32_t)c->n_send, c->prep.Npad, c->d_send_buf, cs);
-    c->launches++;
-    CUDA_OK(cudaGetLastError());
+    halo_pack(*c, stage_input_buffer(c, stage));
     API_END(c)
 }
 int mlb_halo_unpack(mlb_ctx * c, int32_t stage) {
     API_BEGIN(c)
     CUDA_OK(cudaSetDevice(c->device));
-    const int b = stage_input_buffer(c, stage);
-    cudaStream_t cs = c->comm_stream ? c->comm_stream : c->stream;
-    launch_scatter(c->d_recv_buf, c->d_recv_idx, (uint32_t)c->n_recv, c->prep.Npad, c->U[b], cs);
-    c->launches++;
-    if (stage == 0 && c->prep.N > c->prep.N_owned) {   // ghosts' primitives for the CFL kernel (update_primitives of their owners)
-        const uint32_t off = c->prep.N_owned & ~31u;    // keep the SoA column alignment
-        c->kt->primitives_soa(c->gas, c->prep.N - off, c->prep.Npad, c->U[b] + 4 * (size_t)off, c->prim + off, cs);
-        c->launches++;
-    }
-    CUDA_OK(cudaGetLastError());
-    if (c->comm_stream) { CUDA_OK(cudaEventRecord(c->ev_halo, cs)); c->halo_pending = true; }
+    halo_unpack(*c, stage_input_buffer(c, stage), stage == 0);
     API_END(c)
 }
 int mlb_n_stages(const mlb_ctx * c) { return c ? c->n_stages : 0; }
@@ -1132,32 +1283,137 @@ int mlb_owned_cells(mlb_ctx * c, uint32_t * n_owned, uint32_t * cells_out) {
     API_END(c)
 }
 
-// Recursive coordinate bisection on cell centroids (deterministic; ties broken by cell id).
+// ---- native multi-GPU driver ------------------------------------------------------------------------------------------------
+int mlb_comm_unique_id(void * id_out) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!id_out) throw std::runtime_error("mlb_comm_unique_id: NULL argument");
+    static_assert(sizeof(ncclUniqueId) == MLB_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NCCL_OK(nccl().GetUniqueId(&id));
+    std::memcpy(id_out, &id, sizeof(id));
+    API_END(none)
+}
+
+int mlb_comm_init(mlb_ctx * c, const void * id) {
+    API_BEGIN(c)
+    if (!id) throw std::runtime_error("mlb_comm_init: NULL id");
+    if (c->n_ranks < 2 || !c->comm_stream) throw std::runtime_error("mlb_comm_init: the context is not partitioned");
+    if (c->nccl_p2p) throw std::runtime_error("mlb_comm_init: the context already has a communicator");
+    CUDA_OK(cudaSetDevice(c->device));
+    const NcclApi & N = nccl();
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, sizeof(uid));
+    NCCL_OK(N.CommInitRank(&c->nccl_p2p, c->n_ranks, uid, c->rank));
+    NCCL_OK(N.CommSplit(c->nccl_p2p, 0, c->rank, &c->nccl_coll, nullptr));
+    exchange_halo_plan(*c);
+    API_END(c)
+}
+
+int mlb_run_distributed(mlb_ctx * c, uint32_t n_steps, double cfl, double * t_out, double * dt_last_out) {
+    API_BEGIN(c)
+    CUDA_OK(cudaSetDevice(c->device));
+    require_comm(*c);
+    if (!(cfl > 0.0) && n_steps) require_dt(*c);
+    // As in mlb_run: one eager step (NCCL sets up its connections, kernels get their attributes), then the step is captured -
+    // both streams, the grouped send/recv and the all-reduce included - and replayed as one CUDA graph per step.
+    static const bool graphs = [] { const char * e = getenv("MLB_RUN_GRAPH"); return !(e && e[0] == '0'); }();
+    uint32_t done = 0;
+    if (graphs && !c->profiling && n_steps >= 4 && c->num.integrator != MLB_INTEGRATOR_FE) {
+        do_step_distributed(*c, cfl);
+        done = 1;
+        const uint64_t l0 = c->launches;
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ge = nullptr;
+        CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+        bool ok = true;
+        std::string why;
+        try { do_step_distributed(*c, cfl); } catch (const std::exception & e) { ok = false; why = e.what(); }
+        const cudaError_t ec = cudaStreamEndCapture(c->stream, &g);
+        const uint64_t per_step = c->launches - l0;
+        c->launches = l0;                             // nothing ran during the capture
+        if (ok && ec == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) {
+            for (; done < n_steps; done++) { CUDA_OK(cudaGraphLaunch(ge, c->stream)); c->launches += per_step; }
+            c->graph_replays += n_steps - 1;
+        } else {
+            cudaGetLastError();
+            c->halo_pending = false; c->stage_begun = -1;
+            if (ge) cudaGraphExecDestroy(ge);
+            if (g) cudaGraphDestroy(g);
+            // every rank must issue the same collectives: a rank that cannot capture cannot silently fall back on its own
+            throw std::runtime_error("mlb_run_distributed: the step could not be captured into a CUDA graph (" +
+                                     (why.empty() ? std::string(cudaGetErrorString(ec)) : why) + "); set MLB_RUN_GRAPH=0 on every rank");
+        }
+        if (ge) cudaGraphExecDestroy(ge);
+        if (g) cudaGraphDestroy(g);
+    }
+    for (; done < n_steps; done++) do_step_distributed(*c, cfl);
+    if (c->comm_stream) CUDA_OK(cudaStreamSynchronize(c->comm_stream));
+    double sc[SC_COUNT];
+    read_scalars(*c, sc);
+    if (t_out) *t_out = sc[SC_T];
+    if (dt_last_out) *dt_last_out = sc[SC_DT];
+    if (sc[SC_DT] < 0.0) throw std::runtime_error("dt negative: " + std::to_string(sc[SC_DT]) + ".");
+    API_END(c)
+}
+
+int mlb_take_step_distributed_host(mlb_ctx * c, double cfl, double * U_owned_inout, double * dt_out) {
+    API_BEGIN(c)
+    if (!U_owned_inout) throw std::runtime_error("mlb_take_step_distributed_host: NULL buffer");
+    CUDA_OK(cudaSetDevice(c->device));
+    require_comm(*c);
+    if (!(cfl > 0.0)) require_dt(*c);
+    const size_t n = (size_t)c->prep.N_owned * 4;
+    // owned cells are the first N_owned rows of the AoS state: the host buffer is copied straight into / out of it
+    CUDA_OK(cudaMemcpyAsync(c->U[c->cur], U_owned_inout, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->kt->primitives_soa(c->gas, c->prep.N_owned, c->prep.Npad, c->U[c->cur], c->prim, c->stream);
+    c->launches++;
+    do_step_distributed(*c, cfl);
+    CUDA_OK(cudaMemcpyAsync(U_owned_inout, c->U[c->cur], n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    double sc[SC_COUNT];
+    read_scalars(*c, sc);
+    if (dt_out) *dt_out = sc[SC_DT];
+    if (sc[SC_DT] < 0.0) throw std::runtime_error("dt negative: " + std::to_string(sc[SC_DT]) + ".");
+    API_END(c)
+}
+
+// Recursive coordinate bisection on cell centroids (deterministic: the order is (coordinate, cell id), a strict total order,
+// so the two halves of every cut are uniquely defined whatever the selection algorithm visits first).
+static void rcb(std::vector<std::pair<double, uint32_t>> & key, const double * xy, uint32_t * ids, size_t lo, size_t hi, int32_t p0, int32_t np,
+                int32_t * part_out) {
+    if (np == 1) { for (size_t i = lo; i < hi; i++) part_out[ids[i]] = p0; return; }
+    double mn[2] = {1e300, 1e300}, mx[2] = {-1e300, -1e300};
+    for (size_t i = lo; i < hi; i++)
+        for (int d = 0; d < 2; d++) { const double x = xy[2 * (size_t)ids[i] + d]; mn[d] = std::min(mn[d], x); mx[d] = std::max(mx[d], x); }
+    const int d = (mx[1] - mn[1] > mx[0] - mn[0]) ? 1 : 0;
+    const int32_t npl = np / 2;
+    const size_t mid = lo + (size_t)((double)(hi - lo) * npl / np);
+    for (size_t i = lo; i < hi; i++) key[i] = {xy[2 * (size_t)ids[i] + d], ids[i]};     // contiguous keys: the selection stays in cache lines
+    std::nth_element(key.begin() + lo, key.begin() + mid, key.begin() + hi);
+    for (size_t i = lo; i < hi; i++) ids[i] = key[i].second;
+    rcb(key, xy, ids, lo, mid, p0, npl, part_out);
+    rcb(key, xy, ids, mid, hi, p0 + npl, np - npl, part_out);
+}
+
+int mlb_partition_coords(uint64_t n_cells, const double * cell_xy, int32_t n_parts, int32_t * part_out) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!cell_xy || !part_out || n_parts < 1 || n_cells > 0xFFFFFFFEull) throw std::runtime_error("mlb_partition_coords: bad argument");
+    std::vector<uint32_t> ids(n_cells);
+    for (uint64_t i = 0; i < n_cells; i++) ids[i] = (uint32_t)i;
+    std::vector<std::pair<double, uint32_t>> key(n_cells);
+    rcb(key, cell_xy, ids.data(), 0, n_cells, 0, n_parts, part_out);
+    API_END(none)
+}
+
 int mlb_partition(const mlb_mesh * mesh, int32_t n_parts, int32_t * part_out) {
     mlb_ctx * none = nullptr;
     API_BEGIN0(none)
     if (!mesh || !part_out || n_parts < 1) throw std::runtime_error("mlb_partition: bad argument");
+    if (mesh->cell_coords) return mlb_partition_coords(mesh->n_cells, mesh->cell_coords, n_parts, part_out);
     HostMesh hm;
-    host_mesh_from_view(hm, *mesh);
-    std::vector<uint32_t> ids(hm.nc);
-    for (uint32_t i = 0; i < hm.nc; i++) ids[i] = i;
-    struct Job { size_t lo, hi; int32_t p0, np; };
-    std::vector<Job> stack{{0, hm.nc, 0, n_parts}};
-    while (!stack.empty()) {
-        Job j = stack.back(); stack.pop_back();
-        if (j.np == 1) { for (size_t i = j.lo; i < j.hi; i++) part_out[ids[i]] = j.p0; continue; }
-        double mn[2] = {1e300, 1e300}, mx[2] = {-1e300, -1e300};
-        for (size_t i = j.lo; i < j.hi; i++)
-            for (int d = 0; d < 2; d++) { const double x = hm.cell_xy[2 * (size_t)ids[i] + d]; mn[d] = std::min(mn[d], x); mx[d] = std::max(mx[d], x); }
-        const int d = (mx[1] - mn[1] > mx[0] - mn[0]) ? 1 : 0;
-        const int32_t npl = j.np / 2;
-        const size_t mid = j.lo + (size_t)((double)(j.hi - j.lo) * npl / j.np);
-        std::nth_element(ids.begin() + j.lo, ids.begin() + mid, ids.begin() + j.hi, [&](uint32_t a, uint32_t b) {
-            const double xa = hm.cell_xy[2 * (size_t)a + d], xb = hm.cell_xy[2 * (size_t)b + d];
-            return xa != xb ? xa < xb : a < b; });
-        stack.push_back({j.lo, mid, j.p0, npl});
-        stack.push_back({mid, j.hi, j.p0 + npl, j.np - npl});
-    }
+    host_mesh_from_view(hm, *mesh);                    // centroids as Mesh::compute_cell_centroids makes them
+    return mlb_partition_coords(hm.nc, hm.cell_xy.data(), n_parts, part_out);
     API_END(none)
 }
 
@@ -1201,12 +1457,9 @@ int mlb_compute_primitives(int32_t device, int32_t fp_mode, const mlb_physics * 
 }
 
 // ---- host-only preprocessing plan (no device needed) ------------------------------------------------------------
-int mlb_plan_create(mlb_plan ** out, const mlb_mesh * mesh, const mlb_numerics * numerics, const mlb_bc * bcs, int32_t n_bcs,
-                    const int32_t * part, const mlb_parallel * parallel) {
-    mlb_ctx * none = nullptr;
-    API_BEGIN0(none)
-    if (!out || !mesh || !numerics) throw std::runtime_error("mlb_plan_create: NULL argument");
-    *out = nullptr;
+static mlb_plan * plan_create(const mlb_mesh * mesh, const mlb_numerics * numerics, const mlb_bc * bcs, int32_t n_bcs,
+                              const int32_t * part, const mlb_parallel * parallel, const mlb_local_mesh * local) {
+    if (!mesh || !numerics) throw std::runtime_error("mlb_plan_create: NULL argument");
     std::unique_ptr<mlb_plan> p(new mlb_plan());
     HostMesh hm;
     host_mesh_from_view(hm, *mesh);
@@ -1218,10 +1471,28 @@ int mlb_plan_create(mlb_plan ** out, const mlb_mesh * mesh, const mlb_numerics *
     opt.keep_ref_tables = numerics->recon == MLB_RECON_TENO && !part;
     opt.fast_tables = numerics->recon == MLB_RECON_TENO && numerics->fp_mode == MLB_FP_FAST;
     opt.part = part; opt.rank = parallel ? parallel->rank : 0; opt.n_ranks = parallel ? parallel->n_ranks : 1;
+    if (local) opt.psi_ref_tri = local->cell0_nodes;
     p->rank = opt.rank;
     if (part) p->part.assign(part, part + hm.nc);
     preprocess(hm, *numerics, zones, opt, p->prep);
-    *out = p.release();
+    return p.release();
+}
+int mlb_plan_create(mlb_plan ** out, const mlb_mesh * mesh, const mlb_numerics * numerics, const mlb_bc * bcs, int32_t n_bcs,
+                    const int32_t * part, const mlb_parallel * parallel) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!out) throw std::runtime_error("mlb_plan_create: NULL argument");
+    *out = nullptr;
+    *out = plan_create(mesh, numerics, bcs, n_bcs, part, parallel, nullptr);
+    API_END(none)
+}
+int mlb_plan_create_local(mlb_plan ** out, const mlb_mesh * local_mesh, const mlb_numerics * numerics, const mlb_bc * bcs, int32_t n_bcs,
+                          const int32_t * part_local, const mlb_parallel * parallel, const mlb_local_mesh * local) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!out || !part_local || !parallel || !local) throw std::runtime_error("mlb_plan_create_local: NULL argument");
+    *out = nullptr;
+    *out = plan_create(local_mesh, numerics, bcs, n_bcs, part_local, parallel, local);
     API_END(none)
 }
 int mlb_plan_get(mlb_plan * p, const char * name, void * out, uint64_t * nbytes) {

@@ -152,8 +152,7 @@ __device__ __forceinline__ void riemann_flux(double * F, double nx, double ny, c
 // FAST mode: the same wave-speed estimates and fluxes (numerics/riemann_solver.h:206-519) with the algebra arranged for the
 // FP64 pipe, which is what bounds the face kernel (a double-precision division or square root is a ~10-instruction
 // dependent chain): one reciprocal per state instead of four divisions, a^2 = gamma p (1/rho), a q = sqrt(gamma (1/rho)
-// (p + c (p* - p))) instead of sqrt(..) * sqrt(1 + c (p*/p - 1)), rho E taken from the conserved state instead of being
-// rebuilt from h, and only the side of the fan the face lies in is evaluated.  Differences to riemann_flux<RS>() are a
+// (p + c (p* - p))) instead of sqrt(..) * sqrt(1 + c (p*/p - 1)), and only the side of the fan the face lies in is evaluated.  Differences to riemann_flux<RS>() are a
 // few ulp (inside the 1e-12 per-step budget; tests/test_gpu_parity.py::test_riemann_*).  The rarely taken TRRS / TSRS
 // estimators stay out of line.
 // ---------------------------------------------------------------------------------------------------------------
@@ -163,9 +162,13 @@ __device__ __forceinline__ FaceCons face_cons(const GasParams & g, const double 
     FaceCons s;
     s.rho = U[0]; s.ir = 1.0 / U[0];
     s.u = U[1] * s.ir; s.v = U[2] * s.ir;
-    const double e = U[3] * s.ir - 0.5 * (s.u * s.u + s.v * s.v);
+    const double ke = 0.5 * (s.u * s.u + s.v * s.v);
+    const double e = U[3] * s.ir - ke;
     s.p = fmax(g.p_min, fmin(g.p_max, (g.gamma - 1.0) * s.rho * e));   // physics.h:842-845
-    s.E = U[3];
+    // rho E as the reference rebuilds it from h (flux_functor.h:140-149 -> riemann_solver.h): with reference-faithful TENO weights
+    //  a face state can be far outside the physical range, e - ke cancels, and U[3] itself would be a DIFFERENT
+    // (more accurate) number than the one the reference's flux sees
+    s.E = ((e + s.p * s.ir) + ke) * s.rho - s.p;
     return s;
 }
 __device__ __forceinline__ FaceCons face_cons(const FaceState & f) {   // ghost states arrive as (rho, u, v, p, h)

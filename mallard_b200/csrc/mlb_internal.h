@@ -50,6 +50,7 @@ constexpr int MAX_K = 55;       // (p+1)(p+2)/2 for p <= 9
 // Preprocessor output (all in LIBRARY numbering; perm arrays map back to the reference)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t NO_FACE = 0xFFFFFFFFu;
+constexpr int32_t CUT_FACE = -2;   // cells_of_face[f][1] of a rank-local mesh: the neighbour exists in the global mesh but not here
 constexpr int TILE = 8;         // cells per interleaved TENO table tile (one warp = 8 cells x 4 variables)
 
 // Streaming (FAST mode) table layout: tiles of FAST_CT = 8 cells; a tile belongs to ONE WARP, which streams it through its
@@ -129,6 +130,7 @@ struct PrepOptions {
     bool device_tables = false;       // ... and leave their matrices to the device (teno_tables.cu); the host emits ids + node coordinates
     const int32_t * part = nullptr;   // partition vector (reference numbering) or null
     int rank = 0, n_ranks = 1;
+    const double * psi_ref_tri = nullptr;   // rank-local meshes: node coordinates of the GLOBAL mesh's cell 0 (integral_psi_target)
 };
 
 void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<std::string> & bc_zones,

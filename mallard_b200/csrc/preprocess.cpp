@@ -216,6 +216,7 @@ struct RingSearch {
                 const uint32_t f = m.foc[m.ofc[c] + j];
                 const int32_t a = m.cof[2 * (size_t)f], b = m.cof[2 * (size_t)f + 1];
                 if (b == -1) continue;
+                if (b == CUT_FACE) throw std::runtime_error("rank-local mesh: the stencil search reached the cut (the mesh needs more ghost layers)");
                 nb[n++] = (a == (int32_t)c) ? (uint32_t)b : (uint32_t)a;
             }
             for (int a = 1; a < n; a++)                  // Mesh::h_neighbors_of_cell: sorted, unique (mesh.cpp:158-165)
@@ -672,6 +673,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
     P.slot_nslot.assign((size_t)n_slots * Np, 0);
     P.rhs_order.assign(Np, 0);
     if (teno) P.slot_fx.assign((size_t)n_slots * 4 * Np, 0.0);
+    std::string slot_err;
 #pragma omp parallel for schedule(static)
     for (int64_t ii = 0; ii < (int64_t)n_recon; ii++) {
         const uint32_t i = (uint32_t)ii, c = order[i];
@@ -680,6 +682,14 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
         for (int j = 0; j < nfc; j++) {
             const uint32_t f = m.foc[m.ofc[c] + j];
             const int32_t a = m.cof[2 * (size_t)f], b = m.cof[2 * (size_t)f + 1];
+            if (b == CUT_FACE) {   // rank-local mesh: fine on a first-ring ghost of a first-order context (its faces are never used)
+                if (i < n_owned || teno) {
+#pragma omp critical
+                    slot_err = "rank-local mesh: an owned or reconstructed ghost cell has a cut face (the mesh needs more ghost layers)";
+                }
+                keys[j] = UINT64_MAX;
+                continue;
+            }
             const uint32_t side = (a == (int32_t)c) ? 0u : 1u;
             const size_t at = (size_t)j * Np + i;
             if (iperm_faces[f] != NO_FACE) P.slot_face[at] = iperm_faces[f] | (side << 31);
@@ -714,6 +724,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
         P.rhs_order[i] = code;
     }
 
+    if (!slot_err.empty()) throw std::runtime_error(slot_err);
     tick("slots done");
     // ---- face-centred view of the same connectivity (face flux kernel)
     P.face_cl.assign(P.NFpad, 0u);
@@ -770,7 +781,13 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
             MatrixScratch w;
             const uint32_t self = 0;
             double a0;
-            integrate_basis_rows(m, T, 0, &self, 1, &a0, w);
+            if (opt.psi_ref_tri) {   // rank-local mesh: the caller hands over the GLOBAL mesh's cell 0
+                HostMesh one;
+                one.nc = 1; one.nn = 3;
+                one.node_xy.assign(opt.psi_ref_tri, opt.psi_ref_tri + 6);
+                one.onc = {0u, 3u}; one.noc = {0u, 1u, 2u};
+                integrate_basis_rows(one, T, 0, &self, 1, &a0, w);
+            } else integrate_basis_rows(m, T, 0, &self, 1, &a0, w);
             for (int k = 0; k < K; k++) T.psi_bar[k] = w.A[k] / a0;
         }
         std::string err;

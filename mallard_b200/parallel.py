@@ -11,9 +11,16 @@ conserved states (4 doubles per cell) are exchanged peer to peer, per step one d
 The preprocessor numbers the owned cells whose TENO stencils contain no ghost first, so the bulk of a stage (the
 table-streaming reconstruction kernel) runs while the ghost states are in flight.
 
-The communicator is torch.distributed: NCCL over NVLink/NVSwitch on the GPU box (send/recv straight from / into the
-library's device buffers, enqueued on the library's compute stream — no host staging, no host synchronisation inside a
-step); the exchange *plan* and the packing order are backend independent and are exercised with gloo in the CPU tests.
+Two drivers of the same schedule:
+  * native=True (what bench.py measures): the library's own NCCL driver (mlb_comm_init / mlb_run_distributed, csrc/api.cu) —
+    grouped ncclSend/ncclRecv between the library's device buffers, ncclAllReduce(max) of the device-resident spectral radius,
+    the whole step captured once and replayed as a CUDA graph: no host code between the stages of a step.  torch.distributed
+    only ships the 128-byte NCCL unique id to the ranks.
+  * native=False: the split-phase C ABI (mlb_halo_pack / mlb_stage_begin / mlb_stage ...) driven from here with
+    torch.distributed as the communicator — the same calls a host with its own communicator (MPI) would make; the exchange
+    *plan* and the packing order are backend independent and are exercised with gloo in the CPU tests.
+
+`local=` takes a rank-local mesh (local_mesh.extract_local / synthetic.jittered_tri_local): no rank ever holds the global mesh.
 """
 import numpy as np
 import torch
@@ -71,18 +78,33 @@ def device_tensor(ptr, n_doubles, device):
 class DistributedSolver:
     """Solver::run's loop over a partitioned mesh.  `part` is the partition vector in reference numbering."""
 
-    def __init__(self, mesh, part, rank=None, world=None, device=None, group=None, **solver_kw):
+    @classmethod
+    def from_solver(cls, solver, rank, world, device, group=None, local=None, native=True):
+        """Wraps a partitioned Solver that already exists (its creation may have to be retried collectively)."""
+        return cls(None, None, rank, world, device, group, local, native, solver=solver)
+
+    def __init__(self, mesh, part, rank=None, world=None, device=None, group=None, local=None, native=False, solver=None, **solver_kw):
+        """mesh / part: the global mesh and partition vector, or (local=dict(global_ids, n_global, cell0_nodes)) this rank's
+        part of the mesh and the owners of ITS cells."""
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
         self.device = torch.cuda.current_device() if device is None else device
         self.group = group
-        self.s = Solver(mesh, part=part, rank=self.rank, n_ranks=self.world, device=self.device, **solver_kw)
+        self.native = native
+        self.local = local
+        self.s = solver if solver is not None else Solver(mesh, part=part, rank=self.rank, n_ranks=self.world, device=self.device, local=local, **solver_kw)
         s = self.s
-        peers, _, rc = s.halo_info()
-        recv = [s.halo_recv_ids(i, rc[i]) for i in range(len(peers))]
-        send = exchange_plan(self.rank, self.world, peers, recv, group)
-        send_peers = sorted(send)
-        s.halo_set_send_ids(send_peers, [send[p] for p in send_peers])
+        if native:
+            from . import comm_unique_id
+            box = [comm_unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(box, src=0, group=group)       # 128 bytes; everything after this is inside the library
+            s.comm_init(box[0])
+        else:
+            peers, _, rc = s.halo_info()
+            recv = [s.halo_recv_ids(i, rc[i]) for i in range(len(peers))]      # ids of the mesh, or global ids (local ingest)
+            send = exchange_plan(self.rank, self.world, peers, recv, group)
+            send_peers = sorted(send)
+            s.halo_set_send_ids(send_peers, [send[p] for p in send_peers])
         self.peers, self.send_counts, self.recv_counts = s.halo_info()
         sp, rp = s.halo_buffers()
         self.send_t = device_tensor(sp, 4 * int(self.send_counts.sum()), self.device)
@@ -121,6 +143,9 @@ class DistributedSolver:
             s.stage(st)
 
     def run(self, n_steps, cfl=None):
+        if self.native:
+            self.s.run_distributed(n_steps, cfl if cfl is not None else 0.0)
+            return self.s.time()
         for _ in range(n_steps):
             self.step(cfl)
         self.s.finish_step()   # synchronises the compute stream
@@ -129,13 +154,20 @@ class DistributedSolver:
     def step_host(self, U_owned, cfl):
         """The take_step seam with HOST buffers for the rank's own cells: H2D of U_owned ([n_owned][4], owned_cells order),
         one step (halo exchanges and the dt all-reduce included), D2H of the result into U_owned."""
+        if self.native:
+            return self.s.take_step_distributed_host(U_owned, cfl)[0]
         self.s.set_owned(U_owned)
         self.step(cfl)
         return self.s.get_owned(U_owned)
 
     def gather_state(self):
         """Global state in reference numbering on every rank (owned cells of all ranks combined)."""
-        U = torch.from_numpy(self.s.get_state())      # zeros outside the owned cells
+        U = self.s.get_state()                        # zeros outside the owned cells
+        if self.local is not None:                    # local-mesh numbering -> global numbering
+            G = np.zeros((int(self.local["n_global"]), 4))
+            G[np.asarray(self.local["global_ids"], dtype=np.int64)] = U
+            U = G
+        U = torch.from_numpy(U)
         if self.world > 1:
             Ud = U.cuda(self.device)
             dist.all_reduce(Ud, op=dist.ReduceOp.SUM, group=self.group)

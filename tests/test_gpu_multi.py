@@ -24,11 +24,23 @@ def _state(xy):
 
 
 class Loopback:
-    """n rank contexts on one device; exchange = copies between their send/receive buffers."""
+    """n rank contexts on one device; exchange = copies between their send/receive buffers.
+    async_copies=True: nothing synchronises the host inside a step - the copies are enqueued on the RECEIVER's communication
+    stream (mlb_comm_stream), ordered against the sender's pack and the sender's next pack by events, exactly the ordering
+    NCCL's send/recv pairs provide; the interior reconstruction (mlb_stage_begin) then really runs concurrently with them.
+    locals_=[LocalPart...]: every context is created from its rank-local mesh (mlb_create_local)."""
 
-    def __init__(self, mesh, part, n, begin=True, **kw):
+    def __init__(self, mesh, part, n, begin=True, async_copies=False, locals_=None, **kw):
         self.begin = begin   # enqueue the interior reconstruction right after the exchange (mlb_stage_begin), or leave it to mlb_stage
-        self.s = [mb.Solver(mesh, part=part, rank=r, n_ranks=n, device=0, **kw) for r in range(n)]
+        self.async_copies = async_copies
+        self.locals_ = locals_
+        if locals_ is None:
+            self.s = [mb.Solver(mesh, part=part, rank=r, n_ranks=n, device=0, **kw) for r in range(n)]
+        else:
+            self.s = [mb.Solver(lp.mesh, part=lp.part_local, rank=r, n_ranks=n, device=0, local=lp.local, **kw) for r, lp in enumerate(locals_)]
+        self.cs = [torch.cuda.ExternalStream(s.comm_stream, device=0) for s in self.s]
+        self.ev_packed = [torch.cuda.Event() for _ in self.s]
+        self.ev_copied = [None for _ in self.s]
         wants = []
         for s in self.s:
             peers, _, rc = s.halo_info()
@@ -43,7 +55,35 @@ class Loopback:
             a, b = s.halo_buffers()
             self.buf.append((device_tensor(a, 4 * int(sc.sum()), 0), device_tensor(b, 4 * int(rc.sum()), 0)))
 
+    def exchange_async(self, stage):
+        for r, s in enumerate(self.s):
+            for e in self.ev_copied:                      # a send buffer is rewritten only after every reader of the last round is done
+                if e is not None:
+                    self.cs[r].wait_event(e)
+            s.halo_pack(stage)
+            self.ev_packed[r].record(self.cs[r])
+        for r, (peers, sc, rc) in enumerate(self.info):
+            ro = 0
+            with torch.cuda.stream(self.cs[r]):
+                for p, n_recv in zip(peers, rc):
+                    pp, psc, _ = self.info[int(p)]
+                    so = 4 * int(psc[:list(pp).index(r)].sum())
+                    n = 4 * int(n_recv)
+                    if n:
+                        self.cs[r].wait_event(self.ev_packed[int(p)])
+                        self.buf[r][1][ro:ro + n].copy_(self.buf[int(p)][0][so:so + n], non_blocking=True)
+                    ro += n
+            e = torch.cuda.Event()
+            e.record(self.cs[r])
+            self.ev_copied[r] = e
+        for s in self.s:
+            s.halo_unpack(stage)
+            if self.begin:
+                s.stage_begin(stage)
+
     def exchange(self, stage):
+        if self.async_copies:
+            return self.exchange_async(stage)
         for s in self.s:
             s.halo_pack(stage)
         for s in self.s:
@@ -65,7 +105,7 @@ class Loopback:
 
     def step(self, cfl):
         self.exchange(0)
-        mx = max(s.local_max_spectral_radius() for s in self.s)
+        mx = max(s.local_max_spectral_radius() for s in self.s)      # the one host round trip per step of this test driver
         for s in self.s:
             s.apply_dt(cfl, mx)
             s.stage(0)
@@ -76,8 +116,17 @@ class Loopback:
         for s in self.s:
             s.finish_step()
 
+    def set_state(self, U0):
+        for r, s in enumerate(self.s):
+            s.set_state(U0 if self.locals_ is None else U0[self.locals_[r].global_cell_ids.astype(np.int64)])
+
     def state(self):
-        return sum(s.get_state() for s in self.s)   # every rank exports zeros outside its own cells
+        if self.locals_ is None:
+            return sum(s.get_state() for s in self.s)   # every rank exports zeros outside its own cells
+        U = np.zeros((self.locals_[0].n_global, 4))
+        for lp, s in zip(self.locals_, self.s):
+            U[lp.global_cell_ids.astype(np.int64)] += s.get_state()
+        return U
 
 
 @pytest.mark.parametrize("recon,integ,n_ranks,fp", [("FO", "SSPRK3", 2, "strict"), ("FO", "RK4", 3, "strict"), ("TENO", "SSPRK3", 2, "strict"),
@@ -91,8 +140,7 @@ def test_partitioned_ranks_reproduce_the_single_context_run(recon, integ, n_rank
     one.set_state(U0)
     part = mb.partition(mesh, n_ranks)
     many = Loopback(mesh, part, n_ranks, begin=(n_ranks != 3), **kw)
-    for s in many.s:
-        s.set_state(U0)
+    many.set_state(U0)
     for _ in range(3):
         one.calc_dt(0.3)
         one.take_step()
@@ -127,8 +175,7 @@ def test_partitioned_unstructured_mesh_reproduces_the_single_context_run(n_ranks
     assert sorted(np.unique(part)) == list(range(n_ranks))
     many = Loopback(mesh, part, n_ranks, **kw)
     assert max(len(i[0]) for i in many.info) >= 2          # some rank talks to more than one peer
-    for s in many.s:
-        s.set_state(U0)
+    many.set_state(U0)
     for _ in range(3):
         one.calc_dt(0.3)
         one.take_step()
@@ -141,6 +188,65 @@ def test_partitioned_unstructured_mesh_reproduces_the_single_context_run(n_ranks
         assert np.abs(Un - U1).max() <= 1e-12 * np.abs(U1).max()
 
 
+@pytest.mark.parametrize("n_ranks,fp,integ", [(4, "strict", "SSPRK3"), (3, "fast", "RK4")])
+def test_rank_local_ingest_reproduces_the_single_context_run(n_ranks, fp, integ):
+    """mlb_create_local: every rank context is built from ITS PART of the mesh only (generated without the global mesh,
+    synthetic.jittered_tri_local) and exchanges GLOBAL ids with its peers; the run must be bit-identical (STRICT) to the
+    single-context run on the global mesh.  The copies between the ranks' buffers are asynchronous (no host synchronisation
+    inside a step): the interior reconstruction overlaps them as it overlaps NCCL's transfers."""
+    from mallard_b200 import synthetic as syn
+    nx, ny = 48, 36
+    mesh = syn.jittered_tri(nx, ny, 10.0, 10.0, seed=12345)
+    U0 = syn.isentropic_vortex(mesh.arrays["cell_coords"])
+    kw = dict(recon="TENO", riemann="HLLC", integrator=integ, order=3, bcs=syn.EXTRAP4, fp_mode=fp, teno_fixed=True)
+    one = mb.Solver(mesh, **kw)
+    one.set_state(U0)
+    with pytest.raises(mb.MallardError, match="more ghost layers"):
+        lp = syn.jittered_tri_local(nx, ny, 10.0, 10.0, n_ranks, 0, seed=12345, layers=2)
+        mb.Solver(lp.mesh, part=lp.part_local, rank=0, n_ranks=n_ranks, device=0, local=lp.local, **kw)
+    locals_ = [syn.jittered_tri_local(nx, ny, 10.0, 10.0, n_ranks, r, seed=12345, layers=10) for r in range(n_ranks)]
+    assert sum(lp.n_owned for lp in locals_) == mesh.n_cells and max(lp.mesh.n_cells for lp in locals_) < mesh.n_cells
+    many = Loopback(None, None, n_ranks, async_copies=True, locals_=locals_, **kw)
+    many.set_state(U0)
+    for _ in range(4):
+        one.calc_dt(0.3)
+        one.take_step()
+        many.step(0.3)
+    U1, Un = one.get_state(), many.state()
+    assert np.isfinite(U1).all()
+    if fp == "strict":
+        assert np.array_equal(U1, Un)
+    else:
+        assert np.abs(Un - U1).max() <= 1e-12 * np.abs(U1).max()
+
+
+@pytest.mark.parametrize("fp,integ", [("fast", "SSPRK3"), ("fast", "RK4"), ("strict", "SSPRK3")])
+def test_asynchronous_exchange_overlapping_the_interior_reconstruction(fp, integ):
+    """The path that ships: FAST mode has interior tiles (interior_tiles() > 0), so mlb_stage_begin launches their
+    reconstruction on the compute stream while pack / transfer / unpack (and the ghost-primitive refresh of stage 0) run on the
+    communication stream, ordered by ev_state / ev_halo only.  No host synchronisation inside a step; many steps, so that a
+    missing ordering edge has every chance to show."""
+    mesh = mb.Mesh.generate("cartesian_tri", 96, 64, 3.0, 2.0)      # 12 288 cells: thousands of interior tiles per rank
+    U0 = _state(mesh.arrays["cell_coords"] / 2.0)
+    kw = dict(recon="TENO", riemann="HLLC", integrator=integ, order=3, bcs=SYM4, fp_mode=fp, teno_fixed=True, keep_stage_rhs=False)
+    one = mb.Solver(mesh, **kw)
+    one.set_state(U0)
+    n_ranks = 3
+    part = mb.partition(mesh, n_ranks)
+    many = Loopback(mesh, part, n_ranks, async_copies=True, **kw)
+    many.set_state(U0)
+    for _ in range(12):
+        one.calc_dt(0.3)
+        one.take_step()
+        many.step(0.3)
+    U1, Un = one.get_state(), many.state()
+    assert np.isfinite(U1).all()
+    if fp == "strict":
+        assert np.array_equal(U1, Un)
+    else:
+        assert np.abs(Un - U1).max() <= 12 * 1e-12 * np.abs(U1).max()
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -150,10 +256,12 @@ def _free_port():
 def _nccl_worker(rank, world, port, out_dir):
     import torch.distributed as dist
     from mallard_b200.parallel import DistributedSolver
+    from mallard_b200 import synthetic as syn
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="4")
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
+        # (a) split-phase ABI driven from Python over torch.distributed, global mesh on every rank, STRICT
         mesh = mb.Mesh.generate("cartesian_tri", 48, 32, 2.0, 1.0)
         U0 = _state(mesh.arrays["cell_coords"])
         part = mb.partition(mesh, world)
@@ -165,6 +273,23 @@ def _nccl_worker(rank, world, port, out_dir):
         if rank == 0:
             np.save(os.path.join(out_dir, "U.npy"), U)
             np.save(os.path.join(out_dir, "t.npy"), np.array([t, n]))
+        # (b) the native driver (NCCL inside the library, CUDA-graph replayed steps) on rank-local meshes: FAST (interior tiles
+        #     overlap the exchange) with SSPRK3 and RK4, and STRICT
+        nx, ny = 64, 48
+        for tag, fp, integ in (("fast_ssprk3", "fast", "SSPRK3"), ("fast_rk4", "fast", "RK4"), ("strict_ssprk3", "strict", "SSPRK3")):
+            lp = syn.jittered_tri_local(nx, ny, 10.0, 10.0, world, rank, seed=12345, layers=10)
+            dn = DistributedSolver(lp.mesh, lp.part_local, rank, world, rank, local=lp.local, native=True, recon="TENO", riemann="HLLC",
+                                   integrator=integ, order=3, bcs=syn.EXTRAP4, fp_mode=fp, teno_fixed=True, keep_stage_rhs=False)
+            dn.s.set_state(syn.isentropic_vortex(lp.mesh.arrays["cell_coords"]))
+            t, n = dn.run(9, cfl=0.3)                  # 1 eager step + 8 graph replays
+            replays = int(dn.s.get("stats")[11])
+            Uh = dn.s.get_owned()
+            Uh2 = dn.step_host(Uh.copy(), 0.3)         # the host-buffer seam on top: one more step
+            U = dn.gather_state()
+            if rank == 0:
+                np.save(os.path.join(out_dir, "U_%s.npy" % tag), U)
+                np.save(os.path.join(out_dir, "t_%s.npy" % tag), np.array([t, n, replays]))
+            dn.s.close()
     finally:
         dist.destroy_process_group()
 
@@ -172,6 +297,7 @@ def _nccl_worker(rank, world, port, out_dir):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_nccl_halo_exchange_matches_single_gpu(tmp_path):
     import torch.multiprocessing as mp
+    from mallard_b200 import synthetic as syn
     world = min(torch.cuda.device_count(), 4)
     mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     mesh = mb.Mesh.generate("cartesian_tri", 48, 32, 2.0, 1.0)
@@ -180,3 +306,18 @@ def test_nccl_halo_exchange_matches_single_gpu(tmp_path):
     t, _ = one.run(3, cfl=0.3)
     assert np.array_equal(np.load(tmp_path / "U.npy"), one.get_state())
     assert np.load(tmp_path / "t.npy")[0] == t
+    # native driver on rank-local meshes against the single-GPU run on the global mesh
+    g = syn.jittered_tri(64, 48, 10.0, 10.0, seed=12345)
+    U0 = syn.isentropic_vortex(g.arrays["cell_coords"])
+    for tag, fp, integ in (("fast_ssprk3", "fast", "SSPRK3"), ("fast_rk4", "fast", "RK4"), ("strict_ssprk3", "strict", "SSPRK3")):
+        one = mb.Solver(g, "TENO", "HLLC", integ, order=3, bcs=syn.EXTRAP4, fp_mode=fp, teno_fixed=True, keep_stage_rhs=False)
+        one.set_state(U0)
+        t, _ = one.run(10, cfl=0.3)
+        U1, Un = one.get_state(), np.load(tmp_path / ("U_%s.npy" % tag))
+        tn = np.load(tmp_path / ("t_%s.npy" % tag))
+        assert tn[2] == 8, "the distributed steps were not replayed as a CUDA graph"
+        assert np.isfinite(U1).all()
+        if fp == "strict":
+            assert np.array_equal(U1, Un), tag
+        else:
+            assert np.abs(Un - U1).max() <= 1e-12 * 10 * np.abs(U1).max(), tag

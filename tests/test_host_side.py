@@ -339,3 +339,69 @@ def test_gmsh_reader_rejects_what_it_cannot_represent(tmp_path):
     p.write_text("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n3\n1 0 0 0\n2 1 0 0\n3 0 1 0\n$EndNodes\n$Elements\n1\n1 1 2 1 1 1 2\n$EndElements\n")
     with pytest.raises(ValueError, match="no triangles or quadrilaterals"):
         meshio.read_gmsh(str(p))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Rank-local ingest (mlb_create_local / mlb_plan_create_local): no rank holds the global mesh
+# ------------------------------------------------------------------------------------------------------------------
+def test_local_mesh_generator_equals_the_restriction_of_the_global_mesh():
+    """synthetic.jittered_tri_local builds a rank's part of the jittered, id-shuffled triangulation from closed forms; it must be
+    the very arrays local_mesh.extract_local cuts out of the global mesh (and the whole mesh when nothing is cut)."""
+    from mallard_b200 import local_mesh as lm, synthetic as syn
+    nx, ny = 14, 11
+    g = syn.jittered_tri(nx, ny, 10.0, 8.0, seed=12345)
+    whole = syn.jittered_tri_local(nx, ny, 10.0, 8.0, 1, 0, seed=12345)
+    for k in g.arrays:
+        assert np.array_equal(g.arrays[k], whole.mesh.arrays[k]), k
+    assert [(n, f.tolist()) for n, f in g.zones] == [(n, f.tolist()) for n, f in whole.mesh.zones]
+    part = mb.partition(g, 3)
+    assert np.array_equal(part, mb.partition_coords(g.arrays["cell_coords"], 3))       # the partition needs the centroids only
+    for r in range(3):
+        lp = syn.jittered_tri_local(nx, ny, 10.0, 8.0, 3, r, seed=12345, layers=2)
+        keep = np.zeros(g.n_cells, bool)
+        keep[lp.global_cell_ids] = True
+        assert keep[part == r].all() and lp.n_owned == int((part == r).sum())
+        ex, gc, gf = lm.extract_local(g, keep)
+        assert np.array_equal(gc, lp.global_cell_ids) and np.array_equal(part[gc], lp.part_local)
+        for k in ex.arrays:
+            assert np.array_equal(ex.arrays[k], lp.mesh.arrays[k]), (r, k)
+        assert [(n, f.tolist()) for n, f in ex.zones] == [(n, f.tolist()) for n, f in lp.mesh.zones]
+        assert np.array_equal(lm.local_info(g, gc)["cell0_nodes"], lp.local["cell0_nodes"])
+        cof = lp.mesh.arrays["cells_of_face"]
+        assert (cof[:, 1] == lm.CUT).any() and (cof[:, 0] >= 0).all()
+    # extract_local + dilate on a mesh that is not a structured parent's child: quads of the wedge
+    w = mb.Mesh.generate("wedge", 12, 8, 4.0, 1.5)
+    keep = lm.dilate(w, mb.partition(w, 2) == 0, 2)
+    ex, gc, gf = lm.extract_local(w, keep)
+    assert ex.n_cells == int(keep.sum()) and np.array_equal(ex.arrays["cell_volume"], w.arrays["cell_volume"][gc])
+
+
+@pytest.mark.parametrize("fp", ["strict", "fast"])
+def test_plan_of_a_local_mesh_is_bit_identical_to_the_plan_of_the_partitioned_global_mesh(fp):
+    """Stencil membership depends on the order of cell ids and integral_psi_target on the global mesh's cell 0
+    (face_reconstruction.cpp:598-602): the local mesh keeps the global order and is told cell 0's nodes, so every table - ids,
+    pseudo-inverses, slots, accumulation order - is bit-identical; a halo that is too thin is refused, never silently wrong."""
+    from mallard_b200 import synthetic as syn
+    nx, ny, W = 34, 30, 3
+    g = syn.jittered_tri(nx, ny, 10.0, 8.0, seed=12345)
+    part = mb.partition(g, W)
+    for r in range(W):
+        thin = syn.jittered_tri_local(nx, ny, 10.0, 8.0, W, r, seed=12345, layers=3)
+        with pytest.raises(mb.MallardError, match="more ghost layers"):
+            mb.Plan(thin.mesh, "TENO", order=3, bcs=syn.EXTRAP4, part=thin.part_local, rank=r, n_ranks=W, fp_mode=fp, local=thin.local)
+        lp = syn.jittered_tri_local(nx, ny, 10.0, 8.0, W, r, seed=12345, layers=10)
+        pl = mb.Plan(lp.mesh, "TENO", order=3, bcs=syn.EXTRAP4, part=lp.part_local, rank=r, n_ranks=W, fp_mode=fp, local=lp.local)
+        pg = mb.Plan(g, "TENO", order=3, bcs=syn.EXTRAP4, part=part, rank=r, n_ranks=W, fp_mode=fp)
+        assert (pl.N, pl.N_owned, pl.N_recon, pl.NF) == (pg.N, pg.N_owned, pg.N_recon, pg.NF) and lp.mesh.n_cells < g.n_cells
+        assert np.array_equal(lp.global_cell_ids[pl.get("perm_cells")], pg.get("perm_cells"))
+        names = ["slot_face", "slot_nbr", "rhs_order", "n_interior", "teno:integral_psi_target", "teno:oscillation_indicator"]
+        names += ["fm_ids", "fm_mat", "fm_area0", "OIs"] if fp == "fast" else ["st_ids"]
+        for name in names:
+            a, b = pl.get(name), pg.get(name)
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8)), (r, name)
+        assert np.array_equal(lp.global_cell_ids[pl.get("halo_recv_ids")], pg.get("halo_recv_ids"))
+    # first order needs one layer only
+    lp = syn.jittered_tri_local(nx, ny, 10.0, 8.0, W, 1, seed=12345, layers=1)
+    pl = mb.Plan(lp.mesh, "FO", bcs=syn.EXTRAP4, part=lp.part_local, rank=1, n_ranks=W, local=lp.local)
+    pg = mb.Plan(g, "FO", bcs=syn.EXTRAP4, part=part, rank=1, n_ranks=W)
+    assert np.array_equal(pl.get("slot_nbr"), pg.get("slot_nbr")) and np.array_equal(pl.get("rhs_order"), pg.get("rhs_order"))
