@@ -298,6 +298,11 @@ int mlb_host_mesh_generate(mlb_host_mesh **out, int32_t type, uint32_t nx, uint3
 /* connectivity + node coordinates supplied by the caller (any unstructured mesh of triangles / quads); geometry computed as
  * Mesh::compute_cell_centroids / compute_cell_volumes / compute_face_areas / compute_face_normals do (mesh/mesh.cpp:167-261) */
 int mlb_host_mesh_from_arrays(mlb_host_mesh **out, const mlb_mesh *mesh);
+/* Mesh file reader / writer: what `[mesh] type = "file"` needs (Mesh::init's MeshType::FILE branch is a stub that throws,
+ * mesh/mesh.cpp:41-43).  Gmsh MSH 2.2 ASCII, 2-D: triangles and quadrilaterals become cells, tagged 2-node lines name the
+ * boundary zones ($PhysicalNames), "interior" lists the two-cell faces; geometry as Mesh::compute_* computes it. */
+int mlb_host_mesh_read_gmsh(mlb_host_mesh **out, const char *path);
+int mlb_host_mesh_write_gmsh(const mlb_mesh *mesh, const char *path);
 int mlb_host_mesh_view(const mlb_host_mesh *m, mlb_mesh *view);   /* pointers stay valid until mlb_host_mesh_free */
 void mlb_host_mesh_free(mlb_host_mesh *m);
 

@@ -80,6 +80,8 @@ struct mlb_ctx {
     uint32_t * d_perm_cells = nullptr, * d_perm_faces = nullptr;
     uint32_t * d_st_ids = nullptr;
     double * d_st_area = nullptr, * d_st_mat = nullptr;
+    double * d_OI = nullptr, * d_psi_bar = nullptr;   // oscillation-indicator matrix, integral_psi_target, exponents (generic kernel)
+    uint8_t * d_pidx = nullptr;
     bool streaming = false;            // FAST mode: compact streaming tables + teno_stream_kernel
     uint32_t * d_fm_ids = nullptr;
     double * d_fm_mat = nullptr, * d_fm_area0 = nullptr;
@@ -238,8 +240,11 @@ ReconArgs recon_args(mlb_ctx & c, const double * Uin) {
     const TenoTables & T = c.prep.teno;
     r.order = T.order; r.K = T.K; r.M = T.M; r.Mp = T.Mp; r.S = T.S; r.basis = T.basis; r.fixed_weights = c.num.teno_fixed;
     for (size_t i = 0; i < c.prep.qf_x.size(); i++) r.qf_x[i] = c.prep.qf_x[i];
-    for (int i = 0; i < T.K; i++) { r.psi_bar[i] = T.psi_bar[i]; r.pidx[2 * i] = T.pidx[2 * i]; r.pidx[2 * i + 1] = T.pidx[2 * i + 1]; }
-    for (int i = 0; i < T.K * T.K; i++) r.OI[i] = T.OI[i];
+    if (T.K <= 15) {
+        for (int i = 0; i < T.K; i++) { r.psi_bar[i] = T.psi_bar[i]; r.pidx[2 * i] = T.pidx[2 * i]; r.pidx[2 * i + 1] = T.pidx[2 * i + 1]; }
+        for (int i = 0; i < T.K * T.K; i++) r.OI[i] = T.OI[i];
+    }
+    r.OI_dev = c.d_OI; r.psi_bar_dev = c.d_psi_bar; r.pidx_dev = c.d_pidx;
     return r;
 }
 
@@ -479,9 +484,9 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
     preprocess(hm, c->num, bc_zones, opt, c->prep);
     Prep & P = c->prep;
     for (size_t i = 0; i < P.qf_x.size(); i++) { c->phys.qf_x[i] = P.qf_x[i]; c->phys.qf_w[i] = P.qf_w[i]; }
-    if (c->teno && !c->streaming && !c->kt->recon_supported(P.teno.order, P.teno.Mp, P.teno.basis))
-        throw std::runtime_error("TENO: this (basis, order, stencil size) combination has no compiled device kernel "
-                                 "(available: legendre / monomial, order 1-4, max_stencil_size_factor 2.0)");
+    if (c->teno && !c->streaming && !c->kt->recon_supported(P.teno.order, P.teno.K, P.teno.Mp, P.teno.S, P.teno.basis))
+        throw std::runtime_error("TENO: this (basis, order, stencil size) combination exceeds what the device kernels hold in shared memory "
+                                 "(order 1-9; stencils of up to ~500 cells)");
 
     // ---- upload
     DevGeom & g = c->g;
@@ -544,6 +549,7 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
             else { c->d_fm_area0 = c->upload(T.fm_area0); c->d_fm_mat = c->upload(T.fm_mat); }
         } else {
             c->d_st_ids = c->upload(T.st_ids); c->d_st_area = c->upload(T.st_area); c->d_st_mat = c->upload(T.st_mat);
+            c->d_OI = c->upload(T.OI); c->d_psi_bar = c->upload(T.psi_bar); c->d_pidx = c->upload(T.pidx);
         }
         CUDA_OK(cudaStreamSynchronize(c->stream));
         uvec().swap(T.st_ids); dvec().swap(T.st_area); dvec().swap(T.st_mat);   // host copies no longer needed
@@ -1578,6 +1584,22 @@ int mlb_host_mesh_from_arrays(mlb_host_mesh ** out, const mlb_mesh * mesh) {
     v.cell_coords = nullptr;   // geometry is always recomputed here (Mesh::compute_cell_centroids/volumes/face_areas/normals, mesh/mesh.cpp:167-261)
     host_mesh_from_view(m->m, v);
     *out = m.release();
+    API_END(none)
+}
+int mlb_host_mesh_read_gmsh(mlb_host_mesh ** out, const char * path) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!out || !path) throw std::runtime_error("NULL argument");
+    std::unique_ptr<mlb_host_mesh> m(new mlb_host_mesh());
+    host_mesh_read_gmsh(m->m, path);
+    *out = m.release();
+    API_END(none)
+}
+int mlb_host_mesh_write_gmsh(const mlb_mesh * mesh, const char * path) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!mesh || !path) throw std::runtime_error("NULL argument");
+    host_mesh_write_gmsh(*mesh, path);
     API_END(none)
 }
 int mlb_host_mesh_view(const mlb_host_mesh * hm, mlb_mesh * v) {

@@ -70,9 +70,12 @@ struct ReconArgs {
     const double * st_mat;
     int32_t order, K, M, Mp, S, basis, fixed_weights;
     double qf_x[MAX_Q];
-    double psi_bar[15];
+    double psi_bar[15];           // the specialised kernels (order <= 4: K <= 15) take these by value ...
     uint8_t pidx[2 * 15];
     double OI[15 * 15];
+    const double * OI_dev;        // ... the generic kernel (any order <= 9: K <= 55) reads them from device memory
+    const double * psi_bar_dev;
+    const uint8_t * pidx_dev;
 };
 
 struct ReconStreamArgs {       // teno_stream.cuh
@@ -123,7 +126,7 @@ struct KernelTable {
                          double * flux, cudaStream_t);
     void (*primitives)(const GasParams &, uint64_t n, const double * U_aos, double * P_aos, cudaStream_t);
     void (*primitives_soa)(const GasParams &, uint32_t n, uint32_t npad, const double * U, double * P, cudaStream_t);
-    bool (*recon_supported)(int order, int Mp, int basis);
+    bool (*recon_supported)(int order, int K, int Mp, int S, int basis);
     // FAST mode only (null in the STRICT table): streaming TENO reconstruction over the compact tables
     void (*recon_stream)(const ReconStreamArgs &, cudaStream_t);
     bool (*stream_supported)(int order, int M, int Q, int basis, int n_slots);

@@ -617,6 +617,7 @@ __global__ void __launch_bounds__(RECON_THREADS) teno_recon_kernel(const __grid_
 #else
 #include "teno_strict_stream.cuh"
 #endif
+#include "teno_generic.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
 // Spectral radius + max + dt — SpectralRadiusFunctor / Solver::calc_dt (solver/solver.cpp:580-742)
@@ -753,9 +754,12 @@ static void launch_recon_t(const ReconArgs & a, cudaStream_t st) {
     if (grid == 0) return;
     teno_recon_kernel<ORDER, MP><<<grid, RECON_THREADS, smem, st>>>(a);
 }
-static bool recon_supported(int order, int Mp, int basis) {
+static bool recon_specialised(int order, int Mp, int S) {
+    return S <= 1 + MAX_SLOTS && ((order == 1 && Mp == 6) || (order == 2 && Mp == 12) || (order == 3 && Mp == 20) || (order == 4 && Mp == 30));
+}
+static bool recon_supported(int order, int K, int Mp, int S, int basis) {
     if (basis != MLB_BASIS_LEGENDRE && basis != MLB_BASIS_MONOMIAL) return false;
-    return (order == 1 && Mp == 6) || (order == 2 && Mp == 12) || (order == 3 && Mp == 20) || (order == 4 && Mp == 30);
+    return recon_specialised(order, Mp, S) || generic::generic_supported(order, K, Mp, S);
 }
 static void launch_recon(const ReconArgs & a, cudaStream_t st) {
 #ifndef MLB_STREAM_KERNELS
@@ -766,6 +770,9 @@ static void launch_recon(const ReconArgs & a, cudaStream_t st) {
         if (a.order == 4 && a.Mp == 30) return sstream::launch_strict_stream<4, 30>(a, st);
     }
 #endif
+    const char * fg = getenv("MLB_TENO_GENERIC");               // test hook: run the generic kernel where a specialised one exists
+    const bool force_generic = fg && fg[0] == '1';
+    if (force_generic || !recon_specialised(a.order, a.Mp, a.S)) return generic::launch_generic(a, st);
     if (a.order == 1 && a.Mp == 6) launch_recon_t<1, 6>(a, st);
     else if (a.order == 2 && a.Mp == 12) launch_recon_t<2, 12>(a, st);
     else if (a.order == 3 && a.Mp == 20) launch_recon_t<3, 20>(a, st);

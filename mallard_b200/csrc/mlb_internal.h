@@ -32,6 +32,8 @@ struct HostMesh {
 void host_mesh_generate(HostMesh & m, int type, uint32_t nx, uint32_t ny, double Lx, double Ly);
 void host_mesh_from_view(HostMesh & m, const mlb_mesh & v);
 void host_mesh_geometry(HostMesh & m);
+void host_mesh_read_gmsh(HostMesh & m, const char * path);          // mesh_io.cpp
+void host_mesh_write_gmsh(const mlb_mesh & v, const char * path);
 
 // ---------------------------------------------------------------------------------------------------------------
 // Gas constants (physics/physics.cpp:69-73)

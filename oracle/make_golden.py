@@ -90,6 +90,17 @@ CASES = {
                                  riemann="HLLC", integrator="SSPRK3",
                                  recon=dict(type="TENO", basis_type="monomial", basis_order=3, max_stencil_size_factor=2.0),
                                  n_steps=1, every=1, keep_mesh=False, keep_teno=True),
+    # configurations beyond the specialised device kernels (generic kernel): order 5 (K = 21, M = 42; the reference has Dunavant
+    # rules up to order 5 only, so quadrature_order_cell must be given) and a stencil-size factor other than 2
+    "teno_legendre_12x10_p5": dict(mesh=dict(type="cartesian_tri", Nx=12, Ny=10, Lx=1.2, Ly=1.0), ic=SMOOTH_IC, bcs=SYM4, cfl=0.1,
+                                   riemann="HLLC", integrator="SSPRK3",
+                                   recon=dict(type="TENO", basis_type="legendre", basis_order=5, max_stencil_size_factor=2.0,
+                                              quadrature_order_cell=5),
+                                   n_steps=1, every=1, keep_mesh=False, keep_teno=False),
+    "teno_legendre_8x7_p2_f15": dict(mesh=dict(type="cartesian_tri", Nx=8, Ny=7, Lx=1.0, Ly=0.9), ic=SMOOTH_IC, bcs=EXTRAP4, cfl=0.1,
+                                     riemann="HLLC", integrator="SSPRK3",
+                                     recon=dict(type="TENO", basis_type="legendre", basis_order=2, max_stencil_size_factor=1.5),
+                                     n_steps=1, every=1, keep_mesh=False, keep_teno=True),
     "teno_monomial_9x8_p2": dict(mesh=dict(type="cartesian_tri", Nx=9, Ny=8, Lx=1.2, Ly=1.0), ic=SMOOTH_IC, bcs=EXTRAP4, cfl=0.1,
                                  riemann="HLL", integrator="RK4",
                                  recon=dict(type="TENO", basis_type="monomial", basis_order=2, max_stencil_size_factor=2.0),

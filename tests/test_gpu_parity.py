@@ -540,6 +540,55 @@ def test_monomial_basis_vs_oracle(oracle_mod, order, fixed, fp):
     assert err(sg.get_state(), so.get("U")) <= TOL
 
 
+def test_generic_teno_kernel_is_bit_identical_to_the_specialised_one(monkeypatch):
+    """teno_generic.cuh keeps the specialised kernels' operation and summation order with run-time (K, M, S): forced onto a
+    configuration that has a specialised kernel (MLB_TENO_GENERIC=1, read per launch) it must reproduce it bit for bit."""
+    mesh = mb.Mesh.generate("cartesian_tri", 22, 18, 2.0, 1.0)
+    U0 = _random_smooth_state(mesh.arrays["cell_coords"], np.random.default_rng(31))
+    for order, basis in ((3, "legendre"), (2, "monomial"), (4, "legendre")):
+        s = mb.Solver(mesh, "TENO", "HLLC", "SSPRK3", basis=basis, order=order, bcs=SYM4, fp_mode="strict")
+        s.set_state(U0)
+        monkeypatch.delenv("MLB_TENO_GENERIC", raising=False)
+        F_spec, rhs_spec = s.calc_face_values(), s.calc_rhs()
+        monkeypatch.setenv("MLB_TENO_GENERIC", "1")
+        F_gen, rhs_gen = s.calc_face_values(), s.calc_rhs()
+        monkeypatch.delenv("MLB_TENO_GENERIC", raising=False)
+        assert np.abs(F_spec).max() > 0
+        assert np.array_equal(F_spec, F_gen, equal_nan=True) and np.array_equal(rhs_spec, rhs_gen, equal_nan=True), (order, basis)
+        s.close()
+
+
+@pytest.mark.parametrize("fp", ["strict", "fast"])
+@pytest.mark.parametrize("order,factor,qc,basis,fixed", [(5, 2.0, 5, "legendre", True), (6, 2.0, 5, "legendre", True), (7, 2.0, 5, "monomial", True),
+                                                         (9, 2.0, 5, "legendre", True), (2, 1.5, 0, "legendre", False), (3, 3.0, 0, "monomial", True),
+                                                         (4, 2.5, 0, "legendre", True)])
+def test_teno_orders_5_to_9_and_other_stencil_factors_vs_oracle(oracle_mod, order, factor, qc, basis, fixed, fp):
+    """Everything the reference's TOML accepts (face_reconstruction.cpp:110-116,170-180): basis_order up to 9 (Dunavant rules
+    stop at order 5, so quadrature_order_cell is given there, as it must be for the reference) and max_stencil_size_factor
+    other than 2, through the generic kernel, against the oracle (pinned to the reference for p = 5 and factor 1.5 by the
+    fixtures teno_legendre_12x10_p5 / teno_legendre_8x7_p2_f15)."""
+    nx, ny = (30, 26) if order >= 7 else (20, 16)
+    om = oracle_mod.Mesh.generate("cartesian_tri", nx, ny, 2.0, 1.0)
+    mesh = mb.Mesh.generate("cartesian_tri", nx, ny, 2.0, 1.0)
+    kw = dict(recon="TENO", riemann="HLLC", integrator="SSPRK3", bcs=SYM4, basis=basis, order=order, factor=factor, quad_cell_order=qc,
+              teno_fixed=fixed)
+    so = oracle_mod.Solver(om, **kw)
+    sg = mb.Solver(mesh, fp_mode=fp, **kw)
+    U0 = _random_smooth_state(mesh.arrays["cell_coords"], np.random.default_rng(23))
+    so.set_state(U0); sg.set_state(U0)
+    real = gu.real_faces(mesh.arrays["cells_of_face"], mesh.arrays["nodes_of_face"])
+    Fg, Fo = sg.calc_face_values()[real][:, :, 0], so.calc_face_values()[real][:, :, 0]
+    # the higher the order, the worse conditioned the pseudo-inverse rows (entries ~1e6 at p = 9): differences are measured
+    # against the field scale in both modes; STRICT is additionally bit-exact wherever pow() is not involved (legendre)
+    if fp == "strict" and basis == "legendre":
+        assert np.array_equal(Fg, Fo, equal_nan=True)
+    else:
+        assert gu.field_err(Fg, Fo) <= (TOL if order <= 5 else 1e-9)
+    dto, dtg = so.calc_dt(0.3), sg.calc_dt(0.3)
+    so.take_step(dto); sg.take_step()
+    assert gu.field_err(sg.get_state(), so.get("U")) <= (TOL if order <= 5 else 1e-9)
+
+
 def test_device_side_field_ranges_and_nan_count():
     """mlb_field_ranges = max_array / min_array of Solver::do_checks (solver.cpp:434-437; `a > max` / `a < min`, so NaN never
     wins) + the NaN test of check_fields (solver.cpp:470-498), against numpy on the exported state."""

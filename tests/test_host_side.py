@@ -80,6 +80,7 @@ def test_teno_tables_bit_exact_against_reference(name):
     r = meta["recon"]
     for renumber in ("rcm", "none"):
         plan = mb.Plan(mesh, "TENO", basis=r["basis_type"], order=r["basis_order"], factor=r["max_stencil_size_factor"],
+                       quad_cell_order=r.get("quadrature_order_cell", 0), quad_face_order=r.get("quadrature_order_face", 0),
                        bcs=meta["bcs"], renumber=renumber)
         for k in g:
             if k.startswith("teno:") and k not in ("teno:meta", "teno:quad_cell_points", "teno:quad_cell_weights", "teno:quad_face_points"):
