@@ -283,9 +283,7 @@ def main():
     kernels = {k: {"ms_total": v[0], "launches": int(v[1]), "ms_per_launch": v[0] / max(1, v[1])} for k, v in prof.items()}
     if top:
         per_launch_ms = prof[top][0] / prof[top][1]
-        # fused flux + residual + RK kernel: TENO reads the cell's face values (192 B), face geometry 1.5 x 32 B, volume, U^n in, U out
-        # (SURVEY 8d's stage figure minus the reconstruction kernel's share); first order: SURVEY 8d's 152 B per cell-update
-        alg = {"teno_recon": ALG_BYTES_RECON, "teno_stream": ALG_BYTES_RECON, "cell_stage_teno": 312.0, "cell_stage_fo": 152.0,
+        alg = {"teno_recon": ALG_BYTES_RECON, "teno_stream": ALG_BYTES_RECON, "face_flux_teno": 48.0, "gather_stage": 72.0, "face_flux_fo": 80.0,
                "cfl": 200.0}.get(top, ALG_BYTES_STAGE)
         achieved = alg * nc / (per_launch_ms * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this very

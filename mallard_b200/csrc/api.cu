@@ -73,7 +73,7 @@ struct mlb_ctx {
     DevGeom g{};
     double * U[3] = {nullptr, nullptr, nullptr};
     double * k[4] = {nullptr, nullptr, nullptr, nullptr};
-    double * prim = nullptr, * sr = nullptr, * Fc = nullptr, * scal = nullptr, * k_override = nullptr;
+    double * prim = nullptr, * sr = nullptr, * Fc = nullptr, * AF = nullptr, * scal = nullptr, * k_override = nullptr;
     long long * max_bits = nullptr;
     unsigned int * blocks_done = nullptr;
     unsigned long long * step_counter = nullptr;
@@ -301,7 +301,7 @@ void run_stage(mlb_ctx & c, const StagePlan & s, bool bare, double * k_out) {
         if (recon) run_recon(c, Uin);
     }
     StageArgs a{};
-    a.g = c.g; a.ph = c.phys; a.Uin = Uin; a.Fc = c.Fc; a.teno = c.teno ? 1 : 0;
+    a.g = c.g; a.ph = c.phys; a.Uin = Uin; a.Fc = c.Fc; a.AF = c.AF; a.teno = c.teno ? 1 : 0;
     a.k_override = c.has_override ? c.k_override : nullptr;
     a.scal = c.scal; a.step_counter = c.step_counter;
     RkArgs & rk = a.rk;
@@ -315,7 +315,8 @@ void run_stage(mlb_ctx & c, const StagePlan & s, bool bare, double * k_out) {
         rk.c0 = s.c0; rk.c1 = s.c1; rk.coef = s.coef;
         rk.prim_out = s.last ? c.prim : nullptr;
     }
-    c.launch(c.teno ? "cell_stage_teno" : "cell_stage_fo", [&] { c.kt->stage(a, c.stream); });
+    if (!c.has_override) c.launch(c.teno ? "face_flux_teno" : "face_flux_fo", [&] { c.kt->faces(a, c.stream); });
+    c.launch("gather_stage", [&] { c.kt->stage(a, c.stream); });
 }
 
 void finish_plan(mlb_ctx & c, const std::vector<StagePlan> & plan) {
@@ -500,23 +501,10 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
         g.bnd_s = c->upload(bs);
         CUDA_OK(cudaStreamSynchronize(c->stream));
     }
+    g.face_nx = c->upload(P.face_nx); g.face_ny = c->upload(P.face_ny); g.face_area = c->upload(P.face_area);
     g.slot_fx = c->teno ? c->upload(P.slot_fx) : nullptr;
-    {   // per (cell, slot): geometry of the face and which side of it the cell is on (the fused stage kernel never touches a face array)
-        dvec geom((size_t)P.n_slots * 3 * P.Npad, 0.0);
-        std::vector<uint8_t> meta((size_t)P.n_slots * P.Npad, 0);
-        for (int j = 0; j < P.n_slots; j++)
-            for (uint32_t i = 0; i < P.N_owned; i++) {
-                const uint32_t fcode = P.slot_face[(size_t)j * P.Npad + i];
-                if (fcode == NO_FACE) continue;
-                const uint32_t f = fcode & 0x7FFFFFFFu;
-                geom[((size_t)j * 3 + 0) * P.Npad + i] = P.face_nx[f];
-                geom[((size_t)j * 3 + 1) * P.Npad + i] = P.face_ny[f];
-                geom[((size_t)j * 3 + 2) * P.Npad + i] = P.face_area[f];
-                meta[(size_t)j * P.Npad + i] = (uint8_t)(P.slot_nslot[(size_t)j * P.Npad + i] | ((fcode >> 31) << 7));
-            }
-        g.slot_geom = c->upload(geom); g.slot_meta = c->upload(meta);
-        CUDA_OK(cudaStreamSynchronize(c->stream));
-    }
+    g.face_cl = c->upload(P.face_cl); g.face_cr = c->upload(P.face_cr); g.face_slots = c->upload(P.face_slots);
+    c->AF = c->alloc<double>(4 * (size_t)std::max<uint32_t>(P.NFpad, 1));
     c->d_perm_cells = c->upload(P.perm_cells);
     c->d_perm_faces = c->upload(P.perm_faces);
     const size_t NP = P.Npad;

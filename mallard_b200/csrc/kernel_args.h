@@ -18,9 +18,11 @@ struct DevGeom {
     const double * cell_vol;      // [Npad]
     const double * cell_xy;       // [2][Npad]
     const double * bnd_s;         // [Npad] 2*pow(V,1/2) (solver.cpp:662-666), computed on the host with libm pow
+    const double * face_nx, * face_ny, * face_area;   // [NFpad]
     const double * slot_fx;       // [n_slots][4][Npad]
-    const double * slot_geom;     // [n_slots][3][Npad] unit normal (out of the face's cell 0) and area of the face in slot j of a cell
-    const uint8_t * slot_meta;    // [n_slots][Npad] the neighbour's slot of the shared face | side << 7 (side 1: the normal points INTO this cell)
+    const uint32_t * face_cl;     // [NFpad] cell on side 0 (normal points out of it)
+    const int32_t * face_cr;      // [NFpad] cell on side 1 ; < 0: -(bc index + 1) ; INT32_MIN: no flux
+    const uint8_t * face_slots;   // [NFpad] slot of the face in cell 0 | slot in cell 1 << 4 (TENO face values are cell-centred)
 };
 
 struct DevPhys {
@@ -55,6 +57,7 @@ struct StageArgs {
     RkArgs rk;
     const double * Uin;           // AoS [Npad][4]: state the residual is evaluated on
     const double * Fc;            // TENO: cell-centred face values AoS [Npad][n_slots * Q][4]
+    double * AF;                  // [NFpad][4] area * quadrature-averaged flux per face (written by the face kernel)
     const double * k_override;    // AoS [Npad][4] or null: state-independent residual (test hook)
     double * scal;                // device scalars
     unsigned long long * step_counter;
@@ -119,6 +122,7 @@ struct CflArgs {
 
 struct KernelTable {
     const char * name;
+    void (*faces)(const StageArgs &, cudaStream_t);
     void (*stage)(const StageArgs &, cudaStream_t);
     void (*recon)(const ReconArgs &, cudaStream_t);
     void (*cfl)(const CflArgs &, cudaStream_t);

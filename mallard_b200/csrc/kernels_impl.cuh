@@ -2,10 +2,11 @@
 // -fmad=false (every product and sum rounds separately, exactly as the reference's x86-64 build does) and into
 // namespace `fast` with FMA contraction enabled.  Summation orders follow the reference in both.
 //
-//   cell_stage_kernel   cell-centric and fused: Riemann fluxes of a cell's faces (interior and boundary, quadrature loop),
-//                       atomic-free residual in the reference's accumulation order, divide-by-volume, RK stage update,
-//                       primitives (replaces K1 zero, K2 FirstOrder, K4 interior flux + atomic scatter, K5-K9 boundary
-//                       fluxes, K10 divide-by-volume, K11 BLAS-1 stage combinations and K12 update_primitives of SURVEY §2.1)
+//   face_flux_kernel    one thread per face: quadrature loop over the Riemann flux of interior and boundary faces
+//                       (replaces K2 FirstOrder, K4 interior flux, K5-K9 boundary fluxes of SURVEY §2.1)
+//   gather_stage_kernel cell-centric, atomic-free residual gather fused with the RK stage update
+//                       (replaces K1 zero, the atomic scatter of K4-K9, K10 divide-by-volume, K11 BLAS-1 stage
+//                        combinations and K12 update_primitives)
 //   teno_recon_kernel   TENO reconstruction (K3): one thread per (cell, conserved variable), warp = one 8-cell table tile
 //   cfl_kernel          spectral radius + max reduction + dt (K13, K14)
 //
@@ -310,112 +311,108 @@ __device__ __forceinline__ void rk_update(const RkArgs & rk, const double * Uin,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Residual + RK stage, cell-centric and fused: BaseFluxFunctor::call_impl (numerics/flux_functor.h:124-162) and the boundary
-// functors (boundary/*.cpp), the scatter into rhs, DivideVolumeFunctor (solver_rhs.cpp:18-42), the BLAS-1 stage combination
-// (time_integrator.cpp:57-163) and update_primitives (solver.cpp:533-578) in ONE kernel, without atomics and without a
-// per-face array in memory.
-//
-// A block holds CB cells and one thread per (cell, face slot); slot is warp-uniform (thread = slot * CB + cell).  Phase 1: every
-// (cell, slot) thread evaluates ITS face - both sides' face states (own: streamed; neighbour's: one 32-byte gather per
-// quadrature point), the Riemann flux per quadrature point, 1/2 sum_q w_q F_q in the reference's q order, times the face
-// area - and parks the product in shared memory.  An interior face is therefore evaluated twice, once by each of its
-// cells, from identical inputs by identical code: both cells see the same bits, exactly what the reference's one evaluation
-// scatters to both (so STRICT mode stays bit-exact), and the FP64 work that doubles is cheaper than the 64 B per face of
-// round trip through HBM plus the second launch it replaces (profiles/r02a: face kernel 0.32 ms + gather 0.11 ms per
-// stage at 2.1 M cells).  Phase 2: the slot-0 thread of a cell adds -+ the parked products in the reference's (Serial
-// back-end) accumulation order (interior faces in zone order, then boundaries in input order), divides by the
-// volume and applies the stage combination; the last stage also refreshes the primitives.
+// Face fluxes.  One thread per face: quadrature loop over the Riemann flux (BaseFluxFunctor::call_impl,
+// numerics/flux_functor.h:124-162; boundary ghost states boundary/*.cpp), result A * (1/2 sum_q w_q F_q) stored once per
+// face.  The reference scatters -+ that product into both cells with atomic_add; here the cells gather it (next kernel).
 // ---------------------------------------------------------------------------------------------------------------
-#ifndef MLB_CELL_CB
-#define MLB_CELL_CB 64
+#ifndef MLB_FLUX_MINB
+#define MLB_FLUX_MINB 8   // 64 registers: occupancy beats the 216 bytes of spills (A/B on B200: 0.48 -> 0.37 ms per launch, profiles/r01h)
 #endif
-#ifndef MLB_CELL_MINB
-#define MLB_CELL_MINB 4
-#endif
-constexpr int CELL_CB = MLB_CELL_CB;
-
-template <int RS, bool TENO, int QT, int NS>
-__global__ void __launch_bounds__(NS * CELL_CB, MLB_CELL_MINB) cell_stage_kernel(const __grid_constant__ StageArgs a) {
-    __shared__ double4 parked[NS][CELL_CB];
-    __shared__ uint8_t flag[NS][CELL_CB];             // 0: nothing to add; 1: subtract (side 0, normal points out); 3: add (side 1)
-    const int c = threadIdx.x % CELL_CB, slot = threadIdx.x / CELL_CB;
-    const uint32_t i = blockIdx.x * CELL_CB + c;
-    const uint32_t Np = a.g.Npad;
+// QT > 0: the number of face quadrature points is known at compile time and ONE THREAD PER (face, quadrature point) solves
+// one Riemann problem; the QT lanes of a face then combine w_q F_q in the reference's q order with warp shuffles (same
+// rounding as the sequential loop) and lane 0 stores.  Twice the parallelism and half the dependent sqrt/div chain per
+// thread of a per-face loop.  QT = 0: one thread per face loops over a run-time Q.
+template <int RS, bool TENO, int QT>
+__global__ void __launch_bounds__(128, MLB_FLUX_MINB) face_flux_kernel(const __grid_constant__ StageArgs a) {
+    constexpr int TPF = QT > 0 ? QT : 1;                 // threads per face (1, 2 or 4: divides the warp)
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = gid / TPF < a.g.NF;
+    const uint32_t f = valid ? gid / TPF : a.g.NF - 1;   // surplus lanes recompute the last face and do not store
+    const int lane_q = gid % TPF;
     const int Q = !TENO ? 1 : (QT > 0 ? QT : a.g.Q);
-    const int NPT = a.g.n_slots * Q;                  // face-value points per cell
-    uint8_t fl = 0;
-    double fsum[4] = {0.0, 0.0, 0.0, 0.0};
-    if (i < a.g.N_owned && !a.k_override && slot < (int)a.g.nfc[i]) {
-        const size_t at = (size_t)slot * Np + i;
-        const int32_t nbr = a.g.slot_nbr[at];
-        if (nbr != INT32_MIN) {                       // INT32_MIN: boundary zone without a [[boundaries]] entry - no flux
-            const uint32_t meta = a.g.slot_meta[at];  // neighbour's slot of this face | side << 7
-            const bool side1 = (meta >> 7) != 0;
-            const int nslot = meta & 7;
-            const double * gm = a.g.slot_geom + (size_t)slot * 3 * Np + i;
-            const double nx = gm[0], ny = gm[Np], area = gm[2 * (size_t)Np];   // unit normal out of the face's cell 0, face area
-            const BcParams * bc = nbr < 0 ? &a.ph.bcs[-nbr - 1] : nullptr;
-            auto flux_at = [&](int q, double * ft) {
-                double Us[4], Pl[5];
-                if (TENO) ld4(a.Fc, (size_t)i * NPT + (slot * Q + q), Us); else ld4(a.Uin, i, Us);
-                if (nbr >= 0) {
-                    double Un[4];
-                    if (TENO) ld4(a.Fc, (size_t)nbr * NPT + (nslot * Q + q), Un); else ld4(a.Uin, (size_t)nbr, Un);
-                    const double * Ul = side1 ? Un : Us, * Ur = side1 ? Us : Un;    // L = the face's cell 0
-#ifdef MLB_STREAM_KERNELS
-                    riemann_flux_lean<RS>(ft, nx, ny, face_cons(a.ph.gas, Ul), face_cons(a.ph.gas, Ur), a.ph.gas.gamma);
-#else
-                    double Pr[5];
-                    cons_to_prim(a.ph.gas, Ul, Pl);
-                    cons_to_prim(a.ph.gas, Ur, Pr);
-                    const FaceState L = {Ul[0], Pl[0], Pl[1], Pl[2], Pl[4]};
-                    const FaceState R = {Ur[0], Pr[0], Pr[1], Pr[2], Pr[4]};
-                    riemann_flux<RS>(ft, nx, ny, L, R, a.ph.gas.gamma);
-#endif
-                    return;
-                }
-                cons_to_prim(a.ph.gas, Us, Pl);       // boundary face: this cell is the face's cell 0
-                if (bc->type == MLB_BC_WALL_ADIABATIC) {          // boundary_wall_adiabatic.cpp:39-70
-                    ft[0] = 0.0; ft[1] = Pl[2] * nx; ft[2] = Pl[2] * ny; ft[3] = 0.0;
-                } else {
-                    FaceState gh;
-                    ghost_state(*bc, a.ph.gas, nx, ny, Us, Pl, gh);
-#ifdef MLB_STREAM_KERNELS
-                    riemann_flux_lean<RS>(ft, nx, ny, face_cons(a.ph.gas, Us), face_cons(gh), a.ph.gas.gamma);
-#else
-                    const FaceState L = {Us[0], Pl[0], Pl[1], Pl[2], Pl[4]};
-                    riemann_flux<RS>(ft, nx, ny, L, gh, a.ph.gas.gamma);
-#endif
-                }
-            };
-            if (QT > 0) {
-#pragma unroll
-                for (int q = 0; q < (QT > 0 ? QT : 1); q++) {
-                    double ft[4];
-                    flux_at(q, ft);
-                    const double wq = a.ph.qf_w[q];
-#pragma unroll
-                    for (int v = 0; v < 4; v++) fsum[v] += wq * ft[v];     // flux_functor.h:151
-                }
-            } else {
-                for (int q = 0; q < Q; q++) {
-                    double ft[4];
-                    flux_at(q, ft);
-                    const double wq = a.ph.qf_w[q];
-#pragma unroll
-                    for (int v = 0; v < 4; v++) fsum[v] += wq * ft[v];
-                }
-            }
-#pragma unroll
-            for (int v = 0; v < 4; v++) fsum[v] = area * (fsum[v] * 0.5);   // flux_functor.h:153,156-161: (-A)*F == -(A*F) exactly
-            fl = side1 ? 3 : 1;
-        }
-    }
-    parked[slot][c] = make_double4(fsum[0], fsum[1], fsum[2], fsum[3]);
-    flag[slot][c] = fl;
-    __syncthreads();
-    if (slot != 0 || i >= a.g.N_owned) return;
+    const int NPT = a.g.n_slots * Q;                     // face-value points per cell
+    const uint32_t cl = a.g.face_cl[f];
+    const int32_t cr = a.g.face_cr[f];
+    const double nx = a.g.face_nx[f], ny = a.g.face_ny[f], area = a.g.face_area[f];
+    const uint32_t slots = TENO ? a.g.face_slots[f] : 0u;
+    const int sl = slots & 15u, sr = slots >> 4;
+    const bool no_flux = cr == INT32_MIN;                // boundary zone without a [[boundaries]] entry
+    const BcParams * bc = (cr < 0 && !no_flux) ? &a.ph.bcs[-cr - 1] : nullptr;
 
+    auto flux_at = [&](int q, double * ft) {
+        double Ul[4], Pl[5];
+        if (TENO) ld4(a.Fc, (size_t)cl * NPT + (sl * Q + q), Ul); else ld4(a.Uin, cl, Ul);
+        if (cr >= 0) {
+            double Ur[4];
+            if (TENO) ld4(a.Fc, (size_t)cr * NPT + (sr * Q + q), Ur); else ld4(a.Uin, (size_t)cr, Ur);
+#ifdef MLB_STREAM_KERNELS
+            riemann_flux_lean<RS>(ft, nx, ny, face_cons(a.ph.gas, Ul), face_cons(a.ph.gas, Ur), a.ph.gas.gamma);
+#else
+            double Pr[5];
+            cons_to_prim(a.ph.gas, Ul, Pl);
+            cons_to_prim(a.ph.gas, Ur, Pr);
+            const FaceState L = {Ul[0], Pl[0], Pl[1], Pl[2], Pl[4]};
+            const FaceState R = {Ur[0], Pr[0], Pr[1], Pr[2], Pr[4]};
+            riemann_flux<RS>(ft, nx, ny, L, R, a.ph.gas.gamma);
+#endif
+            return;
+        }
+        cons_to_prim(a.ph.gas, Ul, Pl);
+        if (bc->type == MLB_BC_WALL_ADIABATIC) {          // boundary_wall_adiabatic.cpp:39-70
+            ft[0] = 0.0; ft[1] = Pl[2] * nx; ft[2] = Pl[2] * ny; ft[3] = 0.0;
+        } else {
+            FaceState gh;
+            ghost_state(*bc, a.ph.gas, nx, ny, Ul, Pl, gh);
+#ifdef MLB_STREAM_KERNELS
+            riemann_flux_lean<RS>(ft, nx, ny, face_cons(a.ph.gas, Ul), face_cons(gh), a.ph.gas.gamma);
+#else
+            const FaceState L = {Ul[0], Pl[0], Pl[1], Pl[2], Pl[4]};
+            riemann_flux<RS>(ft, nx, ny, L, gh, a.ph.gas.gamma);
+#endif
+        }
+    };
+
+    double fsum[4] = {0.0, 0.0, 0.0, 0.0};
+    if (QT == 0) {
+        if (!no_flux)
+            for (int q = 0; q < Q; q++) {
+                double ft[4];
+                flux_at(q, ft);
+                const double wq = a.ph.qf_w[q];
+#pragma unroll
+                for (int v = 0; v < 4; v++) fsum[v] += wq * ft[v];     // flux_functor.h:151
+            }
+    } else {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        if (!no_flux) {
+            double ft[4];
+            flux_at(lane_q, ft);
+            const double wq = a.ph.qf_w[lane_q];
+#pragma unroll
+            for (int v = 0; v < 4; v++) t[v] = wq * ft[v];
+        }
+#pragma unroll
+        for (int q = 0; q < TPF; q++) {                                // fsum = ((0 + t_0) + t_1) + ..., flux_functor.h:151
+#pragma unroll
+            for (int v = 0; v < 4; v++) fsum[v] += __shfl_sync(0xffffffffu, t[v], q, TPF);
+        }
+        if (lane_q != 0) return;
+    }
+    if (!valid) return;
+#pragma unroll
+    for (int v = 0; v < 4; v++) fsum[v] = area * (fsum[v] * 0.5);   // flux_functor.h:153,156-161: (-A)*F == -(A*F) exactly
+    reinterpret_cast<double4 *>(a.AF)[f] = make_double4(fsum[0], fsum[1], fsum[2], fsum[3]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Residual gather + RK update.  One thread per owned cell, no atomics: each cell sums -+ the stored face products in
+// the reference's (Serial back-end) accumulation order, divides by its volume (DivideVolumeFunctor,
+// solver_rhs.cpp:18-42) and applies the stage combination; the last stage also refreshes the primitives.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_stage_kernel(const __grid_constant__ StageArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.g.N_owned) return;
+    const uint32_t Np = a.g.Npad;
     double k[4];
     if (a.k_override) {
         ld4(a.k_override, i, k);
@@ -423,15 +420,17 @@ __global__ void __launch_bounds__(NS * CELL_CB, MLB_CELL_MINB) cell_stage_kernel
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         const uint32_t order = a.g.rhs_order[i];
         const int nf = a.g.nfc[i];
+        const double4 * AF = reinterpret_cast<const double4 *>(a.AF);
 #pragma unroll
-        for (int jj = 0; jj < NS; jj++) {
+        for (int jj = 0; jj < MAX_SLOTS; jj++) {
             if (jj < nf) {
                 const int s = (order >> (2 * jj)) & 3;
-                const uint8_t f = flag[s][c];
-                if (f) {
-                    const double4 P = parked[s][c];
-                    if (f & 2) { acc[0] += P.x; acc[1] += P.y; acc[2] += P.z; acc[3] += P.w; }
-                    else       { acc[0] -= P.x; acc[1] -= P.y; acc[2] -= P.z; acc[3] -= P.w; }
+                const int32_t nbr = a.g.slot_nbr[(size_t)s * Np + i];
+                if (nbr != INT32_MIN) {
+                    const uint32_t fcode = a.g.slot_face[(size_t)s * Np + i];
+                    const double4 P = AF[fcode & 0x7FFFFFFFu];
+                    if (fcode >> 31) { acc[0] += P.x; acc[1] += P.y; acc[2] += P.z; acc[3] += P.w; }
+                    else             { acc[0] -= P.x; acc[1] -= P.y; acc[2] -= P.z; acc[3] -= P.w; }
                 }
             }
         }
@@ -632,8 +631,9 @@ __global__ void __launch_bounds__(256) cfl_kernel(const __grid_constant__ CflArg
         const double rho_s = a.prim[5 * (size_t)Np + i], u_s = a.prim[i], v_s = a.prim[(size_t)Np + i], p_s = a.prim[2 * (size_t)Np + i];
         const double sos_s = sqrt(a.gas.gamma * p_s / rho_s);
         for (int j = 0; j < nf; j++) {
-            const uint32_t side = a.g.slot_meta[(size_t)j * Np + i] >> 7;
-            const double nx = a.g.slot_geom[((size_t)j * 3) * Np + i], ny = a.g.slot_geom[((size_t)j * 3 + 1) * Np + i];
+            const uint32_t fcode = a.g.slot_face[(size_t)j * Np + i];
+            const uint32_t f = fcode & 0x7FFFFFFFu, side = fcode >> 31;
+            const double nx = a.g.face_nx[f], ny = a.g.face_ny[f];
             const int32_t nbr = a.g.slot_nbr[(size_t)j * Np + i];
             double sx, sy, sos_l, sos_r, ul, vl, ur, vr;
             if (nbr < 0) {   // boundary "hack" :662-666 — l = r = this cell
@@ -723,25 +723,25 @@ __global__ void prims_soa_kernel(const GasParams g, uint32_t n, uint32_t npad, c
 // ---------------------------------------------------------------------------------------------------------------
 // Launchers
 // ---------------------------------------------------------------------------------------------------------------
-template <int RS, int NS>
-static void launch_stage_t(const StageArgs & a, cudaStream_t st) {
-    const unsigned grid = (a.g.N_owned + CELL_CB - 1) / CELL_CB;
-    if (!grid) return;
-    if (!a.teno) cell_stage_kernel<RS, false, 1, NS><<<grid, NS * CELL_CB, 0, st>>>(a);
-    else if (a.g.Q == 1) cell_stage_kernel<RS, true, 1, NS><<<grid, NS * CELL_CB, 0, st>>>(a);
-    else if (a.g.Q == 2) cell_stage_kernel<RS, true, 2, NS><<<grid, NS * CELL_CB, 0, st>>>(a);
-    else cell_stage_kernel<RS, true, 0, NS><<<grid, NS * CELL_CB, 0, st>>>(a);
-}
 template <int RS>
-static void launch_stage_rs(const StageArgs & a, cudaStream_t st) {
-    if (a.g.n_slots <= 3) launch_stage_t<RS, 3>(a, st); else launch_stage_t<RS, 4>(a, st);
+static void launch_faces_rs(const StageArgs & a, cudaStream_t st) {
+    if (a.g.NF == 0) return;
+    auto grid = [&](unsigned tpf) { return (unsigned)(((uint64_t)a.g.NF * tpf + 127u) / 128u); };
+    if (!a.teno) face_flux_kernel<RS, false, 1><<<grid(1), 128, 0, st>>>(a);
+    else if (a.g.Q == 1) face_flux_kernel<RS, true, 1><<<grid(1), 128, 0, st>>>(a);
+    else if (a.g.Q == 2) face_flux_kernel<RS, true, 2><<<grid(2), 128, 0, st>>>(a);
+    else face_flux_kernel<RS, true, 0><<<grid(1), 128, 0, st>>>(a);
+}
+static void launch_faces(const StageArgs & a, cudaStream_t st) {
+    switch (a.ph.riemann) {
+        case MLB_RIEMANN_RUSANOV: launch_faces_rs<MLB_RIEMANN_RUSANOV>(a, st); break;
+        case MLB_RIEMANN_HLL: launch_faces_rs<MLB_RIEMANN_HLL>(a, st); break;
+        default: launch_faces_rs<MLB_RIEMANN_HLLC>(a, st); break;
+    }
 }
 static void launch_stage(const StageArgs & a, cudaStream_t st) {
-    switch (a.ph.riemann) {
-        case MLB_RIEMANN_RUSANOV: launch_stage_rs<MLB_RIEMANN_RUSANOV>(a, st); break;
-        case MLB_RIEMANN_HLL: launch_stage_rs<MLB_RIEMANN_HLL>(a, st); break;
-        default: launch_stage_rs<MLB_RIEMANN_HLLC>(a, st); break;
-    }
+    const unsigned grid = (a.g.N_owned + 255u) / 256u;
+    if (grid) gather_stage_kernel<<<grid, 256, 0, st>>>(a);
 }
 
 template <int ORDER, int MP>
@@ -805,10 +805,10 @@ static void launch_prims_soa(const GasParams & g, uint32_t n, uint32_t npad, con
 #define MLB_STR2(x) #x
 #define MLB_STR(x) MLB_STR2(x)
 #ifdef MLB_STREAM_KERNELS
-static const KernelTable table = {MLB_STR(MLB_KNS), launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
+static const KernelTable table = {MLB_STR(MLB_KNS), launch_faces, launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
                                   launch_prims_soa, recon_supported, stream::launch_stream, stream::stream_supported};
 #else
-static const KernelTable table = {MLB_STR(MLB_KNS), launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
+static const KernelTable table = {MLB_STR(MLB_KNS), launch_faces, launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
                                   launch_prims_soa, recon_supported, nullptr, nullptr};
 #endif
 

@@ -117,6 +117,9 @@ struct Prep {
     dvec cell_xy;          // [2][Npad]
     dvec face_nx, face_ny, face_area;   // [NFpad] unit normal (common_math.h:101-106) and area
     dvec slot_fx;          // TENO: [n_slots][4][Npad] face end points in the cell's reference coordinates
+    uvec face_cl;          // [NFpad] library cell on side 0 of the face
+    ivec face_cr;          // [NFpad] library cell on side 1 ; < 0: -(bc index + 1) ; INT32_MIN: no flux through this face
+    std::vector<uint8_t> face_slots;   // [NFpad] slot in cell 0 | slot in cell 1 << 4
     dvec qf_x, qf_w;       // face quadrature
     TenoTables teno;
     double seconds = 0.0, seconds_stencils = 0.0, seconds_matrices = 0.0;

@@ -726,6 +726,29 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
 
     if (!slot_err.empty()) throw std::runtime_error(slot_err);
     tick("slots done");
+    // ---- face-centred view of the same connectivity (face flux kernel)
+    P.face_cl.assign(P.NFpad, 0u);
+    P.face_cr.assign(P.NFpad, INT32_MIN);
+    P.face_slots.assign(P.NFpad, 0);
+    for (uint32_t i = 0; i < n_recon; i++)
+        for (int j = 0; j < (int)P.n_faces_of_cell[i]; j++) {
+            const size_t at = (size_t)j * Np + i;
+            const uint32_t fcode = P.slot_face[at];
+            if (fcode == NO_FACE) continue;
+            const uint32_t f = fcode & 0x7FFFFFFFu;
+            if (fcode >> 31) P.face_slots[f] |= (uint8_t)(j << 4);
+            else {
+                P.face_cl[f] = i;
+                P.face_slots[f] |= (uint8_t)j;
+                if (P.slot_nbr[at] < 0) P.face_cr[f] = P.slot_nbr[at];
+            }
+            if (P.slot_nbr[at] >= 0) {   // interior face: side 1 cell, whichever side we are looking from
+                if (fcode >> 31) { P.face_cr[f] = (int32_t)i; P.face_cl[f] = (uint32_t)P.slot_nbr[at]; }
+                else P.face_cr[f] = P.slot_nbr[at];
+            }
+        }
+
+    tick("face view done");
     // ---- TENO tables
     if (teno) {
         const int K = T.K, M = T.M, Mp = T.Mp, S = T.S;
