@@ -204,7 +204,7 @@ WEDGE_FULL = WEDGE.replace("n_steps = 400", "t_stop = 0.1").replace("interval = 
 
 
 @pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(DROPIN)), reason="oracle/_ref binaries not built (need /root/reference)")
-def test_wedge_to_t_stop_through_the_reference_host(tmp_path):
+def test_wedge_to_t_stop_through_the_reference_host(tmp_path, capsys):
     """BASELINE configs[2] verbatim (examples/wedge/input.toml: t_stop = 0.1): the reference host loop decides when to stop
     from the dt the library returns, so the step count (7938) is itself a parity result.  Once the oblique shock has formed HLLC's
     star-pressure estimate leaves the PVRS branch for TRRS, whose pow() is libm's on the host and CUDA's on the device (last-ulp
@@ -235,7 +235,8 @@ def test_wedge_to_t_stop_through_the_reference_host(tmp_path):
                     assert np.array_equal(va[k], vb[k]), (f, k)
             per_file.append("%s %.1e" % (f[-10:-4], wf))
             worst = max(worst, wf)
-        print("wedge to t_stop [%s]: %d steps, %d/%d files byte-identical, field difference per file: %s" % (fp, info["steps"], identical, len(fa), ", ".join(per_file)))
+        with capsys.disabled():
+            print("\nwedge to t_stop [%s]: %d steps, %d/%d files byte-identical, field difference per file: %s" % (fp, info["steps"], identical, len(fa), ", ".join(per_file)))
         assert worst <= tol
         if fp == "strict":
             assert identical >= 2
@@ -299,7 +300,7 @@ TENO_SMOOTH = ("1.0 + 0.2 * sin(2 * pi * x) * cos(2 * pi * y)", "0.5 + 0.1 * cos
 @pytest.mark.parametrize("ic,n_steps,basis", [(TENO_RIEMANN, 1, "legendre"), (TENO_SMOOTH, 1, "legendre"), (TENO_SMOOTH, 1, None)],
                          ids=["riemann_2d-IC", "smooth-IC", "smooth-IC-default-basis(monomial)"])
 @pytest.mark.parametrize("fp", ["strict", "fast"])
-def test_teno_toml_through_the_reference_host(tmp_path, ic, n_steps, basis, fp):
+def test_teno_toml_through_the_reference_host(tmp_path, ic, n_steps, basis, fp, capsys):
     """examples/riemann_2d's numerics block (TENO + HLLC + SSPRK3, cfl 0.1) on a small cartesian_tri mesh through the
     UNMODIFIED reference host with the hot path rerouted, against the stock binary, after the first step.  On the
     four-quadrant IC the reference turns non-finite inside that step: the non-finite pattern of every written
@@ -327,5 +328,6 @@ def test_teno_toml_through_the_reference_host(tmp_path, ic, n_steps, basis, fp):
                 # discontinuity branch leaves entries many orders of magnitude apart in one field)
                 den = np.maximum(np.abs(x[ok]), 1e-6 * np.abs(x[ok]).max() + 1e-300)
                 worst = max(worst, float(np.max(np.abs(x[ok] - y[ok]) / den)))
-    print("TENO through the reference host [%s]: %d non-finite entries (coinciding), worst finite difference %.2e" % (fp, n_bad, worst))
+    with capsys.disabled():
+        print("\nTENO through the reference host [%s]: %d non-finite entries (coinciding), worst finite difference %.2e" % (fp, n_bad, worst))
     assert worst <= (1e-11 if fp == "strict" else 1e-9)
