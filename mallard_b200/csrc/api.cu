@@ -122,6 +122,13 @@ struct mlb_ctx {
     cudaEvent_t ev[16] = {};
     uint64_t launches = 0;
     uint64_t graph_replays = 0;        // steps of mlb_run executed as CUDA graph replays
+    // one captured time step, kept across calls of mlb_run / mlb_run_distributed (valid while the things baked into it are the
+    // same: cfl, the buffer rotation, the residual override, single-GPU or distributed schedule)
+    cudaGraphExec_t step_graph = nullptr;
+    double step_graph_cfl = 0.0;
+    int step_graph_cur = -1;
+    bool step_graph_override = false, step_graph_distributed = false;
+    uint64_t step_graph_launches = 0;
     bool profiling = false;
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
     std::map<std::string, ProfileEntry> profile;
@@ -173,6 +180,7 @@ struct mlb_ctx {
             if (nccl_p2p) nccl().CommDestroy(nccl_p2p);
         } catch (...) {}
         for (auto & p : pending) { cudaEventDestroy(p.second.first); cudaEventDestroy(p.second.second); }
+        if (step_graph) cudaGraphExecDestroy(step_graph);
         for (void * p : owned_dev) cudaFree(p);
         if (d_stage) cudaFree(d_stage);
         if (h_stage) cudaFreeHost(h_stage);
@@ -615,6 +623,49 @@ void halo_unpack(mlb_ctx & c, int buf, bool first_stage) {
     if (c.comm_stream) { CUDA_OK(cudaEventRecord(c.ev_halo, cs)); c.halo_pending = true; }
 }
 
+// Runs n_steps of `one_step`, replaying it as a CUDA graph: the first call runs one step eagerly (kernels get their function
+// attributes, NCCL its connections, errors are reported with a message), captures the next one - every stream it forks to
+// included - and keeps the executable graph in the context; later calls replay straight away.  dt, t and the step counter
+// live on the device and the stage buffers of SSPRK3 / RK4 return to the same rotation after a step, so every replay is the same
+// graph.  Returns false (with `why`) if the step cannot be captured; the caller decides whether plain launches are acceptable.
+template <class F>
+bool run_steps_as_graph(mlb_ctx & c, uint32_t n_steps, double cfl, bool distributed, cudaStreamCaptureMode mode, F && one_step, std::string & why) {
+    uint32_t done = 0;
+    const bool cached = c.step_graph && c.step_graph_cfl == cfl && c.step_graph_cur == c.cur && c.step_graph_override == c.has_override &&
+                        c.step_graph_distributed == distributed;
+    if (!cached) {
+        if (c.step_graph) { cudaGraphExecDestroy(c.step_graph); c.step_graph = nullptr; }
+        one_step();
+        done = 1;
+        const uint64_t l0 = c.launches;
+        cudaGraph_t g = nullptr;
+        CUDA_OK(cudaStreamBeginCapture(c.stream, mode));
+        bool ok = true;
+        try { one_step(); } catch (const std::exception & e) { ok = false; why = e.what(); }
+        const cudaError_t ec = cudaStreamEndCapture(c.stream, &g);
+        c.step_graph_launches = c.launches - l0;
+        c.launches = l0;                             // nothing ran during the capture
+        cudaGraphExec_t ge = nullptr;
+        const bool inst = ok && ec == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess;
+        if (g) cudaGraphDestroy(g);
+        if (!inst) {
+            if (why.empty()) why = cudaGetErrorString(ec != cudaSuccess ? ec : cudaGetLastError());
+            cudaGetLastError();
+            c.halo_pending = false; c.stage_begun = -1;
+            for (; done < n_steps; done++) one_step();       // (single GPU) plain launches; a distributed caller reports `why`
+            return false;
+        }
+        c.step_graph = ge; c.step_graph_cfl = cfl; c.step_graph_cur = c.cur; c.step_graph_override = c.has_override;
+        c.step_graph_distributed = distributed;
+    }
+    for (; done < n_steps; done++) {
+        CUDA_OK(cudaGraphLaunch(c.step_graph, c.stream));
+        c.launches += c.step_graph_launches;
+        c.graph_replays++;
+    }
+    return true;
+}
+
 // ---- native multi-GPU driver: NCCL over NVLink, no host code between the stages of a step -----------------------------------
 void require_comm(const mlb_ctx & c) {
     if (!c.nccl_p2p) throw std::runtime_error("the context has no communicator: call mlb_comm_init first");
@@ -892,30 +943,13 @@ int mlb_run(mlb_ctx * c, uint32_t n_steps, double cfl, double * t_out, double * 
         do_step(*c);
     };
     // Small meshes (examples/sod: 1000 cells, examples/wedge: 7500) are launch-bound: 7-10 kernels of a few microseconds per
-    // step.  One step is captured into a CUDA graph and replayed; dt, t and the step counter live on the device, and the
-    // stage buffers of SSPRK3 / RK4 return to the same rotation after a step, so every replay is the same graph.
+    // step, so the step is replayed as a CUDA graph (run_steps_as_graph); large ones lose nothing by it.
     static const bool graphs = [] { const char * e = getenv("MLB_RUN_GRAPH"); return !(e && e[0] == '0'); }();
     uint32_t done = 0;
-    if (graphs && !c->profiling && n_steps >= 8 && c->num.integrator != MLB_INTEGRATOR_FE) {
-        one_step();                                   // eager: function attributes, occupancy queries, error reporting
-        done = 1;
-        const uint64_t l0 = c->launches;
-        cudaGraph_t g = nullptr;
-        cudaGraphExec_t ge = nullptr;
-        CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        bool ok = true;
-        try { one_step(); } catch (...) { ok = false; }
-        const cudaError_t ec = cudaStreamEndCapture(c->stream, &g);
-        const uint64_t per_step = c->launches - l0;
-        c->launches = l0;                             // nothing ran during the capture
-        if (ok && ec == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) {
-            for (; done < n_steps; done++) { CUDA_OK(cudaGraphLaunch(ge, c->stream)); c->launches += per_step; }
-            c->graph_replays += n_steps - 1;
-        } else {
-            cudaGetLastError();                       // capture not possible here: fall through to plain launches
-        }
-        if (ge) cudaGraphExecDestroy(ge);
-        if (g) cudaGraphDestroy(g);
+    if (graphs && !c->profiling && (n_steps >= 8 || (c->step_graph && n_steps)) && c->num.integrator != MLB_INTEGRATOR_FE) {
+        std::string why;
+        run_steps_as_graph(*c, n_steps, cfl, false, cudaStreamCaptureModeThreadLocal, one_step, why);
+        done = n_steps;
     }
     for (; done < n_steps; done++) one_step();
     double sc[SC_COUNT];
@@ -1321,37 +1355,16 @@ int mlb_run_distributed(mlb_ctx * c, uint32_t n_steps, double cfl, double * t_ou
     CUDA_OK(cudaSetDevice(c->device));
     require_comm(*c);
     if (!(cfl > 0.0) && n_steps) require_dt(*c);
-    // As in mlb_run: one eager step (NCCL sets up its connections, kernels get their attributes), then the step is captured -
-    // both streams, the grouped send/recv and the all-reduce included - and replayed as one CUDA graph per step.
+    // As in mlb_run: the step - both streams, the grouped send/recv and the all-reduce included - is captured once and replayed
+    // as one CUDA graph per step.
     static const bool graphs = [] { const char * e = getenv("MLB_RUN_GRAPH"); return !(e && e[0] == '0'); }();
     uint32_t done = 0;
-    if (graphs && !c->profiling && n_steps >= 4 && c->num.integrator != MLB_INTEGRATOR_FE) {
-        do_step_distributed(*c, cfl);
-        done = 1;
-        const uint64_t l0 = c->launches;
-        cudaGraph_t g = nullptr;
-        cudaGraphExec_t ge = nullptr;
-        CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
-        bool ok = true;
+    if (graphs && !c->profiling && (n_steps >= 4 || (c->step_graph && n_steps)) && c->num.integrator != MLB_INTEGRATOR_FE) {
         std::string why;
-        try { do_step_distributed(*c, cfl); } catch (const std::exception & e) { ok = false; why = e.what(); }
-        const cudaError_t ec = cudaStreamEndCapture(c->stream, &g);
-        const uint64_t per_step = c->launches - l0;
-        c->launches = l0;                             // nothing ran during the capture
-        if (ok && ec == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) {
-            for (; done < n_steps; done++) { CUDA_OK(cudaGraphLaunch(ge, c->stream)); c->launches += per_step; }
-            c->graph_replays += n_steps - 1;
-        } else {
-            cudaGetLastError();
-            c->halo_pending = false; c->stage_begun = -1;
-            if (ge) cudaGraphExecDestroy(ge);
-            if (g) cudaGraphDestroy(g);
-            // every rank must issue the same collectives: a rank that cannot capture cannot silently fall back on its own
-            throw std::runtime_error("mlb_run_distributed: the step could not be captured into a CUDA graph (" +
-                                     (why.empty() ? std::string(cudaGetErrorString(ec)) : why) + "); set MLB_RUN_GRAPH=0 on every rank");
-        }
-        if (ge) cudaGraphExecDestroy(ge);
-        if (g) cudaGraphDestroy(g);
+        // every rank must issue the same collectives: a rank that cannot capture reports it instead of diverging silently
+        if (!run_steps_as_graph(*c, n_steps, cfl, true, cudaStreamCaptureModeRelaxed, [&] { do_step_distributed(*c, cfl); }, why))
+            throw std::runtime_error("mlb_run_distributed: the step could not be captured into a CUDA graph (" + why + "); set MLB_RUN_GRAPH=0 on every rank");
+        done = n_steps;
     }
     for (; done < n_steps; done++) do_step_distributed(*c, cfl);
     if (c->comm_stream) CUDA_OK(cudaStreamSynchronize(c->comm_stream));
