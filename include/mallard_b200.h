@@ -54,7 +54,11 @@ typedef struct {
 } mlb_zone;
 
 /* mesh/mesh.h:228-253 — the arrays the hot path consumes.  Geometry pointers may be NULL, in which case the
- * library computes them exactly as Mesh::compute_* does (mesh/mesh.cpp:167-261). */
+ * library computes them exactly as Mesh::compute_* does (mesh/mesh.cpp:167-261).  Cells are triangles or quadrilaterals, in any
+ * mix; TENO on quadrilaterals is new (the reference throws, numerics/face_reconstruction.cpp:485-487): a quadrilateral is
+ * integrated as the two triangles Mesh::compute_cell_volumes splits it into, its reference frame is spanned by the edges
+ * node 0 -> node 1 and node 0 -> node 3, and it carries its own basis means (no oracle; tests/test_gpu_parity.py checks
+ * k-exactness). */
 typedef struct {
     uint32_t n_cells, n_faces, n_nodes;
     const double *node_coords;              /* [n_nodes][2] */
@@ -80,9 +84,13 @@ typedef struct {
     int32_t riemann;                 /* MLB_RIEMANN_* */
     int32_t integrator;              /* MLB_INTEGRATOR_* */
     int32_t basis;                   /* MLB_BASIS_* (TENO) */
-    int32_t basis_order;             /* TENO polynomial order p, 1..9 */
-    double max_stencil_size_factor;  /* TENO, default 2.0 */
-    int32_t quadrature_order_cell;   /* Dunavant order, 0 = reference default p+1 */
+    int32_t basis_order;             /* TENO polynomial order p, 1..9 (what numerics/basis.h:81-176 tabulates).  Every value the
+                                        reference accepts runs; p <= 4 with max_stencil_size_factor 2.0 on triangles (the examples'
+                                        configuration) has the specialised streaming kernels, everything else - p = 5..9, other
+                                        factors, quadrilaterals - a generic kernel (csrc/teno_generic.cuh) */
+    double max_stencil_size_factor;  /* TENO, default 2.0: M = floor(factor * K) cells per stencil (face_reconstruction.cpp:170-180) */
+    int32_t quadrature_order_cell;   /* Dunavant order 1..5, 0 = reference default p+1 (which does not exist for p >= 5: the reference
+                                        throws there too, numerics/quadrature.cpp:269) */
     int32_t quadrature_order_face;   /* Gauss-Legendre order, 0 = reference default (p+1)/2 */
     int32_t fp_mode;                 /* MLB_FP_* */
     int32_t renumber;                /* MLB_RENUMBER_* */
@@ -302,6 +310,12 @@ int mlb_host_mesh_from_arrays(mlb_host_mesh **out, const mlb_mesh *mesh);
  * mesh/mesh.cpp:41-43).  Gmsh MSH 2.2 ASCII, 2-D: triangles and quadrilaterals become cells, tagged 2-node lines name the
  * boundary zones ($PhysicalNames), "interior" lists the two-cell faces; geometry as Mesh::compute_* computes it. */
 int mlb_host_mesh_read_gmsh(mlb_host_mesh **out, const char *path);
+/* the same construction from cell-node lists already in memory (any mix of triangles and quadrilaterals, counter-clockwise):
+ * faces = unique cell edges, tagged boundary edges name the zones, the rest as for the reader */
+int mlb_host_mesh_from_cells(mlb_host_mesh **out, uint32_t n_nodes, const double *node_coords /* [n_nodes][2] */, uint32_t n_cells,
+                             const uint32_t *offsets_nodes_of_cell, const uint32_t *nodes_of_cell, uint32_t n_boundary_edges,
+                             const uint32_t *edge_nodes /* [n][2] */, const int32_t *edge_tags, uint32_t n_names,
+                             const int32_t *name_tags, const char *const *names);
 int mlb_host_mesh_write_gmsh(const mlb_mesh *mesh, const char *path);
 int mlb_host_mesh_view(const mlb_host_mesh *m, mlb_mesh *view);   /* pointers stay valid until mlb_host_mesh_free */
 void mlb_host_mesh_free(mlb_host_mesh *m);

@@ -108,6 +108,26 @@ class Mesh:
         m.zones = [(n, np.ascontiguousarray(f, dtype=np.uint32)) for n, f in zones]
         return m
 
+    @classmethod
+    def from_cells(cls, node_xy, offsets_nodes_of_cell, nodes_of_cell, boundary_edges=None, edge_tags=None, names=None):
+        """Mesh from cell-node lists (triangles / quadrilaterals, counter-clockwise): faces are the unique edges, tagged boundary
+        edges ([n][2] node pairs + tags, names = {tag: zone name}) name the zones - mlb_host_mesh_from_cells."""
+        xy = np.ascontiguousarray(node_xy, dtype=np.float64).reshape(-1, 2)
+        onc = np.ascontiguousarray(offsets_nodes_of_cell, dtype=np.uint32)
+        noc = np.ascontiguousarray(nodes_of_cell, dtype=np.uint32)
+        be = np.ascontiguousarray(boundary_edges if boundary_edges is not None else np.zeros((0, 2)), dtype=np.uint32).reshape(-1, 2)
+        bt = np.ascontiguousarray(edge_tags if edge_tags is not None else np.zeros(0), dtype=np.int32)
+        names = dict(names or {})
+        tags = np.array(sorted(names), dtype=np.int32)
+        cn = (C.c_char_p * max(1, len(tags)))(*[names[int(t)].encode() for t in tags])
+        h = C.c_void_p()
+        if lib().mlb_host_mesh_from_cells(C.byref(h), len(xy), _ptr(xy), len(onc) - 1, _ptr(onc), _ptr(noc), len(be), _ptr(be), _ptr(bt),
+                                          len(tags), _ptr(tags), cn):
+            raise MallardError(_last_error())
+        m = cls()
+        m._take(h)
+        return m
+
     @property
     def n_cells(self):
         return len(self.arrays["offsets_nodes_of_cell"]) - 1

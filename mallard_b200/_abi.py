@@ -119,6 +119,7 @@ SYMBOLS = {
     "mlb_host_mesh_generate": (C.c_int, [C.POINTER(VP), I32, U32, U32, DBL, DBL]),
     "mlb_host_mesh_from_arrays": (C.c_int, [C.POINTER(VP), C.POINTER(MeshView)]),
     "mlb_host_mesh_read_gmsh": (C.c_int, [C.POINTER(VP), C.c_char_p]),
+    "mlb_host_mesh_from_cells": (C.c_int, [C.POINTER(VP), U32, VP, U32, VP, VP, U32, VP, VP, U32, VP, C.POINTER(C.c_char_p)]),
     "mlb_host_mesh_write_gmsh": (C.c_int, [C.POINTER(MeshView), C.c_char_p]),
     "mlb_host_mesh_view": (C.c_int, [VP, C.POINTER(MeshView)]),
     "mlb_host_mesh_free": (None, [VP]),

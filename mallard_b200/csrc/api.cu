@@ -80,7 +80,7 @@ struct mlb_ctx {
     uint32_t * d_perm_cells = nullptr, * d_perm_faces = nullptr;
     uint32_t * d_st_ids = nullptr;
     double * d_st_area = nullptr, * d_st_mat = nullptr;
-    double * d_OI = nullptr, * d_psi_bar = nullptr;   // oscillation-indicator matrix, integral_psi_target, exponents (generic kernel)
+    double * d_OI = nullptr, * d_psi_bar = nullptr, * d_psi_bar_cell = nullptr;   // oscillation-indicator matrix, integral_psi_target, exponents (generic kernel)
     uint8_t * d_pidx = nullptr;
     bool streaming = false;            // FAST mode: compact streaming tables + teno_stream_kernel
     uint32_t * d_fm_ids = nullptr;
@@ -252,7 +252,7 @@ ReconArgs recon_args(mlb_ctx & c, const double * Uin) {
         for (int i = 0; i < T.K; i++) { r.psi_bar[i] = T.psi_bar[i]; r.pidx[2 * i] = T.pidx[2 * i]; r.pidx[2 * i + 1] = T.pidx[2 * i + 1]; }
         for (int i = 0; i < T.K * T.K; i++) r.OI[i] = T.OI[i];
     }
-    r.OI_dev = c.d_OI; r.psi_bar_dev = c.d_psi_bar; r.pidx_dev = c.d_pidx;
+    r.OI_dev = c.d_OI; r.psi_bar_dev = c.d_psi_bar; r.pidx_dev = c.d_pidx; r.psi_bar_cell = c.d_psi_bar_cell;
     return r;
 }
 
@@ -546,6 +546,7 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
         } else {
             c->d_st_ids = c->upload(T.st_ids); c->d_st_area = c->upload(T.st_area); c->d_st_mat = c->upload(T.st_mat);
             c->d_OI = c->upload(T.OI); c->d_psi_bar = c->upload(T.psi_bar); c->d_pidx = c->upload(T.pidx);
+            if (T.mixed) c->d_psi_bar_cell = c->upload(T.psi_bar_cell);
         }
         CUDA_OK(cudaStreamSynchronize(c->stream));
         uvec().swap(T.st_ids); dvec().swap(T.st_area); dvec().swap(T.st_mat);   // host copies no longer needed
@@ -1593,6 +1594,18 @@ int mlb_host_mesh_read_gmsh(mlb_host_mesh ** out, const char * path) {
     if (!out || !path) throw std::runtime_error("NULL argument");
     std::unique_ptr<mlb_host_mesh> m(new mlb_host_mesh());
     host_mesh_read_gmsh(m->m, path);
+    *out = m.release();
+    API_END(none)
+}
+int mlb_host_mesh_from_cells(mlb_host_mesh ** out, uint32_t n_nodes, const double * node_coords, uint32_t n_cells, const uint32_t * offsets_nodes_of_cell,
+                             const uint32_t * nodes_of_cell, uint32_t n_boundary_edges, const uint32_t * edge_nodes, const int32_t * edge_tags,
+                             uint32_t n_names, const int32_t * name_tags, const char * const * names) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!out) throw std::runtime_error("NULL argument");
+    std::unique_ptr<mlb_host_mesh> m(new mlb_host_mesh());
+    host_mesh_from_cells(m->m, n_nodes, node_coords, n_cells, offsets_nodes_of_cell, nodes_of_cell, n_boundary_edges, edge_nodes, edge_tags, n_names,
+                         name_tags, names);
     *out = m.release();
     API_END(none)
 }

@@ -79,6 +79,7 @@ struct ReconArgs {
     const double * OI_dev;        // ... the generic kernel (any order <= 9: K <= 55) reads them from device memory
     const double * psi_bar_dev;
     const uint8_t * pidx_dev;
+    const double * psi_bar_cell;  // [Npad][K] or null: meshes with quadrilaterals carry the basis means per cell
 };
 
 struct ReconStreamArgs {       // teno_stream.cuh

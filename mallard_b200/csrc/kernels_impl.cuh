@@ -587,7 +587,10 @@ __global__ void __launch_bounds__(RECON_THREADS) teno_recon_kernel(const __grid_
 
     double cbar[K];                                                     // psi_bar_k / area_t[s][0] :1028-1029
 #pragma unroll
-    for (int k = 0; k < K; k++) cbar[k] = a.fixed_weights ? -a.psi_bar[k] : a.psi_bar[k] / area0;   // fixed: mean-free basis
+    for (int k = 0; k < K; k++) {
+        const double pb = a.psi_bar_cell ? a.psi_bar_cell[(size_t)cell * K + k] : a.psi_bar[k];
+        cbar[k] = a.fixed_weights ? -pb : pb / area0;   // fixed: mean-free basis
+    }
 
     const int nf = a.g.nfc[cell];
     const int Q = a.g.Q;

@@ -155,6 +155,22 @@ void host_mesh_read_gmsh(HostMesh & m, const char * path) {
     build_from_cells(m, xy, onc, noc, bedges, names);
 }
 
+void host_mesh_from_cells(HostMesh & m, uint32_t n_nodes, const double * node_xy, uint32_t n_cells, const uint32_t * onc, const uint32_t * noc,
+                          uint32_t n_edges, const uint32_t * edge_nodes, const int32_t * edge_tags, uint32_t n_names, const int32_t * name_tags,
+                          const char * const * names) {
+    if (!node_xy || !onc || !noc || (n_edges && (!edge_nodes || !edge_tags)) || (n_names && (!name_tags || !names)))
+        throw std::runtime_error("mesh from cells: NULL argument");
+    std::vector<BoundaryEdge> be(n_edges);
+    for (uint32_t i = 0; i < n_edges; i++) be[i] = {edge_nodes[2 * (size_t)i], edge_nodes[2 * (size_t)i + 1], edge_tags[i]};
+    std::map<int, std::string> nm;
+    for (uint32_t i = 0; i < n_names; i++) nm[name_tags[i]] = names[i];
+    for (uint32_t c = 0; c < n_cells; c++) {
+        const uint32_t k = onc[c + 1] - onc[c];
+        if (k != 3 && k != 4) throw std::runtime_error("mesh from cells: cells must have three or four nodes");
+    }
+    build_from_cells(m, dvec(node_xy, node_xy + 2 * (size_t)n_nodes), uvec(onc, onc + n_cells + 1), uvec(noc, noc + onc[n_cells]), be, nm);
+}
+
 void host_mesh_write_gmsh(const mlb_mesh & v, const char * path) {
     FILE * fh = fopen(path, "w");
     if (!fh) throw std::runtime_error(std::string("mesh file: cannot write ") + path);

@@ -34,6 +34,9 @@ void host_mesh_from_view(HostMesh & m, const mlb_mesh & v);
 void host_mesh_geometry(HostMesh & m);
 void host_mesh_read_gmsh(HostMesh & m, const char * path);          // mesh_io.cpp
 void host_mesh_write_gmsh(const mlb_mesh & v, const char * path);
+void host_mesh_from_cells(HostMesh & m, uint32_t n_nodes, const double * node_xy, uint32_t n_cells, const uint32_t * onc, const uint32_t * noc,
+                          uint32_t n_edges, const uint32_t * edge_nodes, const int32_t * edge_tags, uint32_t n_names, const int32_t * name_tags,
+                          const char * const * names);
 
 // ---------------------------------------------------------------------------------------------------------------
 // Gas constants (physics/physics.cpp:69-73)
@@ -71,6 +74,8 @@ struct TenoTables {
     std::vector<uint8_t> pidx;    // [K][2]
     dvec qc_xy, qc_w;             // Dunavant cell quadrature
     dvec psi_bar, OI;             // [K], [K][K]
+    bool mixed = false;           // the mesh holds quadrilaterals (new; the reference's TENO is triangles only): psi_bar per cell
+    dvec psi_bar_cell;            // [Npad][K] mean of every basis function over the cell itself, library numbering (mixed meshes only)
     // Tile-interleaved tables, n_tiles = ceil(N / TILE):
     //   st_ids  [tile][S][Mp][TILE]      u32   library cell ids; empty stencil -> all NO_FACE
     //   st_area [tile][S][Mp][TILE]      f64   transformed areas (0 padding)

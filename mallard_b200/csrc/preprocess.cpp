@@ -302,41 +302,51 @@ struct MatrixScratch {
 
 // Rows of the reconstruction matrix before the mean is removed: A[i][k] = area_t[i] * (mean of psi_k over stencil cell i,
 // in the target cell's reference coordinates), by cell quadrature (:525-596).
+// Cells with more than three nodes (new: the reference throws, :485-487): the target's reference frame is spanned by the
+// edges node 0 -> node 1 and node 0 -> last node (for a triangle exactly the reference's frame), and a stencil cell is
+// integrated as the fan of triangles (v0, v_j, v_j+1) - the split Mesh::compute_cell_volumes uses (mesh/mesh.cpp:196-215) -
+// A[i][k] = sum_tri area_t(tri) * mean_tri(psi_k), area_t[i] = sum_tri area_t(tri).  For triangles nothing changes, bit for bit.
 void integrate_basis_rows(const HostMesh & m, const TenoTables & t, uint32_t cell, const uint32_t * st, int M,
                           double * area_t, MatrixScratch & w) {
     const int K = t.K, nq = t.nq_cell, p = t.order;
     const double * X = m.node_xy.data();
     const uint32_t * cn = &m.noc[m.onc[cell]];
+    const int kc = m.nnc(cell);
     const double * o = &X[2 * (size_t)cn[0]];
     double J[4], Ji[4];
-    edge_frame(o, &X[2 * (size_t)cn[1]], &X[2 * (size_t)cn[2]], J);
+    edge_frame(o, &X[2 * (size_t)cn[1]], &X[2 * (size_t)cn[kc - 1]], J);
     mat2_inverse(J, Ji);
     w.A.resize((size_t)M * K);
     w.px.resize((size_t)(p + 1) * nq); w.py.resize((size_t)(p + 1) * nq);
     for (int i = 0; i < M; i++) {
         const uint32_t * nn = &m.noc[m.onc[st[i]]];
-        const double * v0 = &X[2 * (size_t)nn[0]], * v1 = &X[2 * (size_t)nn[1]], * v2 = &X[2 * (size_t)nn[2]];
-        double Jn[4];
-        edge_frame(v0, v1, v2, Jn);
-        double a[2] = {v0[0] - o[0], v0[1] - o[1]}, b[2] = {v1[0] - o[0], v1[1] - o[1]}, c[2] = {v2[0] - o[0], v2[1] - o[1]};
-        mat2_apply(Ji, a, a); mat2_apply(Ji, b, b); mat2_apply(Ji, c, c);
-        area_t[i] = tri_area2(a, b, c);
-        for (int q = 0; q < nq; q++) {   // quadrature point: neighbour reference -> physical -> target reference
-            double x[2] = {t.qc_xy[2 * q], t.qc_xy[2 * q + 1]};
-            mat2_apply(Jn, x, x);
-            x[0] += v0[0]; x[1] += v0[1];
-            x[0] -= o[0]; x[1] -= o[1];
-            mat2_apply(Ji, x, x);
-            for (int d = 0; d <= p; d++) {
-                w.px[(size_t)d * nq + q] = basis_1d(t.basis, 0, d, x[0]);
-                w.py[(size_t)d * nq + q] = basis_1d(t.basis, 0, d, x[1]);
+        const int kn = m.nnc(st[i]);
+        area_t[i] = 0.0;
+        for (int tri = 0; tri + 2 < kn; tri++) {
+            const double * v0 = &X[2 * (size_t)nn[0]], * v1 = &X[2 * (size_t)nn[tri + 1]], * v2 = &X[2 * (size_t)nn[tri + 2]];
+            double Jn[4];
+            edge_frame(v0, v1, v2, Jn);
+            double a[2] = {v0[0] - o[0], v0[1] - o[1]}, b[2] = {v1[0] - o[0], v1[1] - o[1]}, c[2] = {v2[0] - o[0], v2[1] - o[1]};
+            mat2_apply(Ji, a, a); mat2_apply(Ji, b, b); mat2_apply(Ji, c, c);
+            const double at = tri_area2(a, b, c);
+            for (int q = 0; q < nq; q++) {   // quadrature point: sub-triangle reference -> physical -> target reference
+                double x[2] = {t.qc_xy[2 * q], t.qc_xy[2 * q + 1]};
+                mat2_apply(Jn, x, x);
+                x[0] += v0[0]; x[1] += v0[1];
+                x[0] -= o[0]; x[1] -= o[1];
+                mat2_apply(Ji, x, x);
+                for (int d = 0; d <= p; d++) {
+                    w.px[(size_t)d * nq + q] = basis_1d(t.basis, 0, d, x[0]);
+                    w.py[(size_t)d * nq + q] = basis_1d(t.basis, 0, d, x[1]);
+                }
             }
-        }
-        for (int k = 0; k < K; k++) {
-            const int ex = t.pidx[2 * k], ey = t.pidx[2 * k + 1];
-            double s = 0.0;
-            for (int q = 0; q < nq; q++) s += t.qc_w[q] * (w.px[(size_t)ex * nq + q] * w.py[(size_t)ey * nq + q]);
-            w.A[(size_t)i * K + k] = s * area_t[i];
+            for (int k = 0; k < K; k++) {
+                const int ex = t.pidx[2 * k], ey = t.pidx[2 * k + 1];
+                double s = 0.0;
+                for (int q = 0; q < nq; q++) s += t.qc_w[q] * (w.px[(size_t)ex * nq + q] * w.py[(size_t)ey * nq + q]);
+                if (tri == 0) w.A[(size_t)i * K + k] = s * at; else w.A[(size_t)i * K + k] += s * at;
+            }
+            if (tri == 0) area_t[i] = at; else area_t[i] += at;
         }
     }
 }
@@ -506,7 +516,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
         T.nq_cell = (int)T.qc_w.size();
         T.keep_ref = opt.keep_ref_tables;
         for (uint32_t c = 0; c < m.nc; c++)
-            if (m.nnc(c) != 3) throw std::runtime_error("TENO has only been implemented for triangular cells.");
+            if (m.nnc(c) != 3) { T.mixed = true; if (m.nnc(c) != 4) throw std::runtime_error("TENO: cells must be triangles or quadrilaterals."); }
     }
 
     // ---- which cells this context holds: owned | ring-1 ghosts (reconstructed, not updated) | state-only ghosts
@@ -706,7 +716,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
                 const uint32_t * cn = &m.noc[m.onc[c]];
                 const double * o0 = &X[2 * (size_t)cn[0]];
                 double J[4], Ji[4];
-                edge_frame(o0, &X[2 * (size_t)cn[1]], &X[2 * (size_t)cn[2]], J);
+                edge_frame(o0, &X[2 * (size_t)cn[1]], &X[2 * (size_t)cn[m.nnc(c) - 1]], J);
                 mat2_inverse(J, Ji);
                 const uint32_t n0 = m.nof[m.onf[f]], n1 = m.nof[m.onf[f] + 1];
                 double x0[2] = {X[2 * (size_t)n0] - o0[0], X[2 * (size_t)n0 + 1] - o0[1]};
@@ -787,8 +797,28 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
                 one.node_xy.assign(opt.psi_ref_tri, opt.psi_ref_tri + 6);
                 one.onc = {0u, 3u}; one.noc = {0u, 1u, 2u};
                 integrate_basis_rows(one, T, 0, &self, 1, &a0, w);
-            } else integrate_basis_rows(m, T, 0, &self, 1, &a0, w);
+            } else {
+                uint32_t ref = 0;                          // the reference's cell 0 (a triangle there; the first triangle of a mixed mesh)
+                while (ref < m.nc && m.nnc(ref) != 3) ref++;
+                if (ref == m.nc) ref = 0;
+                integrate_basis_rows(m, T, ref, &ref, 1, &a0, w);
+            }
             for (int k = 0; k < K; k++) T.psi_bar[k] = w.A[k] / a0;
+        }
+        if (T.mixed) {   // quadrilaterals do not share one reference shape: their own mean of every basis function
+            T.psi_bar_cell.assign((size_t)P.Npad * K, 0.0);
+#pragma omp parallel
+            {
+                MatrixScratch w;
+#pragma omp for schedule(static)
+                for (int64_t ii = 0; ii < (int64_t)n_recon; ii++) {
+                    const uint32_t c = order[ii];
+                    double a0;
+                    if (m.nnc(c) == 3) { for (int k = 0; k < K; k++) T.psi_bar_cell[(size_t)ii * K + k] = T.psi_bar[k]; continue; }
+                    integrate_basis_rows(m, T, c, &c, 1, &a0, w);
+                    for (int k = 0; k < K; k++) T.psi_bar_cell[(size_t)ii * K + k] = w.A[k] / a0;
+                }
+            }
         }
         std::string err;
         const auto t_mat = std::chrono::steady_clock::now();
@@ -807,7 +837,7 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
                         const size_t base = (tile * S + s) * Mp;
                         if (T.st_ids[base * TILE + lane] == NO_FACE) continue;
                         for (int k2 = 0; k2 < M; k2++) st[k2] = T.st_ids[(base + k2) * TILE + lane];
-                        stencil_matrix(m, T, order[i], st.data(), M, T.psi_bar.data(), at.data(), Ai.data(), w);
+                        stencil_matrix(m, T, order[i], st.data(), M, T.mixed ? &T.psi_bar_cell[(size_t)i * K] : T.psi_bar.data(), at.data(), Ai.data(), w);
                         for (int k2 = 0; k2 < M; k2++) T.st_area[(base + k2) * TILE + lane] = at[k2];
                         if (strict_tables)
                             for (int k = 0; k < K; k++)

@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(GTHREADS) teno_generic_kernel(const __grid_con
             for (int s = 0; s < S; s++) {
                 if (w[s] == 0.0) continue;
                 for (int k = 0; k < K; k++) {
-                    const double cbar = a.fixed_weights ? -a.psi_bar_dev[k] : a.psi_bar_dev[k] / area0;   // psi_bar_k / area_t[s][0] :1028-1029
+                    const double pb = a.psi_bar_cell ? a.psi_bar_cell[(size_t)cell * K + k] : a.psi_bar_dev[k];
+                    const double cbar = a.fixed_weights ? -pb : pb / area0;   // psi_bar_k / area_t[s][0] :1028-1029
                     out += w[s] * dof[(size_t)(s * K + k) * GTHREADS] * (Px[a.pidx_dev[2 * k]] * Py[a.pidx_dev[2 * k + 1]] + cbar);
                 }
             }

@@ -65,6 +65,42 @@ def jittered_tri(nx, ny, Lx=1.0, Ly=1.0, seed=12345, amp=0.15, shuffle=True):
     return m.compute_geometry()
 
 
+def mixed_tri_quad(nx, ny, Lx=1.0, Ly=1.0, seed=12345, amp=0.15, tri_fraction=0.5, shuffle=True):
+    """Mixed-element mesh (BASELINE configs[3] as worded: "mixed tri/quad unstructured mesh"): an nx x ny grid on [0,Lx]x[0,Ly] with
+    jittered interior nodes in which a seeded random `tri_fraction` of the quads is cut into two triangles (along either diagonal)
+    and the rest stay quadrilaterals; cell order randomly permuted; zones left / right / top / bottom / interior.  The
+    reference's TENO throws on anything but triangles (face_reconstruction.cpp:485-487): there is no oracle for this mesh family."""
+    rng = np.random.default_rng(seed)
+    ii, jj = np.divmod(np.arange((nx + 1) * (ny + 1), dtype=np.int64), ny + 1)
+    X = np.stack([ii * (Lx / nx), jj * (Ly / ny)], 1)
+    if amp > 0:
+        h = min(Lx / nx, Ly / ny)
+        d = rng.uniform(-amp * h, amp * h, size=X.shape)
+        inner = (ii > 0) & (ii < nx) & (jj > 0) & (jj < ny)
+        X[inner] += d[inner]
+    node = lambda i, j: i * (ny + 1) + j
+    ic, jc = np.divmod(np.arange(nx * ny, dtype=np.int64), ny)
+    bl, br, tl, tr = node(ic, jc), node(ic + 1, jc), node(ic, jc + 1), node(ic + 1, jc + 1)
+    kind = np.where(rng.random(nx * ny) < tri_fraction, 1 + (rng.random(nx * ny) < 0.5).astype(np.int64), 0)   # 0 quad, 1 / 2 the two diagonals
+    cells = []
+    for q in range(nx * ny):
+        if kind[q] == 0:
+            cells.append((bl[q], br[q], tr[q], tl[q]))
+        elif kind[q] == 1:
+            cells += [(bl[q], br[q], tr[q]), (bl[q], tr[q], tl[q])]
+        else:
+            cells += [(bl[q], br[q], tl[q]), (br[q], tr[q], tl[q])]
+    if shuffle:
+        cells = [cells[i] for i in rng.permutation(len(cells))]
+    onc = np.concatenate([[0], np.cumsum([len(c) for c in cells])])
+    noc = np.fromiter((n for c in cells for n in c), dtype=np.int64)
+    jr, ir = np.arange(ny), np.arange(nx)
+    edges = np.concatenate([np.stack([node(0, jr), node(0, jr + 1)], 1), np.stack([node(nx, jr), node(nx, jr + 1)], 1),
+                            np.stack([node(ir, ny), node(ir + 1, ny)], 1), np.stack([node(ir, 0), node(ir + 1, 0)], 1)])
+    tags = np.concatenate([np.full(ny, 1), np.full(ny, 2), np.full(nx, 3), np.full(nx, 4)])
+    return Mesh.from_cells(X, onc, noc, edges, tags, {1: "left", 2: "right", 3: "top", 4: "bottom"})
+
+
 class LocalPart:
     """What jittered_tri_local returns: the rank-local mesh and how it sits in the global one."""
 
