@@ -50,9 +50,10 @@ def test_interface_errors_mirror_reference():
         mb.Solver(m, "FO", "HLLC", "SSPRK3", bcs=[dict(name="inlet", type="symmetry")])
     with pytest.raises(mb.MallardError, match="Missing p for boundary"):        # boundary_p_out.cpp:38-40
         mb.Solver(m, "FO", "HLLC", "SSPRK3", bcs=[dict(name="right", type="p_out")])
-    tri = mb.Mesh.generate("cartesian", 8, 8)
-    with pytest.raises(mb.MallardError, match="only been implemented for triangular"):   # face_reconstruction.cpp:485-487
-        mb.Plan(tri, "TENO", order=2)
+    # where the reference throws "TENO has only been implemented for triangular cells" (face_reconstruction.cpp:485-487), quadrilaterals
+    # are supported here: one central + four directional stencils per cell
+    quads = mb.Plan(mb.Mesh.generate("cartesian", 8, 8), "TENO", order=2)
+    assert (quads.S, quads.n_slots, quads.M) == (5, 4, 12)
 
 
 @pytest.mark.parametrize("mtype,nx,ny,Lx,Ly", [("cartesian", 7, 5, 2.0, 1.0), ("cartesian", 1000, 1, 1.0, 0.001),
@@ -275,7 +276,7 @@ def test_degenerate_meshes_are_handled_on_the_host():
     assert m.n_cells == 1 and dict((n, len(f)) for n, f in m.zones)["interior"] == 0
     p = mb.Plan(m, "FO", bcs=SYM4)
     assert (p.N, p.NF) == (1, 4)
-    with pytest.raises(mb.MallardError, match="only been implemented for triangular cells"):    # face_reconstruction.cpp:485-487
+    with pytest.raises(mb.MallardError, match="too small to fill a stencil"):                    # a single quadrilateral has no neighbours to reconstruct from
         mb.Plan(m, "TENO", order=3, bcs=SYM4)
     for n in (1, 2, 3):
         with pytest.raises(mb.MallardError, match="too small to fill a stencil"):
