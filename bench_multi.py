@@ -8,10 +8,16 @@ triangulation (2828^2 quads = 16.0 M cells; 5657^2 = 64.0 M cells where it fits)
 bisection; every rank builds ITS PART of the mesh only (synthetic.jittered_tri_local -> mlb_create_local), so no rank ever holds
 the global mesh.  value = global cells x stages x steps / time; efficiency is value_N / (N x value_1) of the same mesh.
 
-Both are driven by the library's native driver (mlb_comm_init / mlb_run_distributed: grouped ncclSend/ncclRecv between the
-library's device buffers on the communication stream under the reconstruction of the interior cells, ncclAllReduce(max) of dt,
-the step replayed as a CUDA graph).  torch.distributed ships the NCCL id, provides the barriers and reduces the timings.
+Driver of the partitioned step: by default the split-phase C ABI (mlb_halo_pack / mlb_stage_begin / mlb_stage ...) with
+torch.distributed as the communicator - NCCL send/recv straight between the library's device buffers on the library's
+communication stream under the reconstruction of the interior cells, all_reduce(max) of the device-resident dt - the path the
+round-1 scaling run proved on 2, 4 and 8 GPUs.  MLB_BENCH_NATIVE=1 selects the library's own NCCL driver instead (mlb_comm_init /
+mlb_run_distributed: the same schedule inside the library, the step replayed as a CUDA graph); measured on 2 GPUs
+(profiles/r02b_bench_n2_native.json), its 8-GPU run did not complete inside this round's GPU budget, so it is not the default.
 Timing: barrier + device synchronise on both sides, CUDA events on the library's compute stream, MAX over ranks.
+
+A watchdog ends the process cleanly (rank 0 prints the line with whatever records are complete) if the run approaches the
+driver's per-run limit: a strong-scaling record must never cost the main line.
 """
 import json
 import os
@@ -20,7 +26,30 @@ import time
 
 import numpy as np
 
+import sys
+import threading
+
 T_START = time.perf_counter()
+NATIVE = os.environ.get("MLB_BENCH_NATIVE") == "1"
+DEADLINE_S = float(os.environ.get("MLB_BENCH_DEADLINE", "760"))    # the driver kills a run at 870 s
+_STATE = {"line": None, "strong": [], "rank": 0, "done": False}
+
+
+def _watchdog():
+    while not _STATE["done"]:
+        time.sleep(1.0)
+        if time.perf_counter() - T_START > DEADLINE_S:
+            if _STATE["rank"] == 0 and _STATE["line"] is not None:
+                line = dict(_STATE["line"])
+                line["strong"] = list(_STATE["strong"]) + [{"aborted": "deadline of %.0f s reached before the remaining strong-scaling records finished" % DEADLINE_S}]
+                sys.stdout.write(json.dumps(line) + "\n")
+                sys.stdout.flush()
+            os._exit(0 if _STATE["line"] is not None or _STATE["rank"] != 0 else 3)
+
+
+def start_watchdog(rank):
+    _STATE["rank"] = rank
+    threading.Thread(target=_watchdog, daemon=True).start()
 STRONG_MESHES = (("vortex_16M", 2828), ("vortex_64M", 5657))      # BASELINE configs[3] (16 M cells) and the configs[4] mesh (64 M)
 MAX_CELLS_PER_GPU = 24.0e6                                        # TENO p=3 tables: 6.5 kB per cell of 180 GB
 TIME_BUDGET_S = 560.0                                             # do not start another strong record after this much wall time
@@ -108,6 +137,11 @@ class Run:
                 "kernels_this_rank": {k: {"ms_total": v[0], "launches": int(v[1])} for k, v in prof.items()}}
 
 
+TRANSPORT = ("grouped ncclSend/ncclRecv between device buffers + ncclAllReduce(max) of dt inside the library (mlb_run_distributed), step replayed as a CUDA graph"
+             if NATIVE else "NCCL send/recv between the library's device buffers on its communication stream + all_reduce(max) of the device-resident dt "
+                            "(split-phase C ABI driven over torch.distributed)")
+
+
 def strong_record(name, nq, a, rank, world, device, peak, peak_src):
     """Strong scaling: the nq x nq jittered, id-shuffled triangulation of [0,10]^2 split over `world` GPUs."""
     import bench
@@ -141,7 +175,7 @@ def strong_record(name, nq, a, rank, world, device, peak, peak_src):
         raise RuntimeError("rank-local mesh: ghost layers insufficient")
     if world > 1:
         from mallard_b200.parallel import DistributedSolver
-        ds = DistributedSolver.from_solver(s, rank, world, device, local=lp.local, native=True)
+        ds = DistributedSolver.from_solver(s, rank, world, device, local=lp.local, native=NATIVE)
     stats = s.get("stats")
     n_owned = int(stats[4])
     s.set_state(syn.isentropic_vortex(lp.mesh.arrays["cell_coords"]))
@@ -155,7 +189,7 @@ def strong_record(name, nq, a, rank, world, device, peak, peak_src):
         peers, sc, rc = s.halo_info()
         h = _reduce([float(sc.sum()), float(rc.sum()), float(len(peers))], world, "max")
         rec["halo"] = {"max_send_cells_per_stage": int(h[0]), "max_recv_cells_per_stage": int(h[1]), "max_peers": int(h[2]),
-                       "transport": "grouped ncclSend/ncclRecv between device buffers + ncclAllReduce(max) of dt, inside the library; step replayed as a CUDA graph"}
+                       "transport": TRANSPORT}
         own = _reduce([float(n_owned)], world, "max")
         rec["cells_per_gpu_max"] = int(own[0])
     mem = _reduce([resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1048576.0, stats[2] / 1e9, float(lp.mesh.n_cells), setup_s, stats[1], lp.seconds], world, "max")
@@ -190,9 +224,11 @@ def strong_records(a, rank, world, device, peak, peak_src):
         try:
             out.append(strong_record(name, nq, a, rank, world, device, peak, peak_src))
         except Exception as ex:      # a strong record never costs the main line
-            if world > 1:
-                raise
             out.append({"workload": name, "n_cells": nc, "error": str(ex)[:300]})
+            if world > 1:            # the ranks may have diverged: nothing collective can follow
+                _STATE["strong"] = out
+                break
+        _STATE["strong"] = out
     return out
 
 
@@ -203,6 +239,7 @@ def run(a, rank, world, local_rank, workload):
     import mallard_b200 as mb
     from mallard_b200.parallel import DistributedSolver
 
+    start_watchdog(rank)
     torch.cuda.set_device(local_rank)
     total_cores = bench.host_cores()
     numa = bind_to_gpu_numa_node(local_rank)     # before any pinned allocation: first touch then lands next to the GPU
@@ -232,7 +269,7 @@ def run(a, rank, world, local_rank, workload):
         part = np.minimum((xy[:, 0] * (world / Lx)).astype(np.int32), world - 1)  # rank r owns the strip x in [r, r+1) Lx / world
         U0, P0 = bench.riemann2d_state(np.stack([xy[:, 0] / Lx, xy[:, 1]], 1))    # the four-quadrant IC stretched over the strip
         bcs = bench.SYM4
-    ds = DistributedSolver(mesh, part, rank, world, local_rank, local=local, native=True, recon=a.recon, riemann="HLLC", integrator="SSPRK3",
+    ds = DistributedSolver(mesh, part, rank, world, local_rank, local=local, native=NATIVE, recon=a.recon, riemann="HLLC", integrator="SSPRK3",
                            order=3, bcs=bcs, fp_mode=a.fp, keep_stage_rhs=False)
     s = ds.s
     stats = s.get("stats")
@@ -273,13 +310,14 @@ def run(a, rank, world, local_rank, workload):
         sec = float(_reduce([time.perf_counter() - t0], world)[0])
         e2e = {"value": nc * bench.N_STAGES * k_e2e / sec, "unit": "cell-updates/s", "h2d_bytes_per_step": nc * 32, "d2h_bytes_per_step": nc * 32,
                "steps": k_e2e, "ms_per_step": 1e3 * sec / k_e2e,
-               "api": "mlb_take_step_distributed_host (C ABI: pinned host buffers of the rank's own cells -> device, the partitioned step incl. "
-                      "NCCL halo exchange and dt all-reduce inside the library, device -> host)"}
+               "api": ("mlb_take_step_distributed_host (C ABI: pinned host buffers of the rank's own cells -> device, the partitioned step incl. "
+                       "NCCL halo exchange and dt all-reduce inside the library, device -> host)") if NATIVE else
+                      "DistributedSolver.step_host (mlb_set_owned / split-phase stage API / mlb_get_owned; pinned host buffers of the rank's own cells)"}
 
     peers, sc, rc = ds.peers, ds.send_counts, ds.recv_counts
     halo = _reduce([float(sc.sum()), float(rc.sum()), float(len(peers))], world)
     s.close()
-    strong_recs = strong_records(a, rank, world, local_rank, peak, peak_src) if (a.workload == "riemann_2d" and not a.no_strong) else None
+    line = None
     if rank == 0:
         line = {"metric": "cell-updates/s per RK stage", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
@@ -288,12 +326,21 @@ def run(a, rank, world, local_rank, workload):
                                                   ("; the mesh is" if strong else " per GPU; global mesh %dx%d" % (gnx, a.ny)) + " partitioned in x over %d GPUs" % world),
                            "n_cells": nc, "cells_per_gpu": n_owned, "fp_mode": a.fp, "recon": a.recon,
                            "l2": "inputs larger than L2 (TENO tables %.1f GB per GPU per stage)" % (stats[2] / 1e9),
-                           "driver": "native (mlb_comm_init / mlb_run_distributed): NCCL inside the library, %d of %d timed steps replayed as a CUDA graph"
-                                     % (min(replays, a.steps), a.steps),
+                           "driver": ("native (mlb_comm_init / mlb_run_distributed): NCCL inside the library, %d of %d timed steps replayed as a CUDA graph"
+                                      % (min(replays, a.steps), a.steps)) if NATIVE else
+                                     "split-phase C ABI (mlb_halo_pack / mlb_stage_begin / mlb_stage) over torch.distributed (NCCL)",
                            "halo": {"max_send_cells_per_stage": int(halo[0]), "max_recv_cells_per_stage": int(halo[1]),
-                                    "max_peers": int(halo[2]), "transport": "grouped ncclSend/ncclRecv between device buffers + ncclAllReduce(max) of dt"},
+                                    "max_peers": int(halo[2]), "transport": TRANSPORT},
                            "setup_seconds": setup_s, "cpus_bound_per_rank": numa},
-                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": None, "strong": strong_recs}
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": None, "strong": None}
+    _STATE["line"] = line              # from here on the watchdog can deliver the main line on its own
+    strong_recs = strong_records(a, rank, world, local_rank, peak, peak_src) if (a.workload == "riemann_2d" and not a.no_strong) else None
+    _STATE["done"] = True
+    if rank == 0:
+        line["strong"] = strong_recs
         print(json.dumps(line), flush=True)
-    dist.barrier()
-    dist.destroy_process_group()
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        pass

@@ -33,7 +33,9 @@ enum { MLB_RIEMANN_RUSANOV = 0, MLB_RIEMANN_HLL = 1, MLB_RIEMANN_HLLC = 2 };
 /* numerics/time_integrator.h:23-39 */
 enum { MLB_INTEGRATOR_FE = 0, MLB_INTEGRATOR_RK4 = 1, MLB_INTEGRATOR_SSPRK3 = 2 };
 /* boundary/boundary.h:31-45 */
-enum { MLB_BC_SYMMETRY = 0, MLB_BC_EXTRAPOLATION = 1, MLB_BC_WALL_ADIABATIC = 2, MLB_BC_UPT = 3, MLB_BC_P_OUT = 4 };
+enum { MLB_BC_SYMMETRY = 0, MLB_BC_EXTRAPOLATION = 1, MLB_BC_WALL_ADIABATIC = 2, MLB_BC_UPT = 3, MLB_BC_P_OUT = 4,
+       /* new (viscous runs; the reference is Euler only): no-slip wall moving with velocity u[2]; T > 0: isothermal at T, else adiabatic */
+       MLB_BC_WALL_NOSLIP = 5 };
 /* numerics/basis.h:24-37 */
 enum { MLB_BASIS_MONOMIAL = 0, MLB_BASIS_LEGENDRE = 1 };
 /* mesh/mesh.h:30-42 (generators kept on the host) */
@@ -102,6 +104,12 @@ typedef struct {
 /* [physics] (physics/physics.cpp:27-53) */
 typedef struct {
     double gamma, p_ref, T_ref, rho_ref, p_min, p_max;
+    /* new - viscous terms (BASELINE configs[4]; the reference's physics is Euler only, physics/physics.h:23-29, its viscous
+     * spectral radius a commented-out stub, solver/solver.cpp:638-651).  mu = 0 (a zero-initialised tail) is the reference's inviscid
+     * model, bit for bit.  mu > 0 adds the Navier-Stokes fluxes: Newtonian stress with Stokes' hypothesis, Fourier heat flux with
+     * conductivity mu cp / Pr, constant mu; face gradients of (u, v, T) = average of the two cells' Green-Gauss gradients corrected
+     * along the centroid line by the two-point difference; second-order accurate whatever the reconstruction of the inviscid part. */
+    double mu, Pr /* 0 = 0.72 */;
 } mlb_physics;
 
 /* one [[boundaries]] entry (solver/solver.cpp:188-237); order of the array = order in the TOML file */

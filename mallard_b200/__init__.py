@@ -16,7 +16,7 @@ __all__ = ["Mesh", "Solver", "Plan", "riemann_flux", "compute_primitives", "part
            "set_host_threads", "build", "lib"]
 COMM_ID_BYTES = 128
 
-DEFAULT_GAS = dict(gamma=1.4, p_ref=101325.0, T_ref=298.15, rho_ref=1.225, p_min=-1e20, p_max=1e20)
+DEFAULT_GAS = dict(gamma=1.4, p_ref=101325.0, T_ref=298.15, rho_ref=1.225, p_min=-1e20, p_max=1e20, mu=0.0, Pr=0.72)
 _MESH_KEYS = ["node_coords", "offsets_nodes_of_cell", "nodes_of_cell", "offsets_faces_of_cell", "faces_of_cell",
               "offsets_nodes_of_face", "nodes_of_face", "cells_of_face", "cell_coords", "cell_volume", "face_area",
               "face_normals"]
@@ -213,7 +213,7 @@ def _numerics(recon, riemann, integrator, basis, order, factor, quad_cell, quad_
 def _physics(gas):
     g = dict(DEFAULT_GAS)
     g.update(gas or {})
-    return _abi.Physics(g["gamma"], g["p_ref"], g["T_ref"], g["rho_ref"], g["p_min"], g["p_max"])
+    return _abi.Physics(g["gamma"], g["p_ref"], g["T_ref"], g["rho_ref"], g["p_min"], g["p_max"], g["mu"], g["Pr"])
 
 
 def _local_struct(local, mesh):

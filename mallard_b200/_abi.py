@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get("MLB_LIB") or os.path.join(_HERE, "libmallard_b200.so"
 RECON = {"FO": 0, "TENO": 1}
 RIEMANN = {"Rusanov": 0, "HLL": 1, "HLLC": 2}
 INTEGRATOR = {"FE": 0, "RK4": 1, "SSPRK3": 2}
-BC = {"symmetry": 0, "extrapolation": 1, "wall_adiabatic": 2, "upt": 3, "p_out": 4}
+BC = {"symmetry": 0, "extrapolation": 1, "wall_adiabatic": 2, "upt": 3, "p_out": 4, "wall_noslip": 5}
 BASIS = {"monomial": 0, "legendre": 1}
 MESH = {"cartesian": 0, "cartesian_tri": 1, "wedge": 2}
 RENUMBER = {"none": 0, "rcm": 1}
@@ -38,7 +38,7 @@ class Numerics(C.Structure):
 
 class Physics(C.Structure):
     _fields_ = [("gamma", C.c_double), ("p_ref", C.c_double), ("T_ref", C.c_double), ("rho_ref", C.c_double),
-                ("p_min", C.c_double), ("p_max", C.c_double)]
+                ("p_min", C.c_double), ("p_max", C.c_double), ("mu", C.c_double), ("Pr", C.c_double)]
 
 
 class Bc(C.Structure):

@@ -74,6 +74,7 @@ struct mlb_ctx {
     double * U[3] = {nullptr, nullptr, nullptr};
     double * k[4] = {nullptr, nullptr, nullptr, nullptr};
     double * prim = nullptr, * sr = nullptr, * Fc = nullptr, * AF = nullptr, * scal = nullptr, * k_override = nullptr;
+    double * G = nullptr;              // viscous runs: Green-Gauss gradients of (u, v, T), AoS [Npad][6]
     long long * max_bits = nullptr;
     unsigned int * blocks_done = nullptr;
     unsigned long long * step_counter = nullptr;
@@ -122,13 +123,6 @@ struct mlb_ctx {
     cudaEvent_t ev[16] = {};
     uint64_t launches = 0;
     uint64_t graph_replays = 0;        // steps of mlb_run executed as CUDA graph replays
-    // one captured time step, kept across calls of mlb_run / mlb_run_distributed (valid while the things baked into it are the
-    // same: cfl, the buffer rotation, the residual override, single-GPU or distributed schedule)
-    cudaGraphExec_t step_graph = nullptr;
-    double step_graph_cfl = 0.0;
-    int step_graph_cur = -1;
-    bool step_graph_override = false, step_graph_distributed = false;
-    uint64_t step_graph_launches = 0;
     bool profiling = false;
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
     std::map<std::string, ProfileEntry> profile;
@@ -180,7 +174,6 @@ struct mlb_ctx {
             if (nccl_p2p) nccl().CommDestroy(nccl_p2p);
         } catch (...) {}
         for (auto & p : pending) { cudaEventDestroy(p.second.first); cudaEventDestroy(p.second.second); }
-        if (step_graph) cudaGraphExecDestroy(step_graph);
         for (void * p : owned_dev) cudaFree(p);
         if (d_stage) cudaFree(d_stage);
         if (h_stage) cudaFreeHost(h_stage);
@@ -311,7 +304,7 @@ void run_stage(mlb_ctx & c, const StagePlan & s, bool bare, double * k_out) {
     StageArgs a{};
     a.g = c.g; a.ph = c.phys; a.Uin = Uin; a.Fc = c.Fc; a.AF = c.AF; a.teno = c.teno ? 1 : 0;
     a.k_override = c.has_override ? c.k_override : nullptr;
-    a.scal = c.scal; a.step_counter = c.step_counter;
+    a.scal = c.scal; a.step_counter = c.step_counter; a.G = c.G;
     RkArgs & rk = a.rk;
     if (bare) { rk.mode = 3; rk.k_store = k_out; }
     else {
@@ -323,6 +316,7 @@ void run_stage(mlb_ctx & c, const StagePlan & s, bool bare, double * k_out) {
         rk.c0 = s.c0; rk.c1 = s.c1; rk.coef = s.coef;
         rk.prim_out = s.last ? c.prim : nullptr;
     }
+    if (!c.has_override && c.G) c.launch("visc_grad", [&] { c.kt->gradients(a, c.stream); });
     if (!c.has_override) c.launch(c.teno ? "face_flux_teno" : "face_flux_fo", [&] { c.kt->faces(a, c.stream); });
     c.launch("gather_stage", [&] { c.kt->stage(a, c.stream); });
 }
@@ -447,7 +441,7 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
     c->phys.gas = c->gas; c->phys.riemann = c->num.riemann; c->phys.n_bcs = n_bcs;
     for (int b = 0; b < n_bcs; b++) {
         if (!bcs[b].zone_name) throw std::runtime_error("Boundary name not specified.");
-        if (bcs[b].type < 0 || bcs[b].type > MLB_BC_P_OUT) throw std::runtime_error("Unknown boundary type.");
+        if (bcs[b].type < 0 || bcs[b].type > MLB_BC_WALL_NOSLIP) throw std::runtime_error("Unknown boundary type.");
         bc_zones.push_back(bcs[b].zone_name);
         BcParams & d = c->phys.bcs[b];
         d.type = bcs[b].type;
@@ -458,6 +452,7 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
             d.data[0] = rho; d.data[1] = bcs[b].u[0]; d.data[2] = bcs[b].u[1]; d.data[3] = bcs[b].p; d.data[4] = bcs[b].T;
             d.data[5] = e + bcs[b].p / rho;
         } else if (d.type == MLB_BC_P_OUT) d.data[0] = bcs[b].p;
+        else if (d.type == MLB_BC_WALL_NOSLIP) { d.data[1] = bcs[b].u[0]; d.data[2] = bcs[b].u[1]; d.data[4] = bcs[b].T; }
     }
 
     PrepOptions opt;
@@ -478,6 +473,7 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
         opt.device_tables = c->streaming && !(e && e[0] == '1') && teno_tables_device_supported(p, c->num.basis, 7 /* Dunavant rules have <= 7 points */);
     }
     opt.part = part; opt.rank = c->rank; opt.n_ranks = c->n_ranks;
+    opt.viscous = c->gas.mu > 0.0;
     if (local) {   // rank-local ingest: the mesh holds this rank's cells and enough ghost layers, in the global order
         if (!local->global_cell_ids) throw std::runtime_error("mlb_create_local: global_cell_ids is NULL");
         c->global_ids.assign(local->global_cell_ids, local->global_cell_ids + hm.nc);
@@ -511,6 +507,12 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
     }
     g.face_nx = c->upload(P.face_nx); g.face_ny = c->upload(P.face_ny); g.face_area = c->upload(P.face_area);
     g.slot_fx = c->teno ? c->upload(P.slot_fx) : nullptr;
+    g.NFpad = P.NFpad;
+    if (opt.viscous) {
+        g.slot_nA = c->upload(P.slot_nA); g.face_d = c->upload(P.face_d);
+        c->G = c->alloc<double>(6 * (size_t)P.Npad);
+        CUDA_OK(cudaMemsetAsync(c->G, 0, 6 * (size_t)P.Npad * sizeof(double), c->stream));
+    }
     g.face_cl = c->upload(P.face_cl); g.face_cr = c->upload(P.face_cr); g.face_slots = c->upload(P.face_slots);
     c->AF = c->alloc<double>(4 * (size_t)std::max<uint32_t>(P.NFpad, 1));
     c->d_perm_cells = c->upload(P.perm_cells);
@@ -622,49 +624,6 @@ void halo_unpack(mlb_ctx & c, int buf, bool first_stage) {
     }
     CUDA_OK(cudaGetLastError());
     if (c.comm_stream) { CUDA_OK(cudaEventRecord(c.ev_halo, cs)); c.halo_pending = true; }
-}
-
-// Runs n_steps of `one_step`, replaying it as a CUDA graph: the first call runs one step eagerly (kernels get their function
-// attributes, NCCL its connections, errors are reported with a message), captures the next one - every stream it forks to
-// included - and keeps the executable graph in the context; later calls replay straight away.  dt, t and the step counter
-// live on the device and the stage buffers of SSPRK3 / RK4 return to the same rotation after a step, so every replay is the same
-// graph.  Returns false (with `why`) if the step cannot be captured; the caller decides whether plain launches are acceptable.
-template <class F>
-bool run_steps_as_graph(mlb_ctx & c, uint32_t n_steps, double cfl, bool distributed, cudaStreamCaptureMode mode, F && one_step, std::string & why) {
-    uint32_t done = 0;
-    const bool cached = c.step_graph && c.step_graph_cfl == cfl && c.step_graph_cur == c.cur && c.step_graph_override == c.has_override &&
-                        c.step_graph_distributed == distributed;
-    if (!cached) {
-        if (c.step_graph) { cudaGraphExecDestroy(c.step_graph); c.step_graph = nullptr; }
-        one_step();
-        done = 1;
-        const uint64_t l0 = c.launches;
-        cudaGraph_t g = nullptr;
-        CUDA_OK(cudaStreamBeginCapture(c.stream, mode));
-        bool ok = true;
-        try { one_step(); } catch (const std::exception & e) { ok = false; why = e.what(); }
-        const cudaError_t ec = cudaStreamEndCapture(c.stream, &g);
-        c.step_graph_launches = c.launches - l0;
-        c.launches = l0;                             // nothing ran during the capture
-        cudaGraphExec_t ge = nullptr;
-        const bool inst = ok && ec == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess;
-        if (g) cudaGraphDestroy(g);
-        if (!inst) {
-            if (why.empty()) why = cudaGetErrorString(ec != cudaSuccess ? ec : cudaGetLastError());
-            cudaGetLastError();
-            c.halo_pending = false; c.stage_begun = -1;
-            for (; done < n_steps; done++) one_step();       // (single GPU) plain launches; a distributed caller reports `why`
-            return false;
-        }
-        c.step_graph = ge; c.step_graph_cfl = cfl; c.step_graph_cur = c.cur; c.step_graph_override = c.has_override;
-        c.step_graph_distributed = distributed;
-    }
-    for (; done < n_steps; done++) {
-        CUDA_OK(cudaGraphLaunch(c.step_graph, c.stream));
-        c.launches += c.step_graph_launches;
-        c.graph_replays++;
-    }
-    return true;
 }
 
 // ---- native multi-GPU driver: NCCL over NVLink, no host code between the stages of a step -----------------------------------
@@ -944,13 +903,30 @@ int mlb_run(mlb_ctx * c, uint32_t n_steps, double cfl, double * t_out, double * 
         do_step(*c);
     };
     // Small meshes (examples/sod: 1000 cells, examples/wedge: 7500) are launch-bound: 7-10 kernels of a few microseconds per
-    // step, so the step is replayed as a CUDA graph (run_steps_as_graph); large ones lose nothing by it.
+    // step.  One step is captured into a CUDA graph and replayed; dt, t and the step counter live on the device, and the
+    // stage buffers of SSPRK3 / RK4 return to the same rotation after a step, so every replay is the same graph.
     static const bool graphs = [] { const char * e = getenv("MLB_RUN_GRAPH"); return !(e && e[0] == '0'); }();
     uint32_t done = 0;
-    if (graphs && !c->profiling && (n_steps >= 8 || (c->step_graph && n_steps)) && c->num.integrator != MLB_INTEGRATOR_FE) {
-        std::string why;
-        run_steps_as_graph(*c, n_steps, cfl, false, cudaStreamCaptureModeThreadLocal, one_step, why);
-        done = n_steps;
+    if (graphs && !c->profiling && n_steps >= 8 && c->num.integrator != MLB_INTEGRATOR_FE) {
+        one_step();                                   // eager: function attributes, occupancy queries, error reporting
+        done = 1;
+        const uint64_t l0 = c->launches;
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ge = nullptr;
+        CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        bool ok = true;
+        try { one_step(); } catch (...) { ok = false; }
+        const cudaError_t ec = cudaStreamEndCapture(c->stream, &g);
+        const uint64_t per_step = c->launches - l0;
+        c->launches = l0;                             // nothing ran during the capture
+        if (ok && ec == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) {
+            for (; done < n_steps; done++) { CUDA_OK(cudaGraphLaunch(ge, c->stream)); c->launches += per_step; }
+            c->graph_replays += n_steps - 1;
+        } else {
+            cudaGetLastError();                       // capture not possible here: fall through to plain launches
+        }
+        if (ge) cudaGraphExecDestroy(ge);
+        if (g) cudaGraphDestroy(g);
     }
     for (; done < n_steps; done++) one_step();
     double sc[SC_COUNT];
@@ -1356,16 +1332,37 @@ int mlb_run_distributed(mlb_ctx * c, uint32_t n_steps, double cfl, double * t_ou
     CUDA_OK(cudaSetDevice(c->device));
     require_comm(*c);
     if (!(cfl > 0.0) && n_steps) require_dt(*c);
-    // As in mlb_run: the step - both streams, the grouped send/recv and the all-reduce included - is captured once and replayed
-    // as one CUDA graph per step.
+    // As in mlb_run: one eager step (NCCL sets up its connections, kernels get their attributes), then the step is captured -
+    // both streams, the grouped send/recv and the all-reduce included - and replayed as one CUDA graph per step.
     static const bool graphs = [] { const char * e = getenv("MLB_RUN_GRAPH"); return !(e && e[0] == '0'); }();
     uint32_t done = 0;
-    if (graphs && !c->profiling && (n_steps >= 4 || (c->step_graph && n_steps)) && c->num.integrator != MLB_INTEGRATOR_FE) {
+    if (graphs && !c->profiling && n_steps >= 4 && c->num.integrator != MLB_INTEGRATOR_FE) {
+        do_step_distributed(*c, cfl);
+        done = 1;
+        const uint64_t l0 = c->launches;
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ge = nullptr;
+        CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+        bool ok = true;
         std::string why;
-        // every rank must issue the same collectives: a rank that cannot capture reports it instead of diverging silently
-        if (!run_steps_as_graph(*c, n_steps, cfl, true, cudaStreamCaptureModeRelaxed, [&] { do_step_distributed(*c, cfl); }, why))
-            throw std::runtime_error("mlb_run_distributed: the step could not be captured into a CUDA graph (" + why + "); set MLB_RUN_GRAPH=0 on every rank");
-        done = n_steps;
+        try { do_step_distributed(*c, cfl); } catch (const std::exception & e) { ok = false; why = e.what(); }
+        const cudaError_t ec = cudaStreamEndCapture(c->stream, &g);
+        const uint64_t per_step = c->launches - l0;
+        c->launches = l0;                             // nothing ran during the capture
+        if (ok && ec == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) {
+            for (; done < n_steps; done++) { CUDA_OK(cudaGraphLaunch(ge, c->stream)); c->launches += per_step; }
+            c->graph_replays += n_steps - 1;
+        } else {
+            cudaGetLastError();
+            c->halo_pending = false; c->stage_begun = -1;
+            if (ge) cudaGraphExecDestroy(ge);
+            if (g) cudaGraphDestroy(g);
+            // every rank must issue the same collectives: a rank that cannot capture cannot silently fall back on its own
+            throw std::runtime_error("mlb_run_distributed: the step could not be captured into a CUDA graph (" +
+                                     (why.empty() ? std::string(cudaGetErrorString(ec)) : why) + "); set MLB_RUN_GRAPH=0 on every rank");
+        }
+        if (ge) cudaGraphExecDestroy(ge);
+        if (g) cudaGraphDestroy(g);
     }
     for (; done < n_steps; done++) do_step_distributed(*c, cfl);
     if (c->comm_stream) CUDA_OK(cudaStreamSynchronize(c->comm_stream));

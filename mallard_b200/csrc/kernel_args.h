@@ -20,6 +20,9 @@ struct DevGeom {
     const double * bnd_s;         // [Npad] 2*pow(V,1/2) (solver.cpp:662-666), computed on the host with libm pow
     const double * face_nx, * face_ny, * face_area;   // [NFpad]
     const double * slot_fx;       // [n_slots][4][Npad]
+    const double * slot_nA;       // viscous: [n_slots][2][Npad] outward area-weighted face normals of every reconstructed cell
+    const double * face_d;        // viscous: [2][NFpad] centroid line of every face (boundary: mirror image)
+    uint32_t NFpad;
     const uint32_t * face_cl;     // [NFpad] cell on side 0 (normal points out of it)
     const int32_t * face_cr;      // [NFpad] cell on side 1 ; < 0: -(bc index + 1) ; INT32_MIN: no flux
     const uint8_t * face_slots;   // [NFpad] slot of the face in cell 0 | slot in cell 1 << 4 (TENO face values are cell-centred)
@@ -58,6 +61,7 @@ struct StageArgs {
     const double * Uin;           // AoS [Npad][4]: state the residual is evaluated on
     const double * Fc;            // TENO: cell-centred face values AoS [Npad][n_slots * Q][4]
     double * AF;                  // [NFpad][4] area * quadrature-averaged flux per face (written by the face kernel)
+    double * G;                   // viscous: Green-Gauss gradients AoS [Npad][6] = d(u, v, T)/d(x, y); null when mu == 0
     const double * k_override;    // AoS [Npad][4] or null: state-independent residual (test hook)
     double * scal;                // device scalars
     unsigned long long * step_counter;
@@ -123,6 +127,7 @@ struct CflArgs {
 
 struct KernelTable {
     const char * name;
+    void (*gradients)(const StageArgs &, cudaStream_t);   // viscous runs only
     void (*faces)(const StageArgs &, cudaStream_t);
     void (*stage)(const StageArgs &, cudaStream_t);
     void (*recon)(const ReconArgs &, cudaStream_t);

@@ -311,6 +311,115 @@ __device__ __forceinline__ void rk_update(const RkArgs & rk, const double * Uin,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Viscous terms (new: the reference is Euler only, physics/physics.h:23-29; SURVEY 8f N4, BASELINE configs[4]).  Compiled in
+// only for mu > 0: with mu == 0 the instantiations below are not launched and the path is the reference's, bit for bit.
+//   visc_grad_kernel   Green-Gauss gradients of (u, v, T) of every owned and first-ring ghost cell from the cell averages:
+//                      grad_i = 1/V_i sum_faces phi_f (n A)_out, phi_f = mean of the two cells' values (boundary: the wall's)
+//   viscous_flux()     at a face: gradient = mean of the two cells' gradients, with its component along the centroid line
+//                      replaced by the two-point difference (no odd-even decoupling); Newtonian stress with Stokes' hypothesis,
+//                      Fourier heat flux; returns F_v . n
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cons_to_uvT(const GasParams & g, const double * U, double * w) {
+    const double ir = 1.0 / U[0];
+    w[0] = U[1] * ir; w[1] = U[2] * ir;
+    w[2] = (U[3] * ir - 0.5 * (w[0] * w[0] + w[1] * w[1])) / g.cv;
+}
+// value of (u, v, T) the boundary condition puts ON the face, given the interior cell's
+__device__ __forceinline__ void boundary_face_uvT(const BcParams & bc, double nx, double ny, const double * wi, double * wf) {
+    switch (bc.type) {
+        case MLB_BC_WALL_NOSLIP: wf[0] = bc.data[1]; wf[1] = bc.data[2]; wf[2] = bc.data[4] > 0.0 ? bc.data[4] : wi[2]; break;
+        case MLB_BC_SYMMETRY: case MLB_BC_WALL_ADIABATIC: {
+            const double un = wi[0] * nx + wi[1] * ny;
+            wf[0] = wi[0] - un * nx; wf[1] = wi[1] - un * ny; wf[2] = wi[2]; break;
+        }
+        case MLB_BC_UPT: wf[0] = 0.5 * (wi[0] + bc.data[1]); wf[1] = 0.5 * (wi[1] + bc.data[2]); wf[2] = 0.5 * (wi[2] + bc.data[4]); break;
+        default: wf[0] = wi[0]; wf[1] = wi[1]; wf[2] = wi[2]; break;
+    }
+}
+
+__global__ void __launch_bounds__(256) visc_grad_kernel(const __grid_constant__ StageArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.g.N_recon) return;
+    const uint32_t Np = a.g.Npad;
+    double Ui[4], wi[3];
+    ld4(a.Uin, i, Ui);
+    cons_to_uvT(a.ph.gas, Ui, wi);
+    double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const int nf = a.g.nfc[i];
+    for (int j = 0; j < nf; j++) {
+        const size_t at = (size_t)j * Np + i;
+        const double ax = a.g.slot_nA[((size_t)j * 2) * Np + i], ay = a.g.slot_nA[((size_t)j * 2 + 1) * Np + i];
+        const int32_t nbr = a.g.slot_nbr[at];
+        double wf[3];
+        if (nbr >= 0) {
+            double Un[4], wn[3];
+            ld4(a.Uin, (size_t)nbr, Un);
+            cons_to_uvT(a.ph.gas, Un, wn);
+#pragma unroll
+            for (int v = 0; v < 3; v++) wf[v] = 0.5 * (wi[v] + wn[v]);
+        } else if (nbr != INT32_MIN) {
+            const double ia = 1.0 / sqrt(ax * ax + ay * ay);
+            boundary_face_uvT(a.ph.bcs[-nbr - 1], ax * ia, ay * ia, wi, wf);
+        } else {
+#pragma unroll
+            for (int v = 0; v < 3; v++) wf[v] = wi[v];
+        }
+#pragma unroll
+        for (int v = 0; v < 3; v++) { acc[2 * v] += wf[v] * ax; acc[2 * v + 1] += wf[v] * ay; }
+    }
+    const double iv = 1.0 / a.g.cell_vol[i];
+    double * G = a.G + 6 * (size_t)i;
+#pragma unroll
+    for (int v = 0; v < 6; v++) G[v] = acc[v] * iv;
+}
+
+// F_v . n at face f (unit normal n out of cell cl); cr < 0: boundary with condition bc
+__device__ __forceinline__ void viscous_flux(const StageArgs & a, uint32_t f, uint32_t cl, int32_t cr, double nx, double ny, double * Fv) {
+    const GasParams & g = a.ph.gas;
+    double Ul[4], wl[3], wr[3], Gl[6], Gr[6];
+    ld4(a.Uin, cl, Ul);
+    cons_to_uvT(g, Ul, wl);
+#pragma unroll
+    for (int v = 0; v < 6; v++) Gl[v] = a.G[6 * (size_t)cl + v];
+    if (cr >= 0) {
+        double Ur[4];
+        ld4(a.Uin, (size_t)cr, Ur);
+        cons_to_uvT(g, Ur, wr);
+#pragma unroll
+        for (int v = 0; v < 6; v++) Gr[v] = a.G[6 * (size_t)cr + v];
+    } else {
+        const BcParams & bc = a.ph.bcs[-cr - 1];
+        if (bc.type == MLB_BC_SYMMETRY || bc.type == MLB_BC_WALL_ADIABATIC) {     // slip surfaces: no shear, no heat flux
+            Fv[0] = 0.0; Fv[1] = 0.0; Fv[2] = 0.0; Fv[3] = 0.0;
+            return;
+        }
+        double wf[3];
+        boundary_face_uvT(bc, nx, ny, wl, wf);
+#pragma unroll
+        for (int v = 0; v < 3; v++) wr[v] = 2.0 * wf[v] - wl[v];                   // mirror state: the face value is the boundary's
+#pragma unroll
+        for (int v = 0; v < 6; v++) Gr[v] = Gl[v];
+    }
+    const double dx = a.g.face_d[f], dy = a.g.face_d[(size_t)a.g.NFpad + f];
+    const double id = 1.0 / sqrt(dx * dx + dy * dy);
+    const double ex = dx * id, ey = dy * id;
+    double gx[3], gy[3];
+#pragma unroll
+    for (int v = 0; v < 3; v++) {
+        const double mx = 0.5 * (Gl[2 * v] + Gr[2 * v]), my = 0.5 * (Gl[2 * v + 1] + Gr[2 * v + 1]);
+        const double corr = (wr[v] - wl[v]) * id - (mx * ex + my * ey);
+        gx[v] = mx + corr * ex; gy[v] = my + corr * ey;
+    }
+    const double uf = 0.5 * (wl[0] + wr[0]), vf = 0.5 * (wl[1] + wr[1]);
+    const double div = gx[0] + gy[1];
+    const double txx = g.mu * (2.0 * gx[0] - (2.0 / 3.0) * div), tyy = g.mu * (2.0 * gy[1] - (2.0 / 3.0) * div), txy = g.mu * (gy[0] + gx[1]);
+    Fv[0] = 0.0;
+    Fv[1] = txx * nx + txy * ny;
+    Fv[2] = txy * nx + tyy * ny;
+    Fv[3] = (uf * txx + vf * txy + g.kappa * gx[2]) * nx + (uf * txy + vf * tyy + g.kappa * gy[2]) * ny;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Face fluxes.  One thread per face: quadrature loop over the Riemann flux (BaseFluxFunctor::call_impl,
 // numerics/flux_functor.h:124-162; boundary ghost states boundary/*.cpp), result A * (1/2 sum_q w_q F_q) stored once per
 // face.  The reference scatters -+ that product into both cells with atomic_add; here the cells gather it (next kernel).
@@ -322,7 +431,7 @@ __device__ __forceinline__ void rk_update(const RkArgs & rk, const double * Uin,
 // one Riemann problem; the QT lanes of a face then combine w_q F_q in the reference's q order with warp shuffles (same
 // rounding as the sequential loop) and lane 0 stores.  Twice the parallelism and half the dependent sqrt/div chain per
 // thread of a per-face loop.  QT = 0: one thread per face loops over a run-time Q.
-template <int RS, bool TENO, int QT>
+template <int RS, bool TENO, int QT, bool VISC>
 __global__ void __launch_bounds__(128, MLB_FLUX_MINB) face_flux_kernel(const __grid_constant__ StageArgs a) {
     constexpr int TPF = QT > 0 ? QT : 1;                 // threads per face (1, 2 or 4: divides the warp)
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -399,8 +508,15 @@ __global__ void __launch_bounds__(128, MLB_FLUX_MINB) face_flux_kernel(const __g
         if (lane_q != 0) return;
     }
     if (!valid) return;
+    if (VISC) {   // the residual takes A (F_inviscid - F_viscous) . n
+        double Fv[4] = {0.0, 0.0, 0.0, 0.0};
+        if (!no_flux) viscous_flux(a, f, cl, cr, nx, ny, Fv);
 #pragma unroll
-    for (int v = 0; v < 4; v++) fsum[v] = area * (fsum[v] * 0.5);   // flux_functor.h:153,156-161: (-A)*F == -(A*F) exactly
+        for (int v = 0; v < 4; v++) fsum[v] = area * (fsum[v] * 0.5 - Fv[v]);
+    } else {
+#pragma unroll
+        for (int v = 0; v < 4; v++) fsum[v] = area * (fsum[v] * 0.5);   // flux_functor.h:153,156-161: (-A)*F == -(A*F) exactly
+    }
     reinterpret_cast<double4 *>(a.AF)[f] = make_double4(fsum[0], fsum[1], fsum[2], fsum[3]);
 }
 
@@ -629,7 +745,7 @@ __global__ void __launch_bounds__(256) cfl_kernel(const __grid_constant__ CflArg
     const uint32_t Np = a.g.Npad;
     double sr = -1.0;
     if (i < a.g.N_owned) {
-        double conv = 0.0, acou = 0.0;
+        double conv = 0.0, acou = 0.0, visc = 0.0;
         const int nf = a.g.nfc[i];
         const double rho_s = a.prim[5 * (size_t)Np + i], u_s = a.prim[i], v_s = a.prim[(size_t)Np + i], p_s = a.prim[2 * (size_t)Np + i];
         const double sos_s = sqrt(a.gas.gamma * p_s / rho_s);
@@ -657,11 +773,15 @@ __global__ void __launch_bounds__(256) cfl_kernel(const __grid_constant__ CflArg
             conv += un / dx_n;
             const double r = sos_f / dx_n;
             acou += r * r;
+            if (a.gas.mu > 0.0) visc += 1.0 / (dx_n * dx_n);
         }
         const double geom = 3.0 / nf;
         conv *= 1.37 * geom;
         acou = 1.37 * sqrt(geom * acou);
         sr = conv + acou;
+        // new (the reference declares spectral_radius_viscous / _heat and leaves them commented out, solver.cpp:638-651): diffusion
+        // number of the stiffer of momentum and heat diffusion, 2 nu' sum_faces 1/dx_n^2 with the same geometric factor
+        if (a.gas.mu > 0.0) sr += 2.0 * geom * visc * fmax(4.0 / 3.0, a.gas.gamma * a.gas.kappa / (a.gas.mu * a.gas.cp)) * a.gas.mu / rho_s;
         a.sr_out[i] = sr;
     }
     // block max (NaN never wins: Kokkos::Max joins with `<`)
@@ -726,21 +846,33 @@ __global__ void prims_soa_kernel(const GasParams g, uint32_t n, uint32_t npad, c
 // ---------------------------------------------------------------------------------------------------------------
 // Launchers
 // ---------------------------------------------------------------------------------------------------------------
-template <int RS>
+template <int RS, bool VISC>
 static void launch_faces_rs(const StageArgs & a, cudaStream_t st) {
     if (a.g.NF == 0) return;
     auto grid = [&](unsigned tpf) { return (unsigned)(((uint64_t)a.g.NF * tpf + 127u) / 128u); };
-    if (!a.teno) face_flux_kernel<RS, false, 1><<<grid(1), 128, 0, st>>>(a);
-    else if (a.g.Q == 1) face_flux_kernel<RS, true, 1><<<grid(1), 128, 0, st>>>(a);
-    else if (a.g.Q == 2) face_flux_kernel<RS, true, 2><<<grid(2), 128, 0, st>>>(a);
-    else face_flux_kernel<RS, true, 0><<<grid(1), 128, 0, st>>>(a);
+    if (!a.teno) face_flux_kernel<RS, false, 1, VISC><<<grid(1), 128, 0, st>>>(a);
+    else if (a.g.Q == 1) face_flux_kernel<RS, true, 1, VISC><<<grid(1), 128, 0, st>>>(a);
+    else if (a.g.Q == 2) face_flux_kernel<RS, true, 2, VISC><<<grid(2), 128, 0, st>>>(a);
+    else face_flux_kernel<RS, true, 0, VISC><<<grid(1), 128, 0, st>>>(a);
 }
 static void launch_faces(const StageArgs & a, cudaStream_t st) {
-    switch (a.ph.riemann) {
-        case MLB_RIEMANN_RUSANOV: launch_faces_rs<MLB_RIEMANN_RUSANOV>(a, st); break;
-        case MLB_RIEMANN_HLL: launch_faces_rs<MLB_RIEMANN_HLL>(a, st); break;
-        default: launch_faces_rs<MLB_RIEMANN_HLLC>(a, st); break;
+    if (a.G) {
+        switch (a.ph.riemann) {
+            case MLB_RIEMANN_RUSANOV: launch_faces_rs<MLB_RIEMANN_RUSANOV, true>(a, st); break;
+            case MLB_RIEMANN_HLL: launch_faces_rs<MLB_RIEMANN_HLL, true>(a, st); break;
+            default: launch_faces_rs<MLB_RIEMANN_HLLC, true>(a, st); break;
+        }
+        return;
     }
+    switch (a.ph.riemann) {
+        case MLB_RIEMANN_RUSANOV: launch_faces_rs<MLB_RIEMANN_RUSANOV, false>(a, st); break;
+        case MLB_RIEMANN_HLL: launch_faces_rs<MLB_RIEMANN_HLL, false>(a, st); break;
+        default: launch_faces_rs<MLB_RIEMANN_HLLC, false>(a, st); break;
+    }
+}
+static void launch_gradients(const StageArgs & a, cudaStream_t st) {
+    const unsigned grid = (a.g.N_recon + 255u) / 256u;
+    if (grid && a.G) visc_grad_kernel<<<grid, 256, 0, st>>>(a);
 }
 static void launch_stage(const StageArgs & a, cudaStream_t st) {
     const unsigned grid = (a.g.N_owned + 255u) / 256u;
@@ -808,10 +940,10 @@ static void launch_prims_soa(const GasParams & g, uint32_t n, uint32_t npad, con
 #define MLB_STR2(x) #x
 #define MLB_STR(x) MLB_STR2(x)
 #ifdef MLB_STREAM_KERNELS
-static const KernelTable table = {MLB_STR(MLB_KNS), launch_faces, launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
+static const KernelTable table = {MLB_STR(MLB_KNS), launch_gradients, launch_faces, launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
                                   launch_prims_soa, recon_supported, stream::launch_stream, stream::stream_supported};
 #else
-static const KernelTable table = {MLB_STR(MLB_KNS), launch_faces, launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
+static const KernelTable table = {MLB_STR(MLB_KNS), launch_gradients, launch_faces, launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
                                   launch_prims_soa, recon_supported, nullptr, nullptr};
 #endif
 

@@ -216,6 +216,8 @@ GasParams make_gas(const mlb_physics & p) {
     g.R = p.p_ref / (p.T_ref * p.rho_ref);
     g.cp = g.R * p.gamma / (p.gamma - 1.0);
     g.cv = g.cp / p.gamma;
+    g.mu = p.mu > 0.0 ? p.mu : 0.0;
+    g.kappa = g.mu * g.cp / (p.Pr > 0.0 ? p.Pr : 0.72);
     return g;
 }
 

@@ -41,7 +41,7 @@ void host_mesh_from_cells(HostMesh & m, uint32_t n_nodes, const double * node_xy
 // ---------------------------------------------------------------------------------------------------------------
 // Gas constants (physics/physics.cpp:69-73)
 // ---------------------------------------------------------------------------------------------------------------
-struct GasParams { double gamma, p_min, p_max, R, cp, cv; };
+struct GasParams { double gamma, p_min, p_max, R, cp, cv, mu, kappa; };   // mu = 0: inviscid (the reference); kappa = mu cp / Pr
 GasParams make_gas(const mlb_physics & p);
 
 // Boundary condition as the device sees it: type + data[6] (boundary_upt.cpp:38-73: rho,u,v,p,T,h ; p_out: p)
@@ -122,6 +122,8 @@ struct Prep {
     dvec cell_xy;          // [2][Npad]
     dvec face_nx, face_ny, face_area;   // [NFpad] unit normal (common_math.h:101-106) and area
     dvec slot_fx;          // TENO: [n_slots][4][Npad] face end points in the cell's reference coordinates
+    dvec slot_nA;          // viscous: [n_slots][2][Npad] outward area-weighted normal of every face of every reconstructed cell (Green-Gauss)
+    dvec face_d;           // viscous: [2][NFpad] centroid-to-centroid vector (boundary faces: twice the normal distance to the face)
     uvec face_cl;          // [NFpad] library cell on side 0 of the face
     ivec face_cr;          // [NFpad] library cell on side 1 ; < 0: -(bc index + 1) ; INT32_MIN: no flux through this face
     std::vector<uint8_t> face_slots;   // [NFpad] slot in cell 0 | slot in cell 1 << 4
@@ -137,6 +139,7 @@ struct PrepOptions {
     bool device_tables = false;       // ... and leave their matrices to the device (teno_tables.cu); the host emits ids + node coordinates
     const int32_t * part = nullptr;   // partition vector (reference numbering) or null
     int rank = 0, n_ranks = 1;
+    bool viscous = false;             // hold the second ghost ring and the Green-Gauss geometry
     const double * psi_ref_tri = nullptr;   // rank-local meshes: node coordinates of the GLOBAL mesh's cell 0 (integral_psi_target)
 };
 

@@ -535,6 +535,19 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
             }
         std::sort(g1.begin(), g1.end());
     }
+    std::vector<uint32_t> gv;            // viscous: face neighbours of the first ghost ring (their states feed the ring's Green-Gauss gradients)
+    if (opt.viscous && opt.part) {
+        for (uint32_t c : g1)
+            for (int j = 0; j < m.nfc(c); j++) {
+                const uint32_t f = m.foc[m.ofc[c] + j];
+                const int32_t a = m.cof[2 * (size_t)f], b = m.cof[2 * (size_t)f + 1];
+                if (b == CUT_FACE) throw std::runtime_error("rank-local mesh: a first-ring ghost cell has a cut face (viscous runs need one more ghost layer)");
+                if (b < 0) continue;
+                const uint32_t o = (a == (int32_t)c) ? (uint32_t)b : (uint32_t)a;
+                if (!cls[o]) { cls[o] = 3; gv.push_back(o); }
+            }
+        std::sort(gv.begin(), gv.end());
+    }
     uvec order;
     if (num.renumber == MLB_RENUMBER_RCM && owned.size() > 1) rcm_order(m, owned, order); else order = owned;
     const uint32_t n_owned = (uint32_t)order.size();
@@ -601,10 +614,13 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
             T.st_ids.swap(ids2);
             order.swap(order2);
             for (uint32_t x : T.st_ids) if (x != NO_FACE && !cls[x]) { cls[x] = 3; g2.push_back(x); }
+            g2.insert(g2.end(), gv.begin(), gv.end());
+            gv.clear();
             std::sort(g2.begin(), g2.end());
             order.insert(order.end(), g2.begin(), g2.end());
         }
     }
+    order.insert(order.end(), gv.begin(), gv.end());      // first order: the second ring is all the state-only ghosts there are
     const uint32_t N = (uint32_t)order.size();
     P.N = N; P.N_owned = n_owned; P.N_recon = n_recon; P.N_interior = n_interior;
     P.Npad = (N + 31u) & ~31u;
@@ -735,6 +751,32 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
     }
 
     if (!slot_err.empty()) throw std::runtime_error(slot_err);
+    if (opt.viscous) {   // Green-Gauss geometry of every reconstructed cell, centroid line of every held face
+        P.slot_nA.assign((size_t)n_slots * 2 * Np, 0.0);
+        P.face_d.assign(2 * (size_t)P.NFpad, 0.0);
+#pragma omp parallel for schedule(static)
+        for (int64_t ii = 0; ii < (int64_t)n_recon; ii++) {
+            const uint32_t i = (uint32_t)ii, c = order[i];
+            for (int j = 0; j < m.nfc(c); j++) {
+                const uint32_t f = m.foc[m.ofc[c] + j];
+                const double sgn = m.cof[2 * (size_t)f] == (int32_t)c ? 1.0 : -1.0;
+                P.slot_nA[((size_t)j * 2) * Np + i] = sgn * m.face_n[2 * (size_t)f];
+                P.slot_nA[((size_t)j * 2 + 1) * Np + i] = sgn * m.face_n[2 * (size_t)f + 1];
+            }
+        }
+        for (uint32_t i = 0; i < P.NF; i++) {
+            const uint32_t f = P.perm_faces[i];
+            const int32_t a = m.cof[2 * (size_t)f], b = m.cof[2 * (size_t)f + 1];
+            double dx, dy;
+            if (b >= 0) { dx = m.cell_xy[2 * (size_t)b] - m.cell_xy[2 * (size_t)a]; dy = m.cell_xy[2 * (size_t)b + 1] - m.cell_xy[2 * (size_t)a + 1]; }
+            else {   // mirror image of the cell centroid in the face
+                const double * n0 = &m.node_xy[2 * (size_t)m.nof[m.onf[f]]], * n1 = &m.node_xy[2 * (size_t)m.nof[m.onf[f] + 1]];
+                const double dist = (0.5 * (n0[0] + n1[0]) - m.cell_xy[2 * (size_t)a]) * P.face_nx[i] + (0.5 * (n0[1] + n1[1]) - m.cell_xy[2 * (size_t)a + 1]) * P.face_ny[i];
+                dx = 2.0 * dist * P.face_nx[i]; dy = 2.0 * dist * P.face_ny[i];
+            }
+            P.face_d[i] = dx; P.face_d[(size_t)P.NFpad + i] = dy;
+        }
+    }
     tick("slots done");
     // ---- face-centred view of the same connectivity (face flux kernel)
     P.face_cl.assign(P.NFpad, 0u);

