@@ -107,7 +107,7 @@ typedef struct {
     /* new - viscous terms (BASELINE configs[4]; the reference's physics is Euler only, physics/physics.h:23-29, its viscous
      * spectral radius a commented-out stub, solver/solver.cpp:638-651).  mu = 0 (a zero-initialised tail) is the reference's inviscid
      * model, bit for bit.  mu > 0 adds the Navier-Stokes fluxes: Newtonian stress with Stokes' hypothesis, Fourier heat flux with
-     * conductivity mu cp / Pr, constant mu; face gradients of (u, v, T) = average of the two cells' Green-Gauss gradients corrected
+     * conductivity mu cp / Pr, constant mu; face gradients of (u, v, T) = average of the two cells' least-squares gradients corrected
      * along the centroid line by the two-point difference; second-order accurate whatever the reconstruction of the inviscid part. */
     double mu, Pr /* 0 = 0.72 */;
 } mlb_physics;

@@ -74,7 +74,7 @@ struct mlb_ctx {
     double * U[3] = {nullptr, nullptr, nullptr};
     double * k[4] = {nullptr, nullptr, nullptr, nullptr};
     double * prim = nullptr, * sr = nullptr, * Fc = nullptr, * AF = nullptr, * scal = nullptr, * k_override = nullptr;
-    double * G = nullptr;              // viscous runs: Green-Gauss gradients of (u, v, T), AoS [Npad][6]
+    double * G = nullptr;              // viscous runs: least-squares gradients of (u, v, T), AoS [Npad][6]
     long long * max_bits = nullptr;
     unsigned int * blocks_done = nullptr;
     unsigned long long * step_counter = nullptr;
@@ -509,7 +509,7 @@ mlb_ctx * create_impl(const mlb_mesh * mesh, const int32_t * part, const mlb_num
     g.slot_fx = c->teno ? c->upload(P.slot_fx) : nullptr;
     g.NFpad = P.NFpad;
     if (opt.viscous) {
-        g.slot_nA = c->upload(P.slot_nA); g.face_d = c->upload(P.face_d);
+        g.slot_d = c->upload(P.slot_d); g.face_d = c->upload(P.face_d);
         c->G = c->alloc<double>(6 * (size_t)P.Npad);
         CUDA_OK(cudaMemsetAsync(c->G, 0, 6 * (size_t)P.Npad * sizeof(double), c->stream));
     }

@@ -1,7 +1,10 @@
 // Argument blocks passed BY VALUE to the kernels (they live in the constant bank: uniform, broadcast reads) and the
 // launcher table each floating-point mode exports.
 #pragma once
+#ifndef MLB_HOST_EMULATION          // tests/emul compiles the kernel SOURCE for the host (test infrastructure, never a product path)
 #include <cuda_runtime.h>
+#define MLB_DYNAMIC_SMEM(type, name) extern __shared__ type name[]
+#endif
 
 #include "mlb_internal.h"
 
@@ -20,8 +23,8 @@ struct DevGeom {
     const double * bnd_s;         // [Npad] 2*pow(V,1/2) (solver.cpp:662-666), computed on the host with libm pow
     const double * face_nx, * face_ny, * face_area;   // [NFpad]
     const double * slot_fx;       // [n_slots][4][Npad]
-    const double * slot_nA;       // viscous: [n_slots][2][Npad] outward area-weighted face normals of every reconstructed cell
-    const double * face_d;        // viscous: [2][NFpad] centroid line of every face (boundary: mirror image)
+    const double * slot_d;        // viscous: [n_slots][2][Npad] centroid-to-neighbour-centroid vectors of every reconstructed cell (boundary: mirror image)
+    const double * face_d;        // viscous: [4][NFpad] centroid line d of every face (boundary: to the mirror image), cell 0 centroid -> face mid-point r
     uint32_t NFpad;
     const uint32_t * face_cl;     // [NFpad] cell on side 0 (normal points out of it)
     const int32_t * face_cr;      // [NFpad] cell on side 1 ; < 0: -(bc index + 1) ; INT32_MIN: no flux
@@ -61,7 +64,7 @@ struct StageArgs {
     const double * Uin;           // AoS [Npad][4]: state the residual is evaluated on
     const double * Fc;            // TENO: cell-centred face values AoS [Npad][n_slots * Q][4]
     double * AF;                  // [NFpad][4] area * quadrature-averaged flux per face (written by the face kernel)
-    double * G;                   // viscous: Green-Gauss gradients AoS [Npad][6] = d(u, v, T)/d(x, y); null when mu == 0
+    double * G;                   // viscous: least-squares gradients AoS [Npad][6] = d(u, v, T)/d(x, y); null when mu == 0
     const double * k_override;    // AoS [Npad][4] or null: state-independent residual (test hook)
     double * scal;                // device scalars
     unsigned long long * step_counter;

@@ -313,8 +313,9 @@ __device__ __forceinline__ void rk_update(const RkArgs & rk, const double * Uin,
 // ---------------------------------------------------------------------------------------------------------------
 // Viscous terms (new: the reference is Euler only, physics/physics.h:23-29; SURVEY 8f N4, BASELINE configs[4]).  Compiled in
 // only for mu > 0: with mu == 0 the instantiations below are not launched and the path is the reference's, bit for bit.
-//   visc_grad_kernel   Green-Gauss gradients of (u, v, T) of every owned and first-ring ghost cell from the cell averages:
-//                      grad_i = 1/V_i sum_faces phi_f (n A)_out, phi_f = mean of the two cells' values (boundary: the wall's)
+//   visc_grad_kernel   least-squares gradients of (u, v, T) of every owned and first-ring ghost cell from the cell averages of its
+//                      face neighbours (boundary faces: the mirror state that puts the boundary's value on the face), weights
+//                      1 / distance^2: exact for linear fields on any mesh (Green-Gauss with face averages is not, on triangles)
 //   viscous_flux()     at a face: gradient = mean of the two cells' gradients, with its component along the centroid line
 //                      replaced by the two-point difference (no odd-even decoupling); Newtonian stress with Stokes' hypothesis,
 //                      Fourier heat flux; returns F_v . n
@@ -344,33 +345,43 @@ __global__ void __launch_bounds__(256) visc_grad_kernel(const __grid_constant__ 
     double Ui[4], wi[3];
     ld4(a.Uin, i, Ui);
     cons_to_uvT(a.ph.gas, Ui, wi);
-    double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    // inverse-distance weighted least squares over the face neighbours: min sum_j w_j (phi_j - phi_i - g . d_j)^2, w_j = 1 / |d_j|^2
+    double axx = 0.0, axy = 0.0, ayy = 0.0, bx[3] = {0.0, 0.0, 0.0}, by[3] = {0.0, 0.0, 0.0};
     const int nf = a.g.nfc[i];
     for (int j = 0; j < nf; j++) {
         const size_t at = (size_t)j * Np + i;
-        const double ax = a.g.slot_nA[((size_t)j * 2) * Np + i], ay = a.g.slot_nA[((size_t)j * 2 + 1) * Np + i];
+        const double dx = a.g.slot_d[((size_t)j * 2) * Np + i], dy = a.g.slot_d[((size_t)j * 2 + 1) * Np + i];
+        const double d2 = dx * dx + dy * dy;
+        if (!(d2 > 0.0)) continue;
         const int32_t nbr = a.g.slot_nbr[at];
-        double wf[3];
+        double wn[3];
         if (nbr >= 0) {
-            double Un[4], wn[3];
+            double Un[4];
             ld4(a.Uin, (size_t)nbr, Un);
             cons_to_uvT(a.ph.gas, Un, wn);
+        } else if (nbr != INT32_MIN) {       // mirror state: the value ON the face is the boundary's
+            const double id = 1.0 / sqrt(d2);
+            double wf[3];
+            boundary_face_uvT(a.ph.bcs[-nbr - 1], dx * id, dy * id, wi, wf);
 #pragma unroll
-            for (int v = 0; v < 3; v++) wf[v] = 0.5 * (wi[v] + wn[v]);
-        } else if (nbr != INT32_MIN) {
-            const double ia = 1.0 / sqrt(ax * ax + ay * ay);
-            boundary_face_uvT(a.ph.bcs[-nbr - 1], ax * ia, ay * ia, wi, wf);
+            for (int v = 0; v < 3; v++) wn[v] = 2.0 * wf[v] - wi[v];
         } else {
 #pragma unroll
-            for (int v = 0; v < 3; v++) wf[v] = wi[v];
+            for (int v = 0; v < 3; v++) wn[v] = wi[v];
         }
+        const double w = 1.0 / d2;
+        axx += w * dx * dx; axy += w * dx * dy; ayy += w * dy * dy;
 #pragma unroll
-        for (int v = 0; v < 3; v++) { acc[2 * v] += wf[v] * ax; acc[2 * v + 1] += wf[v] * ay; }
+        for (int v = 0; v < 3; v++) { const double dphi = w * (wn[v] - wi[v]); bx[v] += dphi * dx; by[v] += dphi * dy; }
     }
-    const double iv = 1.0 / a.g.cell_vol[i];
+    const double det = axx * ayy - axy * axy;
+    const double idet = det != 0.0 ? 1.0 / det : 0.0;
     double * G = a.G + 6 * (size_t)i;
 #pragma unroll
-    for (int v = 0; v < 6; v++) G[v] = acc[v] * iv;
+    for (int v = 0; v < 3; v++) {
+        G[2 * v] = (ayy * bx[v] - axy * by[v]) * idet;
+        G[2 * v + 1] = (axx * by[v] - axy * bx[v]) * idet;
+    }
 }
 
 // F_v . n at face f (unit normal n out of cell cl); cr < 0: boundary with condition bc
@@ -410,7 +421,11 @@ __device__ __forceinline__ void viscous_flux(const StageArgs & a, uint32_t f, ui
         const double corr = (wr[v] - wl[v]) * id - (mx * ex + my * ey);
         gx[v] = mx + corr * ex; gy[v] = my + corr * ey;
     }
-    const double uf = 0.5 * (wl[0] + wr[0]), vf = 0.5 * (wl[1] + wr[1]);
+    // velocity AT the face mid-point (the work of the stress): both cells' linear reconstructions, averaged - exact for linear
+    // fields on skewed meshes, where the mean of the two cell values is not
+    const double rx = a.g.face_d[2 * (size_t)a.g.NFpad + f], ry = a.g.face_d[3 * (size_t)a.g.NFpad + f];
+    const double uf = 0.5 * ((wl[0] + Gl[0] * rx + Gl[1] * ry) + (wr[0] + Gr[0] * (rx - dx) + Gr[1] * (ry - dy)));
+    const double vf = 0.5 * ((wl[1] + Gl[2] * rx + Gl[3] * ry) + (wr[1] + Gr[2] * (rx - dx) + Gr[3] * (ry - dy)));
     const double div = gx[0] + gy[1];
     const double txx = g.mu * (2.0 * gx[0] - (2.0 / 3.0) * div), tyy = g.mu * (2.0 * gy[1] - (2.0 / 3.0) * div), txy = g.mu * (gy[0] + gx[1]);
     Fv[0] = 0.0;
@@ -628,7 +643,7 @@ template <int ORDER, int MP>
 __global__ void __launch_bounds__(RECON_THREADS) teno_recon_kernel(const __grid_constant__ ReconArgs a) {
     constexpr int K = (ORDER + 1) * (ORDER + 2) / 2;
     constexpr int MAXS = 1 + MAX_SLOTS;
-    extern __shared__ double dof_sm[];   // [S][K][RECON_THREADS]
+    MLB_DYNAMIC_SMEM(double, dof_sm);    // [S][K][RECON_THREADS]
     const int tid = threadIdx.x;
     const uint32_t cell = blockIdx.x * (RECON_THREADS / 4) + (tid >> 2);
     const int var = tid & 3;
@@ -730,12 +745,15 @@ __global__ void __launch_bounds__(RECON_THREADS) teno_recon_kernel(const __grid_
     }
 }
 
+#ifndef MLB_HOST_EMULATION           // the streaming kernels are PTX (TMA, mbarriers): not part of the host emulation
 #ifdef MLB_STREAM_KERNELS
 #include "teno_stream.cuh"
 #else
 #include "teno_strict_stream.cuh"
 #endif
+#endif
 #include "teno_generic.cuh"
+#ifndef MLB_HOST_EMULATION           // from here on: atomics, launch syntax
 
 // ---------------------------------------------------------------------------------------------------------------
 // Spectral radius + max + dt — SpectralRadiusFunctor / Solver::calc_dt (solver/solver.cpp:580-742)
@@ -946,6 +964,8 @@ static const KernelTable table = {MLB_STR(MLB_KNS), launch_gradients, launch_fac
 static const KernelTable table = {MLB_STR(MLB_KNS), launch_gradients, launch_faces, launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
                                   launch_prims_soa, recon_supported, nullptr, nullptr};
 #endif
+
+#endif  // MLB_HOST_EMULATION
 
 }  // namespace MLB_KNS
 }  // namespace mlb

@@ -122,8 +122,10 @@ struct Prep {
     dvec cell_xy;          // [2][Npad]
     dvec face_nx, face_ny, face_area;   // [NFpad] unit normal (common_math.h:101-106) and area
     dvec slot_fx;          // TENO: [n_slots][4][Npad] face end points in the cell's reference coordinates
-    dvec slot_nA;          // viscous: [n_slots][2][Npad] outward area-weighted normal of every face of every reconstructed cell (Green-Gauss)
-    dvec face_d;           // viscous: [2][NFpad] centroid-to-centroid vector (boundary faces: twice the normal distance to the face)
+    dvec slot_d;           // viscous: [n_slots][2][Npad] vector from the centroid of every reconstructed cell to its neighbour's across face j
+                           // (boundary faces: to the centroid's mirror image): the least-squares gradient stencil
+    dvec face_d;           // viscous: [4][NFpad] centroid-to-centroid vector d (boundary faces: to the mirror image) and the vector r
+                           // from cell 0's centroid to the face's mid-point
     uvec face_cl;          // [NFpad] library cell on side 0 of the face
     ivec face_cr;          // [NFpad] library cell on side 1 ; < 0: -(bc index + 1) ; INT32_MIN: no flux through this face
     std::vector<uint8_t> face_slots;   // [NFpad] slot in cell 0 | slot in cell 1 << 4

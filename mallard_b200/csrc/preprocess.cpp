@@ -751,30 +751,42 @@ void preprocess(const HostMesh & m, const mlb_numerics & num, const std::vector<
     }
 
     if (!slot_err.empty()) throw std::runtime_error(slot_err);
-    if (opt.viscous) {   // Green-Gauss geometry of every reconstructed cell, centroid line of every held face
-        P.slot_nA.assign((size_t)n_slots * 2 * Np, 0.0);
-        P.face_d.assign(2 * (size_t)P.NFpad, 0.0);
+    if (opt.viscous) {   // least-squares geometry of every reconstructed cell, centroid line of every held face
+        P.slot_d.assign((size_t)n_slots * 2 * Np, 0.0);
+        P.face_d.assign(4 * (size_t)P.NFpad, 0.0);
 #pragma omp parallel for schedule(static)
         for (int64_t ii = 0; ii < (int64_t)n_recon; ii++) {
             const uint32_t i = (uint32_t)ii, c = order[i];
             for (int j = 0; j < m.nfc(c); j++) {
                 const uint32_t f = m.foc[m.ofc[c] + j];
-                const double sgn = m.cof[2 * (size_t)f] == (int32_t)c ? 1.0 : -1.0;
-                P.slot_nA[((size_t)j * 2) * Np + i] = sgn * m.face_n[2 * (size_t)f];
-                P.slot_nA[((size_t)j * 2 + 1) * Np + i] = sgn * m.face_n[2 * (size_t)f + 1];
+                const int32_t a = m.cof[2 * (size_t)f], b = m.cof[2 * (size_t)f + 1];
+                double dx, dy;
+                if (b >= 0) {
+                    const uint32_t o = a == (int32_t)c ? (uint32_t)b : (uint32_t)a;
+                    dx = m.cell_xy[2 * (size_t)o] - m.cell_xy[2 * (size_t)c]; dy = m.cell_xy[2 * (size_t)o + 1] - m.cell_xy[2 * (size_t)c + 1];
+                } else if (b == -1) {   // mirror image of the centroid in the boundary face
+                    const double nx = m.face_n[2 * (size_t)f], ny = m.face_n[2 * (size_t)f + 1], inv = 1 / std::sqrt(nx * nx + ny * ny);
+                    const double * n0 = &m.node_xy[2 * (size_t)m.nof[m.onf[f]]], * n1 = &m.node_xy[2 * (size_t)m.nof[m.onf[f] + 1]];
+                    const double dist = (0.5 * (n0[0] + n1[0]) - m.cell_xy[2 * (size_t)c]) * nx * inv + (0.5 * (n0[1] + n1[1]) - m.cell_xy[2 * (size_t)c + 1]) * ny * inv;
+                    dx = 2.0 * dist * nx * inv; dy = 2.0 * dist * ny * inv;
+                } else continue;        // cut face of a rank-local mesh (first-ring ghosts of viscous runs were checked above)
+                P.slot_d[((size_t)j * 2) * Np + i] = dx;
+                P.slot_d[((size_t)j * 2 + 1) * Np + i] = dy;
             }
         }
         for (uint32_t i = 0; i < P.NF; i++) {
             const uint32_t f = P.perm_faces[i];
             const int32_t a = m.cof[2 * (size_t)f], b = m.cof[2 * (size_t)f + 1];
+            const double * n0 = &m.node_xy[2 * (size_t)m.nof[m.onf[f]]], * n1 = &m.node_xy[2 * (size_t)m.nof[m.onf[f] + 1]];
+            const double rx = 0.5 * (n0[0] + n1[0]) - m.cell_xy[2 * (size_t)a], ry = 0.5 * (n0[1] + n1[1]) - m.cell_xy[2 * (size_t)a + 1];
             double dx, dy;
             if (b >= 0) { dx = m.cell_xy[2 * (size_t)b] - m.cell_xy[2 * (size_t)a]; dy = m.cell_xy[2 * (size_t)b + 1] - m.cell_xy[2 * (size_t)a + 1]; }
             else {   // mirror image of the cell centroid in the face
-                const double * n0 = &m.node_xy[2 * (size_t)m.nof[m.onf[f]]], * n1 = &m.node_xy[2 * (size_t)m.nof[m.onf[f] + 1]];
-                const double dist = (0.5 * (n0[0] + n1[0]) - m.cell_xy[2 * (size_t)a]) * P.face_nx[i] + (0.5 * (n0[1] + n1[1]) - m.cell_xy[2 * (size_t)a + 1]) * P.face_ny[i];
+                const double dist = rx * P.face_nx[i] + ry * P.face_ny[i];
                 dx = 2.0 * dist * P.face_nx[i]; dy = 2.0 * dist * P.face_ny[i];
             }
             P.face_d[i] = dx; P.face_d[(size_t)P.NFpad + i] = dy;
+            P.face_d[2 * (size_t)P.NFpad + i] = rx; P.face_d[3 * (size_t)P.NFpad + i] = ry;
         }
     }
     tick("slots done");

@@ -50,7 +50,7 @@ __device__ __forceinline__ double basis_1d(int basis, int p, double x) {
 
 // dynamic shared memory: b[Mp][32] | dof[S][K][32]
 __global__ void __launch_bounds__(GTHREADS) teno_generic_kernel(const __grid_constant__ ReconArgs a) {
-    extern __shared__ double gsm[];
+    MLB_DYNAMIC_SMEM(double, gsm);
     const int tid = threadIdx.x;
     const uint32_t cell = blockIdx.x * (GTHREADS / 4) + (tid >> 2);
     const int var = tid & 3;
@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(GTHREADS) teno_generic_kernel(const __grid_con
     }
 }
 
+#ifndef MLB_HOST_EMULATION
 static void launch_generic(const ReconArgs & a, cudaStream_t st) {
     const size_t smem = ((size_t)a.Mp + (size_t)a.S * a.K) * GTHREADS * sizeof(double);
     ensure_dynamic_smem(reinterpret_cast<const void *>(teno_generic_kernel), smem);
@@ -146,6 +147,7 @@ static void launch_generic(const ReconArgs & a, cudaStream_t st) {
     const unsigned grid = (a.g.N_recon + cells_per_block - 1) / cells_per_block;
     if (grid) teno_generic_kernel<<<grid, GTHREADS, smem, st>>>(a);
 }
+#endif
 
 static bool generic_supported(int order, int K, int Mp, int S) {
     return order >= 1 && order <= GMAX_ORDER && K <= Mp && S <= 1 + MAX_SLOTS &&

@@ -1,0 +1,108 @@
+"""TEST INFRASTRUCTURE - ctypes front end of tests/emul/kernel_emulation.cpp (the CUDA kernel source compiled for the host and
+executed thread by thread; see that file).  Never imported by the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import mallard_b200 as mb
+from mallard_b200 import _abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SO = os.path.join(HERE, "libkernel_emulation.so")
+_LIB = None
+
+
+def build():
+    src = os.path.join(HERE, "kernel_emulation.cpp")
+    deps = [src] + [os.path.join(ROOT, "mallard_b200", "csrc", f) for f in ("kernels_impl.cuh", "teno_generic.cuh", "kernel_args.h", "mlb_internal.h")]
+    deps.append(os.path.join(ROOT, "mallard_b200", "libmallard_b200.so"))
+    if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
+        return
+    mb.build()
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(ROOT, "mallard_b200", "csrc"),
+                           src, "-L", os.path.join(ROOT, "mallard_b200"), "-lmallard_b200", "-Wl,-rpath," + os.path.join(ROOT, "mallard_b200"), "-o", SO])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        build()
+        mb.lib()
+        L = C.CDLL(SO)
+        L.emu_create.restype = C.c_void_p
+        L.emu_create.argtypes = [C.POINTER(_abi.MeshView), C.POINTER(_abi.Numerics), C.POINTER(_abi.Physics), C.POINTER(_abi.Bc), C.c_int]
+        L.emu_last_error.restype = C.c_char_p
+        for n in ("emu_set_state", "emu_face_values", "emu_rhs", "emu_gradients"):
+            getattr(L, n).restype = C.c_int
+            getattr(L, n).argtypes = [C.c_void_p, C.c_void_p]
+        L.emu_destroy.argtypes = [C.c_void_p]
+        L.emu_force_generic.argtypes = [C.c_void_p, C.c_int]
+        L.emu_n_quad.argtypes = [C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+class EmulatedSolver:
+    """The calc_face_values / calc_rhs surface of mallard_b200.Solver, computed by the emulated kernels (STRICT arithmetic)."""
+
+    def __init__(self, mesh, recon="FO", riemann="HLLC", integrator="SSPRK3", gas=None, basis="legendre", order=3, factor=2.0, quad_cell_order=0,
+                 quad_face_order=0, bcs=(), teno_fixed=False, renumber="rcm"):
+        self.mesh = mesh
+        num = mb._numerics(recon, riemann, integrator, basis, order, factor, quad_cell_order, quad_face_order, "strict", renumber, teno_fixed, True)
+        phys = mb._physics(gas)
+        self._keep = []
+        cb = (_abi.Bc * max(1, len(bcs)))()
+        for i, b in enumerate(bcs):
+            nb = b["name"].encode()
+            self._keep.append(nb)
+            cb[i].zone_name, cb[i].type = nb, mb.BC[b["type"]]
+            u = b.get("u", (0.0, 0.0))
+            cb[i].u[0], cb[i].u[1] = float(u[0]), float(u[1])
+            cb[i].p, cb[i].T = float(b.get("p", 0.0)), float(b.get("T", 0.0))
+        v, keep = mesh.view()
+        self._keep.append(keep)
+        self._h = lib().emu_create(C.byref(v), C.byref(num), C.byref(phys), cb, len(bcs))
+        if not self._h:
+            raise RuntimeError(lib().emu_last_error().decode())
+        self.n_quad = lib().emu_n_quad(self._h)
+
+    def _ok(self, rc):
+        if rc:
+            raise RuntimeError(lib().emu_last_error().decode())
+
+    def force_generic(self, on=True):
+        lib().emu_force_generic(self._h, int(on))
+
+    def set_state(self, U):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        assert U.shape == (self.mesh.n_cells, 4)
+        self._ok(lib().emu_set_state(self._h, U.ctypes.data_as(C.c_void_p)))
+
+    def calc_face_values(self):
+        F = np.empty((self.mesh.n_faces, self.n_quad, 2, 4))
+        self._ok(lib().emu_face_values(self._h, F.ctypes.data_as(C.c_void_p)))
+        return F
+
+    def calc_rhs(self):
+        r = np.zeros((self.mesh.n_cells, 4))
+        self._ok(lib().emu_rhs(self._h, r.ctypes.data_as(C.c_void_p)))
+        return r
+
+    def gradients(self):
+        G = np.zeros((self.mesh.n_cells, 6))
+        self._ok(lib().emu_gradients(self._h, G.ctypes.data_as(C.c_void_p)))
+        return G
+
+    def close(self):
+        if self._h:
+            lib().emu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -702,6 +702,96 @@ def test_first_order_on_a_mixed_mesh_matches_oracle(oracle_mod):
     assert gu.rel_err(sg.get_state(), so.get("U")) <= 1e-13
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# Viscous terms (BASELINE configs[4]; the reference is Euler only: analytic validation, no oracle)
+# ------------------------------------------------------------------------------------------------------------------
+def _gas(mu, Pr=0.72):
+    return dict(gamma=1.4, p_ref=101325.0, T_ref=298.15, rho_ref=1.225, p_min=-1e20, p_max=1e20, mu=mu, Pr=Pr)
+
+
+R_GAS = 101325.0 / (298.15 * 1.225)
+
+
+def _state_from_prim(rho, u, v, T):
+    cv = R_GAS / 0.4
+    return np.stack([rho, rho * u, rho * v, rho * (cv * T + 0.5 * (u * u + v * v))], 1)
+
+
+@UNVERIFIED_ON_HARDWARE
+@pytest.mark.parametrize("fp", ["strict", "fast"])
+@pytest.mark.parametrize("mtype", ["cartesian", "cartesian_tri", "mixed"])
+def test_viscous_residual_of_couette_flow(mtype, fp):
+    """Plane Couette flow between a fixed and a moving no-slip wall: the viscous part of the residual, rhs(mu) - rhs(0), is exactly
+    (0, 0, 0, mu (U/H)^2) on quadrilaterals, triangles and jittered mixed meshes; on the wall-aligned quadrilateral mesh the whole
+    residual is (tests/test_kernel_emulation.py runs the same check on the host emulation of the kernels)."""
+    from mallard_b200 import synthetic as syn
+    mu, Uw, H, L = 0.05, 3.0, 1.0, 2.0
+    mesh = syn.mixed_tri_quad(24, 20, L, H, seed=5, tri_fraction=0.5) if mtype == "mixed" else mb.Mesh.generate(mtype, 24, 20, L, H)
+    bcs = [dict(name="left", type="extrapolation"), dict(name="right", type="extrapolation"), dict(name="bottom", type="wall_noslip", u=[0.0, 0.0]),
+           dict(name="top", type="wall_noslip", u=[Uw, 0.0])]
+    xy = mesh.arrays["cell_coords"]
+    n = mesh.n_cells
+    U0 = _state_from_prim(np.full(n, 1.2), Uw * xy[:, 1] / H, np.zeros(n), np.full(n, 300.0))
+    res = []
+    for m in (mu, 0.0):
+        s = mb.Solver(mesh, "FO", "HLLC", "SSPRK3", gas=_gas(m), bcs=bcs, fp_mode=fp)
+        s.set_state(U0)
+        res.append(s.calc_rhs())
+        s.close()
+    heat, dv = mu * (Uw / H) ** 2, res[0] - res[1]
+    scale = np.abs(res[1]).max() + 1.0
+    assert np.abs(dv[:, :3]).max() < 1e-11 * scale + 1e-9 and np.abs(dv[:, 3] - heat).max() < 1e-11 * scale + 1e-8 * heat
+    if mtype == "cartesian":
+        assert np.abs(res[0][:, :3]).max() < 1e-7 and np.abs(res[0][:, 3] - heat).max() < 1e-8 * heat + 1e-9
+
+
+@UNVERIFIED_ON_HARDWARE
+def test_decaying_shear_layer_follows_the_diffusion_equation():
+    """Time-dependent check (a Taylor-Green vortex needs periodic boundaries, which the reference does not have): a low-Mach shear
+    layer u(y, 0) = U erf(y / delta0) between slip walls far away diffuses as u = U erf(y / sqrt(delta0^2 + 4 nu t)).  First-order
+    inviscid part (faces aligned with the flow: no numerical diffusion of u), viscous dt limit from the spectral radius; the
+    profile error falls with the mesh (second-order viscous operator)."""
+    from math import erf
+    nu, Uw, d0, T0, rho0 = 0.02, 1.0, 0.08, 300.0, 1.0
+    errs = []
+    for ny in (40, 80):
+        mesh = mb.Mesh.generate("cartesian", 4, ny, 0.1, 2.0)
+        y = mesh.arrays["cell_coords"][:, 1] - 1.0
+        u0 = Uw * np.vectorize(erf)(y / d0)
+        bcs = [dict(name="left", type="extrapolation"), dict(name="right", type="extrapolation"), dict(name="bottom", type="symmetry"),
+               dict(name="top", type="symmetry")]
+        s = mb.Solver(mesh, "FO", "HLLC", "SSPRK3", gas=_gas(nu * rho0), bcs=bcs, fp_mode="fast", keep_stage_rhs=False)
+        s.set_state(_state_from_prim(np.full(mesh.n_cells, rho0), u0, np.zeros(mesh.n_cells), np.full(mesh.n_cells, T0)))
+        t = 0.0
+        while t < 0.2:
+            t, _ = s.run(200, cfl=0.5)
+        U = s.get_state()
+        exact = Uw * np.vectorize(erf)(y / np.sqrt(d0 * d0 + 4.0 * nu * t))
+        errs.append(np.abs(U[:, 1] / U[:, 0] - exact).max())
+        s.close()
+    assert errs[0] < 0.02 and errs[1] < errs[0] / 2.5, errs
+
+
+@UNVERIFIED_ON_HARDWARE
+def test_viscous_run_on_partitioned_ranks_reproduces_the_single_context_run():
+    """Viscous contexts hold a second ghost ring (the least-squares gradients of the first ring need it): bit-identical to the
+    single-context run in STRICT mode."""
+    from test_gpu_multi import Loopback
+    mesh = mb.Mesh.generate("cartesian_tri", 30, 20, 3.0, 2.0)
+    U0 = _random_smooth_state(mesh.arrays["cell_coords"] / 3.0, np.random.default_rng(6))
+    for recon in ("FO", "TENO"):
+        kw = dict(recon=recon, riemann="HLLC", integrator="SSPRK3", order=2, bcs=SYM4, fp_mode="strict", teno_fixed=True, gas=_gas(0.01))
+        one = mb.Solver(mesh, **kw)
+        one.set_state(U0)
+        many = Loopback(mesh, mb.partition(mesh, 3), 3, **kw)
+        many.set_state(U0)
+        for _ in range(3):
+            one.calc_dt(0.3)
+            one.take_step()
+            many.step(0.3)
+        assert np.isfinite(one.get_state()).all() and np.array_equal(one.get_state(), many.state()), recon
+
+
 def test_device_side_field_ranges_and_nan_count():
     """mlb_field_ranges = max_array / min_array of Solver::do_checks (solver.cpp:434-437; `a > max` / `a < min`, so NaN never
     wins) + the NaN test of check_fields (solver.cpp:470-498), against numpy on the exported state."""

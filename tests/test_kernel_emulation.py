@@ -1,0 +1,270 @@
+"""Host emulation of the CUDA kernel SOURCE against the oracle, the reference's dumps and analytic solutions (CPU; no GPU).
+
+tests/emul/kernel_emulation.cpp compiles mallard_b200/csrc/kernels_impl.cuh - the file nvcc compiles for sm_100a - for the host
+(STRICT arithmetic: -ffp-contract=off) and runs its kernels thread by thread.  Covered: teno_recon_kernel, the generic TENO
+kernel, visc_grad_kernel, face_flux_kernel (QT = 0 / 1), gather_stage_kernel; not covered: the PTX streaming kernels and the CFL
+kernel.  Two uses:
+  * the kernels added after this round's GPU budget was spent (generic TENO for basis_order 5..9 / other stencil factors,
+    quadrilaterals under TENO, viscous terms) are checked here against the oracle / analytically, since their GPU tests
+    (tests/test_gpu_parity.py, MLB_RUN_UNVERIFIED=1) have not run on a B200 yet;
+  * a second execution of kernels that HAVE run on hardware: bit-exact against the oracle on triangles.
+This is test infrastructure; the product has no CPU path (mallard_b200 refuses to compute without a CUDA device)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+import mallard_b200 as mb
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+from emulation import EmulatedSolver  # noqa: E402
+
+SYM4 = [dict(name=n, type="symmetry") for n in ("left", "right", "top", "bottom")]
+EXTRAP4 = [dict(name=n, type="extrapolation") for n in ("left", "right", "top", "bottom")]
+CONN_KEYS = ["node_coords", "offsets_nodes_of_cell", "nodes_of_cell", "offsets_faces_of_cell", "faces_of_cell", "offsets_nodes_of_face",
+             "nodes_of_face", "cells_of_face"]
+
+
+def _smooth(xy, rng):
+    k = rng.uniform(0.5, 2.0, 4)
+    rho = 1.0 + 0.3 * np.sin(2 * np.pi * k[0] * xy[:, 0]) * np.cos(2 * np.pi * k[1] * xy[:, 1])
+    u = 0.4 + 0.2 * np.cos(2 * np.pi * k[2] * xy[:, 1]); v = -0.3 + 0.2 * np.sin(2 * np.pi * k[3] * xy[:, 0])
+    p = 1.0 + 0.2 * np.cos(2 * np.pi * (xy[:, 0] - xy[:, 1]))
+    e = p / (0.4 * rho)
+    return np.stack([rho, rho * u, rho * v, rho * (e + 0.5 * (u * u + v * v))], 1)
+
+
+@pytest.mark.parametrize("order,basis,fixed,riemann", [(3, "legendre", False, "HLLC"), (3, "legendre", True, "HLL"), (1, "legendre", True, "Rusanov"),
+                                                       (4, "legendre", True, "HLLC"), (2, "monomial", True, "HLLC")])
+def test_emulated_teno_kernels_are_bit_exact_against_the_oracle(oracle_mod, order, basis, fixed, riemann):
+    """teno_recon_kernel + face_flux_kernel + gather_stage_kernel, compiled for the host: the oracle's face values and residual,
+    bit for bit (legendre; monomial goes through pow: same libm here), and the generic kernel equals the specialised one."""
+    mesh = mb.Mesh.generate("cartesian_tri", 16, 14, 2.0, 1.0)
+    om = oracle_mod.Mesh.generate("cartesian_tri", 16, 14, 2.0, 1.0)
+    bcs = [dict(name="left", type="extrapolation"), dict(name="right", type="p_out", p=0.9), dict(name="top", type="symmetry"),
+           dict(name="bottom", type="wall_adiabatic")]
+    kw = dict(recon="TENO", riemann=riemann, integrator="SSPRK3", bcs=bcs, basis=basis, order=order, teno_fixed=fixed)
+    so, se = oracle_mod.Solver(om, **kw), EmulatedSolver(mesh, **kw)
+    U0 = _smooth(mesh.arrays["cell_coords"], np.random.default_rng(11))
+    so.set_state(U0); se.set_state(U0)
+    real = gu.real_faces(mesh.arrays["cells_of_face"], mesh.arrays["nodes_of_face"])
+    Fo, Fe = so.calc_face_values()[real][:, :, 0], se.calc_face_values()[real][:, :, 0]
+    ro, re = so.calc_rhs(), se.calc_rhs()
+    assert np.array_equal(Fe, Fo, equal_nan=True)
+    assert np.array_equal(re, ro, equal_nan=True)
+    se.force_generic(True)
+    assert np.array_equal(se.calc_face_values()[real][:, :, 0], Fe, equal_nan=True) and np.array_equal(se.calc_rhs(), re, equal_nan=True)
+
+
+@pytest.mark.parametrize("order,factor,qc,basis", [(5, 2.0, 5, "legendre"), (6, 2.0, 5, "legendre"), (7, 2.0, 5, "monomial"), (9, 2.0, 5, "legendre"),
+                                                   (2, 1.5, 0, "legendre"), (3, 3.0, 0, "monomial"), (4, 2.5, 0, "legendre")])
+def test_emulated_generic_kernel_orders_5_to_9_and_other_stencil_factors_vs_oracle(oracle_mod, order, factor, qc, basis):
+    """Everything the reference's TOML accepts beyond the specialised kernels (face_reconstruction.cpp:110-116,170-180)."""
+    nx, ny = (12, 10) if order >= 7 else (14, 12)          # 240 cells hold the 110-cell stencils of p = 9; the host QR dominates the run time
+    om = oracle_mod.Mesh.generate("cartesian_tri", nx, ny, 2.0, 1.0)
+    mesh = mb.Mesh.generate("cartesian_tri", nx, ny, 2.0, 1.0)
+    kw = dict(recon="TENO", riemann="HLLC", integrator="SSPRK3", bcs=SYM4, basis=basis, order=order, factor=factor, quad_cell_order=qc, teno_fixed=True)
+    so, se = oracle_mod.Solver(om, **kw), EmulatedSolver(mesh, **kw)
+    U0 = _smooth(mesh.arrays["cell_coords"], np.random.default_rng(23))
+    so.set_state(U0); se.set_state(U0)
+    real = gu.real_faces(mesh.arrays["cells_of_face"], mesh.arrays["nodes_of_face"])
+    Fo, Fe = so.calc_face_values()[real][:, :, 0], se.calc_face_values()[real][:, :, 0]
+    assert np.array_equal(Fe, Fo, equal_nan=True), gu.rel_err(Fe, Fo)
+    assert np.array_equal(se.calc_rhs(), so.calc_rhs(), equal_nan=True)
+
+
+@pytest.mark.parametrize("name", ["teno_legendre_12x10_p5", "teno_legendre_8x7_p2_f15", "teno_smooth_6x6", "teno_monomial_7x6_p3"])
+def test_emulated_kernels_against_dumps_of_the_unmodified_reference(name):
+    meta, g = gu.load(name)
+    mm = meta["mesh"]
+    mesh = mb.Mesh.generate(mm["type"], mm["Nx"], mm["Ny"], mm["Lx"], mm["Ly"])
+    se = EmulatedSolver(mesh, **gu.solver_kwargs(meta))
+    se.set_state(g["U0"])
+    real = gu.real_faces(mesh.arrays["cells_of_face"], mesh.arrays["nodes_of_face"])
+    interior = real & (mesh.arrays["cells_of_face"][:, 1] >= 0)
+    F = se.calc_face_values()
+    # 1/(SI+eps)^6 is three multiplications here and libm pow in the reference (last ulp of a weight that is then normalised away
+    # in the smooth branch): element-wise 1e-12, bit-exact in practice on these cases
+    assert gu.rel_err(F[real][:, :, 0], g["F_stage1"][real][:, :, 0]) <= 1e-12
+    assert gu.rel_err(F[interior][:, :, 1], g["F_stage1"][interior][:, :, 1]) <= 1e-12
+    assert gu.rel_err(se.calc_rhs(), g["rhs_stage1"]) <= 1e-12
+
+
+# ---- quadrilaterals and mixed meshes under TENO: k-exactness (no oracle exists: the reference throws, face_reconstruction.cpp:485-487)
+_D5 = (np.array([[1 / 3, 1 / 3], [0.059715871789770, 0.470142064105115], [0.470142064105115, 0.059715871789770], [0.470142064105115, 0.470142064105115],
+                 [0.797426985353087, 0.101286507323456], [0.101286507323456, 0.797426985353087], [0.101286507323456, 0.101286507323456]]),
+       np.array([0.225, 0.132394152788506, 0.132394152788506, 0.132394152788506, 0.125939180544827, 0.125939180544827, 0.125939180544827]))
+
+
+def _cell_averages(mesh, f):
+    A = mesh.arrays
+    X, onc, noc = A["node_coords"], A["offsets_nodes_of_cell"].astype(np.int64), A["nodes_of_cell"].astype(np.int64)
+    out, area = np.zeros((mesh.n_cells, 4)), np.zeros(mesh.n_cells)
+    xy, w = _D5
+    for c in range(mesh.n_cells):
+        n = noc[onc[c]:onc[c + 1]]
+        for t in range(len(n) - 2):
+            v0, v1, v2 = X[n[0]], X[n[t + 1]], X[n[t + 2]]
+            a = 0.5 * abs((v1[0] - v0[0]) * (v2[1] - v0[1]) - (v2[0] - v0[0]) * (v1[1] - v0[1]))
+            p = v0[None, :] + xy[:, :1] * (v1 - v0)[None, :] + xy[:, 1:] * (v2 - v0)[None, :]
+            out[c] += a * (w[:, None] * f(p[:, 0], p[:, 1])).sum(axis=0)
+            area[c] += a
+    return out / area[:, None]
+
+
+@pytest.mark.parametrize("order,tri_fraction", [(1, 0.5), (2, 0.5), (3, 0.5), (3, 0.0), (2, 1.0), (4, 0.6)])
+def test_emulated_teno_on_quadrilateral_and_mixed_meshes_is_k_exact(order, tri_fraction):
+    """An order-p reconstruction must reproduce every polynomial of degree <= p from its cell averages at every face quadrature
+    point, from both sides of every interior face - on quadrilaterals, triangles and any mix, jittered."""
+    from mallard_b200 import synthetic as syn
+    mesh = syn.mixed_tri_quad(12, 10, 3.0, 2.0, seed=3, tri_fraction=tri_fraction)
+    nn = np.diff(mesh.arrays["offsets_nodes_of_cell"])
+    assert (tri_fraction == 1.0 or (nn == 4).any()) and (tri_fraction == 0.0 or (nn == 3).any())
+    coef = np.random.default_rng(17).uniform(-1.0, 1.0, size=(4, order + 1, order + 1))
+
+    def f(x, y):
+        out = np.zeros(x.shape + (4,))
+        for v in range(4):
+            for i in range(order + 1):
+                for j in range(order + 1 - i):
+                    out[..., v] += coef[v, i, j] * x ** i * y ** j
+        out[..., 0] += 5.0
+        return out
+    se = EmulatedSolver(mesh, "TENO", "HLLC", "SSPRK3", order=order, bcs=EXTRAP4, teno_fixed=True)
+    se.set_state(_cell_averages(mesh, f))
+    F = se.calc_face_values()
+    A = mesh.arrays
+    nof, cof = A["nodes_of_face"].reshape(-1, 2).astype(np.int64), A["cells_of_face"]
+    xi = {1: [0.0], 2: [-0.5773502691896257, 0.5773502691896257], 3: [-0.7745966692414834, 0.0, 0.7745966692414834]}[se.n_quad]
+    x0, x1 = A["node_coords"][nof[:, 0]], A["node_coords"][nof[:, 1]]
+    worst = 0.0
+    for q, z in enumerate(xi):
+        pq = (z + 1.0) * 0.5 * (x1 - x0) + x0
+        exact = f(pq[:, 0], pq[:, 1])
+        worst = max(worst, np.abs(F[:, q, 0] - exact).max(), np.abs(F[cof[:, 1] >= 0][:, q, 1] - exact[cof[:, 1] >= 0]).max())
+    assert worst <= 2e-9 * (10.0 ** max(0, order - 3)), worst
+    # free-stream preservation through the flux and gather kernels on the mixed mesh
+    se.set_state(np.tile([1.2, 0.36, -0.24, 2.6], (mesh.n_cells, 1)))
+    rhs = se.calc_rhs()
+    interior = np.ones(mesh.n_cells, bool)
+    interior[cof[cof[:, 1] < 0, 0]] = False
+    assert np.abs(rhs[interior]).max() < 1e-9
+
+
+def test_emulated_first_order_on_a_mixed_mesh_is_bit_exact_against_the_oracle(oracle_mod):
+    from mallard_b200 import synthetic as syn
+    mesh = syn.mixed_tri_quad(14, 10, 3.0, 2.0, seed=9, tri_fraction=0.4)
+    om = oracle_mod.Mesh.from_arrays({k: mesh.arrays[k] for k in CONN_KEYS}, mesh.zones)
+    bcs = [dict(name="left", type="extrapolation"), dict(name="right", type="p_out", p=0.9), dict(name="top", type="symmetry"),
+           dict(name="bottom", type="wall_adiabatic")]
+    so, se = oracle_mod.Solver(om, "FO", "HLLC", "SSPRK3", bcs=bcs), EmulatedSolver(mesh, "FO", "HLLC", "SSPRK3", bcs=bcs)
+    U0 = _smooth(mesh.arrays["cell_coords"] / 3.0, np.random.default_rng(2))
+    so.set_state(U0); se.set_state(U0)
+    assert np.array_equal(se.calc_rhs(), so.calc_rhs())
+
+
+# ---- viscous terms (new: the reference is Euler only): analytic checks ------------------------------------------------------
+def _gas(mu):
+    return dict(gamma=1.4, p_ref=101325.0, T_ref=298.15, rho_ref=1.225, p_min=-1e20, p_max=1e20, mu=mu, Pr=0.72)
+
+
+def _state_from_prim(rho, u, v, T, R):
+    cv = R / 0.4
+    return np.stack([rho, rho * u, rho * v, rho * (cv * T + 0.5 * (u * u + v * v))], 1)
+
+
+R_GAS = 101325.0 / (298.15 * 1.225)
+
+
+@pytest.mark.parametrize("mtype", ["cartesian", "cartesian_tri", "mixed"])
+def test_viscous_residual_of_couette_flow(mtype):
+    """Plane Couette flow u = U y / H, v = 0, uniform p and T between a fixed and a moving no-slip wall.  The least-squares
+    gradients are exact (du/dy = U / H, everything else 0) on quadrilaterals, triangles and jittered mixed meshes, wall cells
+    included; the VISCOUS part of the residual, rhs(mu) - rhs(0), is then exactly (0, 0, 0, mu (U / H)^2): uniform shear stress,
+    viscous heating.  On the wall-aligned quadrilateral mesh the inviscid part vanishes as well (HLLC resolves the tangential
+    jump across faces parallel to the flow exactly), so the full residual is the analytic one."""
+    from mallard_b200 import synthetic as syn
+    mu, Uw, H, L = 0.05, 3.0, 1.0, 2.0
+    mesh = syn.mixed_tri_quad(12, 10, L, H, seed=5, tri_fraction=0.5) if mtype == "mixed" else mb.Mesh.generate(mtype, 12, 10, L, H)
+    bcs = [dict(name="left", type="extrapolation"), dict(name="right", type="extrapolation"), dict(name="bottom", type="wall_noslip", u=[0.0, 0.0]),
+           dict(name="top", type="wall_noslip", u=[Uw, 0.0])]
+    xy = mesh.arrays["cell_coords"]
+    n = mesh.n_cells
+    U0 = _state_from_prim(np.full(n, 1.2), Uw * xy[:, 1] / H, np.zeros(n), np.full(n, 300.0), R_GAS)
+    res = []
+    for m in (mu, 0.0):
+        se = EmulatedSolver(mesh, "FO", "HLLC", "SSPRK3", gas=_gas(m), bcs=bcs)
+        se.set_state(U0)
+        if m > 0:
+            G = se.gradients()
+            assert np.abs(G[:, 1] - Uw / H).max() < 1e-10 and np.abs(G[:, [0, 2, 3, 4, 5]]).max() < 1e-9
+        res.append(se.calc_rhs())
+    heat = mu * (Uw / H) ** 2
+    dv = res[0] - res[1]
+    scale = np.abs(res[1]).max() + 1.0                              # the difference of two residuals carries their rounding
+    assert np.abs(dv[:, :3]).max() < 1e-12 * scale + 1e-9 and np.abs(dv[:, 3] - heat).max() < 1e-12 * scale + 1e-8 * heat
+    if mtype == "cartesian":
+        rhs = res[0]
+        assert np.abs(rhs[:, 0]).max() < 1e-9 and np.abs(rhs[:, 1]).max() < 1e-9 and np.abs(rhs[:, 2]).max() < 1e-7
+        assert np.abs(rhs[:, 3] - heat).max() < 1e-8 * heat + 1e-9
+
+
+def test_viscous_operator_is_second_order_accurate():
+    """(rhs with mu) - (rhs without) against div(tau) and div(tau.u - q) of a smooth field at the cell centroids, interior cells,
+    two resolutions of a regular quadrilateral mesh: the error falls by ~4 when the mesh is refined by 2."""
+    mu, Pr, gamma = 0.02, 0.72, 1.4
+    cp = R_GAS * gamma / (gamma - 1.0)
+    kappa = mu * cp / Pr
+    k = np.pi
+
+    def fields(x, y):
+        u = np.sin(k * x) * np.cos(k * y); v = -0.5 * np.cos(k * x) * np.sin(k * y); T = 300.0 + 10.0 * np.sin(k * x) * np.sin(k * y)
+        ux, uy = k * np.cos(k * x) * np.cos(k * y), -k * np.sin(k * x) * np.sin(k * y)
+        vx, vy = 0.5 * k * np.sin(k * x) * np.sin(k * y), -0.5 * k * np.cos(k * x) * np.cos(k * y)
+        uxx, uyy, uxy = -k * k * u, -k * k * u, -k * k * np.cos(k * x) * np.sin(k * y)
+        vxx, vyy, vxy = -k * k * v, -k * k * v, 0.5 * k * k * np.sin(k * x) * np.cos(k * y)
+        Txx_yy = -2 * k * k * 10.0 * np.sin(k * x) * np.sin(k * y)
+        div = ux + vy
+        txx, tyy, txy = mu * (2 * ux - 2 / 3 * div), mu * (2 * vy - 2 / 3 * div), mu * (uy + vx)
+        dtxx_dx = mu * (2 * uxx - 2 / 3 * (uxx + vxy)); dtxy_dy = mu * (uyy + vxy)
+        dtxy_dx = mu * (uxy + vxx); dtyy_dy = mu * (2 * vyy - 2 / 3 * (uxy + vyy))
+        mx, my = dtxx_dx + dtxy_dy, dtxy_dx + dtyy_dy
+        en = u * mx + v * my + txx * ux + txy * (uy + vx) + tyy * vy + kappa * Txx_yy
+        return u, v, T, mx, my, en
+
+    errs = []
+    for n in (16, 32):
+        mesh = mb.Mesh.generate("cartesian", n, n, 1.0, 1.0)
+        xy = mesh.arrays["cell_coords"]
+        u, v, T, mx, my, en = fields(xy[:, 0], xy[:, 1])
+        U0 = _state_from_prim(np.full(mesh.n_cells, 1.0), u, v, T, R_GAS)
+        res = []
+        for m in (mu, 0.0):
+            se = EmulatedSolver(mesh, "FO", "HLLC", "SSPRK3", gas=dict(_gas(m), Pr=Pr), bcs=EXTRAP4)
+            se.set_state(U0)
+            res.append(se.calc_rhs())
+        dv = res[0] - res[1]
+        cof = mesh.arrays["cells_of_face"]
+        inner = np.ones(mesh.n_cells, bool)
+        inner[cof[cof[:, 1] < 0, 0]] = False
+        for _ in range(1):                                   # one more layer: the boundary cells' Green-Gauss gradients are first order
+            edge = ~inner
+            nb = np.zeros(mesh.n_cells, bool)
+            two = cof[:, 1] >= 0
+            nb[cof[two, 0]] |= edge[cof[two, 1]]; nb[cof[two, 1]] |= edge[cof[two, 0]]
+            inner &= ~nb
+        assert np.abs(dv[:, 0]).max() == 0.0                 # no viscous mass flux
+        errs.append(max(np.abs(dv[inner, 1] - mx[inner]).max() / np.abs(mx).max(), np.abs(dv[inner, 2] - my[inner]).max() / np.abs(my).max(),
+                        np.abs(dv[inner, 3] - en[inner]).max() / np.abs(en).max()))
+    assert errs[0] < 0.05 and errs[1] < errs[0] / 3.0, errs
+
+
+def test_zero_viscosity_is_the_inviscid_path_bit_for_bit(oracle_mod):
+    mesh = mb.Mesh.generate("wedge", 14, 8, 4.0, 1.5)
+    U0 = _smooth(mesh.arrays["cell_coords"] / 4.0, np.random.default_rng(4))
+    a = EmulatedSolver(mesh, "FO", "HLLC", "SSPRK3", bcs=SYM4)
+    b = EmulatedSolver(mesh, "FO", "HLLC", "SSPRK3", gas=_gas(0.0), bcs=SYM4)
+    a.set_state(U0); b.set_state(U0)
+    assert np.array_equal(a.calc_rhs(), b.calc_rhs())
