@@ -32,6 +32,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np  # noqa: E402
 
 N_STAGES = 3
+REF_SAMPLE = (160, 160)     # ONE bounded CPU sample for both `cpu_baseline` and `--impl reference`: cartesian_tri 160x160 = 51 200 cells
 ALG_BYTES_STAGE = 7592.0    # TENO p=3 tri, whole stage (reference layout)
 ALG_BYTES_RECON = 7472.0    # of which the reconstruction kernel: A+ 6400, areas 640, ids 320, offsets 20, state 32, geometry 60
 SYM4 = [dict(name=n, type="symmetry") for n in ("left", "right", "top", "bottom")]
@@ -164,7 +165,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="riemann_2d", choices=["riemann_2d", "vortex", "sod", "wedge"],
+    ap.add_argument("--mu", type=float, default=0.0, help="dynamic viscosity (vortex workloads): > 0 adds the Navier-Stokes terms (BASELINE configs[4])")
+    ap.add_argument("--workload", default="riemann_2d", choices=["riemann_2d", "vortex", "vortex_mixed", "sod", "wedge"],
                     help="riemann_2d = BASELINE configs[1] (the metric's configuration); vortex = configs[3] family: isentropic vortex on a "
                          "jittered, id-shuffled triangulation (--nx 2828 --ny 2828 = 16 M cells)")
     ap.add_argument("--nx", type=int, default=1024)
@@ -176,6 +178,8 @@ def main():
                          "split over the GPUs")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling records (16 M / 64 M-cell partitioned vortex mesh) appended to "
                                                               "the default riemann_2d line")
+    ap.add_argument("--ref-full", action="store_true", help="--impl reference only: run the reference on the FULL --nx x --ny mesh instead of the bounded "
+                                                            "sample (1024x1024: ~8 min of serial set-up, ~30 GB) and cache the number in profiles/reference_full_size.json")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
@@ -184,15 +188,24 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = "examples/riemann_2d: cartesian_tri %dx%d, %s+HLLC+SSPRK3, cfl=0.1, four-quadrant IC" % (
         a.nx, a.ny, "TENO(legendre,p=3)" if a.recon == "TENO" else "first-order reconstruction")
-    if a.workload == "vortex":
-        workload = ("synthetic isentropic vortex on a jittered (+-0.15 h, seed 12345), id-shuffled triangulation %dx%d of [0,10]^2, "
-                    "TENO(legendre,p=3)+HLLC+SSPRK3, cfl=0.1, extrapolation BCs" % (a.nx, a.ny))
+    if a.workload in ("vortex", "vortex_mixed"):
+        workload = ("synthetic isentropic vortex on a jittered (+-0.15 h, seed 12345), id-shuffled %s %dx%d of [0,10]^2, "
+                    "TENO(legendre,p=3)+HLLC+SSPRK3, cfl=0.1, extrapolation BCs%s"
+                    % ("triangulation" if a.workload == "vortex" else "mixed triangle / quadrilateral mesh (half the quads cut in two)", a.nx, a.ny,
+                       ", viscous: mu = %g, Pr = 0.72 (BASELINE configs[4])" % a.mu if a.mu > 0 else ""))
 
     if a.impl == "reference":
         if rank != 0:
             return
         steps = max(1, min(a.steps, 50))
-        value, info = reference_cpu(steps, max(1, min(a.warmup, 2)), nx=160, ny=160)
+        nxr, nyr = (a.nx, a.ny) if a.ref_full else REF_SAMPLE
+        value, info = reference_cpu(steps, max(1, min(a.warmup, 2)), nx=nxr, ny=nyr)
+        if a.ref_full:          # the full-size run (serial set-up ~8 min at 1024^2, ~30 GB): cache the number next to the other evidence
+            try:
+                json.dump({"value": value, "unit": "cell-updates/s", "cores": info["cores"], "sample": info["sample"], "ms_per_step": info["ms_per_step"],
+                           "init_seconds": info.get("init_seconds"), "steps": steps}, open(os.path.join(ROOT, "profiles", "reference_full_size.json"), "w"), indent=1)
+            except Exception:
+                pass
         line = {"impl": "reference", "metric": "cell-updates/s per RK stage", "value": value, "unit": "cell-updates/s", "n_gpus": a.gpus,
                 "steps": steps, "warmup": max(1, min(a.warmup, 2)), "ms_per_step": info["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -236,10 +249,10 @@ def main():
             workload = "examples/wedge: wedge 150x50 quads, upt / p_out / symmetry, first order + HLLC + SSPRK3, cfl 1"
         e = p / (0.4 * rho)
         U0, P0 = np.stack([rho, rho * u, 0.0 * rho, rho * (e + 0.5 * u * u)], 1), None
-    elif a.workload == "vortex":
+    elif a.workload in ("vortex", "vortex_mixed"):
         from mallard_b200 import synthetic as syn
         mb.set_host_threads(host_cores())
-        mesh = syn.jittered_tri(a.nx, a.ny, 10.0, 10.0, seed=12345)
+        mesh = syn.jittered_tri(a.nx, a.ny, 10.0, 10.0, seed=12345) if a.workload == "vortex" else syn.mixed_tri_quad(a.nx, a.ny, 10.0, 10.0, seed=12345)
         U0, P0, bcs = syn.isentropic_vortex(mesh.arrays["cell_coords"]), None, syn.EXTRAP4
         a.no_cpu_baseline = True      # the reference cannot read an unstructured mesh (mesh.cpp:41-43); its per-cell cost is mesh independent
     else:
@@ -250,7 +263,9 @@ def main():
         bcs = SYM4
     nc = mesh.n_cells
     mesh_s = time.perf_counter() - t_setup
-    s = mb.Solver(mesh, a.recon, "HLLC", integ, order=3, bcs=bcs, fp_mode=a.fp, keep_stage_rhs=False)
+    gas = dict(mu=a.mu) if (a.mu > 0 and a.workload in ("vortex", "vortex_mixed")) else None
+    s = mb.Solver(mesh, a.recon, "HLLC", integ, order=3, bcs=bcs, fp_mode=a.fp, keep_stage_rhs=False, gas=gas,
+                  teno_fixed=(a.workload == "vortex_mixed" or a.mu > 0))     # viscous / mixed-mesh runs are meant to stay finite
     stats = s.get("stats")
     setup_s = time.perf_counter() - t_setup
     s.set_state(U0, P0)
@@ -326,17 +341,39 @@ def main():
     cpu = None
     if not a.no_cpu_baseline:
         try:
-            v, info = reference_cpu(20, 2, nx=128, ny=128)      # ~8 s of serial reference set-up + ~2 s of steps on the host cores
+            v, info = reference_cpu(20, 2, nx=REF_SAMPLE[0], ny=REF_SAMPLE[1])      # ~12 s of serial reference set-up + a few seconds of steps on the host cores
             cpu = {"value": v, "unit": "cell-updates/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
         except Exception as ex:   # the baseline is reported, never required for the GPU number
             cpu = {"value": None, "unit": "cell-updates/s", "cores": host_cores(), "kind": "unavailable", "sample": str(ex)[:200]}
 
+    graph_replayed = int(s.get("stats")[11])
+    # ---- the timed steps run on data that turns non-finite (reference-faithful weights, as the reference): the same loop on data that
+    #      stays finite (normalised weights) backs the claim that the cost is data independent
+    finite = None
+    if a.workload == "riemann_2d" and a.recon == "TENO" and not a.no_e2e:
+        try:
+            s.close()
+            sf = mb.Solver(mesh, a.recon, "HLLC", integ, order=3, bcs=bcs, fp_mode=a.fp, keep_stage_rhs=False, teno_fixed=True)
+            sf.set_state(U0, P0)
+            sf.run(a.warmup, cfl=cfl)
+            sf.synchronize()
+            sf.event_record(0)
+            sf.run(a.steps, cfl=cfl)
+            sf.event_record(1)
+            msf = sf.event_elapsed_ms(0, 1)
+            Uf = sf.get_state()
+            finite = {"teno_fixed": 1, "value": nc * N_STAGES * a.steps / (msf * 1e-3), "unit": "cell-updates/s", "ms_per_step": msf / a.steps,
+                      "finite_fraction_of_cells_after_the_run": float(np.isfinite(Uf).all(axis=1).mean()),
+                      "note": "normalised TENO weights (SURVEY N2): same kernels, same launches; compare with the line's value"}
+            sf.close()
+        except Exception as ex:
+            finite = {"error": str(ex)[:200]}
+
     # ---- strong-scaling records: this N's point of the 16 M-cell (BASELINE configs[3]) / 64 M-cell partitioned vortex meshes
     strong = None
-    graph_replayed = int(s.get("stats")[11])
     if a.workload == "riemann_2d" and a.recon == "TENO" and not a.no_strong and (a.nx, a.ny) == (1024, 1024):
         import bench_multi
-        s.close()
+        s.close()                                    # (a closed context ignores a second close)
         mb.set_host_threads(host_cores())
         strong = bench_multi.strong_records(a, 0, 1, 0, peak, peak_src)
 
@@ -344,7 +381,7 @@ def main():
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "n_cells": nc, "fp_mode": a.fp, "recon": a.recon, "l2": (("inputs larger than L2 (TENO tables %.1f GB per stage)" if a.recon == "TENO" else "inputs larger than L2 (%.1f GB of state, connectivity and face products per stage)") % (stats[2] / 1e9))
                              if stats[2] > 252e6 else "working set %.1f MB fits in L2: a launch-bound configuration, steps replayed as a CUDA graph" % (stats[2] / 1e6),
-                       "graph_replayed_steps": graph_replayed,
+                       "graph_replayed_steps": graph_replayed, "data_independence": finite,
                        "device_bytes": stats[2], "preprocess_seconds": stats[1], "setup_seconds": setup_s, "mesh_seconds": mesh_s,
                        "preprocess": {"host_total_s": stats[1], "host_stencil_search_s": stats[8], "host_matrices_s": stats[9],
                                       "device_table_build_s": stats[10]},

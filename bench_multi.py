@@ -269,8 +269,9 @@ def run(a, rank, world, local_rank, workload):
         part = np.minimum((xy[:, 0] * (world / Lx)).astype(np.int32), world - 1)  # rank r owns the strip x in [r, r+1) Lx / world
         U0, P0 = bench.riemann2d_state(np.stack([xy[:, 0] / Lx, xy[:, 1]], 1))    # the four-quadrant IC stretched over the strip
         bcs = bench.SYM4
+    visc = dict(gas=dict(mu=a.mu), teno_fixed=True) if (getattr(a, "mu", 0.0) > 0 and a.workload == "vortex") else {}
     ds = DistributedSolver(mesh, part, rank, world, local_rank, local=local, native=NATIVE, recon=a.recon, riemann="HLLC", integrator="SSPRK3",
-                           order=3, bcs=bcs, fp_mode=a.fp, keep_stage_rhs=False)
+                           order=3, bcs=bcs, fp_mode=a.fp, keep_stage_rhs=False, **visc)
     s = ds.s
     stats = s.get("stats")
     n_owned = int(stats[4])

@@ -82,18 +82,27 @@ def mixed_tri_quad(nx, ny, Lx=1.0, Ly=1.0, seed=12345, amp=0.15, tri_fraction=0.
     ic, jc = np.divmod(np.arange(nx * ny, dtype=np.int64), ny)
     bl, br, tl, tr = node(ic, jc), node(ic + 1, jc), node(ic, jc + 1), node(ic + 1, jc + 1)
     kind = np.where(rng.random(nx * ny) < tri_fraction, 1 + (rng.random(nx * ny) < 0.5).astype(np.int64), 0)   # 0 quad, 1 / 2 the two diagonals
-    cells = []
-    for q in range(nx * ny):
-        if kind[q] == 0:
-            cells.append((bl[q], br[q], tr[q], tl[q]))
-        elif kind[q] == 1:
-            cells += [(bl[q], br[q], tr[q]), (bl[q], tr[q], tl[q])]
-        else:
-            cells += [(bl[q], br[q], tl[q]), (br[q], tr[q], tl[q])]
+    # cells in quad order: a quadrilateral (bl, br, tr, tl) or the two triangles of one of its diagonals; then the cell permutation
+    is_quad = kind == 0
+    n_per_quad = np.where(is_quad, 1, 2)
+    first = np.concatenate([[0], np.cumsum(n_per_quad)])[:-1]
+    n_cells = int(n_per_quad.sum())
+    size = np.full(n_cells, 3, dtype=np.int64)
+    size[first[is_quad]] = 4
+    onc = np.concatenate([[0], np.cumsum(size)])
+    noc = np.empty(int(onc[-1]), dtype=np.int64)
+    q4 = first[is_quad]
+    for k, nd in enumerate((bl, br, tr, tl)):
+        noc[onc[q4] + k] = nd[is_quad]
+    d1, d2 = kind == 1, kind == 2
+    for sel, ta, tb in ((d1, (bl, br, tr), (bl, tr, tl)), (d2, (bl, br, tl), (br, tr, tl))):
+        c0 = first[sel]
+        for k in range(3):
+            noc[onc[c0] + k] = ta[k][sel]
+            noc[onc[c0 + 1] + k] = tb[k][sel]
     if shuffle:
-        cells = [cells[i] for i in rng.permutation(len(cells))]
-    onc = np.concatenate([[0], np.cumsum([len(c) for c in cells])])
-    noc = np.fromiter((n for c in cells for n in c), dtype=np.int64)
+        from .local_mesh import _csr_take
+        noc, onc = _csr_take(onc, noc, rng.permutation(n_cells))
     jr, ir = np.arange(ny), np.arange(nx)
     edges = np.concatenate([np.stack([node(0, jr), node(0, jr + 1)], 1), np.stack([node(nx, jr), node(nx, jr + 1)], 1),
                             np.stack([node(ir, ny), node(ir + 1, ny)], 1), np.stack([node(ir, 0), node(ir + 1, 0)], 1)])

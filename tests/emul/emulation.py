@@ -33,7 +33,10 @@ def lib():
         mb.lib()
         L = C.CDLL(SO)
         L.emu_create.restype = C.c_void_p
-        L.emu_create.argtypes = [C.POINTER(_abi.MeshView), C.POINTER(_abi.Numerics), C.POINTER(_abi.Physics), C.POINTER(_abi.Bc), C.c_int]
+        L.emu_create.argtypes = [C.POINTER(_abi.MeshView), C.POINTER(_abi.Numerics), C.POINTER(_abi.Physics), C.POINTER(_abi.Bc), C.c_int, C.c_void_p,
+                                 C.c_int, C.c_int]
+        L.emu_n_owned.argtypes = [C.c_void_p]
+        L.emu_n_held.argtypes = [C.c_void_p]
         L.emu_last_error.restype = C.c_char_p
         for n in ("emu_set_state", "emu_face_values", "emu_rhs", "emu_gradients"):
             getattr(L, n).restype = C.c_int
@@ -49,7 +52,7 @@ class EmulatedSolver:
     """The calc_face_values / calc_rhs surface of mallard_b200.Solver, computed by the emulated kernels (STRICT arithmetic)."""
 
     def __init__(self, mesh, recon="FO", riemann="HLLC", integrator="SSPRK3", gas=None, basis="legendre", order=3, factor=2.0, quad_cell_order=0,
-                 quad_face_order=0, bcs=(), teno_fixed=False, renumber="rcm"):
+                 quad_face_order=0, bcs=(), teno_fixed=False, renumber="rcm", part=None, rank=0, n_ranks=1):
         self.mesh = mesh
         num = mb._numerics(recon, riemann, integrator, basis, order, factor, quad_cell_order, quad_face_order, "strict", renumber, teno_fixed, True)
         phys = mb._physics(gas)
@@ -64,10 +67,13 @@ class EmulatedSolver:
             cb[i].p, cb[i].T = float(b.get("p", 0.0)), float(b.get("T", 0.0))
         v, keep = mesh.view()
         self._keep.append(keep)
-        self._h = lib().emu_create(C.byref(v), C.byref(num), C.byref(phys), cb, len(bcs))
+        pp = None if part is None else np.ascontiguousarray(part, dtype=np.int32)
+        self._keep.append(pp)
+        self._h = lib().emu_create(C.byref(v), C.byref(num), C.byref(phys), cb, len(bcs), None if pp is None else pp.ctypes.data_as(C.c_void_p), rank, n_ranks)
         if not self._h:
             raise RuntimeError(lib().emu_last_error().decode())
         self.n_quad = lib().emu_n_quad(self._h)
+        self.n_owned, self.n_held = lib().emu_n_owned(self._h), lib().emu_n_held(self._h)
 
     def _ok(self, rc):
         if rc:

@@ -124,7 +124,8 @@ extern "C" {
 
 const char * emu_last_error() { return emu_err.c_str(); }
 
-void * emu_create(const mlb_mesh * mesh, const mlb_numerics * num, const mlb_physics * phys, const mlb_bc * bcs, int n_bcs) {
+void * emu_create(const mlb_mesh * mesh, const mlb_numerics * num, const mlb_physics * phys, const mlb_bc * bcs, int n_bcs, const int32_t * part,
+                  int rank, int n_ranks) {
     try {
         std::unique_ptr<Emu> e(new Emu());
         e->num = *num;
@@ -149,6 +150,7 @@ void * emu_create(const mlb_mesh * mesh, const mlb_numerics * num, const mlb_phy
         PrepOptions opt;
         opt.renumber = num->renumber;
         opt.viscous = e->gas.mu > 0.0;
+        opt.part = part; opt.rank = rank; opt.n_ranks = n_ranks;      // a rank's context of a partitioned mesh (ghosts are filled by emu_set_state)
         preprocess(hm, *num, zones, opt, e->P);
         Prep & P = e->P;
         for (size_t i = 0; i < P.qf_x.size(); i++) { e->phys.qf_x[i] = P.qf_x[i]; e->phys.qf_w[i] = P.qf_w[i]; }
@@ -170,6 +172,10 @@ void emu_destroy(void * h) { delete static_cast<Emu *>(h); }
 void emu_force_generic(void * h, int on) { static_cast<Emu *>(h)->force_generic = on; }
 int emu_n_quad(void * h) { return static_cast<Emu *>(h)->P.Q; }
 
+int emu_n_owned(void * h) { return (int)static_cast<Emu *>(h)->P.N_owned; }
+int emu_n_held(void * h) { return (int)static_cast<Emu *>(h)->P.N; }
+
+// every held cell - owned and ghost - takes its state from the global array: what a completed halo exchange leaves behind
 int emu_set_state(void * h, const double * U_ref) {
     Emu & e = *static_cast<Emu *>(h);
     for (uint32_t i = 0; i < e.P.N; i++)

@@ -268,3 +268,37 @@ def test_zero_viscosity_is_the_inviscid_path_bit_for_bit(oracle_mod):
     b = EmulatedSolver(mesh, "FO", "HLLC", "SSPRK3", gas=_gas(0.0), bcs=SYM4)
     a.set_state(U0); b.set_state(U0)
     assert np.array_equal(a.calc_rhs(), b.calc_rhs())
+
+
+@pytest.mark.parametrize("recon,mu,order,mtype", [("FO", 0.0, 3, "wedge"), ("FO", 0.02, 3, "cartesian_tri"), ("TENO", 0.0, 3, "cartesian_tri"),
+                                                  ("TENO", 0.02, 2, "cartesian_tri"), ("TENO", 0.0, 5, "cartesian_tri"), ("TENO", 0.01, 2, "mixed")])
+def test_emulated_rank_contexts_reproduce_the_single_context_residual(recon, mu, order, mtype):
+    """Partitioned contexts (owned cells + the ghost rings the preprocessor decides to hold: one ring for first order, the stencil
+    reach for TENO, one more ring for the least-squares gradients of viscous runs) with every held cell filled as a completed halo
+    exchange leaves it: every rank's residual of its own cells equals the single-context residual bit for bit - specialised and
+    generic kernels, quadrilaterals, viscous terms."""
+    from mallard_b200 import synthetic as syn
+    if mtype == "mixed":
+        mesh = syn.mixed_tri_quad(14, 12, 3.0, 2.0, seed=4, tri_fraction=0.5)
+    else:
+        mesh = mb.Mesh.generate(mtype, 14, 12, 3.0, 2.0)
+    bcs = EXTRAP4 if mtype == "mixed" else SYM4
+    kw = dict(recon=recon, riemann="HLLC", integrator="SSPRK3", bcs=bcs, order=order, quad_cell_order=5 if order >= 5 else 0, teno_fixed=True, gas=_gas(mu))
+    U0 = _smooth(mesh.arrays["cell_coords"] / 3.0, np.random.default_rng(8))
+    one = EmulatedSolver(mesh, **kw)
+    one.set_state(U0)
+    ref = one.calc_rhs()
+    n_ranks = 3
+    part = mb.partition(mesh, n_ranks)
+    got = np.zeros_like(ref)
+    held = []
+    for r in range(n_ranks):
+        e = EmulatedSolver(mesh, part=part, rank=r, n_ranks=n_ranks, **kw)
+        assert e.n_owned == int((part == r).sum()) and e.n_held > e.n_owned
+        held.append(e.n_held - e.n_owned)
+        e.set_state(U0)
+        got += e.calc_rhs()                       # zeros outside the rank's own cells
+    assert np.isfinite(ref).all() and np.array_equal(got, ref)
+    if recon == "FO":
+        inviscid = EmulatedSolver(mesh, part=part, rank=1, n_ranks=n_ranks, **dict(kw, gas=_gas(0.0)))
+        assert (held[1] > inviscid.n_held - inviscid.n_owned) == (mu > 0)      # the second ghost ring exists exactly when it is needed
