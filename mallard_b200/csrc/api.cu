@@ -1408,8 +1408,11 @@ static void rcb(std::vector<std::pair<double, uint32_t>> & key, const double * x
     for (size_t i = lo; i < hi; i++) key[i] = {xy[2 * (size_t)ids[i] + d], ids[i]};     // contiguous keys: the selection stays in cache lines
     std::nth_element(key.begin() + lo, key.begin() + mid, key.begin() + hi);
     for (size_t i = lo; i < hi; i++) ids[i] = key[i].second;
+    // the two halves touch disjoint ranges of key / ids and disjoint cells of part_out: independent tasks
+#pragma omp task shared(key) if (hi - lo > 200000)
     rcb(key, xy, ids, lo, mid, p0, npl, part_out);
     rcb(key, xy, ids, mid, hi, p0 + npl, np - npl, part_out);
+#pragma omp taskwait
 }
 
 int mlb_partition_coords(uint64_t n_cells, const double * cell_xy, int32_t n_parts, int32_t * part_out) {
@@ -1419,6 +1422,8 @@ int mlb_partition_coords(uint64_t n_cells, const double * cell_xy, int32_t n_par
     std::vector<uint32_t> ids(n_cells);
     for (uint64_t i = 0; i < n_cells; i++) ids[i] = (uint32_t)i;
     std::vector<std::pair<double, uint32_t>> key(n_cells);
+#pragma omp parallel
+#pragma omp single
     rcb(key, cell_xy, ids.data(), 0, n_cells, 0, n_parts, part_out);
     API_END(none)
 }
