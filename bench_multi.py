@@ -29,7 +29,7 @@ import numpy as np
 import sys
 import threading
 
-T_START = time.perf_counter()
+T_START = time.perf_counter() - float(os.environ.get("MLB_BENCH_ELAPSED", "0"))      # (a child of bench.py inherits its parent's clock)
 NATIVE = os.environ.get("MLB_BENCH_NATIVE") == "1"
 DEADLINE_S = float(os.environ.get("MLB_BENCH_DEADLINE", "760"))    # the driver kills a run at 870 s
 _STATE = {"line": None, "strong": [], "rank": 0, "done": False}
@@ -210,25 +210,29 @@ def strong_record(name, nq, a, rank, world, device, peak, peak_src):
     return rec
 
 
-def strong_records(a, rank, world, device, peak, peak_src):
+def strong_records(a, rank, world, device, peak, peak_src, on_record=None):
     out = []
+
+    def add(r):
+        out.append(r)
+        _STATE["strong"] = list(out)
+        if on_record is not None:
+            on_record(r)
     for name, nq in STRONG_MESHES:
         nc = 2 * nq * nq
         if nc / world > MAX_CELLS_PER_GPU:
-            out.append({"workload": name, "n_cells": nc, "skipped": "%.1f M cells per GPU do not fit 180 GB" % (nc / world / 1e6)})
+            add({"workload": name, "n_cells": nc, "skipped": "%.1f M cells per GPU do not fit 180 GB" % (nc / world / 1e6)})
             continue
         elapsed = float(_reduce([time.perf_counter() - T_START], world, "max")[0])
         if elapsed > TIME_BUDGET_S:
-            out.append({"workload": name, "n_cells": nc, "skipped": "time budget of the bench run (%.0f s elapsed)" % elapsed})
+            add({"workload": name, "n_cells": nc, "skipped": "time budget of the bench run (%.0f s elapsed)" % elapsed})
             continue
         try:
-            out.append(strong_record(name, nq, a, rank, world, device, peak, peak_src))
+            add(strong_record(name, nq, a, rank, world, device, peak, peak_src))
         except Exception as ex:      # a strong record never costs the main line
-            out.append({"workload": name, "n_cells": nc, "error": str(ex)[:300]})
+            add({"workload": name, "n_cells": nc, "error": str(ex)[:300]})
             if world > 1:            # the ranks may have diverged: nothing collective can follow
-                _STATE["strong"] = out
                 break
-        _STATE["strong"] = out
     return out
 
 
@@ -246,7 +250,10 @@ def run(a, rank, world, local_rank, workload):
     # host preprocessing is OpenMP-parallel inside every rank: share the cores instead of oversubscribing them
     # (torchrun presets OMP_NUM_THREADS=1, which would serialise the TENO table construction)
     mb.set_host_threads(max(1, min(total_cores // world, bench.host_cores())))
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # (collective timeout above this file's own deadline: a rank left waiting by a failed strong record leaves through the watchdog
+    #  with exit code 0, not through torch's NCCL watchdog with SIGABRT)
+    import datetime
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=1800))
     peak, peak_src = bench.hbm_peak()
 
     t_setup = time.perf_counter()
@@ -340,6 +347,8 @@ def run(a, rank, world, local_rank, workload):
     if rank == 0:
         line["strong"] = strong_recs
         print(json.dumps(line), flush=True)
+    # the line is out: nothing below may keep the job alive (a peer that failed inside a strong record never reaches the barrier)
+    threading.Thread(target=lambda: (time.sleep(30.0), os._exit(0)), daemon=True).start()
     try:
         dist.barrier()
         dist.destroy_process_group()

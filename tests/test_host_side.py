@@ -269,6 +269,37 @@ def test_bench_reference_arm_line_and_no_gpu_failure():
         assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
 
 
+def test_bench_strong_records_cannot_cost_the_main_line(monkeypatch):
+    """At N = 1 the strong-scaling records (16 M cells, ~100 GB of device memory) run in a child process under a deadline: records
+    finished before a crash or a hang are kept, the failure is reported as a record, and the parent always returns."""
+    import json
+    import subprocess
+    import sys
+    import types
+    sys.path.insert(0, ROOT) if ROOT not in sys.path else None
+    import bench
+    a = types.SimpleNamespace(steps=2, warmup=1, fp="fast")
+
+    def child(script):
+        return lambda cmd, **kw: subprocess.Popen([sys.executable, "-c", script], **kw)
+    rec = bench.STRONG_TAG + json.dumps({"workload": "w", "value": 1.0})
+    monkeypatch.setenv("MLB_BENCH_DEADLINE", "100000")
+    ok = bench.strong_records_in_child(a, popen=child("print('noise'); print(%r); print(%r)" % (rec, rec)))
+    assert ok == [{"workload": "w", "value": 1.0}] * 2
+    crash = bench.strong_records_in_child(a, popen=child("import os; print(%r, flush=True); os._exit(9)" % rec))
+    assert crash[0]["value"] == 1.0 and "code 9" in crash[1]["error"]
+    monkeypatch.setenv("MLB_BENCH_DEADLINE", "%f" % (time_since_bench_import(bench) + 3.0))
+    hang = bench.strong_records_in_child(a, popen=child("import time; print(%r, flush=True); time.sleep(600)" % rec), min_left=0.0)
+    assert hang[0]["value"] == 1.0 and "deadline" in hang[1]["aborted"]
+    monkeypatch.setenv("MLB_BENCH_DEADLINE", "1")
+    assert "time budget" in bench.strong_records_in_child(a)[0]["skipped"]
+
+
+def time_since_bench_import(bench):
+    import time
+    return time.perf_counter() - bench.T_START
+
+
 def test_degenerate_meshes_are_handled_on_the_host():
     """Edge cases: a one-cell mesh (empty interior zone, every face on a boundary), and TENO on meshes that cannot fill a
     stencil of M cells or that contain quadrilaterals (the reference throws for both)."""
