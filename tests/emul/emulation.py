@@ -11,27 +11,39 @@ from mallard_b200 import _abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SO = os.path.join(HERE, "libkernel_emulation.so")
-_LIB = None
+SO = {"strict": os.path.join(HERE, "libkernel_emulation.so"), "fast": os.path.join(HERE, "libkernel_emulation_fast.so")}
+# STRICT: the source as kernels_strict.cu compiles it, no contraction.  FAST: as kernels_fast.cu compiles it (MLB_STREAM_KERNELS: lean
+# Riemann flux, reciprocals, monomials by multiplication) with the host compiler contracting a * b + c to FMA - not nvcc's choice of
+# contractions instruction by instruction, but the same class of re-rounding: what it checks is that the FAST-mode tolerances of the
+# tests hold for kernels that have not run on hardware yet.
+FLAGS = {"strict": ["-ffp-contract=off"], "fast": ["-DMLB_STREAM_KERNELS=1", "-ffp-contract=fast", "-mfma"]}
+_LIB = {}
 
 
-def build():
+def fast_available():
+    try:
+        return " fma " in open("/proc/cpuinfo").read().replace("\n", " ")
+    except OSError:
+        return False
+
+
+def build(variant="strict"):
     src = os.path.join(HERE, "kernel_emulation.cpp")
     deps = [src] + [os.path.join(ROOT, "mallard_b200", "csrc", f) for f in ("kernels_impl.cuh", "teno_generic.cuh", "kernel_args.h", "mlb_internal.h")]
     deps.append(os.path.join(ROOT, "mallard_b200", "libmallard_b200.so"))
-    if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
+    so = SO[variant]
+    if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
         return
     mb.build()
-    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(ROOT, "mallard_b200", "csrc"),
-                           src, "-L", os.path.join(ROOT, "mallard_b200"), "-lmallard_b200", "-Wl,-rpath," + os.path.join(ROOT, "mallard_b200"), "-o", SO])
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2"] + FLAGS[variant] + ["-fPIC", "-shared", "-I", os.path.join(ROOT, "mallard_b200", "csrc"),
+                           src, "-L", os.path.join(ROOT, "mallard_b200"), "-lmallard_b200", "-Wl,-rpath," + os.path.join(ROOT, "mallard_b200"), "-o", so])
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        build()
+def lib(variant="strict"):
+    if variant not in _LIB:
+        build(variant)
         mb.lib()
-        L = C.CDLL(SO)
+        L = C.CDLL(SO[variant])
         L.emu_create.restype = C.c_void_p
         L.emu_create.argtypes = [C.POINTER(_abi.MeshView), C.POINTER(_abi.Numerics), C.POINTER(_abi.Physics), C.POINTER(_abi.Bc), C.c_int, C.c_void_p,
                                  C.c_int, C.c_int]
@@ -44,16 +56,17 @@ def lib():
         L.emu_destroy.argtypes = [C.c_void_p]
         L.emu_force_generic.argtypes = [C.c_void_p, C.c_int]
         L.emu_n_quad.argtypes = [C.c_void_p]
-        _LIB = L
-    return _LIB
+        _LIB[variant] = L
+    return _LIB[variant]
 
 
 class EmulatedSolver:
-    """The calc_face_values / calc_rhs surface of mallard_b200.Solver, computed by the emulated kernels (STRICT arithmetic)."""
+    """The calc_face_values / calc_rhs surface of mallard_b200.Solver, computed by the emulated kernels (fp_mode: see FLAGS)."""
 
     def __init__(self, mesh, recon="FO", riemann="HLLC", integrator="SSPRK3", gas=None, basis="legendre", order=3, factor=2.0, quad_cell_order=0,
-                 quad_face_order=0, bcs=(), teno_fixed=False, renumber="rcm", part=None, rank=0, n_ranks=1):
+                 quad_face_order=0, bcs=(), teno_fixed=False, renumber="rcm", part=None, rank=0, n_ranks=1, fp_mode="strict"):
         self.mesh = mesh
+        self._L = lib(fp_mode)
         num = mb._numerics(recon, riemann, integrator, basis, order, factor, quad_cell_order, quad_face_order, "strict", renumber, teno_fixed, True)
         phys = mb._physics(gas)
         self._keep = []
@@ -69,42 +82,42 @@ class EmulatedSolver:
         self._keep.append(keep)
         pp = None if part is None else np.ascontiguousarray(part, dtype=np.int32)
         self._keep.append(pp)
-        self._h = lib().emu_create(C.byref(v), C.byref(num), C.byref(phys), cb, len(bcs), None if pp is None else pp.ctypes.data_as(C.c_void_p), rank, n_ranks)
+        self._h = self._L.emu_create(C.byref(v), C.byref(num), C.byref(phys), cb, len(bcs), None if pp is None else pp.ctypes.data_as(C.c_void_p), rank, n_ranks)
         if not self._h:
-            raise RuntimeError(lib().emu_last_error().decode())
-        self.n_quad = lib().emu_n_quad(self._h)
-        self.n_owned, self.n_held = lib().emu_n_owned(self._h), lib().emu_n_held(self._h)
+            raise RuntimeError(self._L.emu_last_error().decode())
+        self.n_quad = self._L.emu_n_quad(self._h)
+        self.n_owned, self.n_held = self._L.emu_n_owned(self._h), self._L.emu_n_held(self._h)
 
     def _ok(self, rc):
         if rc:
-            raise RuntimeError(lib().emu_last_error().decode())
+            raise RuntimeError(self._L.emu_last_error().decode())
 
     def force_generic(self, on=True):
-        lib().emu_force_generic(self._h, int(on))
+        self._L.emu_force_generic(self._h, int(on))
 
     def set_state(self, U):
         U = np.ascontiguousarray(U, dtype=np.float64)
         assert U.shape == (self.mesh.n_cells, 4)
-        self._ok(lib().emu_set_state(self._h, U.ctypes.data_as(C.c_void_p)))
+        self._ok(self._L.emu_set_state(self._h, U.ctypes.data_as(C.c_void_p)))
 
     def calc_face_values(self):
         F = np.empty((self.mesh.n_faces, self.n_quad, 2, 4))
-        self._ok(lib().emu_face_values(self._h, F.ctypes.data_as(C.c_void_p)))
+        self._ok(self._L.emu_face_values(self._h, F.ctypes.data_as(C.c_void_p)))
         return F
 
     def calc_rhs(self):
         r = np.zeros((self.mesh.n_cells, 4))
-        self._ok(lib().emu_rhs(self._h, r.ctypes.data_as(C.c_void_p)))
+        self._ok(self._L.emu_rhs(self._h, r.ctypes.data_as(C.c_void_p)))
         return r
 
     def gradients(self):
         G = np.zeros((self.mesh.n_cells, 6))
-        self._ok(lib().emu_gradients(self._h, G.ctypes.data_as(C.c_void_p)))
+        self._ok(self._L.emu_gradients(self._h, G.ctypes.data_as(C.c_void_p)))
         return G
 
     def close(self):
         if self._h:
-            lib().emu_destroy(self._h)
+            self._L.emu_destroy(self._h)
             self._h = None
 
     def __del__(self):

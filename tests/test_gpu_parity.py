@@ -747,7 +747,11 @@ def test_viscous_residual_of_couette_flow(mtype, fp):
     scale = np.abs(res[1]).max() + 1.0
     assert np.abs(dv[:, :3]).max() < 1e-11 * scale + 1e-9 and np.abs(dv[:, 3] - heat).max() < 1e-11 * scale + 1e-8 * heat
     if mtype == "cartesian":
-        assert np.abs(res[0][:, :3]).max() < 1e-7 and np.abs(res[0][:, 3] - heat).max() < 1e-8 * heat + 1e-9
+        # STRICT: the inviscid fluxes through opposite faces cancel exactly; FAST re-rounds them (FMA, reciprocals): what is left is a few ulp
+        # of the energy flux per cell height, (rho E + p) U / dy ~ 1e7 here
+        flux = (np.abs(U0[:, 3]).max() + 1.2 * R_GAS * 300.0) * Uw / (H / 20)
+        slack = 0.0 if fp == "strict" else 1e-13 * flux
+        assert np.abs(res[0][:, :3]).max() < 1e-7 + slack and np.abs(res[0][:, 3] - heat).max() < 1e-8 * heat + 1e-9 + slack
 
 
 @UNVERIFIED_ON_HARDWARE

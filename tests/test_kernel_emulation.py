@@ -302,3 +302,128 @@ def test_emulated_rank_contexts_reproduce_the_single_context_residual(recon, mu,
     if recon == "FO":
         inviscid = EmulatedSolver(mesh, part=part, rank=1, n_ranks=n_ranks, **dict(kw, gas=_gas(0.0)))
         assert (held[1] > inviscid.n_held - inviscid.n_owned) == (mu > 0)      # the second ghost ring exists exactly when it is needed
+
+
+# ---- FAST floating-point mode of the same kernels (MLB_STREAM_KERNELS source + FMA contraction by the host compiler, see
+#      tests/emul/emulation.py: FLAGS): the tolerances the gated GPU tests (tests/test_gpu_parity.py, fp = "fast") assert -------------
+from emulation import fast_available  # noqa: E402
+
+FAST_EMULATION = pytest.mark.skipif(not fast_available(), reason="this host has no FMA unit: the FAST emulation cannot be built")
+TOL = 1e-12
+
+
+@FAST_EMULATION
+@pytest.mark.parametrize("order,factor,qc,basis,fixed", [(3, 2.0, 0, "legendre", False), (3, 2.0, 0, "monomial", True), (5, 2.0, 5, "legendre", True),
+                                                         (7, 2.0, 5, "monomial", True), (2, 1.5, 0, "legendre", False), (4, 2.5, 0, "legendre", True)])
+def test_fast_emulation_stays_inside_the_tolerance_of_the_gpu_tests(oracle_mod, order, factor, qc, basis, fixed):
+    """FAST against the oracle on the field scale: 1e-12 up to p = 5, 1e-9 above (conditioning of the pseudo-inverse rows), face values
+    and residual - specialised kernel where one exists, generic kernel otherwise and when forced."""
+    nx, ny = (12, 10) if order >= 7 else (14, 12)
+    om = oracle_mod.Mesh.generate("cartesian_tri", nx, ny, 2.0, 1.0)
+    mesh = mb.Mesh.generate("cartesian_tri", nx, ny, 2.0, 1.0)
+    kw = dict(recon="TENO", riemann="HLLC", integrator="SSPRK3", bcs=SYM4, basis=basis, order=order, factor=factor, quad_cell_order=qc, teno_fixed=fixed)
+    so, sf = oracle_mod.Solver(om, **kw), EmulatedSolver(mesh, fp_mode="fast", **kw)
+    U0 = _smooth(mesh.arrays["cell_coords"], np.random.default_rng(23))
+    so.set_state(U0); sf.set_state(U0)
+    real = gu.real_faces(mesh.arrays["cells_of_face"], mesh.arrays["nodes_of_face"])
+    Fo, ro = so.calc_face_values()[real][:, :, 0], so.calc_rhs()
+    tol = TOL if order <= 5 else 1e-9
+    for generic in (False, True):
+        sf.force_generic(generic)
+        Ff, rf = sf.calc_face_values()[real][:, :, 0], sf.calc_rhs()
+        assert np.array_equal(np.isfinite(Ff), np.isfinite(Fo)) and np.array_equal(np.isfinite(rf), np.isfinite(ro))
+        assert gu.field_err(Ff, Fo) <= tol and gu.field_err(rf, ro) <= tol, (generic, gu.field_err(Ff, Fo), gu.field_err(rf, ro))
+        assert not np.array_equal(rf, ro) or order == 0          # (it IS a different rounding: the check is not vacuous)
+
+
+@FAST_EMULATION
+@pytest.mark.parametrize("order,tri_fraction", [(2, 0.5), (3, 0.0), (4, 0.6)])
+def test_fast_emulation_on_mixed_meshes_is_k_exact(order, tri_fraction):
+    from mallard_b200 import synthetic as syn
+    mesh = syn.mixed_tri_quad(12, 10, 3.0, 2.0, seed=3, tri_fraction=tri_fraction)
+    coef = np.random.default_rng(17).uniform(-1.0, 1.0, size=(4, order + 1, order + 1))
+
+    def f(x, y):
+        out = np.zeros(x.shape + (4,))
+        for v in range(4):
+            for i in range(order + 1):
+                for j in range(order + 1 - i):
+                    out[..., v] += coef[v, i, j] * x ** i * y ** j
+        out[..., 0] += 5.0
+        return out
+    U0 = _cell_averages(mesh, f)
+    F = {}
+    for fp in ("strict", "fast"):
+        se = EmulatedSolver(mesh, "TENO", "HLLC", "SSPRK3", order=order, bcs=EXTRAP4, teno_fixed=True, fp_mode=fp)
+        se.set_state(U0)
+        F[fp] = se.calc_face_values()
+        n_quad = se.n_quad
+    A = mesh.arrays
+    nof, cof = A["nodes_of_face"].reshape(-1, 2).astype(np.int64), A["cells_of_face"]
+    xi = {1: [0.0], 2: [-0.5773502691896257, 0.5773502691896257], 3: [-0.7745966692414834, 0.0, 0.7745966692414834]}[n_quad]
+    x0, x1 = A["node_coords"][nof[:, 0]], A["node_coords"][nof[:, 1]]
+    worst = 0.0
+    for q, z in enumerate(xi):
+        pq = (z + 1.0) * 0.5 * (x1 - x0) + x0
+        exact = f(pq[:, 0], pq[:, 1])
+        worst = max(worst, np.abs(F["fast"][:, q, 0] - exact).max(), np.abs(F["fast"][cof[:, 1] >= 0][:, q, 1] - exact[cof[:, 1] >= 0]).max())
+    assert worst <= 2e-9 * (10.0 ** max(0, order - 3)), worst
+    assert gu.field_err(F["fast"], F["strict"]) <= 1e-10 and not np.array_equal(F["fast"], F["strict"])
+
+
+@FAST_EMULATION
+@pytest.mark.parametrize("mtype", ["cartesian", "cartesian_tri", "mixed"])
+def test_fast_emulation_of_the_viscous_couette_residual(mtype):
+    """The assertion of tests/test_gpu_parity.py::test_viscous_residual_of_couette_flow[*-fast] with the FAST source."""
+    from mallard_b200 import synthetic as syn
+    mu, Uw, H, L = 0.05, 3.0, 1.0, 2.0
+    mesh = syn.mixed_tri_quad(24, 20, L, H, seed=5, tri_fraction=0.5) if mtype == "mixed" else mb.Mesh.generate(mtype, 24, 20, L, H)
+    bcs = [dict(name="left", type="extrapolation"), dict(name="right", type="extrapolation"), dict(name="bottom", type="wall_noslip", u=[0.0, 0.0]),
+           dict(name="top", type="wall_noslip", u=[Uw, 0.0])]
+    xy, n = mesh.arrays["cell_coords"], mesh.n_cells
+    U0 = _state_from_prim(np.full(n, 1.2), Uw * xy[:, 1] / H, np.zeros(n), np.full(n, 300.0), R_GAS)
+    res = []
+    for m in (mu, 0.0):
+        se = EmulatedSolver(mesh, "FO", "HLLC", "SSPRK3", gas=_gas(m), bcs=bcs, fp_mode="fast")
+        se.set_state(U0)
+        res.append(se.calc_rhs())
+    heat, dv = mu * (Uw / H) ** 2, res[0] - res[1]
+    scale = np.abs(res[1]).max() + 1.0
+    assert np.abs(dv[:, :3]).max() < 1e-11 * scale + 1e-9 and np.abs(dv[:, 3] - heat).max() < 1e-11 * scale + 1e-8 * heat
+    if mtype == "cartesian":
+        # STRICT: the inviscid fluxes through opposite faces cancel exactly; FAST re-rounds them (FMA, reciprocals): what is left is a few ulp
+        # of the energy flux per cell height, (rho E + p) U / dy ~ 1e7 here
+        flux = (np.abs(U0[:, 3]).max() + 1.2 * R_GAS * 300.0) * Uw / (H / 20)
+        slack = 1e-13 * flux
+        assert np.abs(res[0][:, :3]).max() < 1e-7 + slack and np.abs(res[0][:, 3] - heat).max() < 1e-8 * heat + 1e-9 + slack
+
+
+def test_emulated_decaying_shear_layer_follows_the_diffusion_equation():
+    """tests/test_gpu_parity.py::test_decaying_shear_layer_follows_the_diffusion_equation with the emulated kernels and SSPRK3 in numpy
+    (fixed dt below the acoustic limit): u(y, t) = U erf(y / sqrt(delta0^2 + 4 nu t)); the thresholds of the GPU test hold and the
+    error falls by ~4 when the mesh is refined by 2 (measured: 7.6e-3 -> 1.8e-3)."""
+    from math import erf
+    nu, Uw, d0, T0, rho0 = 0.02, 1.0, 0.08, 300.0, 1.0
+    errs = []
+    for ny in (40, 80):
+        mesh = mb.Mesh.generate("cartesian", 4, ny, 0.1, 2.0)
+        y = mesh.arrays["cell_coords"][:, 1] - 1.0
+        bcs = [dict(name="left", type="extrapolation"), dict(name="right", type="extrapolation"), dict(name="bottom", type="symmetry"),
+               dict(name="top", type="symmetry")]
+        s = EmulatedSolver(mesh, "FO", "HLLC", "SSPRK3", gas=_gas(nu * rho0), bcs=bcs, fp_mode="fast" if fast_available() else "strict")
+        n = mesh.n_cells
+        U = _state_from_prim(np.full(n, rho0), Uw * np.vectorize(erf)(y / d0), np.zeros(n), np.full(n, T0), R_GAS)
+        dt, t = 3.0e-5, 0.0                                  # acoustic limit h / (c + U) = 7e-5 on both meshes (h = 0.025), viscous limit far above
+
+        def rhs(V):
+            s.set_state(V)
+            return s.calc_rhs()
+        while t < 0.2:
+            U1 = U + dt * rhs(U)
+            U2 = 0.75 * U + 0.25 * (U1 + dt * rhs(U1))
+            U = U / 3.0 + (2.0 / 3.0) * (U2 + dt * rhs(U2))
+            t += dt
+        assert np.isfinite(U).all()
+        exact = Uw * np.vectorize(erf)(y / np.sqrt(d0 * d0 + 4.0 * nu * t))
+        errs.append(np.abs(U[:, 1] / U[:, 0] - exact).max())
+    assert errs[0] < 0.02 and errs[1] < errs[0] / 2.5, errs
