@@ -627,6 +627,12 @@ void halo_unpack(mlb_ctx & c, int buf, bool first_stage) {
 }
 
 // ---- native multi-GPU driver: NCCL over NVLink, no host code between the stages of a step -----------------------------------
+// MLB_COMM_TRACE=1: one stderr line per phase of the collective set-up and of the first steps (which rank stopped where, should a
+// run not come back: the 8-GPU hang of profiles/r02d_8gpu_native_hang.txt left no trace of its own)
+void comm_trace(const mlb_ctx & c, const char * what) {
+    static const bool on = [] { const char * e = getenv("MLB_COMM_TRACE"); return e && e[0] == '1'; }();
+    if (on) { fprintf(stderr, "[mlb comm] rank %d/%d: %s\n", c.rank, c.n_ranks, what); fflush(stderr); }
+}
 void require_comm(const mlb_ctx & c) {
     if (!c.nccl_p2p) throw std::runtime_error("the context has no communicator: call mlb_comm_init first");
 }
@@ -676,9 +682,11 @@ void exchange_halo_plan(mlb_ctx & c) {
     std::vector<uint64_t> want((size_t)n, 0), all((size_t)n * n, 0);
     for (size_t i = 0; i < c.peers.size(); i++) want[c.peers[i]] = c.recv_counts[i];
     uint64_t * d_want = dev_upload(want, c.stream), * d_all = dev_alloc<uint64_t>((size_t)n * n);
+    comm_trace(c, "halo plan: all-gather of the count matrix");
     NCCL_OK(N.AllGather(d_want, d_all, (size_t)n, ncclUint64, c.nccl_coll, c.stream));
     CUDA_OK(cudaMemcpyAsync(all.data(), d_all, all.size() * 8, cudaMemcpyDeviceToHost, c.stream));
     CUDA_OK(cudaStreamSynchronize(c.stream));
+    comm_trace(c, "halo plan: count matrix received, exchanging the id lists");
     std::vector<uint32_t> out_ids;
     for (size_t i = 0; i < c.peers.size(); i++)
         for (uint32_t id : c.recv_ref_ids[i]) out_ids.push_back(to_global(c, id));
@@ -706,6 +714,7 @@ void exchange_halo_plan(mlb_ctx & c) {
     if (n_in) CUDA_OK(cudaMemcpyAsync(in_ids.data(), d_in, n_in * 4, cudaMemcpyDeviceToHost, c.stream));
     CUDA_OK(cudaStreamSynchronize(c.stream));
     cudaFree(d_want); cudaFree(d_all); cudaFree(d_out); cudaFree(d_in);
+    comm_trace(c, "halo plan: id lists received");
     set_send_ids(c, (int32_t)from.size(), from.data(), counts.data(), in_ids.data());
 }
 
@@ -1321,9 +1330,12 @@ int mlb_comm_init(mlb_ctx * c, const void * id) {
     const NcclApi & N = nccl();
     ncclUniqueId uid;
     std::memcpy(&uid, id, sizeof(uid));
+    comm_trace(*c, "ncclCommInitRank");
     NCCL_OK(N.CommInitRank(&c->nccl_p2p, c->n_ranks, uid, c->rank));
+    comm_trace(*c, "ncclCommSplit (communicator of the dt all-reduce)");
     NCCL_OK(N.CommSplit(c->nccl_p2p, 0, c->rank, &c->nccl_coll, nullptr));
     exchange_halo_plan(*c);
+    comm_trace(*c, "communicators and halo plan ready");
     API_END(c)
 }
 
@@ -1337,16 +1349,19 @@ int mlb_run_distributed(mlb_ctx * c, uint32_t n_steps, double cfl, double * t_ou
     static const bool graphs = [] { const char * e = getenv("MLB_RUN_GRAPH"); return !(e && e[0] == '0'); }();
     uint32_t done = 0;
     if (graphs && !c->profiling && n_steps >= 4 && c->num.integrator != MLB_INTEGRATOR_FE) {
+        comm_trace(*c, "run: eager step");
         do_step_distributed(*c, cfl);
         done = 1;
         const uint64_t l0 = c->launches;
         cudaGraph_t g = nullptr;
         cudaGraphExec_t ge = nullptr;
+        comm_trace(*c, "run: capturing a step");
         CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
         bool ok = true;
         std::string why;
         try { do_step_distributed(*c, cfl); } catch (const std::exception & e) { ok = false; why = e.what(); }
         const cudaError_t ec = cudaStreamEndCapture(c->stream, &g);
+        comm_trace(*c, "run: step captured, replaying");
         const uint64_t per_step = c->launches - l0;
         c->launches = l0;                             // nothing ran during the capture
         if (ok && ec == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) {
@@ -1365,9 +1380,11 @@ int mlb_run_distributed(mlb_ctx * c, uint32_t n_steps, double cfl, double * t_ou
         if (g) cudaGraphDestroy(g);
     }
     for (; done < n_steps; done++) do_step_distributed(*c, cfl);
+    comm_trace(*c, "run: all steps enqueued, waiting for the device");
     if (c->comm_stream) CUDA_OK(cudaStreamSynchronize(c->comm_stream));
     double sc[SC_COUNT];
     read_scalars(*c, sc);
+    comm_trace(*c, "run: done");
     if (t_out) *t_out = sc[SC_T];
     if (dt_last_out) *dt_last_out = sc[SC_DT];
     if (sc[SC_DT] < 0.0) throw std::runtime_error("dt negative: " + std::to_string(sc[SC_DT]) + ".");
