@@ -101,6 +101,14 @@ CASES = {
                                      riemann="HLLC", integrator="SSPRK3",
                                      recon=dict(type="TENO", basis_type="legendre", basis_order=2, max_stencil_size_factor=1.5),
                                      n_steps=1, every=1, keep_mesh=False, keep_teno=True),
+    # TENO face states through every boundary functor (upt, p_out, wall_adiabatic, symmetry: boundary/*.cpp) and through RK4's four
+    # stages; TENO + HLL on the four-quadrant data (non-finite pattern of the HLL flux)
+    "teno_bcs_rk4_10x8": dict(mesh=dict(type="cartesian_tri", Nx=10, Ny=8, Lx=1.0, Ly=0.8), ic=SMOOTH_IC,
+                              bcs=[dict(name="left", type="upt", u=[0.5, 0.3], p=1.0, T=0.0036), dict(name="right", type="p_out", p=0.95),
+                                   dict(name="top", type="symmetry"), dict(name="bottom", type="wall_adiabatic")],
+                              cfl=0.1, riemann="HLLC", integrator="RK4", recon=TENO3, n_steps=1, every=1, keep_mesh=False, keep_teno=False),
+    "teno_hll_riemann_9x7": dict(mesh=dict(type="cartesian_tri", Nx=9, Ny=7, Lx=1.0, Ly=0.8), ic=RIEMANN2D_IC, bcs=EXTRAP4, cfl=0.1,
+                                 riemann="HLL", integrator="SSPRK3", recon=TENO3, n_steps=1, every=1, keep_mesh=False, keep_teno=False),
     "teno_monomial_9x8_p2": dict(mesh=dict(type="cartesian_tri", Nx=9, Ny=8, Lx=1.2, Ly=1.0), ic=SMOOTH_IC, bcs=EXTRAP4, cfl=0.1,
                                  riemann="HLL", integrator="RK4",
                                  recon=dict(type="TENO", basis_type="monomial", basis_order=2, max_stencil_size_factor=2.0),

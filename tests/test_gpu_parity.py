@@ -113,6 +113,9 @@ BIT_EXACT_STRICT = {"sod_rusanov_fe", "wedge_30x10", "wedge_wall_30x10"}   # no 
 
 
 GENERIC_KERNEL_FIXTURES = {"teno_legendre_12x10_p5", "teno_legendre_8x7_p2_f15"}     # served by csrc/teno_generic.cuh
+# reference dumps added after the round-2 GPU budget ran out (TENO through upt / p_out / wall boundaries + RK4; TENO + HLL on the four-quadrant
+# data): the kernels they exercise HAVE run on a B200, these comparisons have not - gated like the rest (tests/test_gpu_hardware_trial.py)
+LATE_FIXTURES = {"teno_bcs_rk4_10x8", "teno_hll_riemann_9x7"}
 
 
 @pytest.mark.parametrize("fp", ["strict", "fast"])
@@ -120,6 +123,8 @@ GENERIC_KERNEL_FIXTURES = {"teno_legendre_12x10_p5", "teno_legendre_8x7_p2_f15"}
 def test_against_reference_dumps(name, fp):
     if name in GENERIC_KERNEL_FIXTURES and os.environ.get("MLB_RUN_UNVERIFIED") != "1":
         pytest.skip("generic TENO kernel: written after the round-2 GPU budget ran out, not yet run on a B200 (set MLB_RUN_UNVERIFIED=1)")
+    if name in LATE_FIXTURES and os.environ.get("MLB_RUN_UNVERIFIED") != "1":
+        pytest.skip("fixture added after the round-2 GPU budget ran out: comparison not yet run on a B200 (set MLB_RUN_UNVERIFIED=1)")
     meta, g = gu.load(name)
     mm = meta["mesh"]
     mesh = mb.Mesh.generate(mm["type"], mm["Nx"], mm["Ny"], mm["Lx"], mm["Ly"])

@@ -75,7 +75,8 @@ def test_emulated_generic_kernel_orders_5_to_9_and_other_stencil_factors_vs_orac
     assert np.array_equal(se.calc_rhs(), so.calc_rhs(), equal_nan=True)
 
 
-@pytest.mark.parametrize("name", ["teno_legendre_12x10_p5", "teno_legendre_8x7_p2_f15", "teno_smooth_6x6", "teno_monomial_7x6_p3"])
+@pytest.mark.parametrize("name", ["teno_legendre_12x10_p5", "teno_legendre_8x7_p2_f15", "teno_smooth_6x6", "teno_monomial_7x6_p3",
+                                  "teno_bcs_rk4_10x8", "teno_hll_riemann_9x7"])
 def test_emulated_kernels_against_dumps_of_the_unmodified_reference(name):
     meta, g = gu.load(name)
     mm = meta["mesh"]
