@@ -195,19 +195,53 @@ def strong_record(name, nq, a, rank, world, device, peak, peak_src):
     mem = _reduce([resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1048576.0, stats[2] / 1e9, float(lp.mesh.n_cells), setup_s, stats[1], lp.seconds], world, "max")
     rec.update(host_rss_gb_per_rank_max=float(mem[0]), device_gb_per_rank_max=float(mem[1]), local_mesh_cells_max=int(mem[2]), ghost_layers=layers,
                setup_seconds=float(mem[3]), preprocess_seconds=float(mem[4]), mesh_seconds=float(mem[5]), graph_replayed_steps=int(s.get("stats")[11]))
-    # efficiency against this mesh's own 1-GPU run: measured in the same job when N == 1, else taken from the committed N=1 line
-    base = None
+    s.close()
+    if rank == 0:
+        strong_efficiency(rec, name, world)
+    return rec
+
+
+LIVE_BASELINES = os.environ.get("MLB_STRONG_BASELINES", "/tmp/mlb_strong_baselines.json")
+
+
+def strong_efficiency(rec, name, world, live_path=None, max_age_s=6 * 3600.0):
+    """Strong-scaling efficiency of a record = value_N / (N / N0 x value_N0), N0 the smallest GPU count this mesh has been measured
+    on (1 where the mesh fits one GPU; the 64 M-cell mesh starts at 4).  The base point is the one measured ON THIS BOX by an earlier
+    bench.py run of the same series (the driver's scaling run goes N = 1, 2, 4, 8 on one lease: every run leaves its records in
+    LIVE_BASELINES) - same clocks, same host - and only failing that the committed number of an earlier round (profiles/
+    r02_strong_baselines.json, which says where it comes from)."""
+    import bench
+    live_path = live_path or LIVE_BASELINES
+    live = {}
     try:
-        base = json.load(open(os.path.join(bench.ROOT, "profiles", "r02_strong_baselines.json"))).get(name)
+        if time.time() - os.path.getmtime(live_path) < max_age_s:
+            live = json.load(open(live_path))
+    except Exception:
+        live = {}
+    base, src = live.get(name), "measured on this box by the N = %d run of the same series"
+    if not (base and base.get("n_gpus", 0) < world):
+        base, src = None, "profiles/r02_strong_baselines.json (%s)"
+        try:
+            base = json.load(open(os.path.join(bench.ROOT, "profiles", "r02_strong_baselines.json"))).get(name)
+        except Exception:
+            pass
+        if not (base and base.get("n_gpus", 0) < world):
+            base = None
+    if base and base.get("value"):
+        n0 = int(base["n_gpus"])
+        rec["efficiency"] = rec["value"] / (world / n0 * base["value"])
+        rec["efficiency_base"] = "%s on %d GPU(s): %.4g cell-updates/s, %s" % (name, n0, base["value"], src % (base.get("source") or n0))
+    elif world == 1:
+        rec["efficiency"] = 1.0
+    # leave this run's point for the larger runs that follow (keep the smallest GPU count per mesh)
+    try:
+        if name not in live or live[name].get("n_gpus", 1 << 30) >= world:
+            live[name] = {"n_gpus": world, "value": rec["value"], "ms_per_step": rec["ms_per_step"]}
+            tmp = live_path + ".%d.tmp" % os.getpid()
+            json.dump(live, open(tmp, "w"))
+            os.replace(tmp, live_path)
     except Exception:
         pass
-    if world == 1:
-        rec["efficiency"] = 1.0
-    elif base and base.get("n_gpus") and base.get("value"):
-        rec["efficiency"] = rec["value"] / (world / base["n_gpus"] * base["value"])
-        rec["efficiency_base"] = "profiles/r02_strong_baselines.json: %s on %d GPU(s), %.4g cell-updates/s" % (name, base["n_gpus"], base["value"])
-    s.close()
-    return rec
 
 
 def strong_records(a, rank, world, device, peak, peak_src, on_record=None):

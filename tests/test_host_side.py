@@ -295,6 +295,30 @@ def test_bench_strong_records_cannot_cost_the_main_line(monkeypatch):
     assert "time budget" in bench.strong_records_in_child(a)[0]["skipped"]
 
 
+def test_strong_scaling_efficiency_uses_the_base_point_measured_on_the_same_box(tmp_path):
+    """bench.py's `strong` records: efficiency = value_N / (N / N0 x value_N0) against the smallest GPU count the mesh was measured on
+    by an earlier run of the same series on this box; the committed number of an earlier round only when there is none."""
+    import json
+    import bench_multi as bm
+    live = str(tmp_path / "live.json")
+    r1 = {"value": 8e8, "ms_per_step": 60.0}
+    bm.strong_efficiency(r1, "vortex_16M", 1, live)
+    assert r1["efficiency"] == 1.0
+    r8 = {"value": 6e9, "ms_per_step": 8.0}
+    bm.strong_efficiency(r8, "vortex_16M", 8, live)
+    assert abs(r8["efficiency"] - 6e9 / (8 * 8e8)) < 1e-12 and "this box" in r8["efficiency_base"]
+    r4 = {"value": 3e9, "ms_per_step": 64.0}
+    bm.strong_efficiency(r4, "vortex_64M", 4, live)                     # first point of a mesh that does not fit fewer GPUs: no efficiency yet
+    assert "efficiency" not in r4
+    r8 = {"value": 5.7e9, "ms_per_step": 33.0}
+    bm.strong_efficiency(r8, "vortex_64M", 8, live)
+    assert abs(r8["efficiency"] - 0.95) < 1e-12 and "on 4 GPU(s)" in r8["efficiency_base"]
+    assert json.load(open(live))["vortex_64M"]["n_gpus"] == 4           # the smallest count stays the base
+    rf = {"value": 6e9, "ms_per_step": 8.0}
+    bm.strong_efficiency(rf, "vortex_16M", 8, str(tmp_path / "absent.json"))
+    assert "r02_strong_baselines.json" in rf["efficiency_base"] and rf["efficiency"] > 0
+
+
 def time_since_bench_import(bench):
     import time
     return time.perf_counter() - bench.T_START
