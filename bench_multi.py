@@ -382,7 +382,7 @@ def run(a, rank, world, local_rank, workload):
         line["strong"] = strong_recs
         print(json.dumps(line), flush=True)
     # the line is out: nothing below may keep the job alive (a peer that failed inside a strong record never reaches the barrier)
-    threading.Thread(target=lambda: (time.sleep(30.0), os._exit(0)), daemon=True).start()
+    threading.Thread(target=lambda: (time.sleep(float(os.environ.get("MLB_BENCH_EXIT_GRACE", "30"))), os._exit(0)), daemon=True).start()
     try:
         dist.barrier()
         dist.destroy_process_group()
