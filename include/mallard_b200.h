@@ -129,6 +129,12 @@ typedef struct {
 } mlb_parallel;
 
 const char *mlb_version(void);
+/* Revision of the structs and signatures in this header; bumped whenever one of them changes (4: mlb_physics gained mu / Pr,
+ * MLB_BC_WALL_NOSLIP).  A host built against an older header would hand the library structs of the wrong size: it calls
+ * mlb_check_abi(MLB_ABI_VERSION) once before anything else and gets a clean error instead (oracle/dropin_harness.cpp and the
+ * ctypes mirror do). */
+#define MLB_ABI_VERSION 4
+int mlb_check_abi(int32_t header_abi_version);
 /* OpenMP threads used by the host preprocessor (n <= 0: query only); returns the value in effect */
 int mlb_set_host_threads(int32_t n);
 /* message of the last failed call on `ctx` (or of the last failed mlb_create / stateless call when ctx == NULL) */

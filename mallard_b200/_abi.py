@@ -53,10 +53,13 @@ class LocalMesh(C.Structure):
     _fields_ = [("n_global_cells", C.c_uint32), ("global_cell_ids", C.c_void_p), ("cell0_nodes", C.c_double * 6)]
 
 
+ABI_VERSION = 4     # MLB_ABI_VERSION of the header revision these structures mirror (tests/test_host_side.py compares the two)
+
 # every symbol include/mallard_b200.h declares: name -> (restype, argtypes)
 VP, I32, U32, U64, DBL = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, C.c_double
 SYMBOLS = {
     "mlb_version": (C.c_char_p, []),
+    "mlb_check_abi": (C.c_int, [I32]),
     "mlb_set_host_threads": (C.c_int, [I32]),
     "mlb_last_error": (C.c_char_p, [VP]),
     "mlb_create": (C.c_int, [C.POINTER(VP), C.POINTER(MeshView), C.POINTER(Numerics), C.POINTER(Physics), C.POINTER(Bc), I32, C.POINTER(Parallel)]),
@@ -148,5 +151,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
+        if L.mlb_check_abi(ABI_VERSION):       # the structs above mirror ONE revision of include/mallard_b200.h
+            raise RuntimeError("mallard_b200: " + L.mlb_last_error(None).decode() + " - the built library and mallard_b200/_abi.py disagree (rebuild)")
         _LIB = L
     return _LIB

@@ -729,6 +729,14 @@ void exchange_halo_plan(mlb_ctx & c) {
 extern "C" {
 
 const char * mlb_version(void) { return "mallard_b200 0.1 (sm_100a)"; }
+int mlb_check_abi(int32_t header_abi_version) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (header_abi_version != MLB_ABI_VERSION)
+        throw std::runtime_error("ABI mismatch: the caller was built against revision " + std::to_string(header_abi_version) +
+                                 " of mallard_b200.h, this library implements revision " + std::to_string(MLB_ABI_VERSION) + " (rebuild the caller)");
+    API_END(none)
+}
 int mlb_set_host_threads(int32_t n) {
     if (n > 0) omp_set_num_threads(n);
     return omp_get_max_threads();

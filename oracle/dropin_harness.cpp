@@ -63,6 +63,8 @@ int main(int argc, char ** argv) {
         else if (!strcmp(argv[i], "--native-io")) native_io = true;
     }
     if (input_file.empty()) { fprintf(stderr, "usage: mallard_dropin -i input.toml [--fp strict|fast] [--quiet]\n"); return 2; }
+    // this binary was compiled against one revision of the header; the library next to it may be newer (struct sizes!)
+    if (mlb_check_abi(MLB_ABI_VERSION)) { fprintf(stderr, "mallard_dropin: %s\n", mlb_last_error(nullptr)); return 3; }
     Kokkos::initialize(argc, argv);
     int rc = 0;
     {

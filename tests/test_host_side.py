@@ -27,6 +27,34 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in mb.lib().mlb_version()
 
 
+def test_abi_revision_is_checked_on_both_sides_of_the_boundary(tmp_path):
+    """Every struct crosses the boundary by pointer: a host built against an older header would pass structs of the wrong size.  The
+    header carries a revision (MLB_ABI_VERSION), the ctypes mirror and the drop-in harness present theirs to mlb_check_abi, and a binary
+    that predates the header it embeds is a build error (this is how a stale oracle/_ref/bin/mallard_dropin was caught in round 2)."""
+    import re
+    import subprocess
+    from mallard_b200 import _abi
+    header = open(os.path.join(ROOT, "include", "mallard_b200.h")).read()
+    assert int(re.search(r"#define MLB_ABI_VERSION (\d+)", header).group(1)) == _abi.ABI_VERSION
+    L = mb.lib()
+    assert L.mlb_check_abi(_abi.ABI_VERSION) == 0
+    assert L.mlb_check_abi(_abi.ABI_VERSION - 1) != 0 and "ABI mismatch" in L.mlb_last_error(None).decode()
+    dropin = os.path.join(ROOT, "oracle", "_ref", "bin", "mallard_dropin")
+    if os.path.exists(dropin):
+        import __graft_entry__ as ge
+        assert not ge.reference_binaries_stale(os.path.dirname(dropin)), "oracle/_ref/bin is older than the header / harness it was built from: run build()"
+        toml = tmp_path / "input.toml"
+        toml.write_text('[run]\nn_steps = 1\ncfl = 1.0\n[mesh]\ntype = "cartesian"\nNx = 8\nNy = 1\nLx = 1.0\nLy = 0.1\n[initialize]\ntype = "constant"\n'
+                        'u = [0.0, 0.0]\np = 1.0\nT = 300.0\n[[boundaries]]\nname = "left"\ntype = "symmetry"\n[[boundaries]]\nname = "right"\ntype = "symmetry"\n'
+                        '[[boundaries]]\nname = "top"\ntype = "symmetry"\n[[boundaries]]\nname = "bottom"\ntype = "symmetry"\n[numerics]\nriemann_solver = "HLLC"\n'
+                        'time_integrator = "SSPRK3"\ncheck_nan = false\n[numerics.face_reconstruction]\ntype = "FO"\n[physics]\ntype = "euler"\ngamma = 1.4\n'
+                        'p_ref = 101325.0\nT_ref = 298.15\nrho_ref = 1.225\n[output]\ncheck_interval = 1000000\n')
+        import torch
+        if not torch.cuda.is_available():      # the harness gets past the ABI check and then fails where it must: no device, no fallback
+            p = subprocess.run([dropin, "-i", str(toml), "--quiet"], capture_output=True, text=True, cwd=tmp_path, env=dict(os.environ, OMP_PROC_BIND="false"))
+            assert p.returncode != 0 and "ABI mismatch" not in p.stderr and "no CPU fallback" in p.stderr, p.stderr[-600:]
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():
