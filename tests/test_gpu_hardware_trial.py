@@ -30,7 +30,11 @@ GROUPS = {
     "viscous_terms": ("test_viscous_residual_of_couette_flow or test_decaying_shear_layer_follows_the_diffusion_equation "
                       "or test_viscous_run_on_partitioned_ranks_reproduces_the_single_context_run"),
 }
-TIME_LIMIT_S = float(os.environ.get("MLB_TRIAL_TIME_LIMIT", "600"))
+# The driver gives the whole `pytest -m gpu` run 1200 s (GPUTEST_r01.json: steps.0.timeout_s) and the measured suite takes ~190 s of them:
+# a group may take TIME_LIMIT_S, all groups together BUDGET_S - a group that finds the budget spent is reported as XFAIL, not run.
+TIME_LIMIT_S = float(os.environ.get("MLB_TRIAL_TIME_LIMIT", "330"))
+BUDGET_S = float(os.environ.get("MLB_TRIAL_BUDGET", "660"))
+_spent = [0.0]
 
 
 def child_command(group):
@@ -63,12 +67,18 @@ def run_group(group, command=None, time_limit=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("group", sorted(GROUPS))
+@pytest.mark.parametrize("group", ["late_reference_fixtures", "quadrilaterals_under_teno", "viscous_terms", "generic_teno_kernel"])   # cheapest first
 def test_first_hardware_run_of_paths_written_after_the_gpu_budget(group):
     if os.environ.get("MLB_RUN_UNVERIFIED") == "1":
         pytest.skip("MLB_RUN_UNVERIFIED=1: the gated tests run in-process")
+    import time
     import torch
-    green, summary, log = run_group(group)
+    left = BUDGET_S - _spent[0]
+    if left < 30.0:
+        pytest.xfail("first hardware run of %s: not run, the time budget of the trial (%.0f s) was spent by the groups before it" % (group, BUDGET_S))
+    t0 = time.perf_counter()
+    green, summary, log = run_group(group, time_limit=min(TIME_LIMIT_S, left))
+    _spent[0] += time.perf_counter() - t0
     try:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "hardware_trial_%s.log" % group), "w") as f:
