@@ -163,23 +163,25 @@ STRONG_TAG = "STRONG_RECORD "
 T_START = time.perf_counter()
 
 
-def strong_records_in_child(a, popen=subprocess.Popen, min_left=120.0):
-    """N = 1: the strong-scaling records (a 16 M-cell mesh: ~100 GB of device memory, minutes of set-up) run in a CHILD process under a
-    deadline, after the main line has been measured: whatever happens there - a crash, an out-of-memory kill, a hang - the main line
-    is printed.  Records completed before a failure are kept (the child prints each one as it finishes)."""
+def strong_records_in_child(a, popen=subprocess.Popen, min_left=120.0, task="strong"):
+    """N = 1: the strong-scaling records (a 16 M-cell mesh: ~100 GB of device memory, minutes of set-up) - and, task by task, the records of
+    bench_multi.EXPERIMENTS - run in a CHILD process under a deadline, after the main line has been measured: whatever happens there - a
+    crash, an out-of-memory kill, a hang, an illegal address in a kernel that has never run on hardware - the main line is printed.
+    Records completed before a failure are kept (the child prints each one as it finishes)."""
     import signal
     deadline = float(os.environ.get("MLB_BENCH_DEADLINE", "760"))          # the driver kills a scaling run at 870 s
     elapsed = time.perf_counter() - T_START
     left = deadline - elapsed
     if left < min_left:
-        return [{"skipped": "time budget of the bench run (%.0f s elapsed)" % elapsed}]
-    cmd = [sys.executable, os.path.abspath(__file__), "--strong-child", "--gpus", "1", "--steps", str(a.steps), "--warmup", str(a.warmup), "--fp", a.fp]
+        return [{"workload": task, "skipped": "time budget of the bench run (%.0f s elapsed)" % elapsed}]
+    cmd = [sys.executable, os.path.abspath(__file__), "--strong-child", "--child-task", task, "--gpus", "1", "--steps", str(a.steps), "--warmup", str(a.warmup),
+           "--fp", a.fp]
     env = dict(os.environ, MLB_BENCH_ELAPSED="%.1f" % elapsed)
     recs, note, out = [], None, ""
     try:
         p = popen(cmd, stdout=subprocess.PIPE, text=True, env=env, start_new_session=True)
     except Exception as ex:
-        return [{"error": "could not start the strong-scaling child process: %s" % str(ex)[:200]}]
+        return [{"workload": task, "error": "could not start the child process: %s" % str(ex)[:200]}]
     try:
         out, _ = p.communicate(timeout=left)
     except subprocess.TimeoutExpired:
@@ -191,7 +193,7 @@ def strong_records_in_child(a, popen=subprocess.Popen, min_left=120.0):
             out, _ = p.communicate(timeout=30)
         except Exception:
             out = ""
-        note = {"aborted": "deadline of %.0f s reached before the remaining strong-scaling records finished" % deadline}
+        note = {"workload": task, "aborted": "deadline of %.0f s reached before the remaining records of this child finished" % deadline}
     for l in (out or "").splitlines():
         if l.startswith(STRONG_TAG):
             try:
@@ -199,7 +201,7 @@ def strong_records_in_child(a, popen=subprocess.Popen, min_left=120.0):
             except Exception:
                 pass
     if note is None and p.returncode != 0:
-        note = {"error": "the strong-scaling child process ended with code %s" % p.returncode}
+        note = {"workload": task, "error": "the child process ended with code %s" % p.returncode}
     if note is not None:
         recs.append(note)
     return recs
@@ -228,6 +230,7 @@ def main():
                                                             "sample (1024x1024: ~8 min of serial set-up, ~30 GB) and cache the number in profiles/reference_full_size.json")
     ap.add_argument("--strong-child", action="store_true", help="internal (N = 1): run the strong-scaling records only and print them as one JSON list; "
                                                                 "bench.py starts this in a child process so that no failure there can cost the main line")
+    ap.add_argument("--child-task", default="strong", help="internal: strong | one of bench_multi.EXPERIMENTS")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
@@ -276,7 +279,11 @@ def main():
         torch.cuda.set_device(0)
         mb.set_host_threads(host_cores())
         peak, peak_src = hbm_peak()
-        bench_multi.strong_records(a, 0, 1, 0, peak, peak_src, on_record=lambda r: print(STRONG_TAG + json.dumps(r), flush=True))
+        emit = lambda r: print(STRONG_TAG + json.dumps(r), flush=True)      # noqa: E731
+        if a.child_task == "strong":
+            bench_multi.strong_records(a, 0, 1, 0, peak, peak_src, on_record=emit)
+        else:
+            emit(bench_multi.experiment_record(a.child_task, a, peak, peak_src))
         return
 
     torch.cuda.set_device(0)
@@ -426,10 +433,13 @@ def main():
             finite = {"error": str(ex)[:200]}
 
     # ---- strong-scaling records: this N's point of the 16 M-cell (BASELINE configs[3]) / 64 M-cell partitioned vortex meshes
-    strong = None
+    strong, experiments = None, []
     if a.workload == "riemann_2d" and a.recon == "TENO" and not a.no_strong and (a.nx, a.ny) == (1024, 1024):
         s.close()                                    # (a closed context ignores a second close): the 16 M-cell mesh needs the GPU's memory
         strong = strong_records_in_child(a)
+        import bench_multi
+        for task in bench_multi.EXPERIMENTS:       # configs[4] numerics and configs[3] as worded, one child each (see bench_multi.experiment_record)
+            experiments += strong_records_in_child(a, task=task)
 
     line = {"metric": "cell-updates/s per RK stage", "value": value, "unit": "cell-updates/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -441,7 +451,8 @@ def main():
                                       "device_table_build_s": stats[10]},
                        "note": ("reference-faithful TENO: like the reference, the state turns non-finite inside step 1 (SURVEY 0.2); cost is "
                                 "data-independent") if a.recon == "TENO" else "first-order path (the numerics of examples/sod and examples/wedge)"},
-            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "kernels": kernels, "strong": strong}
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "kernels": kernels, "strong": strong,
+            "experiments": experiments or None}
     print(json.dumps(line))
 
 
