@@ -271,6 +271,13 @@ def main():
     import mallard_b200 as mb
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    if a.strong_child and world > 1:      # N > 1, inside the per-rank child processes started by bench_multi.experiment_children()
+        import bench_multi
+        peak, peak_src = hbm_peak()
+        rec = bench_multi.viscous_strong_child(a, rank, world, local_rank, peak, peak_src)
+        if rank == 0:
+            print(STRONG_TAG + json.dumps(rec), flush=True)
+        return
     if world > 1:
         import bench_multi
         return bench_multi.run(a, rank, world, local_rank, workload)

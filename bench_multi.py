@@ -41,9 +41,14 @@ def _watchdog():
         if time.perf_counter() - T_START > DEADLINE_S:
             if _STATE["rank"] == 0 and _STATE["line"] is not None:
                 line = dict(_STATE["line"])
-                line["strong"] = list(_STATE["strong"]) + [{"aborted": "deadline of %.0f s reached before the remaining strong-scaling records finished" % DEADLINE_S}]
+                line["strong"] = list(_STATE["strong"]) + [{"aborted": "deadline of %.0f s reached before the remaining records finished" % DEADLINE_S}]
                 sys.stdout.write(json.dumps(line) + "\n")
                 sys.stdout.flush()
+            for pid in _STATE.get("children", []):       # (per-rank child processes of experiment_children)
+                try:
+                    os.killpg(pid, 9)
+                except Exception:
+                    pass
             os._exit(0 if _STATE["line"] is not None or _STATE["rank"] != 0 else 3)
 
 
@@ -142,15 +147,17 @@ TRANSPORT = ("grouped ncclSend/ncclRecv between device buffers + ncclAllReduce(m
                             "(split-phase C ABI driven over torch.distributed)")
 
 
-def strong_record(name, nq, a, rank, world, device, peak, peak_src):
-    """Strong scaling: the nq x nq jittered, id-shuffled triangulation of [0,10]^2 split over `world` GPUs."""
+def strong_record(name, nq, a, rank, world, device, peak, peak_src, mu=0.0):
+    """Strong scaling: the nq x nq jittered, id-shuffled triangulation of [0,10]^2 split over `world` GPUs.  mu > 0: with the
+    Navier-Stokes terms and normalised TENO weights (BASELINE configs[4])."""
     import bench
     import mallard_b200 as mb
     from mallard_b200 import synthetic as syn
     nc = 2 * nq * nq
     rec = {"workload": "%s: isentropic vortex, jittered (+-0.15 h, seed 12345), id-shuffled triangulation %dx%d of [0,10]^2 (%d cells), "
-                       "TENO(legendre,p=3)+HLLC+SSPRK3, cfl 0.1, extrapolation BCs; recursive coordinate bisection over %d GPU(s), rank-local ingest"
-                       % (name, nq, nq, nc, world), "n_cells": nc, "n_gpus": world, "scaling": "strong"}
+                       "TENO(legendre,p=3%s)+HLLC+SSPRK3, cfl 0.1, extrapolation BCs%s; recursive coordinate bisection over %d GPU(s), rank-local ingest"
+                       % (name, nq, nq, nc, ", normalised weights" if mu > 0 else "", ", Navier-Stokes terms: mu = %g, Pr = 0.72" % mu if mu > 0 else "", world),
+           "n_cells": nc, "n_gpus": world, "scaling": "strong"}
     t0 = time.perf_counter()
     layers, lp, ds, s = 8, None, None, None
     for attempt in range(3):
@@ -158,6 +165,8 @@ def strong_record(name, nq, a, rank, world, device, peak, peak_src):
         ok = 1.0
         try:
             kw = dict(recon="TENO", riemann="HLLC", integrator="SSPRK3", order=3, bcs=syn.EXTRAP4, fp_mode=a.fp, keep_stage_rhs=False)
+            if mu > 0:
+                kw.update(gas=dict(mu=mu), teno_fixed=True)
             if world > 1:
                 s = mb.Solver(lp.mesh, part=lp.part_local, rank=rank, n_ranks=world, device=device, local=lp.local, **kw)
             else:
@@ -197,7 +206,7 @@ def strong_record(name, nq, a, rank, world, device, peak, peak_src):
                setup_seconds=float(mem[3]), preprocess_seconds=float(mem[4]), mesh_seconds=float(mem[5]), graph_replayed_steps=int(s.get("stats")[11]))
     s.close()
     if rank == 0:
-        strong_efficiency(rec, name, world)
+        strong_efficiency(rec, name + ("_viscous" if mu > 0 else ""), world)
     return rec
 
 
@@ -332,6 +341,84 @@ def experiment_record(task, a, peak, peak_src):
     return rec
 
 
+VISCOUS_MU = 1.0e-3
+EXPERIMENT_START_BY_S = 430.0       # a 64 M-cell viscous record costs ~4 min (mesh, preprocessing, run): do not start it later than this
+
+
+def viscous_strong_child(a, rank, world, local_rank, peak, peak_src):
+    """Body of the per-rank CHILD process (bench.py --strong-child --child-task viscous_strong under RANK / WORLD_SIZE > 1): its own
+    process group, the largest strong-scaling mesh that fits `world` GPUs, viscous."""
+    import datetime
+    import torch
+    import torch.distributed as dist
+    import bench
+    import mallard_b200 as mb
+    torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(local_rank)
+    mb.set_host_threads(max(1, bench.host_cores() // world))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=1800))
+    fits = [(n, q) for n, q in STRONG_MESHES if 2 * q * q / world <= MAX_CELLS_PER_GPU]
+    name, nq = fits[-1]
+    rec = strong_record(name, nq, a, rank, world, local_rank, peak, peak_src, mu=VISCOUS_MU)
+    rec["verification"] = ("viscous kernels and the second ghost ring of viscous contexts were written after the round-2 GPU budget was spent; validated by "
+                           "the host emulation of their source (tests/test_kernel_emulation.py); first measured here, in a process of its own")
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        pass
+    return rec
+
+
+def experiment_children(a, rank, world, popen=None):
+    """N > 1: BASELINE configs[4] (viscous, the 64 M-cell mesh where it fits) in CHILD processes, one per rank, with a process group of
+    their own - code that runs on hardware for the first time must not be able to take the main line (or the measured strong-scaling
+    records) with it.  Every rank decides the same way (collective), starts its child, waits for it under the deadline; rank 0 returns
+    the records its child printed."""
+    import signal
+    import subprocess
+    import bench
+    elapsed = float(_reduce([time.perf_counter() - T_START], world, "max")[0])
+    if elapsed > EXPERIMENT_START_BY_S:
+        return [{"workload": "viscous_strong", "skipped": "time budget of the bench run (%.0f s elapsed)" % elapsed}]
+    left = DEADLINE_S - elapsed - 40.0          # the parent's own watchdog fires at DEADLINE_S: be done before it
+    env = dict(os.environ, MLB_BENCH_ELAPSED="%.1f" % elapsed, MASTER_PORT=str(int(os.environ.get("MASTER_PORT", "29500")) + 23))
+    for k in ("TORCHELASTIC_USE_AGENT_STORE", "TORCHELASTIC_RUN_ID", "TORCHELASTIC_RESTART_COUNT", "TORCHELASTIC_MAX_RESTARTS"):
+        env.pop(k, None)                        # the children rendezvous among themselves (rank 0's child hosts the store), not through torchrun's agent
+    cmd = [sys.executable, os.path.join(bench.ROOT, "bench.py"), "--strong-child", "--child-task", "viscous_strong", "--gpus", str(world), "--steps", str(a.steps),
+           "--warmup", str(a.warmup), "--fp", a.fp]
+    recs, note, out = [], None, ""
+    try:
+        p = (popen or subprocess.Popen)(cmd, stdout=subprocess.PIPE, text=True, env=env, start_new_session=True)
+    except Exception as ex:
+        return [{"workload": "viscous_strong", "error": "could not start the child process: %s" % str(ex)[:200]}]
+    _STATE["children"] = [p.pid]                # the watchdog takes them along should it fire
+    try:
+        out, _ = p.communicate(timeout=left)
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(p.pid, signal.SIGKILL)
+        except Exception:
+            p.kill()
+        try:
+            out, _ = p.communicate(timeout=30)
+        except Exception:
+            out = ""
+        note = {"workload": "viscous_strong", "aborted": "no result within %.0f s (children killed)" % left}
+    _STATE["children"] = []
+    for l in (out or "").splitlines():
+        if l.startswith(bench.STRONG_TAG):
+            try:
+                recs.append(json.loads(l[len(bench.STRONG_TAG):]))
+            except Exception:
+                pass
+    if note is None and p.returncode != 0:
+        note = {"workload": "viscous_strong", "error": "the child process of rank %d ended with code %s" % (rank, p.returncode)}
+    if note is not None:
+        recs.append(note)
+    return recs
+
+
 def run(a, rank, world, local_rank, workload):
     import torch
     import torch.distributed as dist
@@ -439,9 +526,16 @@ def run(a, rank, world, local_rank, workload):
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": None, "strong": None}
     _STATE["line"] = line              # from here on the watchdog can deliver the main line on its own
     strong_recs = strong_records(a, rank, world, local_rank, peak, peak_src) if (a.workload == "riemann_2d" and not a.no_strong) else None
+    experiments = None
+    if strong_recs is not None and not any("error" in r for r in strong_recs):      # (after an error the ranks may have diverged: nothing collective)
+        try:
+            experiments = experiment_children(a, rank, world)
+        except Exception as ex:
+            experiments = [{"workload": "viscous_strong", "error": str(ex)[:300]}]
     _STATE["done"] = True
     if rank == 0:
         line["strong"] = strong_recs
+        line["experiments"] = experiments
         print(json.dumps(line), flush=True)
     # the line is out: nothing below may keep the job alive (a peer that failed inside a strong record never reaches the barrier)
     threading.Thread(target=lambda: (time.sleep(float(os.environ.get("MLB_BENCH_EXIT_GRACE", "30"))), os._exit(0)), daemon=True).start()

@@ -172,6 +172,10 @@ def install(monkeypatch=None, world=1):
     if not isinstance(real_child, functools.partial):
         setattr_(bench, "strong_records_in_child",
                  functools.partial(real_child, popen=lambda cmd, **kw: subprocess.Popen([cmd[0], me] + list(cmd[2:]), **kw)))
+    real_exp = bench_multi.experiment_children
+    if not isinstance(real_exp, functools.partial):      # N > 1: the per-rank children of the viscous record carry the stand-ins too
+        setattr_(bench_multi, "experiment_children",
+                 functools.partial(real_exp, popen=lambda cmd, **kw: subprocess.Popen([cmd[0], me] + list(cmd[2:]), **kw)))
     if world > 1:
         import torch.distributed as dist
         real_init = dist.init_process_group

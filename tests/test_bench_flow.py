@@ -87,6 +87,9 @@ def test_multi_gpu_line_with_its_strong_records(world, tmp_path):
     assert strong[0]["efficiency"] > 0 and "this box" in strong[0]["efficiency_base"] and "efficiency" not in strong[1]
     assert strong[0]["halo"]["max_peers"] >= 1 and strong[0]["ghost_layers"] >= 8 and strong[0]["roofline"]["rank"] == "slowest"
     assert json.load(open(live))["vortex_64M"]["n_gpus"] == world
+    ex = d["experiments"]                       # BASELINE configs[4]: the largest mesh that fits, viscous, in per-rank child processes with their own group
+    assert len(ex) == 1 and ex[0]["n_cells"] == 12800 and ex[0]["n_gpus"] == world and "Navier-Stokes" in ex[0]["workload"] and ex[0]["value"] > 0
+    assert ex[0]["halo"]["max_peers"] >= 1 and "verification" in ex[0]
 
 
 def test_a_failing_strong_record_does_not_cost_the_main_line(tmp_path):
