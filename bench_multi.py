@@ -283,7 +283,65 @@ def strong_records(a, rank, world, device, peak, peak_src, on_record=None):
 #      (configs[4]: viscous terms; configs[3] as literally worded: mixed triangles / quadrilaterals under TENO).  Their kernels were
 #      written after the round-2 GPU budget had been spent and are validated by the host emulation of their source
 #      (tests/test_kernel_emulation.py); these records are their measurement.
-EXPERIMENTS = ("vortex_viscous", "vortex_mixed")
+EXPERIMENTS = ("vortex_viscous", "vortex_mixed", "small_step")
+
+
+def small_step_record(a):
+    """BASELINE configs[0] / configs[2] verbatim (examples/sod: 1000 cells, examples/wedge: 7500 cells; first order + HLLC + SSPRK3, cfl 1):
+    launch-bound meshes.  mlb_run as it ships (one step = 7 kernels, replayed as a CUDA graph) against MLB_SMALL_STEP=1 (all steps in one
+    cooperative kernel, csrc/small_step.cuh), from the same state: microseconds per step both ways and whether the two final states are the
+    same bits."""
+    import mallard_b200 as mb
+    n = int(os.environ.get("MLB_EXPERIMENT_STEPS", "2000"))
+    R = 101325.0 / (298.15 * 1.225)
+    rec = {"workload": "small_step: examples/sod (cartesian 1000x1) and examples/wedge (150x50), first order + HLLC + SSPRK3, cfl 1, %d steps per leg: "
+                       "CUDA-graph replayed multi-kernel step vs one cooperative kernel for the whole run (MLB_SMALL_STEP=1, opt-in)" % n,
+           "n_gpus": 1, "unit": "us per step", "fp_mode": a.fp,
+           "verification": "cooperative kernel written after the round-2 GPU budget was spent; its phases run on the host against the oracle and the "
+                           "reference's dumps (tests/test_kernel_emulation.py); first measured here"}
+    for case in ("sod", "wedge"):
+        if case == "sod":
+            mesh = mb.Mesh.generate("cartesian", 1000, 1, 1.0, 1.0e-3)
+            x = mesh.arrays["cell_coords"][:, 0]
+            rho, p, u = np.where(x < 0.5, 1.0, 0.125), np.where(x < 0.5, 1.0, 0.1), np.zeros_like(x)
+            bcs = [dict(name=z, type="symmetry") for z in ("left", "right", "top", "bottom")]
+        else:
+            mesh = mb.Mesh.generate("wedge", 150, 50, 4.0, 1.5)
+            p, u = np.full(mesh.n_cells, 101325.0), np.full(mesh.n_cells, 600.0)
+            rho = p / (R * 300.0)
+            bcs = [dict(name="left", type="upt", u=[600.0, 0.0], p=101325.0, T=300.0), dict(name="right", type="p_out", p=101325.0),
+                   dict(name="top", type="symmetry"), dict(name="bottom", type="symmetry")]
+        U0 = np.stack([rho, rho * u, 0.0 * rho, p / 0.4 + 0.5 * rho * u * u], 1)
+        out = {"n_cells": mesh.n_cells}
+        states = {}
+        for leg, env in (("graph_replayed_kernels", None), ("cooperative_kernel", {"MLB_SMALL_STEP": "1"}),
+                         ("cooperative_kernel_8_blocks", {"MLB_SMALL_STEP": "1", "MLB_SMALL_STEP_BLOCKS": "8"})):
+            for k in ("MLB_SMALL_STEP", "MLB_SMALL_STEP_BLOCKS"):
+                os.environ.pop(k, None)
+            os.environ.update(env or {})
+            s = mb.Solver(mesh, "FO", "HLLC", "SSPRK3", bcs=bcs, fp_mode=a.fp, keep_stage_rhs=False)
+            s.set_state(U0)
+            s.run(64, cfl=1.0)                         # warm-up (graph instantiation / cooperative launch attributes)
+            s.set_state(U0)
+            s.synchronize()
+            s.event_record(0)
+            s.run(n, cfl=1.0)
+            s.event_record(1)
+            ms = s.event_elapsed_ms(0, 1)
+            states[leg] = s.get_state()
+            st = s.get("stats")
+            out[leg] = {"us_per_step": 1e3 * ms / n, "cell_updates_per_s": mesh.n_cells * 3 * n / (ms * 1e-3),
+                        "steps_in_the_cooperative_kernel": int(st[12]) if len(st) > 12 else None, "graph_replayed_steps": int(st[11])}
+            s.close()
+        for k in ("MLB_SMALL_STEP", "MLB_SMALL_STEP_BLOCKS"):
+            os.environ.pop(k, None)
+        ref = states["graph_replayed_kernels"]
+        out["finite"] = bool(np.isfinite(ref).all())
+        for leg in ("cooperative_kernel", "cooperative_kernel_8_blocks"):
+            out[leg]["same_bits_as_the_multi_kernel_path"] = bool(np.array_equal(states[leg], ref))
+            out[leg]["max_difference_of_the_field_scale"] = float(np.abs(states[leg] - ref).max() / max(np.abs(ref).max(), 1e-300))
+        rec[case] = out
+    return rec
 
 
 def experiment_record(task, a, peak, peak_src):
@@ -291,6 +349,8 @@ def experiment_record(task, a, peak, peak_src):
     import mallard_b200 as mb
     from mallard_b200 import synthetic as syn
     mb.set_host_threads(bench.host_cores())
+    if task == "small_step":
+        return small_step_record(a)
     t0 = time.perf_counter()
     if task == "vortex_viscous":
         nq, mu = int(os.environ.get("MLB_EXPERIMENT_NQ", "1024")), 1.0e-3

@@ -10,6 +10,7 @@
 
 #include "kernel_args.h"
 #include "nccl_dyn.h"
+#include "stage_plan.h"
 
 using namespace mlb;
 
@@ -123,6 +124,7 @@ struct mlb_ctx {
     cudaEvent_t ev[16] = {};
     uint64_t launches = 0;
     uint64_t graph_replays = 0;        // steps of mlb_run executed as CUDA graph replays
+    uint64_t small_steps = 0;          // steps of mlb_run executed inside the cooperative small-mesh kernel
     bool profiling = false;
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
     std::map<std::string, ProfileEntry> profile;
@@ -205,35 +207,7 @@ struct mlb_plan { Prep prep; uint32_t nc_ref = 0, nf_ref = 0; std::vector<int32_
 
 namespace {
 
-// ---------------------------------------------------------------------------------------------------------------
-// Stage schedule (numerics/time_integrator.cpp:57-163).  Buffers: U[cur] = solution, the two others are temporaries.
-// ---------------------------------------------------------------------------------------------------------------
-struct StagePlan { int in, out, base, mode, n_prev, last; double coef, c0, c1, cprev[3]; int kprev[3]; int kstore; };
-
-std::vector<StagePlan> make_plan(const mlb_ctx & c) {
-    const int A = c.cur, B = (c.cur + 1) % 3, C = (c.cur + 2) % 3;
-    std::vector<StagePlan> p;
-    auto mk = [&](int in, int out, int mode, double coef, int kstore) {
-        StagePlan s{}; s.in = in; s.out = out; s.base = A; s.mode = mode; s.coef = coef; s.kstore = kstore; return s; };
-    if (c.num.integrator == MLB_INTEGRATOR_FE) {
-        StagePlan s = mk(A, B, 0, 1.0, 0); s.last = 1; p.push_back(s);
-    } else if (c.num.integrator == MLB_INTEGRATOR_RK4) {
-        p.push_back(mk(A, B, 0, 0.5, 0));
-        p.push_back(mk(B, C, 0, 0.5, 1));
-        p.push_back(mk(C, B, 0, 1.0, 2));
-        StagePlan s = mk(B, A, 2, 1.0 / 6.0, 3);
-        s.n_prev = 3; s.kprev[0] = 0; s.kprev[1] = 1; s.kprev[2] = 2;
-        s.cprev[0] = 1.0 / 6.0; s.cprev[1] = 1.0 / 3.0; s.cprev[2] = 1.0 / 3.0; s.last = 1;
-        p.push_back(s);
-    } else {
-        p.push_back(mk(A, B, 0, 1.0, 0));
-        StagePlan s1 = mk(B, C, 1, 0.25, 1); s1.c0 = 3.0 / 4.0; s1.c1 = 1.0 / 4.0; p.push_back(s1);
-        StagePlan s2 = mk(C, A, 2, 2.0 / 3.0, 2);
-        s2.n_prev = 2; s2.kprev[0] = 0; s2.kprev[1] = 1; s2.cprev[0] = 1.0 / 6.0; s2.cprev[1] = 1.0 / 6.0; s2.last = 1;
-        p.push_back(s2);
-    }
-    return p;
-}
+std::vector<StagePlan> make_plan(const mlb_ctx & c) { return make_stage_plan(c.cur, c.num.integrator); }   // stage_plan.h
 
 ReconArgs recon_args(mlb_ctx & c, const double * Uin) {
     ReconArgs r{};
@@ -286,6 +260,26 @@ void run_recon(mlb_ctx & c, const double * Uin, int phase = 0) {
     }
 }
 
+// the argument block of one stage's face / gather kernels
+StageArgs stage_args(mlb_ctx & c, const StagePlan & s, bool bare, double * k_out) {
+    StageArgs a{};
+    a.g = c.g; a.ph = c.phys; a.Uin = c.U[s.in]; a.Fc = c.Fc; a.AF = c.AF; a.teno = c.teno ? 1 : 0;
+    a.k_override = c.has_override ? c.k_override : nullptr;
+    a.scal = c.scal; a.step_counter = c.step_counter; a.G = c.G;
+    RkArgs & rk = a.rk;
+    if (bare) { rk.mode = 3; rk.k_store = k_out; }
+    else {
+        rk.mode = s.mode; rk.n_prev = s.n_prev; rk.last_stage = s.last;
+        rk.base = c.U[s.base]; rk.out = c.U[s.out];
+        const bool need_k = c.num.keep_stage_rhs || !s.last;
+        rk.k_store = need_k ? c.k[s.kstore] : nullptr;
+        for (int j = 0; j < s.n_prev; j++) { rk.kprev[j] = c.k[s.kprev[j]]; rk.cprev[j] = s.cprev[j]; }
+        rk.c0 = s.c0; rk.c1 = s.c1; rk.coef = s.coef;
+        rk.prim_out = s.last ? c.prim : nullptr;
+    }
+    return a;
+}
+
 void run_stage(mlb_ctx & c, const StagePlan & s, bool bare, double * k_out) {
     const double * Uin = c.U[s.in];
     const bool recon = c.teno && !c.has_override;
@@ -301,21 +295,7 @@ void run_stage(mlb_ctx & c, const StagePlan & s, bool bare, double * k_out) {
         wait_halo(c);
         if (recon) run_recon(c, Uin);
     }
-    StageArgs a{};
-    a.g = c.g; a.ph = c.phys; a.Uin = Uin; a.Fc = c.Fc; a.AF = c.AF; a.teno = c.teno ? 1 : 0;
-    a.k_override = c.has_override ? c.k_override : nullptr;
-    a.scal = c.scal; a.step_counter = c.step_counter; a.G = c.G;
-    RkArgs & rk = a.rk;
-    if (bare) { rk.mode = 3; rk.k_store = k_out; }
-    else {
-        rk.mode = s.mode; rk.n_prev = s.n_prev; rk.last_stage = s.last;
-        rk.base = c.U[s.base]; rk.out = c.U[s.out];
-        const bool need_k = c.num.keep_stage_rhs || !s.last;
-        rk.k_store = need_k ? c.k[s.kstore] : nullptr;
-        for (int j = 0; j < s.n_prev; j++) { rk.kprev[j] = c.k[s.kprev[j]]; rk.cprev[j] = s.cprev[j]; }
-        rk.c0 = s.c0; rk.c1 = s.c1; rk.coef = s.coef;
-        rk.prim_out = s.last ? c.prim : nullptr;
-    }
+    const StageArgs a = stage_args(c, s, bare, k_out);
     if (!c.has_override && c.G) c.launch("visc_grad", [&] { c.kt->gradients(a, c.stream); });
     if (!c.has_override) c.launch(c.teno ? "face_flux_teno" : "face_flux_fo", [&] { c.kt->faces(a, c.stream); });
     c.launch("gather_stage", [&] { c.kt->stage(a, c.stream); });
@@ -332,12 +312,39 @@ void do_step(mlb_ctx & c) {
     finish_plan(c, plan);
 }
 
-void do_calc_dt(mlb_ctx & c, double cfl) {
+CflArgs cfl_args(mlb_ctx & c, double cfl) {
     CflArgs a{};
     a.g = c.g; a.gas = c.gas; a.U = c.U[c.cur]; a.prim = c.prim; a.sr_out = c.sr; a.scal = c.scal;
     a.max_bits = c.max_bits; a.blocks_done = c.blocks_done; a.cfl = cfl;
+    return a;
+}
+
+void do_calc_dt(mlb_ctx & c, double cfl) {
+    const CflArgs a = cfl_args(c, cfl);
     wait_halo(c);   // the CFL kernel reads the ghosts' primitives
     c.launch("cfl", [&] { c.kt->cfl(a, c.stream); });
+}
+
+// Small first-order meshes: whole steps in one cooperative launch (csrc/small_step.cuh).  Opt-in (MLB_SMALL_STEP=1, read per call)
+// until it has been measured on hardware; the result is that of the multi-kernel path (same bodies, same argument blocks).
+bool small_step_eligible(const mlb_ctx & c) {
+    const char * e = getenv("MLB_SMALL_STEP");
+    return e && e[0] == '1' && !c.teno && !c.G && !c.has_override && c.n_ranks == 1 && !c.profiling && !c.halo_pending &&
+           c.num.integrator != MLB_INTEGRATOR_FE && c.prep.N_owned <= 262144u;
+}
+void run_small_steps(mlb_ctx & c, uint32_t n_steps, double cfl) {
+    const auto plan = make_plan(c);
+    SmallStepArgs p{};
+    for (size_t st = 0; st < plan.size(); st++) p.st[st] = stage_args(c, plan[st], false, nullptr);
+    p.cfl = cfl_args(c, cfl > 0.0 ? cfl : 0.0);
+    p.n_stages = (int32_t)plan.size();
+    p.n_steps = n_steps;
+    const char * b = getenv("MLB_SMALL_STEP_BLOCKS");      // A/B knob: cap the grid (fewer blocks = cheaper grid barriers)
+    const int max_blocks = b ? atoi(b) : 0;
+    c.launch("small_step", [&] { c.kt->small_step(p, max_blocks, c.stream); });
+    CUDA_OK(cudaGetLastError());
+    c.small_steps += n_steps;
+    finish_plan(c, plan);
 }
 
 void read_scalars(mlb_ctx & c, double * out) {
@@ -924,7 +931,11 @@ int mlb_run(mlb_ctx * c, uint32_t n_steps, double cfl, double * t_out, double * 
     // stage buffers of SSPRK3 / RK4 return to the same rotation after a step, so every replay is the same graph.
     static const bool graphs = [] { const char * e = getenv("MLB_RUN_GRAPH"); return !(e && e[0] == '0'); }();
     uint32_t done = 0;
-    if (graphs && !c->profiling && n_steps >= 8 && c->num.integrator != MLB_INTEGRATOR_FE) {
+    if (n_steps && small_step_eligible(*c)) {         // launch-bound first-order meshes: all n_steps in ONE cooperative kernel (opt-in)
+        run_small_steps(*c, n_steps, cfl);
+        done = n_steps;
+    }
+    if (done < n_steps && graphs && !c->profiling && n_steps >= 8 && c->num.integrator != MLB_INTEGRATOR_FE) {
         one_step();                                   // eager: function attributes, occupancy queries, error reporting
         done = 1;
         const uint64_t l0 = c->launches;
@@ -1107,8 +1118,9 @@ int mlb_get_array(mlb_ctx * c, const char * name, void * out, uint64_t * nbytes)
                                     : (uint64_t)c->n_ftiles * FAST_S * MC * FAST_CT * 4;
         if (out) CUDA_OK(cudaMemcpy(out, src, *nbytes, cudaMemcpyDeviceToHost));
     } else if (n == "stats") {
-        double s[12] = {(double)c->launches, P.seconds, (double)c->device_bytes, (double)P.N, (double)P.N_owned, (double)P.NF,
-                        (double)P.N_recon, (double)c->n_stages, P.seconds_stencils, P.seconds_matrices, c->table_build_ms * 1e-3, (double)c->graph_replays};
+        double s[13] = {(double)c->launches, P.seconds, (double)c->device_bytes, (double)P.N, (double)P.N_owned, (double)P.NF,
+                        (double)P.N_recon, (double)c->n_stages, P.seconds_stencils, P.seconds_matrices, c->table_build_ms * 1e-3, (double)c->graph_replays,
+                        (double)c->small_steps};
         host(s, sizeof(s));
     } else if (n.rfind("teno:", 0) == 0) {
         if (!c->teno) throw std::runtime_error("context has no TENO tables");

@@ -128,6 +128,14 @@ struct CflArgs {
     double cfl;                   // <= 0: only the local max is produced (multi-GPU: host/all-reduce finishes)
 };
 
+// small_step.cuh: every stage's argument block (same content run_stage hands the stand-alone kernels) + the CFL kernel's
+struct SmallStepArgs {
+    StageArgs st[4];
+    CflArgs cfl;                  // cfl <= 0: fixed dt (already in scal[SC_DT])
+    int32_t n_stages;
+    uint32_t n_steps;
+};
+
 struct KernelTable {
     const char * name;
     void (*gradients)(const StageArgs &, cudaStream_t);   // viscous runs only
@@ -143,6 +151,8 @@ struct KernelTable {
     // FAST mode only (null in the STRICT table): streaming TENO reconstruction over the compact tables
     void (*recon_stream)(const ReconStreamArgs &, cudaStream_t);
     bool (*stream_supported)(int order, int M, int Q, int basis, int n_slots);
+    // whole steps of a small first-order mesh in one cooperative launch (small_step.cuh); max_blocks <= 0: as many as are resident
+    void (*small_step)(const SmallStepArgs &, int max_blocks, cudaStream_t);
 };
 
 const KernelTable * kernels_strict();

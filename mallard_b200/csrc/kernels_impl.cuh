@@ -18,7 +18,12 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <stdexcept>
+#include <string>
 #include <utility>
+#ifndef MLB_HOST_EMULATION
+#include <cooperative_groups.h>
+#endif
 
 #include "kernel_args.h"
 
@@ -446,10 +451,10 @@ __device__ __forceinline__ void viscous_flux(const StageArgs & a, uint32_t f, ui
 // one Riemann problem; the QT lanes of a face then combine w_q F_q in the reference's q order with warp shuffles (same
 // rounding as the sequential loop) and lane 0 stores.  Twice the parallelism and half the dependent sqrt/div chain per
 // thread of a per-face loop.  QT = 0: one thread per face loops over a run-time Q.
+// (the body takes the global thread index as a parameter: small_step_kernel below walks the faces with a grid-stride loop)
 template <int RS, bool TENO, int QT, bool VISC>
-__global__ void __launch_bounds__(128, MLB_FLUX_MINB) face_flux_kernel(const __grid_constant__ StageArgs a) {
+__device__ __forceinline__ void face_flux_body(const StageArgs & a, const uint32_t gid) {
     constexpr int TPF = QT > 0 ? QT : 1;                 // threads per face (1, 2 or 4: divides the warp)
-    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = gid / TPF < a.g.NF;
     const uint32_t f = valid ? gid / TPF : a.g.NF - 1;   // surplus lanes recompute the last face and do not store
     const int lane_q = gid % TPF;
@@ -534,14 +539,17 @@ __global__ void __launch_bounds__(128, MLB_FLUX_MINB) face_flux_kernel(const __g
     }
     reinterpret_cast<double4 *>(a.AF)[f] = make_double4(fsum[0], fsum[1], fsum[2], fsum[3]);
 }
+template <int RS, bool TENO, int QT, bool VISC>
+__global__ void __launch_bounds__(128, MLB_FLUX_MINB) face_flux_kernel(const __grid_constant__ StageArgs a) {
+    face_flux_body<RS, TENO, QT, VISC>(a, blockIdx.x * blockDim.x + threadIdx.x);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Residual gather + RK update.  One thread per owned cell, no atomics: each cell sums -+ the stored face products in
 // the reference's (Serial back-end) accumulation order, divides by its volume (DivideVolumeFunctor,
 // solver_rhs.cpp:18-42) and applies the stage combination; the last stage also refreshes the primitives.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gather_stage_kernel(const __grid_constant__ StageArgs a) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void gather_stage_body(const StageArgs & a, const uint32_t i) {
     if (i >= a.g.N_owned) return;
     const uint32_t Np = a.g.Npad;
     double k[4];
@@ -592,6 +600,9 @@ __global__ void __launch_bounds__(256) gather_stage_kernel(const __grid_constant
         }
         if (i == 0) { a.scal[SC_T] = a.scal[SC_T] + dt; *a.step_counter += 1ull; }   // solver.cpp:529-530
     }
+}
+__global__ void __launch_bounds__(256) gather_stage_kernel(const __grid_constant__ StageArgs a) {
+    gather_stage_body(a, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -753,13 +764,12 @@ __global__ void __launch_bounds__(RECON_THREADS) teno_recon_kernel(const __grid_
 #endif
 #endif
 #include "teno_generic.cuh"
-#ifndef MLB_HOST_EMULATION           // from here on: atomics, launch syntax
 
 // ---------------------------------------------------------------------------------------------------------------
 // Spectral radius + max + dt — SpectralRadiusFunctor / Solver::calc_dt (solver/solver.cpp:580-742)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) cfl_kernel(const __grid_constant__ CflArgs a) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// spectral radius of cell i (stored as cfl_local before scaling); -1 for i >= N_owned
+__device__ __forceinline__ double spectral_radius_body(const CflArgs & a, const uint32_t i) {
     const uint32_t Np = a.g.Npad;
     double sr = -1.0;
     if (i < a.g.N_owned) {
@@ -802,6 +812,14 @@ __global__ void __launch_bounds__(256) cfl_kernel(const __grid_constant__ CflArg
         if (a.gas.mu > 0.0) sr += 2.0 * geom * visc * fmax(4.0 / 3.0, a.gas.gamma * a.gas.kappa / (a.gas.mu * a.gas.cp)) * a.gas.mu / rho_s;
         a.sr_out[i] = sr;
     }
+    return sr;
+}
+
+#include "small_step.cuh"
+
+#ifndef MLB_HOST_EMULATION           // from here on: shared memory, atomics, launch syntax
+__global__ void __launch_bounds__(256) cfl_kernel(const __grid_constant__ CflArgs a) {
+    const double sr = spectral_radius_body(a, blockIdx.x * blockDim.x + threadIdx.x);
     // block max (NaN never wins: Kokkos::Max joins with `<`)
     __shared__ double red[256];
     red[threadIdx.x] = (sr == sr) ? sr : -1.0;
@@ -959,10 +977,10 @@ static void launch_prims_soa(const GasParams & g, uint32_t n, uint32_t npad, con
 #define MLB_STR(x) MLB_STR2(x)
 #ifdef MLB_STREAM_KERNELS
 static const KernelTable table = {MLB_STR(MLB_KNS), launch_gradients, launch_faces, launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
-                                  launch_prims_soa, recon_supported, stream::launch_stream, stream::stream_supported};
+                                  launch_prims_soa, recon_supported, stream::launch_stream, stream::stream_supported, small::launch_small_step};
 #else
 static const KernelTable table = {MLB_STR(MLB_KNS), launch_gradients, launch_faces, launch_stage, launch_recon, launch_cfl, launch_riemann, launch_prims,
-                                  launch_prims_soa, recon_supported, nullptr, nullptr};
+                                  launch_prims_soa, recon_supported, nullptr, nullptr, small::launch_small_step};
 #endif
 
 #endif  // MLB_HOST_EMULATION

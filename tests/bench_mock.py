@@ -46,7 +46,7 @@ class FakeSolver:
         self._alive()
         assert name == "stats", name
         return np.array([self.launch_count, 1.5, 3.0e8 if self.nc < 100000 else 6.5e3 * self.nc, self.nc, self.n_owned, 1.5 * self.nc, self.n_owned + 100,
-                         self.n_stages, 1.0, 0.1, 0.3, self._replays], dtype=np.float64)
+                         self.n_stages, 1.0, 0.1, 0.3, self._replays, 0.0], dtype=np.float64)
 
     def set_state(self, U, P=None):
         self._alive()

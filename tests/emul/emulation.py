@@ -29,7 +29,8 @@ def fast_available():
 
 def build(variant="strict"):
     src = os.path.join(HERE, "kernel_emulation.cpp")
-    deps = [src] + [os.path.join(ROOT, "mallard_b200", "csrc", f) for f in ("kernels_impl.cuh", "teno_generic.cuh", "kernel_args.h", "mlb_internal.h")]
+    deps = [src] + [os.path.join(ROOT, "mallard_b200", "csrc", f) for f in ("kernels_impl.cuh", "teno_generic.cuh", "small_step.cuh", "stage_plan.h",
+                                                                             "kernel_args.h", "mlb_internal.h")]
     deps.append(os.path.join(ROOT, "mallard_b200", "libmallard_b200.so"))
     so = SO[variant]
     if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
@@ -56,6 +57,10 @@ def lib(variant="strict"):
         L.emu_destroy.argtypes = [C.c_void_p]
         L.emu_force_generic.argtypes = [C.c_void_p, C.c_int]
         L.emu_n_quad.argtypes = [C.c_void_p]
+        L.emu_run.argtypes = [C.c_void_p, C.c_uint, C.c_double, C.c_double, C.c_uint, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.emu_get_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.emu_step_count.restype = C.c_ulonglong
+        L.emu_step_count.argtypes = [C.c_void_p]
         _LIB[variant] = L
     return _LIB[variant]
 
@@ -114,6 +119,21 @@ class EmulatedSolver:
         G = np.zeros((self.mesh.n_cells, 6))
         self._ok(self._L.emu_gradients(self._h, G.ctypes.data_as(C.c_void_p)))
         return G
+
+    def run(self, n_steps, cfl=None, dt=None, small_blocks=0):
+        """n_steps time steps (first-order contexts): the multi-kernel sequence of mlb_run, or - small_blocks > 0 - the phases of the
+        cooperative small-mesh kernel on a grid of that many blocks.  Returns (t, dt of the last step)."""
+        t, d = C.c_double(), C.c_double()
+        self._ok(self._L.emu_run(self._h, int(n_steps), float(cfl or 0.0), float(dt or 0.0), int(small_blocks), C.byref(t), C.byref(d)))
+        return t.value, d.value
+
+    def get_state(self):
+        U = np.zeros((self.mesh.n_cells, 4))
+        self._ok(self._L.emu_get_state(self._h, U.ctypes.data_as(C.c_void_p)))
+        return U
+
+    def step_count(self):
+        return int(self._L.emu_step_count(self._h))
 
     def close(self):
         if self._h:

@@ -44,6 +44,7 @@ using std::fmax; using std::fmin; using std::sqrt; using std::pow; using std::fa
 
 #define MLB_KNS emu
 #include "../../mallard_b200/csrc/kernels_impl.cuh"
+#include "../../mallard_b200/csrc/stage_plan.h"
 
 using namespace mlb;
 
@@ -67,6 +68,13 @@ struct Emu {
     bool teno = false;
     std::vector<double> U, k0, Fc, AF, G, bnd_s;
     int force_generic = 0;
+    // time stepping (first-order contexts): the buffers, scalars and schedule of api.cu's mlb_ctx
+    std::vector<double> Ub[3], kb[4], prim, sr;
+    double scal[SC_COUNT] = {-1.0, 0.0, -1.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    unsigned long long step_counter = 0;
+    double max_val = -1.0;            // stands in for max_bits (the emulation keeps the running maximum as a double)
+    unsigned int blocks_done = 0;
+    int cur = 0;
 };
 
 ReconArgs recon_args(Emu & e) {
@@ -118,9 +126,103 @@ template <int RS> void run_faces(Emu & e, const StageArgs & a) {
     else { if (visc) run_kernel(emu::face_flux_kernel<RS, true, 0, true>, a, grid, 128); else run_kernel(emu::face_flux_kernel<RS, true, 0, false>, a, grid, 128); }
 }
 
+// ---- whole time steps (first order): api.cu's stage_args / cfl_args on the emulation's buffers
+StageArgs step_stage_args(Emu & e, const StagePlan & s) {
+    StageArgs a{};
+    a.g = e.g; a.ph = e.phys; a.Uin = e.Ub[s.in].data(); a.Fc = nullptr; a.AF = e.AF.data(); a.teno = 0;
+    a.scal = e.scal; a.step_counter = &e.step_counter; a.G = nullptr;
+    RkArgs & rk = a.rk;
+    rk.mode = s.mode; rk.n_prev = s.n_prev; rk.last_stage = s.last;
+    rk.base = e.Ub[s.base].data(); rk.out = e.Ub[s.out].data();
+    rk.k_store = e.kb[s.kstore].data();                                  // keep_stage_rhs = true
+    for (int j = 0; j < s.n_prev; j++) { rk.kprev[j] = e.kb[s.kprev[j]].data(); rk.cprev[j] = s.cprev[j]; }
+    rk.c0 = s.c0; rk.c1 = s.c1; rk.coef = s.coef;
+    rk.prim_out = s.last ? e.prim.data() : nullptr;
+    return a;
+}
+CflArgs step_cfl_args(Emu & e, double cfl) {
+    CflArgs a{};
+    a.g = e.g; a.gas = e.gas; a.U = e.Ub[e.cur].data(); a.prim = e.prim.data(); a.sr_out = e.sr.data(); a.scal = e.scal;
+    a.max_bits = reinterpret_cast<long long *>(&e.max_val); a.blocks_done = &e.blocks_done; a.cfl = cfl;
+    return a;
+}
+
+template <int RS> void step_faces_fo(const StageArgs & a) {
+    run_kernel(emu::face_flux_kernel<RS, false, 1, false>, a, (a.g.NF + 127u) / 128u, 128);
+}
+void step_faces(const Emu & e, const StageArgs & a) {
+    switch (e.num.riemann) {
+        case MLB_RIEMANN_RUSANOV: step_faces_fo<MLB_RIEMANN_RUSANOV>(a); break;
+        case MLB_RIEMANN_HLL: step_faces_fo<MLB_RIEMANN_HLL>(a); break;
+        default: step_faces_fo<MLB_RIEMANN_HLLC>(a); break;
+    }
+}
+
+// the multi-kernel sequence of mlb_run: CFL "kernel" (cell loop + max + dt), then per stage face kernel and gather kernel
+void steps_kernel_by_kernel(Emu & e, uint32_t n_steps, double cfl) {
+    const auto plan = make_stage_plan(e.cur, e.num.integrator);
+    for (uint32_t n = 0; n < n_steps; n++) {
+        if (cfl > 0.0) {
+            const CflArgs ca = step_cfl_args(e, cfl);
+            double mx = -1.0;
+            for (uint32_t i = 0; i < e.g.N_owned; i++) { const double sr = emu::spectral_radius_body(ca, i); if (sr == sr) mx = std::fmax(mx, sr); }
+            e.scal[SC_MAX_SR] = mx; e.scal[SC_DT] = cfl / mx; e.scal[SC_CFL] = cfl;      // cfl_kernel's last block, apply_dt
+        }
+        for (const StagePlan & sp : plan) {
+            const StageArgs a = step_stage_args(e, sp);
+            step_faces(e, a);
+            run_kernel(emu::gather_stage_kernel, a, (a.g.N_owned + 255u) / 256u, 256);
+        }
+    }
+}
+
+// the cooperative kernel: phases separated by grid barriers = every thread of the grid finishes a phase before the next one starts
+template <int RS> void steps_small_rs(const SmallStepArgs & p, unsigned blocks) {
+    const uint32_t nthreads = blocks * emu::small::SS_THREADS;
+    const int first = p.cfl.cfl > 0.0 ? 0 : 1, n_phases = 1 + 2 * p.n_stages;
+    for (uint32_t step = 0; step < p.n_steps; step++)
+        for (int ph = first; ph < n_phases; ph++)
+            for (uint32_t tid = 0; tid < nthreads; tid++) emu::small::small_step_phase<RS>(p, ph, tid, nthreads);
+}
+void steps_small(Emu & e, uint32_t n_steps, double cfl, unsigned blocks) {
+    const auto plan = make_stage_plan(e.cur, e.num.integrator);
+    SmallStepArgs p{};
+    for (size_t st = 0; st < plan.size(); st++) p.st[st] = step_stage_args(e, plan[st]);
+    p.cfl = step_cfl_args(e, cfl > 0.0 ? cfl : 0.0);
+    p.n_stages = (int32_t)plan.size(); p.n_steps = n_steps;
+    switch (e.num.riemann) {
+        case MLB_RIEMANN_RUSANOV: steps_small_rs<MLB_RIEMANN_RUSANOV>(p, blocks); break;
+        case MLB_RIEMANN_HLL: steps_small_rs<MLB_RIEMANN_HLL>(p, blocks); break;
+        default: steps_small_rs<MLB_RIEMANN_HLLC>(p, blocks); break;
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+// n_steps time steps of a first-order context from its current state.  cfl > 0: dt from the CFL condition every step, else the fixed
+// dt_fixed.  small_blocks == 0: the multi-kernel sequence of mlb_run; > 0: the cooperative kernel's phases on a grid of that many blocks.
+int emu_run(void * h, unsigned n_steps, double cfl, double dt_fixed, unsigned small_blocks, double * t_out, double * dt_out) {
+    Emu & e = *static_cast<Emu *>(h);
+    try {
+        if (e.teno || e.gas.mu > 0.0) throw std::runtime_error("emu_run: first-order inviscid contexts only");
+        if (e.num.integrator == MLB_INTEGRATOR_FE) throw std::runtime_error("emu_run: SSPRK3 / RK4 only (FE alternates its buffers from step to step)");
+        if (!(cfl > 0.0)) e.scal[SC_DT] = dt_fixed;
+        if (small_blocks) steps_small(e, n_steps, cfl, small_blocks); else steps_kernel_by_kernel(e, n_steps, cfl);
+        if (t_out) *t_out = e.scal[SC_T];
+        if (dt_out) *dt_out = e.scal[SC_DT];
+        return 0;
+    } catch (const std::exception & ex) { emu_err = ex.what(); return 1; }
+}
+// U[nc_ref][4] of the owned cells after emu_run (reference numbering)
+int emu_get_state(void * h, double * U_ref) {
+    Emu & e = *static_cast<Emu *>(h);
+    for (uint32_t i = 0; i < e.P.N_owned; i++)
+        for (int v = 0; v < 4; v++) U_ref[4 * (size_t)e.P.perm_cells[i] + v] = e.Ub[e.cur][4 * (size_t)i + v];
+    return 0;
+}
+unsigned long long emu_step_count(void * h) { return static_cast<Emu *>(h)->step_counter; }
 
 const char * emu_last_error() { return emu_err.c_str(); }
 
@@ -162,6 +264,12 @@ void * emu_create(const mlb_mesh * mesh, const mlb_numerics * num, const mlb_phy
         g.slot_fx = e->teno ? P.slot_fx.data() : nullptr;
         g.face_cl = P.face_cl.data(); g.face_cr = P.face_cr.data(); g.face_slots = P.face_slots.data();
         if (opt.viscous) { g.slot_d = P.slot_d.data(); g.face_d = P.face_d.data(); e->G.assign(6 * (size_t)P.Npad, 0.0); }
+        e->bnd_s.assign(P.Npad, 0.0);
+        for (uint32_t i = 0; i < P.N; i++) e->bnd_s[i] = 2.0 * std::pow(P.cell_vol[i], 1.0 / 2);     // as create_impl (api.cu), solver.cpp:664-665
+        g.bnd_s = e->bnd_s.data();
+        for (auto & b : e->Ub) b.assign(4 * (size_t)P.Npad, 0.0);
+        for (auto & b : e->kb) b.assign(4 * (size_t)P.Npad, 0.0);
+        e->prim.assign(6 * (size_t)P.Npad, 0.0); e->sr.assign(P.Npad, 0.0);
         e->U.assign(4 * (size_t)P.Npad, 0.0); e->k0.assign(4 * (size_t)P.Npad, 0.0);
         e->AF.assign(4 * (size_t)std::max<uint32_t>(P.NFpad, 1), 0.0);
         if (e->teno) e->Fc.assign((size_t)P.n_slots * P.Q * 4 * P.Npad, 0.0);
@@ -180,6 +288,14 @@ int emu_set_state(void * h, const double * U_ref) {
     Emu & e = *static_cast<Emu *>(h);
     for (uint32_t i = 0; i < e.P.N; i++)
         for (int v = 0; v < 4; v++) e.U[4 * (size_t)i + v] = U_ref[4 * (size_t)e.P.perm_cells[i] + v];
+    // the stepping state: mlb_set_state with prim == NULL (primitives_soa_kernel: five primitives + the density plane)
+    e.Ub[e.cur] = e.U;
+    for (uint32_t i = 0; i < e.P.N; i++) {
+        double P5[5];
+        emu::cons_to_prim(e.gas, &e.U[4 * (size_t)i], P5);
+        for (int v = 0; v < 5; v++) e.prim[(size_t)v * e.P.Npad + i] = P5[v];
+        e.prim[5 * (size_t)e.P.Npad + i] = e.U[4 * (size_t)i];
+    }
     return 0;
 }
 

@@ -23,7 +23,7 @@ def _line(stdout):
 def test_default_single_gpu_line_with_its_strong_records(tmp_path):
     """`python bench.py --steps 20 --warmup 5` as the driver runs it: the configs[1] mesh at full size (mesh generation and the
     initial state are the real code), the end-to-end leg, the finite-data leg, the strong-scaling child process."""
-    env = dict(os.environ, MLB_MOCK_STRONG="vortex_16M:40,vortex_64M:5657", MLB_STRONG_BASELINES=str(tmp_path / "live.json"), MLB_EXPERIMENT_NQ="24")
+    env = dict(os.environ, MLB_MOCK_STRONG="vortex_16M:40,vortex_64M:5657", MLB_STRONG_BASELINES=str(tmp_path / "live.json"), MLB_EXPERIMENT_NQ="24", MLB_EXPERIMENT_STEPS="10")
     p = subprocess.run([sys.executable, MOCK, "--gpus", "1", "--steps", "20", "--warmup", "5"], capture_output=True, text=True, env=env, timeout=600)
     assert p.returncode == 0, p.stderr[-3000:]
     d = _line(p.stdout)
@@ -38,7 +38,8 @@ def test_default_single_gpu_line_with_its_strong_records(tmp_path):
     assert "do not fit" in strong[1]["skipped"]                      # 64 M cells on one GPU
     assert json.load(open(tmp_path / "live.json"))["vortex_16M"]["n_gpus"] == 1
     ex = d["experiments"]                                            # configs[4] numerics and configs[3] as worded, one child process each
-    assert [r["workload"].split(":")[0] for r in ex] == ["vortex_viscous", "vortex_mixed"]
+    assert [r["workload"].split(":")[0] for r in ex] == ["vortex_viscous", "vortex_mixed", "small_step"]
+    assert ex[2]["sod"]["n_cells"] == 1000 and ex[2]["wedge"]["cooperative_kernel"]["same_bits_as_the_multi_kernel_path"] is True
     assert ex[0]["n_cells"] == 2 * 24 * 24 and ex[0]["value"] > 0 and ex[0]["inviscid_same_mesh"]["value"] > 0 and ex[0]["finite_fraction_of_cells_after_the_run"] == 1.0
     assert 24 * 24 < ex[1]["n_cells"] < 2 * 24 * 24 and ex[1]["value"] > 0 and "kernels" in ex[1]
 

@@ -1,6 +1,6 @@
 """First run on a B200 of the code paths written after the round-2 GPU budget had been spent ("Verification status on
 hardware"): the generic TENO kernel (basis_order 5-9, other stencil factors), quadrilaterals / mixed meshes under TENO, the viscous
-terms, and the comparisons with reference dumps that were generated after that point.  Their GPU tests live in tests/test_gpu_parity.py behind MLB_RUN_UNVERIFIED=1; their kernels have only been executed through
+terms, the cooperative small-mesh kernel, and the comparisons with reference dumps that were generated after that point.  Their GPU tests live in tests/test_gpu_parity.py behind MLB_RUN_UNVERIFIED=1; their kernels have only been executed through
 the host emulation of the same source (tests/test_kernel_emulation.py).
 
 Here every group runs ONCE in a CHILD pytest process with MLB_RUN_UNVERIFIED=1 and a time limit, so that whatever a never-executed
@@ -26,6 +26,7 @@ GROUPS = {
     "generic_teno_kernel": ("test_generic_teno_kernel_is_bit_identical_to_the_specialised_one or test_teno_orders_5_to_9_and_other_stencil_factors_vs_oracle "
                             "or (test_against_reference_dumps and (teno_legendre_12x10_p5 or teno_legendre_8x7_p2_f15))"),
     "late_reference_fixtures": "test_against_reference_dumps and (teno_bcs_rk4_10x8 or teno_hll_riemann_9x7)",
+    "cooperative_small_mesh_kernel": "test_cooperative_small_mesh_kernel_equals_the_multi_kernel_path",
     "quadrilaterals_under_teno": "test_teno_on_quadrilateral_and_mixed_meshes_is_k_exact or test_first_order_on_a_mixed_mesh_matches_oracle",
     "viscous_terms": ("test_viscous_residual_of_couette_flow or test_decaying_shear_layer_follows_the_diffusion_equation "
                       "or test_viscous_run_on_partitioned_ranks_reproduces_the_single_context_run"),
@@ -67,7 +68,7 @@ def run_group(group, command=None, time_limit=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("group", ["late_reference_fixtures", "quadrilaterals_under_teno", "viscous_terms", "generic_teno_kernel"])   # cheapest first
+@pytest.mark.parametrize("group", ["late_reference_fixtures", "cooperative_small_mesh_kernel", "quadrilaterals_under_teno", "viscous_terms", "generic_teno_kernel"])   # cheapest first
 def test_first_hardware_run_of_paths_written_after_the_gpu_budget(group):
     if os.environ.get("MLB_RUN_UNVERIFIED") == "1":
         pytest.skip("MLB_RUN_UNVERIFIED=1: the gated tests run in-process")

@@ -806,6 +806,68 @@ def test_viscous_run_on_partitioned_ranks_reproduces_the_single_context_run():
         assert np.isfinite(one.get_state()).all() and np.array_equal(one.get_state(), many.state()), recon
 
 
+@UNVERIFIED_ON_HARDWARE
+@pytest.mark.parametrize("fp", ["strict", "fast"])
+@pytest.mark.parametrize("case", ["sod", "wedge", "tri_hll_rk4"])
+def test_cooperative_small_mesh_kernel_equals_the_multi_kernel_path(oracle_mod, monkeypatch, case, fp):
+    """MLB_SMALL_STEP=1: mlb_run executes all steps of a small first-order mesh in ONE cooperative kernel (csrc/small_step.cuh: the
+    bodies of the CFL / face / gather kernels between grid barriers).  Same bits as the replayed multi-kernel step in STRICT mode
+    (and as the oracle), within rounding of FMA contraction in FAST mode; t, dt and the step counter agree; stats[12] proves which
+    path ran.  (tests/test_kernel_emulation.py runs the same phases on the host against the oracle and the reference's dumps.)"""
+    if case == "sod":
+        args, bcs, riemann, integ, cfl, n = ("cartesian", 1000, 1, 1.0, 1.0e-3), SYM4, "HLLC", "SSPRK3", 1.0, 120
+    elif case == "wedge":
+        args, riemann, integ, cfl, n = ("wedge", 150, 50, 4.0, 1.5), "HLLC", "SSPRK3", 1.0, 80
+        bcs = [dict(name="left", type="upt", u=[600.0, 0.0], p=101325.0, T=300.0), dict(name="right", type="p_out", p=101325.0),
+               dict(name="top", type="symmetry"), dict(name="bottom", type="wall_adiabatic")]
+    else:
+        args, bcs, riemann, integ, cfl, n = ("cartesian_tri", 40, 30, 1.0, 0.8), [dict(name=z, type="extrapolation") for z in ("left", "right", "top", "bottom")], "HLL", "RK4", 0.6, 30
+    mesh = mb.Mesh.generate(*args)
+    xy = mesh.arrays["cell_coords"]
+    if case == "sod":
+        rho, p = np.where(xy[:, 0] < 0.5, 1.0, 0.125), np.where(xy[:, 0] < 0.5, 1.0, 0.1)
+        U0 = np.stack([rho, 0 * rho, 0 * rho, p / 0.4], 1)
+    elif case == "wedge":
+        R = 101325.0 / (298.15 * 1.225)
+        rho = np.full(mesh.n_cells, 101325.0 / (R * 300.0))
+        U0 = np.stack([rho, rho * 600.0, 0 * rho, 101325.0 / 0.4 + 0.5 * rho * 600.0 ** 2], 1)
+    else:
+        U0 = _random_smooth_state(xy, np.random.default_rng(3))
+    kw = dict(recon="FO", riemann=riemann, integrator=integ, bcs=bcs)
+    a, b = mb.Solver(mesh, fp_mode=fp, **kw), mb.Solver(mesh, fp_mode=fp, **kw)
+    a.set_state(U0); b.set_state(U0)
+    monkeypatch.delenv("MLB_SMALL_STEP", raising=False)
+    ta = a.run(n, cfl=cfl)
+    monkeypatch.setenv("MLB_SMALL_STEP", "1")
+    tb = b.run(n, cfl=cfl)
+    for blocks in ("1", "5"):                                       # grid-stride loops over fewer blocks than there is work for
+        monkeypatch.setenv("MLB_SMALL_STEP_BLOCKS", blocks)
+        c = mb.Solver(mesh, fp_mode=fp, **kw)
+        c.set_state(U0)
+        tc = c.run(n, cfl=cfl)
+        assert np.array_equal(c.get_state(), b.get_state()) and tc == tb, blocks
+        c.close()
+    monkeypatch.delenv("MLB_SMALL_STEP_BLOCKS", raising=False)
+    monkeypatch.delenv("MLB_SMALL_STEP", raising=False)
+    assert int(a.get("stats")[12]) == 0 and int(b.get("stats")[12]) == n
+    Ua, Ub = a.get_state(), b.get_state()
+    assert np.isfinite(Ua).all() and np.abs(Ua - U0).max() > 0
+    assert a.time()[1] == b.time()[1] == n
+    if fp == "strict":
+        assert np.array_equal(Ua, Ub) and ta == tb
+        so = oracle_mod.Solver(oracle_mod.Mesh.generate(*args), **kw)
+        so.set_state(U0)
+        for _ in range(n):
+            so.take_step(so.calc_dt(cfl))
+        assert gu.field_err(Ub, so.get("U")) <= 1e-12                # (HLLC's TRRS branch: pow() of libm vs CUDA)
+    else:
+        assert gu.field_err(Ub, Ua) <= 1e-12 and abs(ta[0] - tb[0]) <= 1e-12 * ta[0]
+    # continuing with the other path from the cooperative kernel's state: the buffers are left as the multi-kernel step leaves them
+    a.run(9, cfl=cfl); b.run(9, cfl=cfl)
+    assert np.array_equal(a.get_state(), b.get_state()) if fp == "strict" else gu.field_err(b.get_state(), a.get_state()) <= 1e-12
+    a.close(); b.close()
+
+
 def test_device_side_field_ranges_and_nan_count():
     """mlb_field_ranges = max_array / min_array of Solver::do_checks (solver.cpp:434-437; `a > max` / `a < min`, so NaN never
     wins) + the NaN test of check_fields (solver.cpp:470-498), against numpy on the exported state."""

@@ -428,3 +428,79 @@ def test_emulated_decaying_shear_layer_follows_the_diffusion_equation():
         exact = Uw * np.vectorize(erf)(y / np.sqrt(d0 * d0 + 4.0 * nu * t))
         errs.append(np.abs(U[:, 1] / U[:, 0] - exact).max())
     assert errs[0] < 0.02 and errs[1] < errs[0] / 2.5, errs
+
+
+# ---- whole time steps: the multi-kernel sequence of mlb_run and the cooperative small-mesh kernel (csrc/small_step.cuh) ---------------
+WEDGE_BCS = [dict(name="left", type="upt", u=[600.0, 0.0], p=101325.0, T=300.0), dict(name="right", type="p_out", p=101325.0),
+             dict(name="top", type="symmetry"), dict(name="bottom", type="wall_adiabatic")]
+
+
+def _wedge_state(mesh):
+    R = 101325.0 / (298.15 * 1.225)
+    n = mesh.n_cells
+    p, T, u = np.full(n, 101325.0), np.full(n, 300.0), np.full(n, 600.0)
+    rho = p / (R * T)
+    return np.stack([rho, rho * u, 0.0 * rho, rho * (p / (0.4 * rho) + 0.5 * u * u)], 1)
+
+
+@pytest.mark.parametrize("mtype,nx,ny,Lx,Ly,riemann,integ,bcs,cfl,n_steps", [
+    ("cartesian", 200, 1, 1.0, 0.005, "HLLC", "SSPRK3", SYM4, 1.0, 40),            # examples/sod numerics, downsized
+    ("wedge", 30, 10, 4.0, 1.5, "HLLC", "SSPRK3", WEDGE_BCS, 1.0, 60),             # examples/wedge numerics + a wall, downsized
+    ("cartesian_tri", 14, 11, 1.0, 0.8, "HLL", "RK4", EXTRAP4, 0.6, 12),
+    ("cartesian", 24, 9, 2.0, 1.0, "Rusanov", "SSPRK3", SYM4, 0.8, 15)])
+def test_emulated_time_steps_and_the_cooperative_small_mesh_kernel_vs_oracle(oracle_mod, mtype, nx, ny, Lx, Ly, riemann, integ, bcs, cfl, n_steps):
+    """n steps of calc_dt + take_step: the oracle, the emulated multi-kernel sequence of mlb_run (CFL kernel, face kernel, gather / RK kernel
+    per stage) and the phases of the cooperative kernel on grids of 1, 3 and 7 blocks (grid-stride loops, dt published between phases):
+    the same bits, the same time, the same step count."""
+    mesh = mb.Mesh.generate(mtype, nx, ny, Lx, Ly)
+    om = oracle_mod.Mesh.generate(mtype, nx, ny, Lx, Ly)
+    if mtype == "wedge":
+        U0 = _wedge_state(mesh)
+    elif ny == 1:
+        x = mesh.arrays["cell_coords"][:, 0]
+        rho, p = np.where(x < 0.5, 1.0, 0.125), np.where(x < 0.5, 1.0, 0.1)
+        U0 = np.stack([rho, 0 * rho, 0 * rho, p / 0.4], 1)
+    else:
+        U0 = _smooth(mesh.arrays["cell_coords"], np.random.default_rng(3))
+    kw = dict(recon="FO", riemann=riemann, integrator=integ, bcs=bcs)
+    so = oracle_mod.Solver(om, **kw)
+    so.set_state(U0)
+    t = 0.0
+    for _ in range(n_steps):
+        dt = so.calc_dt(cfl)
+        so.take_step(dt)
+        t += dt
+    Uo = so.get("U")
+    assert np.isfinite(Uo).all() and np.abs(Uo - U0).max() > 0
+    for blocks in (0, 1, 3, 7):
+        se = EmulatedSolver(mesh, **kw)
+        se.set_state(U0)
+        te, dte = se.run(n_steps, cfl=cfl, small_blocks=blocks)
+        assert np.array_equal(se.get_state(), Uo), blocks
+        assert te == t and dte == dt and se.step_count() == n_steps, blocks
+    # a fixed dt (cfl <= 0: no CFL phase), continued from where the run above stopped
+    a, b = EmulatedSolver(mesh, **kw), EmulatedSolver(mesh, **kw)
+    a.set_state(Uo); b.set_state(Uo)
+    a.run(5, dt=0.5 * dt); b.run(5, dt=0.5 * dt, small_blocks=2)
+    for _ in range(5):
+        so.take_step(0.5 * dt)
+    assert np.array_equal(a.get_state(), so.get("U")) and np.array_equal(b.get_state(), so.get("U"))
+
+
+@pytest.mark.parametrize("name", ["wedge_30x10", "wedge_wall_30x10", "sod_hll_rk4"])
+def test_emulated_cooperative_kernel_against_the_unmodified_reference_after_many_steps(name):
+    """The reference's own state after 100 / 200 (wedge) and 40 (sod, HLL + RK4) steps (tests/golden, dumped by the unmodified reference):
+    the cooperative kernel's phases reproduce it to 1e-12 of the field scale (bit for bit wherever pow() is not involved)."""
+    meta, g = gu.load(name)
+    mm = meta["mesh"]
+    mesh = mb.Mesh.generate(mm["type"], mm["Nx"], mm["Ny"], mm["Lx"], mm["Ly"])
+    se = EmulatedSolver(mesh, **gu.solver_kwargs(meta))
+    se.set_state(g["U0"])
+    done = 0
+    for k in sorted(int(key[4:].split(":")[0]) for key in g if key.startswith("step") and key.endswith(":U")):
+        n = k + 1 - done
+        se.run(n, cfl=meta["cfl"], small_blocks=3)
+        done += n
+        err = gu.field_err(se.get_state(), g["step%d:U" % k])
+        assert err <= 1e-12, (k, err)
+    assert done >= 40 and se.step_count() == done
