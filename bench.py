@@ -33,6 +33,8 @@ import numpy as np  # noqa: E402
 
 N_STAGES = 3
 REF_SAMPLE = (160, 160)     # ONE bounded CPU sample for both `cpu_baseline` and `--impl reference`: cartesian_tri 160x160 = 51 200 cells
+if os.environ.get("MLB_REF_SAMPLE"):      # (the CPU suite checks the line's format on a smaller sample)
+    REF_SAMPLE = tuple(int(x) for x in os.environ["MLB_REF_SAMPLE"].split("x"))
 ALG_BYTES_STAGE = 7592.0    # TENO p=3 tri, whole stage (reference layout)
 ALG_BYTES_RECON = 7472.0    # of which the reconstruction kernel: A+ 6400, areas 640, ids 320, offsets 20, state 32, geometry 60
 SYM4 = [dict(name=n, type="symmetry") for n in ("left", "right", "top", "bottom")]

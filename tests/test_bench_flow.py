@@ -46,12 +46,12 @@ def test_default_single_gpu_line_with_its_strong_records(tmp_path):
 
 def test_reference_arm_line_matches_the_contract():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "5"],
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, MLB_REF_SAMPLE="48x40"))
     assert p.returncode == 0, p.stderr[-2000:]
     d = _line(p.stdout)
     assert d["impl"] == "reference" and d["warmup"] == 5 and d["steps"] == 2 and d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1 and "160x160" in d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1 and "48x40" in d["cpu_baseline"]["sample"]
 
 
 def _free_port():
@@ -69,7 +69,7 @@ def _launch(world, args, extra_env):
     return [p.communicate(timeout=600) + (p.returncode,) for p in procs]
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [3])
 def test_multi_gpu_line_with_its_strong_records(world, tmp_path):
     """The N > 1 leg as torchrun starts it (one process per rank; gloo instead of NCCL): the weak main line, then the strong records on
     rank-local parts of ONE mesh, efficiency against the base point an earlier run of the series left on the box."""
