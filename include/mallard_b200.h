@@ -171,7 +171,10 @@ int mlb_take_step(mlb_ctx *ctx);
 /* same seam with host buffers: H2D of U, one step, D2H of U (the end-to-end path a host-resident driver pays) */
 int mlb_take_step_host(mlb_ctx *ctx, double cfl /* <=0: keep dt */, double *U_inout, double *dt_out);
 /* ---- Solver::run's loop (solver/solver.cpp:352-373) minus checks/output: n_steps x { calc_dt ; take_step },
- *      device-resident and asynchronous; returns after the last step completed.  cfl <= 0 → fixed dt. */
+ *      device-resident and asynchronous; returns after the last step completed.  cfl <= 0 → fixed dt.
+ *      Launch-bound meshes: a step is captured once and replayed as a CUDA graph (n_steps >= 8); with MLB_SMALL_STEP=1 in the
+ *      environment a first-order run of up to 262 144 cells executes ALL its steps in one cooperative kernel (same results;
+ *      opt-in until measured on hardware, csrc/small_step.cuh). */
 int mlb_run(mlb_ctx *ctx, uint32_t n_steps, double cfl, double *t_out, double *dt_last_out);
 int mlb_get_time(mlb_ctx *ctx, double *t, uint64_t *step);
 
