@@ -276,7 +276,8 @@ def main():
     if a.strong_child and world > 1:      # N > 1, inside the per-rank child processes started by bench_multi.experiment_children()
         import bench_multi
         peak, peak_src = hbm_peak()
-        rec = bench_multi.viscous_strong_child(a, rank, world, local_rank, peak, peak_src)
+        child = bench_multi.native_weak_child if a.child_task == "native_weak" else bench_multi.viscous_strong_child
+        rec = child(a, rank, world, local_rank, peak, peak_src)
         if rank == 0:
             print(STRONG_TAG + json.dumps(rec), flush=True)
         return

@@ -430,42 +430,98 @@ def viscous_strong_child(a, rank, world, local_rank, peak, peak_src):
     return rec
 
 
-def experiment_children(a, rank, world, popen=None):
-    """N > 1: BASELINE configs[4] (viscous, the 64 M-cell mesh where it fits) in CHILD processes, one per rank, with a process group of
-    their own - code that runs on hardware for the first time must not be able to take the main line (or the measured strong-scaling
-    records) with it.  Every rank decides the same way (collective), starts its child, waits for it under the deadline; rank 0 returns
-    the records its child printed."""
+def weak_problem(a, rank, world):
+    """The main line's configuration: every rank owns one nx x ny block of a (nx * world) x ny cartesian_tri mesh, cut in x."""
+    import bench
+    import mallard_b200 as mb
+    gnx = a.nx * world
+    Lx = gnx / float(a.ny)
+    mesh = mb.Mesh.generate("cartesian_tri", gnx, a.ny, Lx, 1.0)
+    xy = mesh.arrays["cell_coords"]
+    part = np.minimum((xy[:, 0] * (world / Lx)).astype(np.int32), world - 1)
+    U0, P0 = bench.riemann2d_state(np.stack([xy[:, 0] / Lx, xy[:, 1]], 1))
+    return mesh, part, U0, P0
+
+
+def native_weak_child(a, rank, world, local_rank, peak, peak_src):
+    """Body of the per-rank child for task `native_weak`: the weak-scaling main line through the library's own NCCL driver (the path whose
+    first 8-GPU run hung, profiles/r02d_8gpu_native_hang.txt), with MLB_COMM_TRACE=1 so that a run that stops says where."""
+    import datetime
+    import torch
+    import torch.distributed as dist
+    import bench
+    import mallard_b200 as mb
+    from mallard_b200.parallel import DistributedSolver
+    os.environ["MLB_COMM_TRACE"] = "1"
+    torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(local_rank)
+    mb.set_host_threads(max(1, bench.host_cores() // world))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=1800))
+    mesh, part, U0, P0 = weak_problem(a, rank, world)
+    ds = DistributedSolver(mesh, part, rank, world, local_rank, native=True, recon="TENO", riemann="HLLC", integrator="SSPRK3", order=3, bcs=bench.SYM4,
+                           fp_mode=a.fp, keep_stage_rhs=False)
+    ds.set_state(U0, P0)
+    run_ = Run(ds.s, ds, world)
+    run_.timed(a.warmup, 0.1)
+    ms = run_.timed(a.steps, 0.1)
+    rec = {"workload": "native_weak: the main line's configuration (cartesian_tri %dx%d per GPU, %d GPUs) through mlb_comm_init / mlb_run_distributed: NCCL inside "
+                       "the library, the step replayed as a CUDA graph" % (a.nx, a.ny, world), "n_cells": mesh.n_cells, "n_gpus": world,
+           "value": mesh.n_cells * bench.N_STAGES * a.steps / (ms * 1e-3), "unit": "cell-updates/s", "ms_per_step": ms / a.steps,
+           "graph_replayed_steps": int(ds.s.get("stats")[11]),
+           "nccl_settings": {k: os.environ.get(k) for k in ("NCCL_GRAPH_REGISTER", "NCCL_NVLS_ENABLE") if os.environ.get(k) is not None}}
+    ds.s.close()
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        pass
+    return rec
+
+
+def experiment_children(a, rank, world, popen=None, task="viscous_strong", start_by=None, time_limit=None, extra_env=None):
+    """N > 1: one CHILD process per rank, with a process group of their own, for code that runs on hardware for the first time - it must not
+    be able to take the main line (or the measured strong-scaling records) with it.  Tasks: `viscous_strong` = BASELINE configs[4] (viscous,
+    the 64 M-cell mesh where it fits); `native_weak` = the main line's configuration through the library's own NCCL driver
+    (mlb_comm_init / mlb_run_distributed) with MLB_COMM_TRACE=1.  Every rank decides the same way (collective), starts its child, waits for
+    it under the time limit; rank 0 returns the records its child printed; the last `[mlb comm]` lines of EVERY rank's child are attached
+    to a record that did not complete (which rank stopped where)."""
     import signal
     import subprocess
     import bench
     elapsed = float(_reduce([time.perf_counter() - T_START], world, "max")[0])
-    if elapsed > EXPERIMENT_START_BY_S:
-        return [{"workload": "viscous_strong", "skipped": "time budget of the bench run (%.0f s elapsed)" % elapsed}]
+    _STATE["children_ok"] = None                # (the same on every rank: decided collectively below)
+    if elapsed > (EXPERIMENT_START_BY_S if start_by is None else start_by):
+        return [{"workload": task, "skipped": "time budget of the bench run (%.0f s elapsed)" % elapsed}]
     left = DEADLINE_S - elapsed - 40.0          # the parent's own watchdog fires at DEADLINE_S: be done before it
-    env = dict(os.environ, MLB_BENCH_ELAPSED="%.1f" % elapsed, MASTER_PORT=str(int(os.environ.get("MASTER_PORT", "29500")) + 23))
+    if time_limit is not None:
+        left = min(left, time_limit)
+    env = dict(os.environ, MLB_BENCH_ELAPSED="%.1f" % elapsed, MASTER_PORT=str(int(os.environ.get("MASTER_PORT", "29500")) + 23 + 2 * len(_STATE.setdefault("tasks", []))))
+    _STATE["tasks"].append(task)                # (every group of children gets a port of its own)
+    env.update(extra_env or {})
     for k in ("TORCHELASTIC_USE_AGENT_STORE", "TORCHELASTIC_RUN_ID", "TORCHELASTIC_RESTART_COUNT", "TORCHELASTIC_MAX_RESTARTS"):
         env.pop(k, None)                        # the children rendezvous among themselves (rank 0's child hosts the store), not through torchrun's agent
-    cmd = [sys.executable, os.path.join(bench.ROOT, "bench.py"), "--strong-child", "--child-task", "viscous_strong", "--gpus", str(world), "--steps", str(a.steps),
-           "--warmup", str(a.warmup), "--fp", a.fp]
-    recs, note, out = [], None, ""
+    cmd = [sys.executable, os.path.join(bench.ROOT, "bench.py"), "--strong-child", "--child-task", task, "--gpus", str(world), "--steps", str(a.steps),
+           "--warmup", str(a.warmup), "--fp", a.fp, "--nx", str(a.nx), "--ny", str(a.ny)]
+    recs, note, out, err = [], None, "", ""
     try:
-        p = (popen or subprocess.Popen)(cmd, stdout=subprocess.PIPE, text=True, env=env, start_new_session=True)
+        p = (popen or subprocess.Popen)(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, start_new_session=True)
     except Exception as ex:
-        return [{"workload": "viscous_strong", "error": "could not start the child process: %s" % str(ex)[:200]}]
+        return [{"workload": task, "error": "could not start the child process: %s" % str(ex)[:200]}]
     _STATE["children"] = [p.pid]                # the watchdog takes them along should it fire
     try:
-        out, _ = p.communicate(timeout=left)
+        out, err = p.communicate(timeout=left)
     except subprocess.TimeoutExpired:
         try:
             os.killpg(p.pid, signal.SIGKILL)
         except Exception:
             p.kill()
         try:
-            out, _ = p.communicate(timeout=30)
+            out, err = p.communicate(timeout=30)
         except Exception:
-            out = ""
-        note = {"workload": "viscous_strong", "aborted": "no result within %.0f s (children killed)" % left}
+            out, err = "", ""
+        note = {"workload": task, "aborted": "no result within %.0f s (children killed)" % left}
     _STATE["children"] = []
+    sys.stderr.write(err or "")                 # the children's log lines belong in this run's log
     for l in (out or "").splitlines():
         if l.startswith(bench.STRONG_TAG):
             try:
@@ -473,7 +529,18 @@ def experiment_children(a, rank, world, popen=None):
             except Exception:
                 pass
     if note is None and p.returncode != 0:
-        note = {"workload": "viscous_strong", "error": "the child process of rank %d ended with code %s" % (rank, p.returncode)}
+        note = {"workload": task, "error": "the child process of rank %d ended with code %s" % (rank, p.returncode)}
+    # did every rank's child finish?  (collective over the PARENTS' group, which is intact whatever the children did)
+    bad = float(_reduce([0.0 if (note is None and (recs or rank != 0)) else 1.0], world, "max")[0])
+    _STATE["children_ok"] = bad == 0
+    if bad > 0:
+        import torch.distributed as dist
+        trace = [l for l in (err or "").splitlines() if l.startswith("[mlb comm]")][-3:] or [l for l in (err or "").splitlines() if l.strip()][-2:]
+        traces = [None] * world
+        dist.all_gather_object(traces, {"rank": rank, "exit_code": p.returncode, "last_lines": trace})
+        if note is None:
+            note = {"workload": task, "error": "the child process of another rank did not finish"}
+        note["children"] = traces
     if note is not None:
         recs.append(note)
     return recs
@@ -590,8 +657,17 @@ def run(a, rank, world, local_rank, workload):
     if strong_recs is not None and not any("error" in r for r in strong_recs):      # (after an error the ranks may have diverged: nothing collective)
         try:
             experiments = experiment_children(a, rank, world)
+            # the library's own NCCL driver on this many GPUs (diagnosis of the round-2 8-GPU hang): NCCL's defaults first; if that does not
+            # come back, once more without graph-time buffer registration and NVLS (neither can matter for 230 kB exchanges and an 8-byte
+            # all-reduce) - the record says which attempt, if any, completed
+            limit = float(os.environ.get("MLB_NATIVE_TRIAL_LIMIT", "80"))
+            nat = experiment_children(a, rank, world, task="native_weak", start_by=560.0, time_limit=limit)
+            experiments += nat
+            if _STATE.get("children_ok") is False:
+                experiments += experiment_children(a, rank, world, task="native_weak", start_by=600.0, time_limit=limit,
+                                                   extra_env={"NCCL_GRAPH_REGISTER": "0", "NCCL_NVLS_ENABLE": "0"})
         except Exception as ex:
-            experiments = [{"workload": "viscous_strong", "error": str(ex)[:300]}]
+            experiments = (experiments or []) + [{"workload": "experiments", "error": str(ex)[:300]}]
     _STATE["done"] = True
     if rank == 0:
         line["strong"] = strong_recs

@@ -207,5 +207,10 @@ if __name__ == "__main__":       # child of tests/test_bench_flow.py: `python te
             time.sleep(float(os.environ.get("MLB_MOCK_PEER_WAIT", "0")))
             return real(name, nq, a, rank, world, *rest)
         bench_multi.strong_record = failing
+    hang = os.environ.get("MLB_MOCK_HANG_TASK")
+    if hang and "--child-task" in sys.argv and sys.argv[sys.argv.index("--child-task") + 1] == hang:      # a child that stops inside NCCL
+        sys.stderr.write("[mlb comm] rank %s/%s: run: capturing a step\n" % (os.environ.get("RANK"), os.environ.get("WORLD_SIZE")))
+        sys.stderr.flush()
+        time.sleep(600)
     sys.argv = ["bench.py"] + sys.argv[1:]
     bench.main()

@@ -89,8 +89,9 @@ def test_multi_gpu_line_with_its_strong_records(world, tmp_path):
     assert strong[0]["halo"]["max_peers"] >= 1 and strong[0]["ghost_layers"] >= 8 and strong[0]["roofline"]["rank"] == "slowest"
     assert json.load(open(live))["vortex_64M"]["n_gpus"] == world
     ex = d["experiments"]                       # BASELINE configs[4]: the largest mesh that fits, viscous, in per-rank child processes with their own group
-    assert len(ex) == 1 and ex[0]["n_cells"] == 12800 and ex[0]["n_gpus"] == world and "Navier-Stokes" in ex[0]["workload"] and ex[0]["value"] > 0
+    assert len(ex) == 2 and ex[0]["n_cells"] == 12800 and ex[0]["n_gpus"] == world and "Navier-Stokes" in ex[0]["workload"] and ex[0]["value"] > 0
     assert ex[0]["halo"]["max_peers"] >= 1 and "verification" in ex[0]
+    assert ex[1]["workload"].startswith("native_weak") and ex[1]["value"] > 0 and ex[1]["n_cells"] == d["config"]["n_cells"]   # the library's own NCCL driver, diagnosed in children
 
 
 def test_a_failing_strong_record_does_not_cost_the_main_line(tmp_path):
@@ -103,3 +104,21 @@ def test_a_failing_strong_record_does_not_cost_the_main_line(tmp_path):
     d = _line(out[0][0])
     assert d["value"] > 0 and d["n_gpus"] == 2
     assert any("error" in r or "aborted" in r for r in d["strong"]), d["strong"]
+
+
+def test_a_hanging_native_driver_child_is_reported_with_every_ranks_last_trace_line(tmp_path):
+    """The diagnostic children of the library's own NCCL driver: a child that does not come back is killed at its time limit, the record
+    carries the last `[mlb comm]` line of EVERY rank's child, the second attempt (NCCL settings changed) follows, and the main line and the
+    records before it are intact."""
+    out = _launch(2, ["--gpus", "2", "--steps", "4", "--warmup", "3", "--nx", "32", "--ny", "32"],
+                  dict(MLB_MOCK_STRONG="vortex_16M:60", MLB_STRONG_BASELINES=str(tmp_path / "live.json"), MLB_BENCH_EXIT_GRACE="3",
+                       MLB_MOCK_HANG_TASK="native_weak", MLB_NATIVE_TRIAL_LIMIT="15"))
+    assert [o[2] for o in out] == [0, 0], [o[1][-1500:] for o in out]
+    d = _line(out[0][0])
+    assert d["value"] > 0 and d["strong"][0]["value"] > 0
+    ex = d["experiments"]
+    assert "Navier-Stokes" in ex[0]["workload"] and ex[0]["value"] > 0
+    hung = [r for r in ex if r.get("workload") == "native_weak"]
+    assert len(hung) == 2 and all("aborted" in r for r in hung)                  # NCCL's defaults, then without graph registration / NVLS
+    assert sorted(c["rank"] for c in hung[0]["children"]) == [0, 1]
+    assert all("capturing a step" in c["last_lines"][-1] for c in hung[0]["children"])
