@@ -502,14 +502,15 @@ def experiment_children(a, rank, world, popen=None, task="viscous_strong", start
         env.pop(k, None)                        # the children rendezvous among themselves (rank 0's child hosts the store), not through torchrun's agent
     cmd = [sys.executable, os.path.join(bench.ROOT, "bench.py"), "--strong-child", "--child-task", task, "--gpus", str(world), "--steps", str(a.steps),
            "--warmup", str(a.warmup), "--fp", a.fp, "--nx", str(a.nx), "--ny", str(a.ny)]
-    recs, note, out, err = [], None, "", ""
+    recs, note, out, err, p = [], None, "", "", None
     try:
         p = (popen or subprocess.Popen)(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, start_new_session=True)
-    except Exception as ex:
-        return [{"workload": task, "error": "could not start the child process: %s" % str(ex)[:200]}]
-    _STATE["children"] = [p.pid]                # the watchdog takes them along should it fire
+    except Exception as ex:                     # (no early return: the collective below needs every rank)
+        note = {"workload": task, "error": "rank %d could not start its child process: %s" % (rank, str(ex)[:200])}
+    _STATE["children"] = [p.pid] if p else []   # the watchdog takes them along should it fire
     try:
-        out, err = p.communicate(timeout=left)
+        if p:
+            out, err = p.communicate(timeout=left)
     except subprocess.TimeoutExpired:
         try:
             os.killpg(p.pid, signal.SIGKILL)
@@ -530,6 +531,7 @@ def experiment_children(a, rank, world, popen=None, task="viscous_strong", start
                 pass
     if note is None and p.returncode != 0:
         note = {"workload": task, "error": "the child process of rank %d ended with code %s" % (rank, p.returncode)}
+    code = p.returncode if p else None
     # did every rank's child finish?  (collective over the PARENTS' group, which is intact whatever the children did)
     bad = float(_reduce([0.0 if (note is None and (recs or rank != 0)) else 1.0], world, "max")[0])
     _STATE["children_ok"] = bad == 0
@@ -537,7 +539,7 @@ def experiment_children(a, rank, world, popen=None, task="viscous_strong", start
         import torch.distributed as dist
         trace = [l for l in (err or "").splitlines() if l.startswith("[mlb comm]")][-3:] or [l for l in (err or "").splitlines() if l.strip()][-2:]
         traces = [None] * world
-        dist.all_gather_object(traces, {"rank": rank, "exit_code": p.returncode, "last_lines": trace})
+        dist.all_gather_object(traces, {"rank": rank, "exit_code": code, "last_lines": trace})
         if note is None:
             note = {"workload": task, "error": "the child process of another rank did not finish"}
         note["children"] = traces
