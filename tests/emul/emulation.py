@@ -47,7 +47,7 @@ def lib(variant="strict"):
         L = C.CDLL(SO[variant])
         L.emu_create.restype = C.c_void_p
         L.emu_create.argtypes = [C.POINTER(_abi.MeshView), C.POINTER(_abi.Numerics), C.POINTER(_abi.Physics), C.POINTER(_abi.Bc), C.c_int, C.c_void_p,
-                                 C.c_int, C.c_int]
+                                 C.c_int, C.c_int, C.c_void_p]
         L.emu_n_owned.argtypes = [C.c_void_p]
         L.emu_n_held.argtypes = [C.c_void_p]
         L.emu_last_error.restype = C.c_char_p
@@ -69,7 +69,8 @@ class EmulatedSolver:
     """The calc_face_values / calc_rhs surface of mallard_b200.Solver, computed by the emulated kernels (fp_mode: see FLAGS)."""
 
     def __init__(self, mesh, recon="FO", riemann="HLLC", integrator="SSPRK3", gas=None, basis="legendre", order=3, factor=2.0, quad_cell_order=0,
-                 quad_face_order=0, bcs=(), teno_fixed=False, renumber="rcm", part=None, rank=0, n_ranks=1, fp_mode="strict"):
+                 quad_face_order=0, bcs=(), teno_fixed=False, renumber="rcm", part=None, rank=0, n_ranks=1, fp_mode="strict", local=None):
+        """local: `mesh` is a rank-local mesh (local_mesh.extract_local / synthetic.jittered_tri_local) and `part` the owners of ITS cells."""
         self.mesh = mesh
         self._L = lib(fp_mode)
         num = mb._numerics(recon, riemann, integrator, basis, order, factor, quad_cell_order, quad_face_order, "strict", renumber, teno_fixed, True)
@@ -87,7 +88,10 @@ class EmulatedSolver:
         self._keep.append(keep)
         pp = None if part is None else np.ascontiguousarray(part, dtype=np.int32)
         self._keep.append(pp)
-        self._h = self._L.emu_create(C.byref(v), C.byref(num), C.byref(phys), cb, len(bcs), None if pp is None else pp.ctypes.data_as(C.c_void_p), rank, n_ranks)
+        c0 = None if local is None else np.ascontiguousarray(local["cell0_nodes"], dtype=np.float64)
+        self._keep.append(c0)
+        self._h = self._L.emu_create(C.byref(v), C.byref(num), C.byref(phys), cb, len(bcs), None if pp is None else pp.ctypes.data_as(C.c_void_p), rank, n_ranks,
+                                     None if c0 is None else c0.ctypes.data_as(C.c_void_p))
         if not self._h:
             raise RuntimeError(self._L.emu_last_error().decode())
         self.n_quad = self._L.emu_n_quad(self._h)

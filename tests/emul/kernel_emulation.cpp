@@ -226,8 +226,9 @@ unsigned long long emu_step_count(void * h) { return static_cast<Emu *>(h)->step
 
 const char * emu_last_error() { return emu_err.c_str(); }
 
+// cell0_nodes != NULL: `mesh` is a rank-local mesh (mlb_create_local): the six node coordinates of the GLOBAL mesh's cell 0
 void * emu_create(const mlb_mesh * mesh, const mlb_numerics * num, const mlb_physics * phys, const mlb_bc * bcs, int n_bcs, const int32_t * part,
-                  int rank, int n_ranks) {
+                  int rank, int n_ranks, const double * cell0_nodes) {
     try {
         std::unique_ptr<Emu> e(new Emu());
         e->num = *num;
@@ -253,6 +254,7 @@ void * emu_create(const mlb_mesh * mesh, const mlb_numerics * num, const mlb_phy
         opt.renumber = num->renumber;
         opt.viscous = e->gas.mu > 0.0;
         opt.part = part; opt.rank = rank; opt.n_ranks = n_ranks;      // a rank's context of a partitioned mesh (ghosts are filled by emu_set_state)
+        if (cell0_nodes) { opt.psi_ref_tri = cell0_nodes; opt.keep_ref_tables = false; }      // as create_impl (api.cu) for mlb_create_local
         preprocess(hm, *num, zones, opt, e->P);
         Prep & P = e->P;
         for (size_t i = 0; i < P.qf_x.size(); i++) { e->phys.qf_x[i] = P.qf_x[i]; e->phys.qf_w[i] = P.qf_w[i]; }

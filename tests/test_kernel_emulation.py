@@ -504,3 +504,34 @@ def test_emulated_cooperative_kernel_against_the_unmodified_reference_after_many
         err = gu.field_err(se.get_state(), g["step%d:U" % k])
         assert err <= 1e-12, (k, err)
     assert done >= 40 and se.step_count() == done
+
+
+@pytest.mark.parametrize("recon,mu", [("TENO", 1.0e-3), ("TENO", 0.0), ("FO", 1.0e-3)])
+def test_emulated_rank_local_contexts_reproduce_the_single_context_residual(recon, mu):
+    """What bench.py's strong-scaling records run at N > 1 (BASELINE configs[3] / [4]): every rank builds its context from ITS PART of the
+    jittered, id-shuffled triangulation only (synthetic.jittered_tri_local -> mlb_create_local: ghost layers, cut faces, global order kept),
+    viscous contexts with their second ghost ring.  Each rank's residual of its own cells equals the single-context residual of the global
+    mesh bit for bit."""
+    from mallard_b200 import synthetic as syn
+    nq, world = 26, 3
+    mesh = syn.jittered_tri(nq, nq, 10.0, 10.0, seed=12345)
+    U0 = syn.isentropic_vortex(mesh.arrays["cell_coords"])
+    kw = dict(recon=recon, riemann="HLLC", integrator="SSPRK3", order=3, bcs=EXTRAP4, teno_fixed=True, gas=_gas(mu))
+    one = EmulatedSolver(mesh, **kw)
+    one.set_state(U0)
+    ref = one.calc_rhs()
+    assert np.isfinite(ref).all()
+    got, n_owned = np.zeros_like(ref), 0
+    for r in range(world):
+        lp = syn.jittered_tri_local(nq, nq, 10.0, 10.0, world, r, seed=12345, layers=8)
+        gids = np.asarray(lp.local["global_ids"], dtype=np.int64)
+        assert np.array_equal(lp.mesh.arrays["cell_coords"], mesh.arrays["cell_coords"][gids])
+        e = EmulatedSolver(lp.mesh, part=lp.part_local, rank=r, n_ranks=world, local=lp.local, **kw)
+        assert e.n_owned == lp.n_owned
+        n_owned += e.n_owned
+        e.set_state(U0[gids])                     # every held cell filled as a completed halo exchange leaves it
+        rhs = e.calc_rhs()                        # local numbering, zeros outside the rank's own cells
+        own = lp.part_local == r
+        assert np.abs(rhs[~own]).max() == 0.0
+        got[gids[own]] = rhs[own]
+    assert n_owned == mesh.n_cells and np.array_equal(got, ref)
