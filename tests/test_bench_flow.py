@@ -112,7 +112,7 @@ def test_a_hanging_native_driver_child_is_reported_with_every_ranks_last_trace_l
     records before it are intact."""
     out = _launch(2, ["--gpus", "2", "--steps", "4", "--warmup", "3", "--nx", "32", "--ny", "32"],
                   dict(MLB_MOCK_STRONG="vortex_16M:60", MLB_STRONG_BASELINES=str(tmp_path / "live.json"), MLB_BENCH_EXIT_GRACE="3",
-                       MLB_MOCK_HANG_TASK="native_weak", MLB_NATIVE_TRIAL_LIMIT="15"))
+                       MLB_MOCK_HANG_TASK="native_weak", MLB_NATIVE_TRIAL_LIMIT="10"))
     assert [o[2] for o in out] == [0, 0], [o[1][-1500:] for o in out]
     d = _line(out[0][0])
     assert d["value"] > 0 and d["strong"][0]["value"] > 0
