@@ -598,7 +598,9 @@ def test_teno_orders_5_to_9_and_other_stencil_factors_vs_oracle(oracle_mod, orde
     Fg, Fo = sg.calc_face_values()[real][:, :, 0], so.calc_face_values()[real][:, :, 0]
     # the higher the order, the worse conditioned the pseudo-inverse rows (entries ~1e6 at p = 9): differences are measured
     # against the field scale in both modes; STRICT is additionally bit-exact wherever pow() is not involved (legendre)
-    if fp == "strict" and basis == "legendre":
+    # (reference-faithful weights, fixed = False: 1 / (SI + eps)^6 is three multiplications on the device and libm pow in the oracle / reference -
+    #  the last ulp of a weight that only the normalised variant divides away; measured on the host emulation: 1e-17 of the field scale)
+    if fp == "strict" and basis == "legendre" and fixed:
         assert np.array_equal(Fg, Fo, equal_nan=True)
     else:
         assert gu.field_err(Fg, Fo) <= (TOL if order <= 5 else 1e-9)
