@@ -61,6 +61,12 @@ def lib(variant="strict"):
         L.emu_get_state.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_step_count.restype = C.c_ulonglong
         L.emu_step_count.argtypes = [C.c_void_p]
+        L.emu_get_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        L.emu_time.restype = C.c_double
+        L.emu_time.argtypes = [C.c_void_p]
+        L.emu_calc_dt.restype = C.c_double
+        L.emu_calc_dt.argtypes = [C.c_void_p, C.c_double]
+        L.emu_get_primitives.argtypes = [C.c_void_p, C.c_void_p]
         _LIB[variant] = L
     return _LIB[variant]
 
@@ -136,6 +142,22 @@ class EmulatedSolver:
         self._ok(self._L.emu_get_state(self._h, U.ctypes.data_as(C.c_void_p)))
         return U
 
+    def get_array(self, name):
+        out = np.zeros(self.mesh.n_cells if name == "cfl_local" else (self.mesh.n_cells, 4))
+        self._ok(self._L.emu_get_array(self._h, name.encode(), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def calc_dt(self, cfl):
+        return float(self._L.emu_calc_dt(self._h, float(cfl)))
+
+    def get_primitives(self):
+        P = np.zeros((self.mesh.n_cells, 5))
+        self._ok(self._L.emu_get_primitives(self._h, P.ctypes.data_as(C.c_void_p)))
+        return P
+
+    def time(self):
+        return float(self._L.emu_time(self._h))
+
     def step_count(self):
         return int(self._L.emu_step_count(self._h))
 
@@ -149,3 +171,88 @@ class EmulatedSolver:
             self.close()
         except Exception:
             pass
+
+
+class EmulatedAsSolver:
+    """mallard_b200.Solver's surface, as far as the gated GPU tests of tests/test_gpu_parity.py use it, computed by the emulated kernels: lets
+    those tests - the very functions, with their tolerances - run on the host before they run on hardware (tests/
+    test_gated_gpu_tests_on_the_emulator.py).  Reads MLB_TENO_GENERIC / MLB_SMALL_STEP / MLB_SMALL_STEP_BLOCKS per call like the library."""
+
+    def __init__(self, mesh, recon="FO", riemann="HLLC", integrator="SSPRK3", gas=None, basis="legendre", order=3, factor=2.0, quad_cell_order=0,
+                 quad_face_order=0, bcs=(), fp_mode="strict", renumber="rcm", teno_fixed=False, keep_stage_rhs=True, device=0, part=None, rank=0,
+                 n_ranks=1, local=None):
+        if part is not None or local is not None:
+            raise NotImplementedError("the emulated Solver is a single context")
+        self.mesh, self.fp_mode = mesh, fp_mode
+        self._e = EmulatedSolver(mesh, recon, riemann, integrator, gas=gas, basis=basis, order=order, factor=factor, quad_cell_order=quad_cell_order,
+                                 quad_face_order=quad_face_order, bcs=bcs, teno_fixed=teno_fixed, renumber=renumber, fp_mode=fp_mode)
+        self.n_quad, self.n_stages = self._e.n_quad, {"FE": 1, "RK4": 4, "SSPRK3": 3}[integrator]
+        self._small_ok = recon == "FO" and integrator != "FE" and not (gas or {}).get("mu", 0.0) > 0      # small_step_eligible (api.cu)
+        self._dirty, self._dt, self._small_steps, self.launch_count = False, -1.0, 0, 0
+
+    def _generic(self):
+        self._e.force_generic(os.environ.get("MLB_TENO_GENERIC") == "1")
+
+    def _current(self):                 # the residual / face-value entry points work on the state the last step left
+        if self._dirty:
+            self._e.set_state(self._e.get_state())
+            self._dirty = False
+
+    def set_state(self, U, P=None):
+        self._e.set_state(U)
+        self._dirty = False
+
+    def calc_face_values(self):
+        self._generic(); self._current()
+        return self._e.calc_face_values()
+
+    def calc_rhs(self):
+        self._generic(); self._current()
+        return self._e.calc_rhs()
+
+    def calc_dt(self, cfl):
+        self._dt = self._e.calc_dt(cfl)
+        if self._dt < 0:
+            raise mb.MallardError("dt negative: %f." % self._dt)
+        return self._dt
+
+    def take_step(self, dt=None):
+        self._generic()
+        self._e.run(1, dt=self._dt if dt is None else dt)
+        self._dirty = True
+
+    def run(self, n_steps, cfl=0.0):
+        self._generic()
+        small = os.environ.get("MLB_SMALL_STEP") == "1" and self._small_ok
+        blocks = (int(os.environ.get("MLB_SMALL_STEP_BLOCKS", "0") or 0) or 4) if small else 0
+        t, dt = self._e.run(n_steps, cfl=cfl if cfl > 0 else None, dt=None if cfl > 0 else self._dt, small_blocks=blocks)
+        self._small_steps += n_steps if small else 0
+        self._dirty, self._dt = True, dt
+        if dt < 0:
+            raise mb.MallardError("dt negative: %f." % dt)
+        return t, dt
+
+    def get_state(self, prim=False, cfl_local=False):
+        U = self._e.get_state()
+        if not prim and not cfl_local:
+            return U
+        out = [U]
+        if prim:
+            out.append(self._e.get_primitives())
+        if cfl_local:
+            out.append(self._e.get_array("cfl_local"))
+        return tuple(out)
+
+    def get(self, name):
+        if name == "stats":
+            return np.array([0.0] * 12 + [float(self._small_steps)])
+        return self._e.get_array(name)
+
+    def time(self):
+        return self._e.time(), self._e.step_count()
+
+    def synchronize(self):
+        pass
+
+    def close(self):
+        self._e.close()

@@ -98,8 +98,9 @@ template <int ORDER, int MP> void run_recon_t(const ReconArgs & a) {
     run_kernel(emu::teno_recon_kernel<ORDER, MP>, a, (a.g.N_recon + emu::RECON_THREADS / 4 - 1) / (emu::RECON_THREADS / 4), emu::RECON_THREADS);
 }
 
-void run_recon(Emu & e) {
-    const ReconArgs a = recon_args(e);
+void run_recon(Emu & e, const double * Uin = nullptr) {
+    ReconArgs a = recon_args(e);
+    if (Uin) a.Uin = Uin;
     const bool spec = !e.force_generic && a.S <= 1 + MAX_SLOTS &&
                       ((a.order == 1 && a.Mp == 6) || (a.order == 2 && a.Mp == 12) || (a.order == 3 && a.Mp == 20) || (a.order == 4 && a.Mp == 30));
     if (spec) {
@@ -129,8 +130,8 @@ template <int RS> void run_faces(Emu & e, const StageArgs & a) {
 // ---- whole time steps (first order): api.cu's stage_args / cfl_args on the emulation's buffers
 StageArgs step_stage_args(Emu & e, const StagePlan & s) {
     StageArgs a{};
-    a.g = e.g; a.ph = e.phys; a.Uin = e.Ub[s.in].data(); a.Fc = nullptr; a.AF = e.AF.data(); a.teno = 0;
-    a.scal = e.scal; a.step_counter = &e.step_counter; a.G = nullptr;
+    a.g = e.g; a.ph = e.phys; a.Uin = e.Ub[s.in].data(); a.Fc = e.teno ? e.Fc.data() : nullptr; a.AF = e.AF.data(); a.teno = e.teno ? 1 : 0;
+    a.scal = e.scal; a.step_counter = &e.step_counter; a.G = e.gas.mu > 0.0 ? e.G.data() : nullptr;
     RkArgs & rk = a.rk;
     rk.mode = s.mode; rk.n_prev = s.n_prev; rk.last_stage = s.last;
     rk.base = e.Ub[s.base].data(); rk.out = e.Ub[s.out].data();
@@ -147,29 +148,32 @@ CflArgs step_cfl_args(Emu & e, double cfl) {
     return a;
 }
 
-template <int RS> void step_faces_fo(const StageArgs & a) {
-    run_kernel(emu::face_flux_kernel<RS, false, 1, false>, a, (a.g.NF + 127u) / 128u, 128);
-}
-void step_faces(const Emu & e, const StageArgs & a) {
+void step_faces(Emu & e, const StageArgs & a) {          // run_stage's launches before the gather: gradients (viscous), face fluxes
+    if (a.G) run_kernel(emu::visc_grad_kernel, a, (a.g.N_recon + 255u) / 256u, 256);
     switch (e.num.riemann) {
-        case MLB_RIEMANN_RUSANOV: step_faces_fo<MLB_RIEMANN_RUSANOV>(a); break;
-        case MLB_RIEMANN_HLL: step_faces_fo<MLB_RIEMANN_HLL>(a); break;
-        default: step_faces_fo<MLB_RIEMANN_HLLC>(a); break;
+        case MLB_RIEMANN_RUSANOV: run_faces<MLB_RIEMANN_RUSANOV>(e, a); break;
+        case MLB_RIEMANN_HLL: run_faces<MLB_RIEMANN_HLL>(e, a); break;
+        default: run_faces<MLB_RIEMANN_HLLC>(e, a); break;
     }
+}
+
+// Solver::calc_dt: the CFL kernel (cell loop + max; the last block's dt = cfl / max)
+double emulated_calc_dt(Emu & e, double cfl) {
+    const CflArgs ca = step_cfl_args(e, cfl);
+    double mx = -1.0;
+    for (uint32_t i = 0; i < e.g.N_owned; i++) { const double sr = emu::spectral_radius_body(ca, i); if (sr == sr) mx = std::fmax(mx, sr); }
+    e.scal[SC_MAX_SR] = mx; e.scal[SC_DT] = cfl / mx; e.scal[SC_CFL] = cfl;
+    return e.scal[SC_DT];
 }
 
 // the multi-kernel sequence of mlb_run: CFL "kernel" (cell loop + max + dt), then per stage face kernel and gather kernel
 void steps_kernel_by_kernel(Emu & e, uint32_t n_steps, double cfl) {
     const auto plan = make_stage_plan(e.cur, e.num.integrator);
     for (uint32_t n = 0; n < n_steps; n++) {
-        if (cfl > 0.0) {
-            const CflArgs ca = step_cfl_args(e, cfl);
-            double mx = -1.0;
-            for (uint32_t i = 0; i < e.g.N_owned; i++) { const double sr = emu::spectral_radius_body(ca, i); if (sr == sr) mx = std::fmax(mx, sr); }
-            e.scal[SC_MAX_SR] = mx; e.scal[SC_DT] = cfl / mx; e.scal[SC_CFL] = cfl;      // cfl_kernel's last block, apply_dt
-        }
+        if (cfl > 0.0) emulated_calc_dt(e, cfl);
         for (const StagePlan & sp : plan) {
             const StageArgs a = step_stage_args(e, sp);
+            if (e.teno) run_recon(e, a.Uin);
             step_faces(e, a);
             run_kernel(emu::gather_stage_kernel, a, (a.g.N_owned + 255u) / 256u, 256);
         }
@@ -206,7 +210,8 @@ extern "C" {
 int emu_run(void * h, unsigned n_steps, double cfl, double dt_fixed, unsigned small_blocks, double * t_out, double * dt_out) {
     Emu & e = *static_cast<Emu *>(h);
     try {
-        if (e.teno || e.gas.mu > 0.0) throw std::runtime_error("emu_run: first-order inviscid contexts only");
+        if ((e.teno || e.gas.mu > 0.0) && small_blocks) throw std::runtime_error("emu_run: the cooperative kernel takes first-order inviscid contexts only");
+        if (e.P.N != e.P.N_owned) throw std::runtime_error("emu_run: single contexts only (no halo exchange in the emulation)");
         if (e.num.integrator == MLB_INTEGRATOR_FE) throw std::runtime_error("emu_run: SSPRK3 / RK4 only (FE alternates its buffers from step to step)");
         if (!(cfl > 0.0)) e.scal[SC_DT] = dt_fixed;
         if (small_blocks) steps_small(e, n_steps, cfl, small_blocks); else steps_kernel_by_kernel(e, n_steps, cfl);
@@ -223,6 +228,33 @@ int emu_get_state(void * h, double * U_ref) {
     return 0;
 }
 unsigned long long emu_step_count(void * h) { return static_cast<Emu *>(h)->step_counter; }
+double emu_time(void * h) { return static_cast<Emu *>(h)->scal[SC_T]; }
+// what mlb_get_array / mlb_get_state export after a step, reference numbering: "rhs0".."rhs3" (stage residuals, keep_stage_rhs), "U_temp"
+// (the reference's solution_vec[1]: the last intermediate stage state), "cfl_local" (spectral radius x dt, [nc_ref])
+int emu_get_array(void * h, const char * name, double * out) {
+    Emu & e = *static_cast<Emu *>(h);
+    const std::string n = name;
+    const auto plan = make_stage_plan(e.cur, e.num.integrator);
+    const double * src = nullptr;
+    if (n.size() == 4 && n.rfind("rhs", 0) == 0 && n[3] >= '0' && n[3] < '4') src = e.kb[n[3] - '0'].data();
+    else if (n == "U_temp") src = e.Ub[plan[plan.size() - 2].out].data();
+    else if (n == "cfl_local") {
+        for (uint32_t i = 0; i < e.P.N_owned; i++) { const double r = e.sr[i]; out[e.P.perm_cells[i]] = r == 0.0 ? 0.0 : e.scal[SC_DT] * r; }
+        return 0;
+    } else { emu_err = "emu_get_array: unknown array " + n; return 1; }
+    for (uint32_t i = 0; i < e.P.N_owned; i++)
+        for (int v = 0; v < 4; v++) out[4 * (size_t)e.P.perm_cells[i] + v] = src[4 * (size_t)i + v];
+    return 0;
+}
+// Solver::calc_dt on the stepping state (sets the dt the next fixed-dt emu_run uses); < 0 as the device reports it
+double emu_calc_dt(void * h, double cfl) { return emulated_calc_dt(*static_cast<Emu *>(h), cfl); }
+// primitives [nc_ref][5] of the stepping state (refreshed by the last stage, Solver::update_primitives)
+int emu_get_primitives(void * h, double * P_ref) {
+    Emu & e = *static_cast<Emu *>(h);
+    for (uint32_t i = 0; i < e.P.N_owned; i++)
+        for (int v = 0; v < 5; v++) P_ref[5 * (size_t)e.P.perm_cells[i] + v] = e.prim[(size_t)v * e.P.Npad + i];
+    return 0;
+}
 
 const char * emu_last_error() { return emu_err.c_str(); }
 
