@@ -13,6 +13,13 @@ per-stage halo exchange of ghost-cell states goes over NCCL.
 triangulation; with torchrun the ONE mesh is split by recursive coordinate bisection: strong scaling); `--recon FO` the
 first-order numerics of examples/sod and examples/wedge; `--fp strict` the bit-faithful mode.
 
+Every default line also carries (each measured AFTER the main line, in child processes that cannot take it with them):
+    strong       the 16 M-cell (BASELINE configs[3]) and 64 M-cell jittered, id-shuffled vortex meshes split over the N GPUs (rank-local ingest),
+                 efficiency against the base point an earlier run of the same series left on the box (bench_multi.py)
+    experiments  N = 1: configs[4] numerics (viscous) and configs[3] as worded (mixed triangles / quadrilaterals) on one GPU, the cooperative
+                 small-mesh kernel on examples/sod and examples/wedge; N > 1: configs[4] itself (viscous, the 64 M-cell mesh where it fits) and
+                 the library's own NCCL driver with its phase trace
+
 `--impl reference` times the UNMODIFIED reference (oracle/_ref, Kokkos OpenMP, FP64) on the host cores on a bounded sample
 of the same workload (same numerics, smaller mesh) — or the oracle port if the reference binary is absent.
 """
