@@ -198,7 +198,9 @@ int mlb_set_rhs_override(mlb_ctx *ctx, const double *rhs /* [nc][4] */);
  *   (u32, reference CSR layout and numbering, numerics/face_reconstruction.h:201-260),
  *   "teno:reconstruction_matrices", "teno:transformed_areas", "teno:integral_psi_target",
  *   "teno:oscillation_indicator" (f64), "teno:poly_indices" (u8[K][2]),
- *   "stats" (f64[8]: launches, preprocess seconds, device bytes, ...).
+ *   "stats" (f64[13]: kernel launches, preprocess seconds, device bytes, held cells, owned cells, faces, reconstructed cells, stages per step,
+ *            host seconds of the stencil search, of the matrices, device seconds of the table build, steps replayed as a CUDA graph, steps run
+ *            inside the cooperative small-mesh kernel).
  * out == NULL → only the byte size is returned in *nbytes. */
 int mlb_get_array(mlb_ctx *ctx, const char *name, void *out, uint64_t *nbytes);
 
