@@ -398,6 +398,22 @@ def experiment_record(task, a, peak, peak_src):
         out = {"value": nc * bench.N_STAGES * a.steps / (ms * 1e-3), "ms_per_step": ms / a.steps, "setup_seconds": setup_s, "device_gb": stats[2] / 1e9,
                "finite_fraction_of_cells_after_the_run": float(np.isfinite(U).all(axis=1).mean()),
                "kernels": {k: {"ms_per_launch": v[0] / max(1, v[1]), "launches": int(v[1])} for k, v in prof.items()}}
+        if leg != "inviscid_same_mesh":
+            # the residual of the initial state through the FAST kernels (timed above) and through the bit-faithful STRICT ones, on the device:
+            # both modes of kernels that have no reference to be compared with must at least agree with each other to rounding
+            try:
+                s.set_state(U0)
+                rf = s.calc_rhs()
+                ss = mb.Solver(mesh, "TENO", "HLLC", "SSPRK3", order=3, bcs=syn.EXTRAP4, fp_mode="strict" if a.fp == "fast" else "fast", teno_fixed=True, **extra)
+                ss.set_state(U0)
+                rs = ss.calc_rhs()
+                ss.close()
+                col = np.abs(rs).max(axis=0)
+                scale = np.maximum(np.maximum(col, 1e-3 * col.max()), 1e-300)
+                out["fast_vs_strict_residual"] = {"max_difference_of_the_field_scale": float((np.abs(rf - rs).max(axis=0) / scale).max()),
+                                                  "finite": bool(np.isfinite(rf).all() and np.isfinite(rs).all())}
+            except Exception as ex:
+                out["fast_vs_strict_residual"] = {"error": str(ex)[:200]}
         s.close()
         if leg == "inviscid_same_mesh":
             rec[leg] = {k: out[k] for k in ("value", "ms_per_step", "kernels")}

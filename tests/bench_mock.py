@@ -55,6 +55,10 @@ class FakeSolver:
         assert P is None or np.asarray(P).shape == (self.nc, 5)
         self._U = U.copy()
 
+    def calc_rhs(self):
+        self._alive()
+        return np.ones((self.nc, 4))
+
     def get_state(self, prim=False):
         self._alive()
         return self._U.copy()

@@ -42,6 +42,7 @@ def test_default_single_gpu_line_with_its_strong_records(tmp_path):
     assert ex[2]["sod"]["n_cells"] == 1000 and ex[2]["wedge"]["cooperative_kernel"]["same_bits_as_the_multi_kernel_path"] is True
     assert ex[0]["n_cells"] == 2 * 24 * 24 and ex[0]["value"] > 0 and ex[0]["inviscid_same_mesh"]["value"] > 0 and ex[0]["finite_fraction_of_cells_after_the_run"] == 1.0
     assert 24 * 24 < ex[1]["n_cells"] < 2 * 24 * 24 and ex[1]["value"] > 0 and "kernels" in ex[1]
+    assert ex[0]["fast_vs_strict_residual"] == {"max_difference_of_the_field_scale": 0.0, "finite": True} and "fast_vs_strict_residual" in ex[1]
 
 
 def test_reference_arm_line_matches_the_contract():
