@@ -196,7 +196,12 @@ def strong_record(name, nq, a, rank, world, device, peak, peak_src, mu=0.0):
     setup_s = time.perf_counter() - t0
     run = Run(s, ds, world)
     run.timed(a.warmup, 0.1)
+    clocks = bench.ClockSampler(device) if rank == 0 else None      # the base point of a strong-scaling series is only as good as its clocks
+    if clocks:
+        clocks.start()
     ms = run.timed(a.steps, 0.1)
+    if clocks:
+        rec["clocks"] = clocks.stop()
     rec.update(value=nc * bench.N_STAGES * a.steps / (ms * 1e-3), unit="cell-updates/s", ms_per_step=ms / a.steps, steps=a.steps, warmup=a.warmup)
     rec["roofline"] = run.recon_roofline(max(2, min(a.steps, 5)), 0.1, bench.N_STAGES, peak, peak_src, bench.ALG_BYTES_RECON)
     if world > 1:
