@@ -636,7 +636,14 @@ def run(a, rank, world, local_rank, workload):
     value = nc * bench.N_STAGES * a.steps / (ms * 1e-3)
     replays = int(s.get("stats")[11])
     ds.set_state(U0, P0)
-    roof = run_.recon_roofline(max(2, min(a.steps, 5)), 0.1, bench.N_STAGES, peak, peak_src, bench.ALG_BYTES_RECON) if a.recon == "TENO" else None
+    roof = None
+    if a.recon == "TENO":       # (per-kernel events under the split-phase driver: never the reason for a missing line - every rank takes the same branch,
+        try:                    #  the reductions inside are the only collectives and come after the last call that can throw)
+            roof = run_.recon_roofline(max(2, min(a.steps, 5)), 0.1, bench.N_STAGES, peak, peak_src, bench.ALG_BYTES_RECON)
+        except mb.MallardError as ex:
+            raise               # a device-side failure: nothing after it can be trusted
+        except Exception as ex:
+            roof = {"error": str(ex)[:200]}
 
     # ---- end to end: per step H2D of the rank's own cells from pinned memory, the step (halo + all-reduce), D2H
     e2e = None
