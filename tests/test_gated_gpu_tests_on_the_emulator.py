@@ -75,3 +75,8 @@ def test_cooperative_small_mesh_kernel(emulated, oracle_mod, monkeypatch, case, 
 def test_reference_dumps_behind_the_gate(emulated, monkeypatch, name, fp):
     monkeypatch.setenv("MLB_RUN_UNVERIFIED", "1")
     gp.test_against_reference_dumps(name, fp)
+
+
+def test_run_from_a_gmsh_file(emulated, tmp_path):
+    """Not gated, but the reader moved behind the C ABI (csrc/mesh_io.cpp) after the GPU suite last ran: the same check with the emulated kernels."""
+    gp.test_mesh_read_from_a_gmsh_file_runs_like_the_same_mesh_from_arrays(tmp_path)
