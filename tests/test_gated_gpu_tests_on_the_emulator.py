@@ -59,6 +59,12 @@ def test_viscous_couette(emulated, mtype, fp):
     gp.test_viscous_residual_of_couette_flow(mtype, fp)
 
 
+@pytest.mark.parametrize("fp", FP)
+@pytest.mark.parametrize("mtype", ["cartesian", "mixed"])
+def test_isothermal_walls(emulated, mtype, fp):
+    gp.test_steady_heat_conduction_between_isothermal_walls(mtype, fp)
+
+
 @pytest.mark.skipif(not FULL, reason="~1 min on the host (MLB_EMULATE_GATED=full); the CPU suite integrates the same problem with a fixed dt in test_kernel_emulation.py")
 def test_decaying_shear_layer(emulated):
     gp.test_decaying_shear_layer_follows_the_diffusion_equation()

@@ -774,6 +774,33 @@ def test_viscous_residual_of_couette_flow(mtype, fp):
 
 
 @UNVERIFIED_ON_HARDWARE
+@pytest.mark.parametrize("fp", ["strict", "fast"])
+@pytest.mark.parametrize("mtype", ["cartesian", "mixed"])
+def test_steady_heat_conduction_between_isothermal_walls(mtype, fp):
+    """MLB_BC_WALL_NOSLIP with T > 0 (isothermal walls): gas at rest, uniform pressure, T linear between a cold and a hot wall - a uniform
+    heat flux, so the viscous part of the residual vanishes in every cell, wall cells included (tests/test_kernel_emulation.py runs the same
+    check, and the exactness of the temperature gradient, on the host emulation)."""
+    from mallard_b200 import synthetic as syn
+    mu, H, L, T0, T1 = 0.05, 1.0, 2.0, 280.0, 340.0
+    mesh = syn.mixed_tri_quad(24, 20, L, H, seed=7, tri_fraction=0.5) if mtype == "mixed" else mb.Mesh.generate(mtype, 24, 20, L, H)
+    bcs = [dict(name="left", type="extrapolation"), dict(name="right", type="extrapolation"), dict(name="bottom", type="wall_noslip", u=[0.0, 0.0], T=T0),
+           dict(name="top", type="wall_noslip", u=[0.0, 0.0], T=T1)]
+    y = mesh.arrays["cell_coords"][:, 1]
+    T = T0 + (T1 - T0) * y / H
+    U0 = _state_from_prim(1.0e5 / (R_GAS * T), np.zeros_like(y), np.zeros_like(y), T)
+    res = []
+    for m in (mu, 0.0):
+        s = mb.Solver(mesh, "FO", "HLLC", "SSPRK3", gas=_gas(m), bcs=bcs, fp_mode=fp)
+        s.set_state(U0)
+        res.append(s.calc_rhs())
+        s.close()
+    dv = res[0] - res[1]
+    flux = mu * (R_GAS * 1.4 / 0.4) / 0.72 * (T1 - T0) / H
+    h = mesh.arrays["cell_volume"].min() ** 0.5
+    assert np.abs(dv[:, :3]).max() == 0.0 and np.abs(dv[:, 3]).max() < 1e-9 * flux / h
+
+
+@UNVERIFIED_ON_HARDWARE
 def test_decaying_shear_layer_follows_the_diffusion_equation():
     """Time-dependent check (a Taylor-Green vortex needs periodic boundaries, which the reference does not have): a low-Mach shear
     layer u(y, 0) = U erf(y / delta0) between slip walls far away diffuses as u = U erf(y / sqrt(delta0^2 + 4 nu t)).  First-order

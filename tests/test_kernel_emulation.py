@@ -535,3 +535,32 @@ def test_emulated_rank_local_contexts_reproduce_the_single_context_residual(reco
         assert np.abs(rhs[~own]).max() == 0.0
         got[gids[own]] = rhs[own]
     assert n_owned == mesh.n_cells and np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("mtype", ["cartesian", "cartesian_tri", "mixed"])
+def test_steady_heat_conduction_between_isothermal_walls(mtype):
+    """MLB_BC_WALL_NOSLIP with T > 0 (isothermal wall): gas at rest, uniform pressure, T linear between a cold and a hot wall.  The heat flux
+    kappa dT/dy is uniform, so the viscous part of the residual vanishes in every cell, wall cells included (the mirror state puts the wall's
+    temperature ON the face), and the gradient of T is exact on quadrilaterals, triangles and jittered mixed meshes."""
+    from mallard_b200 import synthetic as syn
+    mu, H, L, T0, T1 = 0.05, 1.0, 2.0, 280.0, 340.0
+    mesh = syn.mixed_tri_quad(12, 10, L, H, seed=7, tri_fraction=0.5) if mtype == "mixed" else mb.Mesh.generate(mtype, 12, 10, L, H)
+    bcs = [dict(name="left", type="extrapolation"), dict(name="right", type="extrapolation"), dict(name="bottom", type="wall_noslip", u=[0.0, 0.0], T=T0),
+           dict(name="top", type="wall_noslip", u=[0.0, 0.0], T=T1)]
+    y = mesh.arrays["cell_coords"][:, 1]
+    T = T0 + (T1 - T0) * y / H
+    p = 1.0e5
+    U0 = _state_from_prim(p / (R_GAS * T), np.zeros_like(y), np.zeros_like(y), T, R_GAS)
+    res = []
+    for m in (mu, 0.0):
+        se = EmulatedSolver(mesh, "FO", "HLLC", "SSPRK3", gas=_gas(m), bcs=bcs)
+        se.set_state(U0)
+        if m > 0:
+            G = se.gradients()
+            assert np.abs(G[:, 5] - (T1 - T0) / H).max() < 1e-9 * (T1 - T0) / H and np.abs(G[:, :5]).max() < 1e-9
+        res.append(se.calc_rhs())
+    dv = res[0] - res[1]
+    kappa = mu * (R_GAS * 1.4 / 0.4) / 0.72
+    flux = kappa * (T1 - T0) / H                                     # the uniform heat flux; a cell's residual is its (vanishing) divergence
+    h = (mesh.arrays["cell_volume"].min()) ** 0.5
+    assert np.abs(dv[:, :3]).max() == 0.0 and np.abs(dv[:, 3]).max() < 1e-9 * flux / h
