@@ -65,6 +65,12 @@ def test_isothermal_walls(emulated, mtype, fp):
     gp.test_steady_heat_conduction_between_isothermal_walls(mtype, fp)
 
 
+@pytest.mark.parametrize("fp", FP)
+@pytest.mark.parametrize("order,mtype", [(2, "cartesian_tri"), (3, "cartesian")])
+def test_couette_under_teno(emulated, order, mtype, fp):
+    gp.test_couette_flow_under_teno_is_a_steady_state_up_to_viscous_heating(order, mtype, fp)
+
+
 @pytest.mark.skipif(not FULL, reason="~1 min on the host (MLB_EMULATE_GATED=full); the CPU suite integrates the same problem with a fixed dt in test_kernel_emulation.py")
 def test_decaying_shear_layer(emulated):
     gp.test_decaying_shear_layer_follows_the_diffusion_equation()

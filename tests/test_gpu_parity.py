@@ -801,6 +801,29 @@ def test_steady_heat_conduction_between_isothermal_walls(mtype, fp):
 
 
 @UNVERIFIED_ON_HARDWARE
+@pytest.mark.parametrize("fp", ["strict", "fast"])
+@pytest.mark.parametrize("order,mtype", [(2, "cartesian_tri"), (3, "cartesian_tri"), (3, "cartesian")])
+def test_couette_flow_under_teno_is_a_steady_state_up_to_viscous_heating(order, mtype, fp):
+    """The viscous terms behind the TENO face kernel (face_flux_kernel<RS, true, Q, true>; on the device the quadrature lanes of a face are
+    combined with shuffles before lane 0 subtracts the viscous flux): a k-exact reconstruction reproduces plane Couette flow, the inviscid
+    fluxes of this steady Euler solution cancel, what is left is the viscous heating mu (U / H)^2 in the energy equation of every cell that
+    does not touch a wall.  Regular meshes: see tests/test_kernel_emulation.py (same check on the host emulation) for why."""
+    mu, Uw, H, L = 0.05, 3.0, 1.0, 2.0
+    mesh = mb.Mesh.generate(mtype, 14, 12, L, H)
+    bcs = [dict(name="left", type="extrapolation"), dict(name="right", type="extrapolation"), dict(name="bottom", type="wall_noslip", u=[0.0, 0.0]),
+           dict(name="top", type="wall_noslip", u=[Uw, 0.0])]
+    U0 = _cell_averages(mesh, lambda x, y: np.stack([np.full_like(x, 1.2), 1.2 * Uw * y / H, 0.0 * x, 1.0 / 0.4 + 0.6 * (Uw * y / H) ** 2], -1))
+    s = mb.Solver(mesh, "TENO", "HLLC", "SSPRK3", order=order, gas=_gas(mu), bcs=bcs, teno_fixed=True, fp_mode=fp)
+    s.set_state(U0)
+    rhs = s.calc_rhs()
+    s.close()
+    cof = mesh.arrays["cells_of_face"]
+    inner = np.ones(mesh.n_cells, bool)
+    inner[cof[cof[:, 1] < 0, 0]] = False
+    assert np.abs(rhs[inner, :3]).max() < 1e-9 and np.abs(rhs[inner, 3] - mu * (Uw / H) ** 2).max() < 1e-9
+
+
+@UNVERIFIED_ON_HARDWARE
 def test_decaying_shear_layer_follows_the_diffusion_equation():
     """Time-dependent check (a Taylor-Green vortex needs periodic boundaries, which the reference does not have): a low-Mach shear
     layer u(y, 0) = U erf(y / delta0) between slip walls far away diffuses as u = U erf(y / sqrt(delta0^2 + 4 nu t)).  First-order

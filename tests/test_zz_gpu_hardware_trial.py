@@ -29,7 +29,7 @@ GROUPS = {
     "late_reference_fixtures": "test_against_reference_dumps and (teno_bcs_rk4_10x8 or teno_hll_riemann_9x7)",
     "cooperative_small_mesh_kernel": "test_cooperative_small_mesh_kernel_equals_the_multi_kernel_path",
     "quadrilaterals_under_teno": "test_teno_on_quadrilateral_and_mixed_meshes_is_k_exact or test_first_order_on_a_mixed_mesh_matches_oracle",
-    "viscous_terms": ("test_viscous_residual_of_couette_flow or test_decaying_shear_layer_follows_the_diffusion_equation or test_steady_heat_conduction_between_isothermal_walls "
+    "viscous_terms": ("test_viscous_residual_of_couette_flow or test_decaying_shear_layer_follows_the_diffusion_equation or test_steady_heat_conduction_between_isothermal_walls or test_couette_flow_under_teno_is_a_steady_state_up_to_viscous_heating "
                       "or test_viscous_run_on_partitioned_ranks_reproduces_the_single_context_run"),
 }
 # The driver gives the whole `pytest -m gpu` run 1200 s (GPUTEST_r01.json: steps.0.timeout_s) and the measured suite takes ~190 s of them:
