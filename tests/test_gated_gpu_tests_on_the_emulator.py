@@ -66,7 +66,7 @@ def test_isothermal_walls(emulated, mtype, fp):
 
 
 @pytest.mark.parametrize("fp", FP)
-@pytest.mark.parametrize("order,mtype", [(2, "cartesian_tri"), (3, "cartesian")])
+@pytest.mark.parametrize("order,mtype", [(2, "cartesian_tri"), (3, "cartesian"), (5, "cartesian_tri")])
 def test_couette_under_teno(emulated, order, mtype, fp):
     gp.test_couette_flow_under_teno_is_a_steady_state_up_to_viscous_heating(order, mtype, fp)
 

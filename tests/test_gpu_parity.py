@@ -802,7 +802,7 @@ def test_steady_heat_conduction_between_isothermal_walls(mtype, fp):
 
 @UNVERIFIED_ON_HARDWARE
 @pytest.mark.parametrize("fp", ["strict", "fast"])
-@pytest.mark.parametrize("order,mtype", [(2, "cartesian_tri"), (3, "cartesian_tri"), (3, "cartesian")])
+@pytest.mark.parametrize("order,mtype", [(2, "cartesian_tri"), (3, "cartesian_tri"), (3, "cartesian"), (5, "cartesian_tri")])   # p = 5: three quadrature points per face (run-time loop), generic reconstruction kernel
 def test_couette_flow_under_teno_is_a_steady_state_up_to_viscous_heating(order, mtype, fp):
     """The viscous terms behind the TENO face kernel (face_flux_kernel<RS, true, Q, true>; on the device the quadrature lanes of a face are
     combined with shuffles before lane 0 subtracts the viscous flux): a k-exact reconstruction reproduces plane Couette flow, the inviscid
@@ -813,7 +813,7 @@ def test_couette_flow_under_teno_is_a_steady_state_up_to_viscous_heating(order, 
     bcs = [dict(name="left", type="extrapolation"), dict(name="right", type="extrapolation"), dict(name="bottom", type="wall_noslip", u=[0.0, 0.0]),
            dict(name="top", type="wall_noslip", u=[Uw, 0.0])]
     U0 = _cell_averages(mesh, lambda x, y: np.stack([np.full_like(x, 1.2), 1.2 * Uw * y / H, 0.0 * x, 1.0 / 0.4 + 0.6 * (Uw * y / H) ** 2], -1))
-    s = mb.Solver(mesh, "TENO", "HLLC", "SSPRK3", order=order, gas=_gas(mu), bcs=bcs, teno_fixed=True, fp_mode=fp)
+    s = mb.Solver(mesh, "TENO", "HLLC", "SSPRK3", order=order, quad_cell_order=5 if order >= 5 else 0, gas=_gas(mu), bcs=bcs, teno_fixed=True, fp_mode=fp)
     s.set_state(U0)
     rhs = s.calc_rhs()
     s.close()
