@@ -933,16 +933,16 @@ static bool recon_supported(int order, int K, int Mp, int S, int basis) {
     return recon_specialised(order, Mp, S) || generic::generic_supported(order, K, Mp, S);
 }
 static void launch_recon(const ReconArgs & a, cudaStream_t st) {
+    const char * fg = getenv("MLB_TENO_GENERIC");               // test hook: run the generic kernel where a specialised one exists
+    const bool force_generic = fg && fg[0] == '1';
 #ifndef MLB_STREAM_KERNELS
-    if (sstream::strict_stream_supported(a)) {       // bit-faithful AND streaming (teno_strict_stream.cuh); same results as below
+    if (!force_generic && sstream::strict_stream_supported(a)) {       // bit-faithful AND streaming (teno_strict_stream.cuh); same results as below
         if (a.order == 1 && a.Mp == 6) return sstream::launch_strict_stream<1, 6>(a, st);
         if (a.order == 2 && a.Mp == 12) return sstream::launch_strict_stream<2, 12>(a, st);
         if (a.order == 3 && a.Mp == 20) return sstream::launch_strict_stream<3, 20>(a, st);
         if (a.order == 4 && a.Mp == 30) return sstream::launch_strict_stream<4, 30>(a, st);
     }
 #endif
-    const char * fg = getenv("MLB_TENO_GENERIC");               // test hook: run the generic kernel where a specialised one exists
-    const bool force_generic = fg && fg[0] == '1';
     if (force_generic || !recon_specialised(a.order, a.Mp, a.S)) return generic::launch_generic(a, st);
     if (a.order == 1 && a.Mp == 6) launch_recon_t<1, 6>(a, st);
     else if (a.order == 2 && a.Mp == 12) launch_recon_t<2, 12>(a, st);
