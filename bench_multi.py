@@ -695,11 +695,11 @@ def run(a, rank, world, local_rank, workload):
             # the library's own NCCL driver on this many GPUs (diagnosis of the round-2 8-GPU hang): NCCL's defaults first; if that does not
             # come back, once more without graph-time buffer registration and NVLS (neither can matter for 230 kB exchanges and an 8-byte
             # all-reduce) - the record says which attempt, if any, completed
-            limit = float(os.environ.get("MLB_NATIVE_TRIAL_LIMIT", "80"))
-            nat = experiment_children(a, rank, world, task="native_weak", start_by=560.0, time_limit=limit)
+            limit = float(os.environ.get("MLB_NATIVE_TRIAL_LIMIT", "100"))       # global mesh + context + NCCL set-up take ~45 s of it
+            nat = experiment_children(a, rank, world, task="native_weak", start_by=540.0, time_limit=limit)
             experiments += nat
             if _STATE.get("children_ok") is False:
-                experiments += experiment_children(a, rank, world, task="native_weak", start_by=600.0, time_limit=limit,
+                experiments += experiment_children(a, rank, world, task="native_weak", start_by=590.0, time_limit=limit,
                                                    extra_env={"NCCL_GRAPH_REGISTER": "0", "NCCL_NVLS_ENABLE": "0"})
         except Exception as ex:
             experiments = (experiments or []) + [{"workload": "experiments", "error": str(ex)[:300]}]
