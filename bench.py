@@ -172,6 +172,26 @@ STRONG_TAG = "STRONG_RECORD "
 T_START = time.perf_counter()
 
 
+def json_line(obj):
+    """One line of STRICT JSON: a non-finite float (a record of a run that went wrong may hold one) becomes a string, not the bare NaN /
+    Infinity token Python would print and other parsers reject."""
+    import math
+
+    def safe(x):
+        if isinstance(x, np.generic):
+            x = x.item()
+        if isinstance(x, float) and not math.isfinite(x):
+            return repr(x)
+        if isinstance(x, dict):
+            return {str(k): safe(v) for k, v in x.items()}
+        if isinstance(x, (list, tuple)):
+            return [safe(v) for v in x]
+        if isinstance(x, np.ndarray):
+            return [safe(v) for v in x.tolist()]
+        return x
+    return json.dumps(safe(obj), allow_nan=False)
+
+
 def strong_records_in_child(a, popen=subprocess.Popen, min_left=120.0, task="strong"):
     """N = 1: the strong-scaling records (a 16 M-cell mesh: ~100 GB of device memory, minutes of set-up) - and, task by task, the records of
     bench_multi.EXPERIMENTS - run in a CHILD process under a deadline, after the main line has been measured: whatever happens there - a
@@ -273,7 +293,7 @@ def main():
                 "config": {"workload": workload, "sample": info["sample"]},
                 "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
                 "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json_line(line))
         return
 
     import torch
@@ -286,7 +306,7 @@ def main():
         child = bench_multi.native_weak_child if a.child_task == "native_weak" else bench_multi.viscous_strong_child
         rec = child(a, rank, world, local_rank, peak, peak_src)
         if rank == 0:
-            print(STRONG_TAG + json.dumps(rec), flush=True)
+            print(STRONG_TAG + json_line(rec), flush=True)
         return
     if world > 1:
         import bench_multi
@@ -296,7 +316,7 @@ def main():
         torch.cuda.set_device(0)
         mb.set_host_threads(host_cores())
         peak, peak_src = hbm_peak()
-        emit = lambda r: print(STRONG_TAG + json.dumps(r), flush=True)      # noqa: E731
+        emit = lambda r: print(STRONG_TAG + json_line(r), flush=True)      # noqa: E731
         if a.child_task == "strong":
             bench_multi.strong_records(a, 0, 1, 0, peak, peak_src, on_record=emit)
         else:
@@ -470,7 +490,7 @@ def main():
                                 "data-independent") if a.recon == "TENO" else "first-order path (the numerics of examples/sod and examples/wedge)"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "kernels": kernels, "strong": strong,
             "experiments": experiments or None}
-    print(json.dumps(line))
+    print(json_line(line))
 
 
 if __name__ == "__main__":

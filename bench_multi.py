@@ -42,7 +42,8 @@ def _watchdog():
             if _STATE["rank"] == 0 and _STATE["line"] is not None:
                 line = dict(_STATE["line"])
                 line["strong"] = list(_STATE["strong"]) + [{"aborted": "deadline of %.0f s reached before the remaining records finished" % DEADLINE_S}]
-                sys.stdout.write(json.dumps(line) + "\n")
+                import bench
+                sys.stdout.write(bench.json_line(line) + "\n")
                 sys.stdout.flush()
             for pid in _STATE.get("children", []):       # (per-rank child processes of experiment_children)
                 try:
@@ -707,7 +708,7 @@ def run(a, rank, world, local_rank, workload):
     if rank == 0:
         line["strong"] = strong_recs
         line["experiments"] = experiments
-        print(json.dumps(line), flush=True)
+        print(bench.json_line(line), flush=True)
     # the line is out: nothing below may keep the job alive (a peer that failed inside a strong record never reaches the barrier)
     threading.Thread(target=lambda: (time.sleep(float(os.environ.get("MLB_BENCH_EXIT_GRACE", "30"))), os._exit(0)), daemon=True).start()
     try:
