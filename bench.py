@@ -189,7 +189,10 @@ def json_line(obj):
         if isinstance(x, np.ndarray):
             return [safe(v) for v in x.tolist()]
         return x
-    return json.dumps(safe(obj), allow_nan=False)
+    try:
+        return json.dumps(safe(obj), allow_nan=False)
+    except (TypeError, ValueError):          # never the reason for a missing line
+        return json.dumps(obj, default=str)
 
 
 def strong_records_in_child(a, popen=subprocess.Popen, min_left=120.0, task="strong"):
