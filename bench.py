@@ -17,7 +17,8 @@ Every default line also carries (each measured AFTER the main line, in child pro
     strong       the 16 M-cell (BASELINE configs[3]) and 64 M-cell jittered, id-shuffled vortex meshes split over the N GPUs (rank-local ingest),
                  efficiency against the base point an earlier run of the same series left on the box (bench_multi.py)
     experiments  N = 1: configs[4] numerics (viscous) and configs[3] as worded (mixed triangles / quadrilaterals) on one GPU, the cooperative
-                 small-mesh kernel on examples/sod and examples/wedge; N > 1: configs[4] itself (viscous, the 64 M-cell mesh where it fits) and
+                 small-mesh kernel on examples/sod and examples/wedge, and two measured paths so far only in the builder's own runs (STRICT
+                 mode of the main configuration; the first-order numerics on 33.5 M cells); N > 1: configs[4] itself (viscous, the 64 M-cell mesh where it fits) and
                  the library's own NCCL driver with its phase trace
 
 `--impl reference` times the UNMODIFIED reference (oracle/_ref, Kokkos OpenMP, FP64) on the host cores on a bounded sample

@@ -294,7 +294,48 @@ def strong_records(a, rank, world, device, peak, peak_src, on_record=None):
 #      (configs[4]: viscous terms; configs[3] as literally worded: mixed triangles / quadrilaterals under TENO).  Their kernels were
 #      written after the round-2 GPU budget had been spent and are validated by the host emulation of their source
 #      (tests/test_kernel_emulation.py); these records are their measurement.
-EXPERIMENTS = ("vortex_viscous", "vortex_mixed", "small_step")
+EXPERIMENTS = ("vortex_viscous", "vortex_mixed", "small_step", "strict_mode", "first_order_33M")
+
+
+def measured_path_record(task, a, peak):
+    """Two paths that HAVE run on hardware, measured by the builder only so far (profiles/r01j_bench_strict.json, r02a_bench_first_order_33M...):
+    `strict_mode` = the main line's configuration in the bit-faithful floating-point mode; `first_order_33M` = the first-order numerics of
+    examples/sod and examples/wedge on a 33.5 M-cell triangulation (152 B per cell-update: SURVEY 8d).  Same timing as the main line."""
+    import bench
+    import mallard_b200 as mb
+    if task == "strict_mode":
+        nx = ny = int(os.environ.get("MLB_EXPERIMENT_NQ", "1024"))
+        recon, fp, alg, what = "TENO", "strict", bench.ALG_BYTES_STAGE, "examples/riemann_2d (cartesian_tri %dx%d, TENO(legendre,p=3)+HLLC+SSPRK3, cfl 0.1) in STRICT mode" % (nx, ny)
+    else:
+        nx = ny = int(os.environ.get("MLB_EXPERIMENT_NQ", "4096"))
+        recon, fp, alg, what = "FO", a.fp, 152.0, "first order + HLLC + SSPRK3 on cartesian_tri %dx%d, four-quadrant data, cfl 0.1" % (nx, ny)
+    t0 = time.perf_counter()
+    mesh = mb.Mesh.generate("cartesian_tri", nx, ny, 1.0, 1.0)
+    U0, P0 = bench.riemann2d_state(mesh.arrays["cell_coords"])
+    s = mb.Solver(mesh, recon, "HLLC", "SSPRK3", order=3, bcs=bench.SYM4, fp_mode=fp, keep_stage_rhs=False)
+    setup_s = time.perf_counter() - t0
+    s.set_state(U0, P0)
+    s.run(a.warmup, cfl=0.1)
+    s.synchronize()
+    s.event_record(0)
+    s.run(a.steps, cfl=0.1)
+    s.event_record(1)
+    ms = s.event_elapsed_ms(0, 1)
+    s.set_state(U0, P0)
+    s.profile(True)
+    s.run(max(2, min(a.steps, 5)), cfl=0.1)
+    prof = s.profile_read()
+    s.profile(False)
+    nc = mesh.n_cells
+    n_prof = max(2, min(a.steps, 5))
+    stage_ms = sum(v[0] for k, v in prof.items() if k != "cfl") / (n_prof * bench.N_STAGES)
+    rec = {"workload": task + ": " + what, "n_cells": nc, "n_gpus": 1, "fp_mode": fp, "value": nc * bench.N_STAGES * a.steps / (ms * 1e-3), "unit": "cell-updates/s",
+           "ms_per_step": ms / a.steps, "steps": a.steps, "warmup": a.warmup, "setup_seconds": setup_s, "device_gb": s.get("stats")[2] / 1e9,
+           "kernels": {k: {"ms_per_launch": v[0] / max(1, v[1]), "launches": int(v[1])} for k, v in prof.items()},
+           "roofline": {"bound": "hbm", "stage_algorithmic_bytes_per_cell": alg, "stage_achieved": alg * nc / (stage_ms * 1e-3) / 1e9 if stage_ms > 0 else None,
+                        "peak": peak, "unit": "GB/s", "stage_frac": alg * nc / (stage_ms * 1e-3) / 1e9 / peak if stage_ms > 0 else None}}
+    s.close()
+    return rec
 
 
 def small_step_record(a):
@@ -362,6 +403,8 @@ def experiment_record(task, a, peak, peak_src):
     mb.set_host_threads(bench.host_cores())
     if task == "small_step":
         return small_step_record(a)
+    if task in ("strict_mode", "first_order_33M"):
+        return measured_path_record(task, a, peak)
     t0 = time.perf_counter()
     if task == "vortex_viscous":
         nq, mu = int(os.environ.get("MLB_EXPERIMENT_NQ", "1024")), 1.0e-3

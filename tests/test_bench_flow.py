@@ -38,7 +38,8 @@ def test_default_single_gpu_line_with_its_strong_records(tmp_path):
     assert "do not fit" in strong[1]["skipped"]                      # 64 M cells on one GPU
     assert json.load(open(tmp_path / "live.json"))["vortex_16M"]["n_gpus"] == 1
     ex = d["experiments"]                                            # configs[4] numerics and configs[3] as worded, one child process each
-    assert [r["workload"].split(":")[0] for r in ex] == ["vortex_viscous", "vortex_mixed", "small_step"]
+    assert [r["workload"].split(":")[0] for r in ex] == ["vortex_viscous", "vortex_mixed", "small_step", "strict_mode", "first_order_33M"]
+    assert ex[3]["fp_mode"] == "strict" and ex[3]["roofline"]["stage_frac"] > 0 and ex[4]["n_cells"] == 2 * 24 * 24 and ex[4]["kernels"]["face_flux_fo"]["launches"] > 0
     assert ex[2]["sod"]["n_cells"] == 1000 and ex[2]["wedge"]["cooperative_kernel"]["same_bits_as_the_multi_kernel_path"] is True
     assert ex[0]["n_cells"] == 2 * 24 * 24 and ex[0]["value"] > 0 and ex[0]["inviscid_same_mesh"]["value"] > 0 and ex[0]["finite_fraction_of_cells_after_the_run"] == 1.0
     assert 24 * 24 < ex[1]["n_cells"] < 2 * 24 * 24 and ex[1]["value"] > 0 and "kernels" in ex[1]
