@@ -221,6 +221,13 @@ int mlb_partition(const mlb_mesh *mesh, int32_t n_parts, int32_t *part_out /* [n
 /* the same recursive coordinate bisection from the centroids alone (a rank that holds only its part of the mesh can still
  * compute the global partition: 16 bytes per cell) */
 int mlb_partition_coords(uint64_t n_cells, const double *cell_xy /* [n_cells][2] */, int32_t n_parts, int32_t *part_out);
+/* Graph partition: multilevel recursive bisection (heavy-edge matching, greedy graph growing, Fiduccia-Mattheyses refinement) of the
+ * cell-face dual graph - no coordinates involved; part sizes are exactly those of mlb_partition (load balance is identical, what
+ * differs is where the cuts run: shorter on domains that are not convex).  Deterministic and independent of the number of host
+ * threads, so every rank can compute it for itself.  mlb_partition_graph takes the graph from mesh->cells_of_face (cut faces, -2, and
+ * boundary faces, -1, carry no edge); _csr takes any symmetric adjacency structure. */
+int mlb_partition_graph(const mlb_mesh *mesh, int32_t n_parts, int32_t *part_out /* [nc] */);
+int mlb_partition_graph_csr(uint32_t n, const uint64_t *xadj /* [n+1] */, const uint32_t *adj, int32_t n_parts, int32_t *part_out);
 int mlb_create_partitioned(mlb_ctx **out, const mlb_mesh *mesh, const int32_t *part, const mlb_numerics *numerics,
                            const mlb_physics *physics, const mlb_bc *bcs, int32_t n_bcs, const mlb_parallel *parallel);
 /* Rank-local ingest: the context is created from THIS RANK'S PART of the mesh only - its own cells plus enough layers of ghost

@@ -12,7 +12,7 @@ import numpy as np
 from . import _abi
 from ._abi import BASIS, BC, FP, INTEGRATOR, MESH, RECON, RENUMBER, RIEMANN, build, lib  # noqa: F401
 
-__all__ = ["Mesh", "Solver", "Plan", "riemann_flux", "compute_primitives", "partition", "partition_coords", "comm_unique_id",
+__all__ = ["Mesh", "Solver", "Plan", "riemann_flux", "compute_primitives", "partition", "partition_coords", "partition_graph", "comm_unique_id",
            "set_host_threads", "build", "lib"]
 COMM_ID_BYTES = 128
 
@@ -185,6 +185,23 @@ def partition_coords(cell_xy, n_parts):
     xy = np.ascontiguousarray(cell_xy, dtype=np.float64).reshape(-1, 2)
     part = np.empty(xy.shape[0], dtype=np.int32)
     if lib().mlb_partition_coords(xy.shape[0], _ptr(xy), n_parts, _ptr(part)):
+        raise MallardError(_last_error())
+    return part
+
+
+def partition_graph(mesh, n_parts, xadj=None, adj=None):
+    """Graph partition (multilevel recursive bisection of the cell-face dual graph, csrc/partition_graph.cpp): no coordinates involved,
+    part sizes identical to `partition`'s.  mesh=None: partition the symmetric CSR graph (xadj [n+1] uint64, adj uint32)."""
+    if mesh is None:
+        xadj = np.ascontiguousarray(xadj, dtype=np.uint64)
+        adj = np.ascontiguousarray(adj, dtype=np.uint32)
+        part = np.empty(len(xadj) - 1, dtype=np.int32)
+        if lib().mlb_partition_graph_csr(len(xadj) - 1, _ptr(xadj), _ptr(adj), n_parts, _ptr(part)):
+            raise MallardError(_last_error())
+        return part
+    v, keep = mesh.view()
+    part = np.empty(mesh.n_cells, dtype=np.int32)
+    if lib().mlb_partition_graph(C.byref(v), n_parts, _ptr(part)):
         raise MallardError(_last_error())
     return part
 

@@ -91,6 +91,8 @@ SYMBOLS = {
     "mlb_partition": (C.c_int, [C.POINTER(MeshView), I32, VP]),
     "mlb_create_partitioned": (C.c_int, [C.POINTER(VP), C.POINTER(MeshView), VP, C.POINTER(Numerics), C.POINTER(Physics), C.POINTER(Bc), I32, C.POINTER(Parallel)]),
     "mlb_partition_coords": (C.c_int, [U64, VP, I32, VP]),
+    "mlb_partition_graph": (C.c_int, [C.POINTER(MeshView), I32, VP]),
+    "mlb_partition_graph_csr": (C.c_int, [U32, VP, VP, I32, VP]),
     "mlb_create_local": (C.c_int, [C.POINTER(VP), C.POINTER(MeshView), VP, C.POINTER(LocalMesh), C.POINTER(Numerics), C.POINTER(Physics), C.POINTER(Bc), I32, C.POINTER(Parallel)]),
     "mlb_comm_unique_id": (C.c_int, [VP]),
     "mlb_comm_init": (C.c_int, [VP, VP]),

@@ -1476,6 +1476,27 @@ int mlb_partition(const mlb_mesh * mesh, int32_t n_parts, int32_t * part_out) {
     API_END(none)
 }
 
+// Graph partition (partition_graph.cpp): multilevel recursive bisection of the cell-face dual graph, no coordinates involved
+int mlb_partition_graph_csr(uint32_t n, const uint64_t * xadj, const uint32_t * adj, int32_t n_parts, int32_t * part_out) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!xadj || (!adj && xadj[n]) || !part_out || n_parts < 1 || n > 0xFFFFFFFEu) throw std::runtime_error("mlb_partition_graph_csr: bad argument");
+    for (uint32_t v = 0; v < n; v++) if (xadj[v + 1] < xadj[v]) throw std::runtime_error("mlb_partition_graph_csr: xadj must be non-decreasing");
+    graph_partition(n, xadj, adj, n_parts, part_out);
+    API_END(none)
+}
+
+int mlb_partition_graph(const mlb_mesh * mesh, int32_t n_parts, int32_t * part_out) {
+    mlb_ctx * none = nullptr;
+    API_BEGIN0(none)
+    if (!mesh || !mesh->cells_of_face || !part_out || n_parts < 1) throw std::runtime_error("mlb_partition_graph: bad argument");
+    std::vector<uint64_t> xadj;
+    std::vector<uint32_t> adj;
+    dual_graph(mesh->n_cells, mesh->n_faces, mesh->cells_of_face, xadj, adj);
+    graph_partition(mesh->n_cells, xadj.data(), adj.data(), n_parts, part_out);
+    API_END(none)
+}
+
 // ---- stateless kernels -------------------------------------------------------------------------------------------
 int mlb_riemann_flux(int32_t device, int32_t riemann, int32_t fp_mode, uint64_t n, const double * n_unit, const double * L,
                      const double * R, double gamma, double * flux) {

@@ -38,6 +38,11 @@ void host_mesh_from_cells(HostMesh & m, uint32_t n_nodes, const double * node_xy
                           uint32_t n_edges, const uint32_t * edge_nodes, const int32_t * edge_tags, uint32_t n_names, const int32_t * name_tags,
                           const char * const * names);
 
+// partition_graph.cpp: multilevel recursive bisection of a graph in CSR form (unit weights), n_parts parts of the sizes recursive
+// coordinate bisection cuts; deterministic, thread-count independent
+void graph_partition(uint32_t n, const uint64_t * xadj, const uint32_t * adj, int32_t n_parts, int32_t * part_out);
+void dual_graph(uint32_t n_cells, uint32_t n_faces, const int32_t * cells_of_face, std::vector<uint64_t> & xadj, std::vector<uint32_t> & adj);
+
 // ---------------------------------------------------------------------------------------------------------------
 // Gas constants (physics/physics.cpp:69-73)
 // ---------------------------------------------------------------------------------------------------------------

@@ -185,6 +185,100 @@ def test_partition_is_balanced_and_deterministic():
     assert np.all(mb.partition(mesh, 1) == 0)
 
 
+def _edge_cut(mesh, part):
+    cof = mesh.arrays["cells_of_face"].reshape(-1, 2)
+    m = (cof[:, 0] >= 0) & (cof[:, 1] >= 0)
+    return int((part[cof[m, 0]] != part[cof[m, 1]]).sum())
+
+
+def _n_components(n, pairs):
+    """connected components of an undirected graph given as an [m][2] edge list (union-find)"""
+    parent = np.arange(n)
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+    for a, b in pairs:
+        ra, rb = find(a), find(b)
+        if ra != rb:
+            parent[ra] = rb
+    return len({find(i) for i in range(n)})
+
+
+def test_graph_partition_is_balanced_deterministic_and_cuts_about_as_few_faces_as_the_coordinate_bisection():
+    """mlb_partition_graph (csrc/partition_graph.cpp; north_star: "graph-partitioned"): multilevel recursive bisection of the cell-face dual
+    graph.  The part sizes are exactly the coordinate bisection's, the result does not depend on the number of host threads, every part of
+    these (convex) meshes is connected, and the cut is within 20 % of the straight cuts coordinate bisection makes on them - and shorter
+    where a part count that is no power of two makes coordinate bisection cut 1 : 2."""
+    from mallard_b200 import synthetic as syn
+    meshes = [mb.Mesh.generate("cartesian_tri", 48, 32, 3.0, 2.0), syn.jittered_tri(40, 40, 10.0, 10.0, seed=7), mb.Mesh.generate("wedge", 60, 20, 4.0, 1.5)]
+    for mesh in meshes:
+        cof = mesh.arrays["cells_of_face"].reshape(-1, 2)
+        inner = cof[(cof[:, 0] >= 0) & (cof[:, 1] >= 0)]
+        for n in (2, 3, 4, 8):
+            mb.set_host_threads(4)
+            pg = mb.partition_graph(mesh, n)
+            mb.set_host_threads(1)
+            assert np.array_equal(pg, mb.partition_graph(mesh, n))
+            pr = mb.partition(mesh, n)
+            assert np.array_equal(np.bincount(pg, minlength=n), np.bincount(pr, minlength=n))
+            assert _edge_cut(mesh, pg) <= 1.2 * _edge_cut(mesh, pr) + 4
+            for r in range(n):
+                ids = np.flatnonzero(pg == r)
+                loc = -np.ones(mesh.n_cells, dtype=np.int64)
+                loc[ids] = np.arange(len(ids))
+                e = inner[(pg[inner[:, 0]] == r) & (pg[inner[:, 1]] == r)]
+                assert _n_components(len(ids), loc[e]) == 1
+        assert _edge_cut(mesh, mb.partition_graph(mesh, 3)) <= _edge_cut(mesh, mb.partition(mesh, 3))
+    mb.set_host_threads(os.cpu_count() or 1)
+    assert np.all(mb.partition_graph(meshes[0], 1) == 0)
+
+
+def test_graph_partition_follows_the_connectivity_not_the_coordinates():
+    """A domain folded like a U (two 40 x 10 strips of quadrilaterals joined at one end, lying on top of each other in the coordinates a
+    bisection would look at): the graph partitioner, given the CSR graph alone, cuts the 80 x 10 channel across - 10 edges per cut -
+    wherever it is folded; degenerate inputs (no edges, isolated vertices, more parts than vertices) keep the size contract."""
+    nx, ny = 80, 10
+    idx = np.arange(nx * ny).reshape(nx, ny)
+    pairs = np.concatenate([np.stack([idx[:-1].ravel(), idx[1:].ravel()], 1), np.stack([idx[:, :-1].ravel(), idx[:, 1:].ravel()], 1)])
+    both = np.concatenate([pairs, pairs[:, ::-1]])
+    both = both[np.lexsort((both[:, 1], both[:, 0]))]
+    xadj = np.concatenate([[0], np.cumsum(np.bincount(both[:, 0], minlength=nx * ny))]).astype(np.uint64)
+    for n in (2, 4):
+        part = mb.partition_graph(None, n, xadj=xadj, adj=both[:, 1])
+        assert np.bincount(part, minlength=n).tolist() == [nx * ny // n] * n
+        assert int((part[pairs[:, 0]] != part[pairs[:, 1]]).sum()) == ny * (n - 1)
+    # no edges at all / more parts than vertices: sizes as the coordinate bisection would make them
+    lonely = mb.partition_graph(None, 3, xadj=np.zeros(8, dtype=np.uint64), adj=np.zeros(0, dtype=np.uint32))
+    assert sorted(np.bincount(lonely, minlength=3).tolist()) == [2, 2, 3]
+    tiny = mb.partition_graph(None, 4, xadj=np.array([0, 1, 2], dtype=np.uint64), adj=np.array([1, 0], dtype=np.uint32))
+    assert len(tiny) == 2 and set(tiny.tolist()) <= {0, 1, 2, 3}
+    with pytest.raises(mb.MallardError):
+        mb.partition_graph(None, 2, xadj=np.array([0, 1], dtype=np.uint64), adj=np.array([5], dtype=np.uint32))
+
+
+def test_graph_partition_drives_a_partitioned_plan():
+    """any partition vector is a valid input of the preprocessor: the plans of a graph-partitioned mesh own every cell exactly once and
+    announce halos that are each other's mirror image"""
+    mesh = mb.Mesh.generate("cartesian_tri", 30, 20, 3.0, 2.0)
+    n = 3
+    part = mb.partition_graph(mesh, n)
+    owned = np.zeros(mesh.n_cells, dtype=np.int64)
+    for r in range(n):
+        plan = mb.Plan(mesh, "TENO", order=3, bcs=SYM4, fp_mode="fast", part=part, rank=r, n_ranks=n)
+        perm = plan.get("perm_cells")
+        owned[perm[:plan.N_owned]] += 1
+        assert (part[perm[:plan.N_owned]] == r).all()
+        peers, counts, ids = plan.get("halo_peers"), plan.get("halo_recv_counts"), plan.get("halo_recv_ids")
+        off = 0
+        for p, c in zip(peers, counts):
+            assert (part[ids[off:off + int(c)]] == p).all()
+            off += int(c)
+    assert (owned == 1).all()
+
+
 @pytest.mark.parametrize("order", [1, 2, 3])
 def test_streaming_tables_are_the_reference_tables_compacted(order):
     """FAST mode streams compact tables (mallard_b200/csrc/teno_stream.cuh): rows 1..K-1 x columns 1..M-1 of every

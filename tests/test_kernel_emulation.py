@@ -272,13 +272,15 @@ def test_zero_viscosity_is_the_inviscid_path_bit_for_bit(oracle_mod):
 
 
 @pytest.mark.parametrize("recon,mu,order,mtype", [("FO", 0.0, 3, "wedge"), ("FO", 0.02, 3, "cartesian_tri"), ("TENO", 0.0, 3, "cartesian_tri"),
-                                                  ("TENO", 0.02, 2, "cartesian_tri"), ("TENO", 0.0, 5, "cartesian_tri"), ("TENO", 0.01, 2, "mixed")])
+                                                  ("TENO", 0.02, 2, "cartesian_tri"), ("TENO", 0.0, 5, "cartesian_tri"), ("TENO", 0.01, 2, "mixed"),
+                                                  ("TENO", 0.0, 3, "cartesian_tri:graph"), ("TENO", 0.02, 2, "mixed:graph")])
 def test_emulated_rank_contexts_reproduce_the_single_context_residual(recon, mu, order, mtype):
     """Partitioned contexts (owned cells + the ghost rings the preprocessor decides to hold: one ring for first order, the stencil
     reach for TENO, one more ring for the least-squares gradients of viscous runs) with every held cell filled as a completed halo
     exchange leaves it: every rank's residual of its own cells equals the single-context residual bit for bit - specialised and
     generic kernels, quadrilaterals, viscous terms."""
     from mallard_b200 import synthetic as syn
+    mtype, _, partitioner = mtype.partition(":")          # ":graph" = cut by mlb_partition_graph instead of the coordinate bisection
     if mtype == "mixed":
         mesh = syn.mixed_tri_quad(14, 12, 3.0, 2.0, seed=4, tri_fraction=0.5)
     else:
@@ -290,7 +292,7 @@ def test_emulated_rank_contexts_reproduce_the_single_context_residual(recon, mu,
     one.set_state(U0)
     ref = one.calc_rhs()
     n_ranks = 3
-    part = mb.partition(mesh, n_ranks)
+    part = mb.partition_graph(mesh, n_ranks) if partitioner == "graph" else mb.partition(mesh, n_ranks)
     got = np.zeros_like(ref)
     held = []
     for r in range(n_ranks):

@@ -28,7 +28,8 @@ def _worker(rank, world, port, recon, out_dir):
     try:
         mesh = mb.Mesh.generate("cartesian_tri", 14, 10, 2.0, 1.0)
         nc = mesh.n_cells
-        part = mb.partition(mesh, world)
+        recon, _, partitioner = recon.partition(":")
+        part = mb.partition_graph(mesh, world) if partitioner == "graph" else mb.partition(mesh, world)
         plan = mb.Plan(mesh, recon, order=2, bcs=SYM4, part=part, rank=rank, n_ranks=world)
         perm = plan.get("perm_cells")
         owned, ghosts = perm[:plan.N_owned], perm[plan.N_owned:plan.N]
@@ -62,10 +63,10 @@ def _worker(rank, world, port, recon, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,recon", [(2, "FO"), (2, "TENO"), (3, "TENO")])
+@pytest.mark.parametrize("world,recon", [(2, "FO"), (2, "TENO"), (3, "TENO"), (3, "TENO:graph")])
 def test_halo_plan_and_exchange_over_gloo(tmp_path, world, recon):
     mp.spawn(_worker, args=(world, _free_port(), recon, str(tmp_path)), nprocs=world, join=True)
     got = [tuple(int(x) for x in open(tmp_path / ("ok%d" % r)).read().split()) for r in range(world)]
     assert sum(n for n, _ in got) == 2 * 14 * 10 and all(g > 0 for _, g in got)
-    if recon == "TENO":   # stencil halos are several rings deep, first-order halos one ring
+    if recon.startswith("TENO"):   # stencil halos are several rings deep, first-order halos one ring
         assert min(g for _, g in got) > 14
