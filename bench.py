@@ -18,8 +18,9 @@ Every default line also carries (each measured AFTER the main line, in child pro
                  efficiency against the base point an earlier run of the same series left on the box (bench_multi.py)
     experiments  N = 1: configs[4] numerics (viscous) and configs[3] as worded (mixed triangles / quadrilaterals) on one GPU, the cooperative
                  small-mesh kernel on examples/sod and examples/wedge, and two measured paths so far only in the builder's own runs (STRICT
-                 mode of the main configuration; the first-order numerics on 33.5 M cells); N > 1: configs[4] itself (viscous, the 64 M-cell mesh where it fits) and
-                 the library's own NCCL driver with its phase trace
+                 mode of the main configuration; the first-order numerics on 33.5 M cells); N > 1: configs[4] itself (viscous, the 64 M-cell mesh where it fits), the 16 M-cell
+                 mesh cut by the graph partitioner (mlb_partition_graph_csr) next to its coordinate-bisection `strong` record, and the library's own
+                 NCCL driver with its phase trace
 
 `--impl reference` times the UNMODIFIED reference (oracle/_ref, Kokkos OpenMP, FP64) on the host cores on a bounded sample
 of the same workload (same numerics, smaller mesh) — or the oracle port if the reference binary is absent.
@@ -307,7 +308,7 @@ def main():
     if a.strong_child and world > 1:      # N > 1, inside the per-rank child processes started by bench_multi.experiment_children()
         import bench_multi
         peak, peak_src = hbm_peak()
-        child = bench_multi.native_weak_child if a.child_task == "native_weak" else bench_multi.viscous_strong_child
+        child = {"native_weak": bench_multi.native_weak_child, "graph_strong": bench_multi.graph_strong_child}.get(a.child_task, bench_multi.viscous_strong_child)
         rec = child(a, rank, world, local_rank, peak, peak_src)
         if rank == 0:
             print(STRONG_TAG + json_line(rec), flush=True)

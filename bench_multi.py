@@ -153,21 +153,34 @@ TRANSPORT = ("grouped ncclSend/ncclRecv between device buffers + ncclAllReduce(m
                             "(split-phase C ABI driven over torch.distributed)")
 
 
-def strong_record(name, nq, a, rank, world, device, peak, peak_src, mu=0.0):
+def strong_record(name, nq, a, rank, world, device, peak, peak_src, mu=0.0, graph=False):
     """Strong scaling: the nq x nq jittered, id-shuffled triangulation of [0,10]^2 split over `world` GPUs.  mu > 0: with the
-    Navier-Stokes terms and normalised TENO weights (BASELINE configs[4])."""
+    Navier-Stokes terms and normalised TENO weights (BASELINE configs[4]).  graph: cut by the library's graph partitioner
+    (mlb_partition_graph_csr on the closed-form dual graph of the mesh, computed by every rank for itself) instead of the
+    recursive coordinate bisection."""
     import bench
     import mallard_b200 as mb
     from mallard_b200 import synthetic as syn
     nc = 2 * nq * nq
     rec = {"workload": "%s: isentropic vortex, jittered (+-0.15 h, seed 12345), id-shuffled triangulation %dx%d of [0,10]^2 (%d cells), "
-                       "TENO(legendre,p=3%s)+HLLC+SSPRK3, cfl 0.1, extrapolation BCs%s; recursive coordinate bisection over %d GPU(s), rank-local ingest"
-                       % (name, nq, nq, nc, ", normalised weights" if mu > 0 else "", ", Navier-Stokes terms: mu = %g, Pr = 0.72" % mu if mu > 0 else "", world),
-           "n_cells": nc, "n_gpus": world, "scaling": "strong"}
+                       "TENO(legendre,p=3%s)+HLLC+SSPRK3, cfl 0.1, extrapolation BCs%s; %s over %d GPU(s), rank-local ingest"
+                       % (name, nq, nq, nc, ", normalised weights" if mu > 0 else "", ", Navier-Stokes terms: mu = %g, Pr = 0.72" % mu if mu > 0 else "",
+                          "graph-partitioned (mlb_partition_graph_csr: multilevel recursive bisection of the cell-face dual graph)" if graph
+                          else "recursive coordinate bisection", world),
+           "n_cells": nc, "n_gpus": world, "scaling": "strong", "partitioner": "graph" if graph else "coordinate bisection"}
     t0 = time.perf_counter()
+    part_fn = None
+    if graph:      # every rank cuts the global dual graph for itself (deterministic, thread-count independent: all ranks agree)
+        xadj, adj = syn.jittered_tri_dual_graph(nq, nq, seed=12345)
+        t1 = time.perf_counter()
+        gpart = mb.partition_graph(None, world, xadj=xadj, adj=adj)
+        rows = np.repeat(np.arange(nc, dtype=np.int64), np.diff(xadj).astype(np.int64))
+        rec.update(partition_seconds=time.perf_counter() - t1, dual_graph_seconds=t1 - t0, edge_cut=int((gpart[rows] != gpart[adj]).sum() // 2))
+        del xadj, adj, rows
+        part_fn = lambda n: gpart      # noqa: E731
     layers, lp, ds, s = 8, None, None, None
     for attempt in range(3):
-        lp = syn.jittered_tri_local(nq, nq, 10.0, 10.0, world, rank, seed=12345, layers=layers)
+        lp = syn.jittered_tri_local(nq, nq, 10.0, 10.0, world, rank, seed=12345, layers=layers, part_fn=part_fn)
         ok = 1.0
         try:
             kw = dict(recon="TENO", riemann="HLLC", integrator="SSPRK3", order=3, bcs=syn.EXTRAP4, fp_mode=a.fp, keep_stage_rhs=False)
@@ -217,14 +230,16 @@ def strong_record(name, nq, a, rank, world, device, peak, peak_src, mu=0.0):
                setup_seconds=float(mem[3]), preprocess_seconds=float(mem[4]), mesh_seconds=float(mem[5]), graph_replayed_steps=int(s.get("stats")[11]))
     s.close()
     if rank == 0:
-        strong_efficiency(rec, name + ("_viscous" if mu > 0 else ""), world)
+        # (a graph-partitioned record is compared with the same base point as the coordinate-bisection record of its mesh - one GPU
+        #  holds the whole mesh whoever cuts it - and leaves no point of its own)
+        strong_efficiency(rec, name + ("_viscous" if mu > 0 else ""), world, store=not graph)
     return rec
 
 
 LIVE_BASELINES = os.environ.get("MLB_STRONG_BASELINES", "/tmp/mlb_strong_baselines.json")
 
 
-def strong_efficiency(rec, name, world, live_path=None, max_age_s=6 * 3600.0):
+def strong_efficiency(rec, name, world, live_path=None, max_age_s=6 * 3600.0, store=True):
     """Strong-scaling efficiency of a record = value_N / (N / N0 x value_N0), N0 the smallest GPU count this mesh has been measured
     on (1 where the mesh fits one GPU; the 64 M-cell mesh starts at 4).  The base point is the one measured ON THIS BOX by an earlier
     bench.py run of the same series (the driver's scaling run goes N = 1, 2, 4, 8 on one lease: every run leaves its records in
@@ -255,7 +270,7 @@ def strong_efficiency(rec, name, world, live_path=None, max_age_s=6 * 3600.0):
         rec["efficiency"] = 1.0
     # leave this run's point for the larger runs that follow (keep the smallest GPU count per mesh)
     try:
-        if name not in live or live[name].get("n_gpus", 1 << 30) >= world:
+        if store and (name not in live or live[name].get("n_gpus", 1 << 30) >= world):
             live[name] = {"n_gpus": world, "value": rec["value"], "ms_per_step": rec["ms_per_step"]}
             tmp = live_path + ".%d.tmp" % os.getpid()
             json.dump(live, open(tmp, "w"))
@@ -500,6 +515,32 @@ def viscous_strong_child(a, rank, world, local_rank, peak, peak_src):
     return rec
 
 
+def graph_strong_child(a, rank, world, local_rank, peak, peak_src):
+    """Body of the per-rank child for task `graph_strong`: the 16 M-cell strong-scaling mesh (BASELINE configs[3]) cut by the library's
+    GRAPH partitioner (north_star: "the mesh is graph-partitioned across the GPUs") instead of the coordinate bisection - same mesh,
+    same numerics, same timing as the `strong` record next to it, so the two partitioners are compared on the device (ms per step,
+    ghost cells per stage, peers)."""
+    import datetime
+    import torch
+    import torch.distributed as dist
+    import bench
+    import mallard_b200 as mb
+    torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(local_rank)
+    mb.set_host_threads(max(1, bench.host_cores() // world))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=1800))
+    name, nq = STRONG_MESHES[0]
+    rec = strong_record(name, nq, a, rank, world, local_rank, peak, peak_src, graph=True)
+    rec["verification"] = ("the graph partitioner is host code (CPU suite: sizes, determinism, connectivity, plans and emulated rank contexts on graph partitions); "
+                           "this is the first run of a graph-partitioned mesh on hardware, in a process of its own")
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        pass
+    return rec
+
+
 def weak_problem(a, rank, world):
     """The main line's configuration: every rank owns one nx x ny block of a (nx * world) x ny cartesian_tri mesh, cut in x."""
     import bench
@@ -551,7 +592,7 @@ def native_weak_child(a, rank, world, local_rank, peak, peak_src):
 def experiment_children(a, rank, world, popen=None, task="viscous_strong", start_by=None, time_limit=None, extra_env=None):
     """N > 1: one CHILD process per rank, with a process group of their own, for code that runs on hardware for the first time - it must not
     be able to take the main line (or the measured strong-scaling records) with it.  Tasks: `viscous_strong` = BASELINE configs[4] (viscous,
-    the 64 M-cell mesh where it fits); `native_weak` = the main line's configuration through the library's own NCCL driver
+    the 64 M-cell mesh where it fits); `graph_strong` = the 16 M-cell mesh cut by the graph partitioner; `native_weak` = the main line's configuration through the library's own NCCL driver
     (mlb_comm_init / mlb_run_distributed) with MLB_COMM_TRACE=1.  Every rank decides the same way (collective), starts its child, waits for
     it under the time limit; rank 0 returns the records its child printed; the last `[mlb comm]` lines of EVERY rank's child are attached
     to a record that did not complete (which rank stopped where)."""
@@ -736,6 +777,8 @@ def run(a, rank, world, local_rank, workload):
     if strong_recs is not None and not any("error" in r for r in strong_recs):      # (after an error the ranks may have diverged: nothing collective)
         try:
             experiments = experiment_children(a, rank, world)
+            # the 16 M-cell mesh once more, cut by the graph partitioner (~1 min of partitioning per rank on top of a strong record)
+            experiments += experiment_children(a, rank, world, task="graph_strong", start_by=470.0)
             # the library's own NCCL driver on this many GPUs (diagnosis of the round-2 8-GPU hang): NCCL's defaults first; if that does not
             # come back, once more without graph-time buffer registration and NVLS (neither can matter for 230 kB exchanges and an 8-byte
             # all-reduce) - the record says which attempt, if any, completed

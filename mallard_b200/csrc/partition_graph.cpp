@@ -13,6 +13,7 @@
 // independent subproblems (OpenMP tasks), so the partition does not depend on the number of threads that compute it - every rank
 // of a job can compute it for itself and all agree (what mlb_create_partitioned / mlb_create_local require).
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
@@ -28,6 +29,9 @@ namespace mlb {
 namespace {
 
 constexpr uint32_t NONE = 0xFFFFFFFFu;
+double g_t[4] = {0, 0, 0, 0};      // MLB_PARTITION_DEBUG: seconds in coarsening / initial bisections / refinement / subgraph extraction (single-thread runs)
+struct Tick { int k; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(); explicit Tick(int k_) : k(k_) {}
+              ~Tick() { g_t[k] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); } };
 constexpr uint32_t COARSEN_TO = 512;
 
 struct Graph {
@@ -102,25 +106,42 @@ bool coarsen(const Graph & g, Graph & c, std::vector<uint32_t> & cmap, uint64_t 
     c.n = nc;
     c.vw.assign(nc, 0);
     c.xadj.assign((size_t)nc + 1, 0);
-    c.adj.clear(); c.ew.clear();
-    c.adj.reserve(g.adj.size() / 2); c.ew.reserve(g.adj.size() / 2);
-    std::vector<uint64_t> pos(nc, UINT64_MAX);
+    // rows of the coarse graph: the members' neighbours mapped to coarse ids, duplicates merged by a linear look through the row so
+    // far (rows of a mesh graph hold a handful of entries).  Two passes - rows at an upper-bound offset, then compacted - so that the
+    // rows are independent: taskloops, executed by whatever threads of the enclosing team are idle; the result does not depend on them.
+    std::vector<uint64_t> ub((size_t)nc + 1, 0);
     for (uint32_t cv = 0; cv < nc; cv++) {
-        const uint64_t row = c.adj.size();
+        uint64_t d = g.xadj[first[cv] + 1] - g.xadj[first[cv]];
+        if (second[cv] != NONE) d += g.xadj[second[cv] + 1] - g.xadj[second[cv]];
+        ub[cv + 1] = ub[cv] + d;
+    }
+    std::vector<uint32_t> tadj(ub[nc]), tew(ub[nc]), cnt(nc, 0);
+#pragma omp taskloop grainsize(16384) shared(g, c, cmap, first, second, ub, tadj, tew, cnt)
+    for (uint32_t cv = 0; cv < nc; cv++) {
+        const uint64_t row = ub[cv];
+        uint32_t k = 0, w = 0;
         const uint32_t mem[2] = {first[cv], second[cv]};
-        for (int k = 0; k < 2; k++) {
-            const uint32_t v = mem[k];
+        for (int m = 0; m < 2; m++) {
+            const uint32_t v = mem[m];
             if (v == NONE) continue;
-            c.vw[cv] += g.vw[v];
+            w += g.vw[v];
             for (uint64_t e = g.xadj[v]; e < g.xadj[v + 1]; e++) {
                 const uint32_t cu = cmap[g.adj[e]];
                 if (cu == cv) continue;
-                if (pos[cu] != UINT64_MAX && pos[cu] >= row) c.ew[pos[cu]] += g.ew[e];
-                else { pos[cu] = c.adj.size(); c.adj.push_back(cu); c.ew.push_back(g.ew[e]); }
+                uint32_t j = 0;
+                while (j < k && tadj[row + j] != cu) j++;
+                if (j < k) tew[row + j] += g.ew[e];
+                else { tadj[row + k] = cu; tew[row + k] = g.ew[e]; k++; }
             }
         }
-        c.xadj[cv + 1] = c.adj.size();
+        c.vw[cv] = w;
+        cnt[cv] = k;
     }
+    for (uint32_t cv = 0; cv < nc; cv++) c.xadj[cv + 1] = c.xadj[cv] + cnt[cv];
+    c.adj.resize(c.xadj[nc]); c.ew.resize(c.xadj[nc]);
+#pragma omp taskloop grainsize(16384) shared(c, ub, tadj, tew, cnt)
+    for (uint32_t cv = 0; cv < nc; cv++)
+        for (uint32_t j = 0; j < cnt[cv]; j++) { c.adj[c.xadj[cv] + j] = tadj[ub[cv] + j]; c.ew[c.xadj[cv] + j] = tew[ub[cv] + j]; }
     return true;
 }
 
@@ -139,9 +160,15 @@ struct Refiner {
 
     Refiner(const Graph & g_, std::vector<uint8_t> & w, int64_t t0, int64_t mt, int64_t at) : g(g_), where(w), target0(t0), move_tol(mt), accept_tol(at) {
         ed.assign(g.n, 0); id.assign(g.n, 0); locked.assign(g.n, 0);
+        const uint32_t n = g.n;
+        int64_t * edp = ed.data(), * idp = id.data();
+        const Graph * gp = &g;
+        const uint8_t * wp = where.data();
+#pragma omp taskloop grainsize(32768) firstprivate(edp, idp, gp, wp)
+        for (uint32_t v = 0; v < n; v++)
+            for (uint64_t e = gp->xadj[v]; e < gp->xadj[v + 1]; e++) (wp[gp->adj[e]] == wp[v] ? idp[v] : edp[v]) += gp->ew[e];
         for (uint32_t v = 0; v < g.n; v++) {
             if (where[v] == 0) w0 += g.vw[v];
-            for (uint64_t e = g.xadj[v]; e < g.xadj[v + 1]; e++) (where[g.adj[e]] == where[v] ? id[v] : ed[v]) += g.ew[e];
             cut += ed[v];
         }
         cut /= 2;
@@ -312,6 +339,7 @@ void bisect(const Graph & g, uint32_t n0, std::vector<uint8_t> & where) {
     while (cur->n > COARSEN_TO) {
         Graph c;
         std::vector<uint32_t> cmap;
+        Tick tick(0);
         if (!coarsen(*cur, c, cmap, max_vw)) break;
         levels.push_back(std::move(c));
         cmaps.push_back(std::move(cmap));
@@ -325,9 +353,17 @@ void bisect(const Graph & g, uint32_t n0, std::vector<uint8_t> & where) {
     };
     // one uncoarsening step: w on levels[l] -> the graph it was coarsened from, refined there; returns the cut
     auto step = [&](size_t l, std::vector<uint8_t> & w) {
+        Tick tick(2);
         const Graph & fine = l == 0 ? g : levels[l - 1];
         std::vector<uint8_t> wf(fine.n);
-        for (uint32_t v = 0; v < fine.n; v++) wf[v] = w[cmaps[l][v]];
+        {
+            uint8_t * wfp = wf.data();
+            const uint8_t * wc = w.data();
+            const uint32_t * cm = cmaps[l].data();
+            const uint32_t nf = fine.n;
+#pragma omp taskloop grainsize(65536) firstprivate(wfp, wc, cm)
+            for (uint32_t v = 0; v < nf; v++) wfp[v] = wc[cm[v]];
+        }
         w.swap(wf);
         const bool finest = l == 0;
         const int64_t tol = level_tol(fine);
@@ -337,7 +373,8 @@ void bisect(const Graph & g, uint32_t n0, std::vector<uint8_t> & where) {
         return r.cut;
     };
     std::vector<Candidate> cands;
-    initial_bisections(*cur, target_w, cur == &g ? 0 : level_tol(*cur), cands);
+    { Tick tick(1);
+    initial_bisections(*cur, target_w, cur == &g ? 0 : level_tol(*cur), cands); }
     std::vector<uint8_t> w;
     size_t l = levels.size();                  // levels still to be undone
     if (cur == &g) {                           // (a graph small enough not to be coarsened: exact sizes here and now)
@@ -383,6 +420,7 @@ void recurse(const Graph & g, const std::vector<uint32_t> & ids, int32_t p0, int
     bisect(g, n0, where);
     Graph sub[2];
     std::vector<uint32_t> sub_ids[2], local(g.n);
+    { Tick tick(3);
     for (uint32_t v = 0; v < g.n; v++) { local[v] = (uint32_t)sub_ids[where[v]].size(); sub_ids[where[v]].push_back(ids[v]); }
     for (int s = 0; s < 2; s++) { sub[s].n = (uint32_t)sub_ids[s].size(); sub[s].xadj.assign((size_t)sub[s].n + 1, 0); sub[s].vw.assign(sub[s].n, 1); }
     for (uint32_t v = 0; v < g.n; v++) {
@@ -390,6 +428,7 @@ void recurse(const Graph & g, const std::vector<uint32_t> & ids, int32_t p0, int
         for (uint64_t e = g.xadj[v]; e < g.xadj[v + 1]; e++)
             if (where[g.adj[e]] == where[v] && g.adj[e] != v) { s.adj.push_back(local[g.adj[e]]); s.ew.push_back(1); }
         s.xadj[local[v] + 1] = s.adj.size();
+    }
     }
 #pragma omp task shared(sub, sub_ids) if (g.n > 100000)
     recurse(sub[0], sub_ids[0], p0, npl, part_out);
@@ -412,6 +451,8 @@ void graph_partition(uint32_t n, const uint64_t * xadj, const uint32_t * adj, in
 #pragma omp parallel
 #pragma omp single
     recurse(g, ids, 0, n_parts, part_out);
+    if (getenv("MLB_PARTITION_DEBUG"))
+        fprintf(stderr, "[mlb partition] seconds (summed over threads): coarsening %.2f, initial bisections %.2f, refinement %.2f, subgraphs %.2f\n", g_t[0], g_t[1], g_t[2], g_t[3]);
 }
 
 // dual graph of a mesh: cells are adjacent through their common faces (cells_of_face), in face order

@@ -118,6 +118,34 @@ class LocalPart:
         self.n_global, self.n_owned, self.seconds = n_global, n_owned, seconds
 
 
+def jittered_tri_dual_graph(nx, ny, seed=12345, amp=0.15):
+    """Cell-face dual graph (CSR: xadj uint64 [nc + 1], adj uint32) of jittered_tri(nx, ny, ..., seed, amp) in ITS cell numbering, from
+    closed forms - which triangles a triangle of the structured parent touches (csrc/mesh_host.cpp gen_tris: cr = 2 q, cl = 2 q + 1 of
+    quad q = ic * ny + jc) and the generator's cell permutation - without building the mesh: what mlb_partition_graph_csr needs to
+    cut a 16 M- or 64 M-cell mesh on a rank that never holds it (tests/test_host_side.py compares with the mesh's own cells_of_face)."""
+    rng = np.random.default_rng(seed)
+    nc = 2 * nx * ny
+    if amp > 0:
+        rng.uniform(-1.0, 1.0, size=((nx + 1) * (ny + 1), 2))      # (the node jitter comes first in the generator's random stream)
+    pc = rng.permutation(nc)                                        # new cell i = old cell pc[i]
+    ipc = np.empty(nc, dtype=np.int64)
+    ipc[pc] = np.arange(nc)
+    q = np.arange(nx * ny, dtype=np.int64)
+    ic, jc = q // ny, q % ny
+    nbr = np.full((nc, 3), -1, dtype=np.int64)                      # old numbering
+    nbr[0::2, 0] = 2 * q + 1                                        # cr: the diagonal, the quad below (its cl), the quad to the right (its cl)
+    nbr[0::2, 1] = np.where(jc > 0, 2 * (q - 1) + 1, -1)
+    nbr[0::2, 2] = np.where(ic < nx - 1, 2 * (q + ny) + 1, -1)
+    nbr[1::2, 0] = 2 * q                                            # cl: the diagonal, the quad above (its cr), the quad to the left (its cr)
+    nbr[1::2, 1] = np.where(jc < ny - 1, 2 * (q + 1), -1)
+    nbr[1::2, 2] = np.where(ic > 0, 2 * (q - ny), -1)
+    nbr = nbr[pc]                                                   # rows in the new numbering
+    ok = nbr >= 0
+    xadj = np.concatenate([[0], np.cumsum(ok.sum(axis=1))]).astype(np.uint64)
+    adj = ipc[nbr[ok]].astype(np.uint32)                            # row-major: every row's neighbours are contiguous
+    return xadj, adj
+
+
 def jittered_tri_local(nx, ny, Lx, Ly, n_parts, rank, seed=12345, amp=0.15, layers=10, part_fn=None):
     """The part of jittered_tri(nx, ny, Lx, Ly, seed, amp) that rank `rank` of `n_parts` needs: the cells the library's recursive
     coordinate bisection (mlb_partition_coords on the global centroids) assigns to it plus `layers` layers of quads around them,

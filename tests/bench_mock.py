@@ -205,11 +205,11 @@ if __name__ == "__main__":       # child of tests/test_bench_flow.py: `python te
     if fail is not None:
         real = bench_multi.strong_record
 
-        def failing(name, nq, a, rank, world, *rest):
+        def failing(name, nq, a, rank, world, *rest, **kw):
             if rank == int(fail):
                 raise RuntimeError("mock failure of the strong record on rank %d" % rank)
             time.sleep(float(os.environ.get("MLB_MOCK_PEER_WAIT", "0")))
-            return real(name, nq, a, rank, world, *rest)
+            return real(name, nq, a, rank, world, *rest, **kw)
         bench_multi.strong_record = failing
     hang = os.environ.get("MLB_MOCK_HANG_TASK")
     if hang and "--child-task" in sys.argv and sys.argv[sys.argv.index("--child-task") + 1] == hang:      # a child that stops inside NCCL

@@ -91,9 +91,12 @@ def test_multi_gpu_line_with_its_strong_records(world, tmp_path):
     assert strong[0]["halo"]["max_peers"] >= 1 and strong[0]["ghost_layers"] >= 8 and strong[0]["roofline"]["rank"] == "slowest"
     assert json.load(open(live))["vortex_64M"]["n_gpus"] == world
     ex = d["experiments"]                       # BASELINE configs[4]: the largest mesh that fits, viscous, in per-rank child processes with their own group
-    assert len(ex) == 2 and ex[0]["n_cells"] == 12800 and ex[0]["n_gpus"] == world and "Navier-Stokes" in ex[0]["workload"] and ex[0]["value"] > 0
+    assert len(ex) == 3 and ex[0]["n_cells"] == 12800 and ex[0]["n_gpus"] == world and "Navier-Stokes" in ex[0]["workload"] and ex[0]["value"] > 0
     assert ex[0]["halo"]["max_peers"] >= 1 and "verification" in ex[0]
-    assert ex[1]["workload"].startswith("native_weak") and ex[1]["value"] > 0 and ex[1]["n_cells"] == d["config"]["n_cells"]   # the library's own NCCL driver, diagnosed in children
+    # the 16 M-cell mesh of the first strong record once more, cut by the graph partitioner: same base point, no point of its own left behind
+    assert ex[1]["partitioner"] == "graph" and ex[1]["n_cells"] == strong[0]["n_cells"] and ex[1]["value"] > 0 and ex[1]["edge_cut"] > 0
+    assert strong[0]["partitioner"] == "coordinate bisection" and ex[1]["efficiency_base"] == strong[0]["efficiency_base"] and ex[1]["partition_seconds"] > 0
+    assert ex[2]["workload"].startswith("native_weak") and ex[2]["value"] > 0 and ex[2]["n_cells"] == d["config"]["n_cells"]   # the library's own NCCL driver, diagnosed in children
 
 
 def test_a_failing_strong_record_does_not_cost_the_main_line(tmp_path):
