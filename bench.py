@@ -170,6 +170,39 @@ def reference_cpu(n_steps, n_warmup, nx=96, ny=96):
     return nc * N_STAGES * n_steps / sec, dict(kind="port", cores=1, sample=sample + " (oracle port, scalar)", ms_per_step=1e3 * sec / n_steps)
 
 
+def kernel_roofline_table(prof, nc, a, peak, _unused, solver):
+    """{kernel: ms per launch, algorithmic bytes per cell (DESIGN.md kernel table; triangles: 1.5 faces per cell, Q face quadrature points),
+    achieved GB/s and fraction of the measured HBM peak on those bytes, and the same on ncu's dram__bytes of the committed capture}"""
+    Q = 2                                                   # TENO p = 3: two Gauss points per face (numerics/quadrature.h)
+    alg = {"teno_stream": ALG_BYTES_RECON, "teno_recon": ALG_BYTES_RECON,
+           "face_flux_teno": 1.5 * (48.0 + 2 * Q * 32.0),  # per face: 48 B of connectivity / geometry / product (DESIGN.md) + both sides' Q face states
+           "face_flux_fo": 1.5 * (48.0 + 2 * 32.0),        # per face: the same 48 B + the two cells' states
+           "gather_stage": 72.0 + 1.5 * 32.0,              # state in / out, volume, stage vector + the face products of the cell's faces
+           "cfl": 200.0}
+    traffic, fp64 = {}, {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if tj.get("n_cells") == nc and tj.get("workload") == a.workload and tj.get("fp_mode") == a.fp:
+            traffic = tj.get("bytes_per_launch", {})
+            fp64 = tj.get("fp64_pipe_pct_of_peak", {})
+    except Exception:
+        pass
+    out = {}
+    for k, (ms_total, launches) in prof.items():
+        if not launches or k not in alg:
+            continue
+        ms = ms_total / launches
+        row = {"ms_per_launch": ms, "algorithmic_bytes_per_cell": alg[k], "achieved": alg[k] * nc / (ms * 1e-3) / 1e9, "unit": "GB/s"}
+        row["frac"] = row["achieved"] / peak
+        if traffic.get(k):
+            row["traffic"] = traffic[k]
+            row["frac_traffic"] = traffic[k] / (ms * 1e-3) / 1e9 / peak
+        if fp64.get(k) is not None:
+            row["fp64_pipe_pct_of_peak_ncu"] = fp64[k]
+        out[k] = row
+    return out
+
+
 STRONG_TAG = "STRONG_RECORD "
 T_START = time.perf_counter()
 
@@ -426,6 +459,15 @@ def main():
         roof["stage_achieved"] = alg_stage * nc / (stage_ms * 1e-3) / 1e9
         roof["stage_frac"] = roof["stage_achieved"] / peak
 
+    # ---- every kernel of the step against ITS bound (north_star: "the fused TENO+Riemann face kernel and RK update reach >= 60 % of
+    #      their roofline"): event-timed launch duration against the algorithmic bytes of DESIGN.md's kernel table, and - where the committed
+    #      ncu capture is of this very workload - against the bytes DRAM really moved; the FP64-pipe figure is ncu's, from the same capture
+    kernel_rooflines = None
+    try:
+        kernel_rooflines = kernel_roofline_table(prof, nc, a, peak, None, s)
+    except Exception as ex:          # reporting only: never the reason for a missing line
+        kernel_rooflines = {"error": str(ex)[:200]}
+
     # ---- end to end through the take_step seam with host buffers (pinned): H2D U, calc_dt + step, D2H U every step
     e2e = None
     if not a.no_e2e:
@@ -493,7 +535,7 @@ def main():
                                       "device_table_build_s": stats[10]},
                        "note": ("reference-faithful TENO: like the reference, the state turns non-finite inside step 1 (SURVEY 0.2); cost is "
                                 "data-independent") if a.recon == "TENO" else "first-order path (the numerics of examples/sod and examples/wedge)"},
-            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "kernels": kernels, "strong": strong,
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "kernels": kernels, "kernel_rooflines": kernel_rooflines, "strong": strong,
             "experiments": experiments or None}
     print(json_line(line))
 

@@ -32,6 +32,9 @@ def test_default_single_gpu_line_with_its_strong_records(tmp_path):
     assert d["e2e"]["h2d_bytes_per_step"] == 2 * 1024 * 1024 * 32 and d["gpu_launches"] == 200
     assert d["roofline"]["kernel"] == "teno_stream" and 0 < d["roofline"]["frac"] and d["roofline"]["peak"] > 0
     assert d["cpu_baseline"]["kind"] == "reference" and d["config"]["data_independence"]["teno_fixed"] == 1
+    kr = d["kernel_rooflines"]                                       # every kernel of the step against its own bound
+    assert set(kr) == {"teno_stream", "face_flux_teno", "gather_stage", "cfl"} and all(0 < r["frac"] and r["ms_per_launch"] > 0 for r in kr.values())
+    assert kr["face_flux_teno"]["traffic"] > 0 and kr["face_flux_teno"]["frac_traffic"] > 0 and kr["face_flux_teno"]["fp64_pipe_pct_of_peak_ncu"] > 0
     strong = d["strong"]
     assert [r.get("n_cells") for r in strong] == [3200, 2 * 5657 * 5657]
     assert strong[0]["efficiency"] == 1.0 and strong[0]["roofline"]["frac"] > 0 and strong[0]["n_gpus"] == 1
