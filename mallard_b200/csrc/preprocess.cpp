@@ -104,6 +104,10 @@ double legendre(int deriv, int p, double x) {
     for (int j = 0; j < P.nt; j++) {
         const int e = P.t[j].e;
         if (e < deriv) continue;
+        // reference quirk (numerics/basis.h:122): the hard-coded d/dx P9 stops at "- 4620.0*3.0*x*x" - the constant 315.0*1.0 that the
+        // 315 x term would leave is missing.  Reproduced: the oscillation-indicator matrix of basis_order 9 is built from these
+        // derivatives (:743-788) and must be the reference's bit for bit (found by pinning against a dump of the reference at order 9).
+        if (p == 9 && deriv == 1 && e == 1) continue;
         double term = P.t[j].c;
         for (int k = 0; k < deriv; k++) term *= (double)(e - k);
         for (int k = 0; k < e - deriv; k++) term *= x;

@@ -101,6 +101,18 @@ CASES = {
                                      riemann="HLLC", integrator="SSPRK3",
                                      recon=dict(type="TENO", basis_type="legendre", basis_order=2, max_stencil_size_factor=1.5),
                                      n_steps=1, every=1, keep_mesh=False, keep_teno=True),
+    # the upper end of what the reference accepts (basis_order up to 9: K = 55, M = 110; basis.h holds Legendre polynomials up to degree 9)
+    # and an odd order in between with the reference's default basis - pins the oracle where only the generic device kernel runs
+    "teno_monomial_14x12_p7": dict(mesh=dict(type="cartesian_tri", Nx=14, Ny=12, Lx=1.2, Ly=1.0), ic=SMOOTH_IC, bcs=EXTRAP4, cfl=0.1,
+                                   riemann="HLLC", integrator="SSPRK3",
+                                   recon=dict(type="TENO", basis_type="monomial", basis_order=7, max_stencil_size_factor=2.0,
+                                              quadrature_order_cell=5),
+                                   n_steps=1, every=1, keep_mesh=False, keep_teno=False),
+    "teno_legendre_16x14_p9": dict(mesh=dict(type="cartesian_tri", Nx=16, Ny=14, Lx=1.2, Ly=1.0), ic=SMOOTH_IC, bcs=SYM4, cfl=0.1,
+                                   riemann="Rusanov", integrator="SSPRK3",
+                                   recon=dict(type="TENO", basis_type="legendre", basis_order=9, max_stencil_size_factor=2.0,
+                                              quadrature_order_cell=5),
+                                   n_steps=1, every=1, keep_mesh=False, keep_teno=False),
     # TENO face states through every boundary functor (upt, p_out, wall_adiabatic, symmetry: boundary/*.cpp) and through RK4's four
     # stages; TENO + HLL on the four-quadrant data (non-finite pattern of the HLL flux)
     "teno_bcs_rk4_10x8": dict(mesh=dict(type="cartesian_tri", Nx=10, Ny=8, Lx=1.0, Ly=0.8), ic=SMOOTH_IC,

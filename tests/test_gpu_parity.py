@@ -112,7 +112,7 @@ def _solver(meta, mesh, fp, **kw):
 BIT_EXACT_STRICT = {"sod_rusanov_fe", "wedge_30x10", "wedge_wall_30x10"}   # no libm pow anywhere on these paths
 
 
-GENERIC_KERNEL_FIXTURES = {"teno_legendre_12x10_p5", "teno_legendre_8x7_p2_f15"}     # served by csrc/teno_generic.cuh
+GENERIC_KERNEL_FIXTURES = {"teno_legendre_12x10_p5", "teno_legendre_8x7_p2_f15", "teno_monomial_14x12_p7", "teno_legendre_16x14_p9"}     # served by csrc/teno_generic.cuh
 # reference dumps added after the round-2 GPU budget ran out (TENO through upt / p_out / wall boundaries + RK4; TENO + HLL on the four-quadrant
 # data): the kernels they exercise HAVE run on a B200, these comparisons have not - gated like the rest (tests/test_zz_gpu_hardware_trial.py)
 LATE_FIXTURES = {"teno_bcs_rk4_10x8", "teno_hll_riemann_9x7"}

@@ -259,6 +259,23 @@ def test_graph_partition_follows_the_connectivity_not_the_coordinates():
         mb.partition_graph(None, 2, xadj=np.array([0, 1], dtype=np.uint64), adj=np.array([5], dtype=np.uint32))
 
 
+def test_closed_form_dual_graph_of_the_jittered_mesh_is_the_mesh_s_own():
+    """synthetic.jittered_tri_dual_graph (what a rank that never holds the 16 M-cell mesh hands mlb_partition_graph_csr): the same edges as the
+    generated mesh's cells_of_face, hence the same partition as mlb_partition_graph of the mesh"""
+    from mallard_b200 import synthetic as syn
+    for nx, ny, seed in ((13, 9, 5), (8, 20, 12345)):
+        m = syn.jittered_tri(nx, ny, 10.0, 10.0, seed=seed)
+        xadj, adj = syn.jittered_tri_dual_graph(nx, ny, seed=seed)
+        cof = m.arrays["cells_of_face"].reshape(-1, 2)
+        inner = cof[(cof[:, 0] >= 0) & (cof[:, 1] >= 0)]
+        rows = np.repeat(np.arange(m.n_cells), np.diff(xadj).astype(np.int64))
+        assert set(zip(rows.tolist(), adj.tolist())) == set(map(tuple, np.concatenate([inner, inner[:, ::-1]]).tolist()))
+        # the partition depends on the order of a vertex's neighbours only through ties: sizes and cut quality are those of the mesh's graph
+        a, b = mb.partition_graph(None, 4, xadj=xadj, adj=adj), mb.partition_graph(m, 4)
+        assert np.array_equal(np.bincount(a, minlength=4), np.bincount(b, minlength=4))
+        assert abs(_edge_cut(m, a) - _edge_cut(m, b)) <= 0.25 * _edge_cut(m, b) + 4
+
+
 def test_graph_partition_drives_a_partitioned_plan():
     """any partition vector is a valid input of the preprocessor: the plans of a graph-partitioned mesh own every cell exactly once and
     announce halos that are each other's mirror image"""
