@@ -147,8 +147,9 @@ def write_toml(case, path, n_steps=None):
     L += ["", "[numerics]", 'riemann_solver = "%s"' % case["riemann"], 'time_integrator = "%s"' % case["integrator"],
           "check_nan = false", "", "[numerics.face_reconstruction]"]
     L += ["%s = %s" % (k, toml_value(v)) for k, v in case["recon"].items()]
-    L += ["", "[physics]", 'type = "euler"', "gamma = 1.4", "p_ref = 101325.0", "T_ref = 298.15", "rho_ref = 1.225", "",
-          "[output]", "check_interval = 1000000", ""]
+    ph = dict(gamma=1.4, p_ref=101325.0, T_ref=298.15, rho_ref=1.225)
+    ph.update(case.get("physics", {}))          # (oracle/pin_sweep.py varies the gas: gamma, reference state, pressure clamp)
+    L += ["", "[physics]", 'type = "euler"'] + ["%s = %r" % (k, float(v)) for k, v in ph.items()] + ["", "[output]", "check_interval = 1000000", ""]
     with open(path, "w") as f:
         f.write("\n".join(L))
 

@@ -1,0 +1,258 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE.  Pins the oracle (and the product's HOST preprocessor tables) against the UNMODIFIED reference over a grid of
+configurations wider than the committed fixtures: for every case the reference (oracle/_ref/bin/ref_harness) dumps one step, and
+the oracle restatement must reproduce every TENO table, the stage-1 face values and residual, dt, the residual of every stage and
+the state after the step BIT FOR BIT; the preprocessor's reference-layout tables (mlb_plan_*) likewise.  Nothing is written to
+tests/golden/ (the dumps of the larger cases are tens of MB); the result table goes to stdout:
+    python oracle/pin_sweep.py > profiles/r02h_pin_sweep.txt
+Runs only where /root/reference has been built (oracle/build_ref.sh); ~15 min on 8 cores."""
+import itertools
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path[:0] = [HERE, ROOT, os.path.join(ROOT, "tests")]
+import make_golden as mg  # noqa: E402
+import mlbd  # noqa: E402
+import golden_util as gu  # noqa: E402
+import oracle  # noqa: E402
+import mallard_b200 as mb  # noqa: E402
+
+TENO_KEYS_PLAN = ("teno:stencils", "teno:offsets_stencils", "teno:offsets_stencil_groups", "teno:transformed_areas",
+                  "teno:reconstruction_matrices", "teno:oscillation_indicator", "teno:integral_psi_target", "teno:poly_indices")
+
+
+def run_reference(case):
+    with tempfile.TemporaryDirectory() as td:
+        toml, out = os.path.join(td, "input.toml"), os.path.join(td, "out.mlbd")
+        mg.write_toml(case, toml)
+        env = dict(os.environ, OMP_NUM_THREADS="1", OMP_PROC_BIND="false")
+        subprocess.check_call([mg.HARNESS, "dump", toml, out, str(case["n_steps"]), str(case["every"])], env=env,
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        return mlbd.read(out)
+
+
+def compare(case):
+    """-> list of (what, verdict) where verdict is 'ok' or a description of the first difference"""
+    d = run_reference(case)
+    meta = {k: v for k, v in case.items() if k not in ("keep_mesh", "keep_teno")}
+    out = []
+
+    def eq(what, got, ref):
+        got = np.asarray(got).reshape(np.asarray(ref).shape)
+        if np.array_equal(got, ref, equal_nan=True):
+            out.append((what, "ok"))
+        elif got.dtype.kind == "f":
+            bad = got != ref
+            bad &= ~(np.isnan(got) & np.isnan(ref))
+            fin = bad & np.isfinite(got) & np.isfinite(ref)
+            rel = float((np.abs(got[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1e-300)).max()) if fin.any() else float("inf")
+            out.append((what, "DIFFERS in %d of %d entries, max relative %.2e" % (int(bad.sum()), got.size, rel)))
+        else:
+            out.append((what, "DIFFERS in %d of %d entries" % (int((got != ref).sum()), got.size)))
+    mesh = gu.oracle_mesh(oracle, meta)
+    s = gu.oracle_solver(oracle, meta, mesh)
+    teno = meta["recon"]["type"] == "TENO"
+    if teno:
+        for k in sorted(d):
+            if k.startswith("teno:") and k not in ("teno:meta", "teno:quad_cell_points", "teno:quad_cell_weights"):
+                eq("oracle " + k, s.get(k), d[k])
+        mm = meta["mesh"]
+        r = meta["recon"]
+        pm = mb.Mesh.generate(mm["type"], mm["Nx"], mm["Ny"], mm["Lx"], mm["Ly"])
+        plan = mb.Plan(pm, "TENO", basis=r.get("basis_type", "monomial"), order=r["basis_order"], factor=r.get("max_stencil_size_factor", 2.0),
+                       quad_cell_order=r.get("quadrature_order_cell", 0), quad_face_order=r.get("quadrature_order_face", 0), bcs=meta["bcs"])
+        for k in TENO_KEYS_PLAN:
+            if k in d:
+                eq("preprocessor " + k, plan.get(k), d[k])
+    s.set_state(d["U0"], d["P0"])
+    F = s.calc_face_values().copy()
+    real = gu.real_faces(mesh.get("cells_of_face"), mesh.get("nodes_of_face"))
+    interior = real & (mesh.get("cells_of_face")[:, 1] >= 0)
+    eq("oracle F side 0", F[real][:, :, 0], d["F_stage1"][real][:, :, 0])
+    eq("oracle F side 1", F[interior][:, :, 1], d["F_stage1"][interior][:, :, 1])
+    eq("oracle rhs stage 1", s.calc_rhs(), d["rhs_stage1"])
+    try:
+        dt = s.calc_dt(meta["cfl"])
+        eq("oracle dt", np.array([dt]), d["step0:dt"])
+        s.take_step(dt)
+        n_rhs = {"FE": 1, "RK4": 4, "SSPRK3": 3}[meta["integrator"]]
+        for r_ in range(n_rhs):
+            eq("oracle rhs%d" % r_, s.get("rhs%d" % r_), d["step0:rhs%d" % r_])
+        eq("oracle U after the step", s.get("U"), d["step0:U"])
+        eq("oracle P after the step", s.get("P"), d["step0:P"])
+    except Exception as ex:      # the reference's dt turned non-finite / negative: the oracle throws where Solver::calc_dt throws
+        out.append(("oracle step", "calc_dt threw (%s); reference dt %r" % (str(ex)[:60], d.get("step0:dt"))))
+    return out
+
+
+def compare_kernels(case):
+    """--kernels: the CUDA kernel SOURCE executed on the host (tests/emul: teno_recon_kernel / the generic TENO kernel, face_flux_kernel,
+    gather_stage_kernel as nvcc compiles them, STRICT build and FMA-contracting FAST build) against the same dump of the reference:
+    face values and stage-1 residual.  -> [(what, error string)]: STRICT element-wise relative error, FAST relative to the field scale."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
+    from emulation import EmulatedSolver, fast_available
+    d = run_reference(case)
+    meta = {k: v for k, v in case.items() if k not in ("keep_mesh", "keep_teno")}
+    mm = meta["mesh"]
+    pm = mb.Mesh.generate(mm["type"], mm["Nx"], mm["Ny"], mm["Lx"], mm["Ly"])
+    cof = pm.arrays["cells_of_face"].reshape(-1, 2)
+    real = gu.real_faces(cof, pm.arrays["nodes_of_face"])
+    interior = real & (cof[:, 1] >= 0)
+    out = []
+    for fp in ("strict", "fast") if fast_available() else ("strict",):
+        es = EmulatedSolver(pm, fp_mode=fp, **gu.solver_kwargs(meta))
+        es.set_state(d["U0"])
+        F, rhs = es.calc_face_values(), es.calc_rhs()
+        err = gu.rel_err if fp == "strict" else gu.field_err
+        out.append((fp, max(err(F[real][:, :, 0], d["F_stage1"][real][:, :, 0]), err(F[interior][:, :, 1], d["F_stage1"][interior][:, :, 1])),
+                    err(rhs, d["rhs_stage1"])))
+        es.close()
+    return out
+
+
+def compare_meshes():
+    """--meshes: the three generators (mesh/mesh.cpp:305-848) over a grid of sizes and extents, incl. the degenerate ones: every
+    connectivity and geometry array and every zone of the oracle's AND of the product's host generator (mlb_host_mesh_generate)
+    against the reference's, bit for bit."""
+    grid = [("cartesian", nx, ny, Lx, Ly) for nx, ny, Lx, Ly in ((1, 1, 1.0, 1.0), (1, 4, 0.3, 1.0), (5, 1, 2.0, 0.1), (3, 7, 1.0, 1.5), (16, 9, 3.2, 0.7))]
+    grid += [("cartesian_tri", nx, ny, Lx, Ly) for nx, ny, Lx, Ly in ((1, 1, 1.0, 1.0), (1, 5, 0.2, 1.0), (6, 1, 2.0, 0.1), (4, 7, 1.3, 1.5), (13, 10, 0.9, 2.7))]
+    grid += [("wedge", nx, ny, Lx, Ly) for nx, ny, Lx, Ly in ((1, 1, 4.0, 1.5), (2, 2, 4.0, 1.5), (5, 3, 0.4, 1.0), (24, 8, 4.0, 1.5), (9, 17, 2.0, 0.6), (31, 5, 7.3, 1.1))]
+    n_bad = 0
+    print("# mesh generators against the unmodified reference: %d arrays + 5 zones per mesh, oracle and product (mlb_host_mesh_generate), bit for bit" % len(gu.MESH_KEYS))
+    for mtype, nx, ny, Lx, Ly in grid:
+        bcs = mg.SYM4
+        ic = mg.SMOOTH_IC
+        case = dict(mesh=dict(type=mtype, Nx=nx, Ny=ny, Lx=Lx, Ly=Ly), ic=ic, bcs=bcs, cfl=0.5, riemann="HLLC", integrator="FE", recon=dict(type="FO"), n_steps=1, every=1)
+        try:
+            d = run_reference(case)
+        except subprocess.CalledProcessError as ex:
+            print("%-14s %3d x %-3d [%g x %g]  reference refused the configuration (exit code %d)" % (mtype, nx, ny, Lx, Ly, ex.returncode), flush=True)
+            continue
+        om = oracle.Mesh.generate(mtype, nx, ny, Lx, Ly)
+        pm = mb.Mesh.generate(mtype, nx, ny, Lx, Ly)
+        bad = []
+        for who, get, zone in (("oracle", lambda k: om.get(k), lambda z: om.zone(z)), ("product", lambda k: pm.arrays[k], lambda z: dict(pm.zones)[z])):
+            for k in gu.MESH_KEYS:
+                ref = d[k]
+                got = np.asarray(get(k)).reshape(ref.shape)
+                if k == "face_normals":        # phantom faces: 0/0 = NaN in both
+                    if not np.array_equal(np.isnan(ref), np.isnan(got)):
+                        bad.append(who + " " + k + " (NaN pattern)")
+                    ref, got = np.nan_to_num(ref), np.nan_to_num(got)
+                if not np.array_equal(ref, got):
+                    bad.append(who + " " + k)
+            for i, z in enumerate(gu.ZONES):
+                if not np.array_equal(d["zone:%d:%s" % (i, z)], zone(z)):
+                    bad.append(who + " zone " + z)
+        print("%-14s %3d x %-3d [%g x %g]  %d cells  %s" % (mtype, nx, ny, Lx, Ly, pm.n_cells, "all bit-exact" if not bad else "DIFFER: " + ", ".join(bad)), flush=True)
+        n_bad += len(bad)
+    print("# %d differing arrays" % n_bad)
+    return 1 if n_bad else 0
+
+
+def cases():
+    smooth, riemann = mg.SMOOTH_IC, mg.RIEMANN2D_IC
+    sym, ext = mg.SYM4, mg.EXTRAP4
+
+    def teno(nx, ny, basis, order, factor=2.0, qc=0, qf=0, ic=smooth, bcs=sym, riemann_="HLLC", integ="SSPRK3", cfl=0.1, L=None):
+        r = dict(type="TENO", basis_type=basis, basis_order=order, max_stencil_size_factor=factor)
+        if qc:
+            r["quadrature_order_cell"] = qc
+        if qf:
+            r["quadrature_order_face"] = qf
+        Lx, Ly = L or (nx / 10.0, ny / 10.0 * 0.9)
+        return dict(mesh=dict(type="cartesian_tri", Nx=nx, Ny=ny, Lx=Lx, Ly=Ly), ic=ic, bcs=bcs, cfl=cfl, riemann=riemann_, integrator=integ,
+                    recon=r, n_steps=1, every=1)
+    # every order with both bases (mesh sized so that every stencil finds its M = 2 K cells)
+    size = {1: (6, 5), 2: (8, 7), 3: (9, 8), 4: (10, 9), 5: (12, 10), 6: (13, 11), 7: (14, 12), 8: (15, 13), 9: (16, 14)}
+    for order, basis in itertools.product(range(1, 10), ("legendre", "monomial")):
+        nx, ny = size[order]
+        yield "p%d %s" % (order, basis), teno(nx, ny, basis, order, qc=5 if order >= 5 else 0, bcs=ext if order % 2 else sym)
+    # stencil-size factors, cell / face quadrature orders the TOML may ask for, the other Riemann solvers and integrators
+    for factor in (1.5, 2.5, 3.0):
+        yield "p3 legendre factor %.1f" % factor, teno(12, 10, "legendre", 3, factor=factor)
+    yield "p2 monomial factor 3.0", teno(10, 9, "monomial", 2, factor=3.0, bcs=ext)
+    for qc in (1, 2, 4, 5):
+        yield "p3 legendre quadrature_order_cell %d" % qc, teno(9, 8, "legendre", 3, qc=qc)
+    for qf in (1, 3, 4, 5):
+        yield "p3 legendre quadrature_order_face %d" % qf, teno(9, 8, "legendre", 3, qf=qf, bcs=ext)
+    yield "p3 legendre Rusanov RK4 four-quadrant data", teno(9, 8, "legendre", 3, ic=riemann, riemann_="Rusanov", integ="RK4", L=(1.2, 1.1))
+    yield "p2 legendre HLL FE four-quadrant data", teno(8, 7, "legendre", 2, ic=riemann, riemann_="HLL", integ="FE", bcs=ext, L=(1.1, 1.2))
+    yield "p4 monomial HLLC RK4 cfl 0.4", teno(10, 9, "monomial", 4, integ="RK4", cfl=0.4, bcs=ext)
+    # TENO face states through every boundary functor (boundary/*.cpp), incl. an order only the generic kernel serves
+    mixed = [dict(name="left", type="upt", u=[0.5, 0.3], p=1.0, T=0.0036), dict(name="right", type="p_out", p=0.95),
+             dict(name="top", type="extrapolation"), dict(name="bottom", type="wall_adiabatic")]
+    yield "p2 monomial, upt / p_out / extrapolation / wall_adiabatic", teno(9, 8, "monomial", 2, bcs=mixed, integ="RK4", L=(1.0, 0.8))
+    yield "p5 legendre, upt / p_out / extrapolation / wall_adiabatic", teno(12, 10, "legendre", 5, qc=5, bcs=mixed, riemann_="HLL", L=(1.0, 0.8))
+    # the gas: another gamma and reference state; a pressure clamp (physics/physics.h:844) that bites inside the field
+    c = teno(9, 8, "legendre", 3, L=(1.0, 1.0)); c["physics"] = dict(gamma=1.667, p_ref=2.0e5, T_ref=350.0, rho_ref=0.9)
+    yield "p3 legendre, gamma 1.667 and another reference state", c
+    c = teno(9, 8, "monomial", 2, bcs=ext, L=(1.0, 1.0)); c["physics"] = dict(p_min=0.95, p_max=1.04)
+    yield "p2 monomial, pressure clamped to [0.95, 1.04]", c
+    c = dict(mesh=dict(type="wedge", Nx=24, Ny=8, Lx=4.0, Ly=1.5), ic=mg.WEDGE_IC, bcs=mg.WEDGE_BCS, cfl=0.7, riemann="HLLC", integrator="SSPRK3", recon=dict(type="FO"),
+             n_steps=1, every=1, physics=dict(gamma=1.3, p_ref=9.0e4, T_ref=280.0, rho_ref=1.1))
+    yield "first order wedge HLLC SSPRK3, gamma 1.3 and another reference state", c
+    # first order: the three generators with every Riemann solver
+    for mtype, nx, ny, Lx, Ly, ic, bcs in (("cartesian", 40, 3, 1.0, 0.075, mg.SOD_IC, sym), ("cartesian_tri", 11, 9, 1.1, 1.2, riemann, ext),
+                                           ("wedge", 24, 8, 4.0, 1.5, mg.WEDGE_IC, mg.WEDGE_WALL_BCS)):
+        for rs, integ in (("Rusanov", "RK4"), ("HLL", "SSPRK3"), ("HLLC", "FE")):
+            yield "first order %s %s %s" % (mtype, rs, integ), dict(mesh=dict(type=mtype, Nx=nx, Ny=ny, Lx=Lx, Ly=Ly), ic=ic, bcs=bcs, cfl=0.5, riemann=rs,
+                                                                      integrator=integ, recon=dict(type="FO"), n_steps=1, every=1)
+
+
+def main():
+    if not os.path.exists(mg.HARNESS):
+        raise SystemExit("oracle/_ref/bin/ref_harness is not built (oracle/build_ref.sh needs /root/reference)")
+    oracle.build()
+    sel = [x for x in sys.argv[1:] if not x.startswith("--")]
+    if "--meshes" in sys.argv:
+        return compare_meshes()
+    if "--kernels" in sys.argv:
+        print("# CUDA kernel source on the host (tests/emul) against the unmodified reference: max error of the face values / of the stage-1 residual;")
+        print("# STRICT build element-wise relative, FAST build (FMA contraction) relative to the field scale")
+        worst = {"strict": 0.0, "fast": 0.0}
+        for name, case in cases():
+            if sel and not any(x in name for x in sel):
+                continue
+            t0 = time.perf_counter()
+            try:
+                res = compare_kernels(case)
+            except subprocess.CalledProcessError as ex:
+                print("%-52s reference refused the configuration (exit code %d)" % (name, ex.returncode), flush=True)
+                continue
+            print("%-52s %s  (%.0f s)" % (name, "   ".join("%s F %.1e rhs %.1e" % r for r in res), time.perf_counter() - t0), flush=True)
+            for fp, eF, er in res:
+                worst[fp] = max(worst[fp], eF, er)
+        print("# worst: STRICT %.2e, FAST %.2e" % (worst["strict"], worst["fast"]))
+        return 0
+    n_bad = 0
+    print("# oracle restatement and preprocessor tables against the unmodified reference, one step per case, every array bit for bit")
+    for name, case in cases():
+        if sel and not any(x in name for x in sel):
+            continue
+        t0 = time.perf_counter()
+        try:
+            res = compare(case)
+        except subprocess.CalledProcessError as ex:
+            print("%-52s reference refused the configuration (exit code %d)" % (name, ex.returncode), flush=True)
+            continue
+        bad = [(w, v) for w, v in res if v != "ok" and not v.startswith("calc_dt threw")]
+        notes = [v for w, v in res if v.startswith("calc_dt threw")]
+        print("%-52s %2d arrays compared, %s  (%.0f s)%s" % (name, len(res), "all bit-exact" if not bad else "%d DIFFER" % len(bad), time.perf_counter() - t0,
+                                                            "  [" + notes[0] + "]" if notes else ""), flush=True)
+        for w, v in bad:
+            print("      %s: %s" % (w, v), flush=True)
+        n_bad += len(bad)
+    print("# %d differing arrays" % n_bad)
+    return 1 if n_bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

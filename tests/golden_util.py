@@ -31,6 +31,8 @@ def oracle_mesh(oracle, meta):
 def solver_kwargs(meta):
     r = meta["recon"]
     kw = dict(recon=r["type"], riemann=meta["riemann"], integrator=meta["integrator"], bcs=meta["bcs"])
+    if meta.get("physics"):
+        kw["gas"] = dict(meta["physics"])
     if r["type"] == "TENO":
         kw.update(basis=r.get("basis_type", "monomial"), order=r["basis_order"], factor=r.get("max_stencil_size_factor", 2.0),
                   quad_cell_order=r.get("quadrature_order_cell", 0), quad_face_order=r.get("quadrature_order_face", 0))

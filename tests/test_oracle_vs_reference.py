@@ -3,6 +3,8 @@
  (2) stage-level dumps of the unmodified reference (tests/golden/*.npz; oracle/make_golden.py).
 The oracle is compiled without FMA like the reference's x86-64 build, so (2) is asserted BIT-EXACT.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -111,3 +113,18 @@ def test_bit_exact_against_reference_dump(oracle_mod, name):
                 assert np.array_equal(s.get("rhs%d" % r), g[key + "rhs%d" % r], equal_nan=True), (i, r)
             assert np.array_equal(s.get("U"), g[key + "U"], equal_nan=True), i
             assert np.array_equal(s.get("P"), g[key + "P"], equal_nan=True), i
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "bin", "ref_harness")),
+                    reason="the unmodified reference is not built here (oracle/build_ref.sh needs /root/reference)")
+@pytest.mark.parametrize("case_name", ["p6 monomial", "p3 legendre quadrature_order_face 4", "p3 legendre factor 2.5", "first order wedge Rusanov RK4"])
+def test_pin_sweep_cases_run_live_against_the_unmodified_reference(oracle_mod, case_name):
+    """oracle/pin_sweep.py (profiles/r02h_pin_sweep.txt: 44 configurations, every array bit for bit) - a few of its cases run here, live:
+    the reference dumps a step on the spot, the oracle and the preprocessor's reference-layout tables must reproduce every array."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import pin_sweep
+    case = dict(pin_sweep.cases())[case_name]
+    res = pin_sweep.compare(case)
+    assert len(res) >= 7
+    assert all(v == "ok" for _, v in res), [(w, v) for w, v in res if v != "ok"]
