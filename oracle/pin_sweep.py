@@ -111,9 +111,27 @@ def compare_kernels(case):
         es.set_state(d["U0"])
         F, rhs = es.calc_face_values(), es.calc_rhs()
         err = gu.rel_err if fp == "strict" else gu.field_err
-        out.append((fp, max(err(F[real][:, :, 0], d["F_stage1"][real][:, :, 0]), err(F[interior][:, :, 1], d["F_stage1"][interior][:, :, 1])),
-                    err(rhs, d["rhs_stage1"])))
+        eF = max(err(F[real][:, :, 0], d["F_stage1"][real][:, :, 0]), err(F[interior][:, :, 1], d["F_stage1"][interior][:, :, 1]))
+        er = err(rhs, d["rhs_stage1"])
         es.close()
+        # one whole step through the emulated kernels (spectral radius / dt from the CFL kernel's body, every stage's face and gather
+        # kernels, the RK combination, the primitives of the last stage): dt, U and the primitives against the reference's
+        eU = None
+        if meta["integrator"] != "FE":                  # (the emulation's stepping entry point covers SSPRK3 / RK4)
+            from emulation import EmulatedAsSolver
+            ss = EmulatedAsSolver(pm, fp_mode=fp, **gu.solver_kwargs(meta))
+            ss.set_state(d["U0"], d["P0"])      # (as mlb_set_state(U, P): the reference steps from the primitives its initial condition defines)
+            try:
+                dt = ss.calc_dt(meta["cfl"])
+                ss.take_step()
+                U, P = ss.get_state(prim=True)
+                eU = max(err(np.array([dt]), d["step0:dt"]), err(U, d["step0:U"]), err(P, d["step0:P"]))
+            except mb.MallardError:
+                eU = float("nan")                         # dt not positive: the reference's is not either (four-quadrant data)
+                if np.isfinite(d["step0:dt"][0]) and d["step0:dt"][0] > 0:
+                    eU = float("inf")
+            ss.close()
+        out.append((fp, eF, er, eU))
     return out
 
 
@@ -215,7 +233,8 @@ def main():
     if "--meshes" in sys.argv:
         return compare_meshes()
     if "--kernels" in sys.argv:
-        print("# CUDA kernel source on the host (tests/emul) against the unmodified reference: max error of the face values / of the stage-1 residual;")
+        print("# CUDA kernel source on the host (tests/emul) against the unmodified reference: max error of the face values / of the stage-1 residual /")
+        print("# after one whole step (dt, U, primitives; nan = dt not positive in the reference either; - = FE, which the emulation does not step);")
         print("# STRICT build element-wise relative, FAST build (FMA contraction) relative to the field scale")
         worst = {"strict": 0.0, "fast": 0.0}
         for name, case in cases():
@@ -227,9 +246,10 @@ def main():
             except subprocess.CalledProcessError as ex:
                 print("%-52s reference refused the configuration (exit code %d)" % (name, ex.returncode), flush=True)
                 continue
-            print("%-52s %s  (%.0f s)" % (name, "   ".join("%s F %.1e rhs %.1e" % r for r in res), time.perf_counter() - t0), flush=True)
-            for fp, eF, er in res:
-                worst[fp] = max(worst[fp], eF, er)
+            print("%-52s %s  (%.0f s)" % (name, "   ".join("%s F %.1e rhs %.1e step %s" % (fp, eF, er, "-" if eU is None else "%.1e" % eU) for fp, eF, er, eU in res),
+                                        time.perf_counter() - t0), flush=True)
+            for fp, eF, er, eU in res:
+                worst[fp] = max(worst[fp], eF, er, eU if (eU is not None and eU == eU) else 0.0)
         print("# worst: STRICT %.2e, FAST %.2e" % (worst["strict"], worst["fast"]))
         return 0
     n_bad = 0

@@ -67,6 +67,7 @@ def lib(variant="strict"):
         L.emu_calc_dt.restype = C.c_double
         L.emu_calc_dt.argtypes = [C.c_void_p, C.c_double]
         L.emu_get_primitives.argtypes = [C.c_void_p, C.c_void_p]
+        L.emu_set_primitives.argtypes = [C.c_void_p, C.c_void_p]
         _LIB[variant] = L
     return _LIB[variant]
 
@@ -114,6 +115,12 @@ class EmulatedSolver:
         U = np.ascontiguousarray(U, dtype=np.float64)
         assert U.shape == (self.mesh.n_cells, 4)
         self._ok(self._L.emu_set_state(self._h, U.ctypes.data_as(C.c_void_p)))
+
+    def set_primitives(self, P):
+        """the P of mlb_set_state(U, P): primitives [n_cells][5] the stepping state starts from instead of those recomputed from U"""
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        assert P.shape == (self.mesh.n_cells, 5)
+        self._ok(self._L.emu_set_primitives(self._h, P.ctypes.data_as(C.c_void_p)))
 
     def calc_face_values(self):
         F = np.empty((self.mesh.n_faces, self.n_quad, 2, 4))
@@ -200,6 +207,8 @@ class EmulatedAsSolver:
 
     def set_state(self, U, P=None):
         self._e.set_state(U)
+        if P is not None:
+            self._e.set_primitives(P)
         self._dirty = False
 
     def calc_face_values(self):

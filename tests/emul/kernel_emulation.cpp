@@ -256,6 +256,15 @@ int emu_get_primitives(void * h, double * P_ref) {
     return 0;
 }
 
+// mlb_set_state with prim != NULL (api.cu: import_state): the stepping state's primitives are the caller's (the reference steps from the
+// primitives its initial condition defines, which need not be the ones recomputed from U in every bit); the density plane stays U's
+int emu_set_primitives(void * h, const double * P_ref) {
+    Emu & e = *static_cast<Emu *>(h);
+    for (uint32_t i = 0; i < e.P.N; i++)
+        for (int v = 0; v < 5; v++) e.prim[(size_t)v * e.P.Npad + i] = P_ref[5 * (size_t)e.P.perm_cells[i] + v];
+    return 0;
+}
+
 const char * emu_last_error() { return emu_err.c_str(); }
 
 // cell0_nodes != NULL: `mesh` is a rank-local mesh (mlb_create_local): the six node coordinates of the GLOBAL mesh's cell 0
