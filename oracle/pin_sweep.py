@@ -175,6 +175,101 @@ def compare_meshes():
     return 1 if n_bad else 0
 
 
+def compare_unstructured():
+    """--unstructured: the jittered, id-shuffled triangulations of the strong-scaling records (BASELINE configs[3] family,
+    mallard_b200.synthetic.jittered_tri) INJECTED into the unmodified reference (ref_harness `mesh` mode: the reference computes its own
+    geometry, stencils and matrices on the injected connectivity).  Compared bit for bit: geometry, every TENO table of the oracle and of
+    the preprocessor, face values, residuals, dt, U, P of the oracle; then the emulated kernels (STRICT / FAST) as in --kernels."""
+    from mallard_b200 import synthetic as syn
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
+    from emulation import EmulatedSolver, EmulatedAsSolver, fast_available
+    keys = ["node_coords", "offsets_nodes_of_cell", "nodes_of_cell", "offsets_faces_of_cell", "faces_of_cell", "offsets_nodes_of_face", "nodes_of_face",
+            "cells_of_face"]
+    n_bad = 0
+    print("# jittered, id-shuffled triangulations injected into the unmodified reference: oracle / preprocessor arrays bit for bit, emulated kernels as in --kernels")
+    grid = [(9, 8, 12345, 0.15, True, "legendre", 3, "HLLC", "SSPRK3"), (12, 10, 7, 0.15, True, "monomial", 2, "HLL", "RK4"), (10, 9, 3, 0.3, True, "legendre", 4, "Rusanov", "SSPRK3"),
+            (8, 7, 99, 0.15, False, "legendre", 1, "HLLC", "SSPRK3"), (13, 11, 5, 0.2, True, "legendre", 5, "HLLC", "SSPRK3"), (11, 9, 21, 0.15, True, None, 0, "HLLC", "SSPRK3")]
+    for nx, ny, seed, amp, shuffle, basis, order, rs, integ in grid:
+        mesh = syn.jittered_tri(nx, ny, 1.0, 0.9, seed=seed, amp=amp, shuffle=shuffle)
+        a = mesh.arrays
+        recon = dict(type="FO") if basis is None else dict(type="TENO", basis_type=basis, basis_order=order, max_stencil_size_factor=2.0)
+        if order >= 5:
+            recon["quadrature_order_cell"] = 5
+        case = dict(mesh=dict(type="cartesian_tri", Nx=nx, Ny=ny, Lx=1.0, Ly=0.9), ic=mg.SMOOTH_IC, bcs=mg.EXTRAP4, cfl=0.1, riemann=rs, integrator=integ, recon=recon,
+                    n_steps=1, every=1)
+        name = "%dx%d seed %d amp %.2f %s, %s" % (nx, ny, seed, amp, "shuffled" if shuffle else "ordered",
+                                                  "first order" if basis is None else "p%d %s" % (order, basis)) + " " + rs + " " + integ
+        t0 = time.perf_counter()
+        with tempfile.TemporaryDirectory() as td:
+            toml, inj, out = os.path.join(td, "input.toml"), os.path.join(td, "mesh.mlbd"), os.path.join(td, "out.mlbd")
+            mg.write_toml(case, toml)
+            rec = {k: (a[k].reshape(-1, 2) if k in ("node_coords", "cells_of_face") else a[k]) for k in keys}
+            for i, (zn, zf) in enumerate(mesh.zones):
+                rec["zone:%d:%s" % (i, zn)] = np.ascontiguousarray(zf, dtype=np.uint32)
+            mlbd.write(inj, rec)
+            subprocess.check_call([mg.HARNESS, "mesh", inj, toml, out, "1", "1"], env=dict(os.environ, OMP_NUM_THREADS="1", OMP_PROC_BIND="false"),
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            d = mlbd.read(out)
+        bad, n_cmp = [], 0
+
+        def eq(what, got, ref):
+            nonlocal n_cmp
+            n_cmp += 1
+            got = np.asarray(got).reshape(np.asarray(ref).shape)
+            if not np.array_equal(got, ref, equal_nan=True):
+                bad.append(what)
+        for k in ("cell_coords", "cell_volume", "face_area", "face_normals"):
+            eq("product geometry " + k, a[k], d[k])
+        om = oracle.Mesh.from_arrays({k: a[k] for k in keys}, mesh.zones)
+        for k in ("cell_coords", "cell_volume", "face_area", "face_normals"):
+            eq("oracle geometry " + k, om.get(k), d[k])
+        kw = dict(recon=recon["type"], riemann=rs, integrator=integ, bcs=mg.EXTRAP4)
+        if basis is not None:
+            kw.update(basis=basis, order=order, factor=2.0, quad_cell_order=recon.get("quadrature_order_cell", 0))
+        so = oracle.Solver(om, **kw)
+        if basis is not None:
+            plan = mb.Plan(mesh, "TENO", basis=basis, order=order, factor=2.0, quad_cell_order=recon.get("quadrature_order_cell", 0), bcs=mg.EXTRAP4)
+            for k in sorted(d):
+                if k.startswith("teno:") and k not in ("teno:meta", "teno:quad_cell_points", "teno:quad_cell_weights"):
+                    eq("oracle " + k, so.get(k), d[k])
+                    if k in TENO_KEYS_PLAN:
+                        eq("preprocessor " + k, plan.get(k), d[k])
+        so.set_state(d["U0"], d["P0"])
+        F = so.calc_face_values().copy()
+        cof = a["cells_of_face"].reshape(-1, 2)
+        interior = cof[:, 1] >= 0
+        eq("oracle F side 0", F[:, :, 0], d["F_stage1"][:, :, 0])
+        eq("oracle F side 1", F[interior][:, :, 1], d["F_stage1"][interior][:, :, 1])
+        eq("oracle rhs stage 1", so.calc_rhs(), d["rhs_stage1"])
+        dt = so.calc_dt(0.1)
+        eq("oracle dt", np.array([dt]), d["step0:dt"])
+        so.take_step(dt)
+        eq("oracle U after the step", so.get("U"), d["step0:U"])
+        eq("oracle P after the step", so.get("P"), d["step0:P"])
+        kern = []
+        for fp in ("strict", "fast") if fast_available() else ("strict",):
+            err = gu.rel_err if fp == "strict" else gu.field_err
+            es = EmulatedSolver(mesh, fp_mode=fp, **kw)
+            es.set_state(d["U0"])
+            Fe, re_ = es.calc_face_values(), es.calc_rhs()
+            eF = max(err(Fe[:, :, 0], d["F_stage1"][:, :, 0]), err(Fe[interior][:, :, 1], d["F_stage1"][interior][:, :, 1]))
+            er = err(re_, d["rhs_stage1"])
+            es.close()
+            ss = EmulatedAsSolver(mesh, fp_mode=fp, **kw)
+            ss.set_state(d["U0"], d["P0"])
+            dte = ss.calc_dt(0.1)
+            ss.take_step()
+            U, P = ss.get_state(prim=True)
+            eU = max(err(np.array([dte]), d["step0:dt"]), err(U, d["step0:U"]), err(P, d["step0:P"]))
+            ss.close()
+            kern.append("%s F %.1e rhs %.1e step %.1e" % (fp, eF, er, eU))
+        print("%-62s %2d arrays: %s | kernels: %s  (%.0f s)" % (name, n_cmp, "all bit-exact" if not bad else "DIFFER: " + ", ".join(bad), "   ".join(kern),
+                                                              time.perf_counter() - t0), flush=True)
+        n_bad += len(bad)
+    print("# %d differing arrays" % n_bad)
+    return 1 if n_bad else 0
+
+
 def cases():
     smooth, riemann = mg.SMOOTH_IC, mg.RIEMANN2D_IC
     sym, ext = mg.SYM4, mg.EXTRAP4
@@ -230,6 +325,8 @@ def main():
         raise SystemExit("oracle/_ref/bin/ref_harness is not built (oracle/build_ref.sh needs /root/reference)")
     oracle.build()
     sel = [x for x in sys.argv[1:] if not x.startswith("--")]
+    if "--unstructured" in sys.argv:
+        return compare_unstructured()
     if "--meshes" in sys.argv:
         return compare_meshes()
     if "--kernels" in sys.argv:
