@@ -189,15 +189,22 @@ def compare_unstructured():
     print("# jittered, id-shuffled triangulations injected into the unmodified reference: oracle / preprocessor arrays bit for bit, emulated kernels as in --kernels")
     grid = [(9, 8, 12345, 0.15, True, "legendre", 3, "HLLC", "SSPRK3"), (12, 10, 7, 0.15, True, "monomial", 2, "HLL", "RK4"), (10, 9, 3, 0.3, True, "legendre", 4, "Rusanov", "SSPRK3"),
             (8, 7, 99, 0.15, False, "legendre", 1, "HLLC", "SSPRK3"), (13, 11, 5, 0.2, True, "legendre", 5, "HLLC", "SSPRK3"), (11, 9, 21, 0.15, True, None, 0, "HLLC", "SSPRK3")]
+    # mixed triangle / quadrilateral meshes (BASELINE configs[3] as worded): first order only - the reference's TENO refuses quadrilaterals
+    grid += [(10, 8, 4, 0.15, True, "mixed", 0, "HLLC", "SSPRK3"), (9, 11, 8, 0.25, True, "mixed", 0, "Rusanov", "RK4")]
     for nx, ny, seed, amp, shuffle, basis, order, rs, integ in grid:
-        mesh = syn.jittered_tri(nx, ny, 1.0, 0.9, seed=seed, amp=amp, shuffle=shuffle)
+        mixed = basis == "mixed"
+        if mixed:
+            basis = None
+            mesh = syn.mixed_tri_quad(nx, ny, 1.0, 0.9, seed=seed, amp=amp, tri_fraction=0.5, shuffle=shuffle)
+        else:
+            mesh = syn.jittered_tri(nx, ny, 1.0, 0.9, seed=seed, amp=amp, shuffle=shuffle)
         a = mesh.arrays
         recon = dict(type="FO") if basis is None else dict(type="TENO", basis_type=basis, basis_order=order, max_stencil_size_factor=2.0)
         if order >= 5:
             recon["quadrature_order_cell"] = 5
         case = dict(mesh=dict(type="cartesian_tri", Nx=nx, Ny=ny, Lx=1.0, Ly=0.9), ic=mg.SMOOTH_IC, bcs=mg.EXTRAP4, cfl=0.1, riemann=rs, integrator=integ, recon=recon,
                     n_steps=1, every=1)
-        name = "%dx%d seed %d amp %.2f %s, %s" % (nx, ny, seed, amp, "shuffled" if shuffle else "ordered",
+        name = "%s%dx%d seed %d amp %.2f %s, %s" % ("mixed tri/quad " if mixed else "", nx, ny, seed, amp, "shuffled" if shuffle else "ordered",
                                                   "first order" if basis is None else "p%d %s" % (order, basis)) + " " + rs + " " + integ
         t0 = time.perf_counter()
         with tempfile.TemporaryDirectory() as td:
