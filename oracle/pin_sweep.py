@@ -189,6 +189,7 @@ def compare_unstructured():
     print("# jittered, id-shuffled triangulations injected into the unmodified reference: oracle / preprocessor arrays bit for bit, emulated kernels as in --kernels")
     grid = [(9, 8, 12345, 0.15, True, "legendre", 3, "HLLC", "SSPRK3"), (12, 10, 7, 0.15, True, "monomial", 2, "HLL", "RK4"), (10, 9, 3, 0.3, True, "legendre", 4, "Rusanov", "SSPRK3"),
             (8, 7, 99, 0.15, False, "legendre", 1, "HLLC", "SSPRK3"), (13, 11, 5, 0.2, True, "legendre", 5, "HLLC", "SSPRK3"), (11, 9, 21, 0.15, True, None, 0, "HLLC", "SSPRK3")]
+    grid += [(48, 40, 12345, 0.15, True, "legendre", 3, "HLLC", "SSPRK3")]      # 3840 cells: the bench's numerics on a mesh with thousands of distinct stencils
     # mixed triangle / quadrilateral meshes (BASELINE configs[3] as worded): first order only - the reference's TENO refuses quadrilaterals
     grid += [(10, 8, 4, 0.15, True, "mixed", 0, "HLLC", "SSPRK3"), (9, 11, 8, 0.25, True, "mixed", 0, "Rusanov", "RK4")]
     for nx, ny, seed, amp, shuffle, basis, order, rs, integ in grid:
