@@ -89,6 +89,12 @@ def test_reference_dumps_behind_the_gate(emulated, monkeypatch, name, fp):
     gp.test_against_reference_dumps(name, fp)
 
 
+def test_injected_jittered_mesh_against_the_unmodified_reference(emulated, tmp_path, capsys):
+    if not os.path.exists(gp.REF_HARNESS):
+        pytest.skip("the unmodified reference is not built here")
+    gp.test_multi_tile_streaming_path_vs_unmodified_reference_on_an_injected_jittered_mesh(tmp_path, capsys)
+
+
 def test_run_from_a_gmsh_file(emulated, tmp_path):
     """Not gated, but the reader moved behind the C ABI (csrc/mesh_io.cpp) after the GPU suite last ran: the same check with the emulated kernels."""
     gp.test_mesh_read_from_a_gmsh_file_runs_like_the_same_mesh_from_arrays(tmp_path)

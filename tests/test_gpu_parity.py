@@ -426,6 +426,55 @@ def test_multi_tile_streaming_path_vs_unmodified_reference_128x128(tmp_path, cap
         print("\n128x128 (32768 cells) against the unmodified reference:\n  " + "\n  ".join(report))
 
 
+@pytest.mark.skipif(not os.path.exists(REF_HARNESS), reason="oracle/_ref/bin/ref_harness not built (needs /root/reference)")
+@UNVERIFIED_ON_HARDWARE
+def test_multi_tile_streaming_path_vs_unmodified_reference_on_an_injected_jittered_mesh(tmp_path, capsys):
+    """The unstructured counterpart of the 128^2 test: a jittered, id-shuffled 110 x 100 triangulation (22 000 cells: several tiles per
+    warp of the streaming kernels, BASELINE configs[3] family) is INJECTED into the unmodified reference (`ref_harness mesh`; the reference
+    has no generator for it and computes its own geometry, stencils and matrices on the injected connectivity); stage-1 face values, the
+    residual, dt and the state after the step, STRICT and FAST, against its dump.  (oracle/pin_sweep.py --unstructured is the same
+    comparison for the oracle, the preprocessor and the emulated kernels on smaller meshes.)"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import make_golden as mg
+    import mlbd
+    from mallard_b200 import synthetic as syn
+    mesh = syn.jittered_tri(110, 100, 1.0, 0.9, seed=12345)
+    a = mesh.arrays
+    case = dict(mesh=dict(type="cartesian_tri", Nx=110, Ny=100, Lx=1.0, Ly=0.9), ic=mg.SMOOTH_IC, bcs=mg.EXTRAP4, cfl=0.1,
+                riemann="HLLC", integrator="SSPRK3", recon=mg.TENO3, n_steps=1)
+    toml, inj, out = str(tmp_path / "input.toml"), str(tmp_path / "mesh.mlbd"), str(tmp_path / "out.mlbd")
+    mg.write_toml(case, toml)
+    rec = {k: (a[k].reshape(-1, 2) if k in ("node_coords", "cells_of_face") else a[k]) for k in
+           ("node_coords", "offsets_nodes_of_cell", "nodes_of_cell", "offsets_faces_of_cell", "faces_of_cell", "offsets_nodes_of_face", "nodes_of_face", "cells_of_face")}
+    for i, (zn, zf) in enumerate(mesh.zones):
+        rec["zone:%d:%s" % (i, zn)] = np.ascontiguousarray(zf, dtype=np.uint32)
+    mlbd.write(inj, rec)
+    env = dict(os.environ, OMP_NUM_THREADS="1", OMP_PROC_BIND="false")
+    subprocess.check_call([REF_HARNESS, "mesh", inj, toml, out, "1", "1"], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    g = mlbd.read(out)
+    os.remove(out)
+    assert mesh.n_cells == 22000 and np.array_equal(a["cell_volume"].reshape(-1), g["cell_volume"].reshape(-1))      # the reference's own geometry
+    interior = a["cells_of_face"].reshape(-1, 2)[:, 1] >= 0
+    report = []
+    for fp in ("strict", "fast"):
+        s = mb.Solver(mesh, "TENO", "HLLC", "SSPRK3", order=3, bcs=syn.EXTRAP4, fp_mode=fp)
+        s.set_state(g["U0"], g["P0"])
+        F = s.calc_face_values()
+        _check_against("F side 0", fp, F[:, :, 0], g["F_stage1"][:, :, 0], TOL, report)
+        _check_against("F side 1", fp, F[interior][:, :, 1], g["F_stage1"][interior][:, :, 1], TOL, report)
+        _check_against("rhs", fp, s.calc_rhs(), g["rhs_stage1"], TOL if fp == "strict" else 1e-10, report)
+        dt = s.calc_dt(0.1)
+        assert abs(dt - g["step0:dt"][0]) <= TOL * dt
+        s.take_step()
+        U, P = s.get_state(prim=True)
+        _check_against("U", fp, U, g["step0:U"], TOL, report)
+        _check_against("P", fp, P, g["step0:P"], TOL, report)
+        s.close()
+    with capsys.disabled():
+        print("\njittered 110x100 (22000 cells) injected into the unmodified reference:\n  " + "\n  ".join(report))
+
+
 @pytest.mark.parametrize("fp", ["strict", "fast"])
 def test_multi_tile_streaming_path_vs_oracle_jittered_22k(oracle_mod, fp, capsys):
     """The same on an unstructured numbering: jittered, id-shuffled 110 x 100 triangulation (22 000 cells), vortex, against the

@@ -26,7 +26,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GROUPS = {
     "generic_teno_kernel": ("test_generic_teno_kernel_is_bit_identical_to_the_specialised_one or test_teno_orders_5_to_9_and_other_stencil_factors_vs_oracle "
                             "or (test_against_reference_dumps and (teno_legendre_12x10_p5 or teno_legendre_8x7_p2_f15 or teno_monomial_14x12_p7 or teno_legendre_16x14_p9))"),
-    "late_reference_fixtures": "test_against_reference_dumps and (teno_bcs_rk4_10x8 or teno_hll_riemann_9x7)",
+    "late_reference_fixtures": ("(test_against_reference_dumps and (teno_bcs_rk4_10x8 or teno_hll_riemann_9x7)) "
+                                "or test_multi_tile_streaming_path_vs_unmodified_reference_on_an_injected_jittered_mesh"),
     "cooperative_small_mesh_kernel": "test_cooperative_small_mesh_kernel_equals_the_multi_kernel_path",
     "quadrilaterals_under_teno": "test_teno_on_quadrilateral_and_mixed_meshes_is_k_exact or test_first_order_on_a_mixed_mesh_matches_oracle",
     "viscous_terms": ("test_viscous_residual_of_couette_flow or test_decaying_shear_layer_follows_the_diffusion_equation or test_steady_heat_conduction_between_isothermal_walls or test_couette_flow_under_teno_is_a_steady_state_up_to_viscous_heating "
