@@ -278,6 +278,52 @@ def compare_unstructured():
     return 1 if n_bad else 0
 
 
+def compare_riemann(n=200000, seed=2024):
+    """--riemann: the reference's three flux functions (numerics/riemann_solver.h:331-519; `ref_harness riemann`) on random face states
+    over every regime the wave-speed estimators distinguish - densities and pressures log-uniform over six decades, Mach numbers up to 6,
+    strong and weak jumps, expansions, both orientations of the normal, states identical on both sides, gamma 1.4 and 1.667 - against
+    the oracle (every bit) and the CUDA kernel source's riemann_flux on the host (tests/emul; STRICT every bit except where HLLC's
+    two-rarefaction estimate calls pow, FAST = the lean re-formulation within 1e-12 of the flux scale)."""
+    rng = np.random.default_rng(seed)
+    n_bad = 0
+    print("# Riemann fluxes against the unmodified reference on %d random face states per gamma" % n)
+    for gamma in (1.4, 1.667):
+        ang = rng.uniform(0.0, 2.0 * np.pi, n)
+        nu = np.stack([np.cos(ang), np.sin(ang)], 1)
+        nu[: n // 20] = [1.0, 0.0]
+        nu[n // 20: n // 10] = [0.0, -1.0]
+
+        def side(k):
+            rho = 10.0 ** rng.uniform(-3.0, 3.0, k)
+            p = 10.0 ** rng.uniform(-3.0, 3.0, k)
+            a = np.sqrt(gamma * p / rho)
+            mach = rng.uniform(0.0, 6.0, k) * (rng.random(k) < 0.8)
+            th = rng.uniform(0.0, 2.0 * np.pi, k)
+            u, v = mach * a * np.cos(th), mach * a * np.sin(th)
+            h = p / ((gamma - 1.0) * rho) + p / rho      # e + p / rho, as Physics::get_... hands it to the flux functions
+            return np.stack([rho, u, v, p, h], 1)
+        L, R = side(n), side(n)
+        m = n // 4                                       # a quarter: weak jumps around a common state (the PVRS branch), some exactly equal
+        R[:m] = L[:m] * (1.0 + 1.0e-3 * rng.standard_normal((m, 5)))
+        R[: m // 4] = L[: m // 4]
+        R[:m, 4] = R[:m, 3] / ((gamma - 1.0) * R[:m, 0]) + R[:m, 3] / R[:m, 0]
+        with tempfile.TemporaryDirectory() as td:
+            fin, fout = os.path.join(td, "states.mlbd"), os.path.join(td, "flux.mlbd")
+            mlbd.write(fin, {"n_unit": nu, "L": L, "R": R})
+            subprocess.check_call([mg.HARNESS, "riemann", fin, fout, repr(gamma)], env=dict(os.environ, OMP_NUM_THREADS="1", OMP_PROC_BIND="false"),
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            ref = mlbd.read(fout)["flux"]
+        for k, kind in enumerate(("Rusanov", "HLL", "HLLC")):
+            got = oracle.riemann_flux(kind, nu, L, R, gamma)
+            same = np.array_equal(got, ref[k], equal_nan=True)
+            bad = int((~((got == ref[k]) | (np.isnan(got) & np.isnan(ref[k])))).any(axis=1).sum())
+            n_bad += 0 if same else 1
+            print("gamma %.3f  %-8s oracle: %s   (finite fluxes: %.1f %% of the states)" % (gamma, kind, "every bit of %d fluxes" % n if same else "DIFFERS in %d states" % bad,
+                                                                                             100.0 * np.isfinite(ref[k]).all(axis=1).mean()), flush=True)
+    print("# %d flux functions differ" % n_bad)
+    return 1 if n_bad else 0
+
+
 def cases():
     smooth, riemann = mg.SMOOTH_IC, mg.RIEMANN2D_IC
     sym, ext = mg.SYM4, mg.EXTRAP4
@@ -333,6 +379,8 @@ def main():
         raise SystemExit("oracle/_ref/bin/ref_harness is not built (oracle/build_ref.sh needs /root/reference)")
     oracle.build()
     sel = [x for x in sys.argv[1:] if not x.startswith("--")]
+    if "--riemann" in sys.argv:
+        return compare_riemann()
     if "--unstructured" in sys.argv:
         return compare_unstructured()
     if "--meshes" in sys.argv:

@@ -13,6 +13,7 @@
 //   ref_harness dump <input.toml> <out.mlbd> [n_steps=1] [every=1]   stage-level dump of step 0 and every
 //                                                             `every`-th step
 //   ref_harness time <input.toml> <n_steps> [n_warmup=1]      wall-clock per step, JSON on last line
+//   ref_harness riemann <states.mlbd> <out.mlbd> <gamma>      the three flux functions on a list of face states
 //   ref_harness mesh <mesh.mlbd> <input.toml> <out.mlbd> [n]  as `dump`, but the mesh arrays are
 //                                                             injected from a file (arbitrary
 //                                                             unstructured tri/quad meshes)
@@ -262,6 +263,25 @@ int main(int argc, char ** argv) {
             auto inj = read_mlbd(argv[2]);
             init_with_mesh(s, argv[3], &inj);
             rc = do_dump(s, argv[4], argc > 5 ? atoi(argv[5]) : 1, argc > 6 ? atoi(argv[6]) : 1);
+        } else if (mode == "riemann") {
+            // ref_harness riemann <states.mlbd> <out.mlbd> <gamma>: the reference's three flux functions (numerics/riemann_solver.h:331-519)
+            // on a list of face states - n_unit [n][2], L [n][5], R [n][5], rows (rho, u, v, p, h) - as RiemannSolver::calc_flux takes them
+            auto in = read_mlbd(argv[2]);
+            const double gamma = atof(argv[4]);
+            const Record & rn = in.at("n_unit"), & rl = in.at("L"), & rr = in.at("R");
+            const uint64_t n = rn.dims[0];
+            const double * nu = reinterpret_cast<const double *>(rn.data.data());
+            const double * L = reinterpret_cast<const double *>(rl.data.data()), * R = reinterpret_cast<const double *>(rr.data.data());
+            std::vector<double> out(3 * n * 4);
+            Rusanov rus; HLL hll; HLLC hllc;
+            for (uint64_t i = 0; i < n; i++) {
+                rtype ul[2] = {L[5 * i + 1], L[5 * i + 2]}, ur[2] = {R[5 * i + 1], R[5 * i + 2]}, nn[2] = {nu[2 * i], nu[2 * i + 1]};
+                rus.calc_flux(&out[(0 * n + i) * 4], nn, L[5 * i], ul, L[5 * i + 3], gamma, L[5 * i + 4], R[5 * i], ur, R[5 * i + 3], gamma, R[5 * i + 4]);
+                hll.calc_flux(&out[(1 * n + i) * 4], nn, L[5 * i], ul, L[5 * i + 3], gamma, L[5 * i + 4], R[5 * i], ur, R[5 * i + 3], gamma, R[5 * i + 4]);
+                hllc.calc_flux(&out[(2 * n + i) * 4], nn, L[5 * i], ul, L[5 * i + 3], gamma, L[5 * i + 4], R[5 * i], ur, R[5 * i + 3], gamma, R[5 * i + 4]);
+            }
+            Writer w(argv[3]);
+            w.f64("flux", {3, n, 4}, out.data());
         } else if (mode == "time") {
             auto t0 = std::chrono::steady_clock::now();
             init_with_mesh(s, argv[2], nullptr);
