@@ -68,8 +68,20 @@ def lib(variant="strict"):
         L.emu_calc_dt.argtypes = [C.c_void_p, C.c_double]
         L.emu_get_primitives.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_set_primitives.argtypes = [C.c_void_p, C.c_void_p]
+        L.emu_riemann_flux.argtypes = [C.c_int, C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         _LIB[variant] = L
     return _LIB[variant]
+
+
+def riemann_flux(kind, n_unit, L, R, gamma=1.4, fp_mode="strict"):
+    """mallard_b200.riemann_flux through the emulated kernel source: rows (rho, u, v, p, h), kind in Rusanov / HLL / HLLC."""
+    n_unit = np.ascontiguousarray(n_unit, dtype=np.float64).reshape(-1, 2)
+    L = np.ascontiguousarray(L, dtype=np.float64).reshape(-1, 5)
+    R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 5)
+    out = np.empty((L.shape[0], 4))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)      # noqa: E731
+    lib(fp_mode).emu_riemann_flux(mb.RIEMANN[kind], L.shape[0], p(n_unit), p(L), p(R), float(gamma), p(out))
+    return out
 
 
 class EmulatedSolver:

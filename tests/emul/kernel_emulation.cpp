@@ -203,6 +203,20 @@ void steps_small(Emu & e, uint32_t n_steps, double cfl, unsigned blocks) {
 
 }  // namespace
 
+// mlb_riemann_flux (the body of riemann_kernel, kernels_impl.cuh): the flux function this build's face kernel calls - riemann_flux in the
+// STRICT build, the lean re-formulation in the FAST build - on a list of face states, rows (rho, u, v, p, h)
+template <int RS>
+static void riemann_list(uint64_t n, const double * nunit, const double * L, const double * R, double gamma, double * flux) {
+    for (uint64_t i = 0; i < n; i++) {
+        const emu::FaceState l = {L[5 * i], L[5 * i + 1], L[5 * i + 2], L[5 * i + 3], L[5 * i + 4]};
+        const emu::FaceState r = {R[5 * i], R[5 * i + 1], R[5 * i + 2], R[5 * i + 3], R[5 * i + 4]};
+#ifdef MLB_STREAM_KERNELS
+        emu::riemann_flux_lean<RS>(&flux[4 * i], nunit[2 * i], nunit[2 * i + 1], emu::face_cons(l), emu::face_cons(r), gamma);
+#else
+        emu::riemann_flux<RS>(&flux[4 * i], nunit[2 * i], nunit[2 * i + 1], l, r, gamma);
+#endif
+    }
+}
 extern "C" {
 
 // n_steps time steps of a first-order context from its current state.  cfl > 0: dt from the CFL condition every step, else the fixed
@@ -262,6 +276,15 @@ int emu_set_primitives(void * h, const double * P_ref) {
     Emu & e = *static_cast<Emu *>(h);
     for (uint32_t i = 0; i < e.P.N; i++)
         for (int v = 0; v < 5; v++) e.prim[(size_t)v * e.P.Npad + i] = P_ref[5 * (size_t)e.P.perm_cells[i] + v];
+    return 0;
+}
+
+int emu_riemann_flux(int riemann, unsigned long long n, const double * nunit, const double * L, const double * R, double gamma, double * flux) {
+    switch (riemann) {
+        case MLB_RIEMANN_RUSANOV: riemann_list<MLB_RIEMANN_RUSANOV>(n, nunit, L, R, gamma, flux); break;
+        case MLB_RIEMANN_HLL: riemann_list<MLB_RIEMANN_HLL>(n, nunit, L, R, gamma, flux); break;
+        default: riemann_list<MLB_RIEMANN_HLLC>(n, nunit, L, R, gamma, flux); break;
+    }
     return 0;
 }
 

@@ -144,3 +144,24 @@ def test_unstructured_meshes_injected_into_the_unmodified_reference(oracle_mod, 
     assert out.count("all bit-exact") == 9 and "DIFFER" not in out
     strict = [l.split("kernels: strict ")[1].split("   fast")[0] for l in out.splitlines() if "kernels: strict" in l]
     assert sum(s == "F 0.0e+00 rhs 0.0e+00 step 0.0e+00" for s in strict) >= 8 and all(s.endswith("step 0.0e+00") for s in strict)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "bin", "ref_harness")),
+                    reason="the unmodified reference is not built here (oracle/build_ref.sh needs /root/reference)")
+def test_riemann_fluxes_on_random_states_against_the_unmodified_reference(oracle_mod, capsys):
+    """oracle/pin_sweep.py --riemann, live on 30 000 states per gamma: densities and pressures over six decades, Mach numbers up to 6, weak jumps
+    and identical states - the reference's own flux functions (`ref_harness riemann`) against the oracle (every bit, non-finite results
+    included) and against the kernel source's flux functions on the host: STRICT every bit, FAST (the lean re-formulation) within 1e-10 of
+    the flux scale everywhere and within 1e-12 on all but a handful of near-vacuum contact states."""
+    import re
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import pin_sweep
+    assert pin_sweep.compare_riemann(n=30000, seed=7) == 0
+    out = capsys.readouterr().out
+    assert out.count("oracle: every bit of 30000 fluxes") == 6
+    assert out.count("kernel STRICT: 0 states differ (max 0.0e+00 of the flux scale), non-finite pattern equal") == 6
+    fast = re.findall(r"FAST \(lean\): max (\S+) of the flux scale \((\d+) of (\d+) states above 1e-12\), (\d+) states finite in one", out)
+    assert len(fast) == 6
+    for mx, above, total, mismatch in fast:
+        assert float(mx) <= 1e-10 and int(above) <= 1e-3 * int(total) and int(mismatch) == 0
