@@ -341,6 +341,54 @@ def compare_riemann(n=200000, seed=2024):
     return 1 if n_bad else 0
 
 
+def compare_prims(n=200000, seed=11):
+    """--prims: Euler::compute_primitives_from_conservatives (physics/physics.h:826-860; `ref_harness prims`) on random conserved states -
+    magnitudes over six decades, supersonic and nearly static, states whose internal energy is negative (the clamp's and Q14's territory:
+    fmin(p_max, NaN)), an active clamp - against the oracle and the kernel source's cons_to_prim on the host, every bit."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
+    import emulation
+    rng = np.random.default_rng(seed)
+    n_bad = 0
+    print("# primitives of %d random conserved states per gas against the unmodified reference" % n)
+    for gas in (dict(), dict(gamma=1.667, p_ref=2.0e5, T_ref=350.0, rho_ref=0.9), dict(p_min=0.5, p_max=40.0), dict(gamma=1.3, p_min=1.0e-2, p_max=1.0e2)):
+        g = dict(gamma=1.4, p_ref=101325.0, T_ref=298.15, rho_ref=1.225, p_min=-1e20, p_max=1e20)
+        g.update(gas)
+        rho = 10.0 ** rng.uniform(-3.0, 3.0, n)
+        p = 10.0 ** rng.uniform(-3.0, 3.0, n)
+        a = np.sqrt(g["gamma"] * p / rho)
+        mach = rng.uniform(0.0, 8.0, n) * (rng.random(n) < 0.8)
+        th = rng.uniform(0.0, 2.0 * np.pi, n)
+        u, v = mach * a * np.cos(th), mach * a * np.sin(th)
+        E = p / (g["gamma"] - 1.0) + 0.5 * rho * (u * u + v * v)
+        E[: n // 20] *= rng.uniform(0.0, 1.0, n // 20)            # less total energy than the kinetic energy alone: negative pressure before the clamp
+        U = np.stack([rho, rho * u, rho * v, E], 1)
+        U[n // 20: n // 20 + 50, 3] = np.nan                      # Q14: a NaN energy comes out as p_max
+        with tempfile.TemporaryDirectory() as td:
+            fin, fout = os.path.join(td, "U.mlbd"), os.path.join(td, "P.mlbd")
+            mlbd.write(fin, {"U": U, "gas": np.array([g[k] for k in ("gamma", "p_ref", "T_ref", "rho_ref", "p_min", "p_max")])})
+            subprocess.check_call([mg.HARNESS, "prims", fin, fout, repr(g["gamma"])], env=dict(os.environ, OMP_NUM_THREADS="1", OMP_PROC_BIND="false"),
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            ref = mlbd.read(fout)["P"]
+        po = oracle.prims(U, g)[0]
+        res = ["oracle " + ("every bit" if np.array_equal(po, ref, equal_nan=True) else "DIFFERS in %d states" % int((~((po == ref) | (np.isnan(po) & np.isnan(ref)))).any(axis=1).sum()))]
+        n_bad += 0 if np.array_equal(po, ref, equal_nan=True) else 1
+        for fp in ("strict", "fast") if emulation.fast_available() else ("strict",):
+            pk = emulation.primitives(U, g, fp)
+            same = np.array_equal(pk, ref, equal_nan=True)
+            if fp == "strict":
+                n_bad += 0 if same else 1
+                res.append("kernel STRICT " + ("every bit" if same else "DIFFERS in %d states" % int((~((pk == ref) | (np.isnan(pk) & np.isnan(ref)))).any(axis=1).sum())))
+            else:
+                fin_ = np.isfinite(ref).all(axis=1) & np.isfinite(pk).all(axis=1)
+                scale = np.maximum(np.abs(ref[fin_]), 1e-300)
+                res.append("kernel FAST max %.1e element-wise, non-finite pattern %s" % (float((np.abs(pk[fin_] - ref[fin_]) / scale).max()),
+                                                                                         "equal" if np.array_equal(np.isfinite(pk), np.isfinite(ref)) else "DIFFERS"))
+        clamped = float(((ref[:, 2] == g["p_min"]) | (ref[:, 2] == g["p_max"])).mean())
+        print("gas %-62s %s   (pressure on the clamp: %.1f %% of the states)" % (str(gas) if gas else "(the examples' air)", ";  ".join(res), 100.0 * clamped), flush=True)
+    print("# %d comparisons differ" % n_bad)
+    return 1 if n_bad else 0
+
+
 def cases():
     smooth, riemann = mg.SMOOTH_IC, mg.RIEMANN2D_IC
     sym, ext = mg.SYM4, mg.EXTRAP4
@@ -396,6 +444,8 @@ def main():
         raise SystemExit("oracle/_ref/bin/ref_harness is not built (oracle/build_ref.sh needs /root/reference)")
     oracle.build()
     sel = [x for x in sys.argv[1:] if not x.startswith("--")]
+    if "--prims" in sys.argv:
+        return compare_prims()
     if "--riemann" in sys.argv:
         rc = compare_riemann()
         print("# FAST above 1e-12: states with pressure jumps of 1e4 ... 1e6 next to a near-vacuum side, where the reference's own formula moves by 3e-12")

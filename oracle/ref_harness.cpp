@@ -14,6 +14,7 @@
 //                                                             `every`-th step
 //   ref_harness time <input.toml> <n_steps> [n_warmup=1]      wall-clock per step, JSON on last line
 //   ref_harness riemann <states.mlbd> <out.mlbd> <gamma>      the three flux functions on a list of face states
+//   ref_harness prims <states.mlbd> <out.mlbd> <gamma>        the primitives of a list of conserved states
 //   ref_harness mesh <mesh.mlbd> <input.toml> <out.mlbd> [n]  as `dump`, but the mesh arrays are
 //                                                             injected from a file (arbitrary
 //                                                             unstructured tri/quad meshes)
@@ -282,6 +283,19 @@ int main(int argc, char ** argv) {
             }
             Writer w(argv[3]);
             w.f64("flux", {3, n, 4}, out.data());
+        } else if (mode == "prims") {
+            // ref_harness prims <in.mlbd> <out.mlbd> <gamma>: Euler::compute_primitives_from_conservatives (physics/physics.h:826-860) on a list
+            // of conserved states U [n][4]; "gas" [6] = gamma, p_ref, T_ref, rho_ref, p_min, p_max
+            auto in = read_mlbd(argv[2]);
+            const Record & ru = in.at("U"), & rg = in.at("gas");
+            const uint64_t n = ru.dims[0];
+            const double * U = reinterpret_cast<const double *>(ru.data.data()), * g = reinterpret_cast<const double *>(rg.data.data());
+            Euler eu;
+            eu.init(g[4], g[5], g[0], g[1], g[2], g[3]);
+            std::vector<double> P(n * N_PRIMITIVE);
+            for (uint64_t i = 0; i < n; i++) eu.h_compute_primitives_from_conservatives(&P[i * N_PRIMITIVE], &U[4 * i]);
+            Writer w(argv[3]);
+            w.f64("P", {n, (uint64_t)N_PRIMITIVE}, P.data());
         } else if (mode == "time") {
             auto t0 = std::chrono::steady_clock::now();
             init_with_mesh(s, argv[2], nullptr);

@@ -68,6 +68,7 @@ def lib(variant="strict"):
         L.emu_calc_dt.argtypes = [C.c_void_p, C.c_double]
         L.emu_get_primitives.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_set_primitives.argtypes = [C.c_void_p, C.c_void_p]
+        L.emu_primitives.argtypes = [C.POINTER(_abi.Physics), C.c_ulonglong, C.c_void_p, C.c_void_p]
         L.emu_riemann_flux.argtypes = [C.c_int, C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         _LIB[variant] = L
     return _LIB[variant]
@@ -82,6 +83,15 @@ def riemann_flux(kind, n_unit, L, R, gamma=1.4, fp_mode="strict"):
     p = lambda a: a.ctypes.data_as(C.c_void_p)      # noqa: E731
     lib(fp_mode).emu_riemann_flux(mb.RIEMANN[kind], L.shape[0], p(n_unit), p(L), p(R), float(gamma), p(out))
     return out
+
+
+def primitives(U, gas=None, fp_mode="strict"):
+    """mallard_b200.compute_primitives through the emulated kernel source: U [n][4] -> (u, v, p, T, h) [n][5]"""
+    U = np.ascontiguousarray(U, dtype=np.float64).reshape(-1, 4)
+    P = np.empty((U.shape[0], 5))
+    phys = mb._physics(gas)
+    lib(fp_mode).emu_primitives(C.byref(phys), U.shape[0], U.ctypes.data_as(C.c_void_p), P.ctypes.data_as(C.c_void_p))
+    return P
 
 
 class EmulatedSolver:

@@ -279,6 +279,12 @@ int emu_set_primitives(void * h, const double * P_ref) {
     return 0;
 }
 
+// mlb_compute_primitives (prims_aos_kernel's body): cons_to_prim of the kernel source on a list of conserved states
+int emu_primitives(const mlb_physics * phys, unsigned long long n, const double * U, double * P) {
+    const GasParams g = make_gas(*phys);
+    for (unsigned long long i = 0; i < n; i++) emu::cons_to_prim(g, &U[4 * i], &P[5 * i]);
+    return 0;
+}
 int emu_riemann_flux(int riemann, unsigned long long n, const double * nunit, const double * L, const double * R, double gamma, double * flux) {
     switch (riemann) {
         case MLB_RIEMANN_RUSANOV: riemann_list<MLB_RIEMANN_RUSANOV>(n, nunit, L, R, gamma, flux); break;

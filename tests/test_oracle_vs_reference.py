@@ -165,3 +165,16 @@ def test_riemann_fluxes_on_random_states_against_the_unmodified_reference(oracle
     assert len(fast) == 6
     for mx, above, total, mismatch in fast:
         assert float(mx) <= 1e-10 and int(above) <= 1e-3 * int(total) and int(mismatch) == 0
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "bin", "ref_harness")),
+                    reason="the unmodified reference is not built here (oracle/build_ref.sh needs /root/reference)")
+def test_primitives_of_random_states_against_the_unmodified_reference(oracle_mod, capsys):
+    """oracle/pin_sweep.py --prims, live on 20 000 states per gas: Euler::compute_primitives_from_conservatives called directly (`ref_harness prims`),
+    incl. negative internal energies, an active pressure clamp and NaN energies - oracle and STRICT kernel source: every bit."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import pin_sweep
+    assert pin_sweep.compare_prims(n=20000, seed=3) == 0
+    out = capsys.readouterr().out
+    assert out.count("oracle every bit;  kernel STRICT every bit") == 4 and out.count("non-finite pattern equal") == 4
