@@ -389,6 +389,34 @@ def compare_prims(n=200000, seed=11):
     return 1 if n_bad else 0
 
 
+def compare_random(n_cases=24, seed=99):
+    """--random: randomly drawn TENO configurations on cartesian_tri meshes of random size and aspect ratio (regular meshes are where the
+    squared distances of the stencil search tie exactly and std::sort's order decides membership, SURVEY Q4): order 1 - 4, both bases,
+    stencil factors 1.5 / 2 / 2.5, all Riemann solvers, both multi-stage integrators; every array as in the default mode."""
+    rng = np.random.default_rng(seed)
+    n_bad = 0
+    print("# %d random TENO configurations on cartesian_tri meshes against the unmodified reference, every array bit for bit (seed %d)" % (n_cases, seed))
+    for t in range(n_cases):
+        order = int(rng.integers(1, 5)); basis = ["legendre", "monomial"][int(rng.integers(0, 2))]
+        nx = int(rng.integers(6, 26)); ny = int(rng.integers(6, 22))
+        Lx = float(rng.choice([1.0, 2.0, 0.5, 1.7, 3.0])); Ly = float(rng.choice([1.0, 0.5, 1.3, 2.0]))
+        factor = float(rng.choice([2.0, 2.0, 1.5, 2.5]))
+        case = dict(mesh=dict(type="cartesian_tri", Nx=nx, Ny=ny, Lx=Lx, Ly=Ly), ic=mg.SMOOTH_IC, bcs=[mg.SYM4, mg.EXTRAP4][t % 2], cfl=0.1,
+                    riemann=["HLLC", "HLL", "Rusanov"][t % 3], integrator=["SSPRK3", "RK4"][t % 2],
+                    recon=dict(type="TENO", basis_type=basis, basis_order=order, max_stencil_size_factor=factor), n_steps=1, every=1)
+        name = "p%d %-8s %2dx%-2d [%g x %g] factor %.1f %s %s" % (order, basis, nx, ny, Lx, Ly, factor, case["riemann"], case["integrator"])
+        try:
+            res = compare(case)
+        except subprocess.CalledProcessError as ex:
+            print("%-62s reference refused the configuration (exit code %d)" % (name, ex.returncode), flush=True)
+            continue
+        bad = [(w, v) for w, v in res if v != "ok" and not v.startswith("calc_dt threw")]
+        print("%-62s %2d arrays compared, %s" % (name, len(res), "all bit-exact" if not bad else "DIFFER: " + "; ".join("%s: %s" % b for b in bad)), flush=True)
+        n_bad += len(bad)
+    print("# %d differing arrays" % n_bad)
+    return 1 if n_bad else 0
+
+
 def cases():
     smooth, riemann = mg.SMOOTH_IC, mg.RIEMANN2D_IC
     sym, ext = mg.SYM4, mg.EXTRAP4
@@ -444,6 +472,9 @@ def main():
         raise SystemExit("oracle/_ref/bin/ref_harness is not built (oracle/build_ref.sh needs /root/reference)")
     oracle.build()
     sel = [x for x in sys.argv[1:] if not x.startswith("--")]
+    if "--random" in sys.argv:
+        extra = [x for x in sys.argv[sys.argv.index("--random") + 1:] if x.isdigit()]
+        return compare_random(int(extra[0]) if extra else 24, int(extra[1]) if len(extra) > 1 else 99)
     if "--prims" in sys.argv:
         return compare_prims()
     if "--riemann" in sys.argv:
