@@ -417,6 +417,62 @@ def compare_random(n_cases=24, seed=99):
     return 1 if n_bad else 0
 
 
+def compare_long_runs(n_steps=100):
+    """--long: first-order runs of n_steps steps (calc_dt + take_step each) on injected unstructured meshes - jittered triangles, mixed
+    triangles / quadrilaterals - in the unmodified reference, the oracle and the emulated kernel sequence of mlb_run: the state after the
+    last step.  Oracle and STRICT kernels: every bit (no drift at all); FAST: relative to the field scale."""
+    from mallard_b200 import synthetic as syn
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
+    from emulation import EmulatedAsSolver, fast_available
+    keys = ["node_coords", "offsets_nodes_of_cell", "nodes_of_cell", "offsets_faces_of_cell", "faces_of_cell", "offsets_nodes_of_face", "nodes_of_face",
+            "cells_of_face"]
+    wall = [dict(name="left", type="upt", u=[0.5, 0.3], p=1.0, T=0.0036), dict(name="right", type="p_out", p=0.95),
+            dict(name="top", type="symmetry"), dict(name="bottom", type="wall_adiabatic")]
+    n_bad = 0
+    print("# %d first-order steps on injected unstructured meshes: state after the last step against the unmodified reference" % n_steps)
+    for label, mesh, rs, integ, bcs in (("jittered 14x12, shuffled ids", syn.jittered_tri(14, 12, 1.0, 0.9, seed=21), "HLLC", "SSPRK3", mg.EXTRAP4),
+                                        ("mixed tri/quad 12x10, shuffled ids", syn.mixed_tri_quad(12, 10, 1.0, 0.9, seed=4, tri_fraction=0.5), "Rusanov", "RK4", mg.SYM4),
+                                        ("mixed tri/quad 11x9, upt / p_out / symmetry / wall", syn.mixed_tri_quad(11, 9, 1.0, 0.9, seed=9, tri_fraction=0.4), "HLL", "SSPRK3", wall)):
+        a = mesh.arrays
+        case = dict(mesh=dict(type="cartesian_tri", Nx=4, Ny=4, Lx=1.0, Ly=0.9), ic=mg.SMOOTH_IC, bcs=bcs, cfl=0.6, riemann=rs, integrator=integ, recon=dict(type="FO"),
+                    n_steps=n_steps, every=n_steps)
+        with tempfile.TemporaryDirectory() as td:
+            toml, inj, out = os.path.join(td, "input.toml"), os.path.join(td, "mesh.mlbd"), os.path.join(td, "out.mlbd")
+            mg.write_toml(case, toml)
+            rec = {k: (a[k].reshape(-1, 2) if k in ("node_coords", "cells_of_face") else a[k]) for k in keys}
+            for i, (zn, zf) in enumerate(mesh.zones):
+                rec["zone:%d:%s" % (i, zn)] = np.ascontiguousarray(zf, dtype=np.uint32)
+            mlbd.write(inj, rec)
+            subprocess.check_call([mg.HARNESS, "mesh", inj, toml, out, str(n_steps), str(n_steps)], env=dict(os.environ, OMP_NUM_THREADS="1", OMP_PROC_BIND="false"),
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            d = mlbd.read(out)
+        last = "step%d:" % (n_steps - 1)
+        kw = dict(recon="FO", riemann=rs, integrator=integ, bcs=bcs)
+        om = oracle.Mesh.from_arrays({k: a[k] for k in keys}, mesh.zones)
+        so = oracle.Solver(om, **kw)
+        so.set_state(d["U0"], d["P0"])
+        for _ in range(n_steps):
+            so.take_step(so.calc_dt(0.6))
+        same_o = np.array_equal(so.get("U"), d[last + "U"]) and np.array_equal(so.get("P"), d[last + "P"])
+        n_bad += 0 if same_o else 1
+        res = ["oracle " + ("every bit" if same_o else "DIFFERS")]
+        for fp in ("strict", "fast") if fast_available() else ("strict",):
+            ss = EmulatedAsSolver(mesh, fp_mode=fp, **kw)
+            ss.set_state(d["U0"], d["P0"])
+            ss.run(n_steps, cfl=0.6)
+            U, P = ss.get_state(prim=True)
+            if fp == "strict":
+                same = np.array_equal(U, d[last + "U"]) and np.array_equal(P, d[last + "P"])
+                n_bad += 0 if same else 1
+                res.append("kernels STRICT " + ("every bit" if same else "DIFFER (U %.1e)" % gu.rel_err(U, d[last + "U"])))
+            else:
+                res.append("kernels FAST %.1e of the field scale" % max(gu.field_err(U, d[last + "U"]), gu.field_err(P, d[last + "P"])))
+            ss.close()
+        print("%-52s %5d cells  %s %s  %s" % (label, mesh.n_cells, rs, integ, ";  ".join(res)), flush=True)
+    print("# %d comparisons differ" % n_bad)
+    return 1 if n_bad else 0
+
+
 def cases():
     smooth, riemann = mg.SMOOTH_IC, mg.RIEMANN2D_IC
     sym, ext = mg.SYM4, mg.EXTRAP4
@@ -472,6 +528,8 @@ def main():
         raise SystemExit("oracle/_ref/bin/ref_harness is not built (oracle/build_ref.sh needs /root/reference)")
     oracle.build()
     sel = [x for x in sys.argv[1:] if not x.startswith("--")]
+    if "--long" in sys.argv:
+        return compare_long_runs()
     if "--random" in sys.argv:
         extra = [x for x in sys.argv[sys.argv.index("--random") + 1:] if x.isdigit()]
         return compare_random(int(extra[0]) if extra else 24, int(extra[1]) if len(extra) > 1 else 99)
