@@ -465,6 +465,20 @@ def compare_long_runs(n_steps=100):
                 same = np.array_equal(U, d[last + "U"]) and np.array_equal(P, d[last + "P"])
                 n_bad += 0 if same else 1
                 res.append("kernels STRICT " + ("every bit" if same else "DIFFER (U %.1e)" % gu.rel_err(U, d[last + "U"])))
+                # the cooperative small-mesh kernel's phases (csrc/small_step.cuh: all steps in one launch, grid barriers between the phases)
+                os.environ["MLB_SMALL_STEP"] = "1"
+                try:
+                    sc = EmulatedAsSolver(mesh, fp_mode=fp, **kw)
+                    sc.set_state(d["U0"], d["P0"])
+                    sc.run(n_steps, cfl=0.6)
+                    Uc, Pc = sc.get_state(prim=True)
+                    took = int(sc.get("stats")[12])
+                    sc.close()
+                finally:
+                    os.environ.pop("MLB_SMALL_STEP", None)
+                same_c = np.array_equal(Uc, d[last + "U"]) and np.array_equal(Pc, d[last + "P"]) and took == n_steps
+                n_bad += 0 if same_c else 1
+                res.append("cooperative kernel's phases " + ("every bit" if same_c else "DIFFER"))
             else:
                 res.append("kernels FAST %.1e of the field scale" % max(gu.field_err(U, d[last + "U"]), gu.field_err(P, d[last + "P"])))
             ss.close()
