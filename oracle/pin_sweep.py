@@ -117,7 +117,7 @@ def compare_kernels(case):
         # one whole step through the emulated kernels (spectral radius / dt from the CFL kernel's body, every stage's face and gather
         # kernels, the RK combination, the primitives of the last stage): dt, U and the primitives against the reference's
         eU = None
-        if meta["integrator"] != "FE":                  # (the emulation's stepping entry point covers SSPRK3 / RK4)
+        if True:
             from emulation import EmulatedAsSolver
             ss = EmulatedAsSolver(pm, fp_mode=fp, **gu.solver_kwargs(meta))
             ss.set_state(d["U0"], d["P0"])      # (as mlb_set_state(U, P): the reference steps from the primitives its initial condition defines)
@@ -560,7 +560,7 @@ def main():
         return compare_meshes()
     if "--kernels" in sys.argv:
         print("# CUDA kernel source on the host (tests/emul) against the unmodified reference: max error of the face values / of the stage-1 residual /")
-        print("# after one whole step (dt, U, primitives; nan = dt not positive in the reference either; - = FE, which the emulation does not step);")
+        print("# after one whole step (dt, U, primitives; nan = dt not positive in the reference either);")
         print("# STRICT build element-wise relative, FAST build (FMA contraction) relative to the field scale")
         worst = {"strict": 0.0, "fast": 0.0}
         for name, case in cases():

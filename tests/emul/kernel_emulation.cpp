@@ -168,8 +168,8 @@ double emulated_calc_dt(Emu & e, double cfl) {
 
 // the multi-kernel sequence of mlb_run: CFL "kernel" (cell loop + max + dt), then per stage face kernel and gather kernel
 void steps_kernel_by_kernel(Emu & e, uint32_t n_steps, double cfl) {
-    const auto plan = make_stage_plan(e.cur, e.num.integrator);
     for (uint32_t n = 0; n < n_steps; n++) {
+        const auto plan = make_stage_plan(e.cur, e.num.integrator);      // (do_step, api.cu: the plan of every step starts from the current buffer)
         if (cfl > 0.0) emulated_calc_dt(e, cfl);
         for (const StagePlan & sp : plan) {
             const StageArgs a = step_stage_args(e, sp);
@@ -177,6 +177,7 @@ void steps_kernel_by_kernel(Emu & e, uint32_t n_steps, double cfl) {
             step_faces(e, a);
             run_kernel(emu::gather_stage_kernel, a, (a.g.N_owned + 255u) / 256u, 256);
         }
+        if (e.num.integrator == MLB_INTEGRATOR_FE) e.cur = plan.back().out;   // finish_plan (api.cu): forward Euler's result lives in the other buffer
     }
 }
 
@@ -226,7 +227,7 @@ int emu_run(void * h, unsigned n_steps, double cfl, double dt_fixed, unsigned sm
     try {
         if ((e.teno || e.gas.mu > 0.0) && small_blocks) throw std::runtime_error("emu_run: the cooperative kernel takes first-order inviscid contexts only");
         if (e.P.N != e.P.N_owned) throw std::runtime_error("emu_run: single contexts only (no halo exchange in the emulation)");
-        if (e.num.integrator == MLB_INTEGRATOR_FE) throw std::runtime_error("emu_run: SSPRK3 / RK4 only (FE alternates its buffers from step to step)");
+        if (e.num.integrator == MLB_INTEGRATOR_FE && small_blocks) throw std::runtime_error("emu_run: the cooperative kernel takes SSPRK3 / RK4 only (as small_step_eligible, api.cu)");
         if (!(cfl > 0.0)) e.scal[SC_DT] = dt_fixed;
         if (small_blocks) steps_small(e, n_steps, cfl, small_blocks); else steps_kernel_by_kernel(e, n_steps, cfl);
         if (t_out) *t_out = e.scal[SC_T];
@@ -251,7 +252,10 @@ int emu_get_array(void * h, const char * name, double * out) {
     const auto plan = make_stage_plan(e.cur, e.num.integrator);
     const double * src = nullptr;
     if (n.size() == 4 && n.rfind("rhs", 0) == 0 && n[3] >= '0' && n[3] < '4') src = e.kb[n[3] - '0'].data();
-    else if (n == "U_temp") src = e.Ub[plan[plan.size() - 2].out].data();
+    else if (n == "U_temp") {
+        if (plan.size() < 2) { emu_err = "emu_get_array: forward Euler has no intermediate stage state"; return 1; }
+        src = e.Ub[plan[plan.size() - 2].out].data();
+    }
     else if (n == "cfl_local") {
         for (uint32_t i = 0; i < e.P.N_owned; i++) { const double r = e.sr[i]; out[e.P.perm_cells[i]] = r == 0.0 ? 0.0 : e.scal[SC_DT] * r; }
         return 0;
